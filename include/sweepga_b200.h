@@ -1,0 +1,236 @@
+/*
+ * sweepga_b200.h — C ABI of the B200-native sweepga mapping filter.
+ *
+ * Drop-in boundary for ONE path of pangenome/sweepga: the body of
+ *   PafFilter::apply_filters            (reference src/paf_filter.rs:379-747)
+ * and the thin callers either side of it
+ *   PafFilter::filter_paf               (src/paf_filter.rs:278-289)
+ *   unified_filter::filter_file         (src/unified_filter.rs:280-347, PAF side)
+ *   library_api::apply_paf_filter       (src/library_api.rs:267-281)
+ *   plane_sweep_exact::plane_sweep_*    (src/plane_sweep_exact.rs:268-461)
+ *   plane_sweep_core::plane_sweep       (src/plane_sweep_core.rs:80-149)
+ *   CLI / library flag parsers          (src/main.rs:244-293, src/library_api.rs:31-63,
+ *                                        src/cli.rs:26-130, src/pansn.rs:176-225)
+ *
+ * Plain pointers and sizes only; no torch / CUDA types in any signature.
+ * All compute entry points run hand-written sm_100a kernels; there is NO CPU
+ * fallback: every compute call fails with SWG_ERR_CUDA when no device is usable.
+ *
+ * The reference-side binding (Rust `extern "C"` block + build.rs) a maintainer
+ * would add is shown in INTEGRATION.md.
+ */
+#ifndef SWEEPGA_B200_H
+#define SWEEPGA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- enums (values are part of the ABI) -------------------------------- */
+
+/* FilterMode, reference src/filter_types.rs:17-22 */
+enum { SWG_ONE_TO_ONE = 0, SWG_ONE_TO_MANY = 1, SWG_MANY_TO_MANY = 2 };
+
+/* ScoringFunction, reference src/filter_types.rs:8-14 */
+enum {
+    SWG_SCORE_IDENTITY = 0,
+    SWG_SCORE_LENGTH = 1,
+    SWG_SCORE_LENGTH_IDENTITY = 2,
+    SWG_SCORE_LOG_LENGTH_IDENTITY = 3,
+    SWG_SCORE_MATCHES = 4
+};
+
+/* ChainStatus (reference src/mapping.rs:82-86) + "not in the result map" */
+enum { SWG_DROPPED = 0, SWG_SCAFFOLD = 1, SWG_RESCUED = 2, SWG_UNASSIGNED = 3 };
+
+/* return codes */
+enum {
+    SWG_OK = 0,
+    SWG_ERR_ARG = -1,     /* NULL pointer / bad enum / bad size                          */
+    SWG_ERR_RANGE = -2,   /* coordinate does not fit the u32 SoA, end < start, id >= n_seq */
+    SWG_ERR_CUDA = -3,    /* no usable device / CUDA runtime error (no CPU fallback)     */
+    SWG_ERR_OOM = -4,     /* device or pinned-host allocation failed                     */
+    SWG_ERR_IO = -5,      /* PAF front end: cannot open / read / write                   */
+    SWG_ERR_PARSE = -6,   /* flag parsers: the reference would return Err / exit         */
+    SWG_ERR_UNSUPPORTED = -7 /* .1aln container (reference delegates it to fastga-rs)     */
+};
+
+#define SWG_NO_LIMIT (~(uint64_t)0)         /* Option<usize>::None (Some(0) stays representable) */
+#define SWG_KEEP_ALL (~(uint64_t)0)         /* usize::MAX for the primitive sweeps        */
+
+/* ---- FilterConfig (live fields only), reference src/paf_filter.rs:18-49 - */
+typedef struct swg_config {
+    uint64_t min_block_length;        /* --min-aln-length                                 */
+    uint64_t mapping_max_per_query;   /* SWG_NO_LIMIT = None                              */
+    uint64_t mapping_max_per_target;  /* SWG_NO_LIMIT = None                              */
+    uint64_t scaffold_max_per_query;  /* SWG_NO_LIMIT = None                              */
+    uint64_t scaffold_max_per_target; /* SWG_NO_LIMIT = None                              */
+    uint64_t scaffold_gap;            /* --scaffold-jump; 0 disables scaffolding          */
+    uint64_t min_scaffold_length;     /* --scaffold-mass (compared with the query SPAN)   */
+    uint64_t scaffold_max_deviation;  /* --scaffold-dist; 0 = no rescue                   */
+    double overlap_threshold;         /* --overlap                                        */
+    double scaffold_overlap_threshold;/* --scaffold-overlap                               */
+    double min_identity;              /* --min-aln-identity                               */
+    double min_scaffold_identity;     /* --min-scaffold-identity                          */
+    uint8_t mapping_filter_mode;      /* SWG_ONE_TO_ONE ...                               */
+    uint8_t scaffold_filter_mode;
+    uint8_t scoring_function;         /* SWG_SCORE_*                                      */
+    uint8_t keep_self;                /* PafFilter::with_keep_self                        */
+    uint8_t scaffolds_only;           /* PafFilter::with_scaffolds_only                   */
+    uint8_t reserved[3];
+} swg_config;
+
+/* Defaults of the CLI (reference src/cli.rs:204-276): many:many, overlap 0.95,
+ * log-length-ani, jump 50k, mass 10k, scaffold many:many, scaffold-overlap 0.5, dist 0. */
+void swg_config_default(swg_config *cfg);
+
+/* ---- compact mapping table (SoA), replaces Vec<RecordMeta> -------------- *
+ * Element i is the i-th RecordMeta of the Vec handed to apply_filters (the
+ * reference orders everything by Vec position; `rank` is only a map key, so the
+ * caller keeps the index -> rank table).  Sequence names are interned by the
+ * caller into ONE table shared by queries and targets (query_id == target_id
+ * <=> same name, the --self test of src/paf_filter.rs:386).  Per sequence the
+ * caller supplies the id of its genome prefix under the two prefix rules of the
+ * reference:
+ *   seq_genome_id   P  = name up to and including the LAST '#', else the name
+ *                        (src/paf_filter.rs:1022-1030)
+ *   seq_genome2_id  P2 = "f0#f1#" if the name has >= 2 '#'-separated fields,
+ *                        else the name (src/plane_sweep_scaffold.rs:13-22)
+ * Ids need not be first-appearance ordered; equality is all that is used.
+ * Coordinates are u32 (checked by the marshaller; larger -> SWG_ERR_RANGE).    */
+typedef struct swg_mappings {
+    uint64_t n;
+    const uint32_t *query_id;
+    const uint32_t *target_id;
+    const uint32_t *query_start;
+    const uint32_t *query_end;
+    const uint32_t *target_start;
+    const uint32_t *target_end;
+    const uint32_t *block_length;
+    const uint32_t *matches;
+    const double *identity;
+    const uint8_t *strand;        /* '+' is forward; any other byte is reverse (paf_filter.rs:311) */
+    const double *score;          /* optional (may be NULL): caller-computed plane-sweep score,
+                                     used instead of the device-computed one (glibc-log exactness) */
+    uint32_t n_seq;
+    const uint32_t *seq_genome_id;
+    const uint32_t *seq_genome2_id;
+} swg_mappings;
+
+/* Result, replaces HashMap<rank, RecordMeta{chain_id, chain_status}>.
+ * status[i] = SWG_DROPPED when the record is absent from the reference's map.
+ * chain_id[i] = k for "chain_k" (1-based), 0 for None.                           */
+typedef struct swg_result {
+    uint8_t *status;
+    uint32_t *chain_id;
+} swg_result;
+
+typedef struct swg_stats {
+    uint64_t n_input;
+    uint64_t n_stage1;            /* after length/self/identity retain (paf_filter.rs:384-388) */
+    uint64_t n_after_sweep;       /* after apply_plane_sweep_to_mappings                       */
+    uint64_t n_chains;            /* merge_mappings_into_chains                                */
+    uint64_t n_chains_after_mass; /* length/identity chain filter (paf_filter.rs:449-455)      */
+    uint64_t n_chains_kept;       /* after the scaffold plane sweep                            */
+    uint64_t n_anchors;           /* members of kept chains + captured inversions              */
+    uint64_t n_rescued;
+    uint64_t n_kept;              /* records with status != SWG_DROPPED                        */
+    uint64_t score_near_ties;     /* score pairs within 2 ulp compared by a sweep (see DESIGN) */
+    uint64_t gpu_launches;        /* kernels launched by this call                             */
+    double ms_h2d, ms_device, ms_d2h; /* CUDA-event times of the three phases of swg_filter    */
+} swg_stats;
+
+typedef struct swg_ctx swg_ctx;
+
+/* One context per GPU (one process per GPU in the multi-GPU driver).  Owns a
+ * stream, pinned staging and grow-only HBM scratch.  Not thread-safe.
+ * Returns NULL when the device cannot be initialised; the reason is then
+ * available from swg_last_error(NULL).                                         */
+swg_ctx *swg_create(int device);
+void swg_destroy(swg_ctx *ctx);
+const char *swg_last_error(const swg_ctx *ctx);
+
+/* apply_filters with HOST buffers: H2D + filter + D2H (src/paf_filter.rs:379-747). */
+int swg_filter(swg_ctx *ctx, const swg_config *cfg, const swg_mappings *host_in,
+               swg_result *host_out, swg_stats *stats);
+
+/* Same with DEVICE-resident SoA in and device-resident result out (no copies);
+ * runs on the context's stream and returns after it has drained.               */
+int swg_filter_device(swg_ctx *ctx, const swg_config *cfg, const swg_mappings *dev_in,
+                      swg_result *dev_out, swg_stats *stats);
+
+/* Raw stream handle (cudaStream_t) the context launches on — for event timing. */
+void *swg_stream(swg_ctx *ctx);
+
+/* Upload a host table once / free it; lets a caller time swg_filter_device on
+ * resident data without touching CUDA itself.                                   */
+int swg_upload(swg_ctx *ctx, const swg_mappings *host_in, swg_mappings *dev_out, swg_result *dev_res);
+void swg_release(swg_ctx *ctx, swg_mappings *dev, swg_result *dev_res);
+int swg_download_result(swg_ctx *ctx, uint64_t n, const swg_result *dev_res, swg_result *host_out);
+
+/* ---- primitives: plane_sweep_exact.rs:268-461 --------------------------- *
+ * keep[i] = 1 iff local index i is in the Vec<usize> the reference returns.
+ * n_keep = SWG_KEEP_ALL for usize::MAX.  HOST buffers.                          */
+int swg_plane_sweep_query(swg_ctx *ctx, uint64_t n, const uint32_t *qs, const uint32_t *qe,
+                          const uint32_t *ts, const uint32_t *te, const double *identity,
+                          uint64_t n_keep, double overlap_threshold, int scoring, uint8_t *keep);
+int swg_plane_sweep_target(swg_ctx *ctx, uint64_t n, const uint32_t *qs, const uint32_t *qe,
+                           const uint32_t *ts, const uint32_t *te, const double *identity,
+                           uint64_t n_keep, double overlap_threshold, int scoring, uint8_t *keep);
+int swg_plane_sweep_both(swg_ctx *ctx, uint64_t n, const uint32_t *qs, const uint32_t *qe,
+                         const uint32_t *ts, const uint32_t *te, const double *identity,
+                         uint64_t n_keep_query, uint64_t n_keep_target, double overlap_threshold,
+                         int scoring, uint8_t *keep);
+
+/* ---- host-side mirrors of the flag parsers ------------------------------ */
+/* src/main.rs:244-293 (CLI grammar).  *mode, *per_query, *per_target (SWG_NO_LIMIT = None). */
+int swg_parse_filter_mode_cli(const char *s, uint8_t *mode, uint64_t *per_query, uint64_t *per_target);
+/* src/library_api.rs:31-63 (library grammar; differs on "many:1"-style inputs).  */
+int swg_parse_filter_mode_lib(const char *s, uint8_t *mode, uint64_t *per_query, uint64_t *per_target);
+/* src/main.rs:3485-3492 */
+int swg_parse_scoring(const char *s, uint8_t *scoring);
+/* src/cli.rs:26-61 */
+int swg_parse_metric_number(const char *s, uint64_t *out);
+/* src/cli.rs:76-130; has_ani = 0 => ani_percentile None */
+int swg_parse_identity_value(const char *s, int has_ani, double ani_percentile, double *out);
+/* src/pansn.rs:176-191, 207-225; has_avg = 0 => avg_seq_len None */
+uint64_t swg_round_nice(uint64_t v);
+void swg_clamp_scaffold_params(uint64_t user_jump, uint64_t user_mass, int has_avg, uint64_t avg_seq_len,
+                               int adaptive, uint64_t *jump_out, uint64_t *mass_out);
+
+/* ---- PAF front end (host parse -> SoA -> GPU filter -> tagged write) ----- */
+typedef struct swg_paf swg_paf;
+/* extract_metadata, src/paf_filter.rs:292-376 (+ parse_cigar_counts src/paf.rs:32-64). */
+swg_paf *swg_paf_parse(const char *path, char *err, size_t err_len);
+void swg_paf_free(swg_paf *p);
+uint64_t swg_paf_n_records(const swg_paf *p);
+uint64_t swg_paf_n_lines(const swg_paf *p);
+uint32_t swg_paf_n_seq(const swg_paf *p);
+const uint64_t *swg_paf_rank(const swg_paf *p);            /* line number of record i          */
+const char *swg_paf_seq_name(const swg_paf *p, uint32_t id);
+int swg_paf_view(const swg_paf *p, swg_mappings *out);     /* borrow the SoA (valid until free) */
+/* write_filtered_output, src/paf_filter.rs:1689-1726 */
+int swg_paf_write(const swg_paf *p, const char *out_path, const uint8_t *status, const uint32_t *chain_id);
+
+/* PafFilter::filter_paf (src/paf_filter.rs:278-289). */
+int swg_filter_paf(swg_ctx *ctx, const swg_config *cfg, const char *in_path, const char *out_path,
+                   swg_stats *stats);
+/* unified_filter::filter_file (src/unified_filter.rs:280-347): sniffs "1 " => .1aln
+ * => SWG_ERR_UNSUPPORTED (the container codec lives in fastga-rs, not in sweepga). */
+int swg_filter_file(swg_ctx *ctx, const swg_config *cfg, const char *in_path, const char *out_path,
+                    int keep_self, swg_stats *stats);
+
+/* ---- multi-GPU sharding helper ------------------------------------------ *
+ * Size-balanced (LPT) assignment of genome-pair units (P(q),P(t)) to n_shards.
+ * shard_of[i] receives the shard of record i.  Host only, no device needed.     */
+int swg_shard_plan(const swg_mappings *host_in, int n_shards, uint32_t *shard_of, uint64_t *shard_sizes);
+
+const char *swg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWEEPGA_B200_H */

@@ -1,0 +1,446 @@
+"""Host-side mirror of the reference's filter interface, over the C ABI.
+
+Names, argument meaning and error behaviour follow the reference:
+  FilterConfig                       src/paf_filter.rs:18-49 (live fields)
+  PafFilter.new/with_keep_self/with_scaffolds_only/filter_paf/apply_filters
+                                     src/paf_filter.rs:239-289, 379-382
+  filter_file                        src/unified_filter.rs:280-347
+  apply_paf_filter, filter_config_from_align_cfg, parse_filter_mode (library grammar)
+                                     src/library_api.rs:31-63, 223-281
+  parse_filter_mode_cli, parse_metric_number, parse_identity_value, clamp_scaffold_params, round_nice
+                                     src/main.rs:244-293, src/cli.rs:26-130, src/pansn.rs:176-225
+  plane_sweep_query/target/both      src/plane_sweep_exact.rs:268-461
+Python is only the binding: every compute call goes through libsweepga_b200.so (CUDA, sm_100a).
+"""
+import ctypes as C
+import os
+import tempfile
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib
+
+FilterMode = {"OneToOne": _lib.ONE_TO_ONE, "OneToMany": _lib.ONE_TO_MANY, "ManyToMany": _lib.MANY_TO_MANY}
+ScoringFunction = {"Identity": 0, "Length": 1, "LengthIdentity": 2, "LogLengthIdentity": 3, "Matches": 4}
+ChainStatus = {0: None, 1: "scaffold", 2: "rescued", 3: "unassigned"}
+
+
+class SwgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"sweepga_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+# ------------------------------------------------------------------------------------------------
+# flag parsers (host logic in C++, src/host_parsers.cpp)
+# ------------------------------------------------------------------------------------------------
+def _opt(v):
+    return None if v == _lib.NO_LIMIT else int(v)
+
+
+def parse_filter_mode_cli(s: str):
+    """src/main.rs:244-293 -> (mode, max_per_query|None, max_per_target|None); raises on "0" (process::exit)."""
+    m, q, t = C.c_uint8(), C.c_uint64(), C.c_uint64()
+    rc = lib.swg_parse_filter_mode_cli(s.encode(), C.byref(m), C.byref(q), C.byref(t))
+    if rc != 0:
+        raise SwgError(rc, f"invalid filter value {s!r}")
+    return m.value, _opt(q.value), _opt(t.value)
+
+
+def parse_filter_mode(s: str):
+    """src/library_api.rs:31-63 (the library grammar; differs from the CLI on 'many:1')."""
+    m, q, t = C.c_uint8(), C.c_uint64(), C.c_uint64()
+    lib.swg_parse_filter_mode_lib(s.encode(), C.byref(m), C.byref(q), C.byref(t))
+    return m.value, _opt(q.value), _opt(t.value)
+
+
+def parse_scoring(s: str) -> int:
+    v = C.c_uint8()
+    lib.swg_parse_scoring(s.encode(), C.byref(v))
+    return v.value
+
+
+def parse_metric_number(s: str) -> int:
+    v = C.c_uint64()
+    rc = lib.swg_parse_metric_number(s.encode(), C.byref(v))
+    if rc != 0:
+        raise ValueError(f"invalid metric number {s!r}")
+    return v.value
+
+
+def parse_identity_value(s: str, ani_percentile: Optional[float] = None) -> float:
+    v = C.c_double()
+    rc = lib.swg_parse_identity_value(s.encode(), 0 if ani_percentile is None else 1, ani_percentile or 0.0, C.byref(v))
+    if rc != 0:
+        raise ValueError(f"invalid identity value {s!r}")
+    return v.value
+
+
+def round_nice(v: int) -> int:
+    return lib.swg_round_nice(v)
+
+
+def clamp_scaffold_params(user_jump, user_mass, avg_seq_len, adaptive):
+    j, m = C.c_uint64(), C.c_uint64()
+    lib.swg_clamp_scaffold_params(user_jump, user_mass, 0 if avg_seq_len is None else 1, avg_seq_len or 0, 1 if adaptive else 0,
+                                  C.byref(j), C.byref(m))
+    return j.value, m.value
+
+
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class FilterConfig:
+    """Live fields of the reference FilterConfig (src/paf_filter.rs:18-49); defaults = CLI defaults."""
+    min_block_length: int = 0
+    mapping_filter_mode: int = _lib.MANY_TO_MANY
+    mapping_max_per_query: Optional[int] = None
+    mapping_max_per_target: Optional[int] = None
+    scaffold_filter_mode: int = _lib.MANY_TO_MANY
+    scaffold_max_per_query: Optional[int] = None
+    scaffold_max_per_target: Optional[int] = None
+    overlap_threshold: float = 0.95
+    scaffold_gap: int = 50_000
+    min_scaffold_length: int = 10_000
+    scaffold_overlap_threshold: float = 0.5
+    scaffold_max_deviation: int = 0
+    scoring_function: int = _lib.SCORE_LOG_LENGTH_IDENTITY
+    min_identity: float = 0.0
+    min_scaffold_identity: float = 0.0
+    keep_self: bool = False        # PafFilter::with_keep_self
+    scaffolds_only: bool = False   # PafFilter::with_scaffolds_only
+
+    @classmethod
+    def from_cli(cls, num_mappings="many:many", scaffold_filter="many:many", scoring="log-length-ani", overlap=0.95,
+                 scaffold_overlap=0.5, scaffold_jump="50k", scaffold_mass="10k", scaffold_dist="0", min_aln_length=None,
+                 min_aln_identity="0", min_scaffold_identity="0", keep_self=False, scaffolds_only=False,
+                 avg_seq_len=None, no_adaptive_scaffolds=False, ani_percentile=None):
+        """The CLI's FilterConfig construction (src/main.rs:3476-3619), flag strings in, config out."""
+        mm, mq, mt = parse_filter_mode_cli(str(num_mappings))
+        sm, sq, st = parse_filter_mode_cli(str(scaffold_filter))
+        jump = parse_metric_number(str(scaffold_jump))
+        mass = parse_metric_number(str(scaffold_mass))
+        jump, mass = clamp_scaffold_params(jump, mass, avg_seq_len, not no_adaptive_scaffolds)
+        mid = parse_identity_value(str(min_aln_identity), ani_percentile)
+        msid = mid if str(min_scaffold_identity) == "" else parse_identity_value(str(min_scaffold_identity), ani_percentile)
+        return cls(min_block_length=0 if min_aln_length is None else parse_metric_number(str(min_aln_length)),
+                   mapping_filter_mode=mm, mapping_max_per_query=mq, mapping_max_per_target=mt,
+                   scaffold_filter_mode=sm, scaffold_max_per_query=sq, scaffold_max_per_target=st,
+                   overlap_threshold=float(overlap), scaffold_gap=jump, min_scaffold_length=mass,
+                   scaffold_overlap_threshold=float(scaffold_overlap), scaffold_max_deviation=parse_metric_number(str(scaffold_dist)),
+                   scoring_function=parse_scoring(scoring), min_identity=mid, min_scaffold_identity=msid,
+                   keep_self=keep_self, scaffolds_only=scaffolds_only)
+
+    def to_c(self) -> _lib.swg_config:
+        c = _lib.swg_config()
+        n = lambda v: _lib.NO_LIMIT if v is None else int(v)
+        c.min_block_length = int(self.min_block_length)
+        c.mapping_max_per_query, c.mapping_max_per_target = n(self.mapping_max_per_query), n(self.mapping_max_per_target)
+        c.scaffold_max_per_query, c.scaffold_max_per_target = n(self.scaffold_max_per_query), n(self.scaffold_max_per_target)
+        c.scaffold_gap, c.min_scaffold_length = int(self.scaffold_gap), int(self.min_scaffold_length)
+        c.scaffold_max_deviation = int(self.scaffold_max_deviation)
+        c.overlap_threshold, c.scaffold_overlap_threshold = float(self.overlap_threshold), float(self.scaffold_overlap_threshold)
+        c.min_identity, c.min_scaffold_identity = float(self.min_identity), float(self.min_scaffold_identity)
+        c.mapping_filter_mode, c.scaffold_filter_mode = int(self.mapping_filter_mode), int(self.scaffold_filter_mode)
+        c.scoring_function = int(self.scoring_function)
+        c.keep_self, c.scaffolds_only = int(bool(self.keep_self)), int(bool(self.scaffolds_only))
+        return c
+
+
+def filter_config_from_align_cfg(num_mappings="many:many", scaffold_filter="many:many", scaffold_jump=50_000,
+                                 scaffold_mass=10_000, scaffold_dist=0, overlap=0.95, min_identity=0.0, min_map_length=0,
+                                 avg_seq_len=0) -> FilterConfig:
+    """src/library_api.rs:223-259: library grammar, adaptive clamp always on, scaffold overlap fixed at 0.5,
+    LogLengthIdentity, min_scaffold_identity = min_identity."""
+    mm, mq, mt = parse_filter_mode(num_mappings)
+    sm, sq, st = parse_filter_mode(scaffold_filter)
+    jump, mass = clamp_scaffold_params(scaffold_jump, scaffold_mass, avg_seq_len if avg_seq_len > 0 else None, True)
+    return FilterConfig(min_block_length=min_map_length, mapping_filter_mode=mm, mapping_max_per_query=mq, mapping_max_per_target=mt,
+                        scaffold_filter_mode=sm, scaffold_max_per_query=sq, scaffold_max_per_target=st, overlap_threshold=overlap,
+                        scaffold_gap=jump, min_scaffold_length=mass, scaffold_overlap_threshold=0.5,
+                        scaffold_max_deviation=scaffold_dist, scoring_function=_lib.SCORE_LOG_LENGTH_IDENTITY,
+                        min_identity=min_identity, min_scaffold_identity=min_identity)
+
+
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class MappingTable:
+    """The compact SoA that replaces Vec<RecordMeta> (include/sweepga_b200.h: swg_mappings)."""
+    query_id: np.ndarray
+    target_id: np.ndarray
+    query_start: np.ndarray
+    query_end: np.ndarray
+    target_start: np.ndarray
+    target_end: np.ndarray
+    block_length: np.ndarray
+    matches: np.ndarray
+    identity: np.ndarray
+    strand: np.ndarray              # uint8: ord('+') forward, anything else reverse
+    seq_genome_id: np.ndarray       # per sequence: id of P(name)
+    seq_genome2_id: np.ndarray      # per sequence: id of P2(name)
+    score: Optional[np.ndarray] = None
+    names: Optional[list] = None
+    rank: Optional[np.ndarray] = None  # PAF line number of each record (parse only)
+
+    def __post_init__(self):
+        for f in ("query_id", "target_id", "query_start", "query_end", "target_start", "target_end", "block_length", "matches",
+                  "seq_genome_id", "seq_genome2_id"):
+            setattr(self, f, np.ascontiguousarray(getattr(self, f), dtype=np.uint32))
+        self.identity = np.ascontiguousarray(self.identity, dtype=np.float64)
+        self.strand = np.ascontiguousarray(self.strand, dtype=np.uint8)
+        if self.score is not None:
+            self.score = np.ascontiguousarray(self.score, dtype=np.float64)
+
+    @property
+    def n(self):
+        return int(self.query_id.shape[0])
+
+    @property
+    def n_seq(self):
+        return int(self.seq_genome_id.shape[0])
+
+    def to_c(self) -> _lib.swg_mappings:
+        m = _lib.swg_mappings()
+        m.n = self.n
+        for f in ("query_id", "target_id", "query_start", "query_end", "target_start", "target_end", "block_length", "matches",
+                  "seq_genome_id", "seq_genome2_id"):
+            setattr(m, f, _ptr(getattr(self, f), C.c_uint32))
+        m.identity = _ptr(self.identity, C.c_double)
+        m.strand = _ptr(self.strand, C.c_uint8)
+        m.score = _ptr(self.score, C.c_double) if self.score is not None else None
+        m.n_seq = self.n_seq
+        return m
+
+    def take(self, idx):
+        """Sub-table of the given record indices (sequence table shared)."""
+        g = lambda a: a[idx]
+        return MappingTable(g(self.query_id), g(self.target_id), g(self.query_start), g(self.query_end), g(self.target_start),
+                            g(self.target_end), g(self.block_length), g(self.matches), g(self.identity), g(self.strand),
+                            self.seq_genome_id, self.seq_genome2_id, None if self.score is None else g(self.score), self.names)
+
+    @staticmethod
+    def from_names(qnames, tnames, qs, qe, ts, te, blen, matches, identity, strand):
+        """Intern names (first-appearance ids, one shared table) and derive P / P2 prefix ids."""
+        ids, names = {}, []
+        def iid(s):
+            if s not in ids:
+                ids[s] = len(names)
+                names.append(s)
+            return ids[s]
+        q = np.empty(len(qnames), np.uint32)
+        t = np.empty(len(qnames), np.uint32)
+        for i, (a, b) in enumerate(zip(qnames, tnames)):
+            q[i] = iid(a)
+            t[i] = iid(b)
+        P, P2 = prefix_ids(names)
+        st = np.array([ord("+") if s == "+" else ord("-") for s in strand], np.uint8)
+        return MappingTable(q, t, qs, qe, ts, te, blen, matches, identity, st, P, P2, None, names)
+
+
+def prefix_P(name: str) -> str:
+    """src/paf_filter.rs:1022-1030"""
+    p = name.rfind("#")
+    return name if p < 0 else name[: p + 1]
+
+
+def prefix_P2(name: str) -> str:
+    """src/plane_sweep_scaffold.rs:13-22"""
+    parts = name.split("#")
+    return f"{parts[0]}#{parts[1]}#" if len(parts) >= 2 else name
+
+
+def prefix_ids(names):
+    pid, p2id = {}, {}
+    P = np.array([pid.setdefault(prefix_P(n), len(pid)) for n in names], np.uint32)
+    P2 = np.array([p2id.setdefault(prefix_P2(n), len(p2id)) for n in names], np.uint32)
+    return P, P2
+
+
+# ------------------------------------------------------------------------------------------------
+class Context:
+    """swg_ctx: one per GPU.  Raises (never falls back) when no sm_100 device is usable."""
+
+    def __init__(self, device: int = 0):
+        self._h = lib.swg_create(device)
+        if not self._h:
+            raise SwgError(_lib.ERR_CUDA, (lib.swg_last_error(None) or b"").decode())
+
+    def close(self):
+        if self._h:
+            lib.swg_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SwgError(rc, (lib.swg_last_error(self._h) or b"").decode())
+
+    def filter(self, cfg: FilterConfig, table: MappingTable, status=None, chain_id=None):
+        """apply_filters on HOST buffers (H2D + kernels + D2H).  Returns (status u8[n], chain_id u32[n], stats)."""
+        n = table.n
+        status = np.zeros(n, np.uint8) if status is None else status
+        chain_id = np.zeros(n, np.uint32) if chain_id is None else chain_id
+        res = _lib.swg_result(_ptr(status, C.c_uint8), _ptr(chain_id, C.c_uint32))
+        stats = _lib.swg_stats()
+        cm, cc = table.to_c(), cfg.to_c()
+        self._check(lib.swg_filter(self._h, C.byref(cc), C.byref(cm), C.byref(res), C.byref(stats)))
+        return status, chain_id, stats
+
+    def upload(self, table: MappingTable):
+        dev, dres = _lib.swg_mappings(), _lib.swg_result()
+        cm = table.to_c()
+        self._check(lib.swg_upload(self._h, C.byref(cm), C.byref(dev), C.byref(dres)))
+        return dev, dres
+
+    def filter_device(self, cfg: FilterConfig, dev, dres):
+        stats = _lib.swg_stats()
+        cc = cfg.to_c()
+        self._check(lib.swg_filter_device(self._h, C.byref(cc), C.byref(dev), C.byref(dres), C.byref(stats)))
+        return stats
+
+    def download(self, n, dres):
+        status, chain_id = np.zeros(n, np.uint8), np.zeros(n, np.uint32)
+        res = _lib.swg_result(_ptr(status, C.c_uint8), _ptr(chain_id, C.c_uint32))
+        self._check(lib.swg_download_result(self._h, n, C.byref(dres), C.byref(res)))
+        return status, chain_id
+
+    def release(self, dev, dres):
+        lib.swg_release(self._h, C.byref(dev), C.byref(dres))
+
+    def stream(self):
+        return lib.swg_stream(self._h)
+
+    # plane_sweep_exact.rs:268-461 -> list of kept local indices (ascending), like the reference's Vec<usize>
+    def _sweep(self, fn, mappings, *tail):
+        qs, qe, ts, te, idy = (np.ascontiguousarray([m[k] for m in mappings], dtype=dt)
+                               for k, dt in ((0, np.uint32), (1, np.uint32), (2, np.uint32), (3, np.uint32), (4, np.float64)))
+        keep = np.zeros(len(mappings), np.uint8)
+        self._check(fn(self._h, len(mappings), _ptr(qs, C.c_uint32), _ptr(qe, C.c_uint32), _ptr(ts, C.c_uint32), _ptr(te, C.c_uint32),
+                       _ptr(idy, C.c_double), *tail, _ptr(keep, C.c_uint8)))
+        return [int(i) for i in np.nonzero(keep)[0]]
+
+    def plane_sweep_query(self, mappings, mappings_to_keep, overlap_threshold, scoring=3):
+        return self._sweep(lib.swg_plane_sweep_query, mappings, _n(mappings_to_keep), overlap_threshold, scoring)
+
+    def plane_sweep_target(self, mappings, mappings_to_keep, overlap_threshold, scoring=3):
+        return self._sweep(lib.swg_plane_sweep_target, mappings, _n(mappings_to_keep), overlap_threshold, scoring)
+
+    def plane_sweep_both(self, mappings, query_to_keep, target_to_keep, overlap_threshold, scoring=3):
+        return self._sweep(lib.swg_plane_sweep_both, mappings, _n(query_to_keep), _n(target_to_keep), overlap_threshold, scoring)
+
+
+USIZE_MAX = (1 << 64) - 1
+
+
+def _n(v):
+    return USIZE_MAX if v is None else int(v)
+
+
+# ------------------------------------------------------------------------------------------------
+def parse_paf(path: str) -> MappingTable:
+    """extract_metadata (src/paf_filter.rs:292-376) on all host threads -> MappingTable (+ rank, names)."""
+    err = C.create_string_buffer(256)
+    h = lib.swg_paf_parse(os.fsencode(path), err, 256)
+    if not h:
+        raise SwgError(_lib.ERR_IO, err.value.decode())
+    try:
+        m = _lib.swg_mappings()
+        lib.swg_paf_view(h, C.byref(m))
+        n, ns = int(m.n), int(m.n_seq)
+        cp = lambda p, cnt, dt: np.ctypeslib.as_array(p, shape=(cnt,)).astype(dt, copy=True) if cnt else np.zeros(0, dt)
+        t = MappingTable(cp(m.query_id, n, np.uint32), cp(m.target_id, n, np.uint32), cp(m.query_start, n, np.uint32),
+                         cp(m.query_end, n, np.uint32), cp(m.target_start, n, np.uint32), cp(m.target_end, n, np.uint32),
+                         cp(m.block_length, n, np.uint32), cp(m.matches, n, np.uint32), cp(m.identity, n, np.float64),
+                         cp(m.strand, n, np.uint8), cp(m.seq_genome_id, ns, np.uint32), cp(m.seq_genome2_id, ns, np.uint32))
+        t.names = [lib.swg_paf_seq_name(h, i).decode() for i in range(ns)]
+        t.rank = cp(lib.swg_paf_rank(h), n, np.uint64)
+        return t
+    finally:
+        lib.swg_paf_free(h)
+
+
+class PafFilter:
+    """PafFilter (src/paf_filter.rs:229-289).  `device` picks the GPU; there is no CPU path."""
+
+    def __init__(self, config: FilterConfig, device: int = 0):
+        self.config = FilterConfig(**vars(config))  # keep_self / scaffolds_only ride along (builder methods below override)
+        self.device = device
+        self._ctx = None
+
+    @classmethod
+    def new(cls, config: FilterConfig, device: int = 0):
+        return cls(config, device)
+
+    def with_keep_self(self, keep_self: bool):
+        self.config.keep_self = bool(keep_self)
+        return self
+
+    def with_scaffolds_only(self, scaffolds_only: bool):
+        self.config.scaffolds_only = bool(scaffolds_only)
+        return self
+
+    def _context(self):
+        if self._ctx is None:
+            self._ctx = Context(self.device)
+        return self._ctx
+
+    def filter_paf(self, input_path: str, output_path: str):
+        ctx = self._context()
+        stats = _lib.swg_stats()
+        cc = self.config.to_c()
+        ctx._check(lib.swg_filter_paf(ctx._h, C.byref(cc), os.fsencode(input_path), os.fsencode(output_path), C.byref(stats)))
+        return stats
+
+    def apply_filters(self, table: MappingTable):
+        """-> {index: (chain_id or None, status)} like HashMap<rank, RecordMeta>; index = position in `table`
+        (or the PAF rank when the table came from parse_paf)."""
+        status, chain, _ = self._context().filter(self.config, table)
+        keys = table.rank if table.rank is not None else np.arange(table.n)
+        return {int(keys[i]): (f"chain_{int(chain[i])}" if chain[i] else None, ChainStatus[int(status[i])])
+                for i in np.nonzero(status)[0]}
+
+
+def filter_file(input_path, output_path, config: FilterConfig, force_paf_output=False, keep_self=False, device=0):
+    """unified_filter::filter_file (src/unified_filter.rs:280-347).  .1aln input -> SwgError(UNSUPPORTED)."""
+    with Context(device) as ctx:
+        stats = _lib.swg_stats()
+        cc = config.to_c()
+        ctx._check(lib.swg_filter_file(ctx._h, C.byref(cc), os.fsencode(input_path), os.fsencode(output_path), int(keep_self),
+                                       C.byref(stats)))
+        return stats
+
+
+def apply_paf_filter(paf_path: str, filter_config: FilterConfig, device=0) -> str:
+    """library_api::apply_paf_filter (src/library_api.rs:267-281): returns the path of a new filtered temp file."""
+    fd, out = tempfile.mkstemp(suffix=".filtered.paf")
+    os.close(fd)
+    PafFilter(filter_config, device).with_keep_self(False).filter_paf(paf_path, out)
+    return out
+
+
+def shard_plan(table: MappingTable, n_shards: int):
+    """Size-balanced genome-pair sharding for the multi-GPU driver -> (shard_of[n], shard_sizes[n_shards])."""
+    shard_of = np.zeros(table.n, np.uint32)
+    sizes = np.zeros(n_shards, np.uint64)
+    cm = table.to_c()
+    rc = lib.swg_shard_plan(C.byref(cm), n_shards, _ptr(shard_of, C.c_uint32), _ptr(sizes, C.c_uint64))
+    if rc != 0:
+        raise SwgError(rc, "swg_shard_plan")
+    return shard_of, sizes

@@ -1,0 +1,429 @@
+// filter_kernels.cuh — the sm_100a kernels of the mapping filter.
+//
+// Each kernel cites the reference code it replaces (paths relative to /root/reference).
+// All parity-critical f64 expressions use explicit round-to-nearest intrinsics or are plain
+// IEEE ops compiled with -fmad=false (no contraction).  No tensor cores: nothing here is a
+// dense contraction; every kernel is HBM/L2 bound integer/byte work.
+#pragma once
+#include "common.cuh"
+
+namespace swg {
+
+// flags[i] bits
+constexpr u8 F_ALIVE = 1;   // passed the stage-1 retain (paf_filter.rs:384-388)
+constexpr u8 F_ZLQ = 2;     // zero-length query interval
+constexpr u8 F_ZLT = 4;     // zero-length target interval
+constexpr u8 F_PREMEM = 8;  // member of a chain that passed the mass/identity filter (pre_sweep_scaffold_members)
+
+// counters (u64 each) shared with the host
+enum {
+    C_ALIVE = 0, C_ZLQ, C_ZLT, C_MAXCOORD, C_BAD, C_KEPT_M, C_GROUPS, C_CHAINS, C_PASS, C_PASS_ZEROSPAN,
+    C_KEPT_CHAINS, C_ANCHORS, C_RESCUED, C_KEPT, C_NEAR_TIES, C_WORK, C_EVGROUPS, C_INV, C_TMP0, C_TMP1, C_COUNT = 32
+};
+
+struct DevIn {
+    const u32 *qid, *tid, *qs, *qe, *ts, *te, *blen, *matches;
+    const double *identity;
+    const u8 *strand;
+    const double *score; // optional
+    const u32 *P, *P2;
+    u32 n, n_seq;
+};
+
+// ---------------------------------------------------------------------------------------------
+// open-addressing hash: genome pair (P(q),P(t)) -> min record index ("first appearance" of the
+// IndexMap at paf_filter.rs:1037-1046)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 hash64(u64 k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+    return (u32)k;
+}
+__device__ __forceinline__ void hash_insert_min(u64 *hk, u32 *hv, u32 mask, u64 key, u32 val) {
+    u32 s = hash64(key) & mask;
+    while (true) {
+        u64 prev = atomicCAS((unsigned long long *)&hk[s], (unsigned long long)NONE64, (unsigned long long)key);
+        if (prev == NONE64 || prev == key) { atomicMin(&hv[s], val); return; }
+        s = (s + 1) & mask;
+    }
+}
+__device__ __forceinline__ u32 hash_lookup(const u64 *hk, const u32 *hv, u32 mask, u64 key) {
+    u32 s = hash64(key) & mask;
+    while (true) {
+        u64 k = hk[s];
+        if (k == key) return hv[s];
+        if (k == NONE64) return NONE32;
+        s = (s + 1) & mask;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K0: stage-1 retain + range checks + genome-pair first appearance  (paf_filter.rs:384-388)
+// 33 B read + 1 B written per record.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_prefilter(DevIn in, u64 min_len, double min_id, int keep_self, u8 *__restrict__ flags,
+                                                   u64 *__restrict__ ctr, u64 *hk, u32 *hv, u32 hmask) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool alive = false, zq = false, zt = false, bad = false;
+    u32 maxc = 0;
+    u64 g = NONE64;
+    if (i < in.n) {
+        u32 q = in.qid[i], t = in.tid[i];
+        u32 qs = in.qs[i], qe = in.qe[i], ts = in.ts[i], te = in.te[i];
+        bad = q >= in.n_seq || t >= in.n_seq || qe < qs || te < ts;
+        double id = in.identity[i];
+        alive = !bad && (u64)in.blen[i] >= min_len && (keep_self || q != t) && id >= min_id;
+        zq = alive && qe == qs;
+        zt = alive && te == ts;
+        maxc = max(qe, te);
+        if (alive) g = ((u64)in.P[q] << 32) | in.P[t];
+        flags[i] = (u8)((alive ? F_ALIVE : 0) | (zq ? F_ZLQ : 0) | (zt ? F_ZLT : 0));
+    }
+    const u32 full = 0xFFFFFFFFu;
+    u32 na = __popc(__ballot_sync(full, alive)), nq = __popc(__ballot_sync(full, zq)), nt = __popc(__ballot_sync(full, zt)),
+        nb = __popc(__ballot_sync(full, bad));
+    u32 mx = __reduce_max_sync(full, maxc);
+    if (lane_id() == 0) {
+        if (na) atomicAdd((unsigned long long *)&ctr[C_ALIVE], (unsigned long long)na);
+        if (nq) atomicAdd((unsigned long long *)&ctr[C_ZLQ], (unsigned long long)nq);
+        if (nt) atomicAdd((unsigned long long *)&ctr[C_ZLT], (unsigned long long)nt);
+        if (nb) atomicAdd((unsigned long long *)&ctr[C_BAD], (unsigned long long)nb);
+        atomicMax((unsigned long long *)&ctr[C_MAXCOORD], (unsigned long long)mx);
+    }
+    // one hash insert per distinct genome pair per warp; the lowest lane holds the lowest index
+    u32 peers = __match_any_sync(full, g);
+    if (alive && lane_id() == (u32)(__ffs(peers) - 1)) hash_insert_min(hk, hv, hmask, g, i);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: chain sort keys for the mappings that survived the primary sweep (the set M).
+// key = (qid | tid | strand | query_start): replaces the (query,target,strand) IndexMap +
+// stable sort_by_key(query_start) of paf_filter.rs:761-777.   keep_q/keep_t may be NULL
+// (closed form: every alive mapping with a non-empty interval survives an n = inf sweep).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_chain_keys(DevIn in, const u8 *__restrict__ flags, const u8 *__restrict__ keep_q,
+                                                    const u8 *__restrict__ keep_t, int sb, int cb, u64 *__restrict__ keys,
+                                                    u32 *__restrict__ vals, u64 *__restrict__ ctr) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool kept = false;
+    if (i < in.n) {
+        kept = (flags[i] & F_ALIVE) && (!keep_q || keep_q[i]) && (!keep_t || keep_t[i]);
+        u64 k = NONE64;
+        if (kept) {
+            u64 sbit = in.strand[i] == '+' ? 0 : 1;
+            k = ((((u64)in.qid[i] << sb | in.tid[i]) << 1 | sbit) << cb) | in.qs[i];
+        }
+        keys[i] = k;
+        vals[i] = i;
+    }
+    u32 nk = __popc(__ballot_sync(0xFFFFFFFFu, kept));
+    if (lane_id() == 0 && nk) atomicAdd((unsigned long long *)&ctr[C_KEPT_M], (unsigned long long)nk);
+}
+
+// scaffold_gap == 0 exit (paf_filter.rs:409-434): survivors are Unassigned, no chain id
+__global__ void __launch_bounds__(256) k_unassigned(u32 n, const u8 *__restrict__ flags, const u8 *__restrict__ keep_q,
+                                                    const u8 *__restrict__ keep_t, u8 *__restrict__ status, u64 *__restrict__ ctr) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool kept = false;
+    if (i < n) {
+        kept = (flags[i] & F_ALIVE) && (!keep_q || keep_q[i]) && (!keep_t || keep_t[i]);
+        status[i] = kept ? 3 : 0;
+    }
+    u32 nk = __popc(__ballot_sync(0xFFFFFFFFu, kept));
+    if (lane_id() == 0 && nk) atomicAdd((unsigned long long *)&ctr[C_KEPT], (unsigned long long)nk);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: best-buddy chaining, one warp per (query,target,strand) group  (paf_filter.rs:780-851)
+// plus union-find roots (union_find.rs:25-41: the root of a set is always its head) and the
+// per-chain aggregates (paf_filter.rs:875-894).  The sequential scan over i is kept (it has
+// mutable per-j state); the j-window is scanned by the 32 lanes.
+// ---------------------------------------------------------------------------------------------
+struct ChainSparse { // indexed by the sorted position of the chain head
+    u32 *qmin, *qmax, *tmin, *tmax;
+    u64 *sum_matches, *sum_block;
+    u32 *minidx; // min original index over the group's members (first appearance of the group in M)
+};
+
+__global__ void __launch_bounds__(256)
+k_best_buddy(const uint4 *__restrict__ srec, const uint2 *__restrict__ srec2, const u64 *__restrict__ skey,
+             const u32 *__restrict__ sidx, const u32 *__restrict__ gstart, u32 n_groups, u32 n_m, int cb, u64 G,
+             u64 *bps, u32 *root, ChainSparse cs, u32 *group_counter) {
+    const u32 full = 0xFFFFFFFFu;
+    const u32 lane = lane_id();
+    const u64 G5 = G / 5;
+    while (true) {
+        u32 g = 0;
+        if (lane == 0) g = atomicAdd(group_counter, 1u);
+        g = __shfl_sync(full, g, 0);
+        if (g >= n_groups) break;
+        const u32 s = gstart[g], e = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
+        const bool fwd = ((skey[s] >> cb) & 1) == 0;
+        u32 B = NONE32;
+        for (u32 p = s + lane; p < e; p += 32) {
+            B = min(B, sidx[p]);
+            root[p] = p;
+            bps[p] = NONE64;
+        }
+        B = __reduce_min_sync(full, B);
+        __syncwarp();
+        for (u32 i = s; i + 1 < e; i++) {
+            const uint4 a = srec[i]; // x=qs y=qe z=ts w=te
+            const u64 bound = (u64)a.y + G;
+            u64 bd = NONE64;
+            u32 bj = NONE32;
+            for (u32 base = i + 1; base < e; base += 32) {
+                u32 j = base + lane;
+                bool inwin = false;
+                if (j < e) {
+                    const uint4 b = srec[j];
+                    inwin = (u64)b.x <= bound;
+                    if (inwin) {
+                        u64 qgap, rgap;
+                        if (b.x >= a.y) qgap = b.x - a.y;
+                        else { u64 ov = a.y - b.x; qgap = ov <= G5 ? ov : G + 1; }
+                        if (fwd) {
+                            if (b.z >= a.w) rgap = b.z - a.w;
+                            else { u64 ov = a.w - b.z; rgap = ov <= G5 ? ov : G + 1; }
+                        } else {
+                            if (a.z >= b.w) rgap = a.z - b.w;
+                            else { u64 ov = b.w - a.z; rgap = ov <= G5 ? ov : G + 1; }
+                        }
+                        if (qgap <= G && rgap <= G) {
+                            u64 d = qgap * qgap + rgap * rgap;
+                            if (d < bd && d < bps[j]) { bd = d; bj = j; }
+                        }
+                    }
+                }
+                if (!__all_sync(full, inwin)) break;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                u64 od = __shfl_down_sync(full, bd, o);
+                u32 oj = __shfl_down_sync(full, bj, o);
+                if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+            }
+            if (lane == 0 && bj != NONE32) {
+                bps[bj] = bd;
+                root[bj] = root[i];
+            }
+            __syncwarp();
+        }
+        // aggregates: heads initialise their slot, then every member reduces into its head's slot
+        for (u32 p = s + lane; p < e; p += 32) {
+            if (root[p] == p) {
+                cs.qmin[p] = NONE32; cs.qmax[p] = 0; cs.tmin[p] = NONE32; cs.tmax[p] = 0;
+                cs.sum_matches[p] = 0; cs.sum_block[p] = 0; cs.minidx[p] = B;
+            }
+        }
+        __syncwarp();
+        for (u32 base = s; base < e; base += 32) {
+            u32 p = base + lane;
+            bool ok = p < e;
+            u32 r = ok ? root[p] : NONE32;
+            uint4 a = ok ? srec[p] : make_uint4(NONE32, 0, NONE32, 0);
+            uint2 m = ok ? srec2[p] : make_uint2(0, 0);
+            u64 sm = m.y, sbk = m.x;
+            // segmented warp reduction over runs of equal root (chain members are mostly adjacent)
+            u32 peers = __match_any_sync(full, r);
+            u32 leader = __ffs(peers) - 1;
+            if (ok) {
+                if (__popc(peers) == 1) {
+                    atomicMin(&cs.qmin[r], a.x); atomicMax(&cs.qmax[r], a.y);
+                    atomicMin(&cs.tmin[r], a.z); atomicMax(&cs.tmax[r], a.w);
+                    atomicAdd((unsigned long long *)&cs.sum_matches[r], (unsigned long long)sm);
+                    atomicAdd((unsigned long long *)&cs.sum_block[r], (unsigned long long)sbk);
+                }
+            }
+            // multi-member groups: the leader folds its peers' values (<= 31 shuffles, peers-bounded)
+            u32 todo = __ballot_sync(full, ok && __popc(peers) > 1 && lane == leader);
+            while (todo) {
+                u32 L = __ffs(todo) - 1;
+                todo &= todo - 1;
+                u32 pm = __shfl_sync(full, peers, L);
+                u32 rr = __shfl_sync(full, r, L);
+                // reduce over lanes in pm
+                u32 vqmin = (pm >> lane) & 1 ? a.x : NONE32, vqmax = (pm >> lane) & 1 ? a.y : 0;
+                u32 vtmin = (pm >> lane) & 1 ? a.z : NONE32, vtmax = (pm >> lane) & 1 ? a.w : 0;
+                u64 vsm = (pm >> lane) & 1 ? sm : 0, vsb = (pm >> lane) & 1 ? sbk : 0;
+                vqmin = __reduce_min_sync(full, vqmin); vqmax = __reduce_max_sync(full, vqmax);
+                vtmin = __reduce_min_sync(full, vtmin); vtmax = __reduce_max_sync(full, vtmax);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    vsm += __shfl_down_sync(full, vsm, o);
+                    vsb += __shfl_down_sync(full, vsb, o);
+                }
+                if (lane == 0) {
+                    atomicMin(&cs.qmin[rr], vqmin); atomicMax(&cs.qmax[rr], vqmax);
+                    atomicMin(&cs.tmin[rr], vtmin); atomicMax(&cs.tmax[rr], vtmax);
+                    atomicAdd((unsigned long long *)&cs.sum_matches[rr], (unsigned long long)vsm);
+                    atomicAdd((unsigned long long *)&cs.sum_block[rr], (unsigned long long)vsb);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// chain table (dense, C rows)
+// ---------------------------------------------------------------------------------------------
+struct ChainTable {
+    u32 *pos;              // sorted position of the head
+    u32 *qid, *tid;
+    u8 *fwd;
+    u32 *qs, *qe, *ts, *te; // bounding box
+    double *wid;           // weighted_identity
+    u8 *pass;              // length/identity filter (paf_filter.rs:449-455)
+    u32 *k;                // chain number (1-based) or 0
+};
+
+// ---------------------------------------------------------------------------------------------
+// score_with_function, plane_sweep_exact.rs:29-86 (length = QUERY span on both axes)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double score_fn(int scoring, double identity, u32 qs, u32 qe) {
+    double length = (double)(qe - qs);
+    const double ninf = __longlong_as_double(0xFFF0000000000000LL);
+    switch (scoring) {
+    case 0: return identity <= 0.0 ? ninf : identity;
+    case 1: return length <= 0.0 ? ninf : length;
+    case 2:
+    case 4: return (length <= 0.0 || identity <= 0.0) ? ninf : __dmul_rn(length, identity);
+    default: return (length <= 0.0 || identity <= 0.0) ? ninf : __dmul_rn(identity, log(length));
+    }
+}
+// order-preserving map f64 -> u64, DESCENDING score = ascending key (MappingOrder::cmp, :183-194)
+__device__ __forceinline__ u64 score_desc_key(double s) {
+    u64 b = (u64)__double_as_longlong(s);
+    if (b == 0x8000000000000000ULL) b = 0; // -0.0 == +0.0 under partial_cmp
+    u64 asc = (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+    return ~asc;
+}
+// query_overlap/target_overlap > thr, plane_sweep_exact.rs:113-144
+__device__ __forceinline__ bool overlaps_more_than(u32 s1, u32 e1, u32 s2, u32 e2, double thr) {
+    u32 os = max(s1, s2), oe = min(e1, e2);
+    double ol = oe > os ? (double)(oe - os) : 0.0;
+    double ml = fmin((double)(e1 - s1), (double)(e2 - s2));
+    double ov = ml > 0.0 ? __ddiv_rn(ol, ml) : 0.0;
+    return ov > thr;
+}
+
+// ---------------------------------------------------------------------------------------------
+// General plane sweep over event-sorted groups, one warp per group
+// (plane_sweep_exact.rs:197-433: event loop + mark_good).  The active set is a rank-ordered
+// array (score desc, start asc, item asc) in a per-group slice of global scratch (L1/L2
+// resident for ordinary group sizes).  good/flagged follow the closed form
+// "kept <=> ever in the top-n at an evaluated position and never flagged overlapped".
+// ---------------------------------------------------------------------------------------------
+struct ActEntry {
+    u64 skey;  // score_desc_key
+    u32 start; // axis start
+    u32 item;
+};
+__device__ __forceinline__ bool act_less(const ActEntry &a, const ActEntry &b) {
+    if (a.skey != b.skey) return a.skey < b.skey;
+    if (a.start != b.start) return a.start < b.start;
+    return a.item < b.item;
+}
+
+__global__ void __launch_bounds__(128)
+k_sweep_groups(const u64 *__restrict__ ekey, const u32 *__restrict__ eitem, const u32 *__restrict__ gstart, u32 n_groups,
+               u32 n_events, const u32 *__restrict__ it_start, const u32 *__restrict__ it_end,
+               const double *__restrict__ it_score, u64 n_keep, double thr, ActEntry *act, u8 *good, u8 *flagged,
+               u8 *__restrict__ keep, u32 *group_counter, u64 *ctr) {
+    const u32 full = 0xFFFFFFFFu;
+    const u32 lane = lane_id();
+    while (true) {
+        u32 g = 0;
+        if (lane == 0) g = atomicAdd(group_counter, 1u);
+        g = __shfl_sync(full, g, 0);
+        if (g >= n_groups) break;
+        const u32 es = gstart[g], ee = (g + 1 < n_groups) ? gstart[g + 1] : n_events;
+        const u32 items = (ee - es) >> 1;
+        if (items <= 1) { // plane_sweep_exact.rs:274-276
+            if (lane == 0) keep[eitem[es]] = 1;
+            continue;
+        }
+        ActEntry *A = act + (es >> 1);
+        u32 size = 0;
+        u32 e = es;
+        while (e < ee) {
+            const u64 cur = ekey[e] >> 1; // (group | pos)
+            // apply all events at this position: Begins (type 0) sort before Ends (type 1)
+            while (e < ee && (ekey[e] >> 1) == cur) {
+                const u32 item = eitem[e];
+                const bool is_end = ekey[e] & 1;
+                ActEntry x;
+                x.skey = score_desc_key(it_score[item]);
+                x.start = it_start[item];
+                x.item = item;
+                // position of x in A: number of entries ordered before it
+                u32 cnt = 0;
+                for (u32 b = lane; b < size; b += 32) cnt += act_less(A[b], x) ? 1 : 0;
+                cnt = __reduce_add_sync(full, cnt);
+                if (!is_end) {
+                    // near-tie audit: neighbours whose score key differs by <= 2 ulp but is not equal
+                    if (lane == 0) {
+                        u32 near = 0;
+                        if (cnt > 0) { u64 d = x.skey - A[cnt - 1].skey; near += (d != 0 && d <= 2); }
+                        if (cnt < size) { u64 d = A[cnt].skey - x.skey; near += (d != 0 && d <= 2); }
+                        if (near) atomicAdd((unsigned long long *)&ctr[C_NEAR_TIES], (unsigned long long)near);
+                    }
+                    // shift [cnt, size) up by one, from the top, 32 at a time
+                    for (u32 hi = size; hi > cnt;) {
+                        u32 lo = hi > cnt + 32 ? hi - 32 : cnt;
+                        u32 b = lo + lane;
+                        ActEntry t;
+                        bool mv = b < hi;
+                        if (mv) t = A[b];
+                        __syncwarp();
+                        if (mv) A[b + 1] = t;
+                        __syncwarp();
+                        hi = lo;
+                    }
+                    if (lane == 0) A[cnt] = x;
+                    size++;
+                } else {
+                    // remove the entry at cnt (it is there: every End follows its Begin)
+                    for (u32 lo = cnt + 1; lo < size; lo += 32) {
+                        u32 b = lo + lane;
+                        ActEntry t;
+                        bool mv = b < size;
+                        if (mv) t = A[b];
+                        __syncwarp();
+                        if (mv) A[b - 1] = t;
+                        __syncwarp();
+                    }
+                    size--;
+                }
+                __syncwarp();
+                e++;
+            }
+            if (size == 0) continue;
+            // mark_good (plane_sweep_exact.rs:197-259)
+            const u32 top = (u64)size <= n_keep ? size : (u32)n_keep;
+            for (u32 b = lane; b < top; b += 32) good[A[b].item] = 1;
+            if (thr < 1.0 && top < size) {
+                for (u32 b = top + lane; b < size; b += 32) {
+                    const u32 m = A[b].item;
+                    if (flagged[m]) continue;
+                    const u32 ms = it_start[m], me = it_end[m];
+                    for (u32 t = 0; t < top; t++) {
+                        const u32 k = A[t].item;
+                        if (overlaps_more_than(ms, me, it_start[k], it_end[k], thr)) { flagged[m] = 1; break; }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        // result for this group
+        for (u32 b = es + lane; b < ee; b += 32) {
+            if ((ekey[b] & 1) == 0) {
+                u32 item = eitem[b];
+                keep[item] = (good[item] && !flagged[item]) ? 1 : 0;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+} // namespace swg

@@ -1,0 +1,874 @@
+// filter_pipeline.cu — swg_ctx, the device pipeline that replaces the body of
+// PafFilter::apply_filters (reference src/paf_filter.rs:379-747) and its C ABI.
+//
+// Stage order mirrors the reference:
+//   K0  stage-1 retain                                   paf_filter.rs:384-388
+//   GS  primary plane sweep (closed form when n = inf)   paf_filter.rs:972-1123, plane_sweep_exact.rs
+//   K1+sort+K2  (q,t,strand) grouping + stable sort      paf_filter.rs:761-777
+//   K3  best-buddy chaining + roots + aggregates         paf_filter.rs:780-928, union_find.rs
+//   K4  chain table, mass/identity filter                paf_filter.rs:449-455
+//   O*  insertion-order reproduction -> chain_N          SURVEY Appendix B
+//   GS  scaffold plane sweep (closed form when n = inf)  plane_sweep_scaffold.rs:47-251
+//   K5  anchors                                          paf_filter.rs:517-528
+//   K6  inversion capture                                paf_filter.rs:535-597
+//   K7  rescue                                           paf_filter.rs:613-732
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "sweepga_b200.h"
+#include "common.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+#include "filter_kernels.cuh"
+
+namespace swg {
+
+struct RangeError { std::string msg; };
+struct OomError { size_t bytes; };
+
+// ---- generic element-wise launcher (named by Tag so the launch list is readable) ------------
+template <class Tag, class F> __global__ void __launch_bounds__(256) k_for(u32 n, F f) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) f(i);
+}
+template <class Tag, class F> static inline void launch_for(u32 n, cudaStream_t st, LaunchCounter &lc, F f) {
+    if (n == 0) return;
+    k_for<Tag, F><<<cdiv(n, 256), 256, 0, st>>>(n, f);
+    lc.n++;
+}
+struct t_iota; struct t_maxp; struct t_scores; struct t_gkey; struct t_events; struct t_chain_order; struct t_tspace; struct t_segfirst;
+struct t_segapply; struct t_keys_c2min; struct t_keys_g2min; struct t_final_k; struct t_assign; struct t_invkeys; struct t_invtab;
+struct t_inversion; struct t_anchor_keys; struct t_rescue; struct t_count_kept; struct t_chain_score;
+
+// ---- grow-only HBM arena ----------------------------------------------------------------------
+// One block sized for the common path; a call that needs more (general sweeps, degenerate
+// inputs) chains extra blocks, and the next reserve() consolidates them into one.
+struct Arena {
+    struct Block { char *base; size_t cap, off; };
+    std::vector<Block> blocks;
+    static char *dev_alloc(size_t bytes) {
+        char *p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); throw OomError{bytes}; }
+        return p;
+    }
+    void release() {
+        for (auto &b : blocks) cudaFree(b.base);
+        blocks.clear();
+    }
+    void reserve(size_t bytes) {
+        size_t total = 0;
+        for (auto &b : blocks) total += b.cap;
+        if (blocks.size() != 1 || blocks[0].cap < bytes) {
+            size_t want = std::max(bytes, total);
+            release();
+            blocks.push_back(Block{dev_alloc(want), want, 0});
+        }
+        blocks[0].off = 0;
+    }
+    template <class T> T *take(size_t n) {
+        size_t b = (n * sizeof(T) + 255) & ~(size_t)255;
+        if (b == 0) b = 256;
+        Block *blk = blocks.empty() ? nullptr : &blocks.back();
+        if (!blk || blk->off + b > blk->cap) {
+            size_t want = std::max<size_t>(b, (size_t)256 << 20);
+            blocks.push_back(Block{dev_alloc(want), want, 0});
+            blk = &blocks.back();
+        }
+        T *p = reinterpret_cast<T *>(blk->base + blk->off);
+        blk->off += b;
+        return p;
+    }
+    // stack discipline for temporaries: everything taken after mark() dies at rewind()
+    struct Mark { size_t nblocks, off; };
+    Mark mark() const { return Mark{blocks.size(), blocks.empty() ? 0 : blocks.back().off}; }
+    void rewind(const Mark &m) {
+        if (m.nblocks == 0 || blocks.size() < m.nblocks) return;
+        for (size_t i = m.nblocks; i < blocks.size(); i++) blocks[i].off = 0; // later blocks stay allocated (grow-only)
+        // only the block that was current at mark() can be rewound safely
+        if (blocks.size() == m.nblocks) blocks[m.nblocks - 1].off = m.off;
+    }
+};
+
+} // namespace swg
+
+using namespace swg;
+
+struct swg_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    Arena arena;      // per-call scratch
+    Arena io;         // staging of host SoA for swg_filter
+    u64 *h_ctr = nullptr; // pinned mirror of the counters
+    u64 *d_ctr = nullptr;
+    std::string err;
+    LaunchCounter lc;
+};
+
+static std::string g_create_error;
+
+namespace swg {
+
+static void set_err(swg_ctx *c, const std::string &m) { if (c) c->err = m; else g_create_error = m; }
+
+static void read_counters(swg_ctx *c) {
+    SWG_CUDA(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(u64) * C_COUNT, cudaMemcpyDeviceToHost, c->stream));
+    SWG_CUDA(cudaStreamSynchronize(c->stream));
+}
+static u32 read_u32(swg_ctx *c, const u32 *d) {
+    u32 *h = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
+    SWG_CUDA(cudaMemcpyAsync(h, d, sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+    SWG_CUDA(cudaStreamSynchronize(c->stream));
+    return *h;
+}
+
+// sort (key,payload) pairs in arena scratch; returns sorted pointers through the references
+static void sort_pairs(swg_ctx *c, u64 *&k, u64 *&k2, u32 *&v, u32 *&v2, u32 n, int bits) {
+    if (n == 0) return;
+    if (bits > 64) throw RangeError{"sort key wider than 64 bits (too many sequences x coordinate range)"};
+    for (int begin = 0; begin < bits; begin += RS_MAX_PASSES * RS_BITS) { // > 8 passes never happens (64 bits)
+        RadixSortPlan p = rs_plan(n, begin, bits);
+        void *tmp = c->arena.take<char>(p.temp_bytes);
+        rs_sort_pairs(p, k, k2, v, v2, tmp, c->stream, c->sm_count, c->lc);
+    }
+}
+
+// ---- general plane sweep over arbitrary items (records or chains) ----------------------------
+// include == nullptr: all items.  gkey < 2^gb - 1.  keep[] is fully overwritten (0 for excluded).
+static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 include_mask, const u64 *gkey, int gb,
+                               const u32 *it_start, const u32 *it_end, const double *it_score, u64 n_keep, double thr, u8 *keep) {
+    cudaStream_t st = c->stream;
+    SWG_CUDA(cudaMemsetAsync(keep, 0, n_items, st));
+    if (n_items == 0) return;
+    if (gb + 33 > 64) throw RangeError{"plane-sweep group key too wide for a 64-bit event key"};
+    if ((u64)n_items * 2 >= 0xFFFFFFF0ull) throw RangeError{"too many sweep events"};
+    u32 n_ev_all = n_items * 2;
+    u64 *ek = c->arena.take<u64>(n_ev_all), *ek2 = c->arena.take<u64>(n_ev_all);
+    u32 *ev = c->arena.take<u32>(n_ev_all), *ev2 = c->arena.take<u32>(n_ev_all);
+    u64 *ctr = c->d_ctr;
+    SWG_CUDA(cudaMemsetAsync(ctr + C_TMP0, 0, sizeof(u64), st));
+    launch_for<t_events>(n_items, st, c->lc, [=] __device__(u32 i) {
+        bool inc = include ? (include[i] & include_mask) != 0 : true;
+        u64 k0 = NONE64, k1 = NONE64;
+        if (inc) {
+            k0 = (gkey[i] << 33) | ((u64)it_start[i] << 1);
+            k1 = (gkey[i] << 33) | ((u64)it_end[i] << 1) | 1;
+        }
+        ek[2 * i] = k0; ev[2 * i] = i;
+        ek[2 * i + 1] = k1; ev[2 * i + 1] = i;
+        u32 am = __activemask();
+        u32 cnt = __popc(__ballot_sync(am, inc));
+        if (cnt && (threadIdx.x & 31) == (u32)(__ffs(am) - 1)) atomicAdd((unsigned long long *)&ctr[C_TMP0], (unsigned long long)cnt);
+    });
+    sort_pairs(c, ek, ek2, ev, ev2, n_ev_all, gb + 33);
+    read_counters(c);
+    u32 n_ev = (u32)(c->h_ctr[C_TMP0] * 2);
+    if (n_ev == 0) return;
+    u32 *gstart = c->arena.take<u32>(n_ev / 2 + 1);
+    u32 *bsum = c->arena.take<u32>(scan_temp_u32(n_ev));
+    u32 *d_ng = c->arena.take<u32>(2);
+    const u64 *ekc = ek;
+    scan_apply([=] __device__(u32 u) -> u32 { return (u == 0 || (ekc[u] >> 33) != (ekc[u - 1] >> 33)) ? 1u : 0u; },
+               [=] __device__(u32 u, u32 ex, u32 v) { if (v) gstart[ex] = u; }, n_ev, bsum, d_ng, st, c->lc);
+    u32 n_groups = read_u32(c, d_ng);
+    ActEntry *act = c->arena.take<ActEntry>(n_ev / 2 + 1);
+    u8 *good = c->arena.take<u8>(n_items), *flagged = c->arena.take<u8>(n_items);
+    SWG_CUDA(cudaMemsetAsync(good, 0, n_items, st));
+    SWG_CUDA(cudaMemsetAsync(flagged, 0, n_items, st));
+    SWG_CUDA(cudaMemsetAsync(d_ng + 1, 0, sizeof(u32), st));
+    u32 blocks = std::min<u32>(cdiv(n_groups, 4), (u32)c->sm_count * 8);
+    k_sweep_groups<<<blocks, 128, 0, st>>>(ek, ev, gstart, n_groups, n_ev, it_start, it_end, it_score, n_keep, thr, act, good,
+                                          flagged, keep, d_ng + 1, ctr);
+    c->lc.n++;
+    SWG_CUDA(cudaGetLastError());
+}
+
+static void general_sweep(swg_ctx *c, u32 n_items, const u8 *include, u8 include_mask, const u64 *gkey, int gb,
+                          const u32 *it_start, const u32 *it_end, const double *it_score, u64 n_keep, double thr, u8 *keep) {
+    Arena::Mark mk = c->arena.mark(); // temporaries are stream-ordered: safe to reuse after the launches are queued
+    general_sweep_impl(c, n_items, include, include_mask, gkey, gb, it_start, it_end, it_score, n_keep, thr, keep);
+    c->arena.rewind(mk);
+}
+
+// segment-first: for keys sorted ascending with payload vals (n rows), out[vals[u]] = vals[first row of u's segment]
+static void segment_first(swg_ctx *c, const u64 *sk, const u32 *sv, u32 n, u32 *out) {
+    if (n == 0) return;
+    cudaStream_t st = c->stream;
+    u32 *segof = c->arena.take<u32>(n), *segfirst = c->arena.take<u32>(n);
+    u32 *bsum = c->arena.take<u32>(scan_temp_u32(n)), *tot = c->arena.take<u32>(1);
+    scan_apply([=] __device__(u32 u) -> u32 { return (u == 0 || sk[u] != sk[u - 1]) ? 1u : 0u; },
+               [=] __device__(u32 u, u32 ex, u32 v) { u32 s = ex + v - 1; segof[u] = s; if (v) segfirst[s] = sv[u]; }, n, bsum, tot,
+               st, c->lc);
+    launch_for<t_segapply>(n, st, c->lc, [=] __device__(u32 u) { out[sv[u]] = segfirst[segof[u]]; });
+}
+
+// ================================================================================================
+// the pipeline
+// ================================================================================================
+static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *status, u32 *chain_id, swg_stats *stats) {
+    cudaStream_t st = c->stream;
+    LaunchCounter &lc = c->lc;
+    const u32 N = in.n;
+    u64 launches0 = lc.n;
+    swg_stats S;
+    std::memset(&S, 0, sizeof S);
+    S.n_input = N;
+    SWG_CUDA(cudaMemsetAsync(status, 0, N, st));
+    SWG_CUDA(cudaMemsetAsync(chain_id, 0, sizeof(u32) * (size_t)N, st));
+    auto finish = [&]() {
+        S.gpu_launches = lc.n - launches0;
+        if (stats) *stats = S;
+    };
+    if (N == 0) { SWG_CUDA(cudaStreamSynchronize(st)); finish(); return; }
+    if (cfg.scaffold_gap >= (1ull << 31) || cfg.scaffold_max_deviation >= (1ull << 31))
+        throw RangeError{"scaffold_gap / scaffold_max_deviation must be < 2^31"};
+
+    c->arena.reserve((size_t)N * 320 + (64u << 20));
+    Arena &A = c->arena;
+    u64 *ctr = c->d_ctr;
+    SWG_CUDA(cudaMemsetAsync(ctr, 0, sizeof(u64) * C_COUNT, st));
+
+    // ---- K0 ------------------------------------------------------------------------------
+    u8 *flags = A.take<u8>(N);
+    // distinct genome pairs <= min(N, nP^2); table of 2x that, power of two
+    u32 *d_maxp = A.take<u32>(2);
+    SWG_CUDA(cudaMemsetAsync(d_maxp, 0, 2 * sizeof(u32), st));
+    launch_for<t_maxp>(in.n_seq, st, lc, [=] __device__(u32 s) { atomicMax(&d_maxp[0], in.P[s]); atomicMax(&d_maxp[1], in.P2[s]); });
+    const u32 maxP = read_u32(c, d_maxp), maxP2 = read_u32(c, d_maxp + 1);
+    if (maxP >= in.n_seq || maxP2 >= in.n_seq) throw RangeError{"genome prefix id >= n_seq (prefix ids must be dense)"};
+    u64 npairs = std::min<u64>((u64)N, (u64)(maxP + 1) * (maxP + 1));
+    u32 hcap = 1024;
+    while ((u64)hcap < npairs * 2) hcap <<= 1;
+    u64 *hk = A.take<u64>(hcap);
+    u32 *hv = A.take<u32>(hcap);
+    SWG_CUDA(cudaMemsetAsync(hk, 0xFF, sizeof(u64) * hcap, st));
+    SWG_CUDA(cudaMemsetAsync(hv, 0xFF, sizeof(u32) * hcap, st));
+    k_prefilter<<<cdiv(N, 256), 256, 0, st>>>(in, cfg.min_block_length, cfg.min_identity, cfg.keep_self, flags, ctr, hk, hv, hcap - 1);
+    lc.n++;
+    read_counters(c);
+    if (c->h_ctr[C_BAD]) throw RangeError{"record with end < start or sequence id >= n_seq"};
+    const u64 n_alive = c->h_ctr[C_ALIVE], zlq = c->h_ctr[C_ZLQ], zlt = c->h_ctr[C_ZLT];
+    const u32 maxcoord = (u32)c->h_ctr[C_MAXCOORD];
+    S.n_stage1 = n_alive;
+    const int sb = bits_for(in.n_seq);      // ids < n_seq <= 2^sb - 1: the all-ones pattern stays free for dead keys
+    const int cb = bits_for(maxcoord);
+    const int pb = sb; // prefix ids are < n_seq
+
+    // ---- primary plane sweep (paf_filter.rs:972-1123) ----------------------------------------
+    u64 qlim, tlim;
+    switch (cfg.mapping_filter_mode) {
+    case SWG_ONE_TO_ONE: qlim = 1; tlim = 1; break;
+    case SWG_ONE_TO_MANY: qlim = cfg.mapping_max_per_query != SWG_NO_LIMIT ? cfg.mapping_max_per_query : 1; tlim = cfg.mapping_max_per_target; break;
+    default: qlim = cfg.mapping_max_per_query; tlim = cfg.mapping_max_per_target;
+    }
+    u8 *keep_q = nullptr, *keep_t = nullptr;
+    const bool need_q = n_alive > 1 && (qlim != SWG_KEEP_ALL || zlq > 0);
+    const bool need_t = n_alive > 1 && (tlim != SWG_KEEP_ALL || zlt > 0);
+    double *rscore = nullptr;
+    if (need_q || need_t) {
+        rscore = A.take<double>(N);
+        const int scoring = cfg.scoring_function;
+        launch_for<t_scores>(N, st, lc, [=] __device__(u32 i) {
+            rscore[i] = in.score ? in.score[i] : score_fn(scoring, in.identity[i], in.qs[i], in.qe[i]);
+        });
+        u64 *gk = A.take<u64>(N);
+        for (int axis = 0; axis < 2; axis++) {
+            if (axis == 0 ? !need_q : !need_t) continue;
+            launch_for<t_gkey>(N, st, lc, [=] __device__(u32 i) {
+                u32 a = axis == 0 ? in.qid[i] : in.tid[i], b = axis == 0 ? in.tid[i] : in.qid[i];
+                gk[i] = ((u64)a << pb) | in.P[b];
+            });
+            u8 *keep = A.take<u8>(N);
+            general_sweep(c, N, flags, F_ALIVE, gk, sb + pb, axis == 0 ? in.qs : in.ts, axis == 0 ? in.qe : in.te, rscore,
+                          axis == 0 ? qlim : tlim, cfg.overlap_threshold, keep);
+            (axis == 0 ? keep_q : keep_t) = keep;
+        }
+    }
+
+    // ---- no-scaffold exit (paf_filter.rs:409-434) -----------------------------------------------
+    if (cfg.scaffold_gap == 0) {
+        k_unassigned<<<cdiv(N, 256), 256, 0, st>>>(N, flags, keep_q, keep_t, status, ctr);
+        lc.n++;
+        read_counters(c);
+        S.n_after_sweep = S.n_kept = c->h_ctr[C_KEPT];
+        S.score_near_ties = c->h_ctr[C_NEAR_TIES];
+        finish();
+        return;
+    }
+
+    // ---- K1 + sort + K2: group by (q,t,strand), stable order by query_start ------------------------
+    if (2 * sb + 1 + cb > 64) throw RangeError{"(query,target,strand,start) key wider than 64 bits"};
+    u64 *keys = A.take<u64>(N), *keys2 = A.take<u64>(N);
+    u32 *vals = A.take<u32>(N), *vals2 = A.take<u32>(N);
+    k_chain_keys<<<cdiv(N, 256), 256, 0, st>>>(in, flags, keep_q, keep_t, sb, cb, keys, vals, ctr);
+    lc.n++;
+    sort_pairs(c, keys, keys2, vals, vals2, N, 2 * sb + 1 + cb);
+    read_counters(c);
+    const u32 n_m = (u32)c->h_ctr[C_KEPT_M];
+    S.n_after_sweep = n_m;
+    S.score_near_ties = c->h_ctr[C_NEAR_TIES];
+    if (n_m == 0) { finish(); return; }
+    const u64 *skey = keys;
+    const u32 *sidx = vals;
+    uint4 *srec = A.take<uint4>(n_m);
+    uint2 *srec2 = A.take<uint2>(n_m);
+    u32 *gstart = A.take<u32>(n_m + 1);
+    u32 *bsum = A.take<u32>(scan_temp_u32(N));
+    u32 *d_tot = A.take<u32>(4);
+    scan_apply([=] __device__(u32 p) -> u32 { return (p == 0 || (skey[p] >> cb) != (skey[p - 1] >> cb)) ? 1u : 0u; },
+               [=] __device__(u32 p, u32 ex, u32 v) {
+                   if (v) gstart[ex] = p;
+                   u32 i = sidx[p];
+                   srec[p] = make_uint4(in.qs[i], in.qe[i], in.ts[i], in.te[i]);
+                   srec2[p] = make_uint2(in.blen[i], in.matches[i]);
+               },
+               n_m, bsum, d_tot, st, lc);
+    const u32 n_groups = read_u32(c, d_tot);
+
+    // ---- K3: best-buddy chaining ---------------------------------------------------------------
+    u64 *bps = A.take<u64>(n_m);
+    u32 *root = A.take<u32>(n_m);
+    ChainSparse cs;
+    cs.qmin = A.take<u32>(n_m); cs.qmax = A.take<u32>(n_m); cs.tmin = A.take<u32>(n_m); cs.tmax = A.take<u32>(n_m);
+    cs.sum_matches = A.take<u64>(n_m); cs.sum_block = A.take<u64>(n_m); cs.minidx = A.take<u32>(n_m);
+    SWG_CUDA(cudaMemsetAsync(d_tot + 1, 0, sizeof(u32), st));
+    {
+        u32 blocks = std::min<u32>(cdiv(n_groups, 8), (u32)c->sm_count * 8);
+        k_best_buddy<<<blocks, 256, 0, st>>>(srec, srec2, skey, sidx, gstart, n_groups, n_m, cb, cfg.scaffold_gap, bps, root, cs, d_tot + 1);
+        lc.n++;
+    }
+
+    // ---- K4: dense chain table + mass/identity filter + order key (A,B) ----------------------------
+    // upper bound on chains is n_m; the table is sized after counting heads
+    u32 *chain_of_pos = A.take<u32>(n_m);
+    u32 *d_nch = d_tot + 2;
+    {   // count heads first (cheap) so the dense table is sized exactly
+        scan_apply([=] __device__(u32 p) -> u32 { return root[p] == p ? 1u : 0u; },
+                   [=] __device__(u32 p, u32 ex, u32 v) { if (v) chain_of_pos[p] = ex; }, n_m, bsum, d_nch, st, lc);
+    }
+    const u32 C = read_u32(c, d_nch);
+    S.n_chains = C;
+    ChainTable ct;
+    ct.pos = A.take<u32>(C); ct.qid = A.take<u32>(C); ct.tid = A.take<u32>(C); ct.fwd = A.take<u8>(C);
+    ct.qs = A.take<u32>(C); ct.qe = A.take<u32>(C); ct.ts = A.take<u32>(C); ct.te = A.take<u32>(C);
+    ct.wid = A.take<double>(C); ct.pass = A.take<u8>(C); ct.k = A.take<u32>(C);
+    SWG_CUDA(cudaMemsetAsync(ct.k, 0, sizeof(u32) * (size_t)C, st));
+    const int nb = bits_for(N);
+    if (2 * nb > 63) throw RangeError{"too many records for the chain order key"};
+    u64 *okey = A.take<u64>(C), *okey2 = A.take<u64>(C);
+    u32 *oval = A.take<u32>(C), *oval2 = A.take<u32>(C);
+    {
+        const u64 min_len = cfg.min_scaffold_length;
+        const double min_sid = cfg.min_scaffold_identity;
+        const u32 seqmask = (u32)((1ull << sb) - 1);
+        const u32 hmask = hcap - 1;
+        launch_for<t_chain_order>(n_m, st, lc, [=] __device__(u32 p) {
+            if (root[p] != p) return;
+            u32 ci = chain_of_pos[p];
+            u64 k = skey[p] >> cb;
+            u8 fwd = (k & 1) == 0;
+            u32 tid = (u32)(k >> 1) & seqmask, qid = (u32)(k >> (1 + sb)) & seqmask;
+            u32 qmin = cs.qmin[p], qmax = cs.qmax[p], tmin = cs.tmin[p], tmax = cs.tmax[p];
+            u64 sm = cs.sum_matches[p], sbk = cs.sum_block[p];
+            u64 total = (u64)(qmax - qmin);                         // paf_filter.rs:896
+            u64 gap = total > sbk ? total - sbk : 0;                // saturating_sub, :901
+            double lg = gap > 0 ? fmax(log((double)gap), 0.0) : 0.0; // :902-906
+            double eff = __dadd_rn((double)sbk, lg);
+            double wid = eff > 0.0 ? __ddiv_rn((double)sm, eff) : 0.0;
+            bool pass = total >= min_len && wid >= min_sid;          // :449-455
+            ct.pos[ci] = p; ct.qid[ci] = qid; ct.tid[ci] = tid; ct.fwd[ci] = fwd;
+            ct.qs[ci] = qmin; ct.qe[ci] = qmax; ct.ts[ci] = tmin; ct.te[ci] = tmax;
+            ct.wid[ci] = wid; ct.pass[ci] = pass ? 1 : 0;
+            u64 ok = NONE64;
+            if (pass) {
+                u32 Aidx = hash_lookup(hk, hv, hmask, ((u64)in.P[qid] << 32) | in.P[tid]);
+                ok = ((u64)Aidx << nb) | cs.minidx[p];
+                atomicAdd((unsigned long long *)&ctr[C_PASS], 1ull);
+                if (qmax == qmin || tmax == tmin) atomicAdd((unsigned long long *)&ctr[C_PASS_ZEROSPAN], 1ull);
+            }
+            okey[ci] = ok; oval[ci] = ci;
+        });
+    }
+    sort_pairs(c, okey, okey2, oval, oval2, C, 2 * nb); // stable: ties (same group) keep head-position order
+    read_counters(c);
+    const u32 C1 = (u32)c->h_ctr[C_PASS];
+    const u64 pass_zero = c->h_ctr[C_PASS_ZEROSPAN];
+    S.n_chains_after_mass = C1;
+
+    // ---- O*: t-space = passing chains in the reference's `filtered_chains` order ------------------
+    // oc_chain[t] = dense chain id of the t-th filtered chain
+    const u32 *oc_chain = oval;
+    u32 C2 = 0;
+    u32 *fin_t = nullptr; // fin_t[u] = t of the chain numbered u+1
+    u32 *t_qs = nullptr, *t_qe = nullptr, *t_ts = nullptr, *t_te = nullptr;
+    u64 *t_c2key = nullptr;
+    u8 *t_fwd = nullptr;
+    if (C1 > 0) {
+        t_qs = A.take<u32>(C1); t_qe = A.take<u32>(C1); t_ts = A.take<u32>(C1); t_te = A.take<u32>(C1);
+        t_c2key = A.take<u64>(C1);
+        u64 *t_g2key = A.take<u64>(C1);
+        t_fwd = A.take<u8>(C1);
+        double *t_score = A.take<double>(C1);
+        const int scoring = cfg.scoring_function;
+        launch_for<t_tspace>(C1, st, lc, [=] __device__(u32 t) {
+            u32 ci = oc_chain[t];
+            u32 q = ct.qid[ci], tt = ct.tid[ci];
+            t_qs[t] = ct.qs[ci]; t_qe[t] = ct.qe[ci]; t_ts[t] = ct.ts[ci]; t_te[t] = ct.te[ci];
+            t_c2key[t] = ((u64)q << sb) | tt;
+            t_g2key[t] = ((u64)in.P2[q] << sb) | in.P2[tt];
+            t_fwd[t] = ct.fwd[ci];
+            t_score[t] = score_fn(scoring, ct.wid[ci], ct.qs[ci], ct.qe[ci]);
+        });
+        // first-appearance order of chromosome pairs and genome pairs over the filtered chains
+        u32 *c2min = A.take<u32>(C1), *g2min = A.take<u32>(C1);
+        u64 *sk = A.take<u64>(C1), *sk2 = A.take<u64>(C1);
+        u32 *sv = A.take<u32>(C1), *sv2 = A.take<u32>(C1);
+        for (int which = 0; which < 2; which++) {
+            const u64 *src = which == 0 ? t_c2key : t_g2key;
+            launch_for<t_iota>(C1, st, lc, [=] __device__(u32 t) { sk[t] = src[t]; sv[t] = t; });
+            sort_pairs(c, sk, sk2, sv, sv2, C1, 2 * sb);
+            segment_first(c, sk, sv, C1, which == 0 ? c2min : g2min);
+        }
+        // scaffold plane sweep (plane_sweep_scaffold.rs:47-251)
+        u8 *t_keep = nullptr;
+        u64 nq, nt;
+        if (cfg.scaffold_filter_mode == SWG_ONE_TO_ONE) { nq = 1; nt = 1; }
+        else { nq = cfg.scaffold_max_per_query; nt = cfg.scaffold_max_per_target; }
+        const bool need_sweep = C1 > 1 && (nq != SWG_KEEP_ALL || nt != SWG_KEEP_ALL || pass_zero > 0);
+        if (need_sweep) {
+            u8 *k1 = A.take<u8>(C1);
+            t_keep = A.take<u8>(C1);
+            general_sweep(c, C1, nullptr, 0, t_c2key, 2 * sb, t_qs, t_qe, t_score, nq, cfg.scaffold_overlap_threshold, k1);
+            general_sweep(c, C1, k1, 1, t_c2key, 2 * sb, t_ts, t_te, t_score, nt, cfg.scaffold_overlap_threshold, t_keep);
+        }
+        // final order: (g2min, c2min, t): two stable sorts, least significant first (t is the input order)
+        const int ob = bits_for(C1);
+        launch_for<t_keys_c2min>(C1, st, lc, [=] __device__(u32 t) { sk[t] = c2min[t]; sv[t] = t; });
+        sort_pairs(c, sk, sk2, sv, sv2, C1, ob);
+        {
+            const u32 *svc = sv;
+            u64 *skw = sk;
+            launch_for<t_keys_g2min>(C1, st, lc, [=] __device__(u32 u) {
+                u32 t = svc[u];
+                bool kept = t_keep ? t_keep[t] != 0 : true;
+                skw[u] = kept ? (u64)g2min[t] : ((1ull << ob) | 0); // dropped chains sort last
+                if (kept) atomicAdd((unsigned long long *)&ctr[C_KEPT_CHAINS], 1ull);
+            });
+        }
+        sort_pairs(c, sk, sk2, sv, sv2, C1, ob + 1);
+        read_counters(c);
+        C2 = (u32)c->h_ctr[C_KEPT_CHAINS];
+        S.score_near_ties = c->h_ctr[C_NEAR_TIES];
+        fin_t = sv;
+        {
+            const u32 *fin = sv;
+            launch_for<t_final_k>(C2, st, lc, [=] __device__(u32 u) { ct.k[oc_chain[fin[u]]] = u + 1; });
+        }
+    }
+    S.n_chains_kept = C2;
+
+    // ---- K5: anchors = members of kept chains (paf_filter.rs:517-528) ---------------------------------
+    launch_for<t_assign>(n_m, st, lc, [=] __device__(u32 p) {
+        u32 ci = chain_of_pos[root[p]];
+        u32 i = sidx[p];
+        u32 kk = ct.k[ci];
+        if (kk) { status[i] = 1; chain_id[i] = kk; }
+        if (ct.pass[ci]) flags[i] |= F_PREMEM;
+    });
+
+    if (!cfg.scaffolds_only && C2 > 0) {
+        // ---- K6: inversion capture (paf_filter.rs:535-597) ------------------------------------------
+        // kept '+' chains ordered by (chromosome pair, k)
+        u64 *ik = A.take<u64>(C2), *ik2 = A.take<u64>(C2);
+        u32 *iv = A.take<u32>(C2), *iv2 = A.take<u32>(C2);
+        u32 *u_qs = A.take<u32>(C2), *u_qe = A.take<u32>(C2), *u_ts = A.take<u32>(C2);
+        {
+            const u32 *fin = fin_t;
+            launch_for<t_invkeys>(C2, st, lc, [=] __device__(u32 u) {
+                u32 t = fin[u];
+                bool f = t_fwd[t] != 0;
+                ik[u] = f ? t_c2key[t] : NONE64;
+                iv[u] = u;
+                u_qs[u] = t_qs[t]; u_qe[u] = t_qe[t]; u_ts[u] = t_ts[t];
+                if (f) atomicAdd((unsigned long long *)&ctr[C_INV], 1ull);
+            });
+        }
+        sort_pairs(c, ik, ik2, iv, iv2, C2, 2 * sb + 1);
+        read_counters(c);
+        const u32 Cf = (u32)c->h_ctr[C_INV];
+        if (Cf > 0) {
+            const u64 G = cfg.scaffold_gap;
+            const u64 *ikc = ik;
+            const u32 *ivc = iv;
+            launch_for<t_inversion>(N, st, lc, [=] __device__(u32 i) {
+                if (!(flags[i] & F_ALIVE) || in.strand[i] == '+' || status[i] != 0) return;
+                u64 key = ((u64)in.qid[i] << sb) | in.tid[i];
+                u32 lo = 0, hi = Cf;
+                while (lo < hi) { u32 mid = (lo + hi) >> 1; if (ikc[mid] < key) lo = mid + 1; else hi = mid; }
+                u64 mqs = in.qs[i], mqe = in.qe[i], mts = in.ts[i], mte = in.te[i];
+                u64 qc = (mqs + mqe) / 2, tc = (mts + mte) / 2;
+                for (u32 x = lo; x < Cf && ikc[x] == key; x++) {
+                    u32 u = ivc[x];
+                    u64 cqs = u_qs[u], cqe = u_qe[u], cts = u_ts[u];
+                    u64 ext_s = cqs > G ? cqs - G : 0, ext_e = cqe + G;
+                    if (mqe < ext_s || mqs > ext_e) continue;
+                    i64 dv = (i64)tc - (i64)qc - ((i64)cts - (i64)cqs);
+                    u64 dev = dv < 0 ? (u64)(-dv) : (u64)dv;
+                    u64 perp = (u64)__ddiv_rn((double)dev, 1.4142135623730951);
+                    if (perp <= G) { status[i] = 1; chain_id[i] = u + 1; break; }
+                }
+            });
+        }
+
+        // ---- K7: rescue (paf_filter.rs:613-732) -----------------------------------------------------
+        const u64 D = cfg.scaffold_max_deviation;
+        if (D > 0) {
+            if (2 * sb + cb > 63) throw RangeError{"(query,target,center) anchor key wider than 64 bits"};
+            // anchor list (status == 1), keyed by (chromosome pair | query center)
+            u64 *ak = A.take<u64>(N), *ak2 = A.take<u64>(N);
+            u32 *av = A.take<u32>(N), *av2 = A.take<u32>(N);
+            u32 *d_na = A.take<u32>(1);
+            scan_apply([=] __device__(u32 i) -> u32 { return status[i] == 1 ? 1u : 0u; },
+                       [=] __device__(u32 i, u32 ex, u32 v) {
+                           if (!v) return;
+                           u64 qc = ((u64)in.qs[i] + in.qe[i]) / 2;
+                           ak[ex] = ((((u64)in.qid[i] << sb) | in.tid[i]) << cb) | qc;
+                           av[ex] = i;
+                       },
+                       N, bsum, d_na, st, lc);
+            const u32 NA = read_u32(c, d_na);
+            sort_pairs(c, ak, ak2, av, av2, NA, 2 * sb + cb);
+            const u64 *akc = ak;
+            const u32 *avc = av;
+            const u64 cmask = (1ull << cb) - 1;
+            launch_for<t_rescue>(N, st, lc, [=] __device__(u32 i) {
+                if (!(flags[i] & F_ALIVE) || status[i] != 0 || (flags[i] & F_PREMEM)) return;
+                u64 pair = ((u64)in.qid[i] << sb) | in.tid[i];
+                u64 qc = ((u64)in.qs[i] + in.qe[i]) / 2, tc = ((u64)in.ts[i] + in.te[i]) / 2;
+                u64 qlo = qc > D ? qc - D : 0;
+                u64 key = (pair << cb) | qlo;
+                u32 lo = 0, hi = NA;
+                while (lo < hi) { u32 mid = (lo + hi) >> 1; if (akc[mid] < key) lo = mid + 1; else hi = mid; }
+                u64 best_d = NONE64;
+                u32 best_a = NONE32;
+                for (u32 x = lo; x < NA; x++) {
+                    u64 k = akc[x];
+                    if ((k >> cb) != pair) break;
+                    u64 aqc = k & cmask;
+                    if (aqc > qc + D) break;
+                    u32 a = avc[x];
+                    u64 qd = aqc > qc ? aqc - qc : qc - aqc;
+                    u64 atc = ((u64)in.ts[a] + in.te[a]) / 2;
+                    u64 td = atc > tc ? atc - tc : tc - atc;
+                    if (td > D) continue; // then floor(sqrt(qd^2+td^2)) > D
+                    u64 dist = (u64)__dsqrt_rn((double)(qd * qd + td * td));
+                    if (dist <= D && (dist < best_d || (dist == best_d && a < best_a))) { best_d = dist; best_a = a; }
+                }
+                if (best_a != NONE32) { status[i] = 2; chain_id[i] = chain_id[best_a]; }
+            });
+        }
+    }
+
+    // ---- stats ---------------------------------------------------------------------------------
+    launch_for<t_count_kept>(N, st, lc, [=] __device__(u32 i) {
+        u8 s = status[i];
+        u32 m1 = __ballot_sync(__activemask(), s == 1), m2 = __ballot_sync(__activemask(), s == 2);
+        if ((threadIdx.x & 31) == (u32)(__ffs(__activemask()) - 1)) {
+            if (m1) atomicAdd((unsigned long long *)&ctr[C_ANCHORS], (unsigned long long)__popc(m1));
+            if (m2) atomicAdd((unsigned long long *)&ctr[C_RESCUED], (unsigned long long)__popc(m2));
+        }
+    });
+    read_counters(c);
+    S.n_anchors = c->h_ctr[C_ANCHORS];
+    S.n_rescued = c->h_ctr[C_RESCUED];
+    S.n_kept = S.n_anchors + S.n_rescued;
+    S.score_near_ties = c->h_ctr[C_NEAR_TIES];
+    finish();
+}
+
+static int guarded(swg_ctx *c, const char *what, void (*fn)(void *), void *arg) {
+    try {
+        fn(arg);
+        return SWG_OK;
+    } catch (const CudaError &e) {
+        set_err(c, std::string(what) + ": CUDA error '" + cudaGetErrorString(e.code) + "' at " + e.file + ":" + std::to_string(e.line));
+        cudaGetLastError();
+        return SWG_ERR_CUDA;
+    } catch (const RangeError &e) {
+        set_err(c, std::string(what) + ": " + e.msg);
+        return SWG_ERR_RANGE;
+    } catch (const OomError &e) {
+        set_err(c, std::string(what) + ": out of device memory (" + std::to_string(e.bytes) + " bytes)");
+        return SWG_ERR_OOM;
+    } catch (const std::bad_alloc &) {
+        set_err(c, std::string(what) + ": out of host memory");
+        return SWG_ERR_OOM;
+    }
+}
+
+static bool check_cfg(swg_ctx *c, const swg_config *cfg) {
+    if (!cfg || cfg->mapping_filter_mode > 2 || cfg->scaffold_filter_mode > 2 || cfg->scoring_function > 4) {
+        set_err(c, "bad swg_config (NULL or enum out of range)");
+        return false;
+    }
+    return true;
+}
+static bool check_maps(swg_ctx *c, const swg_mappings *m) {
+    if (!m) { set_err(c, "NULL swg_mappings"); return false; }
+    if (m->n == 0) return true;
+    if (m->n >= 0x7FFFFFF0ull) { set_err(c, "n too large (must be < 2^31 per context)"); return false; }
+    if (!m->query_id || !m->target_id || !m->query_start || !m->query_end || !m->target_start || !m->target_end ||
+        !m->block_length || !m->matches || !m->identity || !m->strand || !m->seq_genome_id || !m->seq_genome2_id || m->n_seq == 0) {
+        set_err(c, "swg_mappings has a NULL column or n_seq == 0");
+        return false;
+    }
+    return true;
+}
+static DevIn make_devin(const swg_mappings *m) {
+    DevIn d;
+    d.qid = m->query_id; d.tid = m->target_id; d.qs = m->query_start; d.qe = m->query_end; d.ts = m->target_start;
+    d.te = m->target_end; d.blen = m->block_length; d.matches = m->matches; d.identity = m->identity; d.strand = m->strand;
+    d.score = m->score; d.P = m->seq_genome_id; d.P2 = m->seq_genome2_id; d.n = (u32)m->n; d.n_seq = m->n_seq;
+    return d;
+}
+
+struct UploadArgs { swg_ctx *c; const swg_mappings *in; swg_mappings *dev; swg_result *res; Arena *arena; };
+
+static void do_upload(void *p) {
+    UploadArgs *a = (UploadArgs *)p;
+    swg_ctx *c = a->c;
+    const swg_mappings *h = a->in;
+    SWG_CUDA(cudaSetDevice(c->device));
+    size_t n = h->n;
+    size_t bytes = n * (8 * 4 + 8 + 1 + (h->score ? 8 : 0) + 1 + 4) + (size_t)h->n_seq * 8 + 64 * 256;
+    a->arena->reserve(bytes);
+    Arena &A = *a->arena;
+    swg_mappings d = *h;
+    cudaStream_t st = c->stream;
+    auto up32 = [&](const u32 *src, size_t cnt) { u32 *dst = A.take<u32>(cnt); SWG_CUDA(cudaMemcpyAsync(dst, src, cnt * 4, cudaMemcpyHostToDevice, st)); return (const u32 *)dst; };
+    d.query_id = up32(h->query_id, n); d.target_id = up32(h->target_id, n);
+    d.query_start = up32(h->query_start, n); d.query_end = up32(h->query_end, n);
+    d.target_start = up32(h->target_start, n); d.target_end = up32(h->target_end, n);
+    d.block_length = up32(h->block_length, n); d.matches = up32(h->matches, n);
+    { double *dst = A.take<double>(n); SWG_CUDA(cudaMemcpyAsync(dst, h->identity, n * 8, cudaMemcpyHostToDevice, st)); d.identity = dst; }
+    if (h->score) { double *dst = A.take<double>(n); SWG_CUDA(cudaMemcpyAsync(dst, h->score, n * 8, cudaMemcpyHostToDevice, st)); d.score = dst; }
+    { u8 *dst = A.take<u8>(n); SWG_CUDA(cudaMemcpyAsync(dst, h->strand, n, cudaMemcpyHostToDevice, st)); d.strand = dst; }
+    d.seq_genome_id = up32(h->seq_genome_id, h->n_seq);
+    d.seq_genome2_id = up32(h->seq_genome2_id, h->n_seq);
+    a->res->status = A.take<u8>(n);
+    a->res->chain_id = A.take<u32>(n);
+    *a->dev = d;
+}
+
+
+struct SweepArgs {
+    swg_ctx *c; uint64_t n; const uint32_t *qs, *qe, *ts, *te; const double *identity;
+    uint64_t nq, nt; double thr; int scoring; int axis; uint8_t *keep;
+};
+static void do_sweep(void *p) {
+    SweepArgs *a = (SweepArgs *)p;
+    swg_ctx *c = a->c;
+    SWG_CUDA(cudaSetDevice(c->device));
+    u32 n = (u32)a->n;
+    if (n == 0) return;
+    cudaStream_t st = c->stream;
+    c->arena.reserve((size_t)n * 200 + (16u << 20));
+    Arena &A = c->arena;
+    u32 *qs = A.take<u32>(n), *qe = A.take<u32>(n), *ts = A.take<u32>(n), *te = A.take<u32>(n);
+    double *id = A.take<double>(n), *score = A.take<double>(n);
+    u64 *gk = A.take<u64>(n);
+    u8 *k1 = A.take<u8>(n), *k2 = A.take<u8>(n);
+    SWG_CUDA(cudaMemcpyAsync(qs, a->qs, n * 4, cudaMemcpyHostToDevice, st));
+    SWG_CUDA(cudaMemcpyAsync(qe, a->qe, n * 4, cudaMemcpyHostToDevice, st));
+    SWG_CUDA(cudaMemcpyAsync(ts, a->ts, n * 4, cudaMemcpyHostToDevice, st));
+    SWG_CUDA(cudaMemcpyAsync(te, a->te, n * 4, cudaMemcpyHostToDevice, st));
+    SWG_CUDA(cudaMemcpyAsync(id, a->identity, n * 8, cudaMemcpyHostToDevice, st));
+    SWG_CUDA(cudaMemsetAsync(gk, 0, sizeof(u64) * n, st));
+    SWG_CUDA(cudaMemsetAsync(c->d_ctr, 0, sizeof(u64) * C_COUNT, st));
+    const int scoring = a->scoring;
+    launch_for<t_scores>(n, st, c->lc, [=] __device__(u32 i) { score[i] = score_fn(scoring, id[i], qs[i], qe[i]); });
+    u8 *res = k1;
+    if (a->axis == 0) general_sweep(c, n, nullptr, 0, gk, 1, qs, qe, score, a->nq, a->thr, k1);
+    else if (a->axis == 1) general_sweep(c, n, nullptr, 0, gk, 1, ts, te, score, a->nt, a->thr, k1);
+    else {
+        general_sweep(c, n, nullptr, 0, gk, 1, qs, qe, score, a->nq, a->thr, k1);
+        general_sweep(c, n, k1, 1, gk, 1, ts, te, score, a->nt, a->thr, k2);
+        res = k2;
+    }
+    SWG_CUDA(cudaMemcpyAsync(a->keep, res, n, cudaMemcpyDeviceToHost, st));
+    SWG_CUDA(cudaStreamSynchronize(st));
+}
+
+} // namespace swg
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+swg_ctx *swg_create(int device) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("swg_create: no usable CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback";
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "swg_create: device index out of range"; return nullptr; }
+    swg_ctx *c = new (std::nothrow) swg_ctx();
+    if (!c) return nullptr;
+    c->device = device;
+    try {
+        SWG_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        SWG_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) throw RangeError{"device is not sm_100 class (this build carries sm_100a code only)"};
+        c->sm_count = prop.multiProcessorCount;
+        SWG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        for (auto &ev : c->ev) SWG_CUDA(cudaEventCreate(&ev));
+        SWG_CUDA(cudaMallocHost(&c->h_ctr, sizeof(u64) * (C_COUNT + 8)));
+        SWG_CUDA(cudaMalloc(&c->d_ctr, sizeof(u64) * C_COUNT));
+    } catch (const CudaError &e2) {
+        g_create_error = std::string("swg_create: CUDA error '") + cudaGetErrorString(e2.code) + "'";
+        delete c;
+        return nullptr;
+    } catch (const RangeError &e3) {
+        g_create_error = "swg_create: " + e3.msg;
+        delete c;
+        return nullptr;
+    }
+    return c;
+}
+
+void swg_destroy(swg_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    c->arena.release();
+    c->io.release();
+    if (c->h_ctr) cudaFreeHost(c->h_ctr);
+    if (c->d_ctr) cudaFree(c->d_ctr);
+    for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+void swg__set_error(swg_ctx *c, const char *msg) { set_err(c, msg ? msg : ""); }
+const char *swg_last_error(const swg_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+void *swg_stream(swg_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+struct FilterDevArgs { swg_ctx *c; const swg_config *cfg; const swg_mappings *in; swg_result *out; swg_stats *stats; };
+
+int swg_filter_device(swg_ctx *c, const swg_config *cfg, const swg_mappings *dev_in, swg_result *dev_out, swg_stats *stats) {
+    if (!c) return SWG_ERR_ARG;
+    if (!check_cfg(c, cfg) || !check_maps(c, dev_in) || !dev_out || (dev_in->n && (!dev_out->status || !dev_out->chain_id))) return SWG_ERR_ARG;
+    FilterDevArgs a{c, cfg, dev_in, dev_out, stats};
+    return guarded(c, "swg_filter_device", [](void *p) {
+        FilterDevArgs *a = (FilterDevArgs *)p;
+        SWG_CUDA(cudaSetDevice(a->c->device));
+        SWG_CUDA(cudaEventRecord(a->c->ev[1], a->c->stream));
+        run_filter(a->c, *a->cfg, make_devin(a->in), a->out->status, a->out->chain_id, a->stats);
+        SWG_CUDA(cudaEventRecord(a->c->ev[2], a->c->stream));
+        SWG_CUDA(cudaStreamSynchronize(a->c->stream));
+        if (a->stats) {
+            float ms = 0;
+            SWG_CUDA(cudaEventElapsedTime(&ms, a->c->ev[1], a->c->ev[2]));
+            a->stats->ms_device = ms;
+        }
+    }, &a);
+}
+
+int swg_filter(swg_ctx *c, const swg_config *cfg, const swg_mappings *host_in, swg_result *host_out, swg_stats *stats) {
+    if (!c) return SWG_ERR_ARG;
+    if (!check_cfg(c, cfg) || !check_maps(c, host_in) || !host_out || (host_in->n && (!host_out->status || !host_out->chain_id))) return SWG_ERR_ARG;
+    struct Args { swg_ctx *c; const swg_config *cfg; const swg_mappings *in; swg_result *out; swg_stats *stats; } a{c, cfg, host_in, host_out, stats};
+    return guarded(c, "swg_filter", [](void *p) {
+        Args *a = (Args *)p;
+        swg_ctx *c = a->c;
+        SWG_CUDA(cudaSetDevice(c->device));
+        swg_mappings dev;
+        swg_result dres;
+        UploadArgs ua{c, a->in, &dev, &dres, &c->io};
+        SWG_CUDA(cudaEventRecord(c->ev[0], c->stream));
+        if (a->in->n) do_upload(&ua);
+        SWG_CUDA(cudaEventRecord(c->ev[1], c->stream));
+        swg_stats local;
+        std::memset(&local, 0, sizeof local);
+        if (a->in->n) run_filter(c, *a->cfg, make_devin(&dev), dres.status, dres.chain_id, &local);
+        SWG_CUDA(cudaEventRecord(c->ev[2], c->stream));
+        if (a->in->n) {
+            SWG_CUDA(cudaMemcpyAsync(a->out->status, dres.status, a->in->n, cudaMemcpyDeviceToHost, c->stream));
+            SWG_CUDA(cudaMemcpyAsync(a->out->chain_id, dres.chain_id, a->in->n * 4, cudaMemcpyDeviceToHost, c->stream));
+        }
+        SWG_CUDA(cudaEventRecord(c->ev[3], c->stream));
+        SWG_CUDA(cudaStreamSynchronize(c->stream));
+        float m0 = 0, m1 = 0, m2 = 0;
+        SWG_CUDA(cudaEventElapsedTime(&m0, c->ev[0], c->ev[1]));
+        SWG_CUDA(cudaEventElapsedTime(&m1, c->ev[1], c->ev[2]));
+        SWG_CUDA(cudaEventElapsedTime(&m2, c->ev[2], c->ev[3]));
+        local.ms_h2d = m0; local.ms_device = m1; local.ms_d2h = m2;
+        if (a->stats) *a->stats = local;
+    }, &a);
+}
+
+int swg_upload(swg_ctx *c, const swg_mappings *host_in, swg_mappings *dev_out, swg_result *dev_res) {
+    if (!c || !dev_out || !dev_res) return SWG_ERR_ARG;
+    if (!check_maps(c, host_in) || host_in->n == 0) return SWG_ERR_ARG;
+    Arena *ar = new (std::nothrow) Arena();
+    if (!ar) return SWG_ERR_OOM;
+    UploadArgs ua{c, host_in, dev_out, dev_res, ar};
+    int rc = guarded(c, "swg_upload", [](void *p) { do_upload(p); SWG_CUDA(cudaStreamSynchronize(((UploadArgs *)p)->c->stream)); }, &ua);
+    if (rc != SWG_OK) { ar->release(); delete ar; return rc; }
+    // the arena base is the first column: recover it in swg_release from query_id
+    delete ar; // (the device block itself stays allocated; base == dev_out->query_id)
+    return SWG_OK;
+}
+
+void swg_release(swg_ctx *c, swg_mappings *dev, swg_result *dev_res) {
+    if (!c || !dev) return;
+    cudaSetDevice(c->device);
+    if (dev->query_id) cudaFree((void *)dev->query_id);
+    std::memset(dev, 0, sizeof *dev);
+    if (dev_res) std::memset(dev_res, 0, sizeof *dev_res);
+}
+
+int swg_download_result(swg_ctx *c, uint64_t n, const swg_result *dev_res, swg_result *host_out) {
+    if (!c || !dev_res || !host_out) return SWG_ERR_ARG;
+    struct Args { swg_ctx *c; uint64_t n; const swg_result *d; swg_result *h; } a{c, n, dev_res, host_out};
+    return guarded(c, "swg_download_result", [](void *p) {
+        Args *a = (Args *)p;
+        SWG_CUDA(cudaSetDevice(a->c->device));
+        SWG_CUDA(cudaMemcpyAsync(a->h->status, a->d->status, a->n, cudaMemcpyDeviceToHost, a->c->stream));
+        SWG_CUDA(cudaMemcpyAsync(a->h->chain_id, a->d->chain_id, a->n * 4, cudaMemcpyDeviceToHost, a->c->stream));
+        SWG_CUDA(cudaStreamSynchronize(a->c->stream));
+    }, &a);
+}
+
+// ---- primitives: plane_sweep_exact.rs:268-461 -------------------------------------------------------
+static int sweep_entry(swg_ctx *c, uint64_t n, const uint32_t *qs, const uint32_t *qe, const uint32_t *ts, const uint32_t *te,
+                       const double *identity, uint64_t nq, uint64_t nt, double thr, int scoring, int axis, uint8_t *keep) {
+    if (!c) return SWG_ERR_ARG;
+    if (n && (!qs || !qe || !ts || !te || !identity || !keep)) { set_err(c, "NULL column"); return SWG_ERR_ARG; }
+    if (scoring < 0 || scoring > 4 || n >= 0x7FFFFFF0ull) { set_err(c, "bad scoring / n"); return SWG_ERR_ARG; }
+    for (uint64_t i = 0; i < n; i++)
+        if (qe[i] < qs[i] || te[i] < ts[i]) { set_err(c, "interval with end < start"); return SWG_ERR_RANGE; }
+    SweepArgs a{c, n, qs, qe, ts, te, identity, nq, nt, thr, scoring, axis, keep};
+    return guarded(c, "swg_plane_sweep", do_sweep, &a);
+}
+int swg_plane_sweep_query(swg_ctx *c, uint64_t n, const uint32_t *qs, const uint32_t *qe, const uint32_t *ts, const uint32_t *te,
+                          const double *identity, uint64_t n_keep, double thr, int scoring, uint8_t *keep) {
+    return sweep_entry(c, n, qs, qe, ts, te, identity, n_keep, 0, thr, scoring, 0, keep);
+}
+int swg_plane_sweep_target(swg_ctx *c, uint64_t n, const uint32_t *qs, const uint32_t *qe, const uint32_t *ts, const uint32_t *te,
+                           const double *identity, uint64_t n_keep, double thr, int scoring, uint8_t *keep) {
+    return sweep_entry(c, n, qs, qe, ts, te, identity, 0, n_keep, thr, scoring, 1, keep);
+}
+int swg_plane_sweep_both(swg_ctx *c, uint64_t n, const uint32_t *qs, const uint32_t *qe, const uint32_t *ts, const uint32_t *te,
+                         const double *identity, uint64_t nq, uint64_t nt, double thr, int scoring, uint8_t *keep) {
+    return sweep_entry(c, n, qs, qe, ts, te, identity, nq, nt, thr, scoring, 2, keep);
+}
+
+} // extern "C"

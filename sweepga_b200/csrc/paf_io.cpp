@@ -1,0 +1,441 @@
+// paf_io.cpp — host side of the drop-in boundary: PAF text -> compact SoA, tagged writer,
+// filter_paf / filter_file, and the multi-GPU shard planner.  Parsing stays on the host
+// (north_star); it is chunked over all host threads and emits the u32 SoA the kernels eat.
+//
+//   swg_paf_parse   <- PafFilter::extract_metadata  (src/paf_filter.rs:292-376)
+//                      + paf::parse_cigar_counts    (src/paf.rs:32-64)
+//   swg_paf_write   <- write_filtered_output        (src/paf_filter.rs:1689-1726)
+//   swg_filter_paf  <- PafFilter::filter_paf        (src/paf_filter.rs:278-289)
+//   swg_filter_file <- unified_filter::filter_file  (src/unified_filter.rs:280-347)
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include "sweepga_b200.h"
+#include "host_util.h"
+
+extern "C" void swg__set_error(swg_ctx *ctx, const char *msg); // filter_pipeline.cu
+
+using swg::rust_parse_f64;
+using swg::rust_parse_u64;
+
+struct swg_paf {
+    // the input text (mmap'd or read) — kept so that the writer does not re-read the file
+    const char *text = nullptr;
+    size_t text_len = 0;
+    bool mapped = false;
+    std::vector<char> owned;
+    uint64_t n_lines = 0;
+    // per record
+    std::vector<uint64_t> rank;      // line number
+    std::vector<uint64_t> line_off;  // offset of the line in text
+    std::vector<uint32_t> line_len;  // length without the line terminator
+    std::vector<uint32_t> qid, tid, qs, qe, ts, te, blen, matches;
+    std::vector<double> identity;
+    std::vector<uint8_t> strand;
+    // sequences
+    std::vector<std::string> names;
+    std::vector<uint32_t> P, P2;
+    ~swg_paf() {
+        if (mapped && text) munmap((void *)text, text_len);
+    }
+};
+
+namespace {
+
+struct Chunk {
+    size_t begin = 0, end = 0;
+    uint64_t n_lines = 0;
+    std::vector<uint64_t> rank_local, line_off;
+    std::vector<uint32_t> line_len, qid, tid, qs, qe, ts, te, blen, matches;
+    std::vector<double> identity;
+    std::vector<uint8_t> strand;
+    std::vector<std::string> names; // local name table (first appearance within the chunk)
+    std::string error;
+};
+
+struct SvHash {
+    size_t operator()(const std::string &s) const { return std::hash<std::string>()(s); }
+};
+
+static inline bool parse_u64_field(const char *s, size_t len, uint64_t dflt, uint64_t *out) {
+    uint64_t v;
+    if (rust_parse_u64(s, len, &v)) { *out = v; return true; }
+    *out = dflt; // unwrap_or(default), paf_filter.rs:308-317
+    return true;
+}
+
+// Σ of '=' run lengths; false when the reference's parse_cigar_counts would return Err
+static bool cigar_eq_count(const char *s, size_t len, uint64_t *out) {
+    uint64_t m = 0, num = 0;
+    bool have = false, overflow = false;
+    for (size_t i = 0; i < len; i++) {
+        unsigned d = (unsigned)(s[i] - '0');
+        if (d <= 9) {
+            if (num > (~(uint64_t)0 - d) / 10) overflow = true;
+            num = num * 10 + d;
+            have = true;
+        } else {
+            if (!have || overflow) return false; // "".parse::<u64>() / overflow is Err
+            if (s[i] == '=') m += num;
+            num = 0;
+            have = false;
+        }
+    }
+    *out = m;
+    return true;
+}
+
+static void parse_chunk(const char *text, Chunk &c) {
+    std::unordered_map<std::string, uint32_t, SvHash> ids;
+    std::string last_q, last_t;
+    uint32_t last_qid = 0, last_tid = 0;
+    bool have_q = false, have_t = false;
+    auto intern = [&](const char *s, size_t len, std::string &last, uint32_t &last_id, bool &have) -> uint32_t {
+        if (have && last.size() == len && memcmp(last.data(), s, len) == 0) return last_id;
+        last.assign(s, len);
+        auto it = ids.find(last);
+        uint32_t id;
+        if (it == ids.end()) {
+            id = (uint32_t)c.names.size();
+            ids.emplace(last, id);
+            c.names.push_back(last);
+        } else id = it->second;
+        last_id = id;
+        have = true;
+        return id;
+    };
+    size_t pos = c.begin;
+    uint64_t ln = 0;
+    const char *fs[11];
+    size_t fl[11];
+    while (pos < c.end) {
+        const char *nl = (const char *)memchr(text + pos, '\n', c.end - pos);
+        size_t eol = nl ? (size_t)(nl - text) : c.end;
+        size_t len = eol - pos;
+        if (len > 0 && text[eol - 1] == '\r') len--; // BufRead::lines strips "\r\n"
+        const char *line = text + pos;
+        uint64_t this_ln = ln++;
+        size_t next = nl ? eol + 1 : c.end;
+        // split the first 11 fields
+        int nf = 0;
+        size_t a = 0;
+        while (nf < 11) {
+            const char *tab = (const char *)memchr(line + a, '\t', len - a);
+            size_t b = tab ? (size_t)(tab - line) : len;
+            fs[nf] = line + a;
+            fl[nf] = b - a;
+            nf++;
+            if (!tab) { a = len + 1; break; }
+            a = b + 1;
+        }
+        if (nf < 11) { pos = next; continue; } // fewer than 11 fields: skipped, still consumes a rank
+        uint64_t qs, qe, ts, te, mt, bl;
+        parse_u64_field(fs[2], fl[2], 0, &qs);
+        parse_u64_field(fs[3], fl[3], 0, &qe);
+        parse_u64_field(fs[7], fl[7], 0, &ts);
+        parse_u64_field(fs[8], fl[8], 0, &te);
+        parse_u64_field(fs[9], fl[9], 0, &mt);
+        parse_u64_field(fs[10], fl[10], 1, &bl);
+        double identity = (double)mt / (double)(bl > 1 ? bl : 1);
+        uint64_t exact = mt;
+        // tags from column 12 on, in order, the later one wins (paf_filter.rs:326-343)
+        while (a <= len) {
+            const char *tab = a < len ? (const char *)memchr(line + a, '\t', len - a) : nullptr;
+            size_t b = tab ? (size_t)(tab - line) : len;
+            const char *f = line + a;
+            size_t flen = b - a;
+            if (flen >= 5 && memcmp(f, "dv:f:", 5) == 0) {
+                double dv;
+                if (rust_parse_f64(f + 5, flen - 5, &dv)) identity = 1.0 - dv;
+            } else if (flen >= 5 && memcmp(f, "cg:Z:", 5) == 0) {
+                uint64_t cm;
+                if (cigar_eq_count(f + 5, flen - 5, &cm) && cm > 0) {
+                    exact = cm;
+                    identity = (double)cm / (double)(bl > 1 ? bl : 1);
+                }
+            }
+            if (!tab) break;
+            a = b + 1;
+        }
+        const uint64_t LIM = 0xFFFFFFFFull;
+        if (qs > LIM || qe > LIM || ts > LIM || te > LIM || bl > LIM || exact > LIM) {
+            if (c.error.empty()) c.error = "coordinate / length does not fit the u32 SoA at chunk line " + std::to_string(this_ln);
+            pos = next;
+            continue;
+        }
+        if (qe < qs || te < ts) {
+            if (c.error.empty()) c.error = "record with end < start at chunk line " + std::to_string(this_ln);
+            pos = next;
+            continue;
+        }
+        uint32_t q = intern(fs[0], fl[0], last_q, last_qid, have_q);
+        uint32_t t = intern(fs[5], fl[5], last_t, last_tid, have_t);
+        c.rank_local.push_back(this_ln);
+        c.line_off.push_back(pos);
+        c.line_len.push_back((uint32_t)len);
+        c.qid.push_back(q); c.tid.push_back(t);
+        c.qs.push_back((uint32_t)qs); c.qe.push_back((uint32_t)qe); c.ts.push_back((uint32_t)ts); c.te.push_back((uint32_t)te);
+        c.blen.push_back((uint32_t)bl); c.matches.push_back((uint32_t)exact);
+        c.identity.push_back(identity);
+        c.strand.push_back((fl[4] == 1 && fs[4][0] == '+') ? '+' : '-');
+        pos = next;
+    }
+    c.n_lines = ln;
+}
+
+static std::string prefix_P(const std::string &n) { // src/paf_filter.rs:1022-1030
+    size_t p = n.rfind('#');
+    return p == std::string::npos ? n : n.substr(0, p + 1);
+}
+static std::string prefix_P2(const std::string &n) { // src/plane_sweep_scaffold.rs:13-22
+    size_t p = n.find('#');
+    if (p == std::string::npos) return n;
+    size_t p2 = n.find('#', p + 1);
+    std::string f1 = p2 == std::string::npos ? n.substr(p + 1) : n.substr(p + 1, p2 - p - 1);
+    return n.substr(0, p) + "#" + f1 + "#";
+}
+
+template <class T> static void append(std::vector<T> &dst, const std::vector<T> &src) { dst.insert(dst.end(), src.begin(), src.end()); }
+
+} // namespace
+
+extern "C" {
+
+swg_paf *swg_paf_parse(const char *path, char *err, size_t err_len) {
+    auto fail = [&](const std::string &m) -> swg_paf * {
+        if (err && err_len) snprintf(err, err_len, "%s", m.c_str());
+        return nullptr;
+    };
+    if (!path) return fail("NULL path");
+    size_t plen = strlen(path);
+    if (plen > 3 && strcmp(path + plen - 3, ".gz") == 0)
+        return fail("bgzf/gzip-compressed PAF is not supported by this build (no zlib on the host path); decompress first");
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(std::string("cannot open ") + path);
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) { close(fd); return fail("fstat failed"); }
+    swg_paf *p = new swg_paf();
+    p->text_len = (size_t)sb.st_size;
+    if (p->text_len > 0) {
+        void *m = mmap(nullptr, p->text_len, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m != MAP_FAILED) {
+            p->text = (const char *)m;
+            p->mapped = true;
+            madvise(m, p->text_len, MADV_SEQUENTIAL);
+        } else { // pipes / special files: read
+            p->owned.resize(p->text_len);
+            size_t got = 0;
+            while (got < p->text_len) {
+                ssize_t r = read(fd, p->owned.data() + got, p->text_len - got);
+                if (r <= 0) break;
+                got += (size_t)r;
+            }
+            p->text_len = got;
+            p->text = p->owned.data();
+        }
+    }
+    close(fd);
+    // chunk at line boundaries, one chunk per host thread
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt == 0) nt = 1;
+    size_t min_chunk = (size_t)1 << 20;
+    size_t nchunks = std::max<size_t>(1, std::min<size_t>(nt, p->text_len / min_chunk));
+    std::vector<Chunk> chunks(nchunks);
+    size_t start = 0;
+    for (size_t k = 0; k < nchunks; k++) {
+        size_t target = (k + 1 == nchunks) ? p->text_len : p->text_len / nchunks * (k + 1);
+        size_t end = target;
+        if (k + 1 < nchunks) {
+            const char *nl = (const char *)memchr(p->text + target, '\n', p->text_len - target);
+            end = nl ? (size_t)(nl - p->text) + 1 : p->text_len;
+        }
+        if (end < start) end = start;
+        chunks[k].begin = start;
+        chunks[k].end = end;
+        start = end;
+    }
+    {
+        std::vector<std::thread> th;
+        for (size_t k = 1; k < nchunks; k++) th.emplace_back(parse_chunk, p->text, std::ref(chunks[k]));
+        parse_chunk(p->text, chunks[0]);
+        for (auto &t : th) t.join();
+    }
+    for (auto &c : chunks)
+        if (!c.error.empty()) { std::string m = c.error; delete p; return fail(m); }
+    // merge: global name ids in first-appearance order (chunk order, then within-chunk order)
+    std::unordered_map<std::string, uint32_t> gid, pid, p2id;
+    size_t total = 0;
+    for (auto &c : chunks) total += c.rank_local.size();
+    p->rank.reserve(total); p->line_off.reserve(total); p->line_len.reserve(total);
+    p->qid.reserve(total); p->tid.reserve(total); p->qs.reserve(total); p->qe.reserve(total);
+    p->ts.reserve(total); p->te.reserve(total); p->blen.reserve(total); p->matches.reserve(total);
+    p->identity.reserve(total); p->strand.reserve(total);
+    uint64_t line_base = 0;
+    for (auto &c : chunks) {
+        std::vector<uint32_t> remap(c.names.size());
+        // first appearance inside the chunk is by record order with query before target — the local table
+        // was filled in exactly that order
+        for (size_t i = 0; i < c.names.size(); i++) {
+            auto it = gid.find(c.names[i]);
+            if (it == gid.end()) {
+                uint32_t id = (uint32_t)p->names.size();
+                gid.emplace(c.names[i], id);
+                p->names.push_back(c.names[i]);
+                std::string a = prefix_P(c.names[i]), b = prefix_P2(c.names[i]);
+                auto ia = pid.find(a);
+                if (ia == pid.end()) ia = pid.emplace(a, (uint32_t)pid.size()).first;
+                auto ib = p2id.find(b);
+                if (ib == p2id.end()) ib = p2id.emplace(b, (uint32_t)p2id.size()).first;
+                p->P.push_back(ia->second);
+                p->P2.push_back(ib->second);
+                remap[i] = id;
+            } else remap[i] = it->second;
+        }
+        for (size_t i = 0; i < c.rank_local.size(); i++) {
+            p->rank.push_back(line_base + c.rank_local[i]);
+            p->qid.push_back(remap[c.qid[i]]);
+            p->tid.push_back(remap[c.tid[i]]);
+        }
+        append(p->line_off, c.line_off); append(p->line_len, c.line_len);
+        append(p->qs, c.qs); append(p->qe, c.qe); append(p->ts, c.ts); append(p->te, c.te);
+        append(p->blen, c.blen); append(p->matches, c.matches); append(p->identity, c.identity); append(p->strand, c.strand);
+        line_base += c.n_lines;
+        Chunk().names.swap(c.names);
+    }
+    p->n_lines = line_base;
+    return p;
+}
+
+void swg_paf_free(swg_paf *p) { delete p; }
+uint64_t swg_paf_n_records(const swg_paf *p) { return p ? p->rank.size() : 0; }
+uint64_t swg_paf_n_lines(const swg_paf *p) { return p ? p->n_lines : 0; }
+uint32_t swg_paf_n_seq(const swg_paf *p) { return p ? (uint32_t)p->names.size() : 0; }
+const uint64_t *swg_paf_rank(const swg_paf *p) { return p ? p->rank.data() : nullptr; }
+const char *swg_paf_seq_name(const swg_paf *p, uint32_t id) { return (p && id < p->names.size()) ? p->names[id].c_str() : nullptr; }
+
+int swg_paf_view(const swg_paf *p, swg_mappings *out) {
+    if (!p || !out) return SWG_ERR_ARG;
+    memset(out, 0, sizeof *out);
+    out->n = p->rank.size();
+    out->query_id = p->qid.data(); out->target_id = p->tid.data();
+    out->query_start = p->qs.data(); out->query_end = p->qe.data();
+    out->target_start = p->ts.data(); out->target_end = p->te.data();
+    out->block_length = p->blen.data(); out->matches = p->matches.data();
+    out->identity = p->identity.data(); out->strand = p->strand.data();
+    out->score = nullptr;
+    out->n_seq = (uint32_t)p->names.size();
+    out->seq_genome_id = p->P.data(); out->seq_genome2_id = p->P2.data();
+    return SWG_OK;
+}
+
+int swg_paf_write(const swg_paf *p, const char *out_path, const uint8_t *status, const uint32_t *chain_id) {
+    if (!p || !out_path || (p->rank.size() && (!status || !chain_id))) return SWG_ERR_ARG;
+    FILE *f = fopen(out_path, "wb");
+    if (!f) return SWG_ERR_IO;
+    std::vector<char> buf;
+    buf.reserve((size_t)8 << 20);
+    static const char *st_name[4] = {"", "scaffold", "rescued", "unassigned"};
+    char tag[64];
+    bool ok = true;
+    for (size_t r = 0; r < p->rank.size(); r++) { // records are in input order
+        uint8_t s = status[r];
+        if (s == SWG_DROPPED || s > 3) continue;
+        const char *line = p->text + p->line_off[r];
+        buf.insert(buf.end(), line, line + p->line_len[r]);
+        if (chain_id[r]) {
+            int k = snprintf(tag, sizeof tag, "\tch:Z:chain_%u", chain_id[r]);
+            buf.insert(buf.end(), tag, tag + k);
+        }
+        int k = snprintf(tag, sizeof tag, "\tst:Z:%s\n", st_name[s]);
+        buf.insert(buf.end(), tag, tag + k);
+        if (buf.size() >= ((size_t)8 << 20) - 4096) {
+            ok = ok && fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+            buf.clear();
+        }
+    }
+    if (!buf.empty()) ok = ok && fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+    ok = (fclose(f) == 0) && ok;
+    return ok ? SWG_OK : SWG_ERR_IO;
+}
+
+int swg_filter_paf(swg_ctx *ctx, const swg_config *cfg, const char *in_path, const char *out_path, swg_stats *stats) {
+    if (!ctx || !cfg || !in_path || !out_path) return SWG_ERR_ARG;
+    char err[256];
+    err[0] = 0;
+    swg_paf *p = swg_paf_parse(in_path, err, sizeof err);
+    if (!p) {
+        swg__set_error(ctx, err);
+        return access(in_path, R_OK) == 0 && !strstr(err, "not supported") ? SWG_ERR_RANGE : SWG_ERR_IO;
+    }
+    swg_mappings m;
+    swg_paf_view(p, &m);
+    std::vector<uint8_t> status(m.n);
+    std::vector<uint32_t> chain(m.n);
+    swg_result res{status.data(), chain.data()};
+    int rc = SWG_OK;
+    if (m.n) rc = swg_filter(ctx, cfg, &m, &res, stats);
+    else if (stats) memset(stats, 0, sizeof *stats);
+    if (rc == SWG_OK) rc = swg_paf_write(p, out_path, status.data(), chain.data());
+    swg_paf_free(p);
+    return rc;
+}
+
+int swg_filter_file(swg_ctx *ctx, const swg_config *cfg, const char *in_path, const char *out_path, int keep_self,
+                    swg_stats *stats) {
+    if (!ctx || !cfg || !in_path || !out_path) return SWG_ERR_ARG;
+    // sniff: .1aln files start with "1 " (src/unified_filter.rs:291-306)
+    FILE *f = fopen(in_path, "rb");
+    if (!f) return SWG_ERR_IO;
+    char magic[2] = {0, 0};
+    size_t got = fread(magic, 1, 2, f);
+    fclose(f);
+    if (got == 2 && magic[0] == '1' && magic[1] == ' ') return SWG_ERR_UNSUPPORTED;
+    swg_config c2 = *cfg;
+    c2.keep_self = keep_self ? 1 : 0; // .with_keep_self(keep_self), src/unified_filter.rs:340-343
+    return swg_filter_paf(ctx, &c2, in_path, out_path, stats);
+}
+
+// Size-balanced assignment of genome-pair units to shards (LPT greedy).
+int swg_shard_plan(const swg_mappings *m, int n_shards, uint32_t *shard_of, uint64_t *shard_sizes) {
+    if (!m || n_shards < 1 || (m->n && !shard_of)) return SWG_ERR_ARG;
+    std::unordered_map<uint64_t, uint32_t> unit_id;
+    std::vector<uint64_t> unit_size;
+    std::vector<uint32_t> unit_of(m->n);
+    for (uint64_t i = 0; i < m->n; i++) {
+        uint32_t q = m->query_id[i], t = m->target_id[i];
+        if (q >= m->n_seq || t >= m->n_seq) return SWG_ERR_RANGE;
+        uint64_t key = ((uint64_t)m->seq_genome_id[q] << 32) | m->seq_genome_id[t];
+        auto it = unit_id.find(key);
+        uint32_t u;
+        if (it == unit_id.end()) { u = (uint32_t)unit_size.size(); unit_id.emplace(key, u); unit_size.push_back(0); }
+        else u = it->second;
+        unit_size[u]++;
+        unit_of[i] = u;
+    }
+    std::vector<uint32_t> order(unit_size.size());
+    for (uint32_t u = 0; u < order.size(); u++) order[u] = u;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return unit_size[a] > unit_size[b]; });
+    std::vector<uint64_t> load(n_shards, 0);
+    std::vector<uint32_t> unit_shard(unit_size.size());
+    for (uint32_t u : order) {
+        int best = 0;
+        for (int s = 1; s < n_shards; s++) if (load[s] < load[best]) best = s;
+        unit_shard[u] = (uint32_t)best;
+        load[best] += unit_size[u];
+    }
+    for (uint64_t i = 0; i < m->n; i++) shard_of[i] = unit_shard[unit_of[i]];
+    if (shard_sizes) for (int s = 0; s < n_shards; s++) shard_sizes[s] = load[s];
+    return SWG_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,256 @@
+// radix_sort.cuh — stable LSD radix sort of (u64 key, u32 payload) pairs for sm_100a.
+//
+// Replaces the reference's per-(query,target) HashMap/IndexMap grouping + sort_by_key
+// (src/grouped_mappings.rs:33-39, src/paf_filter.rs:761-777, 1037-1100, 625-634):
+// the group id sits in the high key bits, the position in the low bits, so ONE
+// sort produces every group contiguous and position-ordered ("segmented" by
+// construction), and stability keeps input order for ties exactly like
+// Vec::sort_by_key.
+//
+// Structure (one-sweep): one histogram kernel counts every 8-bit digit of every
+// pass in a single read of the keys; each pass is then ONE kernel that ranks a
+// 6144-pair tile with warp match_any digit histograms, resolves the tile's
+// global digit offsets by decoupled look-back over earlier tiles, stages the
+// tile in shared memory in digit order and writes it out coalesced.
+// HBM traffic per pass: 12 B read + 12 B write per pair (+ 8 B once for the
+// histogram).  Bound: HBM.
+#pragma once
+#include "common.cuh"
+
+namespace swg {
+
+constexpr int RS_BITS = 8;
+constexpr int RS_RADIX = 1 << RS_BITS;
+constexpr int RS_THREADS = 512;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 12;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS; // 6144 pairs
+constexpr int RS_MAX_PASSES = 8;
+
+constexpr u32 RS_FLAG_AGG = 1u << 30;  // tile aggregate available
+constexpr u32 RS_FLAG_INCL = 2u << 30; // inclusive prefix available
+constexpr u32 RS_VAL_MASK = (1u << 30) - 1;
+
+// ---- histogram of all passes in one read --------------------------------------------------
+__global__ void __launch_bounds__(512) rs_histogram_kernel(const u64 *__restrict__ keys, u32 n, int begin_bit, int passes,
+                                                           u32 *__restrict__ hist /*[passes][256]*/) {
+    __shared__ u32 sh[RS_MAX_PASSES * RS_RADIX];
+    for (int i = threadIdx.x; i < passes * RS_RADIX; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    // 128-bit loads: two keys per thread per step
+    const ulonglong2 *k2 = reinterpret_cast<const ulonglong2 *>(keys);
+    u32 n2 = n >> 1;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
+        ulonglong2 v = k2[i];
+        u64 a = v.x >> begin_bit, b = v.y >> begin_bit;
+#pragma unroll
+        for (int p = 0; p < RS_MAX_PASSES; p++) {
+            if (p < passes) {
+                u32 da = (u32)(a >> (p * RS_BITS)) & (RS_RADIX - 1);
+                u32 db = (u32)(b >> (p * RS_BITS)) & (RS_RADIX - 1);
+                if (da == db) atomicAdd(&sh[p * RS_RADIX + da], 2u);
+                else { atomicAdd(&sh[p * RS_RADIX + da], 1u); atomicAdd(&sh[p * RS_RADIX + db], 1u); }
+            }
+        }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        u64 a = keys[n - 1] >> begin_bit;
+        for (int p = 0; p < passes; p++) atomicAdd(&sh[p * RS_RADIX + ((u32)(a >> (p * RS_BITS)) & (RS_RADIX - 1))], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * RS_RADIX; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+// exclusive scan of each pass's 256 bins, in place (one block per pass, 256 threads)
+__global__ void rs_scan_hist_kernel(u32 *__restrict__ hist) {
+    __shared__ u32 ws[8];
+    u32 *h = hist + blockIdx.x * RS_RADIX;
+    u32 v = h[threadIdx.x];
+    u32 x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if ((threadIdx.x & 31) >= o) x += t;
+    }
+    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+    __syncthreads();
+    u32 base = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); w++) base += ws[w];
+    h[threadIdx.x] = base + x - v;
+}
+
+// ---- one pass ---------------------------------------------------------------------------
+struct RsSmem {
+    u32 warp_hist[RS_WARPS][RS_RADIX]; // 16 KB: per-warp digit counts, later exclusive-over-warps offsets
+    u64 stage_k[RS_TILE];              // 48 KB
+    u32 stage_v[RS_TILE];              // 24 KB
+    u32 digit_excl[RS_RADIX];          // tile-local exclusive digit offsets
+    u32 global_base[RS_RADIX];         // global output index of staged position 0 of each digit run
+    u32 wsum[RS_WARPS];
+    u32 tile;
+};
+
+__global__ void __launch_bounds__(RS_THREADS, 2)
+rs_onesweep_kernel(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out, const u32 *__restrict__ vals_in,
+                   u32 *__restrict__ vals_out, u32 n, int shift, const u32 *__restrict__ digit_base,
+                   u32 *tile_status /*[tiles][256]*/, u32 *tile_counter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RsSmem &s = *reinterpret_cast<RsSmem *>(smem_raw);
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) s.tile = atomicAdd(tile_counter, 1u); // in-order tile ids: look-back never waits on an unscheduled tile
+    for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&s.warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const u32 tile = s.tile;
+    const u64 tile_base = (u64)tile * RS_TILE;
+    const u64 warp_base = tile_base + (u64)warp * (32 * RS_ITEMS);
+
+    u64 key[RS_ITEMS];
+    u32 val[RS_ITEMS];
+    u32 rnk[RS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+        u64 idx = warp_base + i * 32 + lane;
+        bool ok = idx < n;
+        key[i] = ok ? keys_in[idx] : NONE64;
+        val[i] = ok ? vals_in[idx] : 0u;
+    }
+    // warp-level multi-split ranking (stable: items ascending, lanes ascending)
+    const u32 lt = lanemask_lt();
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+        bool ok = (warp_base + i * 32 + lane) < n;
+        u32 d = (u32)(key[i] >> shift) & (RS_RADIX - 1);
+        u32 peers = __match_any_sync(0xFFFFFFFFu, ok ? d : (0x100u | lane));
+        u32 leader = __ffs(peers) - 1;
+        u32 prev = 0;
+        if (lane == leader && ok) {
+            prev = s.warp_hist[warp][d];
+            s.warp_hist[warp][d] = prev + __popc(peers);
+        }
+        prev = __shfl_sync(0xFFFFFFFFu, prev, leader);
+        rnk[i] = prev + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // per digit: exclusive scan over warps, tile count; then exclusive scan over digits
+    u32 count = 0;
+    if (tid < RS_RADIX) {
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) {
+            u32 t = s.warp_hist[w][tid];
+            s.warp_hist[w][tid] = count;
+            count += t;
+        }
+    }
+    {
+        u32 x = count;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 t = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += t;
+        }
+        if (lane == 31) s.wsum[warp] = x;
+        __syncthreads();
+        if (tid < RS_RADIX) {
+            u32 base = 0;
+            for (u32 w = 0; w < warp; w++) base += s.wsum[w];
+            s.digit_excl[tid] = base + x - count;
+        }
+    }
+    // decoupled look-back, one thread per digit
+    if (tid < RS_RADIX) {
+        u32 *my = tile_status + (u64)tile * RS_RADIX + tid;
+        u32 excl = 0;
+        if (tile == 0) {
+            st_volatile_u32(my, RS_FLAG_INCL | count);
+        } else {
+            st_volatile_u32(my, RS_FLAG_AGG | count);
+            i64 t = (i64)tile - 1;
+            while (true) {
+                u32 v = ld_volatile_u32(tile_status + (u64)t * RS_RADIX + tid);
+                if (v & RS_FLAG_INCL) { excl += v & RS_VAL_MASK; break; }
+                if (v & RS_FLAG_AGG) { excl += v & RS_VAL_MASK; t--; }
+            }
+            st_volatile_u32(my, RS_FLAG_INCL | (excl + count));
+        }
+        s.global_base[tid] = digit_base[tid] + excl - s.digit_excl[tid];
+    }
+    __syncthreads();
+
+    // stage in digit order
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+        bool ok = (warp_base + i * 32 + lane) < n;
+        if (ok) {
+            u32 d = (u32)(key[i] >> shift) & (RS_RADIX - 1);
+            u32 pos = s.digit_excl[d] + s.warp_hist[warp][d] + rnk[i];
+            s.stage_k[pos] = key[i];
+            s.stage_v[pos] = val[i];
+        }
+    }
+    __syncthreads();
+    const u32 tile_n = (u32)min((u64)RS_TILE, (u64)n - tile_base);
+#pragma unroll 4
+    for (u32 j = tid; j < tile_n; j += RS_THREADS) {
+        u64 k = s.stage_k[j];
+        u32 d = (u32)(k >> shift) & (RS_RADIX - 1);
+        u32 g = s.global_base[d] + j;
+        keys_out[g] = k;
+        vals_out[g] = s.stage_v[j];
+    }
+}
+
+// ---- host driver --------------------------------------------------------------------------
+struct RadixSortPlan {
+    u32 n = 0;
+    int begin_bit = 0, passes = 0;
+    u32 tiles = 0;
+    size_t temp_bytes = 0; // hist + counters + tile status (zeroed by the driver)
+};
+
+static inline RadixSortPlan rs_plan(u32 n, int begin_bit, int end_bit) {
+    RadixSortPlan p;
+    p.n = n;
+    p.begin_bit = begin_bit;
+    int bits = end_bit - begin_bit;
+    if (bits < 1) bits = 1;
+    p.passes = (bits + RS_BITS - 1) / RS_BITS;
+    if (p.passes > RS_MAX_PASSES) p.passes = RS_MAX_PASSES;
+    p.tiles = cdiv(n, RS_TILE);
+    p.temp_bytes = sizeof(u32) * ((size_t)RS_MAX_PASSES * RS_RADIX + 16 + (size_t)p.passes * p.tiles * RS_RADIX);
+    return p;
+}
+
+// Sorts by key bits [begin_bit, begin_bit + 8*passes).  On return (keys, vals) point at the
+// sorted data and (keys_alt, vals_alt) at the scratch (the pointers are swapped as needed).
+static inline void rs_sort_pairs(const RadixSortPlan &p, u64 *&keys, u64 *&keys_alt, u32 *&vals, u32 *&vals_alt, void *temp,
+                                 cudaStream_t st, int sm_count, LaunchCounter &lc) {
+    if (p.n == 0) return;
+    u32 *hist = (u32 *)temp;
+    u32 *counters = hist + RS_MAX_PASSES * RS_RADIX;
+    u32 *status = counters + 16;
+    SWG_CUDA(cudaMemsetAsync(temp, 0, p.temp_bytes, st));
+    static bool attr_set = false;
+    if (!attr_set) {
+        SWG_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+        attr_set = true;
+    }
+    u32 hgrid = (u32)min((u64)sm_count * 4, (u64)cdiv(p.n / 2 + 1, 512));
+    rs_histogram_kernel<<<hgrid, 512, 0, st>>>(keys, p.n, p.begin_bit, p.passes, hist);
+    rs_scan_hist_kernel<<<p.passes, RS_RADIX, 0, st>>>(hist);
+    lc.n += 2;
+    for (int pass = 0; pass < p.passes; pass++) {
+        rs_onesweep_kernel<<<p.tiles, RS_THREADS, sizeof(RsSmem), st>>>(keys, keys_alt, vals, vals_alt, p.n,
+                                                                        p.begin_bit + pass * RS_BITS, hist + pass * RS_RADIX,
+                                                                        status + (size_t)pass * p.tiles * RS_RADIX, counters + pass);
+        lc.n += 1;
+        u64 *tk = keys; keys = keys_alt; keys_alt = tk;
+        u32 *tv = vals; vals = vals_alt; vals_alt = tv;
+    }
+    SWG_CUDA(cudaGetLastError());
+}
+
+} // namespace swg

@@ -1,0 +1,127 @@
+"""ctypes binding of oracle/liboracle.so — the CPU restatement of the reference filter.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_PATH = os.path.join(ROOT, "oracle", "liboracle.so")
+_lib = C.CDLL(_PATH)
+
+from sweepga_b200._lib import swg_config, swg_stats  # POD layouts only
+
+u8p, u32p, u64p, f64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_double)
+_lib.orc_apply_filters.restype = C.c_int
+_lib.orc_apply_filters.argtypes = [C.POINTER(swg_config), C.c_uint64, u32p, u32p, u64p, u64p, u64p, u64p, u64p, u64p, f64p, u8p,
+                                   u32p, u32p, u8p, u32p, C.POINTER(swg_stats)]
+_lib.orc_plane_sweep.restype = C.c_int
+_lib.orc_plane_sweep.argtypes = [C.c_int, C.c_uint64, u64p, u64p, u64p, u64p, f64p, C.c_uint64, C.c_uint64, C.c_double, C.c_int, u8p]
+_lib.orc_score.restype = C.c_double
+_lib.orc_score.argtypes = [C.c_uint64, C.c_uint64, C.c_double, C.c_int]
+_lib.orc_plane_sweep_core.restype = C.c_int
+_lib.orc_plane_sweep_core.argtypes = [C.c_uint64, u32p, u32p, f64p, C.c_uint64, C.c_double, u64p]
+_lib.orc_paf_parse.restype = C.c_void_p
+_lib.orc_paf_parse.argtypes = [C.c_char_p]
+_lib.orc_paf_free.argtypes = [C.c_void_p]
+for f, r in (("orc_paf_n", C.c_uint64), ("orc_paf_n_lines", C.c_uint64), ("orc_paf_n_seq", C.c_uint32)):
+    getattr(_lib, f).restype = r
+    getattr(_lib, f).argtypes = [C.c_void_p]
+_lib.orc_paf_seq_name.restype = C.c_char_p
+_lib.orc_paf_seq_name.argtypes = [C.c_void_p, C.c_uint32]
+_lib.orc_paf_u64.restype = u64p
+_lib.orc_paf_u64.argtypes = [C.c_void_p, C.c_int]
+_lib.orc_paf_u32.restype = u32p
+_lib.orc_paf_u32.argtypes = [C.c_void_p, C.c_int]
+_lib.orc_paf_identity.restype = f64p
+_lib.orc_paf_identity.argtypes = [C.c_void_p]
+_lib.orc_paf_strand.restype = u8p
+_lib.orc_paf_strand.argtypes = [C.c_void_p]
+_lib.orc_paf_write.restype = C.c_int
+_lib.orc_paf_write.argtypes = [C.c_void_p, C.c_char_p, u8p, u32p]
+_lib.orc_filter_paf.restype = C.c_int
+_lib.orc_filter_paf.argtypes = [C.POINTER(swg_config), C.c_char_p, C.c_char_p, C.POINTER(swg_stats)]
+
+USIZE_MAX = (1 << 64) - 1
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def apply_filters(cfg, table):
+    """Oracle apply_filters on a sweepga_b200.MappingTable -> (status u8[n], chain_id u32[n], stats)."""
+    n = table.n
+    c = cfg.to_c()
+    a64 = lambda x: np.ascontiguousarray(x, dtype=np.uint64)
+    qs, qe, ts, te = a64(table.query_start), a64(table.query_end), a64(table.target_start), a64(table.target_end)
+    bl, mt = a64(table.block_length), a64(table.matches)
+    status, chain = np.zeros(n, np.uint8), np.zeros(n, np.uint32)
+    st = swg_stats()
+    _lib.orc_apply_filters(C.byref(c), n, _p(table.query_id, C.c_uint32), _p(table.target_id, C.c_uint32), _p(qs, C.c_uint64),
+                           _p(qe, C.c_uint64), _p(ts, C.c_uint64), _p(te, C.c_uint64), _p(bl, C.c_uint64), _p(mt, C.c_uint64),
+                           _p(table.identity, C.c_double), _p(table.strand, C.c_uint8), _p(table.seq_genome_id, C.c_uint32),
+                           _p(table.seq_genome2_id, C.c_uint32), _p(status, C.c_uint8), _p(chain, C.c_uint32), C.byref(st))
+    return status, chain, st
+
+
+def plane_sweep(axis, mappings, n_keep, thr, scoring=3, n_keep2=None):
+    """axis 'query' | 'target' | 'both'; mappings = [(qs, qe, ts, te, identity), ...] -> kept local indices."""
+    ax = {"query": 0, "target": 1, "both": 2}[axis]
+    cols = [np.ascontiguousarray([m[k] for m in mappings], dtype=np.uint64) for k in range(4)]
+    idy = np.ascontiguousarray([m[4] for m in mappings], dtype=np.float64)
+    keep = np.zeros(len(mappings), np.uint8)
+    nk = USIZE_MAX if n_keep is None else n_keep
+    nk2 = USIZE_MAX if n_keep2 is None else n_keep2
+    _lib.orc_plane_sweep(ax, len(mappings), *[_p(c, C.c_uint64) for c in cols], _p(idy, C.c_double), nk, nk2, thr, scoring, _p(keep, C.c_uint8))
+    return [int(i) for i in np.nonzero(keep)[0]]
+
+
+def score(qs, qe, identity, scoring=3):
+    return _lib.orc_score(qs, qe, identity, scoring)
+
+
+def plane_sweep_core(intervals, max_keep, thr):
+    """intervals = [(begin, end, score), ...] -> kept indices in the reference's output order"""
+    b = np.ascontiguousarray([i[0] for i in intervals], dtype=np.uint32)
+    e = np.ascontiguousarray([i[1] for i in intervals], dtype=np.uint32)
+    s = np.ascontiguousarray([i[2] for i in intervals], dtype=np.float64)
+    out = np.zeros(max(len(intervals), 1), np.uint64)
+    k = _lib.orc_plane_sweep_core(len(intervals), _p(b, C.c_uint32), _p(e, C.c_uint32), _p(s, C.c_double),
+                                  USIZE_MAX if max_keep is None else max_keep, thr, _p(out, C.c_uint64))
+    return [int(x) for x in out[:k]]
+
+
+def parse_paf(path):
+    """Oracle extract_metadata -> sweepga_b200.MappingTable with u64 coordinates kept in .coords64"""
+    from sweepga_b200 import MappingTable
+    h = _lib.orc_paf_parse(os.fsencode(path))
+    if not h:
+        raise IOError(path)
+    try:
+        n, ns = _lib.orc_paf_n(h), _lib.orc_paf_n_seq(h)
+        g64 = lambda w: np.ctypeslib.as_array(_lib.orc_paf_u64(h, w), shape=(n,)).copy() if n else np.zeros(0, np.uint64)
+        g32 = lambda w, cnt: np.ctypeslib.as_array(_lib.orc_paf_u32(h, w), shape=(cnt,)).copy() if cnt else np.zeros(0, np.uint32)
+        ident = np.ctypeslib.as_array(_lib.orc_paf_identity(h), shape=(n,)).copy() if n else np.zeros(0)
+        strand = np.ctypeslib.as_array(_lib.orc_paf_strand(h), shape=(n,)).copy() if n else np.zeros(0, np.uint8)
+        cols = {k: g64(i) for i, k in enumerate(["rank", "qs", "qe", "ts", "te", "blen", "matches"])}
+        t = MappingTable(g32(0, n), g32(1, n), cols["qs"], cols["qe"], cols["ts"], cols["te"], cols["blen"], cols["matches"], ident,
+                         strand, g32(2, ns), g32(3, ns))
+        t.names = [_lib.orc_paf_seq_name(h, i).decode() for i in range(ns)]
+        t.rank = cols["rank"]
+        t.n_lines = _lib.orc_paf_n_lines(h)
+        return t
+    finally:
+        _lib.orc_paf_free(h)
+
+
+def filter_paf(cfg, in_path, out_path):
+    """Oracle PafFilter::filter_paf (parse + filter + tagged write) -> stats"""
+    c = cfg.to_c()
+    st = swg_stats()
+    rc = _lib.orc_filter_paf(C.byref(c), os.fsencode(in_path), os.fsencode(out_path), C.byref(st))
+    if rc != 0:
+        raise IOError(in_path)
+    return st

@@ -1,0 +1,171 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every declared symbol, the host PAF
+front end agrees with the oracle's restatement of extract_metadata, the shard planner, and the
+"fail loudly without a device" contract."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib
+import sweepga_b200 as swg
+from sweepga_b200 import _lib, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "sweepga_b200.h")).read()
+    declared = set(re.findall(r"\b(swg_[a-z0-9_]+)\s*\(", header))
+    declared -= {"swg_ctx", "swg_paf"}
+    lib = C.CDLL(_lib.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, f"declared in include/sweepga_b200.h but not exported: {missing}"
+    bound = {s[0] for s in _lib.SYMBOLS}
+    assert declared <= bound, f"not bound in _lib.py: {sorted(declared - bound)}"
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(_lib.swg_config) == 8 * 8 + 4 * 8 + 8
+    assert C.sizeof(_lib.swg_stats) == 11 * 8 + 3 * 8
+    assert C.sizeof(_lib.swg_mappings) == 8 + 10 * 8 + 8 + 8 + 8 + 8  # n, 10 ptr, score, n_seq(+pad), 2 ptr
+
+
+def test_config_default_matches_cli_defaults():
+    c = _lib.swg_config()
+    _lib.lib.swg_config_default(C.byref(c))
+    d = swg.FilterConfig().to_c()
+    for f, _ in _lib.swg_config._fields_:
+        if f != "reserved":
+            assert getattr(c, f) == getattr(d, f), f
+    e = swg.FilterConfig.from_cli().to_c()
+    for f, _ in _lib.swg_config._fields_:
+        if f != "reserved":
+            assert getattr(c, f) == getattr(e, f), f
+
+
+@pytest.mark.skipif(_has_gpu(), reason="only meaningful on a box without a GPU")
+def test_no_device_fails_loudly():
+    with pytest.raises(swg.SwgError) as e:
+        swg.Context(0)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+QUIRKY = "\n".join([
+    "q#1#a\t1000\t10\t500\t+\tt#1#b\t2000\t20\t510\t450\t490\t60\ttp:A:P\tcg:Z:400=50X40I\tdv:f:0.1",   # dv after cg: dv wins
+    "q#1#a\t1000\t10\t500\t+\tt#1#b\t2000\t20\t510\t450\t490\t60\tdv:f:0.1\tcg:Z:400=50X40I",            # cg after dv: cg wins
+    "too\tshort",                                                                                       # consumes a rank
+    "",
+    "q#1#a\t1000\tx\t500\t-\tt#1#c\t2000\t20\t510\t450\tbad\t60",                                         # parse failures -> 0 / 1
+    "q#1#a\t1000\t10\t500\t*\tt#1#b\t2000\t20\t510\t450\t490\t60\tcg:Z:490M",                              # '*' strand is reverse; M ignored
+    "nohash\t1000\t10\t500\t+\ta#b\t2000\t20\t510\t+450\t490\t60\tcg:Z:=5",                                 # bad cigar ignored; '+450' parses
+    "q#1#a\t1000\t10\t500\t+\tt#1#b\t2000\t20\t510\t450\t490\t60\tdv:f:abc\tcg:Z:0=",                      # bad dv ignored; 0 '=' ignored
+    "q#1#a\t1000\t10\t500\t+\tt#1#b\t2000\t20\t510\t450\t0\t60\r",                                         # block 0, CRLF
+]) + "\nq#1#a\t1000\t700\t900\t+\tt#1#b\t2000\t700\t900\t190\t200\t60"                                     # no trailing newline
+
+
+def test_paf_parser_matches_oracle_on_quirks(tmp_path):
+    p = tmp_path / "q.paf"
+    p.write_text(QUIRKY)
+    a, b = swg.parse_paf(str(p)), oracle_lib.parse_paf(str(p))
+    assert a.n == b.n == 8
+    assert list(a.rank) == list(b.rank) == [0, 1, 4, 5, 6, 7, 8, 9]
+    assert a.names == b.names
+    for f in ("query_id", "target_id", "query_start", "query_end", "target_start", "target_end", "block_length", "matches", "strand",
+              "seq_genome_id", "seq_genome2_id"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    assert np.array_equal(a.identity.view(np.uint64), b.identity.view(np.uint64))  # bit-exact f64
+    assert a.identity[0] == 1.0 - 0.1 and a.identity[1] == 400 / 490
+    assert a.query_start[2] == 0 and a.block_length[2] == 1 and chr(a.strand[2]) == "-" and chr(a.strand[3]) == "-"
+    assert a.matches[4] == 450 and a.matches[1] == 400
+    assert swg.prefix_P("q#1#a") == "q#1#" and swg.prefix_P2("a#b") == "a#b#" and swg.prefix_P("nohash") == "nohash"
+
+
+def test_paf_parser_matches_oracle_on_synthetic(tmp_path):
+    t = synth.yeast_like(40000, seed=2)   # > 1 MiB of text: exercises the multi-threaded chunking
+    p = tmp_path / "y.paf"
+    synth.write_paf(t, str(p))
+    a, b = swg.parse_paf(str(p)), oracle_lib.parse_paf(str(p))
+    assert a.n == b.n == t.n
+    assert a.names == b.names
+    for f in ("query_id", "target_id", "query_start", "query_end", "target_start", "target_end", "block_length", "matches", "strand",
+              "seq_genome_id", "seq_genome2_id"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    assert np.array_equal(a.identity.view(np.uint64), b.identity.view(np.uint64))
+    assert np.array_equal(a.rank, np.arange(t.n, dtype=np.uint64))
+    # the table round-trips: same coordinates and identities as generated
+    assert np.array_equal(a.query_start, t.query_start) and np.array_equal(a.matches, t.matches)
+    # ids are first-appearance ordered
+    seen = []
+    for q, tt in zip(a.query_id[:2000], a.target_id[:2000]):
+        for x in (q, tt):
+            if x not in seen:
+                seen.append(int(x))
+    assert seen == sorted(seen)
+
+
+def test_paf_range_error(tmp_path):
+    p = tmp_path / "big.paf"
+    p.write_text("a\t1\t0\t5000000000\t+\tb\t1\t0\t10\t5\t10\t60\n")
+    with pytest.raises(swg.SwgError):
+        swg.parse_paf(str(p))
+    with pytest.raises(swg.SwgError):
+        swg.parse_paf(str(tmp_path / "missing.paf"))
+
+
+def test_paf_writer_tags(tmp_path):
+    p = tmp_path / "w.paf"
+    p.write_text(QUIRKY)
+    err = C.create_string_buffer(64)
+    h = _lib.lib.swg_paf_parse(str(p).encode(), err, 64)
+    n = _lib.lib.swg_paf_n_records(h)
+    status = np.array([1, 0, 2, 3, 0, 0, 1, 1], np.uint8)
+    chain = np.array([7, 0, 7, 0, 0, 0, 0, 12], np.uint32)
+    out = tmp_path / "o.paf"
+    assert _lib.lib.swg_paf_write(h, str(out).encode(), status.ctypes.data_as(_lib.u8p), chain.ctypes.data_as(_lib.u32p)) == 0
+    _lib.lib.swg_paf_free(h)
+    assert n == 8
+    lines = out.read_text().split("\n")
+    src = QUIRKY.split("\n")
+    assert lines[0] == src[0] + "\tch:Z:chain_7\tst:Z:scaffold"
+    assert lines[1] == src[4] + "\tch:Z:chain_7\tst:Z:rescued"
+    assert lines[2] == src[5] + "\tst:Z:unassigned"
+    assert lines[3] == src[8].rstrip("\r") + "\tst:Z:scaffold"
+    assert lines[4] == src[9] + "\tch:Z:chain_12\tst:Z:scaffold"
+    assert lines[5] == "" and len(lines) == 6
+
+
+def test_shard_plan_keeps_genome_pairs_together_and_balances():
+    t = synth.pansn(200_000, seed=9, n_hap=10)
+    for k in (2, 4, 8):
+        shard_of, sizes = swg.shard_plan(t, k)
+        assert sizes.sum() == t.n and np.array_equal(np.bincount(shard_of, minlength=k), sizes.astype(np.int64))
+        unit = t.seq_genome_id[t.query_id].astype(np.int64) * 1000 + t.seq_genome_id[t.target_id]
+        for u in np.unique(unit)[:50]:
+            assert np.unique(shard_of[unit == u]).size == 1
+        assert sizes.max() <= 1.15 * sizes.mean()
+
+
+def test_oracle_handles_u64_coordinates():
+    """The oracle keeps the reference's u64 arithmetic (the device SoA is u32 by contract)."""
+    kept = oracle_lib.plane_sweep("query", [(0, 100, 0, 100, 0.95), (2**64 - 101, 2**64 - 1, 1000, 1100, 0.9)], 1, 0.95)
+    assert kept == [0, 1]
+
+
+def test_oracle_plane_sweep_core_vectors():
+    """tests/test_plane_sweep_symmetry.rs shape: plane_sweep_core keeps the n best at every Begin, then the
+    greedy overlap pass (src/plane_sweep_core.rs:80-201)."""
+    iv = [(100, 200, 0.9), (150, 250, 0.8), (300, 400, 0.7)]
+    assert sorted(oracle_lib.plane_sweep_core(iv, 1, 0.95)) == [0, 2]
+    assert sorted(oracle_lib.plane_sweep_core(iv, None, 0.95)) == [0, 1, 2]
+    assert oracle_lib.plane_sweep_core([(0, 10, 1.0)], 1, 0.5) == [0]
+    assert oracle_lib.plane_sweep_core([], 1, 0.5) == []

@@ -1,0 +1,179 @@
+"""Parity proper: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bit-exact bar: identical status byte and chain number for every record.  Sizes are chosen so that the
+oracle finishes in seconds; full-size behaviour is covered by size-independent properties
+(idempotence, determinism, shard-invariance) in test_properties_gpu.py.
+"""
+import numpy as np
+import pytest
+
+import oracle_lib
+import sweepga_b200 as swg
+from sweepga_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def fuzz_table(seed, n, n_genomes=3, n_chr=2, span=3000, max_len=400, zero_len_frac=0.02, hashless=False):
+    """Dense, tie-rich tables: few sequences, small coordinates, identities from a small set."""
+    rng = np.random.default_rng(seed)
+    if hashless:
+        names = [f"ctg{i}" for i in range(n_genomes * n_chr)]
+    else:
+        names = [f"G{g}#1#chr{c}" for g in range(n_genomes) for c in range(n_chr)]
+    ns = len(names)
+    qid = rng.integers(0, ns, n)
+    tid = rng.integers(0, ns, n)
+    qs = rng.integers(0, span, n)
+    ln = rng.integers(1, max_len, n)
+    ln[rng.random(n) < zero_len_frac] = 0
+    ts = np.where(rng.random(n) < 0.6, qs + rng.integers(-50, 51, n), rng.integers(0, span, n))
+    ts = np.maximum(ts, 0)
+    tl = np.maximum(ln + rng.integers(-5, 6, n), 0)
+    tl[rng.random(n) < zero_len_frac] = 0
+    ident = rng.choice([0.8, 0.9, 0.95, 1.0, 0.0], n, p=[0.3, 0.3, 0.2, 0.18, 0.02])
+    blk = np.maximum(np.maximum(ln, tl), 1)
+    matches = np.rint(ident * blk).astype(np.int64)
+    identity = matches / blk
+    strand = np.where(rng.random(n) < 0.7, ord("+"), ord("-")).astype(np.uint8)
+    P, P2 = swg.prefix_ids(names)
+    return swg.MappingTable(qid, tid, qs, qs + ln, ts, ts + tl, blk, matches, identity, strand, P, P2, None, names)
+
+
+def check(ctx, cfg, table, what=""):
+    status, chain, stats = ctx.filter(cfg, table)
+    o_status, o_chain, o_stats = oracle_lib.apply_filters(cfg, table)
+    bad = np.nonzero(status != o_status)[0]
+    assert bad.size == 0, f"{what}: status differs at {bad[:10]} (gpu {status[bad[:10]]}, oracle {o_status[bad[:10]]}) of {table.n}"
+    bad = np.nonzero(chain != o_chain)[0]
+    assert bad.size == 0, f"{what}: chain id differs at {bad[:10]} (gpu {chain[bad[:10]]}, oracle {o_chain[bad[:10]]})"
+    for f in ("n_stage1", "n_after_sweep", "n_kept"):
+        assert getattr(stats, f) == getattr(o_stats, f), f"{what}: stats.{f} gpu {getattr(stats, f)} oracle {getattr(o_stats, f)}"
+    if cfg.scaffold_gap > 0:
+        for f in ("n_chains", "n_chains_after_mass", "n_chains_kept", "n_rescued"):
+            assert getattr(stats, f) == getattr(o_stats, f), f"{what}: stats.{f} gpu {getattr(stats, f)} oracle {getattr(o_stats, f)}"
+    assert stats.gpu_launches > 0
+    return status, chain, stats
+
+
+CLI_CASES = {
+    "defaults": {},
+    "1:1_1:1": dict(num_mappings="1:1", scaffold_filter="1:1"),
+    "rescue100k": dict(scaffold_dist="100k"),
+    "1:1_rescue": dict(num_mappings="1:1", scaffold_filter="1:1", scaffold_dist="20k"),
+    "no_scaffold_1:1": dict(num_mappings="1:1", scaffold_jump="0"),
+    "no_scaffold_many": dict(scaffold_jump="0"),
+    "n3": dict(num_mappings="3", scaffold_jump="0", overlap=0.5),
+    "2:3": dict(num_mappings="2:3", scaffold_filter="2:2", scaffold_overlap=0.3),
+    "many:1": dict(num_mappings="many:1", scaffold_filter="1:many"),
+    "scaffolds_only": dict(scaffolds_only=True),
+    "self": dict(keep_self=True, scaffold_mass="0"),
+    "identity_scoring": dict(num_mappings="1:1", scaffold_filter="1:1", scoring="ani"),
+    "length_scoring": dict(num_mappings="1:1", scaffold_filter="1:1", scoring="length"),
+    "length_ani_scoring": dict(num_mappings="1:1", scaffold_filter="1:1", scoring="length-ani"),
+    "min_filters": dict(min_aln_length="5k", min_aln_identity="0.95", min_scaffold_identity="0.97"),
+    "tight_jump": dict(scaffold_jump="2k", scaffold_mass="1k", scaffold_dist="5k"),
+    "mass0": dict(scaffold_mass="0", scaffold_filter="1:1"),
+}
+
+
+@pytest.fixture(scope="module")
+def yeast():
+    return synth.yeast_like(30000, seed=1)
+
+
+@pytest.mark.parametrize("case", list(CLI_CASES))
+def test_yeast_configs(ctx, yeast, case):
+    """BASELINE configs[0] (defaults) and configs[1] (1:1 / 1:1) on the yeast-shaped table, plus flag variants."""
+    check(ctx, swg.FilterConfig.from_cli(**CLI_CASES[case]), yeast, case)
+
+
+@pytest.mark.parametrize("case", ["defaults", "rescue100k", "1:1_1:1"])
+def test_pansn_400k(ctx, case):
+    """configs[2]/[3] generator at a size the oracle finishes in seconds."""
+    check(ctx, swg.FilterConfig.from_cli(**CLI_CASES[case]), synth.pansn(400_000, seed=3, n_hap=12), case)
+
+
+def test_pansn_2m_defaults(ctx):
+    check(ctx, swg.FilterConfig(), synth.pansn(2_000_000, seed=4, n_hap=24), "pansn2m")
+
+
+@pytest.mark.parametrize("case", ["defaults", "rescue100k"])
+def test_skew_small(ctx, case):
+    """configs[4] shape, scaled so the oracle's O(n*window) chaining finishes: one pile + many tiny groups."""
+    check(ctx, swg.FilterConfig.from_cli(**CLI_CASES[case]), synth.skew(n_pile=20_000, n_tiny_groups=3_000, seed=5, window=3_000_000), case)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_fuzz_dense(ctx, seed):
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(2, 600))
+    t = fuzz_table(seed, n, hashless=bool(seed % 5 == 0))
+    modes = ["1:1", "1", "2:2", "many:many", "3:1", "many:1", "1:many"]
+    cfg = swg.FilterConfig.from_cli(
+        num_mappings=modes[seed % len(modes)], scaffold_filter=modes[(seed // 3) % len(modes)],
+        overlap=[0.0, 0.5, 0.95, 1.0][seed % 4], scaffold_overlap=[0.5, 0.0, 1.0][seed % 3],
+        scaffold_jump=str([0, 50, 200, 1000][(seed // 2) % 4]), scaffold_mass=str([0, 100, 500][seed % 3]),
+        scaffold_dist=str([0, 100, 1000][(seed // 5) % 3]), keep_self=bool(seed % 2),
+        scoring=["log-length-ani", "ani", "length", "length-ani", "matches"][seed % 5])
+    check(ctx, cfg, t, f"fuzz{seed}")
+
+
+def test_edge_cases(ctx):
+    cfg = swg.FilterConfig.from_cli(scaffold_mass="0")
+    names = ["A#1#c1", "B#1#c1"]
+    P, P2 = swg.prefix_ids(names)
+    z = lambda *a: np.array(a, dtype=np.int64)
+    # empty
+    t = swg.MappingTable(z(), z(), z(), z(), z(), z(), z(), z(), np.zeros(0), np.zeros(0, np.uint8), P, P2)
+    s, c, st = ctx.filter(cfg, t)
+    assert s.size == 0 and st.n_kept == 0
+    # one record
+    t = swg.MappingTable(z(0), z(1), z(10), z(500), z(10), z(500), z(490), z(480), np.array([480 / 490]), np.array([43], np.uint8), P, P2)
+    check(ctx, cfg, t, "single")
+    check(ctx, swg.FilterConfig.from_cli(num_mappings="1:1", scaffold_filter="1:1", scaffold_mass="0"), t, "single 1:1")
+    # a single self mapping: dropped unless --self
+    t = swg.MappingTable(z(0), z(0), z(10), z(500), z(10), z(500), z(490), z(480), np.array([0.98]), np.array([43], np.uint8), P, P2)
+    check(ctx, cfg, t, "self dropped")
+    # two zero-length records in one group, one alone in its group (size<=1 rule, plane_sweep_exact.rs:274-276)
+    t = swg.MappingTable(z(0, 0, 1), z(1, 1, 0), z(5, 5, 7), z(5, 5, 7), z(5, 9, 7), z(5, 9, 7), z(1, 1, 1), z(1, 1, 1), np.array([1.0, 1.0, 1.0]),
+                         np.array([43, 43, 43], np.uint8), P, P2)
+    check(ctx, cfg, t, "zero-length")
+    check(ctx, swg.FilterConfig.from_cli(scaffold_jump="0"), t, "zero-length no scaffold")
+
+
+def test_range_errors(ctx):
+    names = ["A#1#c1", "B#1#c1"]
+    P, P2 = swg.prefix_ids(names)
+    z = lambda *a: np.array(a, dtype=np.int64)
+    t = swg.MappingTable(z(0), z(1), z(500), z(10), z(10), z(500), z(490), z(480), np.array([0.9]), np.array([43], np.uint8), P, P2)
+    with pytest.raises(swg.SwgError) as e:
+        ctx.filter(swg.FilterConfig(), t)
+    assert e.value.code == -2
+    t = swg.MappingTable(z(0), z(7), z(10), z(500), z(10), z(500), z(490), z(480), np.array([0.9]), np.array([43], np.uint8), P, P2)
+    with pytest.raises(swg.SwgError):
+        ctx.filter(swg.FilterConfig(), t)
+
+
+def test_paf_front_end_matches_oracle(ctx, tmp_path):
+    """parse + filter + tagged write through swg_filter_paf == the oracle's filter_paf, byte for byte."""
+    t = synth.yeast_like(5000, seed=11)
+    src = tmp_path / "y.paf"
+    synth.write_paf(t, str(src))
+    # sprinkle the parser quirks: short line (consumes a rank), CRLF, unparsable number, odd strand, dv after cg
+    lines = src.read_text().split("\n")
+    lines.insert(3, "short\tline")
+    lines.insert(10, "")
+    lines[20] = lines[20] + "\r"
+    f = lines[30].split("\t"); f[9] = "x12"; lines[30] = "\t".join(f)
+    f = lines[31].split("\t"); f[4] = "*"; lines[31] = "\t".join(f)
+    f = lines[32].split("\t"); f.append("dv:f:0.25"); lines[32] = "\t".join(f)
+    src.write_text("\n".join(lines))
+    for flags in ({}, dict(num_mappings="1:1", scaffold_filter="1:1"), dict(scaffold_dist="50k"), dict(scaffold_jump="0")):
+        cfg = swg.FilterConfig.from_cli(**flags)
+        a, b = tmp_path / "gpu.paf", tmp_path / "orc.paf"
+        f = swg.PafFilter(cfg)
+        f._ctx = ctx
+        f.filter_paf(str(src), str(a))
+        oracle_lib.filter_paf(cfg, str(src), str(b))
+        assert a.read_bytes() == b.read_bytes(), flags
