@@ -141,6 +141,9 @@ typedef struct swg_stats {
     uint64_t score_near_ties;     /* score pairs within 2 ulp compared by a sweep (see DESIGN) */
     uint64_t gpu_launches;        /* kernels launched by this call                             */
     double ms_h2d, ms_device, ms_d2h; /* CUDA-event times of the three phases of swg_filter    */
+    double ms_sort_passes;        /* CUDA-event time of the one-sweep passes of the record sort  */
+    uint64_t n_sort_passes;       /* ... how many passes that was                               */
+    uint64_t n_sort_pairs;        /* ... over how many (key,payload) pairs                      */
 } swg_stats;
 
 typedef struct swg_ctx swg_ctx;

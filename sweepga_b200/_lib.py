@@ -50,6 +50,7 @@ class swg_stats(C.Structure):
         ("n_chains_after_mass", C.c_uint64), ("n_chains_kept", C.c_uint64), ("n_anchors", C.c_uint64),
         ("n_rescued", C.c_uint64), ("n_kept", C.c_uint64), ("score_near_ties", C.c_uint64), ("gpu_launches", C.c_uint64),
         ("ms_h2d", C.c_double), ("ms_device", C.c_double), ("ms_d2h", C.c_double),
+        ("ms_sort_passes", C.c_double), ("n_sort_passes", C.c_uint64), ("n_sort_pairs", C.c_uint64),
     ]
 
 

@@ -101,6 +101,9 @@ struct swg_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_sort[2] = {nullptr, nullptr}; // bracket the one-sweep passes of the record sort
+    int sort_passes = 0;
+    u64 sort_pairs = 0;
     Arena arena;      // per-call scratch
     Arena io;         // staging of host SoA for swg_filter
     u64 *h_ctr = nullptr; // pinned mirror of the counters
@@ -127,13 +130,14 @@ static u32 read_u32(swg_ctx *c, const u32 *d) {
 }
 
 // sort (key,payload) pairs in arena scratch; returns sorted pointers through the references
-static void sort_pairs(swg_ctx *c, u64 *&k, u64 *&k2, u32 *&v, u32 *&v2, u32 n, int bits) {
+static void sort_pairs(swg_ctx *c, u64 *&k, u64 *&k2, u32 *&v, u32 *&v2, u32 n, int bits, bool timed = false) {
     if (n == 0) return;
     if (bits > 64) throw RangeError{"sort key wider than 64 bits (too many sequences x coordinate range)"};
     for (int begin = 0; begin < bits; begin += RS_MAX_PASSES * RS_BITS) { // > 8 passes never happens (64 bits)
         RadixSortPlan p = rs_plan(n, begin, bits);
         void *tmp = c->arena.take<char>(p.temp_bytes);
-        rs_sort_pairs(p, k, k2, v, v2, tmp, c->stream, c->sm_count, c->lc);
+        rs_sort_pairs(p, k, k2, v, v2, tmp, c->stream, c->sm_count, c->lc, timed ? c->ev_sort[0] : nullptr, timed ? c->ev_sort[1] : nullptr);
+        if (timed) { c->sort_passes = p.passes; c->sort_pairs = n; }
     }
 }
 
@@ -219,8 +223,17 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     S.n_input = N;
     SWG_CUDA(cudaMemsetAsync(status, 0, N, st));
     SWG_CUDA(cudaMemsetAsync(chain_id, 0, sizeof(u32) * (size_t)N, st));
+    c->sort_passes = 0;
+    c->sort_pairs = 0;
     auto finish = [&]() {
         S.gpu_launches = lc.n - launches0;
+        if (c->sort_passes) { // all work has been synchronised by the last counter read
+            float ms = 0;
+            cudaStreamSynchronize(st);
+            if (cudaEventElapsedTime(&ms, c->ev_sort[0], c->ev_sort[1]) == cudaSuccess) S.ms_sort_passes = ms;
+            S.n_sort_passes = (u64)c->sort_passes;
+            S.n_sort_pairs = c->sort_pairs;
+        }
         if (stats) *stats = S;
     };
     if (N == 0) { SWG_CUDA(cudaStreamSynchronize(st)); finish(); return; }
@@ -306,7 +319,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     u32 *vals = A.take<u32>(N), *vals2 = A.take<u32>(N);
     k_chain_keys<<<cdiv(N, 256), 256, 0, st>>>(in, flags, keep_q, keep_t, sb, cb, keys, vals, ctr);
     lc.n++;
-    sort_pairs(c, keys, keys2, vals, vals2, N, 2 * sb + 1 + cb);
+    sort_pairs(c, keys, keys2, vals, vals2, N, 2 * sb + 1 + cb, true);
     read_counters(c);
     const u32 n_m = (u32)c->h_ctr[C_KEPT_M];
     S.n_after_sweep = n_m;
@@ -730,6 +743,7 @@ swg_ctx *swg_create(int device) {
         c->sm_count = prop.multiProcessorCount;
         SWG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         for (auto &ev : c->ev) SWG_CUDA(cudaEventCreate(&ev));
+        for (auto &ev : c->ev_sort) SWG_CUDA(cudaEventCreate(&ev));
         SWG_CUDA(cudaMallocHost(&c->h_ctr, sizeof(u64) * (C_COUNT + 8)));
         SWG_CUDA(cudaMalloc(&c->d_ctr, sizeof(u64) * C_COUNT));
     } catch (const CudaError &e2) {
@@ -752,6 +766,7 @@ void swg_destroy(swg_ctx *c) {
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     if (c->d_ctr) cudaFree(c->d_ctr);
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : c->ev_sort) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

@@ -227,7 +227,8 @@ static inline RadixSortPlan rs_plan(u32 n, int begin_bit, int end_bit) {
 // Sorts by key bits [begin_bit, begin_bit + 8*passes).  On return (keys, vals) point at the
 // sorted data and (keys_alt, vals_alt) at the scratch (the pointers are swapped as needed).
 static inline void rs_sort_pairs(const RadixSortPlan &p, u64 *&keys, u64 *&keys_alt, u32 *&vals, u32 *&vals_alt, void *temp,
-                                 cudaStream_t st, int sm_count, LaunchCounter &lc) {
+                                 cudaStream_t st, int sm_count, LaunchCounter &lc, cudaEvent_t ev_begin = nullptr,
+                                 cudaEvent_t ev_end = nullptr) {
     if (p.n == 0) return;
     u32 *hist = (u32 *)temp;
     u32 *counters = hist + RS_MAX_PASSES * RS_RADIX;
@@ -242,6 +243,7 @@ static inline void rs_sort_pairs(const RadixSortPlan &p, u64 *&keys, u64 *&keys_
     rs_histogram_kernel<<<hgrid, 512, 0, st>>>(keys, p.n, p.begin_bit, p.passes, hist);
     rs_scan_hist_kernel<<<p.passes, RS_RADIX, 0, st>>>(hist);
     lc.n += 2;
+    if (ev_begin) SWG_CUDA(cudaEventRecord(ev_begin, st));
     for (int pass = 0; pass < p.passes; pass++) {
         rs_onesweep_kernel<<<p.tiles, RS_THREADS, sizeof(RsSmem), st>>>(keys, keys_alt, vals, vals_alt, p.n,
                                                                         p.begin_bit + pass * RS_BITS, hist + pass * RS_RADIX,
@@ -250,6 +252,7 @@ static inline void rs_sort_pairs(const RadixSortPlan &p, u64 *&keys, u64 *&keys_
         u64 *tk = keys; keys = keys_alt; keys_alt = tk;
         u32 *tv = vals; vals = vals_alt; vals_alt = tv;
     }
+    if (ev_end) SWG_CUDA(cudaEventRecord(ev_end, st));
     SWG_CUDA(cudaGetLastError());
 }
 
