@@ -56,6 +56,22 @@ __device__ __forceinline__ u32 hash_lookup(const u64 *hk, const u32 *hv, u32 mas
     }
 }
 
+
+// add per-thread small counts into a u64 counter: warp reduce, then one atomic per CTA
+// (same-address global atomics cost ~0.5 ns each; one per warp was the top cost of the flat kernels)
+template <int NC> __device__ __forceinline__ void block_count_add(u64 *ctr, const int (&slot)[NC], const u32 (&val)[NC]) {
+    __shared__ u32 s_part[NC];
+    if (threadIdx.x < NC) s_part[threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NC; k++) {
+        u32 w = __reduce_add_sync(0xFFFFFFFFu, val[k]);
+        if (lane_id() == 0 && w) atomicAdd(&s_part[k], w);
+    }
+    __syncthreads();
+    if (threadIdx.x < NC && s_part[threadIdx.x]) atomicAdd((unsigned long long *)&ctr[slot[threadIdx.x]], (unsigned long long)s_part[threadIdx.x]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // K0: stage-1 retain + range checks + genome-pair first appearance  (paf_filter.rs:384-388)
 // 33 B read + 1 B written per record.
@@ -79,19 +95,27 @@ __global__ void __launch_bounds__(256) k_prefilter(DevIn in, u64 min_len, double
         flags[i] = (u8)((alive ? F_ALIVE : 0) | (zq ? F_ZLQ : 0) | (zt ? F_ZLT : 0));
     }
     const u32 full = 0xFFFFFFFFu;
-    u32 na = __popc(__ballot_sync(full, alive)), nq = __popc(__ballot_sync(full, zq)), nt = __popc(__ballot_sync(full, zt)),
-        nb = __popc(__ballot_sync(full, bad));
-    u32 mx = __reduce_max_sync(full, maxc);
-    if (lane_id() == 0) {
-        if (na) atomicAdd((unsigned long long *)&ctr[C_ALIVE], (unsigned long long)na);
-        if (nq) atomicAdd((unsigned long long *)&ctr[C_ZLQ], (unsigned long long)nq);
-        if (nt) atomicAdd((unsigned long long *)&ctr[C_ZLT], (unsigned long long)nt);
-        if (nb) atomicAdd((unsigned long long *)&ctr[C_BAD], (unsigned long long)nb);
-        atomicMax((unsigned long long *)&ctr[C_MAXCOORD], (unsigned long long)mx);
+    {
+        const int slots[4] = {C_ALIVE, C_ZLQ, C_ZLT, C_BAD};
+        const u32 vals[4] = {alive ? 1u : 0u, zq ? 1u : 0u, zt ? 1u : 0u, bad ? 1u : 0u};
+        block_count_add<4>(ctr, slots, vals);
     }
+    u32 mx = __reduce_max_sync(full, maxc);
+    if (lane_id() == 0 && mx > (u32)ctr[C_MAXCOORD]) atomicMax((unsigned long long *)&ctr[C_MAXCOORD], (unsigned long long)mx);
     // one hash insert per distinct genome pair per warp; the lowest lane holds the lowest index
     u32 peers = __match_any_sync(full, g);
-    if (alive && lane_id() == (u32)(__ffs(peers) - 1)) hash_insert_min(hk, hv, hmask, g, i);
+    if (alive && lane_id() == (u32)(__ffs(peers) - 1)) {
+        // values only decrease: a plain read that already shows a smaller index makes the atomics unnecessary
+        u32 sl = hash64(g) & hmask;
+        bool done = false;
+        for (int probe = 0; probe < 4; probe++) {
+            u64 k = hk[sl];
+            if (k == g) { done = hv[sl] <= i; break; }
+            if (k == NONE64) break;
+            sl = (sl + 1) & hmask;
+        }
+        if (!done) hash_insert_min(hk, hv, hmask, g, i);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -115,8 +139,9 @@ __global__ void __launch_bounds__(256) k_chain_keys(DevIn in, const u8 *__restri
         keys[i] = k;
         vals[i] = i;
     }
-    u32 nk = __popc(__ballot_sync(0xFFFFFFFFu, kept));
-    if (lane_id() == 0 && nk) atomicAdd((unsigned long long *)&ctr[C_KEPT_M], (unsigned long long)nk);
+    const int slots[1] = {C_KEPT_M};
+    const u32 cvals[1] = {kept ? 1u : 0u};
+    block_count_add<1>(ctr, slots, cvals);
 }
 
 // scaffold_gap == 0 exit (paf_filter.rs:409-434): survivors are Unassigned, no chain id
@@ -128,139 +153,219 @@ __global__ void __launch_bounds__(256) k_unassigned(u32 n, const u8 *__restrict_
         kept = (flags[i] & F_ALIVE) && (!keep_q || keep_q[i]) && (!keep_t || keep_t[i]);
         status[i] = kept ? 3 : 0;
     }
-    u32 nk = __popc(__ballot_sync(0xFFFFFFFFu, kept));
-    if (lane_id() == 0 && nk) atomicAdd((unsigned long long *)&ctr[C_KEPT], (unsigned long long)nk);
+    const int slots[1] = {C_KEPT};
+    const u32 vals[1] = {kept ? 1u : 0u};
+    block_count_add<1>(ctr, slots, vals);
+}
+
+// final tallies for swg_stats (grid-stride, one atomic pair per CTA)
+__global__ void __launch_bounds__(256) k_count_status(u32 n, const u8 *__restrict__ status, u64 *__restrict__ ctr) {
+    u32 a = 0, r = 0;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        u8 s = status[i];
+        a += s == 1;
+        r += s == 2;
+    }
+    const int slots[2] = {C_ANCHORS, C_RESCUED};
+    const u32 vals[2] = {a, r};
+    block_count_add<2>(ctr, slots, vals);
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3: best-buddy chaining, one warp per (query,target,strand) group  (paf_filter.rs:780-851)
-// plus union-find roots (union_find.rs:25-41: the root of a set is always its head) and the
-// per-chain aggregates (paf_filter.rs:875-894).  The sequential scan over i is kept (it has
-// mutable per-j state); the j-window is scanned by the 32 lanes.
+// K3: best-buddy chaining (paf_filter.rs:780-851), union-find roots (union_find.rs:25-41: the root of a
+// set is always its head) and per-chain aggregates (paf_filter.rs:875-894), in three phases:
+//   P1 k_chain_candidates  flat, one thread per position: the unconstrained best successor u(i)
+//                          (smallest d, first minimal j) — all of the O(window) gap arithmetic, coalesced.
+//   P2 k_chain_resolve     the inherently sequential part, one thread per group: walk i ascending;
+//                          if u(i) still beats best_pred_score[u(i)] it IS the reference's choice (the global
+//                          arg-min is eligible, so it is the arg-min over the eligible ones); only a blocked
+//                          i re-scans its window with the eligibility test.  ~10 instructions per step.
+//   P3 k_chain_heads / k_chain_members  flat: bounding boxes and sums per chain (segmented warp
+//                          reduction, then one atomic set per run).
 // ---------------------------------------------------------------------------------------------
 struct ChainSparse { // indexed by the sorted position of the chain head
     u32 *qmin, *qmax, *tmin, *tmax;
     u64 *sum_matches, *sum_block;
-    u32 *minidx; // min original index over the group's members (first appearance of the group in M)
+    u32 *group;       // group index of the chain (head slot)
+    u32 *grp_minidx;  // per GROUP: min original index over its members (first appearance of the group in M)
+};
+struct Cand { // unconstrained best successor of a position
+    u64 d;    // squared gap distance
+    u32 j;    // sorted position of the successor, NONE32 if the window holds no valid candidate
+    u32 pad;
 };
 
+// gap rule of paf_filter.rs:799-833 (query axis and, strand-aware, target axis)
+__device__ __forceinline__ bool bb_candidate(const uint4 &a, const uint4 &b, bool fwd, u64 G, u64 G5, u64 &d) {
+    u64 qgap, rgap;
+    if (b.x >= a.y) qgap = b.x - a.y;
+    else { u64 ov = a.y - b.x; qgap = ov <= G5 ? ov : G + 1; }
+    if (fwd) {
+        if (b.z >= a.w) rgap = b.z - a.w;
+        else { u64 ov = a.w - b.z; rgap = ov <= G5 ? ov : G + 1; }
+    } else {
+        if (a.z >= b.w) rgap = a.z - b.w;
+        else { u64 ov = b.w - a.z; rgap = ov <= G5 ? ov : G + 1; }
+    }
+    if (qgap <= G && rgap <= G) { d = qgap * qgap + rgap * rgap; return true; }
+    return false;
+}
+
+// P1: 24 B read (+ window re-reads served by L1) and 28 B written per position.
 __global__ void __launch_bounds__(256)
-k_best_buddy(const uint4 *__restrict__ srec, const uint2 *__restrict__ srec2, const u64 *__restrict__ skey,
-             const u32 *__restrict__ sidx, const u32 *__restrict__ gstart, u32 n_groups, u32 n_m, int cb, u64 G,
-             u64 *bps, u32 *root, ChainSparse cs, u32 *group_counter) {
+k_chain_candidates(const uint4 *__restrict__ srec, const u64 *__restrict__ skey, const u32 *__restrict__ gid, u32 n_m, int cb,
+                   u64 G, Cand *__restrict__ cand, u64 *__restrict__ bps, u32 *__restrict__ root, u8 *__restrict__ grp_has_cand) {
+    const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_m) return;
+    const uint4 a = srec[p]; // x=qs y=qe z=ts w=te
+    const u64 grp = skey[p] >> cb;
+    const bool fwd = (grp & 1) == 0;
+    const u64 G5 = G / 5;
+    const u64 bound = (u64)a.y + G;
+    u64 bd = NONE64;
+    u32 bj = NONE32;
+    for (u32 j = p + 1; j < n_m; j++) {
+        if ((skey[j] >> cb) != grp) break;
+        const uint4 b = srec[j];
+        if ((u64)b.x > bound) break;
+        u64 d;
+        if (bb_candidate(a, b, fwd, G, G5, d) && d < bd) { bd = d; bj = j; }
+    }
+    Cand c;
+    c.d = bd; c.j = bj; c.pad = 0;
+    cand[p] = c;
+    bps[p] = NONE64;
+    root[p] = p;
+    if (bj != NONE32) grp_has_cand[gid[p]] = 1; // benign race: every writer stores 1
+}
+
+// P2: one thread per group that has at least one candidate; lanes refill from the work list as they finish.
+__global__ void __launch_bounds__(128)
+k_chain_resolve(const Cand *__restrict__ cand, const uint4 *__restrict__ srec, const u64 *__restrict__ skey,
+                const u32 *__restrict__ gstart, u32 n_groups, u32 n_m, const u32 *__restrict__ work, const u32 *__restrict__ n_work_ptr,
+                int cb, u64 G, u64 *bps, u32 *root, u32 *work_counter) {
+    const u32 full = 0xFFFFFFFFu;
+    const u64 G5 = G / 5;
+    const u32 n_work = *n_work_ptr;
+    bool active = false, exhausted = false, fwd = true;
+    u32 e = 0, i = 0;
+    while (true) {
+        const u32 need = __ballot_sync(full, !active && !exhausted);
+        if (need) {
+            const u32 leader = __ffs(need) - 1;
+            u32 base = 0;
+            if (lane_id() == leader) base = atomicAdd(work_counter, (u32)__popc(need));
+            base = __shfl_sync(full, base, leader);
+            if (!active && !exhausted) {
+                const u32 w = base + __popc(need & lanemask_lt());
+                if (w >= n_work) exhausted = true;
+                else {
+                    const u32 g = work[w];
+                    i = gstart[g];
+                    e = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
+                    fwd = ((skey[i] >> cb) & 1) == 0;
+                    active = true;
+                }
+            }
+        }
+        if (__all_sync(full, exhausted && !active)) break;
+        if (active) {
+            const Cand c = cand[i];
+            if (c.j != NONE32) {
+                const u32 ri = root[i]; // final: every possible predecessor of i has been processed
+                if (c.d < bps[c.j]) { // the unconstrained arg-min is eligible => it is the reference's pick
+                    bps[c.j] = c.d;
+                    root[c.j] = ri;
+                } else { // blocked: arg-min over the eligible candidates (paf_filter.rs:835-843)
+                    const uint4 a = srec[i];
+                    const u64 bound = (u64)a.y + G;
+                    u64 bd = NONE64;
+                    u32 bj = NONE32;
+                    for (u32 j = i + 1; j < e; j++) {
+                        const uint4 b = srec[j];
+                        if ((u64)b.x > bound) break;
+                        u64 d;
+                        if (bb_candidate(a, b, fwd, G, G5, d) && d < bd && d < bps[j]) { bd = d; bj = j; }
+                    }
+                    if (bj != NONE32) { bps[bj] = bd; root[bj] = ri; }
+                }
+            }
+            if (++i == e) active = false;
+        }
+    }
+}
+
+// P3a: chain heads seed their slot with their own record; every position feeds its group's min original index.
+__global__ void __launch_bounds__(256)
+k_chain_heads(const uint4 *__restrict__ srec, const uint2 *__restrict__ srec2, const u32 *__restrict__ sidx,
+              const u32 *__restrict__ gid, const u32 *__restrict__ root, u32 n_m, ChainSparse cs) {
+    const u32 full = 0xFFFFFFFFu;
+    const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = p < n_m;
+    u32 g = NONE32, idx = NONE32;
+    if (ok) {
+        g = gid[p];
+        idx = sidx[p];
+        if (root[p] == p) {
+            const uint4 a = srec[p];
+            const uint2 m = srec2[p];
+            cs.qmin[p] = a.x; cs.qmax[p] = a.y; cs.tmin[p] = a.z; cs.tmax[p] = a.w;
+            cs.sum_matches[p] = m.y; cs.sum_block[p] = m.x; cs.group[p] = g;
+        }
+    }
+    // groups are contiguous: usually the whole warp shares one
+    const u32 g0 = __shfl_sync(full, g, 0);
+    if (__all_sync(full, g == g0)) {
+        const u32 mn = __reduce_min_sync(full, idx);
+        if (lane_id() == 0 && g0 != NONE32) atomicMin(&cs.grp_minidx[g0], mn);
+    } else if (ok) {
+        atomicMin(&cs.grp_minidx[g], idx);
+    }
+}
+
+// P3b: members fold into their head's slot (paf_filter.rs:875-894); runs of equal root are reduced in the warp first.
+__global__ void __launch_bounds__(256)
+k_chain_members(const uint4 *__restrict__ srec, const uint2 *__restrict__ srec2, const u32 *__restrict__ root, u32 n_m, ChainSparse cs) {
     const u32 full = 0xFFFFFFFFu;
     const u32 lane = lane_id();
-    const u64 G5 = G / 5;
-    while (true) {
-        u32 g = 0;
-        if (lane == 0) g = atomicAdd(group_counter, 1u);
-        g = __shfl_sync(full, g, 0);
-        if (g >= n_groups) break;
-        const u32 s = gstart[g], e = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
-        const bool fwd = ((skey[s] >> cb) & 1) == 0;
-        u32 B = NONE32;
-        for (u32 p = s + lane; p < e; p += 32) {
-            B = min(B, sidx[p]);
-            root[p] = p;
-            bps[p] = NONE64;
-        }
-        B = __reduce_min_sync(full, B);
-        __syncwarp();
-        for (u32 i = s; i + 1 < e; i++) {
-            const uint4 a = srec[i]; // x=qs y=qe z=ts w=te
-            const u64 bound = (u64)a.y + G;
-            u64 bd = NONE64;
-            u32 bj = NONE32;
-            for (u32 base = i + 1; base < e; base += 32) {
-                u32 j = base + lane;
-                bool inwin = false;
-                if (j < e) {
-                    const uint4 b = srec[j];
-                    inwin = (u64)b.x <= bound;
-                    if (inwin) {
-                        u64 qgap, rgap;
-                        if (b.x >= a.y) qgap = b.x - a.y;
-                        else { u64 ov = a.y - b.x; qgap = ov <= G5 ? ov : G + 1; }
-                        if (fwd) {
-                            if (b.z >= a.w) rgap = b.z - a.w;
-                            else { u64 ov = a.w - b.z; rgap = ov <= G5 ? ov : G + 1; }
-                        } else {
-                            if (a.z >= b.w) rgap = a.z - b.w;
-                            else { u64 ov = b.w - a.z; rgap = ov <= G5 ? ov : G + 1; }
-                        }
-                        if (qgap <= G && rgap <= G) {
-                            u64 d = qgap * qgap + rgap * rgap;
-                            if (d < bd && d < bps[j]) { bd = d; bj = j; }
-                        }
-                    }
-                }
-                if (!__all_sync(full, inwin)) break;
-            }
+    const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = p < n_m;
+    const u32 r = ok ? root[p] : NONE32;
+    const bool member = ok && r != p;
+    if (!__any_sync(full, member)) return;
+    uint4 a = member ? srec[p] : make_uint4(NONE32, 0, NONE32, 0);
+    uint2 m = member ? srec2[p] : make_uint2(0, 0);
+    const u64 smv = m.y, sbk = m.x;
+    const u32 key = member ? r : (0x80000000u | lane) ; // non-members never match anything useful
+    const u32 peers = __match_any_sync(full, key);
+    const u32 leader = __ffs(peers) - 1;
+    if (member && __popc(peers) == 1) {
+        atomicMin(&cs.qmin[r], a.x); atomicMax(&cs.qmax[r], a.y);
+        atomicMin(&cs.tmin[r], a.z); atomicMax(&cs.tmax[r], a.w);
+        atomicAdd((unsigned long long *)&cs.sum_matches[r], (unsigned long long)smv);
+        atomicAdd((unsigned long long *)&cs.sum_block[r], (unsigned long long)sbk);
+    }
+    u32 todo = __ballot_sync(full, member && __popc(peers) > 1 && lane == leader);
+    while (todo) {
+        const u32 Ld = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const u32 pm = __shfl_sync(full, peers, Ld);
+        const u32 rr = __shfl_sync(full, r, Ld);
+        const bool in = (pm >> lane) & 1;
+        const u32 vqmin = __reduce_min_sync(full, in ? a.x : NONE32), vqmax = __reduce_max_sync(full, in ? a.y : 0u);
+        const u32 vtmin = __reduce_min_sync(full, in ? a.z : NONE32), vtmax = __reduce_max_sync(full, in ? a.w : 0u);
+        u64 vsm = in ? smv : 0, vsb = in ? sbk : 0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                u64 od = __shfl_down_sync(full, bd, o);
-                u32 oj = __shfl_down_sync(full, bj, o);
-                if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
-            }
-            if (lane == 0 && bj != NONE32) {
-                bps[bj] = bd;
-                root[bj] = root[i];
-            }
-            __syncwarp();
+        for (int o = 16; o > 0; o >>= 1) {
+            vsm += __shfl_down_sync(full, vsm, o);
+            vsb += __shfl_down_sync(full, vsb, o);
         }
-        // aggregates: heads initialise their slot, then every member reduces into its head's slot
-        for (u32 p = s + lane; p < e; p += 32) {
-            if (root[p] == p) {
-                cs.qmin[p] = NONE32; cs.qmax[p] = 0; cs.tmin[p] = NONE32; cs.tmax[p] = 0;
-                cs.sum_matches[p] = 0; cs.sum_block[p] = 0; cs.minidx[p] = B;
-            }
+        if (lane == 0) {
+            atomicMin(&cs.qmin[rr], vqmin); atomicMax(&cs.qmax[rr], vqmax);
+            atomicMin(&cs.tmin[rr], vtmin); atomicMax(&cs.tmax[rr], vtmax);
+            atomicAdd((unsigned long long *)&cs.sum_matches[rr], (unsigned long long)vsm);
+            atomicAdd((unsigned long long *)&cs.sum_block[rr], (unsigned long long)vsb);
         }
-        __syncwarp();
-        for (u32 base = s; base < e; base += 32) {
-            u32 p = base + lane;
-            bool ok = p < e;
-            u32 r = ok ? root[p] : NONE32;
-            uint4 a = ok ? srec[p] : make_uint4(NONE32, 0, NONE32, 0);
-            uint2 m = ok ? srec2[p] : make_uint2(0, 0);
-            u64 sm = m.y, sbk = m.x;
-            // segmented warp reduction over runs of equal root (chain members are mostly adjacent)
-            u32 peers = __match_any_sync(full, r);
-            u32 leader = __ffs(peers) - 1;
-            if (ok) {
-                if (__popc(peers) == 1) {
-                    atomicMin(&cs.qmin[r], a.x); atomicMax(&cs.qmax[r], a.y);
-                    atomicMin(&cs.tmin[r], a.z); atomicMax(&cs.tmax[r], a.w);
-                    atomicAdd((unsigned long long *)&cs.sum_matches[r], (unsigned long long)sm);
-                    atomicAdd((unsigned long long *)&cs.sum_block[r], (unsigned long long)sbk);
-                }
-            }
-            // multi-member groups: the leader folds its peers' values (<= 31 shuffles, peers-bounded)
-            u32 todo = __ballot_sync(full, ok && __popc(peers) > 1 && lane == leader);
-            while (todo) {
-                u32 L = __ffs(todo) - 1;
-                todo &= todo - 1;
-                u32 pm = __shfl_sync(full, peers, L);
-                u32 rr = __shfl_sync(full, r, L);
-                // reduce over lanes in pm
-                u32 vqmin = (pm >> lane) & 1 ? a.x : NONE32, vqmax = (pm >> lane) & 1 ? a.y : 0;
-                u32 vtmin = (pm >> lane) & 1 ? a.z : NONE32, vtmax = (pm >> lane) & 1 ? a.w : 0;
-                u64 vsm = (pm >> lane) & 1 ? sm : 0, vsb = (pm >> lane) & 1 ? sbk : 0;
-                vqmin = __reduce_min_sync(full, vqmin); vqmax = __reduce_max_sync(full, vqmax);
-                vtmin = __reduce_min_sync(full, vtmin); vtmax = __reduce_max_sync(full, vtmax);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    vsm += __shfl_down_sync(full, vsm, o);
-                    vsb += __shfl_down_sync(full, vsb, o);
-                }
-                if (lane == 0) {
-                    atomicMin(&cs.qmin[rr], vqmin); atomicMax(&cs.qmax[rr], vqmax);
-                    atomicMin(&cs.tmin[rr], vtmin); atomicMax(&cs.tmax[rr], vtmax);
-                    atomicAdd((unsigned long long *)&cs.sum_matches[rr], (unsigned long long)vsm);
-                    atomicAdd((unsigned long long *)&cs.sum_block[rr], (unsigned long long)vsb);
-                }
-            }
-        }
-        __syncwarp();
     }
 }
 

@@ -330,11 +330,13 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     uint4 *srec = A.take<uint4>(n_m);
     uint2 *srec2 = A.take<uint2>(n_m);
     u32 *gstart = A.take<u32>(n_m + 1);
+    u32 *gid = A.take<u32>(n_m);
     u32 *bsum = A.take<u32>(scan_temp_u32(N));
     u32 *d_tot = A.take<u32>(4);
     scan_apply([=] __device__(u32 p) -> u32 { return (p == 0 || (skey[p] >> cb) != (skey[p - 1] >> cb)) ? 1u : 0u; },
                [=] __device__(u32 p, u32 ex, u32 v) {
                    if (v) gstart[ex] = p;
+                   gid[p] = ex + v - 1;
                    u32 i = sidx[p];
                    srec[p] = make_uint4(in.qs[i], in.qe[i], in.ts[i], in.te[i]);
                    srec2[p] = make_uint2(in.blen[i], in.matches[i]);
@@ -342,17 +344,31 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                n_m, bsum, d_tot, st, lc);
     const u32 n_groups = read_u32(c, d_tot);
 
-    // ---- K3: best-buddy chaining ---------------------------------------------------------------
+    // ---- K3: best-buddy chaining (candidates -> sequential resolve -> aggregates) -------------------
     u64 *bps = A.take<u64>(n_m);
     u32 *root = A.take<u32>(n_m);
+    Cand *cand = A.take<Cand>(n_m);
     ChainSparse cs;
     cs.qmin = A.take<u32>(n_m); cs.qmax = A.take<u32>(n_m); cs.tmin = A.take<u32>(n_m); cs.tmax = A.take<u32>(n_m);
-    cs.sum_matches = A.take<u64>(n_m); cs.sum_block = A.take<u64>(n_m); cs.minidx = A.take<u32>(n_m);
-    SWG_CUDA(cudaMemsetAsync(d_tot + 1, 0, sizeof(u32), st));
+    cs.sum_matches = A.take<u64>(n_m); cs.sum_block = A.take<u64>(n_m); cs.group = A.take<u32>(n_m);
+    cs.grp_minidx = A.take<u32>(n_groups);
+    u8 *grp_has_cand = A.take<u8>(n_groups);
+    u32 *work = A.take<u32>(n_groups);
+    u32 *bb_ctr = A.take<u32>(4); // [0] number of groups to resolve, [1] resolve work counter
+    SWG_CUDA(cudaMemsetAsync(bb_ctr, 0, 4 * sizeof(u32), st));
+    SWG_CUDA(cudaMemsetAsync(grp_has_cand, 0, n_groups, st));
+    SWG_CUDA(cudaMemsetAsync(cs.grp_minidx, 0xFF, sizeof(u32) * (size_t)n_groups, st));
     {
-        u32 blocks = std::min<u32>(cdiv(n_groups, 8), (u32)c->sm_count * 8);
-        k_best_buddy<<<blocks, 256, 0, st>>>(srec, srec2, skey, sidx, gstart, n_groups, n_m, cb, cfg.scaffold_gap, bps, root, cs, d_tot + 1);
+        k_chain_candidates<<<cdiv(n_m, 256), 256, 0, st>>>(srec, skey, gid, n_m, cb, cfg.scaffold_gap, cand, bps, root, grp_has_cand);
         lc.n++;
+        scan_apply([=] __device__(u32 g) -> u32 { return grp_has_cand[g] ? 1u : 0u; },
+                   [=] __device__(u32 g, u32 ex, u32 v) { if (v) work[ex] = g; }, n_groups, bsum, bb_ctr, st, lc);
+        // enough threads to hide the dependent-load latency of a step, few enough that every group's lines stay in L2
+        k_chain_resolve<<<(u32)c->sm_count * 8, 128, 0, st>>>(cand, srec, skey, gstart, n_groups, n_m, work, bb_ctr, cb, cfg.scaffold_gap,
+                                                             bps, root, bb_ctr + 1);
+        k_chain_heads<<<cdiv(n_m, 256), 256, 0, st>>>(srec, srec2, sidx, gid, root, n_m, cs);
+        k_chain_members<<<cdiv(n_m, 256), 256, 0, st>>>(srec, srec2, root, n_m, cs);
+        lc.n += 3;
     }
 
     // ---- K4: dense chain table + mass/identity filter + order key (A,B) ----------------------------
@@ -380,30 +396,37 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         const u32 seqmask = (u32)((1ull << sb) - 1);
         const u32 hmask = hcap - 1;
         launch_for<t_chain_order>(n_m, st, lc, [=] __device__(u32 p) {
-            if (root[p] != p) return;
-            u32 ci = chain_of_pos[p];
-            u64 k = skey[p] >> cb;
-            u8 fwd = (k & 1) == 0;
-            u32 tid = (u32)(k >> 1) & seqmask, qid = (u32)(k >> (1 + sb)) & seqmask;
-            u32 qmin = cs.qmin[p], qmax = cs.qmax[p], tmin = cs.tmin[p], tmax = cs.tmax[p];
-            u64 sm = cs.sum_matches[p], sbk = cs.sum_block[p];
-            u64 total = (u64)(qmax - qmin);                         // paf_filter.rs:896
-            u64 gap = total > sbk ? total - sbk : 0;                // saturating_sub, :901
-            double lg = gap > 0 ? fmax(log((double)gap), 0.0) : 0.0; // :902-906
-            double eff = __dadd_rn((double)sbk, lg);
-            double wid = eff > 0.0 ? __ddiv_rn((double)sm, eff) : 0.0;
-            bool pass = total >= min_len && wid >= min_sid;          // :449-455
-            ct.pos[ci] = p; ct.qid[ci] = qid; ct.tid[ci] = tid; ct.fwd[ci] = fwd;
-            ct.qs[ci] = qmin; ct.qe[ci] = qmax; ct.ts[ci] = tmin; ct.te[ci] = tmax;
-            ct.wid[ci] = wid; ct.pass[ci] = pass ? 1 : 0;
-            u64 ok = NONE64;
-            if (pass) {
-                u32 Aidx = hash_lookup(hk, hv, hmask, ((u64)in.P[qid] << 32) | in.P[tid]);
-                ok = ((u64)Aidx << nb) | cs.minidx[p];
-                atomicAdd((unsigned long long *)&ctr[C_PASS], 1ull);
-                if (qmax == qmin || tmax == tmin) atomicAdd((unsigned long long *)&ctr[C_PASS_ZEROSPAN], 1ull);
+            bool pass = false, zero = false;
+            if (root[p] == p) {
+                u32 ci = chain_of_pos[p];
+                u64 k = skey[p] >> cb;
+                u8 fwd = (k & 1) == 0;
+                u32 tid = (u32)(k >> 1) & seqmask, qid = (u32)(k >> (1 + sb)) & seqmask;
+                u32 qmin = cs.qmin[p], qmax = cs.qmax[p], tmin = cs.tmin[p], tmax = cs.tmax[p];
+                u64 sm = cs.sum_matches[p], sbk = cs.sum_block[p];
+                u64 total = (u64)(qmax - qmin);                         // paf_filter.rs:896
+                u64 gap = total > sbk ? total - sbk : 0;                // saturating_sub, :901
+                double lg = gap > 0 ? fmax(log((double)gap), 0.0) : 0.0; // :902-906
+                double eff = __dadd_rn((double)sbk, lg);
+                double wid = eff > 0.0 ? __ddiv_rn((double)sm, eff) : 0.0;
+                pass = total >= min_len && wid >= min_sid;              // :449-455
+                ct.pos[ci] = p; ct.qid[ci] = qid; ct.tid[ci] = tid; ct.fwd[ci] = fwd;
+                ct.qs[ci] = qmin; ct.qe[ci] = qmax; ct.ts[ci] = tmin; ct.te[ci] = tmax;
+                ct.wid[ci] = wid; ct.pass[ci] = pass ? 1 : 0;
+                u64 ok = NONE64;
+                if (pass) {
+                    u32 Aidx = hash_lookup(hk, hv, hmask, ((u64)in.P[qid] << 32) | in.P[tid]);
+                    ok = ((u64)Aidx << nb) | cs.grp_minidx[cs.group[p]];
+                    zero = qmax == qmin || tmax == tmin;
+                }
+                okey[ci] = ok; oval[ci] = ci;
             }
-            okey[ci] = ok; oval[ci] = ci;
+            u32 am = __activemask();
+            u32 np = __popc(__ballot_sync(am, pass)), nz = __popc(__ballot_sync(am, zero));
+            if ((threadIdx.x & 31) == (u32)(__ffs(am) - 1)) {
+                if (np) atomicAdd((unsigned long long *)&ctr[C_PASS], (unsigned long long)np);
+                if (nz) atomicAdd((unsigned long long *)&ctr[C_PASS_ZEROSPAN], (unsigned long long)nz);
+            }
         });
     }
     sort_pairs(c, okey, okey2, oval, oval2, C, 2 * nb); // stable: ties (same group) keep head-position order
@@ -587,14 +610,8 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     }
 
     // ---- stats ---------------------------------------------------------------------------------
-    launch_for<t_count_kept>(N, st, lc, [=] __device__(u32 i) {
-        u8 s = status[i];
-        u32 m1 = __ballot_sync(__activemask(), s == 1), m2 = __ballot_sync(__activemask(), s == 2);
-        if ((threadIdx.x & 31) == (u32)(__ffs(__activemask()) - 1)) {
-            if (m1) atomicAdd((unsigned long long *)&ctr[C_ANCHORS], (unsigned long long)__popc(m1));
-            if (m2) atomicAdd((unsigned long long *)&ctr[C_RESCUED], (unsigned long long)__popc(m2));
-        }
-    });
+    k_count_status<<<std::min<u32>(cdiv(N, 256), (u32)c->sm_count * 8), 256, 0, st>>>(N, status, ctr);
+    lc.n++;
     read_counters(c);
     S.n_anchors = c->h_ctr[C_ANCHORS];
     S.n_rescued = c->h_ctr[C_RESCUED];
