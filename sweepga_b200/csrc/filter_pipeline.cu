@@ -39,7 +39,7 @@ template <class Tag, class F> static inline void launch_for(u32 n, cudaStream_t 
     k_for<Tag, F><<<cdiv(n, 256), 256, 0, st>>>(n, f);
     lc.n++;
 }
-struct t_iota; struct t_maxp; struct t_scores; struct t_gkey; struct t_events; struct t_chain_order; struct t_tspace; struct t_segfirst;
+struct t_iota; struct t_gather; struct t_maxp; struct t_scores; struct t_gkey; struct t_events; struct t_chain_order; struct t_tspace; struct t_segfirst;
 struct t_segapply; struct t_keys_c2min; struct t_keys_g2min; struct t_final_k; struct t_assign; struct t_invkeys; struct t_invtab;
 struct t_inversion; struct t_anchor_keys; struct t_rescue; struct t_count_kept; struct t_chain_score;
 
@@ -240,7 +240,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     if (cfg.scaffold_gap >= (1ull << 31) || cfg.scaffold_max_deviation >= (1ull << 31))
         throw RangeError{"scaffold_gap / scaffold_max_deviation must be < 2^31"};
 
-    c->arena.reserve((size_t)N * 320 + (64u << 20));
+    c->arena.reserve((size_t)N * 360 + (64u << 20));
     Arena &A = c->arena;
     u64 *ctr = c->d_ctr;
     SWG_CUDA(cudaMemsetAsync(ctr, 0, sizeof(u64) * C_COUNT, st));
@@ -260,7 +260,10 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     u32 *hv = A.take<u32>(hcap);
     SWG_CUDA(cudaMemsetAsync(hk, 0xFF, sizeof(u64) * hcap, st));
     SWG_CUDA(cudaMemsetAsync(hv, 0xFF, sizeof(u32) * hcap, st));
-    k_prefilter<<<cdiv(N, 256), 256, 0, st>>>(in, cfg.min_block_length, cfg.min_identity, cfg.keep_self, flags, ctr, hk, hv, hcap - 1);
+    uint4 *rec4 = nullptr;
+    uint2 *rec2 = nullptr;
+    if (cfg.scaffold_gap != 0) { rec4 = A.take<uint4>(N); rec2 = A.take<uint2>(N); }
+    k_prefilter<<<cdiv(N, 256), 256, 0, st>>>(in, cfg.min_block_length, cfg.min_identity, cfg.keep_self, flags, ctr, hk, hv, hcap - 1, rec4, rec2);
     lc.n++;
     read_counters(c);
     if (c->h_ctr[C_BAD]) throw RangeError{"record with end < start or sequence id >= n_seq"};
@@ -337,11 +340,14 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                [=] __device__(u32 p, u32 ex, u32 v) {
                    if (v) gstart[ex] = p;
                    gid[p] = ex + v - 1;
-                   u32 i = sidx[p];
-                   srec[p] = make_uint4(in.qs[i], in.qe[i], in.ts[i], in.te[i]);
-                   srec2[p] = make_uint2(in.blen[i], in.matches[i]);
                },
                n_m, bsum, d_tot, st, lc);
+    // post-sort gather of the packed records (flat, one thread per position: all gathers of a warp in flight at once)
+    launch_for<t_gather>(n_m, st, lc, [=] __device__(u32 p) {
+        const u32 i = sidx[p];
+        srec[p] = __ldg(&rec4[i]);
+        srec2[p] = __ldg(&rec2[i]);
+    });
     const u32 n_groups = read_u32(c, d_tot);
 
     // ---- K3: best-buddy chaining (candidates -> sequential resolve -> aggregates) -------------------
@@ -364,7 +370,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         scan_apply([=] __device__(u32 g) -> u32 { return grp_has_cand[g] ? 1u : 0u; },
                    [=] __device__(u32 g, u32 ex, u32 v) { if (v) work[ex] = g; }, n_groups, bsum, bb_ctr, st, lc);
         // enough threads to hide the dependent-load latency of a step, few enough that every group's lines stay in L2
-        k_chain_resolve<<<(u32)c->sm_count * 8, 128, 0, st>>>(cand, srec, skey, gstart, n_groups, n_m, work, bb_ctr, cb, cfg.scaffold_gap,
+        k_chain_resolve<<<(u32)c->sm_count * 16, 128, 0, st>>>(cand, srec, skey, gstart, n_groups, n_m, work, bb_ctr, cb, cfg.scaffold_gap,
                                                              bps, root, bb_ctr + 1);
         k_chain_heads<<<cdiv(n_m, 256), 256, 0, st>>>(srec, srec2, sidx, gid, root, n_m, cs);
         k_chain_members<<<cdiv(n_m, 256), 256, 0, st>>>(srec, srec2, root, n_m, cs);
@@ -374,64 +380,60 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     // ---- K4: dense chain table + mass/identity filter + order key (A,B) ----------------------------
     // upper bound on chains is n_m; the table is sized after counting heads
     u32 *chain_of_pos = A.take<u32>(n_m);
+    u32 *head_pos = A.take<u32>(n_m); // compacted head positions (C of them)
     u32 *d_nch = d_tot + 2;
-    {   // count heads first (cheap) so the dense table is sized exactly
-        scan_apply([=] __device__(u32 p) -> u32 { return root[p] == p ? 1u : 0u; },
-                   [=] __device__(u32 p, u32 ex, u32 v) { if (v) chain_of_pos[p] = ex; }, n_m, bsum, d_nch, st, lc);
-    }
+    scan_apply([=] __device__(u32 p) -> u32 { return root[p] == p ? 1u : 0u; },
+               [=] __device__(u32 p, u32 ex, u32 v) { if (v) { chain_of_pos[p] = ex; head_pos[ex] = p; } }, n_m, bsum, d_nch, st, lc);
     const u32 C = read_u32(c, d_nch);
     S.n_chains = C;
     ChainTable ct;
-    ct.pos = A.take<u32>(C); ct.qid = A.take<u32>(C); ct.tid = A.take<u32>(C); ct.fwd = A.take<u8>(C);
+    ct.pos = head_pos; ct.qid = A.take<u32>(C); ct.tid = A.take<u32>(C); ct.fwd = A.take<u8>(C);
     ct.qs = A.take<u32>(C); ct.qe = A.take<u32>(C); ct.ts = A.take<u32>(C); ct.te = A.take<u32>(C);
     ct.wid = A.take<double>(C); ct.pass = A.take<u8>(C); ct.k = A.take<u32>(C);
     SWG_CUDA(cudaMemsetAsync(ct.k, 0, sizeof(u32) * (size_t)C, st));
     const int nb = bits_for(N);
     if (2 * nb > 63) throw RangeError{"too many records for the chain order key"};
-    u64 *okey = A.take<u64>(C), *okey2 = A.take<u64>(C);
-    u32 *oval = A.take<u32>(C), *oval2 = A.take<u32>(C);
+    u64 *okey_all = A.take<u64>(C);
     {
         const u64 min_len = cfg.min_scaffold_length;
         const double min_sid = cfg.min_scaffold_identity;
         const u32 seqmask = (u32)((1ull << sb) - 1);
         const u32 hmask = hcap - 1;
-        launch_for<t_chain_order>(n_m, st, lc, [=] __device__(u32 p) {
-            bool pass = false, zero = false;
-            if (root[p] == p) {
-                u32 ci = chain_of_pos[p];
-                u64 k = skey[p] >> cb;
-                u8 fwd = (k & 1) == 0;
-                u32 tid = (u32)(k >> 1) & seqmask, qid = (u32)(k >> (1 + sb)) & seqmask;
-                u32 qmin = cs.qmin[p], qmax = cs.qmax[p], tmin = cs.tmin[p], tmax = cs.tmax[p];
-                u64 sm = cs.sum_matches[p], sbk = cs.sum_block[p];
-                u64 total = (u64)(qmax - qmin);                         // paf_filter.rs:896
-                u64 gap = total > sbk ? total - sbk : 0;                // saturating_sub, :901
-                double lg = gap > 0 ? fmax(log((double)gap), 0.0) : 0.0; // :902-906
-                double eff = __dadd_rn((double)sbk, lg);
-                double wid = eff > 0.0 ? __ddiv_rn((double)sm, eff) : 0.0;
-                pass = total >= min_len && wid >= min_sid;              // :449-455
-                ct.pos[ci] = p; ct.qid[ci] = qid; ct.tid[ci] = tid; ct.fwd[ci] = fwd;
-                ct.qs[ci] = qmin; ct.qe[ci] = qmax; ct.ts[ci] = tmin; ct.te[ci] = tmax;
-                ct.wid[ci] = wid; ct.pass[ci] = pass ? 1 : 0;
-                u64 ok = NONE64;
-                if (pass) {
-                    u32 Aidx = hash_lookup(hk, hv, hmask, ((u64)in.P[qid] << 32) | in.P[tid]);
-                    ok = ((u64)Aidx << nb) | cs.grp_minidx[cs.group[p]];
-                    zero = qmax == qmin || tmax == tmin;
-                }
-                okey[ci] = ok; oval[ci] = ci;
+        launch_for<t_chain_order>(C, st, lc, [=] __device__(u32 ci) {
+            const u32 p = head_pos[ci];
+            u64 k = skey[p] >> cb;
+            u8 fwd = (k & 1) == 0;
+            u32 tid = (u32)(k >> 1) & seqmask, qid = (u32)(k >> (1 + sb)) & seqmask;
+            u32 qmin = cs.qmin[p], qmax = cs.qmax[p], tmin = cs.tmin[p], tmax = cs.tmax[p];
+            u64 sm = cs.sum_matches[p], sbk = cs.sum_block[p];
+            u64 total = (u64)(qmax - qmin);                         // paf_filter.rs:896
+            u64 gap = total > sbk ? total - sbk : 0;                // saturating_sub, :901
+            double lg = gap > 0 ? fmax(log((double)gap), 0.0) : 0.0; // :902-906
+            double eff = __dadd_rn((double)sbk, lg);
+            double wid = eff > 0.0 ? __ddiv_rn((double)sm, eff) : 0.0;
+            bool pass = total >= min_len && wid >= min_sid;         // :449-455
+            ct.qid[ci] = qid; ct.tid[ci] = tid; ct.fwd[ci] = fwd;
+            ct.qs[ci] = qmin; ct.qe[ci] = qmax; ct.ts[ci] = tmin; ct.te[ci] = tmax;
+            ct.wid[ci] = wid; ct.pass[ci] = pass ? 1 : 0;
+            bool zero = false;
+            if (pass) {
+                u32 Aidx = hash_lookup(hk, hv, hmask, ((u64)in.P[qid] << 32) | in.P[tid]);
+                okey_all[ci] = ((u64)Aidx << nb) | cs.grp_minidx[cs.group[p]];
+                zero = qmax == qmin || tmax == tmin;
             }
             u32 am = __activemask();
-            u32 np = __popc(__ballot_sync(am, pass)), nz = __popc(__ballot_sync(am, zero));
-            if ((threadIdx.x & 31) == (u32)(__ffs(am) - 1)) {
-                if (np) atomicAdd((unsigned long long *)&ctr[C_PASS], (unsigned long long)np);
-                if (nz) atomicAdd((unsigned long long *)&ctr[C_PASS_ZEROSPAN], (unsigned long long)nz);
-            }
+            u32 nz = __popc(__ballot_sync(am, zero));
+            if (nz && (threadIdx.x & 31) == (u32)(__ffs(am) - 1)) atomicAdd((unsigned long long *)&ctr[C_PASS_ZEROSPAN], (unsigned long long)nz);
         });
     }
-    sort_pairs(c, okey, okey2, oval, oval2, C, 2 * nb); // stable: ties (same group) keep head-position order
+    // only the chains that pass the mass/identity filter take part in the ordering
+    u64 *okey = A.take<u64>(C), *okey2 = A.take<u64>(C);
+    u32 *oval = A.take<u32>(C), *oval2 = A.take<u32>(C);
+    scan_apply([=] __device__(u32 ci) -> u32 { return ct.pass[ci] ? 1u : 0u; },
+               [=] __device__(u32 ci, u32 ex, u32 v) { if (v) { okey[ex] = okey_all[ci]; oval[ex] = ci; } }, C, bsum, d_tot + 3, st, lc);
+    const u32 C1 = read_u32(c, d_tot + 3);
+    sort_pairs(c, okey, okey2, oval, oval2, C1, 2 * nb); // stable: ties (same group) keep head-position order
     read_counters(c);
-    const u32 C1 = (u32)c->h_ctr[C_PASS];
     const u64 pass_zero = c->h_ctr[C_PASS_ZEROSPAN];
     S.n_chains_after_mass = C1;
 
@@ -540,11 +542,19 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             const u64 G = cfg.scaffold_gap;
             const u64 *ikc = ik;
             const u32 *ivc = iv;
-            launch_for<t_inversion>(N, st, lc, [=] __device__(u32 i) {
-                if (!(flags[i] & F_ALIVE) || in.strand[i] == '+' || status[i] != 0) return;
+            // compact the candidates first (reverse-strand, alive, not yet an anchor): the binary searches then run
+            // in dense warps instead of stalling every warp that holds a single candidate
+            u32 *inv_list = A.take<u32>(N);
+            u32 *d_ninv = A.take<u32>(1);
+            scan_apply([=] __device__(u32 i) -> u32 { return ((flags[i] & F_ALIVE) && in.strand[i] != '+' && status[i] == 0) ? 1u : 0u; },
+                       [=] __device__(u32 i, u32 ex, u32 v) { if (v) inv_list[ex] = i; }, N, bsum, d_ninv, st, lc);
+            launch_for<t_inversion>(N, st, lc, [=] __device__(u32 x0) {
+                if (x0 >= *d_ninv) return;
+                const u32 i = inv_list[x0];
                 u64 key = ((u64)in.qid[i] << sb) | in.tid[i];
                 u32 lo = 0, hi = Cf;
                 while (lo < hi) { u32 mid = (lo + hi) >> 1; if (ikc[mid] < key) lo = mid + 1; else hi = mid; }
+                if (lo >= Cf || ikc[lo] != key) return;
                 u64 mqs = in.qs[i], mqe = in.qe[i], mts = in.ts[i], mte = in.te[i];
                 u64 qc = (mqs + mqe) / 2, tc = (mts + mte) / 2;
                 for (u32 x = lo; x < Cf && ikc[x] == key; x++) {

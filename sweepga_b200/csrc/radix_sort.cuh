@@ -26,6 +26,7 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ITEMS = 12;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS; // 6144 pairs
 constexpr int RS_MAX_PASSES = 8;
+constexpr int RS_LOOKBACK = 8; // predecessor tiles inspected per look-back round (independent loads in flight)
 
 constexpr u32 RS_FLAG_AGG = 1u << 30;  // tile aggregate available
 constexpr u32 RS_FLAG_INCL = 2u << 30; // inclusive prefix available
@@ -91,52 +92,59 @@ struct RsSmem {
     u32 tile;
 };
 
-__global__ void __launch_bounds__(RS_THREADS, 2)
-rs_onesweep_kernel(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out, const u32 *__restrict__ vals_in,
-                   u32 *__restrict__ vals_out, u32 n, int shift, const u32 *__restrict__ digit_base,
-                   u32 *tile_status /*[tiles][256]*/, u32 *tile_counter) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    RsSmem &s = *reinterpret_cast<RsSmem *>(smem_raw);
+template <bool FULL>
+__device__ __forceinline__ void rs_onesweep_tile(RsSmem &s, const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out,
+                                                 const u32 *__restrict__ vals_in, u32 *__restrict__ vals_out, u32 n, int shift,
+                                                 const u32 *__restrict__ digit_base, u32 *tile_status, u32 tile) {
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    if (tid == 0) s.tile = atomicAdd(tile_counter, 1u); // in-order tile ids: look-back never waits on an unscheduled tile
-    for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&s.warp_hist[0][0])[i] = 0;
-    __syncthreads();
-    const u32 tile = s.tile;
     const u64 tile_base = (u64)tile * RS_TILE;
     const u64 warp_base = tile_base + (u64)warp * (32 * RS_ITEMS);
+    const u32 warp_n = FULL ? 32 * RS_ITEMS : (u32)min((u64)(32 * RS_ITEMS), n > warp_base ? (u64)n - warp_base : (u64)0);
 
     u64 key[RS_ITEMS];
     u32 val[RS_ITEMS];
     u32 rnk[RS_ITEMS];
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
-        u64 idx = warp_base + i * 32 + lane;
-        bool ok = idx < n;
-        key[i] = ok ? keys_in[idx] : NONE64;
-        val[i] = ok ? vals_in[idx] : 0u;
+        const bool ok = FULL || (u32)(i * 32 + lane) < warp_n;
+        key[i] = ok ? keys_in[warp_base + i * 32 + lane] : NONE64;
     }
-    // warp-level multi-split ranking (stable: items ascending, lanes ascending)
+    // warp-level multi-split ranking (stable: items ascending, lanes ascending).
+    // pass A: all the match_any's back to back (independent); pass B: the sequential warp-histogram update.
     const u32 lt = lanemask_lt();
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
-        bool ok = (warp_base + i * 32 + lane) < n;
-        u32 d = (u32)(key[i] >> shift) & (RS_RADIX - 1);
-        u32 peers = __match_any_sync(0xFFFFFFFFu, ok ? d : (0x100u | lane));
-        u32 leader = __ffs(peers) - 1;
+        const bool ok = FULL || (u32)(i * 32 + lane) < warp_n;
+        const u32 d = (u32)(key[i] >> shift) & (RS_RADIX - 1);
+        const u32 peers = __match_any_sync(0xFFFFFFFFu, ok ? d : (0x100u | lane));
+        // leader (5 bits) | run length (6 bits) | rank inside the run (5 bits)
+        rnk[i] = (u32)(__ffs(peers) - 1) | ((u32)__popc(peers) << 8) | ((u32)__popc(peers & lt) << 16);
+    }
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+        const bool ok = FULL || (u32)(i * 32 + lane) < warp_n;
+        const u32 d = (u32)(key[i] >> shift) & (RS_RADIX - 1);
+        const u32 leader = rnk[i] & 31;
         u32 prev = 0;
         if (lane == leader && ok) {
             prev = s.warp_hist[warp][d];
-            s.warp_hist[warp][d] = prev + __popc(peers);
+            s.warp_hist[warp][d] = prev + ((rnk[i] >> 8) & 63);
         }
         prev = __shfl_sync(0xFFFFFFFFu, prev, leader);
-        rnk[i] = prev + __popc(peers & lt);
+        rnk[i] = prev + (rnk[i] >> 16);
         __syncwarp();
+    }
+    // payloads are only needed for staging: issue their loads now so the latency hides behind the scans/barriers
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+        const bool ok = FULL || (u32)(i * 32 + lane) < warp_n;
+        val[i] = ok ? vals_in[warp_base + i * 32 + lane] : 0u;
     }
     __syncthreads();
 
-    // per digit: exclusive scan over warps, tile count; then exclusive scan over digits
+    // per digit: exclusive scan over warps, tile count
     u32 count = 0;
+    u32 *my_status = tile_status + (u64)tile * RS_RADIX + tid;
     if (tid < RS_RADIX) {
 #pragma unroll
         for (int w = 0; w < RS_WARPS; w++) {
@@ -144,7 +152,10 @@ rs_onesweep_kernel(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out, 
             s.warp_hist[w][tid] = count;
             count += t;
         }
+        // publish the tile aggregate as early as possible: successors' look-backs can pass over this tile
+        st_volatile_u32(my_status, (tile == 0 ? RS_FLAG_INCL : RS_FLAG_AGG) | count);
     }
+    // exclusive scan over digits (tile-local run offsets)
     {
         u32 x = count;
 #pragma unroll
@@ -160,30 +171,12 @@ rs_onesweep_kernel(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out, 
             s.digit_excl[tid] = base + x - count;
         }
     }
-    // decoupled look-back, one thread per digit
-    if (tid < RS_RADIX) {
-        u32 *my = tile_status + (u64)tile * RS_RADIX + tid;
-        u32 excl = 0;
-        if (tile == 0) {
-            st_volatile_u32(my, RS_FLAG_INCL | count);
-        } else {
-            st_volatile_u32(my, RS_FLAG_AGG | count);
-            i64 t = (i64)tile - 1;
-            while (true) {
-                u32 v = ld_volatile_u32(tile_status + (u64)t * RS_RADIX + tid);
-                if (v & RS_FLAG_INCL) { excl += v & RS_VAL_MASK; break; }
-                if (v & RS_FLAG_AGG) { excl += v & RS_VAL_MASK; t--; }
-            }
-            st_volatile_u32(my, RS_FLAG_INCL | (excl + count));
-        }
-        s.global_base[tid] = digit_base[tid] + excl - s.digit_excl[tid];
-    }
     __syncthreads();
 
-    // stage in digit order
+    // stage in digit order (needs only tile-local offsets; hides the latency of the predecessors' publishing)
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
-        bool ok = (warp_base + i * 32 + lane) < n;
+        const bool ok = FULL || (u32)(i * 32 + lane) < warp_n;
         if (ok) {
             u32 d = (u32)(key[i] >> shift) & (RS_RADIX - 1);
             u32 pos = s.digit_excl[d] + s.warp_hist[warp][d] + rnk[i];
@@ -191,16 +184,64 @@ rs_onesweep_kernel(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out, 
             s.stage_v[pos] = val[i];
         }
     }
-    __syncthreads();
-    const u32 tile_n = (u32)min((u64)RS_TILE, (u64)n - tile_base);
-#pragma unroll 4
-    for (u32 j = tid; j < tile_n; j += RS_THREADS) {
-        u64 k = s.stage_k[j];
-        u32 d = (u32)(k >> shift) & (RS_RADIX - 1);
-        u32 g = s.global_base[d] + j;
-        keys_out[g] = k;
-        vals_out[g] = s.stage_v[j];
+
+    // decoupled look-back, one thread per digit, RS_LOOKBACK predecessors in flight per round
+    if (tid < RS_RADIX) {
+        u32 excl = 0;
+        if (tile != 0) {
+            i64 t = (i64)tile - 1;
+            bool done = false;
+            while (!done) {
+                u32 v[RS_LOOKBACK];
+#pragma unroll
+                for (int k = 0; k < RS_LOOKBACK; k++)
+                    v[k] = (t - k >= 0) ? ld_volatile_u32(tile_status + (u64)(t - k) * RS_RADIX + tid) : RS_FLAG_INCL;
+#pragma unroll
+                for (int k = 0; k < RS_LOOKBACK; k++) {
+                    if (done) break;
+                    if (v[k] & RS_FLAG_INCL) { excl += v[k] & RS_VAL_MASK; done = true; }
+                    else if (v[k] & RS_FLAG_AGG) { excl += v[k] & RS_VAL_MASK; t--; }
+                    else break; // not published yet: poll again from this tile
+                }
+            }
+            st_volatile_u32(my_status, RS_FLAG_INCL | (excl + count));
+        }
+        s.global_base[tid] = digit_base[tid] + excl - s.digit_excl[tid];
     }
+    __syncthreads();
+    const u32 tile_n = FULL ? RS_TILE : (u32)min((u64)RS_TILE, (u64)n - tile_base);
+    if (FULL) {
+#pragma unroll
+        for (int it = 0; it < RS_ITEMS; it++) {
+            const u32 j = it * RS_THREADS + tid;
+            const u64 k = s.stage_k[j];
+            const u32 g = s.global_base[(u32)(k >> shift) & (RS_RADIX - 1)] + j;
+            keys_out[g] = k;
+            vals_out[g] = s.stage_v[j];
+        }
+    } else {
+        for (u32 j = tid; j < tile_n; j += RS_THREADS) {
+            const u64 k = s.stage_k[j];
+            const u32 g = s.global_base[(u32)(k >> shift) & (RS_RADIX - 1)] + j;
+            keys_out[g] = k;
+            vals_out[g] = s.stage_v[j];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS, 2)
+rs_onesweep_kernel(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out, const u32 *__restrict__ vals_in,
+                   u32 *__restrict__ vals_out, u32 n, int shift, const u32 *__restrict__ digit_base,
+                   u32 *tile_status /*[tiles][256]*/, u32 *tile_counter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RsSmem &s = *reinterpret_cast<RsSmem *>(smem_raw);
+    const u32 tid = threadIdx.x;
+    if (tid == 0) s.tile = atomicAdd(tile_counter, 1u); // in-order tile ids: look-back never waits on an unscheduled tile
+    for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&s.warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const u32 tile = s.tile;
+    if ((u64)(tile + 1) * RS_TILE <= (u64)n) rs_onesweep_tile<true>(s, keys_in, keys_out, vals_in, vals_out, n, shift, digit_base, tile_status, tile);
+    else rs_onesweep_tile<false>(s, keys_in, keys_out, vals_in, vals_out, n, shift, digit_base, tile_status, tile);
 }
 
 // ---- host driver --------------------------------------------------------------------------
