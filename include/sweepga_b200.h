@@ -174,6 +174,15 @@ int swg_upload(swg_ctx *ctx, const swg_mappings *host_in, swg_mappings *dev_out,
 void swg_release(swg_ctx *ctx, swg_mappings *dev, swg_result *dev_res);
 int swg_download_result(swg_ctx *ctx, uint64_t n, const swg_result *dev_res, swg_result *host_out);
 
+/* Order keys of the chains kept by the LAST swg_filter / swg_filter_device call on this context, for merging the
+ * chain numbering of genome-pair shards filtered on different GPUs: entry k-1 describes chain_k by the input index
+ * of the first stage-1 record of its genome pair (A) and of the first kept record of its (query,target,strand) group
+ * (B), both taken from the FIRST filtered chain of the chain's genome-pair group (order O3).
+ * Sorting all shards' chains by (global index of A, global index of B, shard-local k) reproduces the single-GPU
+ * numbering.  cap = capacity of the two arrays; *n_chains receives the count.                                  */
+int swg_last_chain_keys(swg_ctx *ctx, uint64_t cap, uint32_t *first_index_genome_pair, uint32_t *first_index_group,
+                        uint64_t *n_chains);
+
 /* ---- primitives: plane_sweep_exact.rs:268-461 --------------------------- *
  * keep[i] = 1 iff local index i is in the Vec<usize> the reference returns.
  * n_keep = SWG_KEEP_ALL for usize::MAX.  HOST buffers.                          */

@@ -291,6 +291,7 @@ struct Chain { // MergedChain, paf_filter.rs:142-155
     double weighted_identity;
     uint64_t sum_matches, sum_block;
     std::vector<size_t> members; // ranks
+    size_t B = 0;                // first member (in M order) of the chain's (q,t,strand) group: its first-appearance key
 };
 
 struct Tables {
@@ -385,6 +386,7 @@ static std::vector<Chain> merge_into_chains(const std::vector<Rec> &md, uint64_t
         for (auto &set : uf.get_sets()) {
             if (set.empty()) continue;
             Chain c;
+            c.B = md[g.second[0]].rank;
             c.qid = (uint32_t)g.first.first.first; c.tid = (uint32_t)g.first.first.second; c.fwd = fwd;
             uint64_t qmin = ~(uint64_t)0, qmax = 0, tmin = ~(uint64_t)0, tmax = 0, sm = 0, sb = 0;
             for (size_t k : set) { // :875-894
@@ -434,7 +436,7 @@ struct Stats { uint64_t v[10]; };
 
 // apply_filters, paf_filter.rs:379-747.  status/chain are indexed like the input table.
 static void apply_filters(const std::vector<Rec> &input, const swg_config &cfg, const Tables &tb,
-                          uint8_t *status, uint32_t *chain_out, swg_stats *st) {
+                          uint8_t *status, uint32_t *chain_out, swg_stats *st, uint32_t *keyA = nullptr, uint32_t *keyB = nullptr) {
     size_t n_in = input.size();
     for (size_t i = 0; i < n_in; i++) { status[i] = SWG_DROPPED; chain_out[i] = 0; }
     std::vector<Rec> md; // :384-388
@@ -459,6 +461,20 @@ static void apply_filters(const std::vector<Rec> &input, const swg_config &cfg, 
     for (const Chain &c : filtered) for (size_t r : c.members) pre_members.insert(r);
     {
         std::vector<size_t> kept = scaffold_sweep(filtered, cfg, tb); // :478
+        if (keyA && keyB) {
+            // merge keys for multi-shard numbering (not part of the reference): per kept chain, the first-appearance
+            // indices (A: genome pair over the stage-1 records, B: group over M) of the first filtered chain of its
+            // genome-pair group (plane_sweep_scaffold.rs:116-130 iteration order)
+            std::unordered_map<Key2, size_t, PairHash> firstA;
+            for (const Rec &m : all_orig) firstA.emplace(Key2{tb.P[m.qid], tb.P[m.tid]}, m.rank);
+            std::unordered_map<Key2, size_t, PairHash> g2first;
+            for (size_t i = 0; i < filtered.size(); i++) g2first.emplace(Key2{tb.P2[filtered[i].qid], tb.P2[filtered[i].tid]}, i);
+            for (size_t k = 0; k < kept.size(); k++) {
+                const Chain &f = filtered[g2first[Key2{tb.P2[filtered[kept[k]].qid], tb.P2[filtered[kept[k]].tid]}]];
+                keyA[k] = (uint32_t)firstA[Key2{tb.P[f.qid], tb.P[f.tid]}];
+                keyB[k] = (uint32_t)f.B;
+            }
+        }
         std::vector<Chain> k2;
         for (size_t i : kept) k2.push_back(filtered[i]);
         filtered.swap(k2);
@@ -669,14 +685,14 @@ int orc_apply_filters(const swg_config *cfg, uint64_t n, const uint32_t *qid, co
                       const uint64_t *qs, const uint64_t *qe, const uint64_t *ts, const uint64_t *te,
                       const uint64_t *blen, const uint64_t *matches, const double *identity,
                       const uint8_t *strand, const uint32_t *seq_P, const uint32_t *seq_P2,
-                      uint8_t *status, uint32_t *chain_id, swg_stats *stats) {
+                      uint8_t *status, uint32_t *chain_id, swg_stats *stats, uint32_t *chain_keyA, uint32_t *chain_keyB) {
     std::vector<orc::Rec> in(n);
     for (uint64_t i = 0; i < n; i++)
         in[i] = {(size_t)i, qid[i], tid[i], qs[i], qe[i], ts[i], te[i], blen[i], matches[i], identity[i], strand[i] == '+'};
     orc::Tables tb{seq_P, seq_P2};
     swg_stats local;
     std::memset(&local, 0, sizeof local);
-    orc::apply_filters(in, *cfg, tb, status, chain_id, &local);
+    orc::apply_filters(in, *cfg, tb, status, chain_id, &local, chain_keyA, chain_keyB);
     if (stats) *stats = local;
     return 0;
 }
@@ -762,7 +778,7 @@ int orc_filter_paf(const swg_config *cfg, const char *in_path, const char *out_p
     std::vector<uint32_t> chain(n);
     orc_apply_filters(cfg, n, p->qid.data(), p->tid.data(), p->qs.data(), p->qe.data(), p->ts.data(), p->te.data(),
                       p->blen.data(), p->matches.data(), p->identity.data(), p->strand.data(), p->P.data(), p->P2.data(),
-                      status.data(), chain.data(), stats);
+                      status.data(), chain.data(), stats, nullptr, nullptr);
     int rc = orc_paf_write(p, out_path, status.data(), chain.data());
     delete p;
     return rc;

@@ -321,6 +321,17 @@ class Context:
         self._check(lib.swg_download_result(self._h, n, C.byref(dres), C.byref(res)))
         return status, chain_id
 
+    def last_chain_keys(self):
+        """Order keys (A, B) of the chains kept by the last filter call on this context (swg_last_chain_keys)."""
+        n = C.c_uint64()
+        lib.swg_last_chain_keys(self._h, 0, None, None, C.byref(n))  # cap 0: only the count is reported
+        k = int(n.value)
+        if k == 0:
+            return np.zeros(0, np.uint32), np.zeros(0, np.uint32)
+        a, b = np.zeros(k, np.uint32), np.zeros(k, np.uint32)
+        self._check(lib.swg_last_chain_keys(self._h, k, _ptr(a, C.c_uint32), _ptr(b, C.c_uint32), C.byref(n)))
+        return a, b
+
     def release(self, dev, dres):
         lib.swg_release(self._h, C.byref(dev), C.byref(dres))
 

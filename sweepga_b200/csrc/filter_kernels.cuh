@@ -254,6 +254,9 @@ k_chain_resolve(const Cand *__restrict__ cand, const uint4 *__restrict__ srec, c
     const u32 n_work = *n_work_ptr;
     bool active = false, exhausted = false, fwd = true;
     u32 e = 0, i = 0;
+    Cand c_cur{0, NONE32, 0}, c_next{0, NONE32, 0};
+    u64 b_cur = 0;
+    u32 r_cur = 0;
     while (true) {
         const u32 need = __ballot_sync(full, !active && !exhausted);
         if (need) {
@@ -270,17 +273,26 @@ k_chain_resolve(const Cand *__restrict__ cand, const uint4 *__restrict__ srec, c
                     e = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
                     fwd = ((skey[i] >> cb) & 1) == 0;
                     active = true;
+                    c_cur = cand[i];
+                    c_next = (i + 1 < e) ? cand[i + 1] : Cand{0, NONE32, 0};
+                    b_cur = (c_cur.j != NONE32) ? bps[c_cur.j] : 0;
+                    r_cur = i; // the first position of a group has no predecessor
                 }
             }
         }
         if (__all_sync(full, exhausted && !active)) break;
         if (active) {
-            const Cand c = cand[i];
-            if (c.j != NONE32) {
-                const u32 ri = root[i]; // final: every possible predecessor of i has been processed
-                if (c.d < bps[c.j]) { // the unconstrained arg-min is eligible => it is the reference's pick
-                    bps[c.j] = c.d;
-                    root[c.j] = ri;
+            // software pipeline: the loads of step i+1 (its candidate, that candidate's best_pred_score, its
+            // root) are issued before step i is decided; step i's own store is forwarded in registers.
+            const Cand c_nn = (i + 2 < e) ? cand[i + 2] : Cand{0, NONE32, 0}; // two steps ahead: its address is free
+            u64 b_next = (c_next.j != NONE32) ? bps[c_next.j] : 0;             // c_next was loaded one step ago
+            u32 r_next = (i + 1 < e) ? root[i + 1] : 0;
+            u32 chosen = NONE32;
+            u64 chosen_d = 0;
+            if (c_cur.j != NONE32) {
+                if (c_cur.d < b_cur) { // the unconstrained arg-min is eligible => it is the reference's pick
+                    chosen = c_cur.j;
+                    chosen_d = c_cur.d;
                 } else { // blocked: arg-min over the eligible candidates (paf_filter.rs:835-843)
                     const uint4 a = srec[i];
                     const u64 bound = (u64)a.y + G;
@@ -292,9 +304,20 @@ k_chain_resolve(const Cand *__restrict__ cand, const uint4 *__restrict__ srec, c
                         u64 d;
                         if (bb_candidate(a, b, fwd, G, G5, d) && d < bd && d < bps[j]) { bd = d; bj = j; }
                     }
-                    if (bj != NONE32) { bps[bj] = bd; root[bj] = ri; }
+                    chosen = bj;
+                    chosen_d = bd;
+                }
+                if (chosen != NONE32) {
+                    bps[chosen] = chosen_d;
+                    root[chosen] = r_cur;
+                    if (chosen == c_next.j) b_next = chosen_d; // supersedes the value prefetched above
+                    if (chosen == i + 1) r_next = r_cur;
                 }
             }
+            c_cur = c_next;
+            c_next = c_nn;
+            b_cur = b_next;
+            r_cur = r_next;
             if (++i == e) active = false;
         }
     }

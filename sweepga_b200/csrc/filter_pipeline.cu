@@ -13,6 +13,7 @@
 //   K6  inversion capture                                paf_filter.rs:535-597
 //   K7  rescue                                           paf_filter.rs:613-732
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -104,6 +105,8 @@ struct swg_ctx {
     cudaEvent_t ev_sort[2] = {nullptr, nullptr}; // bracket the one-sweep passes of the record sort
     int sort_passes = 0;
     u64 sort_pairs = 0;
+    const u32 *last_keyA = nullptr, *last_keyB = nullptr; // order keys of the kept chains of the last call (arena memory)
+    u64 last_n_chains = 0;
     Arena arena;      // per-call scratch
     Arena io;         // staging of host SoA for swg_filter
     u64 *h_ctr = nullptr; // pinned mirror of the counters
@@ -225,6 +228,8 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     SWG_CUDA(cudaMemsetAsync(chain_id, 0, sizeof(u32) * (size_t)N, st));
     c->sort_passes = 0;
     c->sort_pairs = 0;
+    c->last_n_chains = 0;
+    c->last_keyA = c->last_keyB = nullptr;
     auto finish = [&]() {
         S.gpu_launches = lc.n - launches0;
         if (c->sort_passes) { // all work has been synchronised by the last counter read
@@ -370,7 +375,8 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         scan_apply([=] __device__(u32 g) -> u32 { return grp_has_cand[g] ? 1u : 0u; },
                    [=] __device__(u32 g, u32 ex, u32 v) { if (v) work[ex] = g; }, n_groups, bsum, bb_ctr, st, lc);
         // enough threads to hide the dependent-load latency of a step, few enough that every group's lines stay in L2
-        k_chain_resolve<<<(u32)c->sm_count * 16, 128, 0, st>>>(cand, srec, skey, gstart, n_groups, n_m, work, bb_ctr, cb, cfg.scaffold_gap,
+        static const int resolve_mult = getenv("SWG_RESOLVE_MULT") ? atoi(getenv("SWG_RESOLVE_MULT")) : 4;
+        k_chain_resolve<<<(u32)c->sm_count * resolve_mult, 128, 0, st>>>(cand, srec, skey, gstart, n_groups, n_m, work, bb_ctr, cb, cfg.scaffold_gap,
                                                              bps, root, bb_ctr + 1);
         k_chain_heads<<<cdiv(n_m, 256), 256, 0, st>>>(srec, srec2, sidx, gid, root, n_m, cs);
         k_chain_members<<<cdiv(n_m, 256), 256, 0, st>>>(srec, srec2, root, n_m, cs);
@@ -504,9 +510,23 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         fin_t = sv;
         {
             const u32 *fin = sv;
-            launch_for<t_final_k>(C2, st, lc, [=] __device__(u32 u) { ct.k[oc_chain[fin[u]]] = u + 1; });
+            // chain number + the order key of its genome-pair group (first-appearance indices A, B of the group's first
+            // filtered chain): what a multi-GPU driver needs to merge the per-shard numberings (swg_last_chain_keys)
+            u32 *keyA = A.take<u32>(C2 + 1), *keyB = A.take<u32>(C2 + 1);
+            const u64 *okc = okey;
+            const u64 bmask = (1ull << nb) - 1;
+            launch_for<t_final_k>(C2, st, lc, [=] __device__(u32 u) {
+                const u32 t = fin[u];
+                ct.k[oc_chain[t]] = u + 1;
+                const u64 gk = okc[g2min[t]];
+                keyA[u] = (u32)(gk >> nb);
+                keyB[u] = (u32)(gk & bmask);
+            });
+            c->last_keyA = keyA;
+            c->last_keyB = keyB;
         }
     }
+    c->last_n_chains = C2;
     S.n_chains_kept = C2;
 
     // ---- K5: anchors = members of kept chains (paf_filter.rs:517-528) ---------------------------------
@@ -885,6 +905,21 @@ int swg_download_result(swg_ctx *c, uint64_t n, const swg_result *dev_res, swg_r
         SWG_CUDA(cudaSetDevice(a->c->device));
         SWG_CUDA(cudaMemcpyAsync(a->h->status, a->d->status, a->n, cudaMemcpyDeviceToHost, a->c->stream));
         SWG_CUDA(cudaMemcpyAsync(a->h->chain_id, a->d->chain_id, a->n * 4, cudaMemcpyDeviceToHost, a->c->stream));
+        SWG_CUDA(cudaStreamSynchronize(a->c->stream));
+    }, &a);
+}
+
+int swg_last_chain_keys(swg_ctx *c, uint64_t cap, uint32_t *first_index_genome_pair, uint32_t *first_index_group, uint64_t *n_chains) {
+    if (!c || !n_chains) return SWG_ERR_ARG;
+    *n_chains = c->last_n_chains;
+    if (c->last_n_chains == 0) return SWG_OK;
+    if (cap < c->last_n_chains || !first_index_genome_pair || !first_index_group || !c->last_keyA) return SWG_ERR_ARG;
+    struct Args { swg_ctx *c; uint32_t *a, *b; } a{c, first_index_genome_pair, first_index_group};
+    return guarded(c, "swg_last_chain_keys", [](void *p) {
+        Args *a = (Args *)p;
+        SWG_CUDA(cudaSetDevice(a->c->device));
+        SWG_CUDA(cudaMemcpyAsync(a->a, a->c->last_keyA, a->c->last_n_chains * 4, cudaMemcpyDeviceToHost, a->c->stream));
+        SWG_CUDA(cudaMemcpyAsync(a->b, a->c->last_keyB, a->c->last_n_chains * 4, cudaMemcpyDeviceToHost, a->c->stream));
         SWG_CUDA(cudaStreamSynchronize(a->c->stream));
     }, &a);
 }

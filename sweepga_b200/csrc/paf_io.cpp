@@ -405,16 +405,33 @@ int swg_filter_file(swg_ctx *ctx, const swg_config *cfg, const char *in_path, co
     return swg_filter_paf(ctx, &c2, in_path, out_path, stats);
 }
 
-// Size-balanced assignment of genome-pair units to shards (LPT greedy).
+// Size-balanced assignment of genome-pair units to shards (LPT greedy).  A unit must be closed under every grouping
+// of the filter: (P(q),P(t)) for the primary sweep and (P2(q),P2(t)) for the scaffold sweep / chain numbering, so
+// sequences are first merged into classes that share a P id OR a P2 id (for 3-field PanSN names P == P2).
 int swg_shard_plan(const swg_mappings *m, int n_shards, uint32_t *shard_of, uint64_t *shard_sizes) {
     if (!m || n_shards < 1 || (m->n && !shard_of)) return SWG_ERR_ARG;
+    const uint32_t ns = m->n_seq;
+    std::vector<uint32_t> cls(ns);
+    {
+        std::vector<uint32_t> parent(ns);
+        for (uint32_t i = 0; i < ns; i++) parent[i] = i;
+        auto find = [&](uint32_t x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+        std::unordered_map<uint32_t, uint32_t> firstP, firstP2;
+        for (uint32_t i = 0; i < ns; i++) {
+            auto a = firstP.emplace(m->seq_genome_id[i], i);
+            if (!a.second) parent[find(i)] = find(a.first->second);
+            auto b = firstP2.emplace(m->seq_genome2_id[i], i);
+            if (!b.second) parent[find(i)] = find(b.first->second);
+        }
+        for (uint32_t i = 0; i < ns; i++) cls[i] = find(i);
+    }
     std::unordered_map<uint64_t, uint32_t> unit_id;
     std::vector<uint64_t> unit_size;
     std::vector<uint32_t> unit_of(m->n);
     for (uint64_t i = 0; i < m->n; i++) {
         uint32_t q = m->query_id[i], t = m->target_id[i];
-        if (q >= m->n_seq || t >= m->n_seq) return SWG_ERR_RANGE;
-        uint64_t key = ((uint64_t)m->seq_genome_id[q] << 32) | m->seq_genome_id[t];
+        if (q >= ns || t >= ns) return SWG_ERR_RANGE;
+        uint64_t key = ((uint64_t)cls[q] << 32) | cls[t];
         auto it = unit_id.find(key);
         uint32_t u;
         if (it == unit_id.end()) { u = (uint32_t)unit_size.size(); unit_id.emplace(key, u); unit_size.push_back(0); }

@@ -16,7 +16,7 @@ from sweepga_b200._lib import swg_config, swg_stats  # POD layouts only
 u8p, u32p, u64p, f64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_double)
 _lib.orc_apply_filters.restype = C.c_int
 _lib.orc_apply_filters.argtypes = [C.POINTER(swg_config), C.c_uint64, u32p, u32p, u64p, u64p, u64p, u64p, u64p, u64p, f64p, u8p,
-                                   u32p, u32p, u8p, u32p, C.POINTER(swg_stats)]
+                                   u32p, u32p, u8p, u32p, C.POINTER(swg_stats), u32p, u32p]
 _lib.orc_plane_sweep.restype = C.c_int
 _lib.orc_plane_sweep.argtypes = [C.c_int, C.c_uint64, u64p, u64p, u64p, u64p, f64p, C.c_uint64, C.c_uint64, C.c_double, C.c_int, u8p]
 _lib.orc_score.restype = C.c_double
@@ -51,8 +51,8 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
-def apply_filters(cfg, table):
-    """Oracle apply_filters on a sweepga_b200.MappingTable -> (status u8[n], chain_id u32[n], stats)."""
+def apply_filters(cfg, table, with_chain_keys=False):
+    """Oracle apply_filters on a sweepga_b200.MappingTable -> (status u8[n], chain_id u32[n], stats[, keyA, keyB])."""
     n = table.n
     c = cfg.to_c()
     a64 = lambda x: np.ascontiguousarray(x, dtype=np.uint64)
@@ -60,10 +60,15 @@ def apply_filters(cfg, table):
     bl, mt = a64(table.block_length), a64(table.matches)
     status, chain = np.zeros(n, np.uint8), np.zeros(n, np.uint32)
     st = swg_stats()
+    kA = np.zeros(n + 1, np.uint32) if with_chain_keys else None
+    kB = np.zeros(n + 1, np.uint32) if with_chain_keys else None
     _lib.orc_apply_filters(C.byref(c), n, _p(table.query_id, C.c_uint32), _p(table.target_id, C.c_uint32), _p(qs, C.c_uint64),
                            _p(qe, C.c_uint64), _p(ts, C.c_uint64), _p(te, C.c_uint64), _p(bl, C.c_uint64), _p(mt, C.c_uint64),
                            _p(table.identity, C.c_double), _p(table.strand, C.c_uint8), _p(table.seq_genome_id, C.c_uint32),
-                           _p(table.seq_genome2_id, C.c_uint32), _p(status, C.c_uint8), _p(chain, C.c_uint32), C.byref(st))
+                           _p(table.seq_genome2_id, C.c_uint32), _p(status, C.c_uint8), _p(chain, C.c_uint32), C.byref(st),
+                           _p(kA, C.c_uint32) if with_chain_keys else None, _p(kB, C.c_uint32) if with_chain_keys else None)
+    if with_chain_keys:
+        return status, chain, st, kA[: st.n_chains_kept], kB[: st.n_chains_kept]
     return status, chain, st
 
 
