@@ -41,11 +41,11 @@ __device__ __forceinline__ u32 lanemask_lt() {
 }
 __device__ __forceinline__ u32 ld_volatile_u32(const u32 *p) {
     u32 v;
-    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_volatile_u32(u32 *p, u32 v) {
-    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // launch counter (the bench's "gpu_launches" claim): every kernel launch goes through LAUNCH.

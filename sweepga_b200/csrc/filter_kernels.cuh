@@ -323,6 +323,84 @@ k_chain_resolve(const Cand *__restrict__ cand, const uint4 *__restrict__ srec, c
     }
 }
 
+// P2b: the same resolve for LARGE or DENSE groups, one warp per group: the step is decided by the whole warp and a
+// blocked step re-scans its window with 32 lanes (a thread-per-group walk would serialise a window of thousands).
+__device__ __forceinline__ void bb_argmin(u64 &bd, u32 &bj) { // smallest d, then smallest j ("first minimal j")
+    const u32 full = 0xFFFFFFFFu;
+    u32 hi = (u32)(bd >> 32), lo = (u32)bd;
+    u32 mh = __reduce_min_sync(full, hi);
+    u32 ml = __reduce_min_sync(full, hi == mh ? lo : 0xFFFFFFFFu);
+    bool is = hi == mh && lo == ml;
+    bj = __reduce_min_sync(full, is ? bj : NONE32);
+    bd = ((u64)mh << 32) | ml;
+}
+__global__ void __launch_bounds__(128)
+k_chain_resolve_warp(const Cand *__restrict__ cand, const uint4 *__restrict__ srec, const u64 *__restrict__ skey,
+                     const u32 *__restrict__ gstart, u32 n_groups, u32 n_m, const u32 *__restrict__ work, const u32 *__restrict__ n_work_ptr,
+                     int cb, u64 G, u64 *bps, u32 *root, u32 *work_counter) {
+    const u32 full = 0xFFFFFFFFu;
+    const u32 lane = lane_id();
+    const u64 G5 = G / 5;
+    const u32 n_work = *n_work_ptr;
+    while (true) {
+        u32 w = 0;
+        if (lane == 0) w = atomicAdd(work_counter, 1u);
+        w = __shfl_sync(full, w, 0);
+        if (w >= n_work) break;
+        const u32 g = work[w];
+        const u32 s = gstart[g], e = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
+        const bool fwd = ((skey[s] >> cb) & 1) == 0;
+        for (u32 i = s; i + 1 < e; i++) {
+            const Cand c = cand[i];
+            if (c.j == NONE32) continue;
+            const u32 ri = root[i];
+            if (c.d < bps[c.j]) {
+                if (lane == 0) { bps[c.j] = c.d; root[c.j] = ri; }
+            } else {
+                const uint4 a = srec[i];
+                const u64 bound = (u64)a.y + G;
+                u64 bd = NONE64;
+                u32 bj = NONE32;
+                for (u32 base = i + 1; base < e; base += 32) {
+                    const u32 j = base + lane;
+                    bool inwin = false;
+                    if (j < e) {
+                        const uint4 b = srec[j];
+                        inwin = (u64)b.x <= bound;
+                        u64 d;
+                        if (inwin && bb_candidate(a, b, fwd, G, G5, d) && d < bd && d < bps[j]) { bd = d; bj = j; }
+                    }
+                    if (!__all_sync(full, inwin)) break;
+                }
+                bb_argmin(bd, bj);
+                if (lane == 0 && bj != NONE32) { bps[bj] = bd; root[bj] = ri; }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// rough count of candidate evaluations the chaining will need (guards against an input that would run for hours)
+__global__ void __launch_bounds__(256)
+k_chain_work_estimate(const u64 *__restrict__ skey, const u32 *__restrict__ gstart, u32 n_groups, u32 n_m, int cb, u64 G, u64 *ctr) {
+    const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+    u64 est = 0;
+    if (g < n_groups) {
+        const u32 s = gstart[g], e = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
+        const u64 size = e - s;
+        if (size > 1) {
+            const u64 cmask = (((u64)1 << cb) - 1);
+            const u64 span = (skey[e - 1] & cmask) - (skey[s] & cmask) + 1;
+            u64 win = size * G / span + 1; // expected candidates per step
+            if (win > size) win = size;
+            est = size * win;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) est += __shfl_down_sync(0xFFFFFFFFu, est, o);
+    if (lane_id() == 0 && est) atomicAdd((unsigned long long *)&ctr[C_WORK], (unsigned long long)est);
+}
+
 // P3a: chain heads seed their slot with their own record; every position feeds its group's min original index.
 __global__ void __launch_bounds__(256)
 k_chain_heads(const uint4 *__restrict__ srec, const uint2 *__restrict__ srec2, const u32 *__restrict__ sidx,

@@ -354,6 +354,16 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         srec2[p] = __ldg(&rec2[i]);
     });
     const u32 n_groups = read_u32(c, d_tot);
+    {   // refuse inputs whose chaining would need an absurd number of candidate evaluations (e.g. one 50 M-mapping pile:
+        // ~2e13; the reference is O(n * window) there as well) instead of occupying the GPU for hours
+        k_chain_work_estimate<<<cdiv(n_groups, 256), 256, 0, st>>>(skey, gstart, n_groups, n_m, cb, cfg.scaffold_gap, ctr);
+        lc.n++;
+        read_counters(c);
+        static const double max_evals = getenv("SWG_MAX_PAIR_EVALS") ? atof(getenv("SWG_MAX_PAIR_EVALS")) : 2e12;
+        if ((double)c->h_ctr[C_WORK] > max_evals)
+            throw RangeError{"chaining would need ~" + std::to_string((double)c->h_ctr[C_WORK]) +
+                             " candidate evaluations (dense pile); raise SWG_MAX_PAIR_EVALS to run it anyway"};
+    }
 
     // ---- K3: best-buddy chaining (candidates -> sequential resolve -> aggregates) -------------------
     u64 *bps = A.take<u64>(n_m);
@@ -364,20 +374,35 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     cs.sum_matches = A.take<u64>(n_m); cs.sum_block = A.take<u64>(n_m); cs.group = A.take<u32>(n_m);
     cs.grp_minidx = A.take<u32>(n_groups);
     u8 *grp_has_cand = A.take<u8>(n_groups);
-    u32 *work = A.take<u32>(n_groups);
-    u32 *bb_ctr = A.take<u32>(4); // [0] number of groups to resolve, [1] resolve work counter
+    u32 *work = A.take<u32>(n_groups), *work_big = A.take<u32>(n_groups);
+    u32 *bb_ctr = A.take<u32>(4); // [0] #ordinary groups, [1] their work counter, [2] #large/dense groups, [3] their work counter
     SWG_CUDA(cudaMemsetAsync(bb_ctr, 0, 4 * sizeof(u32), st));
     SWG_CUDA(cudaMemsetAsync(grp_has_cand, 0, n_groups, st));
     SWG_CUDA(cudaMemsetAsync(cs.grp_minidx, 0xFF, sizeof(u32) * (size_t)n_groups, st));
     {
         k_chain_candidates<<<cdiv(n_m, 256), 256, 0, st>>>(srec, skey, gid, n_m, cb, cfg.scaffold_gap, cand, bps, root, grp_has_cand);
         lc.n++;
-        scan_apply([=] __device__(u32 g) -> u32 { return grp_has_cand[g] ? 1u : 0u; },
+        // work lists: groups with at least one candidate, split into ordinary (thread per group) and large/dense
+        // (warp per group: size > 4096 or an expected window > 64 candidates)
+        const u64 Gj = cfg.scaffold_gap;
+        const u64 cmask = (1ull << cb) - 1;
+        auto is_big = [=] __device__(u32 g) -> bool {
+            const u32 s0 = gstart[g], e0 = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
+            const u64 size = e0 - s0;
+            const u64 span = (skey[e0 - 1] & cmask) - (skey[s0] & cmask) + 1;
+            return size > 4096 || size * Gj > 64 * span;
+        };
+        scan_apply([=] __device__(u32 g) -> u32 { return (grp_has_cand[g] && !is_big(g)) ? 1u : 0u; },
                    [=] __device__(u32 g, u32 ex, u32 v) { if (v) work[ex] = g; }, n_groups, bsum, bb_ctr, st, lc);
-        // enough threads to hide the dependent-load latency of a step, few enough that every group's lines stay in L2
+        scan_apply([=] __device__(u32 g) -> u32 { return (grp_has_cand[g] && is_big(g)) ? 1u : 0u; },
+                   [=] __device__(u32 g, u32 ex, u32 v) { if (v) work_big[ex] = g; }, n_groups, bsum, bb_ctr + 2, st, lc);
+        // enough threads to hide the dependent-load latency of a step, few enough that every group's lines stay in L1/L2
         static const int resolve_mult = getenv("SWG_RESOLVE_MULT") ? atoi(getenv("SWG_RESOLVE_MULT")) : 4;
         k_chain_resolve<<<(u32)c->sm_count * resolve_mult, 128, 0, st>>>(cand, srec, skey, gstart, n_groups, n_m, work, bb_ctr, cb, cfg.scaffold_gap,
                                                              bps, root, bb_ctr + 1);
+        k_chain_resolve_warp<<<(u32)c->sm_count * 4, 128, 0, st>>>(cand, srec, skey, gstart, n_groups, n_m, work_big, bb_ctr + 2, cb,
+                                                                  cfg.scaffold_gap, bps, root, bb_ctr + 3);
+        lc.n++;
         k_chain_heads<<<cdiv(n_m, 256), 256, 0, st>>>(srec, srec2, sidx, gid, root, n_m, cs);
         k_chain_members<<<cdiv(n_m, 256), 256, 0, st>>>(srec, srec2, root, n_m, cs);
         lc.n += 3;
@@ -921,6 +946,59 @@ int swg_last_chain_keys(swg_ctx *c, uint64_t cap, uint32_t *first_index_genome_p
         SWG_CUDA(cudaMemcpyAsync(a->a, a->c->last_keyA, a->c->last_n_chains * 4, cudaMemcpyDeviceToHost, a->c->stream));
         SWG_CUDA(cudaMemcpyAsync(a->b, a->c->last_keyB, a->c->last_n_chains * 4, cudaMemcpyDeviceToHost, a->c->stream));
         SWG_CUDA(cudaStreamSynchronize(a->c->stream));
+    }, &a);
+}
+
+// Tuning aid (not part of the public header): sort n pseudo-random (key,payload) pairs over `bits` key bits, `reps`
+// times, and report the mean CUDA-event time of ONE one-sweep pass in *ms_per_pass.  Returns 0 and checks sortedness.
+int swg__bench_sort(swg_ctx *c, uint64_t n, int bits, int reps, double *ms_per_pass, int *sorted_ok) {
+    if (!c || !ms_per_pass || n == 0 || n >= 0x7FFFFFF0ull) return SWG_ERR_ARG;
+    struct Args { swg_ctx *c; u32 n; int bits, reps; double *ms; int *ok; } a{c, (u32)n, bits, reps, ms_per_pass, sorted_ok};
+    return guarded(c, "swg__bench_sort", [](void *p) {
+        Args *a = (Args *)p;
+        swg_ctx *c = a->c;
+        SWG_CUDA(cudaSetDevice(c->device));
+        const u32 n = a->n;
+        c->arena.reserve((size_t)n * 40 + (64u << 20));
+        u64 *src = c->arena.take<u64>(n), *k = c->arena.take<u64>(n), *k2 = c->arena.take<u64>(n);
+        u32 *v = c->arena.take<u32>(n), *v2 = c->arena.take<u32>(n);
+        u64 *bad = c->arena.take<u64>(1);
+        const int bits = a->bits;
+        launch_for<t_iota>(n, c->stream, c->lc, [=] __device__(u32 i) {
+            u64 x = (u64)i * 0x9E3779B97F4A7C15ull + 0x7F4A7C15ull;
+            x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
+            src[i] = bits >= 64 ? x : (x & ((1ull << bits) - 1));
+        });
+        double total = 0;
+        int passes = 1;
+        for (int r = 0; r < a->reps; r++) {
+            u64 *kk = k, *kk2 = k2;
+            u32 *vv = v, *vv2 = v2;
+            SWG_CUDA(cudaMemcpyAsync(kk, src, sizeof(u64) * n, cudaMemcpyDeviceToDevice, c->stream));
+            launch_for<t_gather>(n, c->stream, c->lc, [=] __device__(u32 i) { vv[i] = i; });
+            Arena::Mark mk = c->arena.mark();
+            sort_pairs(c, kk, kk2, vv, vv2, n, bits, true);
+            SWG_CUDA(cudaStreamSynchronize(c->stream));
+            c->arena.rewind(mk);
+            float ms = 0;
+            SWG_CUDA(cudaEventElapsedTime(&ms, c->ev_sort[0], c->ev_sort[1]));
+            total += ms;
+            passes = c->sort_passes;
+            if (r == a->reps - 1 && a->ok) {
+                SWG_CUDA(cudaMemsetAsync(bad, 0, sizeof(u64), c->stream));
+                const u64 *ks = kk;
+                const u32 *vs = vv;
+                launch_for<t_maxp>(n - 1, c->stream, c->lc, [=] __device__(u32 i) {
+                    bool b = ks[i] > ks[i + 1] || (ks[i] == ks[i + 1] && vs[i] > vs[i + 1]) || src[vs[i]] != ks[i];
+                    if (b) atomicAdd((unsigned long long *)bad, 1ull);
+                });
+                u64 hb = 1;
+                SWG_CUDA(cudaMemcpyAsync(&hb, bad, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+                SWG_CUDA(cudaStreamSynchronize(c->stream));
+                *a->ok = hb == 0;
+            }
+        }
+        *a->ms = total / a->reps / passes;
     }, &a);
 }
 

@@ -21,12 +21,21 @@ namespace swg {
 
 constexpr int RS_BITS = 8;
 constexpr int RS_RADIX = 1 << RS_BITS;
-constexpr int RS_THREADS = 512;
+#ifndef SWG_RS_THREADS
+#define SWG_RS_THREADS 384
+#endif
+#ifndef SWG_RS_ITEMS
+#define SWG_RS_ITEMS 14
+#endif
+constexpr int RS_THREADS = SWG_RS_THREADS;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 12;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS; // 6144 pairs
+constexpr int RS_ITEMS = SWG_RS_ITEMS;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS; // 5376 pairs (384 threads x 14)
 constexpr int RS_MAX_PASSES = 8;
-constexpr int RS_LOOKBACK = 8; // predecessor tiles inspected per look-back round (independent loads in flight)
+#ifndef SWG_RS_LOOKBACK
+#define SWG_RS_LOOKBACK 8
+#endif
+constexpr int RS_LOOKBACK = SWG_RS_LOOKBACK; // predecessor tiles inspected per look-back round (independent loads in flight)
 
 constexpr u32 RS_FLAG_AGG = 1u << 30;  // tile aggregate available
 constexpr u32 RS_FLAG_INCL = 2u << 30; // inclusive prefix available
