@@ -125,7 +125,16 @@ __device__ __forceinline__ void rs_onesweep_tile(RsSmem &s, const u64 *__restric
     for (int i = 0; i < RS_ITEMS; i++) {
         const bool ok = FULL || (u32)(i * 32 + lane) < warp_n;
         const u32 d = (u32)(key[i] >> shift) & (RS_RADIX - 1);
-        const u32 peers = __match_any_sync(0xFFFFFFFFu, ok ? d : (0x100u | lane));
+        // lanes with the same 8-bit digit, from 8 ballots (much cheaper than MATCH.ANY when the warp holds many
+        // distinct digits, which is every low-order pass)
+        u32 peers = FULL ? 0xFFFFFFFFu : __ballot_sync(0xFFFFFFFFu, ok);
+#pragma unroll
+        for (int b = 0; b < RS_BITS; b++) {
+            const bool bit = (d >> b) & 1;
+            const u32 m = __ballot_sync(0xFFFFFFFFu, bit);
+            peers &= bit ? m : ~m;
+        }
+        if (!FULL && !ok) peers = 1u << lane;
         // leader (5 bits) | run length (6 bits) | rank inside the run (5 bits)
         rnk[i] = (u32)(__ffs(peers) - 1) | ((u32)__popc(peers) << 8) | ((u32)__popc(peers & lt) << 16);
     }
@@ -224,7 +233,11 @@ __device__ __forceinline__ void rs_onesweep_tile(RsSmem &s, const u64 *__restric
         for (int it = 0; it < RS_ITEMS; it++) {
             const u32 j = it * RS_THREADS + tid;
             const u64 k = s.stage_k[j];
+#ifdef SWG_RS_DEBUG_LINEAR_OUT
+            const u32 g = (u32)tile_base + j + (s.global_base[(u32)(k >> shift) & (RS_RADIX - 1)] & 0); // timing experiment only
+#else
             const u32 g = s.global_base[(u32)(k >> shift) & (RS_RADIX - 1)] + j;
+#endif
             keys_out[g] = k;
             vals_out[g] = s.stage_v[j];
         }
@@ -238,7 +251,10 @@ __device__ __forceinline__ void rs_onesweep_tile(RsSmem &s, const u64 *__restric
     }
 }
 
-__global__ void __launch_bounds__(RS_THREADS, 2)
+#ifndef SWG_RS_MINBLOCKS
+#define SWG_RS_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(RS_THREADS, SWG_RS_MINBLOCKS)
 rs_onesweep_kernel(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out, const u32 *__restrict__ vals_in,
                    u32 *__restrict__ vals_out, u32 n, int shift, const u32 *__restrict__ digit_base,
                    u32 *tile_status /*[tiles][256]*/, u32 *tile_counter) {
