@@ -382,15 +382,14 @@ k_chain_resolve_warp(const Cand *__restrict__ cand, const uint4 *__restrict__ sr
 
 // rough count of candidate evaluations the chaining will need (guards against an input that would run for hours)
 __global__ void __launch_bounds__(256)
-k_chain_work_estimate(const u64 *__restrict__ skey, const u32 *__restrict__ gstart, u32 n_groups, u32 n_m, int cb, u64 G, u64 *ctr) {
+k_chain_work_estimate(const uint4 *__restrict__ srec, const u32 *__restrict__ gstart, u32 n_groups, u32 n_m, u64 G, u64 *ctr) {
     const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
     u64 est = 0;
     if (g < n_groups) {
         const u32 s = gstart[g], e = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
         const u64 size = e - s;
         if (size > 1) {
-            const u64 cmask = (((u64)1 << cb) - 1);
-            const u64 span = (skey[e - 1] & cmask) - (skey[s] & cmask) + 1;
+            const u64 span = (u64)srec[e - 1].x - srec[s].x + 1;
             u64 win = size * G / span + 1; // expected candidates per step
             if (win > size) win = size;
             est = size * win;
@@ -537,7 +536,7 @@ __device__ __forceinline__ bool act_less(const ActEntry &a, const ActEntry &b) {
 }
 
 __global__ void __launch_bounds__(128)
-k_sweep_groups(const u64 *__restrict__ ekey, const u32 *__restrict__ eitem, const u32 *__restrict__ gstart, u32 n_groups,
+k_sweep_groups(const u32 *__restrict__ eitem /* item * 2 + type, in (group, pos, type) order */, const u32 *__restrict__ gstart, u32 n_groups,
                u32 n_events, const u32 *__restrict__ it_start, const u32 *__restrict__ it_end,
                const double *__restrict__ it_score, u64 n_keep, double thr, ActEntry *act, u8 *good, u8 *flagged,
                u8 *__restrict__ keep, u32 *group_counter, u64 *ctr) {
@@ -551,18 +550,21 @@ k_sweep_groups(const u64 *__restrict__ ekey, const u32 *__restrict__ eitem, cons
         const u32 es = gstart[g], ee = (g + 1 < n_groups) ? gstart[g + 1] : n_events;
         const u32 items = (ee - es) >> 1;
         if (items <= 1) { // plane_sweep_exact.rs:274-276
-            if (lane == 0) keep[eitem[es]] = 1;
+            if (lane == 0) keep[eitem[es] >> 1] = 1;
             continue;
         }
         ActEntry *A = act + (es >> 1);
         u32 size = 0;
         u32 e = es;
         while (e < ee) {
-            const u64 cur = ekey[e] >> 1; // (group | pos)
             // apply all events at this position: Begins (type 0) sort before Ends (type 1)
-            while (e < ee && (ekey[e] >> 1) == cur) {
-                const u32 item = eitem[e];
-                const bool is_end = ekey[e] & 1;
+            const u32 ev0 = eitem[e];
+            const u32 cur = (ev0 & 1) ? it_end[ev0 >> 1] : it_start[ev0 >> 1];
+            while (e < ee) {
+                const u32 ev = eitem[e];
+                const u32 item = ev >> 1;
+                const bool is_end = ev & 1;
+                if ((is_end ? it_end[item] : it_start[item]) != cur) break;
                 ActEntry x;
                 x.skey = score_desc_key(it_score[item]);
                 x.start = it_start[item];
@@ -628,8 +630,8 @@ k_sweep_groups(const u64 *__restrict__ ekey, const u32 *__restrict__ eitem, cons
         }
         // result for this group
         for (u32 b = es + lane; b < ee; b += 32) {
-            if ((ekey[b] & 1) == 0) {
-                u32 item = eitem[b];
+            if ((eitem[b] & 1) == 0) {
+                u32 item = eitem[b] >> 1;
                 keep[item] = (good[item] && !flagged[item]) ? 1 : 0;
             }
         }

@@ -151,27 +151,47 @@ static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 in
     cudaStream_t st = c->stream;
     SWG_CUDA(cudaMemsetAsync(keep, 0, n_items, st));
     if (n_items == 0) return;
-    if (gb + 33 > 64) throw RangeError{"plane-sweep group key too wide for a 64-bit event key"};
-    if ((u64)n_items * 2 >= 0xFFFFFFF0ull) throw RangeError{"too many sweep events"};
+    if (gb > 62) throw RangeError{"plane-sweep group key wider than 62 bits"};
+    if ((u64)n_items * 2 >= 0x7FFFFFF0ull) throw RangeError{"too many sweep events"};
     u32 n_ev_all = n_items * 2;
     u64 *ek = c->arena.take<u64>(n_ev_all), *ek2 = c->arena.take<u64>(n_ev_all);
     u32 *ev = c->arena.take<u32>(n_ev_all), *ev2 = c->arena.take<u32>(n_ev_all);
     u64 *ctr = c->d_ctr;
     SWG_CUDA(cudaMemsetAsync(ctr + C_TMP0, 0, sizeof(u64), st));
+    // events: payload = item * 2 + type; order = (group, position, Begin before End).  One sort when the key fits
+    // 64 bits, else two chained stable sorts (position|type first, then the group id).
+    const bool wide = (gb + 33 > 64) || (getenv("SWG_FORCE_WIDE_KEYS") != nullptr);
     launch_for<t_events>(n_items, st, c->lc, [=] __device__(u32 i) {
         bool inc = include ? (include[i] & include_mask) != 0 : true;
         u64 k0 = NONE64, k1 = NONE64;
         if (inc) {
-            k0 = (gkey[i] << 33) | ((u64)it_start[i] << 1);
-            k1 = (gkey[i] << 33) | ((u64)it_end[i] << 1) | 1;
+            const u64 g = wide ? 0 : (gkey[i] << 33);
+            k0 = g | ((u64)it_start[i] << 1);
+            k1 = g | ((u64)it_end[i] << 1) | 1;
         }
-        ek[2 * i] = k0; ev[2 * i] = i;
-        ek[2 * i + 1] = k1; ev[2 * i + 1] = i;
+        ek[2 * i] = k0; ev[2 * i] = 2 * i;
+        ek[2 * i + 1] = k1; ev[2 * i + 1] = 2 * i + 1;
         u32 am = __activemask();
         u32 cnt = __popc(__ballot_sync(am, inc));
         if (cnt && (threadIdx.x & 31) == (u32)(__ffs(am) - 1)) atomicAdd((unsigned long long *)&ctr[C_TMP0], (unsigned long long)cnt);
     });
-    sort_pairs(c, ek, ek2, ev, ev2, n_ev_all, gb + 33);
+    int eshift = 33;
+    if (!wide) {
+        sort_pairs(c, ek, ek2, ev, ev2, n_ev_all, gb + 33);
+    } else {
+        sort_pairs(c, ek, ek2, ev, ev2, n_ev_all, 33);
+        {
+            u64 *kk = ek;
+            const u32 *vv = ev;
+            launch_for<t_gather>(n_ev_all, st, c->lc, [=] __device__(u32 u) {
+                const u32 i = vv[u] >> 1;
+                const bool inc = include ? (include[i] & include_mask) != 0 : true;
+                kk[u] = inc ? gkey[i] : NONE64;
+            });
+        }
+        sort_pairs(c, ek, ek2, ev, ev2, n_ev_all, gb + 1);
+        eshift = 0;
+    }
     read_counters(c);
     u32 n_ev = (u32)(c->h_ctr[C_TMP0] * 2);
     if (n_ev == 0) return;
@@ -179,7 +199,7 @@ static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 in
     u32 *bsum = c->arena.take<u32>(scan_temp_u32(n_ev));
     u32 *d_ng = c->arena.take<u32>(2);
     const u64 *ekc = ek;
-    scan_apply([=] __device__(u32 u) -> u32 { return (u == 0 || (ekc[u] >> 33) != (ekc[u - 1] >> 33)) ? 1u : 0u; },
+    scan_apply([=] __device__(u32 u) -> u32 { return (u == 0 || (ekc[u] >> eshift) != (ekc[u - 1] >> eshift)) ? 1u : 0u; },
                [=] __device__(u32 u, u32 ex, u32 v) { if (v) gstart[ex] = u; }, n_ev, bsum, d_ng, st, c->lc);
     u32 n_groups = read_u32(c, d_ng);
     ActEntry *act = c->arena.take<ActEntry>(n_ev / 2 + 1);
@@ -188,7 +208,7 @@ static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 in
     SWG_CUDA(cudaMemsetAsync(flagged, 0, n_items, st));
     SWG_CUDA(cudaMemsetAsync(d_ng + 1, 0, sizeof(u32), st));
     u32 blocks = std::min<u32>(cdiv(n_groups, 4), (u32)c->sm_count * 8);
-    k_sweep_groups<<<blocks, 128, 0, st>>>(ek, ev, gstart, n_groups, n_ev, it_start, it_end, it_score, n_keep, thr, act, good,
+    k_sweep_groups<<<blocks, 128, 0, st>>>(ev, gstart, n_groups, n_ev, it_start, it_end, it_score, n_keep, thr, act, good,
                                           flagged, keep, d_ng + 1, ctr);
     c->lc.n++;
     SWG_CUDA(cudaGetLastError());
@@ -322,12 +342,41 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     }
 
     // ---- K1 + sort + K2: group by (q,t,strand), stable order by query_start ------------------------
-    if (2 * sb + 1 + cb > 64) throw RangeError{"(query,target,strand,start) key wider than 64 bits"};
     u64 *keys = A.take<u64>(N), *keys2 = A.take<u64>(N);
     u32 *vals = A.take<u32>(N), *vals2 = A.take<u32>(N);
-    k_chain_keys<<<cdiv(N, 256), 256, 0, st>>>(in, flags, keep_q, keep_t, sb, cb, keys, vals, ctr);
-    lc.n++;
-    sort_pairs(c, keys, keys2, vals, vals2, N, 2 * sb + 1 + cb, true);
+    int gshift = cb; // group id of a sorted position = skey >> gshift
+    const bool wide = (2 * sb + 1 + cb > 64) || (getenv("SWG_FORCE_WIDE_KEYS") != nullptr);
+    if (!wide) {
+        k_chain_keys<<<cdiv(N, 256), 256, 0, st>>>(in, flags, keep_q, keep_t, sb, cb, keys, vals, ctr);
+        lc.n++;
+        sort_pairs(c, keys, keys2, vals, vals2, N, 2 * sb + 1 + cb, true);
+    } else {
+        // key wider than 64 bits (hundreds of thousands of sequences): two chained stable sorts, least significant
+        // field first: by query_start, then by the (query,target,strand) group id; skey then holds the group id alone
+        u64 *gk = A.take<u64>(N);
+        {
+            u64 *kk = keys;
+            u32 *vv = vals;
+            launch_for<t_gkey>(N, st, lc, [=] __device__(u32 i) {
+                const bool kept = (flags[i] & F_ALIVE) && (!keep_q || keep_q[i]) && (!keep_t || keep_t[i]);
+                const u64 sbit = in.strand[i] == '+' ? 0 : 1;
+                gk[i] = kept ? ((((u64)in.qid[i] << sb) | in.tid[i]) << 1 | sbit) : NONE64;
+                kk[i] = in.qs[i];
+                vv[i] = i;
+                u32 am = __activemask();
+                u32 cnt = __popc(__ballot_sync(am, kept));
+                if (cnt && (threadIdx.x & 31) == (u32)(__ffs(am) - 1)) atomicAdd((unsigned long long *)&ctr[C_KEPT_M], (unsigned long long)cnt);
+            });
+        }
+        sort_pairs(c, keys, keys2, vals, vals2, N, cb, true);
+        {
+            u64 *kk = keys;
+            const u32 *vv = vals;
+            launch_for<t_gather>(N, st, lc, [=] __device__(u32 p) { kk[p] = gk[vv[p]]; });
+        }
+        sort_pairs(c, keys, keys2, vals, vals2, N, 2 * sb + 2);
+        gshift = 0;
+    }
     read_counters(c);
     const u32 n_m = (u32)c->h_ctr[C_KEPT_M];
     S.n_after_sweep = n_m;
@@ -341,7 +390,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     u32 *gid = A.take<u32>(n_m);
     u32 *bsum = A.take<u32>(scan_temp_u32(N));
     u32 *d_tot = A.take<u32>(4);
-    scan_apply([=] __device__(u32 p) -> u32 { return (p == 0 || (skey[p] >> cb) != (skey[p - 1] >> cb)) ? 1u : 0u; },
+    scan_apply([=] __device__(u32 p) -> u32 { return (p == 0 || (skey[p] >> gshift) != (skey[p - 1] >> gshift)) ? 1u : 0u; },
                [=] __device__(u32 p, u32 ex, u32 v) {
                    if (v) gstart[ex] = p;
                    gid[p] = ex + v - 1;
@@ -356,7 +405,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     const u32 n_groups = read_u32(c, d_tot);
     {   // refuse inputs whose chaining would need an absurd number of candidate evaluations (e.g. one 50 M-mapping pile:
         // ~2e13; the reference is O(n * window) there as well) instead of occupying the GPU for hours
-        k_chain_work_estimate<<<cdiv(n_groups, 256), 256, 0, st>>>(skey, gstart, n_groups, n_m, cb, cfg.scaffold_gap, ctr);
+        k_chain_work_estimate<<<cdiv(n_groups, 256), 256, 0, st>>>(srec, gstart, n_groups, n_m, cfg.scaffold_gap, ctr);
         lc.n++;
         read_counters(c);
         static const double max_evals = getenv("SWG_MAX_PAIR_EVALS") ? atof(getenv("SWG_MAX_PAIR_EVALS")) : 2e12;
@@ -380,16 +429,15 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     SWG_CUDA(cudaMemsetAsync(grp_has_cand, 0, n_groups, st));
     SWG_CUDA(cudaMemsetAsync(cs.grp_minidx, 0xFF, sizeof(u32) * (size_t)n_groups, st));
     {
-        k_chain_candidates<<<cdiv(n_m, 256), 256, 0, st>>>(srec, skey, gid, n_m, cb, cfg.scaffold_gap, cand, bps, root, grp_has_cand);
+        k_chain_candidates<<<cdiv(n_m, 256), 256, 0, st>>>(srec, skey, gid, n_m, gshift, cfg.scaffold_gap, cand, bps, root, grp_has_cand);
         lc.n++;
         // work lists: groups with at least one candidate, split into ordinary (thread per group) and large/dense
         // (warp per group: size > 4096 or an expected window > 64 candidates)
         const u64 Gj = cfg.scaffold_gap;
-        const u64 cmask = (1ull << cb) - 1;
         auto is_big = [=] __device__(u32 g) -> bool {
             const u32 s0 = gstart[g], e0 = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
             const u64 size = e0 - s0;
-            const u64 span = (skey[e0 - 1] & cmask) - (skey[s0] & cmask) + 1;
+            const u64 span = (u64)srec[e0 - 1].x - srec[s0].x + 1;
             return size > 4096 || size * Gj > 64 * span;
         };
         scan_apply([=] __device__(u32 g) -> u32 { return (grp_has_cand[g] && !is_big(g)) ? 1u : 0u; },
@@ -398,9 +446,9 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                    [=] __device__(u32 g, u32 ex, u32 v) { if (v) work_big[ex] = g; }, n_groups, bsum, bb_ctr + 2, st, lc);
         // enough threads to hide the dependent-load latency of a step, few enough that every group's lines stay in L1/L2
         static const int resolve_mult = getenv("SWG_RESOLVE_MULT") ? atoi(getenv("SWG_RESOLVE_MULT")) : 4;
-        k_chain_resolve<<<(u32)c->sm_count * resolve_mult, 128, 0, st>>>(cand, srec, skey, gstart, n_groups, n_m, work, bb_ctr, cb, cfg.scaffold_gap,
+        k_chain_resolve<<<(u32)c->sm_count * resolve_mult, 128, 0, st>>>(cand, srec, skey, gstart, n_groups, n_m, work, bb_ctr, gshift, cfg.scaffold_gap,
                                                              bps, root, bb_ctr + 1);
-        k_chain_resolve_warp<<<(u32)c->sm_count * 4, 128, 0, st>>>(cand, srec, skey, gstart, n_groups, n_m, work_big, bb_ctr + 2, cb,
+        k_chain_resolve_warp<<<(u32)c->sm_count * 4, 128, 0, st>>>(cand, srec, skey, gstart, n_groups, n_m, work_big, bb_ctr + 2, gshift,
                                                                   cfg.scaffold_gap, bps, root, bb_ctr + 3);
         lc.n++;
         k_chain_heads<<<cdiv(n_m, 256), 256, 0, st>>>(srec, srec2, sidx, gid, root, n_m, cs);
@@ -432,7 +480,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         const u32 hmask = hcap - 1;
         launch_for<t_chain_order>(C, st, lc, [=] __device__(u32 ci) {
             const u32 p = head_pos[ci];
-            u64 k = skey[p] >> cb;
+            u64 k = skey[p] >> gshift;
             u8 fwd = (k & 1) == 0;
             u32 tid = (u32)(k >> 1) & seqmask, qid = (u32)(k >> (1 + sb)) & seqmask;
             u32 qmin = cs.qmin[p], qmax = cs.qmax[p], tmin = cs.tmin[p], tmax = cs.tmax[p];
@@ -618,45 +666,73 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         // ---- K7: rescue (paf_filter.rs:613-732) -----------------------------------------------------
         const u64 D = cfg.scaffold_max_deviation;
         if (D > 0) {
-            if (2 * sb + cb > 63) throw RangeError{"(query,target,center) anchor key wider than 64 bits"};
-            // anchor list (status == 1), keyed by (chromosome pair | query center)
+            // anchor list (status == 1) ordered by (chromosome pair, query center); one sort when the key fits 64 bits,
+            // else two chained stable sorts (center first, then the pair)
+            const bool wide_a = (2 * sb + cb > 63) || (getenv("SWG_FORCE_WIDE_KEYS") != nullptr);
             u64 *ak = A.take<u64>(N), *ak2 = A.take<u64>(N);
             u32 *av = A.take<u32>(N), *av2 = A.take<u32>(N);
-            u32 *d_na = A.take<u32>(1);
+            u32 *d_na = A.take<u32>(2);
             scan_apply([=] __device__(u32 i) -> u32 { return status[i] == 1 ? 1u : 0u; },
                        [=] __device__(u32 i, u32 ex, u32 v) {
                            if (!v) return;
                            u64 qc = ((u64)in.qs[i] + in.qe[i]) / 2;
-                           ak[ex] = ((((u64)in.qid[i] << sb) | in.tid[i]) << cb) | qc;
+                           ak[ex] = wide_a ? qc : (((((u64)in.qid[i] << sb) | in.tid[i]) << cb) | qc);
                            av[ex] = i;
                        },
                        N, bsum, d_na, st, lc);
             const u32 NA = read_u32(c, d_na);
-            sort_pairs(c, ak, ak2, av, av2, NA, 2 * sb + cb);
-            const u64 *akc = ak;
+            if (!wide_a) {
+                sort_pairs(c, ak, ak2, av, av2, NA, 2 * sb + cb);
+            } else {
+                sort_pairs(c, ak, ak2, av, av2, NA, cb);
+                {
+                    u64 *kk = ak;
+                    const u32 *vv = av;
+                    launch_for<t_gather>(NA, st, lc, [=] __device__(u32 x) { const u32 i = vv[x]; kk[x] = ((u64)in.qid[i] << sb) | in.tid[i]; });
+                }
+                sort_pairs(c, ak, ak2, av, av2, NA, 2 * sb);
+            }
+            u64 *apair = A.take<u64>(NA + 1);
+            u32 *aqc = A.take<u32>(NA + 1);
+            {
+                const u64 *akc = ak;
+                const u32 *avc = av;
+                const u64 cmask = (1ull << cb) - 1;
+                launch_for<t_anchor_keys>(NA, st, lc, [=] __device__(u32 x) {
+                    if (wide_a) { const u32 i = avc[x]; apair[x] = akc[x]; aqc[x] = (u32)(((u64)in.qs[i] + in.qe[i]) / 2); }
+                    else { apair[x] = akc[x] >> cb; aqc[x] = (u32)(akc[x] & cmask); }
+                });
+            }
+            // candidates (alive, not an anchor, not a member of a swept-away scaffold), compacted so the searches run dense
+            u32 *rlist = A.take<u32>(N);
+            scan_apply([=] __device__(u32 i) -> u32 { return ((flags[i] & F_ALIVE) && status[i] == 0 && !(flags[i] & F_PREMEM)) ? 1u : 0u; },
+                       [=] __device__(u32 i, u32 ex, u32 v) { if (v) rlist[ex] = i; }, N, bsum, d_na + 1, st, lc);
             const u32 *avc = av;
-            const u64 cmask = (1ull << cb) - 1;
-            launch_for<t_rescue>(N, st, lc, [=] __device__(u32 i) {
-                if (!(flags[i] & F_ALIVE) || status[i] != 0 || (flags[i] & F_PREMEM)) return;
-                u64 pair = ((u64)in.qid[i] << sb) | in.tid[i];
-                u64 qc = ((u64)in.qs[i] + in.qe[i]) / 2, tc = ((u64)in.ts[i] + in.te[i]) / 2;
-                u64 qlo = qc > D ? qc - D : 0;
-                u64 key = (pair << cb) | qlo;
+            const u32 *d_nr = d_na + 1;
+            launch_for<t_rescue>(N, st, lc, [=] __device__(u32 x0) {
+                if (x0 >= *d_nr) return;
+                const u32 i = rlist[x0];
+                const u64 pair = ((u64)in.qid[i] << sb) | in.tid[i];
+                const u64 qc = ((u64)in.qs[i] + in.qe[i]) / 2, tc = ((u64)in.ts[i] + in.te[i]) / 2;
+                const u64 qlo = qc > D ? qc - D : 0;
                 u32 lo = 0, hi = NA;
-                while (lo < hi) { u32 mid = (lo + hi) >> 1; if (akc[mid] < key) lo = mid + 1; else hi = mid; }
+                while (lo < hi) {
+                    u32 mid = (lo + hi) >> 1;
+                    const u64 mp = apair[mid];
+                    if (mp < pair || (mp == pair && (u64)aqc[mid] < qlo)) lo = mid + 1; else hi = mid;
+                }
                 u64 best_d = NONE64;
                 u32 best_a = NONE32;
                 for (u32 x = lo; x < NA; x++) {
-                    u64 k = akc[x];
-                    if ((k >> cb) != pair) break;
-                    u64 aqc = k & cmask;
-                    if (aqc > qc + D) break;
-                    u32 a = avc[x];
-                    u64 qd = aqc > qc ? aqc - qc : qc - aqc;
-                    u64 atc = ((u64)in.ts[a] + in.te[a]) / 2;
-                    u64 td = atc > tc ? atc - tc : tc - atc;
+                    if (apair[x] != pair) break;
+                    const u64 c_a = aqc[x];
+                    if (c_a > qc + D) break;
+                    const u32 a = avc[x];
+                    const u64 qd = c_a > qc ? c_a - qc : qc - c_a;
+                    const u64 atc = ((u64)in.ts[a] + in.te[a]) / 2;
+                    const u64 td = atc > tc ? atc - tc : tc - atc;
                     if (td > D) continue; // then floor(sqrt(qd^2+td^2)) > D
-                    u64 dist = (u64)__dsqrt_rn((double)(qd * qd + td * td));
+                    const u64 dist = (u64)__dsqrt_rn((double)(qd * qd + td * td));
                     if (dist <= D && (dist < best_d || (dist == best_d && a < best_a))) { best_d = dist; best_a = a; }
                 }
                 if (best_a != NONE32) { status[i] = 2; chain_id[i] = chain_id[best_a]; }

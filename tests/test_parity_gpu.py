@@ -177,3 +177,15 @@ def test_paf_front_end_matches_oracle(ctx, tmp_path):
         f.filter_paf(str(src), str(a))
         oracle_lib.filter_paf(cfg, str(src), str(b))
         assert a.read_bytes() == b.read_bytes(), flags
+
+
+@pytest.mark.parametrize("case", ["defaults", "1:1_1:1", "rescue100k", "1:1_rescue", "2:3"])
+def test_wide_key_paths(ctx, yeast, case, monkeypatch):
+    """Keys wider than 64 bits (hundreds of thousands of sequences) take two chained stable sorts instead of one;
+    SWG_FORCE_WIDE_KEYS routes an ordinary table through that path."""
+    monkeypatch.setenv("SWG_FORCE_WIDE_KEYS", "1")
+    check(ctx, swg.FilterConfig.from_cli(**CLI_CASES[case]), yeast, "wide:" + case)
+    for seed in (3, 11, 17):
+        t = fuzz_table(seed, 400)
+        check(ctx, swg.FilterConfig.from_cli(num_mappings="1:1", scaffold_filter="2:2", scaffold_jump="200", scaffold_mass="0",
+                                            scaffold_dist="300"), t, f"wide fuzz{seed}")
