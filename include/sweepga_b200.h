@@ -197,6 +197,14 @@ int swg_plane_sweep_both(swg_ctx *ctx, uint64_t n, const uint32_t *qs, const uin
                          uint64_t n_keep_query, uint64_t n_keep_target, double overlap_threshold,
                          int scoring, uint8_t *keep);
 
+/* plane_sweep_core::plane_sweep (src/plane_sweep_core.rs:80-149), the secondary Interval API (different semantics:
+ * the n best are marked after every Begin event; greedy overlap pass in score order).  out_idx receives the kept
+ * indices in the order the reference returns them (ascending, or score-descending after the overlap pass);
+ * capacity n.  Events with equal (position, type) are taken in index order (the reference's sort_unstable leaves
+ * that order unspecified).                                                                                     */
+int swg_plane_sweep_core(swg_ctx *ctx, uint64_t n, const uint32_t *begin, const uint32_t *end, const double *score,
+                         uint64_t max_to_keep, double overlap_threshold, uint64_t *out_idx, uint64_t *n_out);
+
 /* ---- host-side mirrors of the flag parsers ------------------------------ */
 /* src/main.rs:244-293 (CLI grammar).  *mode, *per_query, *per_target (SWG_NO_LIMIT = None). */
 int swg_parse_filter_mode_cli(const char *s, uint8_t *mode, uint64_t *per_query, uint64_t *per_target);

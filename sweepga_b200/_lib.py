@@ -70,6 +70,7 @@ SYMBOLS = [
     ("swg_release", None, [_vp, _mapp, _resp]),
     ("swg_download_result", C.c_int, [_vp, C.c_uint64, _resp, _resp]),
     ("swg_last_chain_keys", C.c_int, [_vp, C.c_uint64, u32p, u32p, u64p]),
+    ("swg_plane_sweep_core", C.c_int, [_vp, C.c_uint64, u32p, u32p, f64p, C.c_uint64, C.c_double, u64p, u64p]),
     ("swg_plane_sweep_query", C.c_int, _sweep_args),
     ("swg_plane_sweep_target", C.c_int, _sweep_args),
     ("swg_plane_sweep_both", C.c_int, [_vp, C.c_uint64, u32p, u32p, u32p, u32p, f64p, C.c_uint64, C.c_uint64, C.c_double, C.c_int, u8p]),

@@ -357,6 +357,19 @@ class Context:
         return self._sweep(lib.swg_plane_sweep_both, mappings, _n(query_to_keep), _n(target_to_keep), overlap_threshold, scoring)
 
 
+    def plane_sweep_core(self, intervals, max_to_keep, overlap_threshold):
+        """plane_sweep_core::plane_sweep on [(begin, end, score), ...] -> kept indices in the reference's order."""
+        n = len(intervals)
+        b = np.ascontiguousarray([i[0] for i in intervals], dtype=np.uint32)
+        e = np.ascontiguousarray([i[1] for i in intervals], dtype=np.uint32)
+        s = np.ascontiguousarray([i[2] for i in intervals], dtype=np.float64)
+        out = np.zeros(max(n, 1), np.uint64)
+        cnt = C.c_uint64()
+        self._check(lib.swg_plane_sweep_core(self._h, n, _ptr(b, C.c_uint32), _ptr(e, C.c_uint32), _ptr(s, C.c_double), _n(max_to_keep),
+                                             overlap_threshold, _ptr(out, C.c_uint64), C.byref(cnt)))
+        return [int(x) for x in out[: cnt.value]]
+
+
 USIZE_MAX = (1 << 64) - 1
 
 

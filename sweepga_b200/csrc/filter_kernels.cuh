@@ -639,4 +639,89 @@ k_sweep_groups(const u32 *__restrict__ eitem /* item * 2 + type, in (group, pos,
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// plane_sweep_core::plane_sweep (src/plane_sweep_core.rs:80-201) — the secondary Interval API.  Different
+// semantics from plane_sweep_exact on purpose: the n best active intervals are marked after EVERY Begin event,
+// Ends only remove, and the overlap rule is a greedy pass over the marked set in score order.  One warp
+// (library / test API, not on the filter pipeline).
+// ---------------------------------------------------------------------------------------------
+struct CoreEntry { u64 key; u32 idx; u32 pad; }; // key = order-preserving image of -(score bits as i64)
+__device__ __forceinline__ u64 core_key(double score) {
+    const i64 k = (i64)(0ull - (u64)__double_as_longlong(score)); // wrapping negation like release Rust
+    return (u64)k ^ 0x8000000000000000ULL;
+}
+__global__ void __launch_bounds__(32)
+k_sweep_core_mark(const u32 *__restrict__ ev /* idx*2+type in (pos,type,idx) order */, u32 n_ev, const double *__restrict__ score,
+                  u64 max_keep, CoreEntry *A, u8 *marked) {
+    const u32 full = 0xFFFFFFFFu;
+    const u32 lane = lane_id();
+    u32 size = 0;
+    for (u32 e = 0; e < n_ev; e++) {
+        const u32 idx = ev[e] >> 1;
+        const bool is_end = ev[e] & 1;
+        CoreEntry x;
+        x.key = core_key(score[idx]); x.idx = idx; x.pad = 0;
+        u32 cnt = 0;
+        for (u32 b = lane; b < size; b += 32) cnt += (A[b].key < x.key || (A[b].key == x.key && A[b].idx < x.idx)) ? 1 : 0;
+        cnt = __reduce_add_sync(full, cnt);
+        if (!is_end) {
+            for (u32 hi = size; hi > cnt;) {
+                u32 lo = hi > cnt + 32 ? hi - 32 : cnt;
+                u32 b = lo + lane;
+                CoreEntry t;
+                bool mv = b < hi;
+                if (mv) t = A[b];
+                __syncwarp();
+                if (mv) A[b + 1] = t;
+                __syncwarp();
+                hi = lo;
+            }
+            if (lane == 0) A[cnt] = x;
+            size++;
+            __syncwarp();
+            const u32 top = (u64)size <= max_keep ? size : (u32)max_keep; // mark_best, :152-164
+            for (u32 b = lane; b < top; b += 32) marked[A[b].idx] = 1;
+        } else {
+            for (u32 lo = cnt + 1; lo < size; lo += 32) {
+                u32 b = lo + lane;
+                CoreEntry t;
+                bool mv = b < size;
+                if (mv) t = A[b];
+                __syncwarp();
+                if (mv) A[b - 1] = t;
+                __syncwarp();
+            }
+            size--;
+        }
+        __syncwarp();
+    }
+}
+// filter_by_overlap (:167-201): candidates in score-descending order, keep those that do not overlap a kept one
+__global__ void __launch_bounds__(32)
+k_sweep_core_greedy(const u32 *__restrict__ order, u32 n_c, const u32 *__restrict__ begin, const u32 *__restrict__ end, double thr,
+                    u32 *accepted, u32 *n_accepted) {
+    const u32 full = 0xFFFFFFFFu;
+    const u32 lane = lane_id();
+    u32 na = 0;
+    for (u32 t = 0; t < n_c; t++) {
+        const u32 i = order[t];
+        const u32 bi = begin[i], ei = end[i];
+        bool hit = false;
+        for (u32 a = lane; a < na && !hit; a += 32) {
+            const u32 k = accepted[a];
+            const u32 os = max(bi, begin[k]), oe = min(ei, end[k]);
+            if (os < oe) {
+                const u32 ml = min(ei - bi, end[k] - begin[k]);
+                hit = __ddiv_rn((double)(oe - os), (double)ml) > thr;
+            }
+        }
+        if (!__any_sync(full, hit)) {
+            if (lane == 0) accepted[na] = i;
+            na++;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) *n_accepted = na;
+}
+
 } // namespace swg

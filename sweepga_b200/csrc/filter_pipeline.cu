@@ -864,6 +864,61 @@ static void do_sweep(void *p) {
     SWG_CUDA(cudaStreamSynchronize(st));
 }
 
+struct CoreArgs { swg_ctx *c; u64 n; const u32 *b, *e; const double *s; u64 max_keep; double thr; u64 *out; u64 *n_out; };
+static void do_sweep_core(void *p) {
+    CoreArgs *a = (CoreArgs *)p;
+    swg_ctx *c = a->c;
+    const u32 n = (u32)a->n;
+    *a->n_out = 0;
+    if (n == 0) return;
+    if (n == 1) { a->out[0] = 0; *a->n_out = 1; return; }                       // plane_sweep_core.rs:89-91
+    if (a->max_keep == SWG_KEEP_ALL) { for (u32 i = 0; i < n; i++) a->out[i] = i; *a->n_out = n; return; } // :94-96
+    SWG_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    c->arena.reserve((size_t)n * 160 + (16u << 20));
+    Arena &A = c->arena;
+    u32 *b = A.take<u32>(n), *e = A.take<u32>(n);
+    double *sc = A.take<double>(n);
+    SWG_CUDA(cudaMemcpyAsync(b, a->b, n * 4, cudaMemcpyHostToDevice, st));
+    SWG_CUDA(cudaMemcpyAsync(e, a->e, n * 4, cudaMemcpyHostToDevice, st));
+    SWG_CUDA(cudaMemcpyAsync(sc, a->s, n * 8, cudaMemcpyHostToDevice, st));
+    u64 *ek = A.take<u64>(2 * n), *ek2 = A.take<u64>(2 * n);
+    u32 *ev = A.take<u32>(2 * n), *ev2 = A.take<u32>(2 * n);
+    launch_for<t_events>(n, st, c->lc, [=] __device__(u32 i) {
+        ek[2 * i] = (u64)b[i] << 1; ev[2 * i] = 2 * i;
+        ek[2 * i + 1] = ((u64)e[i] << 1) | 1; ev[2 * i + 1] = 2 * i + 1;
+    });
+    sort_pairs(c, ek, ek2, ev, ev2, 2 * n, 33); // stable: equal (pos,type) keep index order
+    CoreEntry *act = A.take<CoreEntry>(n + 1);
+    u8 *marked = A.take<u8>(n);
+    SWG_CUDA(cudaMemsetAsync(marked, 0, n, st));
+    k_sweep_core_mark<<<1, 32, 0, st>>>(ev, 2 * n, sc, a->max_keep, act, marked);
+    c->lc.n++;
+    // marked set in ascending index order
+    u32 *list = A.take<u32>(n), *bsum = A.take<u32>(scan_temp_u32(n)), *d_cnt = A.take<u32>(2);
+    scan_apply([=] __device__(u32 i) -> u32 { return marked[i] ? 1u : 0u; }, [=] __device__(u32 i, u32 ex, u32 v) { if (v) list[ex] = i; },
+               n, bsum, d_cnt, st, c->lc);
+    u32 nk = read_u32(c, d_cnt);
+    std::vector<u32> host(nk);
+    if (a->thr < 1.0 && nk > 1) {
+        u64 *sk = A.take<u64>(nk), *sk2 = A.take<u64>(nk);
+        u32 *sv = A.take<u32>(nk), *sv2 = A.take<u32>(nk);
+        launch_for<t_iota>(nk, st, c->lc, [=] __device__(u32 t) { sk[t] = score_desc_key(sc[list[t]]); sv[t] = list[t]; });
+        sort_pairs(c, sk, sk2, sv, sv2, nk, 64);
+        u32 *acc = A.take<u32>(nk);
+        k_sweep_core_greedy<<<1, 32, 0, st>>>(sv, nk, b, e, a->thr, acc, d_cnt + 1);
+        c->lc.n++;
+        nk = read_u32(c, d_cnt + 1);
+        host.resize(nk);
+        SWG_CUDA(cudaMemcpyAsync(host.data(), acc, nk * 4, cudaMemcpyDeviceToHost, st));
+    } else if (nk) {
+        SWG_CUDA(cudaMemcpyAsync(host.data(), list, nk * 4, cudaMemcpyDeviceToHost, st));
+    }
+    SWG_CUDA(cudaStreamSynchronize(st));
+    for (u32 i = 0; i < nk; i++) a->out[i] = host[i];
+    *a->n_out = nk;
+}
+
 } // namespace swg
 
 // =================================================================================================
@@ -1088,6 +1143,14 @@ static int sweep_entry(swg_ctx *c, uint64_t n, const uint32_t *qs, const uint32_
         if (qe[i] < qs[i] || te[i] < ts[i]) { set_err(c, "interval with end < start"); return SWG_ERR_RANGE; }
     SweepArgs a{c, n, qs, qe, ts, te, identity, nq, nt, thr, scoring, axis, keep};
     return guarded(c, "swg_plane_sweep", do_sweep, &a);
+}
+int swg_plane_sweep_core(swg_ctx *c, uint64_t n, const uint32_t *begin, const uint32_t *end, const double *score, uint64_t max_to_keep,
+                         double overlap_threshold, uint64_t *out_idx, uint64_t *n_out) {
+    if (!c || !n_out || (n && (!begin || !end || !score || !out_idx)) || n >= 0x3FFFFFF0ull) return SWG_ERR_ARG;
+    for (uint64_t i = 0; i < n; i++)
+        if (end[i] < begin[i]) { set_err(c, "interval with end < begin"); return SWG_ERR_RANGE; }
+    CoreArgs a{c, n, begin, end, score, max_to_keep, overlap_threshold, out_idx, n_out};
+    return guarded(c, "swg_plane_sweep_core", do_sweep_core, &a);
 }
 int swg_plane_sweep_query(swg_ctx *c, uint64_t n, const uint32_t *qs, const uint32_t *qe, const uint32_t *ts, const uint32_t *te,
                           const double *identity, uint64_t n_keep, double thr, int scoring, uint8_t *keep) {

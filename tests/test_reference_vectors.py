@@ -254,6 +254,63 @@ def test_scaffold_overlapping_keeps_best(eng):  # :330-371
 
 
 # ---------------------------------------------------------------------------------------------
+# tests/test_plane_sweep_symmetry.rs — plane_sweep_core::plane_sweep (score = interval length)
+# ---------------------------------------------------------------------------------------------
+def _core(eng, spans, n, thr):
+    iv = [(b, e, float(e - b)) for b, e in spans]
+    if eng.name == "oracle":
+        return oracle_lib.plane_sweep_core(iv, n, thr)
+    return eng.ctx.plane_sweep_core(iv, n, thr)
+
+
+def test_core_symmetry_simple(eng):  # :16-44
+    m = [(100, 200, 300, 400), (150, 250, 350, 450), (300, 400, 100, 200)]
+    assert len(_core(eng, [(a, b) for a, b, _, _ in m], 1, 0.95)) == 2
+    assert len(_core(eng, [(c, d) for _, _, c, d in m], 1, 0.95)) == 2
+
+
+def test_core_symmetry_transposed(eng):  # :46-80
+    o = [(100, 500), (200, 400), (600, 900)]
+    t = [(1000, 1400), (1100, 1300), (1500, 1800)]
+    assert len(_core(eng, o, 2, 0.95)) == len(_core(eng, t, 2, 0.95))
+
+
+def test_core_symmetry_with_overlaps(eng):  # :82-116
+    m = [(0, 100), (50, 150), (200, 300), (250, 350)]
+    for n in (1, 2, 3, 4):
+        assert _core(eng, m, n, 0.95) == _core(eng, list(m), n, 0.95)
+
+
+def test_core_asymmetric(eng):  # :118-152
+    q = _core(eng, [(0, 200), (50, 150), (300, 500)], 1, 0.95)
+    t = _core(eng, [(0, 100), (200, 400), (50, 150)], 1, 0.95)
+    assert 2 in q and 1 in t and q != t
+
+
+def test_core_perfect_symmetry(eng):  # :154-198
+    m = [(100, 300), (400, 600), (700, 900)]
+    for n in (1, 2, 3, MAX):
+        k = _core(eng, m, n, 0.95)
+        assert len(k) == 3
+
+
+def test_core_gpu_matches_oracle_on_random_piles(eng):
+    """not a reference test: the GPU secondary API against the oracle's restatement, incl. the greedy overlap pass"""
+    if eng.name == "oracle":
+        return
+    import numpy as np
+    rng = np.random.default_rng(5)
+    for trial in range(12):
+        n = int(rng.integers(2, 300))
+        b = rng.integers(0, 2000, n)
+        ln = rng.integers(0, 300, n)
+        sc = rng.choice([1.0, 2.5, 7.0, 0.0, 3.25], n) * rng.integers(1, 4, n)
+        iv = [(int(x), int(x + l), float(s)) for x, l, s in zip(b, ln, sc)]
+        for keep, thr in ((1, 0.95), (2, 0.5), (3, 1.0), (None, 0.5), (1, 0.0)):
+            assert eng.ctx.plane_sweep_core(iv, keep, thr) == oracle_lib.plane_sweep_core(iv, keep, thr), (trial, keep, thr)
+
+
+# ---------------------------------------------------------------------------------------------
 # pipeline-level vectors (PAF text + flags -> kept lines)
 # ---------------------------------------------------------------------------------------------
 def paf(*rows):
