@@ -338,32 +338,63 @@ int swg_paf_view(const swg_paf *p, swg_mappings *out) {
     return SWG_OK;
 }
 
+// append "\tch:Z:chain_<k>" / "\tst:Z:<status>\n" without snprintf
+static inline char *put_u32(char *o, uint32_t v) {
+    char tmp[10];
+    int k = 0;
+    do { tmp[k++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (k) *o++ = tmp[--k];
+    return o;
+}
+static void format_range(const swg_paf *p, const uint8_t *status, const uint32_t *chain_id, size_t r0, size_t r1, std::vector<char> &out) {
+    static const char *st_name[4] = {"", "scaffold", "rescued", "unassigned"};
+    static const size_t st_len[4] = {0, 8, 7, 10};
+    size_t need = 0;
+    for (size_t r = r0; r < r1; r++)
+        if (status[r] != SWG_DROPPED && status[r] <= 3) need += (size_t)p->line_len[r] + 48;
+    out.resize(need);
+    char *o = out.data();
+    for (size_t r = r0; r < r1; r++) { // records are in input order
+        const uint8_t s = status[r];
+        if (s == SWG_DROPPED || s > 3) continue;
+        memcpy(o, p->text + p->line_off[r], p->line_len[r]);
+        o += p->line_len[r];
+        if (chain_id[r]) {
+            memcpy(o, "\tch:Z:chain_", 12);
+            o = put_u32(o + 12, chain_id[r]);
+        }
+        memcpy(o, "\tst:Z:", 6);
+        o += 6;
+        memcpy(o, st_name[s], st_len[s]);
+        o += st_len[s];
+        *o++ = '\n';
+    }
+    out.resize((size_t)(o - out.data()));
+}
+
 int swg_paf_write(const swg_paf *p, const char *out_path, const uint8_t *status, const uint32_t *chain_id) {
     if (!p || !out_path || (p->rank.size() && (!status || !chain_id))) return SWG_ERR_ARG;
     FILE *f = fopen(out_path, "wb");
     if (!f) return SWG_ERR_IO;
-    std::vector<char> buf;
-    buf.reserve((size_t)8 << 20);
-    static const char *st_name[4] = {"", "scaffold", "rescued", "unassigned"};
-    char tag[64];
     bool ok = true;
-    for (size_t r = 0; r < p->rank.size(); r++) { // records are in input order
-        uint8_t s = status[r];
-        if (s == SWG_DROPPED || s > 3) continue;
-        const char *line = p->text + p->line_off[r];
-        buf.insert(buf.end(), line, line + p->line_len[r]);
-        if (chain_id[r]) {
-            int k = snprintf(tag, sizeof tag, "\tch:Z:chain_%u", chain_id[r]);
-            buf.insert(buf.end(), tag, tag + k);
+    const size_t n = p->rank.size();
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt == 0) nt = 1;
+    const size_t window = (size_t)4 << 20; // records formatted per round (bounds the extra memory)
+    for (size_t w0 = 0; w0 < n && ok; w0 += window) {
+        const size_t w1 = std::min(n, w0 + window);
+        const size_t parts = std::max<size_t>(1, std::min<size_t>(nt, (w1 - w0) / 65536 + 1));
+        std::vector<std::vector<char>> bufs(parts);
+        std::vector<std::thread> th;
+        for (size_t k = 0; k < parts; k++) {
+            const size_t r0 = w0 + (w1 - w0) * k / parts, r1 = w0 + (w1 - w0) * (k + 1) / parts;
+            if (k + 1 < parts) th.emplace_back(format_range, p, status, chain_id, r0, r1, std::ref(bufs[k]));
+            else format_range(p, status, chain_id, r0, r1, bufs[k]);
         }
-        int k = snprintf(tag, sizeof tag, "\tst:Z:%s\n", st_name[s]);
-        buf.insert(buf.end(), tag, tag + k);
-        if (buf.size() >= ((size_t)8 << 20) - 4096) {
-            ok = ok && fwrite(buf.data(), 1, buf.size(), f) == buf.size();
-            buf.clear();
-        }
+        for (auto &t : th) t.join();
+        for (auto &b : bufs)
+            if (!b.empty()) ok = ok && fwrite(b.data(), 1, b.size(), f) == b.size();
     }
-    if (!buf.empty()) ok = ok && fwrite(buf.data(), 1, buf.size(), f) == buf.size();
     ok = (fclose(f) == 0) && ok;
     return ok ? SWG_OK : SWG_ERR_IO;
 }
