@@ -216,32 +216,71 @@ __device__ __forceinline__ bool bb_candidate(const uint4 &a, const uint4 &b, boo
     return false;
 }
 
+// Arg-min over the successors of position i inside its group (.., e): smallest d, then smallest j ("first minimal
+// j", paf_filter.rs:791-843); ELIG adds the reference's eligibility test d < best_pred_score[j].
+// The first BB_LINEAR successors are scanned in order (ordinary data: a handful of candidates).  If the window goes
+// on (dense piles: 10^4..10^5 candidates) the rest is searched outwards from the first position whose query_start
+// reaches query_end(i): d >= q_gap^2 and q_gap grows monotonically in both directions from there, so the scan stops
+// as soon as q_gap^2 exceeds the best d found — exact, and near-constant work per position in a dense pile.
+constexpr u32 BB_LINEAR = 48;
+template <bool ELIG>
+__device__ __forceinline__ void bb_best_successor(const uint4 *__restrict__ srec, const u64 *bps, u32 i, u32 e, const uint4 &a,
+                                                  bool fwd, u64 G, u64 G5, u64 &bd, u32 &bj) {
+    const u64 bound = (u64)a.y + G;
+    bd = NONE64;
+    bj = NONE32;
+    u32 j = i + 1;
+    const u32 lin_end = min(e, i + 1 + BB_LINEAR);
+    for (; j < lin_end; j++) {
+        const uint4 b = srec[j];
+        if ((u64)b.x > bound) return; // window exhausted
+        u64 d;
+        if (bb_candidate(a, b, fwd, G, G5, d) && d < bd && (!ELIG || d < bps[j])) { bd = d; bj = j; }
+    }
+    if (j >= e) return;
+    u32 lo = j, hi = e; // first position in [j, e) with query_start >= query_end(i)
+    while (lo < hi) {
+        const u32 mid = (lo + hi) >> 1;
+        if (srec[mid].x < a.y) lo = mid + 1; else hi = mid;
+    }
+    const u32 c0 = lo;
+    for (u32 r = c0; r < e; r++) { // right: q_gap = qs - qe >= 0, non-decreasing
+        const uint4 b = srec[r];
+        const u64 qg = (u64)b.x - a.y;
+        if (qg > G || qg * qg > bd) break;
+        u64 d;
+        if (bb_candidate(a, b, fwd, G, G5, d) && (d < bd || (d == bd && r < bj)) && (!ELIG || d < bps[r])) { bd = d; bj = r; }
+    }
+    for (u32 l = c0; l > j;) { // left: overlap = qe - qs > 0, non-decreasing going left
+        l--;
+        const uint4 b = srec[l];
+        const u64 ov = (u64)a.y - b.x;
+        if (ov > G5 || ov * ov > bd) break;
+        u64 d;
+        if (bb_candidate(a, b, fwd, G, G5, d) && (d < bd || (d == bd && l < bj)) && (!ELIG || d < bps[l])) { bd = d; bj = l; }
+    }
+}
+
 // P1: 24 B read (+ window re-reads served by L1) and 28 B written per position.
 __global__ void __launch_bounds__(256)
-k_chain_candidates(const uint4 *__restrict__ srec, const u64 *__restrict__ skey, const u32 *__restrict__ gid, u32 n_m, int cb,
-                   u64 G, Cand *__restrict__ cand, u64 *__restrict__ bps, u32 *__restrict__ root, u8 *__restrict__ grp_has_cand) {
+k_chain_candidates(const uint4 *__restrict__ srec, const u64 *__restrict__ skey, const u32 *__restrict__ gid,
+                   const u32 *__restrict__ gstart, u32 n_groups, u32 n_m, int cb, u64 G, Cand *__restrict__ cand,
+                   u64 *__restrict__ bps, u32 *__restrict__ root, u8 *__restrict__ grp_has_cand) {
     const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_m) return;
     const uint4 a = srec[p]; // x=qs y=qe z=ts w=te
-    const u64 grp = skey[p] >> cb;
-    const bool fwd = (grp & 1) == 0;
-    const u64 G5 = G / 5;
-    const u64 bound = (u64)a.y + G;
-    u64 bd = NONE64;
-    u32 bj = NONE32;
-    for (u32 j = p + 1; j < n_m; j++) {
-        if ((skey[j] >> cb) != grp) break;
-        const uint4 b = srec[j];
-        if ((u64)b.x > bound) break;
-        u64 d;
-        if (bb_candidate(a, b, fwd, G, G5, d) && d < bd) { bd = d; bj = j; }
-    }
+    const bool fwd = ((skey[p] >> cb) & 1) == 0;
+    const u32 g = gid[p];
+    const u32 e = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
+    u64 bd;
+    u32 bj;
+    bb_best_successor<false>(srec, nullptr, p, e, a, fwd, G, G / 5, bd, bj);
     Cand c;
     c.d = bd; c.j = bj; c.pad = 0;
     cand[p] = c;
     bps[p] = NONE64;
     root[p] = p;
-    if (bj != NONE32) grp_has_cand[gid[p]] = 1; // benign race: every writer stores 1
+    if (bj != NONE32) grp_has_cand[g] = 1; // benign race: every writer stores 1
 }
 
 // P2: one thread per group that has at least one candidate; lanes refill from the work list as they finish.
@@ -295,15 +334,9 @@ k_chain_resolve(const Cand *__restrict__ cand, const uint4 *__restrict__ srec, c
                     chosen_d = c_cur.d;
                 } else { // blocked: arg-min over the eligible candidates (paf_filter.rs:835-843)
                     const uint4 a = srec[i];
-                    const u64 bound = (u64)a.y + G;
-                    u64 bd = NONE64;
-                    u32 bj = NONE32;
-                    for (u32 j = i + 1; j < e; j++) {
-                        const uint4 b = srec[j];
-                        if ((u64)b.x > bound) break;
-                        u64 d;
-                        if (bb_candidate(a, b, fwd, G, G5, d) && d < bd && d < bps[j]) { bd = d; bj = j; }
-                    }
+                    u64 bd;
+                    u32 bj;
+                    bb_best_successor<true>(srec, bps, i, e, a, fwd, G, G5, bd, bj);
                     chosen = bj;
                     chosen_d = bd;
                 }
@@ -323,9 +356,10 @@ k_chain_resolve(const Cand *__restrict__ cand, const uint4 *__restrict__ srec, c
     }
 }
 
-// P2b: the same resolve for LARGE or DENSE groups, one warp per group: the step is decided by the whole warp and a
-// blocked step re-scans its window with 32 lanes (a thread-per-group walk would serialise a window of thousands).
-__device__ __forceinline__ void bb_argmin(u64 &bd, u32 &bj) { // smallest d, then smallest j ("first minimal j")
+// P2b: the same resolve for LARGE or DENSE groups, one warp per group.  The step is decided by the whole warp; a
+// blocked step searches its window with 32 lanes (coalesced chunks), with the same q_gap^2 pruning as
+// bb_best_successor: a single thread would pay one dependent-load latency per candidate.
+__device__ __forceinline__ void bb_argmin(u64 &bd, u32 &bj) { // smallest d, then smallest j
     const u32 full = 0xFFFFFFFFu;
     u32 hi = (u32)(bd >> 32), lo = (u32)bd;
     u32 mh = __reduce_min_sync(full, hi);
@@ -333,6 +367,69 @@ __device__ __forceinline__ void bb_argmin(u64 &bd, u32 &bj) { // smallest d, the
     bool is = hi == mh && lo == ml;
     bj = __reduce_min_sync(full, is ? bj : NONE32);
     bd = ((u64)mh << 32) | ml;
+}
+__device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__ srec, const u64 *bps, u32 i, u32 e, const uint4 &a,
+                                                       bool fwd, u64 G, u64 G5, u64 &bd, u32 &bj) {
+    const u32 full = 0xFFFFFFFFu;
+    const u32 lane = lane_id();
+    const u64 bound = (u64)a.y + G;
+    bd = NONE64;
+    bj = NONE32;
+    // linear phase: the first BB_LINEAR successors (two chunks)
+    u32 j0 = i + 1;
+    const u32 lin_end = min(e, i + 1 + 64);
+    bool exhausted = false;
+    for (; j0 < lin_end && !exhausted; j0 += 32) {
+        const u32 j = j0 + lane;
+        bool inwin = false;
+        if (j < lin_end) {
+            const uint4 b = srec[j];
+            inwin = (u64)b.x <= bound;
+            u64 d;
+            if (inwin && bb_candidate(a, b, fwd, G, G5, d) && d < bps[j] && (d < bd || (d == bd && j < bj))) { bd = d; bj = j; }
+        }
+        exhausted = !__all_sync(full, inwin || j >= lin_end) ;
+    }
+    bb_argmin(bd, bj);
+    if (exhausted || lin_end >= e) return;
+    const u32 jl = lin_end; // the rest of the window is [jl, ...)
+    u32 lo = jl, hi = e;
+    while (lo < hi) { // lane-uniform binary search (broadcast loads)
+        const u32 mid = (lo + hi) >> 1;
+        if (srec[mid].x < a.y) lo = mid + 1; else hi = mid;
+    }
+    const u32 c0 = lo;
+    for (u32 base = c0; base < e; base += 32) { // right side, q_gap >= 0 non-decreasing
+        const u64 qg0 = (u64)srec[base].x - a.y;
+        if (qg0 > G || qg0 * qg0 > bd) break;
+        const u32 r = base + lane;
+        u64 ld = NONE64;
+        u32 lj = NONE32;
+        if (r < e) {
+            const uint4 b = srec[r];
+            const u64 qg = (u64)b.x - a.y;
+            u64 d;
+            if (qg <= G && bb_candidate(a, b, fwd, G, G5, d) && d < bps[r]) { ld = d; lj = r; }
+        }
+        bb_argmin(ld, lj);
+        if (ld < bd || (ld == bd && lj < bj)) { bd = ld; bj = lj; }
+    }
+    for (u32 top = c0; top > jl;) { // left side, overlap > 0 non-decreasing going left; chunk = [top-32, top)
+        const u64 ov0 = (u64)a.y - srec[top - 1].x;
+        if (ov0 > G5 || ov0 * ov0 > bd) break;
+        const u32 cnt = min(32u, top - jl);
+        const u32 l = top - 1 - lane;
+        u64 ld = NONE64;
+        u32 lj = NONE32;
+        if (lane < cnt) {
+            const uint4 b = srec[l];
+            u64 d;
+            if (bb_candidate(a, b, fwd, G, G5, d) && d < bps[l]) { ld = d; lj = l; }
+        }
+        bb_argmin(ld, lj);
+        if (ld < bd || (ld == bd && lj < bj)) { bd = ld; bj = lj; }
+        top -= cnt;
+    }
 }
 __global__ void __launch_bounds__(128)
 k_chain_resolve_warp(const Cand *__restrict__ cand, const uint4 *__restrict__ srec, const u64 *__restrict__ skey,
@@ -358,21 +455,9 @@ k_chain_resolve_warp(const Cand *__restrict__ cand, const uint4 *__restrict__ sr
                 if (lane == 0) { bps[c.j] = c.d; root[c.j] = ri; }
             } else {
                 const uint4 a = srec[i];
-                const u64 bound = (u64)a.y + G;
-                u64 bd = NONE64;
-                u32 bj = NONE32;
-                for (u32 base = i + 1; base < e; base += 32) {
-                    const u32 j = base + lane;
-                    bool inwin = false;
-                    if (j < e) {
-                        const uint4 b = srec[j];
-                        inwin = (u64)b.x <= bound;
-                        u64 d;
-                        if (inwin && bb_candidate(a, b, fwd, G, G5, d) && d < bd && d < bps[j]) { bd = d; bj = j; }
-                    }
-                    if (!__all_sync(full, inwin)) break;
-                }
-                bb_argmin(bd, bj);
+                u64 bd;
+                u32 bj;
+                bb_best_successor_warp(srec, bps, i, e, a, fwd, G, G5, bd, bj);
                 if (lane == 0 && bj != NONE32) { bps[bj] = bd; root[bj] = ri; }
             }
             __syncwarp();

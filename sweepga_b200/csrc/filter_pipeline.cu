@@ -408,7 +408,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         k_chain_work_estimate<<<cdiv(n_groups, 256), 256, 0, st>>>(srec, gstart, n_groups, n_m, cfg.scaffold_gap, ctr);
         lc.n++;
         read_counters(c);
-        static const double max_evals = getenv("SWG_MAX_PAIR_EVALS") ? atof(getenv("SWG_MAX_PAIR_EVALS")) : 2e12;
+        static const double max_evals = getenv("SWG_MAX_PAIR_EVALS") ? atof(getenv("SWG_MAX_PAIR_EVALS")) : 1e15;
         if ((double)c->h_ctr[C_WORK] > max_evals)
             throw RangeError{"chaining would need ~" + std::to_string((double)c->h_ctr[C_WORK]) +
                              " candidate evaluations (dense pile); raise SWG_MAX_PAIR_EVALS to run it anyway"};
@@ -429,7 +429,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     SWG_CUDA(cudaMemsetAsync(grp_has_cand, 0, n_groups, st));
     SWG_CUDA(cudaMemsetAsync(cs.grp_minidx, 0xFF, sizeof(u32) * (size_t)n_groups, st));
     {
-        k_chain_candidates<<<cdiv(n_m, 256), 256, 0, st>>>(srec, skey, gid, n_m, gshift, cfg.scaffold_gap, cand, bps, root, grp_has_cand);
+        k_chain_candidates<<<cdiv(n_m, 256), 256, 0, st>>>(srec, skey, gid, gstart, n_groups, n_m, gshift, cfg.scaffold_gap, cand, bps, root, grp_has_cand);
         lc.n++;
         // work lists: groups with at least one candidate, split into ordinary (thread per group) and large/dense
         // (warp per group: size > 4096 or an expected window > 64 candidates)
@@ -450,7 +450,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                                                              bps, root, bb_ctr + 1);
         k_chain_resolve_warp<<<(u32)c->sm_count * 4, 128, 0, st>>>(cand, srec, skey, gstart, n_groups, n_m, work_big, bb_ctr + 2, gshift,
                                                                   cfg.scaffold_gap, bps, root, bb_ctr + 3);
-        lc.n++;
+        lc.n += 2;
         k_chain_heads<<<cdiv(n_m, 256), 256, 0, st>>>(srec, srec2, sidx, gid, root, n_m, cs);
         k_chain_members<<<cdiv(n_m, 256), 256, 0, st>>>(srec, srec2, root, n_m, cs);
         lc.n += 3;

@@ -119,6 +119,17 @@ def test_fuzz_dense(ctx, seed):
     check(ctx, cfg, t, f"fuzz{seed}")
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_dense_windows(ctx, seed):
+    """Groups of ~10^3 mappings with hundreds of candidates per window: the chaining leaves the linear scan and
+    searches outwards from query_end with the q_gap^2 bound (bb_best_successor), blocked steps included."""
+    t = fuzz_table(500 + seed, 6000, n_genomes=1, n_chr=2, span=[4000, 20000][seed % 2], max_len=[400, 60][seed // 4 % 2],
+                   zero_len_frac=0.0)
+    cfg = swg.FilterConfig.from_cli(scaffold_jump=str([200, 1000, 3000, 50][seed % 4]), scaffold_mass=str([0, 300][seed % 2]),
+                                    scaffold_dist=str([0, 500][seed % 2]), keep_self=True)
+    check(ctx, cfg, t, f"dense{seed}")
+
+
 def test_edge_cases(ctx):
     cfg = swg.FilterConfig.from_cli(scaffold_mass="0")
     names = ["A#1#c1", "B#1#c1"]
