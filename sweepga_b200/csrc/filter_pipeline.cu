@@ -13,6 +13,7 @@
 //   K6  inversion capture                                paf_filter.rs:535-597
 //   K7  rescue                                           paf_filter.rs:613-732
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -105,6 +106,9 @@ struct swg_ctx {
     cudaEvent_t ev_sort[2] = {nullptr, nullptr}; // bracket the one-sweep passes of the record sort
     int sort_passes = 0;
     u64 sort_pairs = 0;
+    std::vector<cudaEvent_t> stage_ev;      // SWG_STAGE_TIMING=1: events at stage boundaries of the last call
+    std::vector<const char *> stage_name;
+    size_t stage_used = 0;
     const u32 *last_keyA = nullptr, *last_keyB = nullptr; // order keys of the kept chains of the last call (arena memory)
     u64 last_n_chains = 0;
     Arena arena;      // per-call scratch
@@ -120,6 +124,30 @@ static std::string g_create_error;
 namespace swg {
 
 static void set_err(swg_ctx *c, const std::string &m) { if (c) c->err = m; else g_create_error = m; }
+
+static void stage_mark(swg_ctx *c, const char *name) {
+    static const bool on = getenv("SWG_STAGE_TIMING") != nullptr;
+    if (!on) return;
+    if (c->stage_used == c->stage_ev.size()) {
+        cudaEvent_t e;
+        SWG_CUDA(cudaEventCreate(&e));
+        c->stage_ev.push_back(e);
+        c->stage_name.push_back(name);
+    }
+    c->stage_name[c->stage_used] = name;
+    SWG_CUDA(cudaEventRecord(c->stage_ev[c->stage_used++], c->stream));
+}
+static void stage_report(swg_ctx *c) {
+    if (c->stage_used < 2) return;
+    cudaStreamSynchronize(c->stream);
+    fprintf(stderr, "[swg stages]");
+    for (size_t i = 0; i + 1 < c->stage_used; i++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->stage_ev[i], c->stage_ev[i + 1]);
+        fprintf(stderr, " %s %.3f", c->stage_name[i], ms);
+    }
+    fprintf(stderr, "\n");
+}
 
 static void read_counters(swg_ctx *c) {
     SWG_CUDA(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(u64) * C_COUNT, cudaMemcpyDeviceToHost, c->stream));
@@ -248,9 +276,12 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     SWG_CUDA(cudaMemsetAsync(chain_id, 0, sizeof(u32) * (size_t)N, st));
     c->sort_passes = 0;
     c->sort_pairs = 0;
+    c->stage_used = 0;
     c->last_n_chains = 0;
     c->last_keyA = c->last_keyB = nullptr;
     auto finish = [&]() {
+        stage_mark(c, "end");
+        stage_report(c);
         S.gpu_launches = lc.n - launches0;
         if (c->sort_passes) { // all work has been synchronised by the last counter read
             float ms = 0;
@@ -270,6 +301,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     u64 *ctr = c->d_ctr;
     SWG_CUDA(cudaMemsetAsync(ctr, 0, sizeof(u64) * C_COUNT, st));
 
+    stage_mark(c, "prefilter");
     // ---- K0 ------------------------------------------------------------------------------
     u8 *flags = A.take<u8>(N);
     // distinct genome pairs <= min(N, nP^2); table of 2x that, power of two
@@ -299,6 +331,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     const int cb = bits_for(maxcoord);
     const int pb = sb; // prefix ids are < n_seq
 
+    stage_mark(c, "primary_sweep");
     // ---- primary plane sweep (paf_filter.rs:972-1123) ----------------------------------------
     u64 qlim, tlim;
     switch (cfg.mapping_filter_mode) {
@@ -342,6 +375,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     }
 
     // ---- K1 + sort + K2: group by (q,t,strand), stable order by query_start ------------------------
+    stage_mark(c, "keys+sort");
     u64 *keys = A.take<u64>(N), *keys2 = A.take<u64>(N);
     u32 *vals = A.take<u32>(N), *vals2 = A.take<u32>(N);
     int gshift = cb; // group id of a sorted position = skey >> gshift
@@ -382,6 +416,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     S.n_after_sweep = n_m;
     S.score_near_ties = c->h_ctr[C_NEAR_TIES];
     if (n_m == 0) { finish(); return; }
+    stage_mark(c, "groups+gather");
     const u64 *skey = keys;
     const u32 *sidx = vals;
     uint4 *srec = A.take<uint4>(n_m);
@@ -408,12 +443,13 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         k_chain_work_estimate<<<cdiv(n_groups, 256), 256, 0, st>>>(srec, gstart, n_groups, n_m, cfg.scaffold_gap, ctr);
         lc.n++;
         read_counters(c);
-        static const double max_evals = getenv("SWG_MAX_PAIR_EVALS") ? atof(getenv("SWG_MAX_PAIR_EVALS")) : 1e15;
+        static const double max_evals = getenv("SWG_MAX_PAIR_EVALS") ? atof(getenv("SWG_MAX_PAIR_EVALS")) : 5e12;
         if ((double)c->h_ctr[C_WORK] > max_evals)
             throw RangeError{"chaining would need ~" + std::to_string((double)c->h_ctr[C_WORK]) +
                              " candidate evaluations (dense pile); raise SWG_MAX_PAIR_EVALS to run it anyway"};
     }
 
+    stage_mark(c, "chaining");
     // ---- K3: best-buddy chaining (candidates -> sequential resolve -> aggregates) -------------------
     u64 *bps = A.take<u64>(n_m);
     u32 *root = A.take<u32>(n_m);
@@ -456,6 +492,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         lc.n += 3;
     }
 
+    stage_mark(c, "chain_table");
     // ---- K4: dense chain table + mass/identity filter + order key (A,B) ----------------------------
     // upper bound on chains is n_m; the table is sized after counting heads
     u32 *chain_of_pos = A.take<u32>(n_m);
@@ -516,6 +553,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     const u64 pass_zero = c->h_ctr[C_PASS_ZEROSPAN];
     S.n_chains_after_mass = C1;
 
+    stage_mark(c, "chain_order");
     // ---- O*: t-space = passing chains in the reference's `filtered_chains` order ------------------
     // oc_chain[t] = dense chain id of the t-th filtered chain
     const u32 *oc_chain = oval;
@@ -602,6 +640,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     c->last_n_chains = C2;
     S.n_chains_kept = C2;
 
+    stage_mark(c, "assign+inversion+rescue");
     // ---- K5: anchors = members of kept chains (paf_filter.rs:517-528) ---------------------------------
     launch_for<t_assign>(n_m, st, lc, [=] __device__(u32 p) {
         u32 ci = chain_of_pos[root[p]];
@@ -740,6 +779,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         }
     }
 
+    stage_mark(c, "stats");
     // ---- stats ---------------------------------------------------------------------------------
     k_count_status<<<std::min<u32>(cdiv(N, 256), (u32)c->sm_count * 8), 256, 0, st>>>(N, status, ctr);
     lc.n++;
