@@ -624,18 +624,20 @@ __global__ void __launch_bounds__(128)
 k_sweep_groups(const u32 *__restrict__ eitem /* item * 2 + type, in (group, pos, type) order */, const u32 *__restrict__ gstart, u32 n_groups,
                u32 n_events, const u32 *__restrict__ it_start, const u32 *__restrict__ it_end,
                const double *__restrict__ it_score, u64 n_keep, double thr, ActEntry *act, u8 *good, u8 *flagged,
-               u8 *__restrict__ keep, u32 *group_counter, u64 *ctr) {
+               const u32 *__restrict__ work, const u32 *__restrict__ n_work_ptr, u32 *group_counter, u64 *ctr) {
     const u32 full = 0xFFFFFFFFu;
     const u32 lane = lane_id();
+    const u32 n_work = *n_work_ptr;
     while (true) {
-        u32 g = 0;
-        if (lane == 0) g = atomicAdd(group_counter, 1u);
-        g = __shfl_sync(full, g, 0);
-        if (g >= n_groups) break;
+        u32 w = 0;
+        if (lane == 0) w = atomicAdd(group_counter, 1u);
+        w = __shfl_sync(full, w, 0);
+        if (w >= n_work) break;
+        const u32 g = work[w];
         const u32 es = gstart[g], ee = (g + 1 < n_groups) ? gstart[g + 1] : n_events;
         const u32 items = (ee - es) >> 1;
         if (items <= 1) { // plane_sweep_exact.rs:274-276
-            if (lane == 0) keep[eitem[es] >> 1] = 1;
+            if (lane == 0) good[eitem[es] >> 1] = 1;
             continue;
         }
         ActEntry *A = act + (es >> 1);
@@ -713,14 +715,108 @@ k_sweep_groups(const u32 *__restrict__ eitem /* item * 2 + type, in (group, pos,
             }
             __syncwarp();
         }
-        // result for this group
-        for (u32 b = es + lane; b < ee; b += 32) {
-            if ((eitem[b] & 1) == 0) {
-                u32 item = eitem[b] >> 1;
-                keep[item] = (good[item] && !flagged[item]) ? 1 : 0;
+        __syncwarp();
+    }
+}
+
+// Per-event copies of what the walker needs, in event order, so that a group is one contiguous stream
+struct SweepEvent {
+    u64 skey;  // score_desc_key of the item
+    u32 start; // axis interval of the item
+    u32 end;
+};
+// The same sweep, ONE THREAD PER GROUP, for the ordinary case (a (sequence, partner-genome) group of ~10^2 intervals
+// with a pile depth of a few): the active set lives in a small per-thread array; a group whose depth exceeds
+// SW_DEPTH is handed to the warp kernel above (good/flagged are monotone, so the redo is idempotent).
+constexpr int SW_DEPTH = 12;
+__global__ void __launch_bounds__(128)
+k_sweep_small(const u32 *__restrict__ eitem, const SweepEvent *__restrict__ edata, const u32 *__restrict__ gstart, u32 n_groups,
+              u32 n_events, u64 n_keep, double thr, u8 *good, u8 *flagged, u32 *big_list, u32 *big_count, u32 *group_counter, u64 *ctr) {
+    const u32 full = 0xFFFFFFFFu;
+    bool active = false, exhausted = false;
+    u32 g = 0, e = 0, ee = 0, size = 0;
+    u64 a_key[SW_DEPTH];
+    u32 a_start[SW_DEPTH], a_end[SW_DEPTH], a_item[SW_DEPTH]; // a_item: item * 4 | (flagged << 1) | good-written
+    while (true) {
+        const u32 need = __ballot_sync(full, !active && !exhausted);
+        if (need) {
+            const u32 leader = __ffs(need) - 1;
+            u32 base = 0;
+            if (lane_id() == leader) base = atomicAdd(group_counter, (u32)__popc(need));
+            base = __shfl_sync(full, base, leader);
+            if (!active && !exhausted) {
+                g = base + __popc(need & lanemask_lt());
+                if (g >= n_groups) exhausted = true;
+                else {
+                    e = gstart[g];
+                    ee = (g + 1 < n_groups) ? gstart[g + 1] : n_events;
+                    if (ee - e <= 2) good[eitem[e] >> 1] = 1; // a single interval: kept (plane_sweep_exact.rs:274-276)
+                    else { active = true; size = 0; }
+                }
             }
         }
-        __syncwarp();
+        if (__all_sync(full, exhausted && !active)) break;
+        if (active) {
+            // one event position per iteration: apply its Begins then Ends, then mark_good
+            const u32 ev0 = eitem[e];
+            const SweepEvent d0 = edata[e];
+            const u32 cur = (ev0 & 1) ? d0.end : d0.start;
+            bool overflow = false;
+            while (e < ee) {
+                const u32 ev = eitem[e];
+                const SweepEvent d = edata[e];
+                if (((ev & 1) ? d.end : d.start) != cur) break;
+                const u32 item = ev >> 1;
+                if (!(ev & 1)) { // Begin: insert in (score desc, start asc, item asc) order
+                    if (size == SW_DEPTH) { overflow = true; break; }
+                    u32 pos = size;
+                    while (pos > 0) {
+                        const u32 q = pos - 1;
+                        const bool less = a_key[q] < d.skey || (a_key[q] == d.skey && (a_start[q] < d.start || (a_start[q] == d.start && (a_item[q] >> 2) < item)));
+                        if (less) break;
+                        a_key[pos] = a_key[q]; a_start[pos] = a_start[q]; a_end[pos] = a_end[q]; a_item[pos] = a_item[q];
+                        pos--;
+                    }
+                    a_key[pos] = d.skey; a_start[pos] = d.start; a_end[pos] = d.end; a_item[pos] = item << 2;
+                    u32 near = 0; // near-tie audit: neighbours whose score key differs by <= 2 ulp but is not equal
+                    if (pos > 0) { const u64 df = d.skey - a_key[pos - 1]; near += (df != 0 && df <= 2); }
+                    if (pos < size) { const u64 df = a_key[pos + 1] - d.skey; near += (df != 0 && df <= 2); }
+                    if (near) atomicAdd((unsigned long long *)&ctr[C_NEAR_TIES], (unsigned long long)near);
+                    size++;
+                } else { // End: remove
+                    u32 pos = 0;
+                    while (pos < size && (a_item[pos] >> 2) != item) pos++;
+                    for (u32 q = pos; q + 1 < size; q++) {
+                        a_key[q] = a_key[q + 1]; a_start[q] = a_start[q + 1]; a_end[q] = a_end[q + 1]; a_item[q] = a_item[q + 1];
+                    }
+                    size--;
+                }
+                e++;
+            }
+            if (overflow) {
+                big_list[atomicAdd(big_count, 1u)] = g; // pile deeper than SW_DEPTH: the warp kernel redoes this group
+                active = false;
+            } else {
+                if (size > 0) { // mark_good, plane_sweep_exact.rs:197-259
+                    const u32 top = (u64)size <= n_keep ? size : (u32)n_keep;
+                    for (u32 b = 0; b < top; b++)
+                        if (!(a_item[b] & 1)) { good[a_item[b] >> 2] = 1; a_item[b] |= 1; }
+                    if (thr < 1.0) {
+                        for (u32 b = top; b < size; b++) {
+                            if (a_item[b] & 2) continue;
+                            for (u32 t = 0; t < top; t++) {
+                                if (overlaps_more_than(a_start[b], a_end[b], a_start[t], a_end[t], thr)) {
+                                    flagged[a_item[b] >> 2] = 1;
+                                    a_item[b] |= 2;
+                                    break;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (e >= ee) active = false;
+            }
+        }
     }
 }
 

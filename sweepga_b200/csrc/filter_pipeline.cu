@@ -41,7 +41,7 @@ template <class Tag, class F> static inline void launch_for(u32 n, cudaStream_t 
     k_for<Tag, F><<<cdiv(n, 256), 256, 0, st>>>(n, f);
     lc.n++;
 }
-struct t_iota; struct t_gather; struct t_maxp; struct t_scores; struct t_gkey; struct t_events; struct t_chain_order; struct t_tspace; struct t_segfirst;
+struct t_iota; struct t_sweep_gather; struct t_sweep_keep; struct t_gather; struct t_maxp; struct t_scores; struct t_gkey; struct t_events; struct t_chain_order; struct t_tspace; struct t_segfirst;
 struct t_segapply; struct t_keys_c2min; struct t_keys_g2min; struct t_final_k; struct t_assign; struct t_invkeys; struct t_invtab;
 struct t_inversion; struct t_anchor_keys; struct t_rescue; struct t_count_kept; struct t_chain_score;
 
@@ -186,6 +186,7 @@ static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 in
     u32 *ev = c->arena.take<u32>(n_ev_all), *ev2 = c->arena.take<u32>(n_ev_all);
     u64 *ctr = c->d_ctr;
     SWG_CUDA(cudaMemsetAsync(ctr + C_TMP0, 0, sizeof(u64), st));
+    stage_mark(c, "gs_events");
     // events: payload = item * 2 + type; order = (group, position, Begin before End).  One sort when the key fits
     // 64 bits, else two chained stable sorts (position|type first, then the group id).
     const bool wide = (gb + 33 > 64) || (getenv("SWG_FORCE_WIDE_KEYS") != nullptr);
@@ -204,6 +205,7 @@ static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 in
         if (cnt && (threadIdx.x & 31) == (u32)(__ffs(am) - 1)) atomicAdd((unsigned long long *)&ctr[C_TMP0], (unsigned long long)cnt);
     });
     int eshift = 33;
+    stage_mark(c, "gs_sort");
     if (!wide) {
         sort_pairs(c, ek, ek2, ev, ev2, n_ev_all, gb + 33);
     } else {
@@ -220,6 +222,7 @@ static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 in
         sort_pairs(c, ek, ek2, ev, ev2, n_ev_all, gb + 1);
         eshift = 0;
     }
+    stage_mark(c, "gs_groups");
     read_counters(c);
     u32 n_ev = (u32)(c->h_ctr[C_TMP0] * 2);
     if (n_ev == 0) return;
@@ -230,15 +233,42 @@ static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 in
     scan_apply([=] __device__(u32 u) -> u32 { return (u == 0 || (ekc[u] >> eshift) != (ekc[u - 1] >> eshift)) ? 1u : 0u; },
                [=] __device__(u32 u, u32 ex, u32 v) { if (v) gstart[ex] = u; }, n_ev, bsum, d_ng, st, c->lc);
     u32 n_groups = read_u32(c, d_ng);
-    ActEntry *act = c->arena.take<ActEntry>(n_ev / 2 + 1);
     u8 *good = c->arena.take<u8>(n_items), *flagged = c->arena.take<u8>(n_items);
     SWG_CUDA(cudaMemsetAsync(good, 0, n_items, st));
     SWG_CUDA(cudaMemsetAsync(flagged, 0, n_items, st));
-    SWG_CUDA(cudaMemsetAsync(d_ng + 1, 0, sizeof(u32), st));
-    u32 blocks = std::min<u32>(cdiv(n_groups, 4), (u32)c->sm_count * 8);
-    k_sweep_groups<<<blocks, 128, 0, st>>>(ev, gstart, n_groups, n_ev, it_start, it_end, it_score, n_keep, thr, act, good,
-                                          flagged, keep, d_ng + 1, ctr);
-    c->lc.n++;
+    // per-event copies (score key, axis interval) in event order: a group becomes one contiguous stream
+    SweepEvent *edata = c->arena.take<SweepEvent>(n_ev);
+    {
+        const u32 *evc = ev;
+        launch_for<t_sweep_gather>(n_ev, st, c->lc, [=] __device__(u32 u) {
+            const u32 i = evc[u] >> 1;
+            SweepEvent d;
+            d.skey = score_desc_key(it_score[i]);
+            d.start = it_start[i];
+            d.end = it_end[i];
+            edata[u] = d;
+        });
+    }
+    u32 *big_list = c->arena.take<u32>(n_groups + 1);
+    u32 *sw_ctr = c->arena.take<u32>(4); // [0] thread-kernel group counter, [1] deep groups, [2] warp-kernel work counter
+    SWG_CUDA(cudaMemsetAsync(sw_ctr, 0, 4 * sizeof(u32), st));
+    stage_mark(c, "gs_sweep");
+    k_sweep_small<<<(u32)c->sm_count * 4, 128, 0, st>>>(ev, edata, gstart, n_groups, n_ev, n_keep, thr, good, flagged, big_list, sw_ctr + 1,
+                                                       sw_ctr, ctr);
+    // groups whose pile is deeper than the per-thread array: one warp each, active set in global scratch
+    ActEntry *act = c->arena.take<ActEntry>(n_ev / 2 + 1);
+    k_sweep_groups<<<(u32)c->sm_count * 4, 128, 0, st>>>(ev, gstart, n_groups, n_ev, it_start, it_end, it_score, n_keep, thr, act, good,
+                                                        flagged, big_list, sw_ctr + 1, sw_ctr + 2, ctr);
+    {
+        const u32 *evc = ev;
+        launch_for<t_sweep_keep>(n_ev, st, c->lc, [=] __device__(u32 u) {
+            if (evc[u] & 1) return;
+            const u32 i = evc[u] >> 1;
+            keep[i] = (good[i] && !flagged[i]) ? 1 : 0;
+        });
+    }
+    c->lc.n += 2;
+    stage_mark(c, "gs_done");
     SWG_CUDA(cudaGetLastError());
 }
 
