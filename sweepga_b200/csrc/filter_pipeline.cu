@@ -174,7 +174,7 @@ static void sort_pairs(swg_ctx *c, u64 *&k, u64 *&k2, u32 *&v, u32 *&v2, u32 n, 
 
 // ---- general plane sweep over arbitrary items (records or chains) ----------------------------
 // include == nullptr: all items.  gkey < 2^gb - 1.  keep[] is fully overwritten (0 for excluded).
-static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 include_mask, const u64 *gkey, int gb,
+static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 include_mask, const u64 *gkey, int gb, int pbits,
                                const u32 *it_start, const u32 *it_end, const double *it_score, u64 n_keep, double thr, u8 *keep) {
     cudaStream_t st = c->stream;
     SWG_CUDA(cudaMemsetAsync(keep, 0, n_items, st));
@@ -189,12 +189,13 @@ static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 in
     stage_mark(c, "gs_events");
     // events: payload = item * 2 + type; order = (group, position, Begin before End).  One sort when the key fits
     // 64 bits, else two chained stable sorts (position|type first, then the group id).
-    const bool wide = (gb + 33 > 64) || (getenv("SWG_FORCE_WIDE_KEYS") != nullptr);
+    const int pshift = pbits + 1; // position | type
+    const bool wide = (gb + pshift > 64) || (getenv("SWG_FORCE_WIDE_KEYS") != nullptr);
     launch_for<t_events>(n_items, st, c->lc, [=] __device__(u32 i) {
         bool inc = include ? (include[i] & include_mask) != 0 : true;
         u64 k0 = NONE64, k1 = NONE64;
         if (inc) {
-            const u64 g = wide ? 0 : (gkey[i] << 33);
+            const u64 g = wide ? 0 : (gkey[i] << pshift);
             k0 = g | ((u64)it_start[i] << 1);
             k1 = g | ((u64)it_end[i] << 1) | 1;
         }
@@ -204,12 +205,12 @@ static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 in
         u32 cnt = __popc(__ballot_sync(am, inc));
         if (cnt && (threadIdx.x & 31) == (u32)(__ffs(am) - 1)) atomicAdd((unsigned long long *)&ctr[C_TMP0], (unsigned long long)cnt);
     });
-    int eshift = 33;
+    int eshift = pshift;
     stage_mark(c, "gs_sort");
     if (!wide) {
-        sort_pairs(c, ek, ek2, ev, ev2, n_ev_all, gb + 33);
+        sort_pairs(c, ek, ek2, ev, ev2, n_ev_all, gb + pshift);
     } else {
-        sort_pairs(c, ek, ek2, ev, ev2, n_ev_all, 33);
+        sort_pairs(c, ek, ek2, ev, ev2, n_ev_all, pshift);
         {
             u64 *kk = ek;
             const u32 *vv = ev;
@@ -272,10 +273,10 @@ static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 in
     SWG_CUDA(cudaGetLastError());
 }
 
-static void general_sweep(swg_ctx *c, u32 n_items, const u8 *include, u8 include_mask, const u64 *gkey, int gb,
+static void general_sweep(swg_ctx *c, u32 n_items, const u8 *include, u8 include_mask, const u64 *gkey, int gb, int pbits,
                           const u32 *it_start, const u32 *it_end, const double *it_score, u64 n_keep, double thr, u8 *keep) {
     Arena::Mark mk = c->arena.mark(); // temporaries are stream-ordered: safe to reuse after the launches are queued
-    general_sweep_impl(c, n_items, include, include_mask, gkey, gb, it_start, it_end, it_score, n_keep, thr, keep);
+    general_sweep_impl(c, n_items, include, include_mask, gkey, gb, pbits, it_start, it_end, it_score, n_keep, thr, keep);
     c->arena.rewind(mk);
 }
 
@@ -387,7 +388,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                 gk[i] = ((u64)a << pb) | in.P[b];
             });
             u8 *keep = A.take<u8>(N);
-            general_sweep(c, N, flags, F_ALIVE, gk, sb + pb, axis == 0 ? in.qs : in.ts, axis == 0 ? in.qe : in.te, rscore,
+            general_sweep(c, N, flags, F_ALIVE, gk, sb + pb, cb, axis == 0 ? in.qs : in.ts, axis == 0 ? in.qe : in.te, rscore,
                           axis == 0 ? qlim : tlim, cfg.overlap_threshold, keep);
             (axis == 0 ? keep_q : keep_t) = keep;
         }
@@ -627,8 +628,8 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         if (need_sweep) {
             u8 *k1 = A.take<u8>(C1);
             t_keep = A.take<u8>(C1);
-            general_sweep(c, C1, nullptr, 0, t_c2key, 2 * sb, t_qs, t_qe, t_score, nq, cfg.scaffold_overlap_threshold, k1);
-            general_sweep(c, C1, k1, 1, t_c2key, 2 * sb, t_ts, t_te, t_score, nt, cfg.scaffold_overlap_threshold, t_keep);
+            general_sweep(c, C1, nullptr, 0, t_c2key, 2 * sb, cb, t_qs, t_qe, t_score, nq, cfg.scaffold_overlap_threshold, k1);
+            general_sweep(c, C1, k1, 1, t_c2key, 2 * sb, cb, t_ts, t_te, t_score, nt, cfg.scaffold_overlap_threshold, t_keep);
         }
         // final order: (g2min, c2min, t): two stable sorts, least significant first (t is the input order)
         const int ob = bits_for(C1);
@@ -923,11 +924,11 @@ static void do_sweep(void *p) {
     const int scoring = a->scoring;
     launch_for<t_scores>(n, st, c->lc, [=] __device__(u32 i) { score[i] = score_fn(scoring, id[i], qs[i], qe[i]); });
     u8 *res = k1;
-    if (a->axis == 0) general_sweep(c, n, nullptr, 0, gk, 1, qs, qe, score, a->nq, a->thr, k1);
-    else if (a->axis == 1) general_sweep(c, n, nullptr, 0, gk, 1, ts, te, score, a->nt, a->thr, k1);
+    if (a->axis == 0) general_sweep(c, n, nullptr, 0, gk, 1, 32, qs, qe, score, a->nq, a->thr, k1);
+    else if (a->axis == 1) general_sweep(c, n, nullptr, 0, gk, 1, 32, ts, te, score, a->nt, a->thr, k1);
     else {
-        general_sweep(c, n, nullptr, 0, gk, 1, qs, qe, score, a->nq, a->thr, k1);
-        general_sweep(c, n, k1, 1, gk, 1, ts, te, score, a->nt, a->thr, k2);
+        general_sweep(c, n, nullptr, 0, gk, 1, 32, qs, qe, score, a->nq, a->thr, k1);
+        general_sweep(c, n, k1, 1, gk, 1, 32, ts, te, score, a->nt, a->thr, k2);
         res = k2;
     }
     SWG_CUDA(cudaMemcpyAsync(a->keep, res, n, cudaMemcpyDeviceToHost, st));
