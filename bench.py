@@ -244,12 +244,14 @@ def main():
     for _ in range(min(args.warmup, 2)):
         ctx.filter(cfg, pt, out_s, out_c)
     barrier()
-    e2e_ms, t0 = 0.0, time.perf_counter()
-    for _ in range(args.steps):
-        _, _, st2 = ctx.filter(cfg, pt, out_s, out_c)
-        e2e_ms += st2.ms_h2d + st2.ms_device + st2.ms_d2h
-    barrier()
-    wall_e2e = time.perf_counter() - t0
+    with ClockSampler(local_rank) as clk2:  # the e2e loop is the longer timed region: more clock samples under load
+        e2e_ms, t0 = 0.0, time.perf_counter()
+        for _ in range(args.steps):
+            _, _, st2 = ctx.filter(cfg, pt, out_s, out_c)
+            e2e_ms += st2.ms_h2d + st2.ms_device + st2.ms_d2h
+        barrier()
+        wall_e2e = time.perf_counter() - t0
+    clk.rows += clk2.rows
     assert np.array_equal(out_s, status_dev) and np.array_equal(out_c, chain_dev), "e2e and device-resident results differ"
     h2d = n * (8 * 4 + 8 + 1) + table.n_seq * 8
     d2h = n * 5

@@ -23,7 +23,8 @@ HUMAN_LENGTHS = [248956422, 242193529, 198295559, 190214555, 181538259, 17080597
 def _segment_cumsum(x, seg_start_idx, seg_id):
     """exclusive cumulative sum of x restarted at each segment"""
     c = np.cumsum(x, dtype=np.int64) - x
-    return c - c[seg_start_idx][seg_id]
+    start = np.minimum(seg_start_idx, max(len(x) - 1, 0))  # empty trailing segments point one past the end (never used)
+    return c - c[start][seg_id]
 
 
 def pangenome(genomes, chroms, lengths, n_records, seed, block_mu, block_sigma, block_clip, self_genome=True,
