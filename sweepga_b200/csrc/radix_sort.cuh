@@ -50,16 +50,26 @@ __global__ void __launch_bounds__(512) rs_histogram_kernel(const u64 *__restrict
     // 128-bit loads: two keys per thread per step
     const ulonglong2 *k2 = reinterpret_cast<const ulonglong2 *>(keys);
     u32 n2 = n >> 1;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
-        ulonglong2 v = k2[i];
+    const u32 lane = threadIdx.x & 31;
+    // warp-uniform trip count (the body uses full-mask warp votes)
+    for (u32 wbase = (blockIdx.x * blockDim.x + threadIdx.x) - lane; wbase < n2; wbase += gridDim.x * blockDim.x) {
+        const u32 i = wbase + lane;
+        const bool ok = i < n2;
+        ulonglong2 v = ok ? k2[i] : make_ulonglong2(0, 0);
         u64 a = v.x >> begin_bit, b = v.y >> begin_bit;
 #pragma unroll
         for (int p = 0; p < RS_MAX_PASSES; p++) {
             if (p < passes) {
                 u32 da = (u32)(a >> (p * RS_BITS)) & (RS_RADIX - 1);
                 u32 db = (u32)(b >> (p * RS_BITS)) & (RS_RADIX - 1);
-                if (da == db) atomicAdd(&sh[p * RS_RADIX + da], 2u);
-                else { atomicAdd(&sh[p * RS_RADIX + da], 1u); atomicAdd(&sh[p * RS_RADIX + db], 1u); }
+                // high-order digits of grouped input are usually the same across the warp: one atomic for all 64 keys
+                const u32 d0 = __shfl_sync(0xFFFFFFFFu, da, 0);
+                if (__all_sync(0xFFFFFFFFu, ok && da == d0 && db == d0)) {
+                    if (lane == 0) atomicAdd(&sh[p * RS_RADIX + d0], 64u);
+                } else if (ok) {
+                    if (da == db) atomicAdd(&sh[p * RS_RADIX + da], 2u);
+                    else { atomicAdd(&sh[p * RS_RADIX + da], 1u); atomicAdd(&sh[p * RS_RADIX + db], 1u); }
+                }
             }
         }
     }
