@@ -13,7 +13,7 @@ for spec in sys.argv[1:]:
     extra = [f"-D{x}" for x in parts[4:]]
     out = f"/tmp/libswg_{spec}.so"
     cmd = ["nvcc"] + ge.NVCC_FLAGS + [f"-DSWG_RS_THREADS={th}", f"-DSWG_RS_ITEMS={it}", f"-DSWG_RS_LOOKBACK={lb}", f"-DSWG_RS_MINBLOCKS={mb}", *extra, "-shared", "-o", out] + \
-          [os.path.join(ge.CSRC, s) for s in ge.SOURCES] + ["-lpthread", "-ldl", "-lrt"]
+          [os.path.join(ge.CSRC, s) for s in ge.SOURCES] + ["-lpthread", "-ldl", "-lrt", "-lz"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         print(spec, "BUILD FAILED", r.stderr[-300:]); continue

@@ -19,6 +19,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <zlib.h>
 
 #include "sweepga_b200.h"
 #include "host_util.h"
@@ -217,16 +218,36 @@ swg_paf *swg_paf_parse(const char *path, char *err, size_t err_len) {
         return nullptr;
     };
     if (!path) return fail("NULL path");
-    size_t plen = strlen(path);
-    if (plen > 3 && strcmp(path + plen - 3, ".gz") == 0)
-        return fail("bgzf/gzip-compressed PAF is not supported by this build (no zlib on the host path); decompress first");
+    // open_paf_input (src/paf.rs:10-28): extension "gz" / "bgz" => bgzf (= multi-member gzip) reader
+    const char *dot = strrchr(path, '.');
+    const char *slash = strrchr(path, '/');
+    const bool compressed = dot && (!slash || dot > slash) && (strcmp(dot, ".gz") == 0 || strcmp(dot, ".bgz") == 0);
     int fd = open(path, O_RDONLY);
     if (fd < 0) return fail(std::string("cannot open ") + path);
     struct stat sb;
     if (fstat(fd, &sb) != 0) { close(fd); return fail("fstat failed"); }
     swg_paf *p = new swg_paf();
-    p->text_len = (size_t)sb.st_size;
-    if (p->text_len > 0) {
+    if (compressed) {
+        gzFile gz = gzdopen(fd, "rb");
+        if (!gz) { close(fd); delete p; return fail("gzdopen failed"); }
+        gzbuffer(gz, 1 << 20);
+        size_t cap = (size_t)sb.st_size * 4 + (1 << 20), got = 0;
+        p->owned.resize(cap);
+        while (true) {
+            if (got == p->owned.size()) p->owned.resize(p->owned.size() * 2);
+            int r = gzread(gz, p->owned.data() + got, (unsigned)std::min<size_t>(p->owned.size() - got, (size_t)1 << 30));
+            if (r < 0) { gzclose(gz); delete p; return fail("gzip/bgzf stream is corrupt"); }
+            if (r == 0) break;
+            got += (size_t)r;
+        }
+        gzclose(gz); // closes fd
+        fd = -1;
+        p->owned.resize(got);
+        p->text = p->owned.data();
+        p->text_len = got;
+    } else
+        p->text_len = (size_t)sb.st_size;
+    if (!compressed && p->text_len > 0) {
         void *m = mmap(nullptr, p->text_len, PROT_READ, MAP_PRIVATE, fd, 0);
         if (m != MAP_FAILED) {
             p->text = (const char *)m;
@@ -244,7 +265,7 @@ swg_paf *swg_paf_parse(const char *path, char *err, size_t err_len) {
             p->text = p->owned.data();
         }
     }
-    close(fd);
+    if (fd >= 0) close(fd);
     // chunk at line boundaries, one chunk per host thread
     unsigned nt = std::thread::hardware_concurrency();
     if (nt == 0) nt = 1;

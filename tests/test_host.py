@@ -113,6 +113,27 @@ def test_paf_parser_matches_oracle_on_synthetic(tmp_path):
     assert seen == sorted(seen)
 
 
+def test_paf_gz_and_bgz_inputs(tmp_path):
+    """open_paf_input (src/paf.rs:10-28): extension gz / bgz => bgzf reader; bgzf is multi-member gzip."""
+    import gzip
+    t = synth.yeast_like(3000, seed=5)
+    p = tmp_path / "a.paf"
+    synth.write_paf(t, str(p))
+    data = p.read_bytes()
+    third = len(data) // 3
+    blob = gzip.compress(data[:third]) + gzip.compress(data[third:2 * third]) + gzip.compress(data[2 * third:])
+    (tmp_path / "a.paf.gz").write_bytes(blob)
+    (tmp_path / "b.bgz").write_bytes(blob)
+    a = swg.parse_paf(str(p))
+    for name in ("a.paf.gz", "b.bgz"):
+        b = swg.parse_paf(str(tmp_path / name))
+        assert a.n == b.n and a.names == b.names
+        assert np.array_equal(a.query_start, b.query_start) and np.array_equal(a.identity, b.identity)
+    (tmp_path / "bad.gz").write_bytes(b"\x1f\x8b\x08\x00garbage-not-deflate")
+    with pytest.raises(swg.SwgError):
+        swg.parse_paf(str(tmp_path / "bad.gz"))
+
+
 def test_paf_range_error(tmp_path):
     p = tmp_path / "big.paf"
     p.write_text("a\t1\t0\t5000000000\t+\tb\t1\t0\t10\t5\t10\t60\n")
