@@ -18,7 +18,7 @@ constexpr u8 F_PREMEM = 8;  // member of a chain that passed the mass/identity f
 // counters (u64 each) shared with the host
 enum {
     C_ALIVE = 0, C_ZLQ, C_ZLT, C_MAXCOORD, C_BAD, C_KEPT_M, C_GROUPS, C_CHAINS, C_PASS, C_PASS_ZEROSPAN,
-    C_KEPT_CHAINS, C_ANCHORS, C_RESCUED, C_KEPT, C_NEAR_TIES, C_WORK, C_EVGROUPS, C_INV, C_TMP0, C_TMP1, C_COUNT = 32
+    C_KEPT_CHAINS, C_ANCHORS, C_RESCUED, C_KEPT, C_NEAR_TIES, C_WORK, C_INV, C_TMP0, C_COUNT = 32
 };
 
 struct DevIn {

@@ -41,9 +41,10 @@ template <class Tag, class F> static inline void launch_for(u32 n, cudaStream_t 
     k_for<Tag, F><<<cdiv(n, 256), 256, 0, st>>>(n, f);
     lc.n++;
 }
-struct t_iota; struct t_sweep_gather; struct t_sweep_keep; struct t_gather; struct t_maxp; struct t_scores; struct t_gkey; struct t_events; struct t_chain_order; struct t_tspace; struct t_segfirst;
-struct t_segapply; struct t_keys_c2min; struct t_keys_g2min; struct t_final_k; struct t_assign; struct t_invkeys; struct t_invtab;
-struct t_inversion; struct t_anchor_keys; struct t_rescue; struct t_count_kept; struct t_chain_score;
+// tags: one per element-wise stage, so that the ncu launch list reads k_for<swg::t_assign, ...> etc.
+struct t_iota; struct t_maxp; struct t_scores; struct t_gkey; struct t_events; struct t_sweep_gather; struct t_sweep_keep;
+struct t_gather; struct t_chain_order; struct t_tspace; struct t_segapply; struct t_keys_c2min; struct t_keys_g2min;
+struct t_final_k; struct t_assign; struct t_invkeys; struct t_inversion; struct t_anchor_keys; struct t_rescue;
 
 // ---- grow-only HBM arena ----------------------------------------------------------------------
 // One block sized for the common path; a call that needs more (general sweeps, degenerate
