@@ -78,7 +78,7 @@ template <int NC> __device__ __forceinline__ void block_count_add(u64 *ctr, cons
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_prefilter(DevIn in, u64 min_len, double min_id, int keep_self, u8 *__restrict__ flags,
                                                    u64 *__restrict__ ctr, u64 *hk, u32 *hv, u32 hmask,
-                                                   uint4 *__restrict__ rec4, uint2 *__restrict__ rec2) {
+                                                   uint4 *__restrict__ rec4) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     bool alive = false, zq = false, zt = false, bad = false;
     u32 maxc = 0;
@@ -94,10 +94,9 @@ __global__ void __launch_bounds__(256) k_prefilter(DevIn in, u64 min_len, double
         maxc = max(qe, te);
         if (alive) g = ((u64)in.P[q] << 32) | in.P[t];
         flags[i] = (u8)((alive ? F_ALIVE : 0) | (zq ? F_ZLQ : 0) | (zt ? F_ZLT : 0));
-        if (rec4) { // packed copy for the post-sort gather: one 16 B + one 8 B sector instead of six 4 B gathers
-            rec4[i] = make_uint4(qs, qe, ts, te);
-            rec2[i] = make_uint2(in.blen[i], in.matches[i]);
-        }
+        // packed copy for the post-sort gather: one 16 B sector instead of four 4 B gathers.  `matches` is NOT touched
+        // here: it is first read by the gather after the sort, so its host-to-device copy can overlap K0 + sort.
+        if (rec4) rec4[i] = make_uint4(qs, qe, ts, te);
     }
     const u32 full = 0xFFFFFFFFu;
     {

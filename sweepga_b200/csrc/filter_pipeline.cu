@@ -104,6 +104,8 @@ struct swg_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;          // second stream: the `matches` column is uploaded behind the kernels
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr};
     cudaEvent_t ev_sort[2] = {nullptr, nullptr}; // bracket the one-sweep passes of the record sort
     int sort_passes = 0;
     u64 sort_pairs = 0;
@@ -296,7 +298,8 @@ static void segment_first(swg_ctx *c, const u64 *sk, const u32 *sv, u32 n, u32 *
 // ================================================================================================
 // the pipeline
 // ================================================================================================
-static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *status, u32 *chain_id, swg_stats *stats) {
+static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *status, u32 *chain_id, swg_stats *stats,
+                       cudaEvent_t ev_matches = nullptr /* recorded when in.matches has arrived (swg_filter overlaps that copy) */) {
     cudaStream_t st = c->stream;
     LaunchCounter &lc = c->lc;
     const u32 N = in.n;
@@ -350,9 +353,8 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     SWG_CUDA(cudaMemsetAsync(hk, 0xFF, sizeof(u64) * hcap, st));
     SWG_CUDA(cudaMemsetAsync(hv, 0xFF, sizeof(u32) * hcap, st));
     uint4 *rec4 = nullptr;
-    uint2 *rec2 = nullptr;
-    if (cfg.scaffold_gap != 0) { rec4 = A.take<uint4>(N); rec2 = A.take<uint2>(N); }
-    k_prefilter<<<cdiv(N, 256), 256, 0, st>>>(in, cfg.min_block_length, cfg.min_identity, cfg.keep_self, flags, ctr, hk, hv, hcap - 1, rec4, rec2);
+    if (cfg.scaffold_gap != 0) rec4 = A.take<uint4>(N);
+    k_prefilter<<<cdiv(N, 256), 256, 0, st>>>(in, cfg.min_block_length, cfg.min_identity, cfg.keep_self, flags, ctr, hk, hv, hcap - 1, rec4);
     lc.n++;
     read_counters(c);
     if (c->h_ctr[C_BAD]) throw RangeError{"record with end < start or sequence id >= n_seq"};
@@ -464,10 +466,11 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                },
                n_m, bsum, d_tot, st, lc);
     // post-sort gather of the packed records (flat, one thread per position: all gathers of a warp in flight at once)
+    if (ev_matches) SWG_CUDA(cudaStreamWaitEvent(st, ev_matches, 0)); // first use of in.matches
     launch_for<t_gather>(n_m, st, lc, [=] __device__(u32 p) {
         const u32 i = sidx[p];
         srec[p] = __ldg(&rec4[i]);
-        srec2[p] = __ldg(&rec2[i]);
+        srec2[p] = make_uint2(__ldg(&in.blen[i]), __ldg(&in.matches[i]));
     });
     const u32 n_groups = read_u32(c, d_tot);
     {   // refuse inputs whose chaining would need an absurd number of candidate evaluations (e.g. one 50 M-mapping pile:
@@ -824,6 +827,10 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
 }
 
 static int guarded(swg_ctx *c, const char *what, void (*fn)(void *), void *arg) {
+    struct DrainCopies { // an error must not leave the caller's host buffers in use by an in-flight copy
+        swg_ctx *c;
+        ~DrainCopies() { if (c && c->copy_stream) cudaStreamSynchronize(c->copy_stream); }
+    } drain{c};
     try {
         fn(arg);
         return SWG_OK;
@@ -869,7 +876,7 @@ static DevIn make_devin(const swg_mappings *m) {
     return d;
 }
 
-struct UploadArgs { swg_ctx *c; const swg_mappings *in; swg_mappings *dev; swg_result *res; Arena *arena; };
+struct UploadArgs { swg_ctx *c; const swg_mappings *in; swg_mappings *dev; swg_result *res; Arena *arena; bool overlap_matches = false; };
 
 static void do_upload(void *p) {
     UploadArgs *a = (UploadArgs *)p;
@@ -886,7 +893,7 @@ static void do_upload(void *p) {
     d.query_id = up32(h->query_id, n); d.target_id = up32(h->target_id, n);
     d.query_start = up32(h->query_start, n); d.query_end = up32(h->query_end, n);
     d.target_start = up32(h->target_start, n); d.target_end = up32(h->target_end, n);
-    d.block_length = up32(h->block_length, n); d.matches = up32(h->matches, n);
+    d.block_length = up32(h->block_length, n);
     { double *dst = A.take<double>(n); SWG_CUDA(cudaMemcpyAsync(dst, h->identity, n * 8, cudaMemcpyHostToDevice, st)); d.identity = dst; }
     if (h->score) { double *dst = A.take<double>(n); SWG_CUDA(cudaMemcpyAsync(dst, h->score, n * 8, cudaMemcpyHostToDevice, st)); d.score = dst; }
     { u8 *dst = A.take<u8>(n); SWG_CUDA(cudaMemcpyAsync(dst, h->strand, n, cudaMemcpyHostToDevice, st)); d.strand = dst; }
@@ -894,6 +901,19 @@ static void do_upload(void *p) {
     d.seq_genome2_id = up32(h->seq_genome2_id, h->n_seq);
     a->res->status = A.take<u8>(n);
     a->res->chain_id = A.take<u32>(n);
+    {   // `matches` goes last; with overlap_matches it travels on the copy stream behind the other columns, so the
+        // kernels that do not need it (prefilter, key build, sort) run while it is still on the wire
+        u32 *dst = A.take<u32>(n);
+        cudaStream_t cs = st;
+        if (a->overlap_matches) {
+            SWG_CUDA(cudaEventRecord(c->ev_copy[0], st));
+            SWG_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_copy[0], 0));
+            cs = c->copy_stream;
+        }
+        SWG_CUDA(cudaMemcpyAsync(dst, h->matches, n * 4, cudaMemcpyHostToDevice, cs));
+        if (a->overlap_matches) SWG_CUDA(cudaEventRecord(c->ev_copy[1], cs));
+        d.matches = dst;
+    }
     *a->dev = d;
 }
 
@@ -1019,6 +1039,8 @@ swg_ctx *swg_create(int device) {
         SWG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         for (auto &ev : c->ev) SWG_CUDA(cudaEventCreate(&ev));
         for (auto &ev : c->ev_sort) SWG_CUDA(cudaEventCreate(&ev));
+        SWG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (auto &ev : c->ev_copy) SWG_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         SWG_CUDA(cudaMallocHost(&c->h_ctr, sizeof(u64) * (C_COUNT + 8)));
         SWG_CUDA(cudaMalloc(&c->d_ctr, sizeof(u64) * C_COUNT));
     } catch (const CudaError &e2) {
@@ -1042,6 +1064,8 @@ void swg_destroy(swg_ctx *c) {
     if (c->d_ctr) cudaFree(c->d_ctr);
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : c->ev_sort) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : c->ev_copy) if (ev) cudaEventDestroy(ev);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1081,13 +1105,16 @@ int swg_filter(swg_ctx *c, const swg_config *cfg, const swg_mappings *host_in, s
         SWG_CUDA(cudaSetDevice(c->device));
         swg_mappings dev;
         swg_result dres;
-        UploadArgs ua{c, a->in, &dev, &dres, &c->io};
+        UploadArgs ua{c, a->in, &dev, &dres, &c->io, true};
         SWG_CUDA(cudaEventRecord(c->ev[0], c->stream));
         if (a->in->n) do_upload(&ua);
         SWG_CUDA(cudaEventRecord(c->ev[1], c->stream));
         swg_stats local;
         std::memset(&local, 0, sizeof local);
-        if (a->in->n) run_filter(c, *a->cfg, make_devin(&dev), dres.status, dres.chain_id, &local);
+        if (a->in->n) {
+            run_filter(c, *a->cfg, make_devin(&dev), dres.status, dres.chain_id, &local, c->ev_copy[1]);
+            SWG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy[1], 0)); // early exits never touched `matches`: still wait for its copy
+        }
         SWG_CUDA(cudaEventRecord(c->ev[2], c->stream));
         if (a->in->n) {
             SWG_CUDA(cudaMemcpyAsync(a->out->status, dres.status, a->in->n, cudaMemcpyDeviceToHost, c->stream));
