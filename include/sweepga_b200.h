@@ -144,6 +144,8 @@ typedef struct swg_stats {
     double ms_sort_passes;        /* CUDA-event time of the one-sweep passes of the record sort  */
     uint64_t n_sort_passes;       /* ... how many passes that was                               */
     uint64_t n_sort_pairs;        /* ... over how many (key,payload) pairs                      */
+    double ms_tokenize;           /* swg_filter_paf: newline scan + parse + name interning on the device */
+    double ms_write;              /* swg_filter_paf: output assembly on the device + download + write()  */
 } swg_stats;
 
 typedef struct swg_ctx swg_ctx;
@@ -235,9 +237,20 @@ int swg_paf_view(const swg_paf *p, swg_mappings *out);     /* borrow the SoA (va
 /* write_filtered_output, src/paf_filter.rs:1689-1726 */
 int swg_paf_write(const swg_paf *p, const char *out_path, const uint8_t *status, const uint32_t *chain_id);
 
-/* PafFilter::filter_paf (src/paf_filter.rs:278-289). */
+/* extract_metadata on the device: the text is copied to HBM once and tokenised there (newline scan, field split,
+ * integer / dv:f: parse, cg:Z: '=' count, name interning in first-appearance order).  Returns the same table as
+ * swg_paf_parse; lines outside the plain grammar are patched by the host's line parser, and an input the device
+ * declines (> 64 GiB, 64-bit name-hash collision) goes through swg_paf_parse.  NULL + swg_last_error on failure. */
+swg_paf *swg_paf_parse_device(swg_ctx *ctx, const char *path);
+
+/* PafFilter::filter_paf (src/paf_filter.rs:278-289): tokenise on the device, filter, assemble the tagged output on
+ * the device (write_filtered_output, src/paf_filter.rs:1689-1726), one download, write().  stats: ms_h2d = text
+ * upload, ms_tokenize, ms_device = the filter, ms_write.  SWG_PAF_FRONTEND=host selects swg_filter_paf_host. */
 int swg_filter_paf(swg_ctx *ctx, const swg_config *cfg, const char *in_path, const char *out_path,
                    swg_stats *stats);
+/* Same call with the multi-threaded host parser and writer around swg_filter. */
+int swg_filter_paf_host(swg_ctx *ctx, const swg_config *cfg, const char *in_path, const char *out_path,
+                        swg_stats *stats);
 /* unified_filter::filter_file (src/unified_filter.rs:280-347): sniffs "1 " => .1aln
  * => SWG_ERR_UNSUPPORTED (the container codec lives in fastga-rs, not in sweepga). */
 int swg_filter_file(swg_ctx *ctx, const swg_config *cfg, const char *in_path, const char *out_path,

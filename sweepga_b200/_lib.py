@@ -51,6 +51,7 @@ class swg_stats(C.Structure):
         ("n_rescued", C.c_uint64), ("n_kept", C.c_uint64), ("score_near_ties", C.c_uint64), ("gpu_launches", C.c_uint64),
         ("ms_h2d", C.c_double), ("ms_device", C.c_double), ("ms_d2h", C.c_double),
         ("ms_sort_passes", C.c_double), ("n_sort_passes", C.c_uint64), ("n_sort_pairs", C.c_uint64),
+        ("ms_tokenize", C.c_double), ("ms_write", C.c_double),
     ]
 
 
@@ -90,7 +91,9 @@ SYMBOLS = [
     ("swg_paf_seq_name", C.c_char_p, [_vp, C.c_uint32]),
     ("swg_paf_view", C.c_int, [_vp, _mapp]),
     ("swg_paf_write", C.c_int, [_vp, C.c_char_p, u8p, u32p]),
+    ("swg_paf_parse_device", _vp, [_vp, C.c_char_p]),
     ("swg_filter_paf", C.c_int, [_vp, _cfgp, C.c_char_p, C.c_char_p, _statp]),
+    ("swg_filter_paf_host", C.c_int, [_vp, _cfgp, C.c_char_p, C.c_char_p, _statp]),
     ("swg_filter_file", C.c_int, [_vp, _cfgp, C.c_char_p, C.c_char_p, C.c_int, _statp]),
     ("swg_shard_plan", C.c_int, [_mapp, C.c_int, u32p, u64p]),
     ("swg_version", C.c_char_p, []),

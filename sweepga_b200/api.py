@@ -378,12 +378,18 @@ def _n(v):
 
 
 # ------------------------------------------------------------------------------------------------
-def parse_paf(path: str) -> MappingTable:
-    """extract_metadata (src/paf_filter.rs:292-376) on all host threads -> MappingTable (+ rank, names)."""
-    err = C.create_string_buffer(256)
-    h = lib.swg_paf_parse(os.fsencode(path), err, 256)
-    if not h:
-        raise SwgError(_lib.ERR_IO, err.value.decode())
+def parse_paf(path: str, ctx: "Context" = None) -> MappingTable:
+    """extract_metadata (src/paf_filter.rs:292-376) -> MappingTable (+ rank, names).  With a Context the text is
+    tokenised on the GPU (swg_paf_parse_device), without one on all host threads (swg_paf_parse)."""
+    if ctx is not None:
+        h = lib.swg_paf_parse_device(ctx._h, os.fsencode(path))
+        if not h:
+            raise SwgError(_lib.ERR_IO, lib.swg_last_error(ctx._h).decode())
+    else:
+        err = C.create_string_buffer(256)
+        h = lib.swg_paf_parse(os.fsencode(path), err, 256)
+        if not h:
+            raise SwgError(_lib.ERR_IO, err.value.decode())
     try:
         m = _lib.swg_mappings()
         lib.swg_paf_view(h, C.byref(m))
@@ -425,11 +431,14 @@ class PafFilter:
             self._ctx = Context(self.device)
         return self._ctx
 
-    def filter_paf(self, input_path: str, output_path: str):
+    def filter_paf(self, input_path: str, output_path: str, host_frontend: bool = False):
+        """filter_paf (src/paf_filter.rs:278-289).  The text is tokenised and the tagged output assembled on the GPU;
+        host_frontend=True runs the multi-threaded host parser / writer around the same filter instead."""
         ctx = self._context()
         stats = _lib.swg_stats()
         cc = self.config.to_c()
-        ctx._check(lib.swg_filter_paf(ctx._h, C.byref(cc), os.fsencode(input_path), os.fsencode(output_path), C.byref(stats)))
+        fn = lib.swg_filter_paf_host if host_frontend else lib.swg_filter_paf
+        ctx._check(fn(ctx._h, C.byref(cc), os.fsencode(input_path), os.fsencode(output_path), C.byref(stats)))
         return stats
 
     def apply_filters(self, table: MappingTable):

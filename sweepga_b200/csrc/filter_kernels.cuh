@@ -106,9 +106,16 @@ __global__ void __launch_bounds__(256) k_prefilter(DevIn in, u64 min_len, double
     }
     u32 mx = __reduce_max_sync(full, maxc);
     if (lane_id() == 0 && mx > (u32)ctr[C_MAXCOORD]) atomicMax((unsigned long long *)&ctr[C_MAXCOORD], (unsigned long long)mx);
-    // one hash insert per distinct genome pair per warp; the lowest lane holds the lowest index
-    u32 peers = __match_any_sync(full, g);
-    if (alive && lane_id() == (u32)(__ffs(peers) - 1)) {
+    // one hash insert per distinct genome pair per warp; the lowest lane holds the lowest index.  Records of one
+    // genome pair are normally contiguous, so the whole warp usually shares the pair: two votes instead of MATCH.ANY.
+    const u32 alive_mask = __ballot_sync(full, alive);
+    if (alive_mask == 0) return;
+    const u32 first = __ffs(alive_mask) - 1;
+    const u64 g0 = __shfl_sync(full, g, first);
+    u32 leader_of_mine;
+    if (__all_sync(full, !alive || g == g0)) leader_of_mine = first;
+    else leader_of_mine = __ffs(__match_any_sync(full, g)) - 1;
+    if (alive && lane_id() == leader_of_mine) {
         // values only decrease: a plain read that already shows a smaller index makes the atomics unnecessary
         u32 sl = hash64(g) & hmask;
         bool done = false;

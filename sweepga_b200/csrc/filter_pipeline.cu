@@ -13,6 +13,7 @@
 //   K6  inversion capture                                paf_filter.rs:535-597
 //   K7  rescue                                           paf_filter.rs:613-732
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -25,11 +26,15 @@
 #include "radix_sort.cuh"
 #include "scan.cuh"
 #include "filter_kernels.cuh"
+#include "paf_host.h"
+
+#include <unistd.h>
 
 namespace swg {
 
 struct RangeError { std::string msg; };
 struct OomError { size_t bytes; };
+struct IoError { std::string msg; };
 
 // ---- generic element-wise launcher (named by Tag so the launch list is readable) ------------
 template <class Tag, class F> __global__ void __launch_bounds__(256) k_for(u32 n, F f) {
@@ -117,6 +122,9 @@ struct swg_ctx {
     Arena arena;      // per-call scratch
     Arena io;         // staging of host SoA for swg_filter
     u64 *h_ctr = nullptr; // pinned mirror of the counters
+    std::vector<char *> pin;          // pinned pieces for the file front end (text upload, output download)
+    std::vector<cudaEvent_t> pin_ev;
+    u32 tok_maxlen = 0;               // longest line of the last tokenised file
     u64 *d_ctr = nullptr;
     std::string err;
     LaunchCounter lc;
@@ -841,6 +849,9 @@ static int guarded(swg_ctx *c, const char *what, void (*fn)(void *), void *arg) 
     } catch (const RangeError &e) {
         set_err(c, std::string(what) + ": " + e.msg);
         return SWG_ERR_RANGE;
+    } catch (const IoError &e) {
+        set_err(c, std::string(what) + ": " + e.msg);
+        return SWG_ERR_IO;
     } catch (const OomError &e) {
         set_err(c, std::string(what) + ": out of device memory (" + std::to_string(e.bytes) + " bytes)");
         return SWG_ERR_OOM;
@@ -1013,6 +1024,8 @@ static void do_sweep_core(void *p) {
 
 } // namespace swg
 
+#include "paf_device.cuh"
+
 // =================================================================================================
 // C ABI
 // =================================================================================================
@@ -1061,6 +1074,8 @@ void swg_destroy(swg_ctx *c) {
     c->arena.release();
     c->io.release();
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
+    for (char *p : c->pin) cudaFreeHost(p);
+    for (auto &ev : c->pin_ev) cudaEventDestroy(ev);
     if (c->d_ctr) cudaFree(c->d_ctr);
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : c->ev_sort) if (ev) cudaEventDestroy(ev);
@@ -1262,6 +1277,108 @@ int swg_plane_sweep_target(swg_ctx *c, uint64_t n, const uint32_t *qs, const uin
 int swg_plane_sweep_both(swg_ctx *c, uint64_t n, const uint32_t *qs, const uint32_t *qe, const uint32_t *ts, const uint32_t *te,
                          const double *identity, uint64_t nq, uint64_t nt, double thr, int scoring, uint8_t *keep) {
     return sweep_entry(c, n, qs, qe, ts, te, identity, nq, nt, thr, scoring, 2, keep);
+}
+
+// ---- file front end on the device (paf_device.cuh) ------------------------------------------------
+int swg_filter_paf_host(swg_ctx *ctx, const swg_config *cfg, const char *in_path, const char *out_path, swg_stats *stats); // paf_io.cpp
+
+// extract_metadata on the GPU; the table comes back as a host swg_paf (same accessors as swg_paf_parse).
+swg_paf *swg_paf_parse_device(swg_ctx *c, const char *path) {
+    if (!c) return nullptr;
+    if (!path) { set_err(c, "swg_paf_parse_device: NULL path"); return nullptr; }
+    swg_paf *p = new (std::nothrow) swg_paf();
+    if (!p) return nullptr;
+    {
+        std::string err;
+        if (!paf_open_text(path, p, &err)) { set_err(c, "swg_paf_parse_device: " + err); delete p; return nullptr; }
+    }
+    struct Args { swg_ctx *c; swg_paf *p; bool fallback; } a{c, p, false};
+    const int rc = guarded(c, "swg_paf_parse_device", [](void *q) {
+        Args *a = (Args *)q;
+        swg_ctx *c = a->c;
+        swg_paf *p = a->p;
+        SWG_CUDA(cudaSetDevice(c->device));
+        DevPaf dp;
+        try { tokenize_device(c, *p, dp); } catch (const FrontEndFallback &) { a->fallback = true; return; }
+        const size_t n = dp.n;
+        p->n_lines = dp.n_lines;
+        p->rank.resize(n); p->line_off.resize(n); p->line_len.resize(n);
+        p->qid.resize(n); p->tid.resize(n); p->qs.resize(n); p->qe.resize(n); p->ts.resize(n); p->te.resize(n);
+        p->blen.resize(n); p->matches.resize(n); p->identity.resize(n); p->strand.resize(n);
+        p->names = dp.names; p->P = dp.hP; p->P2 = dp.hP2;
+        if (n == 0) return;
+        cudaStream_t st = c->stream;
+        std::vector<u32> rank32;
+        auto down = [&](void *dst, const void *src, size_t bytes) { SWG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st)); };
+        if (dp.rank) { rank32.resize(n); down(rank32.data(), dp.rank, n * 4); }
+        down(p->line_off.data(), dp.rec.off, n * 8); down(p->line_len.data(), dp.rec.len, n * 4);
+        down(p->qid.data(), dp.qid, n * 4); down(p->tid.data(), dp.tid, n * 4);
+        down(p->qs.data(), dp.rec.qs, n * 4); down(p->qe.data(), dp.rec.qe, n * 4);
+        down(p->ts.data(), dp.rec.ts, n * 4); down(p->te.data(), dp.rec.te, n * 4);
+        down(p->blen.data(), dp.rec.blen, n * 4); down(p->matches.data(), dp.rec.matches, n * 4);
+        down(p->identity.data(), dp.rec.identity, n * 8); down(p->strand.data(), dp.rec.strand, n);
+        SWG_CUDA(cudaStreamSynchronize(st));
+        for (size_t r = 0; r < n; r++) p->rank[r] = dp.rank ? rank32[r] : r;
+    }, &a);
+    if (rc != SWG_OK) { delete p; return nullptr; }
+    if (a.fallback) { // the device front end declined (oversize input, name hash collision): host front end
+        delete p;
+        char e[256];
+        e[0] = 0;
+        swg_paf *h = swg_paf_parse(path, e, sizeof e);
+        if (!h) set_err(c, std::string("swg_paf_parse_device: ") + e);
+        return h;
+    }
+    return p;
+}
+
+// PafFilter::filter_paf (src/paf_filter.rs:278-289) with the text tokenised, filtered and re-assembled on the GPU.
+int swg_filter_paf(swg_ctx *c, const swg_config *cfg, const char *in_path, const char *out_path, swg_stats *stats) {
+    if (!c || !cfg || !in_path || !out_path) return SWG_ERR_ARG;
+    if (!check_cfg(c, cfg)) return SWG_ERR_ARG;
+    {
+        const char *fe = getenv("SWG_PAF_FRONTEND");
+        if (fe && strcmp(fe, "host") == 0) return swg_filter_paf_host(c, cfg, in_path, out_path, stats);
+    }
+    swg_paf hp;
+    {
+        std::string err;
+        if (!paf_open_text(in_path, &hp, &err)) {
+            set_err(c, "swg_filter_paf: " + err);
+            return access(in_path, R_OK) == 0 ? SWG_ERR_RANGE : SWG_ERR_IO;
+        }
+    }
+    struct Args { swg_ctx *c; const swg_config *cfg; const swg_paf *hp; const char *out; swg_stats *stats; bool fallback; } a{c, cfg, &hp, out_path, stats, false};
+    const int rc = guarded(c, "swg_filter_paf", [](void *q) {
+        Args *a = (Args *)q;
+        swg_ctx *c = a->c;
+        SWG_CUDA(cudaSetDevice(c->device));
+        DevPaf dp;
+        const u64 launches0 = c->lc.n;
+        try { tokenize_device(c, *a->hp, dp); } catch (const FrontEndFallback &) { a->fallback = true; return; }
+        swg_stats local;
+        std::memset(&local, 0, sizeof local);
+        u8 *status = c->io.take<u8>(std::max<u32>(dp.n, 1));
+        u32 *chain = c->io.take<u32>(std::max<u32>(dp.n, 1));
+        if (dp.n) {
+            SWG_CUDA(cudaEventRecord(c->ev[1], c->stream));
+            run_filter(c, *a->cfg, devin_of(dp), status, chain, &local);
+            SWG_CUDA(cudaEventRecord(c->ev[2], c->stream));
+            SWG_CUDA(cudaStreamSynchronize(c->stream));
+            float ms = 0;
+            SWG_CUDA(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]));
+            local.ms_device = ms;
+        }
+        const auto t0 = std::chrono::steady_clock::now();
+        write_device(c, dp, status, chain, a->out);
+        local.ms_write = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        local.ms_h2d = dp.ms_upload;
+        local.ms_tokenize = dp.ms_tokenize;
+        local.gpu_launches = c->lc.n - launches0;
+        if (a->stats) *a->stats = local;
+    }, &a);
+    if (rc == SWG_OK && a.fallback) return swg_filter_paf_host(c, cfg, in_path, out_path, stats);
+    return rc;
 }
 
 } // extern "C"

@@ -1,0 +1,59 @@
+// paf_host.h — host-side PAF table shared by the host front end (paf_io.cpp) and the device front end
+// (paf_device.cuh, compiled into filter_pipeline.cu).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include <sys/mman.h>
+#include <unistd.h>
+
+struct swg_paf {
+    // the input text (mmap'd or read) — kept so that the writer does not re-read the file
+    const char *text = nullptr;
+    size_t text_len = 0;
+    bool mapped = false;
+    int fd = -1;                     // kept open for plain (mmap'd) inputs: the device front end preads from it
+    std::vector<char> owned;
+    uint64_t n_lines = 0;
+    // per record
+    std::vector<uint64_t> rank;      // line number
+    std::vector<uint64_t> line_off;  // offset of the line in text
+    std::vector<uint32_t> line_len;  // length without the line terminator
+    std::vector<uint32_t> qid, tid, qs, qe, ts, te, blen, matches;
+    std::vector<double> identity;
+    std::vector<uint8_t> strand;
+    // sequences
+    std::vector<std::string> names;
+    std::vector<uint32_t> P, P2;
+    ~swg_paf() {
+        if (mapped && text) munmap((void *)text, text_len);
+        if (fd >= 0) close(fd);
+    }
+};
+
+namespace swg {
+
+// One PAF line the way PafFilter::extract_metadata reads it (src/paf_filter.rs:292-376).
+struct PafLine {
+    enum Kind { SKIP = 0, OK = 1, ERR_RANGE = 2, ERR_ORDER = 3 };
+    const char *qname = nullptr, *tname = nullptr;
+    size_t qname_len = 0, tname_len = 0;
+    uint32_t qs = 0, qe = 0, ts = 0, te = 0, blen = 0, matches = 0;
+    double identity = 0.0;
+    uint8_t strand = '+';
+};
+// `len` excludes the line terminator ("\n" or "\r\n").  SKIP: fewer than 11 fields.
+PafLine::Kind paf_parse_line(const char *line, size_t len, PafLine *out);
+
+// Opens `path` (plain, .gz or .bgz) and fills text / text_len (mmap when possible); false + message on failure.
+bool paf_open_text(const char *path, swg_paf *p, std::string *err);
+
+std::string paf_prefix_P(const std::string &name);  // src/paf_filter.rs:1022-1030
+std::string paf_prefix_P2(const std::string &name); // src/plane_sweep_scaffold.rs:13-22
+
+// names (first-appearance order) -> dense ids of P(name) and P2(name), each in first-appearance order
+void paf_prefix_ids(const std::vector<std::string> &names, std::vector<uint32_t> *P, std::vector<uint32_t> *P2);
+
+} // namespace swg

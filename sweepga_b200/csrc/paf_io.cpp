@@ -29,27 +29,7 @@ extern "C" void swg__set_error(swg_ctx *ctx, const char *msg); // filter_pipelin
 using swg::rust_parse_f64;
 using swg::rust_parse_u64;
 
-struct swg_paf {
-    // the input text (mmap'd or read) — kept so that the writer does not re-read the file
-    const char *text = nullptr;
-    size_t text_len = 0;
-    bool mapped = false;
-    std::vector<char> owned;
-    uint64_t n_lines = 0;
-    // per record
-    std::vector<uint64_t> rank;      // line number
-    std::vector<uint64_t> line_off;  // offset of the line in text
-    std::vector<uint32_t> line_len;  // length without the line terminator
-    std::vector<uint32_t> qid, tid, qs, qe, ts, te, blen, matches;
-    std::vector<double> identity;
-    std::vector<uint8_t> strand;
-    // sequences
-    std::vector<std::string> names;
-    std::vector<uint32_t> P, P2;
-    ~swg_paf() {
-        if (mapped && text) munmap((void *)text, text_len);
-    }
-};
+#include "paf_host.h"
 
 namespace {
 
@@ -96,6 +76,66 @@ static bool cigar_eq_count(const char *s, size_t len, uint64_t *out) {
     return true;
 }
 
+} // namespace
+
+swg::PafLine::Kind swg::paf_parse_line(const char *line, size_t len, PafLine *out) {
+    const char *fs[11];
+    size_t fl[11];
+    // split the first 11 fields
+    int nf = 0;
+    size_t a = 0;
+    while (nf < 11) {
+        const char *tab = (const char *)memchr(line + a, '\t', len - a);
+        size_t b = tab ? (size_t)(tab - line) : len;
+        fs[nf] = line + a;
+        fl[nf] = b - a;
+        nf++;
+        if (!tab) { a = len + 1; break; }
+        a = b + 1;
+    }
+    if (nf < 11) return PafLine::SKIP; // fewer than 11 fields: skipped, still consumes a rank
+    uint64_t qs, qe, ts, te, mt, bl;
+    parse_u64_field(fs[2], fl[2], 0, &qs);
+    parse_u64_field(fs[3], fl[3], 0, &qe);
+    parse_u64_field(fs[7], fl[7], 0, &ts);
+    parse_u64_field(fs[8], fl[8], 0, &te);
+    parse_u64_field(fs[9], fl[9], 0, &mt);
+    parse_u64_field(fs[10], fl[10], 1, &bl);
+    double identity = (double)mt / (double)(bl > 1 ? bl : 1);
+    uint64_t exact = mt;
+    // tags from column 12 on, in order, the later one wins (paf_filter.rs:326-343)
+    while (a <= len) {
+        const char *tab = a < len ? (const char *)memchr(line + a, '\t', len - a) : nullptr;
+        size_t b = tab ? (size_t)(tab - line) : len;
+        const char *f = line + a;
+        size_t flen = b - a;
+        if (flen >= 5 && memcmp(f, "dv:f:", 5) == 0) {
+            double dv;
+            if (rust_parse_f64(f + 5, flen - 5, &dv)) identity = 1.0 - dv;
+        } else if (flen >= 5 && memcmp(f, "cg:Z:", 5) == 0) {
+            uint64_t cm;
+            if (cigar_eq_count(f + 5, flen - 5, &cm) && cm > 0) {
+                exact = cm;
+                identity = (double)cm / (double)(bl > 1 ? bl : 1);
+            }
+        }
+        if (!tab) break;
+        a = b + 1;
+    }
+    const uint64_t LIM = 0xFFFFFFFFull;
+    if (qs > LIM || qe > LIM || ts > LIM || te > LIM || bl > LIM || exact > LIM) return PafLine::ERR_RANGE;
+    if (qe < qs || te < ts) return PafLine::ERR_ORDER;
+    out->qname = fs[0]; out->qname_len = fl[0];
+    out->tname = fs[5]; out->tname_len = fl[5];
+    out->qs = (uint32_t)qs; out->qe = (uint32_t)qe; out->ts = (uint32_t)ts; out->te = (uint32_t)te;
+    out->blen = (uint32_t)bl; out->matches = (uint32_t)exact;
+    out->identity = identity;
+    out->strand = (fl[4] == 1 && fs[4][0] == '+') ? '+' : '-';
+    return PafLine::OK;
+}
+
+namespace {
+
 static void parse_chunk(const char *text, Chunk &c) {
     std::unordered_map<std::string, uint32_t, SvHash> ids;
     std::string last_q, last_t;
@@ -117,88 +157,45 @@ static void parse_chunk(const char *text, Chunk &c) {
     };
     size_t pos = c.begin;
     uint64_t ln = 0;
-    const char *fs[11];
-    size_t fl[11];
+    swg::PafLine L;
     while (pos < c.end) {
         const char *nl = (const char *)memchr(text + pos, '\n', c.end - pos);
         size_t eol = nl ? (size_t)(nl - text) : c.end;
         size_t len = eol - pos;
         if (len > 0 && text[eol - 1] == '\r') len--; // BufRead::lines strips "\r\n"
-        const char *line = text + pos;
         uint64_t this_ln = ln++;
         size_t next = nl ? eol + 1 : c.end;
-        // split the first 11 fields
-        int nf = 0;
-        size_t a = 0;
-        while (nf < 11) {
-            const char *tab = (const char *)memchr(line + a, '\t', len - a);
-            size_t b = tab ? (size_t)(tab - line) : len;
-            fs[nf] = line + a;
-            fl[nf] = b - a;
-            nf++;
-            if (!tab) { a = len + 1; break; }
-            a = b + 1;
-        }
-        if (nf < 11) { pos = next; continue; } // fewer than 11 fields: skipped, still consumes a rank
-        uint64_t qs, qe, ts, te, mt, bl;
-        parse_u64_field(fs[2], fl[2], 0, &qs);
-        parse_u64_field(fs[3], fl[3], 0, &qe);
-        parse_u64_field(fs[7], fl[7], 0, &ts);
-        parse_u64_field(fs[8], fl[8], 0, &te);
-        parse_u64_field(fs[9], fl[9], 0, &mt);
-        parse_u64_field(fs[10], fl[10], 1, &bl);
-        double identity = (double)mt / (double)(bl > 1 ? bl : 1);
-        uint64_t exact = mt;
-        // tags from column 12 on, in order, the later one wins (paf_filter.rs:326-343)
-        while (a <= len) {
-            const char *tab = a < len ? (const char *)memchr(line + a, '\t', len - a) : nullptr;
-            size_t b = tab ? (size_t)(tab - line) : len;
-            const char *f = line + a;
-            size_t flen = b - a;
-            if (flen >= 5 && memcmp(f, "dv:f:", 5) == 0) {
-                double dv;
-                if (rust_parse_f64(f + 5, flen - 5, &dv)) identity = 1.0 - dv;
-            } else if (flen >= 5 && memcmp(f, "cg:Z:", 5) == 0) {
-                uint64_t cm;
-                if (cigar_eq_count(f + 5, flen - 5, &cm) && cm > 0) {
-                    exact = cm;
-                    identity = (double)cm / (double)(bl > 1 ? bl : 1);
-                }
-            }
-            if (!tab) break;
-            a = b + 1;
-        }
-        const uint64_t LIM = 0xFFFFFFFFull;
-        if (qs > LIM || qe > LIM || ts > LIM || te > LIM || bl > LIM || exact > LIM) {
+        const swg::PafLine::Kind kind = swg::paf_parse_line(text + pos, len, &L);
+        if (kind == swg::PafLine::ERR_RANGE) {
             if (c.error.empty()) c.error = "coordinate / length does not fit the u32 SoA at chunk line " + std::to_string(this_ln);
-            pos = next;
-            continue;
-        }
-        if (qe < qs || te < ts) {
+        } else if (kind == swg::PafLine::ERR_ORDER) {
             if (c.error.empty()) c.error = "record with end < start at chunk line " + std::to_string(this_ln);
-            pos = next;
-            continue;
+        } else if (kind == swg::PafLine::OK) {
+            uint32_t q = intern(L.qname, L.qname_len, last_q, last_qid, have_q);
+            uint32_t t = intern(L.tname, L.tname_len, last_t, last_tid, have_t);
+            c.rank_local.push_back(this_ln);
+            c.line_off.push_back(pos);
+            c.line_len.push_back((uint32_t)len);
+            c.qid.push_back(q); c.tid.push_back(t);
+            c.qs.push_back(L.qs); c.qe.push_back(L.qe); c.ts.push_back(L.ts); c.te.push_back(L.te);
+            c.blen.push_back(L.blen); c.matches.push_back(L.matches);
+            c.identity.push_back(L.identity);
+            c.strand.push_back(L.strand);
         }
-        uint32_t q = intern(fs[0], fl[0], last_q, last_qid, have_q);
-        uint32_t t = intern(fs[5], fl[5], last_t, last_tid, have_t);
-        c.rank_local.push_back(this_ln);
-        c.line_off.push_back(pos);
-        c.line_len.push_back((uint32_t)len);
-        c.qid.push_back(q); c.tid.push_back(t);
-        c.qs.push_back((uint32_t)qs); c.qe.push_back((uint32_t)qe); c.ts.push_back((uint32_t)ts); c.te.push_back((uint32_t)te);
-        c.blen.push_back((uint32_t)bl); c.matches.push_back((uint32_t)exact);
-        c.identity.push_back(identity);
-        c.strand.push_back((fl[4] == 1 && fs[4][0] == '+') ? '+' : '-');
         pos = next;
     }
     c.n_lines = ln;
 }
 
-static std::string prefix_P(const std::string &n) { // src/paf_filter.rs:1022-1030
+template <class T> static void append(std::vector<T> &dst, const std::vector<T> &src) { dst.insert(dst.end(), src.begin(), src.end()); }
+
+} // namespace
+
+std::string swg::paf_prefix_P(const std::string &n) { // src/paf_filter.rs:1022-1030
     size_t p = n.rfind('#');
     return p == std::string::npos ? n : n.substr(0, p + 1);
 }
-static std::string prefix_P2(const std::string &n) { // src/plane_sweep_scaffold.rs:13-22
+std::string swg::paf_prefix_P2(const std::string &n) { // src/plane_sweep_scaffold.rs:13-22
     size_t p = n.find('#');
     if (p == std::string::npos) return n;
     size_t p2 = n.find('#', p + 1);
@@ -206,17 +203,20 @@ static std::string prefix_P2(const std::string &n) { // src/plane_sweep_scaffold
     return n.substr(0, p) + "#" + f1 + "#";
 }
 
-template <class T> static void append(std::vector<T> &dst, const std::vector<T> &src) { dst.insert(dst.end(), src.begin(), src.end()); }
+void swg::paf_prefix_ids(const std::vector<std::string> &names, std::vector<uint32_t> *P, std::vector<uint32_t> *P2) {
+    std::unordered_map<std::string, uint32_t> pid, p2id;
+    P->clear(); P2->clear();
+    P->reserve(names.size()); P2->reserve(names.size());
+    for (const auto &n : names) {
+        auto ia = pid.emplace(paf_prefix_P(n), (uint32_t)pid.size()).first;
+        auto ib = p2id.emplace(paf_prefix_P2(n), (uint32_t)p2id.size()).first;
+        P->push_back(ia->second);
+        P2->push_back(ib->second);
+    }
+}
 
-} // namespace
-
-extern "C" {
-
-swg_paf *swg_paf_parse(const char *path, char *err, size_t err_len) {
-    auto fail = [&](const std::string &m) -> swg_paf * {
-        if (err && err_len) snprintf(err, err_len, "%s", m.c_str());
-        return nullptr;
-    };
+bool swg::paf_open_text(const char *path, swg_paf *p, std::string *err) {
+    auto fail = [&](const std::string &m) { *err = m; return false; };
     if (!path) return fail("NULL path");
     // open_paf_input (src/paf.rs:10-28): extension "gz" / "bgz" => bgzf (= multi-member gzip) reader
     const char *dot = strrchr(path, '.');
@@ -226,17 +226,16 @@ swg_paf *swg_paf_parse(const char *path, char *err, size_t err_len) {
     if (fd < 0) return fail(std::string("cannot open ") + path);
     struct stat sb;
     if (fstat(fd, &sb) != 0) { close(fd); return fail("fstat failed"); }
-    swg_paf *p = new swg_paf();
     if (compressed) {
         gzFile gz = gzdopen(fd, "rb");
-        if (!gz) { close(fd); delete p; return fail("gzdopen failed"); }
+        if (!gz) { close(fd); return fail("gzdopen failed"); }
         gzbuffer(gz, 1 << 20);
         size_t cap = (size_t)sb.st_size * 4 + (1 << 20), got = 0;
         p->owned.resize(cap);
         while (true) {
             if (got == p->owned.size()) p->owned.resize(p->owned.size() * 2);
             int r = gzread(gz, p->owned.data() + got, (unsigned)std::min<size_t>(p->owned.size() - got, (size_t)1 << 30));
-            if (r < 0) { gzclose(gz); delete p; return fail("gzip/bgzf stream is corrupt"); }
+            if (r < 0) { gzclose(gz); return fail("gzip/bgzf stream is corrupt"); }
             if (r == 0) break;
             got += (size_t)r;
         }
@@ -253,6 +252,8 @@ swg_paf *swg_paf_parse(const char *path, char *err, size_t err_len) {
             p->text = (const char *)m;
             p->mapped = true;
             madvise(m, p->text_len, MADV_SEQUENTIAL);
+            p->fd = fd;
+            fd = -1;
         } else { // pipes / special files: read
             p->owned.resize(p->text_len);
             size_t got = 0;
@@ -266,6 +267,21 @@ swg_paf *swg_paf_parse(const char *path, char *err, size_t err_len) {
         }
     }
     if (fd >= 0) close(fd);
+    return true;
+}
+
+extern "C" {
+
+swg_paf *swg_paf_parse(const char *path, char *err, size_t err_len) {
+    auto fail = [&](const std::string &m) -> swg_paf * {
+        if (err && err_len) snprintf(err, err_len, "%s", m.c_str());
+        return nullptr;
+    };
+    swg_paf *p = new swg_paf();
+    {
+        std::string m;
+        if (!swg::paf_open_text(path, p, &m)) { delete p; return fail(m); }
+    }
     // chunk at line boundaries, one chunk per host thread
     unsigned nt = std::thread::hardware_concurrency();
     if (nt == 0) nt = 1;
@@ -294,7 +310,7 @@ swg_paf *swg_paf_parse(const char *path, char *err, size_t err_len) {
     for (auto &c : chunks)
         if (!c.error.empty()) { std::string m = c.error; delete p; return fail(m); }
     // merge: global name ids in first-appearance order (chunk order, then within-chunk order)
-    std::unordered_map<std::string, uint32_t> gid, pid, p2id;
+    std::unordered_map<std::string, uint32_t> gid;
     size_t total = 0;
     for (auto &c : chunks) total += c.rank_local.size();
     p->rank.reserve(total); p->line_off.reserve(total); p->line_len.reserve(total);
@@ -312,13 +328,6 @@ swg_paf *swg_paf_parse(const char *path, char *err, size_t err_len) {
                 uint32_t id = (uint32_t)p->names.size();
                 gid.emplace(c.names[i], id);
                 p->names.push_back(c.names[i]);
-                std::string a = prefix_P(c.names[i]), b = prefix_P2(c.names[i]);
-                auto ia = pid.find(a);
-                if (ia == pid.end()) ia = pid.emplace(a, (uint32_t)pid.size()).first;
-                auto ib = p2id.find(b);
-                if (ib == p2id.end()) ib = p2id.emplace(b, (uint32_t)p2id.size()).first;
-                p->P.push_back(ia->second);
-                p->P2.push_back(ib->second);
                 remap[i] = id;
             } else remap[i] = it->second;
         }
@@ -334,6 +343,7 @@ swg_paf *swg_paf_parse(const char *path, char *err, size_t err_len) {
         Chunk().names.swap(c.names);
     }
     p->n_lines = line_base;
+    swg::paf_prefix_ids(p->names, &p->P, &p->P2);
     return p;
 }
 
@@ -395,9 +405,18 @@ static void format_range(const swg_paf *p, const uint8_t *status, const uint32_t
 
 int swg_paf_write(const swg_paf *p, const char *out_path, const uint8_t *status, const uint32_t *chain_id) {
     if (!p || !out_path || (p->rank.size() && (!status || !chain_id))) return SWG_ERR_ARG;
-    FILE *f = fopen(out_path, "wb");
-    if (!f) return SWG_ERR_IO;
+    const int fd = open(out_path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return SWG_ERR_IO;
     bool ok = true;
+    uint64_t file_off = 0;
+    auto write_at = [fd](const std::vector<char> *b, uint64_t off, bool *good) {
+        size_t done = 0;
+        while (done < b->size()) {
+            const ssize_t w = pwrite(fd, b->data() + done, b->size() - done, (off_t)(off + done));
+            if (w <= 0) { *good = false; return; }
+            done += (size_t)w;
+        }
+    };
     const size_t n = p->rank.size();
     unsigned nt = std::thread::hardware_concurrency();
     if (nt == 0) nt = 1;
@@ -413,14 +432,24 @@ int swg_paf_write(const swg_paf *p, const char *out_path, const uint8_t *status,
             else format_range(p, status, chain_id, r0, r1, bufs[k]);
         }
         for (auto &t : th) t.join();
-        for (auto &b : bufs)
-            if (!b.empty()) ok = ok && fwrite(b.data(), 1, b.size(), f) == b.size();
+        // every part lands at its own file offset: the page-cache copies run on all threads as well
+        th.clear();
+        std::vector<char> good(parts, 1);
+        for (size_t k = 0; k < parts; k++) {
+            if (!bufs[k].empty()) {
+                if (k + 1 < parts) th.emplace_back(write_at, &bufs[k], file_off, (bool *)&good[k]);
+                else write_at(&bufs[k], file_off, (bool *)&good[k]);
+            }
+            file_off += bufs[k].size();
+        }
+        for (auto &t : th) t.join();
+        for (char g : good) ok = ok && g;
     }
-    ok = (fclose(f) == 0) && ok;
+    ok = (close(fd) == 0) && ok;
     return ok ? SWG_OK : SWG_ERR_IO;
 }
 
-int swg_filter_paf(swg_ctx *ctx, const swg_config *cfg, const char *in_path, const char *out_path, swg_stats *stats) {
+int swg_filter_paf_host(swg_ctx *ctx, const swg_config *cfg, const char *in_path, const char *out_path, swg_stats *stats) {
     if (!ctx || !cfg || !in_path || !out_path) return SWG_ERR_ARG;
     char err[256];
     err[0] = 0;

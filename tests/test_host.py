@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     assert C.sizeof(_lib.swg_config) == 8 * 8 + 4 * 8 + 8
-    assert C.sizeof(_lib.swg_stats) == 11 * 8 + 3 * 8 + 3 * 8
+    assert C.sizeof(_lib.swg_stats) == 11 * 8 + 3 * 8 + 3 * 8 + 2 * 8
     assert C.sizeof(_lib.swg_mappings) == 8 + 10 * 8 + 8 + 8 + 8 + 8  # n, 10 ptr, score, n_seq(+pad), 2 ptr
 
 
