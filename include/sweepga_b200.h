@@ -218,6 +218,21 @@ int swg_parse_scoring(const char *s, uint8_t *scoring);
 int swg_parse_metric_number(const char *s, uint64_t *out);
 /* src/cli.rs:76-130; has_ani = 0 => ani_percentile None */
 int swg_parse_identity_value(const char *s, int has_ani, double ani_percentile, double *out);
+/* ---- ANI pre-pass (`--min-identity aniN`): the caller immediately before the filter ---- */
+enum { SWG_ANI_ALL = 0, SWG_ANI_ORTHOGONAL = 1, SWG_ANI_NPERCENTILE = 2 };  /* AniMethod, src/main.rs:174-178 */
+enum { SWG_NSORT_LENGTH = 0, SWG_NSORT_IDENTITY = 1, SWG_NSORT_SCORE = 2 }; /* NSort, src/main.rs:182-186      */
+/* parse_ani_method, src/main.rs:296-331 ("all", "orthogonal" | "1:1", "nX[-length|-identity|-score]").
+ * SWG_ERR_PARSE <=> None (the CLI then falls back to n50-identity, src/main.rs:3579).            */
+int swg_parse_ani_method(const char *s, int *method, double *percentile, int *sort);
+/* calculate_ani_stats / calculate_ani_n_percentile, src/main.rs:334-688: the median over genome pairs of
+ * sum(matches) / sum(block length) over the inter-genome alignments of a PAF — all of them, the survivors of the 1:1
+ * filter (ORTHOGONAL; runs swg_filter_paf into a temp file first), or the best ones in a stable descending sort
+ * until their block lengths cover `percentile` % of the genome size.  The text is tokenised on the GPU and every
+ * pair's f64 sums are accumulated there in the reference's order, so *ani50 is the reference's value bit for bit
+ * (NSORT_SCORE: up to ties within 1 ulp of log).  SWG_ERR_RANGE when the reference would panic on a NaN. */
+int swg_ani_stats(swg_ctx *ctx, const char *paf_path, int method, double percentile, int sort, double *ani50,
+                  uint64_t *n_pairs);
+
 /* src/pansn.rs:176-191, 207-225; has_avg = 0 => avg_seq_len None */
 uint64_t swg_round_nice(uint64_t v);
 void swg_clamp_scaffold_params(uint64_t user_jump, uint64_t user_mass, int has_avg, uint64_t avg_seq_len,

@@ -784,4 +784,104 @@ int orc_filter_paf(const swg_config *cfg, const char *in_path, const char *out_p
     return rc;
 }
 
+// calculate_ani_stats + calculate_ani_n_percentile, src/main.rs:334-688.
+// method 0 = All, 1 = Orthogonal (1:1 filter first, :346-383), 2 = NPercentile(percentile, sort); sort 0 = length,
+// 1 = identity, 2 = score.  Returns 0 and *ani50; -1: I/O; -2: the reference would panic (NaN in partial_cmp).
+int orc_ani_stats(const char *path, int method, double percentile, int sort, double *ani50, uint64_t *n_pairs) {
+    using namespace orc;
+    std::string input = path;
+    std::string tmp;
+    if (method == 1) { // :346-383
+        swg_config c;
+        memset(&c, 0, sizeof c);
+        c.min_block_length = 1000;
+        c.mapping_filter_mode = SWG_ONE_TO_ONE; c.mapping_max_per_query = 1; c.mapping_max_per_target = 1;
+        c.scaffold_filter_mode = SWG_ONE_TO_ONE; c.scaffold_max_per_query = 1; c.scaffold_max_per_target = 1;
+        c.overlap_threshold = 0.95; c.scaffold_gap = 10000; c.min_scaffold_length = 0; c.scaffold_overlap_threshold = 0.95;
+        c.scaffold_max_deviation = 0; c.scoring_function = SWG_SCORE_MATCHES; c.min_identity = 0.0; c.min_scaffold_identity = 0.0;
+        tmp = std::string(path) + ".orc_ani_tmp";
+        if (orc_filter_paf(&c, path, tmp.c_str(), nullptr) != 0) return -1;
+        input = tmp;
+    }
+    struct Aln { std::string qg, tg; double matches, block, identity; };
+    std::vector<Aln> alns;
+    std::unordered_map<std::string, uint64_t> genome_sizes;
+    {
+        std::ifstream in(input, std::ios::binary);
+        if (!in) return -1;
+        std::string line;
+        while (std::getline(in, line)) {
+            if (!line.empty() && line.back() == '\r') line.pop_back();
+            if (line.empty() || line[0] == '#') continue; // :414-416 / :540-542
+            std::vector<std::string> f;
+            size_t s = 0;
+            while (true) {
+                size_t t = line.find('\t', s);
+                if (t == std::string::npos) { f.push_back(line.substr(s)); break; }
+                f.push_back(line.substr(s, t - s));
+                s = t + 1;
+            }
+            if (f.size() < 11) continue;
+            std::string qg = prefix_P(f[0]), tg = prefix_P(f[5]); // :424-433: up to and including the last '#'
+            if (qg == tg) continue;                               // :436-438
+            if (method == 2) {                                    // :560-575: sizes keyed by genome + last '#' field
+                uint64_t ql = 0, tl = 0;
+                if (!rust_parse_u64(f[1], ql)) ql = 0;
+                if (!rust_parse_u64(f[6], tl)) tl = 0;
+                auto last = [](const std::string &n) { size_t p = n.rfind('#'); return p == std::string::npos ? n : n.substr(p + 1); };
+                genome_sizes.emplace(qg + last(f[0]), ql); // or_insert
+                genome_sizes.emplace(tg + last(f[5]), tl);
+            }
+            double m = 0.0, b = 1.0;
+            if (!rust_parse_f64(f[9], m)) m = 0.0;
+            if (!rust_parse_f64(f[10], b)) b = 1.0;
+            double fm = m;
+            for (size_t k = 11; k < f.size(); k++) // :445-453: the FIRST dv:f: tag that parses
+                if (f[k].compare(0, 5, "dv:f:") == 0) {
+                    double dv;
+                    if (rust_parse_f64(f[k].substr(5), dv)) { fm = (1.0 - dv) * b; break; }
+                }
+            alns.push_back(Aln{qg, tg, fm, b, fm / std::max(b, 1.0)});
+        }
+    }
+    if (!tmp.empty()) remove(tmp.c_str());
+    if (n_pairs) *n_pairs = 0;
+    if (alns.empty()) { *ani50 = 0.0; return 0; } // :468-471 / :606-609
+    size_t take = alns.size();
+    if (method == 2) {
+        for (const auto &a : alns) {
+            double key = sort == 0 ? a.block : sort == 1 ? a.identity : a.identity * std::max(std::log(a.block), 1.0);
+            if (key != key) return -2;
+        }
+        auto key = [&](const Aln &a) { return sort == 0 ? a.block : sort == 1 ? a.identity : a.identity * std::max(std::log(a.block), 1.0); };
+        std::stable_sort(alns.begin(), alns.end(), [&](const Aln &x, const Aln &y) { return key(x) > key(y); }); // :612-631
+        double total = 0.0;
+        for (const auto &kv : genome_sizes) total += (double)kv.second; // :634
+        const double thr = total * (percentile / 100.0);                 // :638
+        double cum = 0.0;
+        take = 0;
+        for (const auto &a : alns) { // :654-672: the alignment that crosses the threshold is still counted
+            cum += a.block;
+            take++;
+            if (cum >= thr) break;
+        }
+    }
+    std::map<std::pair<std::string, std::string>, std::pair<double, double>> pairs;
+    for (size_t i = 0; i < take; i++) {
+        const Aln &a = alns[i];
+        auto key = a.qg < a.tg ? std::make_pair(a.qg, a.tg) : std::make_pair(a.tg, a.qg); // :455-459
+        auto &e = pairs[key];
+        e.first += a.matches;
+        e.second += a.block;
+    }
+    std::vector<double> ani;
+    for (const auto &kv : pairs) ani.push_back(kv.second.second > 0.0 ? kv.second.first / kv.second.second : 0.0);
+    for (double v : ani) if (v != v) return -2;
+    std::sort(ani.begin(), ani.end());
+    const size_t mid = ani.size() / 2;
+    *ani50 = (ani.size() % 2 == 0 && ani.size() > 1) ? (ani[mid - 1] + ani[mid]) / 2.0 : ani[mid]; // :490-495
+    if (n_pairs) *n_pairs = ani.size();
+    return 0;
+}
+
 } // extern "C"

@@ -52,4 +52,12 @@ print(f"filter_paf, device front end: {t_gpu:.3f} s wall ({t.n/t_gpu/1e6:.2f} M 
       f"tokenise {st.ms_tokenize:.1f} ms, filter {st.ms_device:.1f} ms, assemble+download+write {st.ms_write:.1f} ms, {st.gpu_launches} launches")
 print(f"filter_paf, host front end:   {t_host:.3f} s wall ({t.n/t_host/1e6:.2f} M lines/s): filter {sth.ms_device:.1f} ms, h2d {sth.ms_h2d:.1f} ms")
 print(f"parse alone incl. numpy copies: host {t_parse:.3f} s, device {t_parse_dev:.3f} s")
+swg.ani_stats(ctx, src, "n100")
+t0 = time.time(); ani = swg.ani_stats(ctx, src, "n100"); t_ani = time.time() - t0
+t0 = time.time(); ani_all = swg.ani_stats(ctx, src, "all"); t_ani_all = time.time() - t0
+if n <= 8_000_000:
+    t0 = time.time(); o_ani = oracle_lib.ani_stats(src, 2, 100.0, 1); t_oani = time.time() - t0
+    print(f"ANI pre-pass (n100-identity): device {t_ani:.3f} s, 'all' {t_ani_all:.3f} s | oracle 1 thread {t_oani:.3f} s | identical: {ani == o_ani} ({ani[0]!r}, {ani[1]} pairs)")
+else:
+    print(f"ANI pre-pass (n100-identity): device {t_ani:.3f} s, 'all' {t_ani_all:.3f} s ({ani[0]!r}, {ani[1]} pairs)")
 print(f"oracle 1 thread: {t_orc:.3f} s ({t.n/t_orc/1e6:.2f} M lines/s) | identical output: {same}")

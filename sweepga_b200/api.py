@@ -83,6 +83,28 @@ def parse_identity_value(s: str, ani_percentile: Optional[float] = None) -> floa
     return v.value
 
 
+ANI_ALL, ANI_ORTHOGONAL, ANI_NPERCENTILE = 0, 1, 2
+NSORT_LENGTH, NSORT_IDENTITY, NSORT_SCORE = 0, 1, 2
+
+
+def parse_ani_method(s: str):
+    """parse_ani_method (src/main.rs:296-331) -> (method, percentile, sort) or None."""
+    m, p, k = C.c_int(), C.c_double(), C.c_int()
+    if lib.swg_parse_ani_method(s.encode(), C.byref(m), C.byref(p), C.byref(k)) != 0:
+        return None
+    return m.value, p.value, k.value
+
+
+def ani_stats(ctx: "Context", paf_path: str, method="n100"):
+    """calculate_ani_stats (src/main.rs:334-688) on the GPU -> (ani50, n_genome_pairs).  `method` is the --ani-method string
+    ("all", "orthogonal", "n50", "n90-length", ...; unknown strings fall back to n50-identity like the CLI) or a tuple."""
+    if isinstance(method, str):
+        method = parse_ani_method(method) or (ANI_NPERCENTILE, 50.0, NSORT_IDENTITY)
+    ani, npairs = C.c_double(), C.c_uint64()
+    ctx._check(lib.swg_ani_stats(ctx._h, os.fsencode(paf_path), int(method[0]), float(method[1]), int(method[2]), C.byref(ani), C.byref(npairs)))
+    return ani.value, int(npairs.value)
+
+
 def round_nice(v: int) -> int:
     return lib.swg_round_nice(v)
 

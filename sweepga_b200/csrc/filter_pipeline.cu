@@ -1025,6 +1025,7 @@ static void do_sweep_core(void *p) {
 } // namespace swg
 
 #include "paf_device.cuh"
+#include "ani_device.cuh"
 
 // =================================================================================================
 // C ABI
@@ -1379,6 +1380,59 @@ int swg_filter_paf(swg_ctx *c, const swg_config *cfg, const char *in_path, const
     }, &a);
     if (rc == SWG_OK && a.fallback) return swg_filter_paf_host(c, cfg, in_path, out_path, stats);
     return rc;
+}
+
+// calculate_ani_stats (src/main.rs:334-688) with the text tokenised and the per-pair sums accumulated on the GPU.
+int swg_ani_stats(swg_ctx *c, const char *paf_path, int method, double percentile, int sort, double *ani50, uint64_t *n_pairs) {
+    if (!c || !paf_path || !ani50) return SWG_ERR_ARG;
+    if (method < SWG_ANI_ALL || method > SWG_ANI_NPERCENTILE || sort < SWG_NSORT_LENGTH || sort > SWG_NSORT_SCORE) {
+        set_err(c, "swg_ani_stats: bad method / sort");
+        return SWG_ERR_ARG;
+    }
+    std::string input = paf_path, tmp;
+    if (method == SWG_ANI_ORTHOGONAL) { // best 1:1 mappings first (main.rs:346-383), then the plain statistic over the survivors
+        swg_config cfg;
+        swg_config_default(&cfg);
+        cfg.min_block_length = 1000;
+        cfg.mapping_filter_mode = SWG_ONE_TO_ONE; cfg.mapping_max_per_query = 1; cfg.mapping_max_per_target = 1;
+        cfg.scaffold_filter_mode = SWG_ONE_TO_ONE; cfg.scaffold_max_per_query = 1; cfg.scaffold_max_per_target = 1;
+        cfg.overlap_threshold = 0.95; cfg.scaffold_gap = 10000; cfg.min_scaffold_length = 0; cfg.scaffold_overlap_threshold = 0.95;
+        cfg.scaffold_max_deviation = 0; cfg.scoring_function = SWG_SCORE_MATCHES; cfg.min_identity = 0.0; cfg.min_scaffold_identity = 0.0;
+        cfg.keep_self = 0; cfg.scaffolds_only = 0;
+        const char *td = getenv("TMPDIR");
+        tmp = std::string(td && *td ? td : "/tmp") + "/swg_ani_XXXXXX";
+        const int fd = mkstemp(&tmp[0]);
+        if (fd < 0) { set_err(c, "swg_ani_stats: cannot create a temp file"); return SWG_ERR_IO; }
+        close(fd);
+        const int rc = swg_filter_paf(c, &cfg, paf_path, tmp.c_str(), nullptr);
+        if (rc != SWG_OK) { unlink(tmp.c_str()); return rc; }
+        input = tmp;
+        method = SWG_ANI_ALL;
+    }
+    swg_paf hp;
+    {
+        std::string err;
+        if (!paf_open_text(input.c_str(), &hp, &err)) {
+            set_err(c, "swg_ani_stats: " + err);
+            if (!tmp.empty()) unlink(tmp.c_str());
+            return access(input.c_str(), R_OK) == 0 ? SWG_ERR_RANGE : SWG_ERR_IO;
+        }
+    }
+    struct Args { swg_ctx *c; const swg_paf *hp; int method; double pct; int sort; AniResult res; bool fallback, nan; } a{c, &hp, method, percentile, sort, {}, false, false};
+    int rc = guarded(c, "swg_ani_stats", [](void *q) {
+        Args *a = (Args *)q;
+        SWG_CUDA(cudaSetDevice(a->c->device));
+        try { a->res = ani_device(a->c, *a->hp, a->method, a->pct, a->sort); }
+        catch (const FrontEndFallback &) { a->fallback = true; }
+        catch (const NanError &) { a->nan = true; }
+    }, &a);
+    if (!tmp.empty()) unlink(tmp.c_str());
+    if (rc != SWG_OK) return rc;
+    if (a.nan) { set_err(c, "swg_ani_stats: NaN among the sort keys or pair ANI values (the reference panics here)"); return SWG_ERR_RANGE; }
+    if (a.fallback) { set_err(c, "swg_ani_stats: input not supported by the device front end (> 64 GiB, or a sequence-name hash collision)"); return SWG_ERR_UNSUPPORTED; }
+    *ani50 = a.res.ani50;
+    if (n_pairs) *n_pairs = a.res.n_pairs;
+    return SWG_OK;
 }
 
 } // extern "C"

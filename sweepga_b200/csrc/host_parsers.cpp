@@ -229,6 +229,30 @@ int swg_parse_identity_value(const char *s, int has_ani, double ani, double *out
     return SWG_OK;
 }
 
+// parse_ani_method, src/main.rs:296-331.  SWG_ERR_PARSE <=> None (the caller then uses n50-identity, main.rs:3579).
+int swg_parse_ani_method(const char *s, int *method, double *percentile, int *sort) {
+    if (!s || !method || !percentile || !sort) return SWG_ERR_ARG;
+    const std::string lower = to_lower_ascii(s);
+    *percentile = 0.0;
+    *sort = SWG_NSORT_IDENTITY;
+    if (lower == "all") { *method = SWG_ANI_ALL; return SWG_OK; }
+    if (lower == "orthogonal" || lower == "1:1") { *method = SWG_ANI_ORTHOGONAL; return SWG_OK; }
+    if (lower.empty() || lower[0] != 'n') return SWG_ERR_PARSE;
+    std::vector<std::string> parts = split(lower.substr(1), '-');
+    double p;
+    if (parts.empty() || !rust_parse_f64(parts[0].data(), parts[0].size(), &p)) return SWG_ERR_PARSE;
+    if (!(p > 0.0 && p <= 100.0)) return SWG_ERR_PARSE;
+    if (parts.size() > 1) {
+        if (parts[1] == "length") *sort = SWG_NSORT_LENGTH;
+        else if (parts[1] == "identity") *sort = SWG_NSORT_IDENTITY;
+        else if (parts[1] == "score") *sort = SWG_NSORT_SCORE;
+        else return SWG_ERR_PARSE;
+    }
+    *method = SWG_ANI_NPERCENTILE;
+    *percentile = p;
+    return SWG_OK;
+}
+
 uint64_t swg_round_nice(uint64_t v) {
     if (v == 0) return 0;
     uint64_t step = v <= 500 ? 50 : v <= 1000 ? 100 : v <= 3000 ? 200 : 500;

@@ -575,9 +575,15 @@ static void tok_read(swg_ctx *c, const u64 *d_tc, u64 *h) {
     SWG_CUDA(cudaStreamSynchronize(c->stream));
 }
 
-// Tokenise hp.text on the device.  All device memory comes from c->io and stays valid until the next front-end call.
-static void tokenize_device(swg_ctx *c, const swg_paf &hp, DevPaf &dp) {
-    const u32 long_thresh = getenv("SWG_TOK_LONG") ? (u32)atoi(getenv("SWG_TOK_LONG")) : 4096u; // read per call: the tests vary it
+struct DevLines { // the text in HBM and the start offset of every line (line_start[n_lines] = one past the last terminator)
+    char *text = nullptr;
+    u64 *line_start = nullptr;
+    u32 n_lines = 0;
+    u32 *bsum = nullptr, *d_cnt = nullptr; // scan scratch sized for the word scan (>= any per-line scan), 4 counters
+};
+
+// Copies hp.text to the device (c->io, which is reset) and finds the line starts.  Events c->ev[0] / c->ev[1] bracket the upload.
+static DevLines load_lines(swg_ctx *c, const swg_paf &hp) {
     const u64 B = hp.text_len;
     cudaStream_t st = c->stream;
     LaunchCounter &lc = c->lc;
@@ -585,12 +591,11 @@ static void tokenize_device(swg_ctx *c, const swg_paf &hp, DevPaf &dp) {
     Arena &A = c->io;
     A.reserve((size_t)B * 2 + ((size_t)64 << 20));
     c->arena.reserve((size_t)64 << 20); // scratch of the small sorts
-    dp = DevPaf();
-    dp.text_len = B;
-    if (B == 0) return;
-    cudaEvent_t e0 = c->ev[0], e1 = c->ev[1], e2 = c->ev[2];
+    DevLines dl;
+    if (B == 0) return dl;
+    cudaEvent_t e0 = c->ev[0], e1 = c->ev[1];
     char *text = A.take<char>(B + 64);
-    dp.text = text;
+    dl.text = text;
     SWG_CUDA(cudaEventRecord(e0, st));
     SWG_CUDA(cudaMemsetAsync(text + (B & ~(u64)15), 0, 48, st));
     SWG_CUDA(cudaEventRecord(c->ev_copy[0], st));
@@ -615,8 +620,12 @@ static void tokenize_device(swg_ctx *c, const swg_paf &hp, DevPaf &dp) {
     const u64 n_lines64 = (u64)n_nl + (last_nl ? 0 : 1);
     if (n_lines64 >= 0x7FFFFFF0ull) throw RangeError{"too many lines (must be < 2^31 per context)"};
     const u32 n_lines = (u32)n_lines64;
-    dp.n_lines = n_lines;
+    dl.n_lines = n_lines;
+    if (n_lines > nw) bsum = A.take<u32>(scan_temp_u32(n_lines)); // lines shorter than 16 bytes on average: the per-line scans need more tiles
+    dl.bsum = bsum;
+    dl.d_cnt = d_cnt;
     u64 *line_start = A.take<u64>((size_t)n_lines + 2);
+    dl.line_start = line_start;
     {
         const u64 first_last[2] = {0, last_nl ? B : B + 1};
         SWG_CUDA(cudaMemcpyAsync(line_start, &first_last[0], 8, cudaMemcpyHostToDevice, st));
@@ -640,6 +649,96 @@ static void tokenize_device(swg_ctx *c, const swg_paf &hp, DevPaf &dp) {
                    }
                },
                nw, bsum, d_cnt, st, lc);
+    return dl;
+}
+
+struct NameTable { // result of intern_names
+    u32 *qid = nullptr, *tid = nullptr;
+    u32 n_seq = 0;
+    std::vector<std::string> names;
+};
+
+// Names -> ids in first-appearance order (query before target within a record).  R needs off / qh / th / qlen / trel /
+// tlen; tc is the TC_COUNT counter block, d_cnt 4 scratch counters.  Memory comes from c->io.
+static NameTable intern_names(swg_ctx *c, const char *text, const char *host_text, const TokCols &R, u32 n, u64 *tc, u32 *d_cnt) {
+    cudaStream_t st = c->stream;
+    LaunchCounter &lc = c->lc;
+    Arena &A = c->io;
+    u64 h_tc[TC_COUNT];
+    NameTable nt;
+    u32 hcap = 1u << 16;
+    u64 *hk = nullptr, *hfirst = nullptr;
+    u32 D = 0;
+    SWG_CUDA(cudaMemsetAsync(tc + TC_COLLISION, 0, sizeof(u64), st));
+    while (true) {
+        hk = A.take<u64>(hcap);
+        hfirst = A.take<u64>(hcap);
+        SWG_CUDA(cudaMemsetAsync(hk, 0xFF, sizeof(u64) * hcap, st));
+        SWG_CUDA(cudaMemsetAsync(hfirst, 0xFF, sizeof(u64) * hcap, st));
+        SWG_CUDA(cudaMemsetAsync(tc + TC_DISTINCT, 0, 2 * sizeof(u64), st)); // TC_DISTINCT, TC_TABLE_FULL
+        k_name_insert<<<cdiv(n, 256), 256, 0, st>>>(R.qh, R.th, n, hk, hfirst, hcap - 1, tc);
+        lc.n++;
+        tok_read(c, tc, h_tc);
+        if (!h_tc[TC_TABLE_FULL]) { D = (u32)h_tc[TC_DISTINCT]; break; }
+        if (hcap >= (1u << 31)) throw FrontEndFallback{"too many distinct sequence names for the device table"};
+        hcap = hcap >= (1u << 27) ? hcap * 2 : hcap * 16;
+    }
+    // occupied slots ordered by first appearance
+    u64 *sk = A.take<u64>(D), *sk2 = A.take<u64>(D);
+    u32 *sv = A.take<u32>(D), *sv2 = A.take<u32>(D);
+    u32 *bsum2 = A.take<u32>(scan_temp_u32(hcap));
+    scan_apply([=] __device__(u32 s) -> u32 { return hk[s] != NONE64 ? 1u : 0u; },
+               [=] __device__(u32 s, u32 ex, u32 v) { if (v) { sk[ex] = hfirst[s]; sv[ex] = s; } }, hcap, bsum2, d_cnt, st, lc);
+    sort_pairs(c, sk, sk2, sv, sv2, D, bits_for(2ull * n + 1));
+    u32 *id_of_slot = A.take<u32>(hcap);
+    u64 *rep_off = A.take<u64>(D);
+    u32 *rep_len = A.take<u32>(D);
+    {
+        const u64 *skc = sk;
+        const u32 *svc = sv;
+        launch_for<t_name_assign>(D, st, lc, [=] __device__(u32 j) {
+            id_of_slot[svc[j]] = j;
+            const u64 order = skc[j];
+            const u32 r = (u32)(order >> 1);
+            const bool side = order & 1;
+            rep_off[j] = R.off[r] + (side ? R.trel[r] : 0);
+            rep_len[j] = side ? R.tlen[r] : R.qlen[r];
+        });
+    }
+    nt.qid = A.take<u32>(n);
+    nt.tid = A.take<u32>(n);
+    k_name_lookup<<<cdiv(n, 256), 256, 0, st>>>(text, R, n, hk, id_of_slot, hcap - 1, rep_off, rep_len, nt.qid, nt.tid, tc);
+    lc.n++;
+    std::vector<u64> h_off(D);
+    std::vector<u32> h_len(D);
+    SWG_CUDA(cudaMemcpyAsync(h_off.data(), rep_off, (size_t)D * 8, cudaMemcpyDeviceToHost, st));
+    SWG_CUDA(cudaMemcpyAsync(h_len.data(), rep_len, (size_t)D * 4, cudaMemcpyDeviceToHost, st));
+    tok_read(c, tc, h_tc);
+    if (h_tc[TC_COLLISION]) throw FrontEndFallback{"64-bit name hash collision"};
+    nt.n_seq = D;
+    nt.names.resize(D);
+    for (u32 j = 0; j < D; j++) nt.names[j].assign(host_text + h_off[j], h_len[j]);
+    return nt;
+}
+
+// Tokenise hp.text on the device.  All device memory comes from c->io and stays valid until the next front-end call.
+static void tokenize_device(swg_ctx *c, const swg_paf &hp, DevPaf &dp) {
+    const u32 long_thresh = getenv("SWG_TOK_LONG") ? (u32)atoi(getenv("SWG_TOK_LONG")) : 4096u; // read per call: the tests vary it
+    const u64 B = hp.text_len;
+    cudaStream_t st = c->stream;
+    LaunchCounter &lc = c->lc;
+    Arena &A = c->io;
+    dp = DevPaf();
+    dp.text_len = B;
+    const DevLines dl = load_lines(c, hp);
+    if (B == 0) return;
+    cudaEvent_t e0 = c->ev[0], e1 = c->ev[1], e2 = c->ev[2];
+    char *text = dl.text;
+    dp.text = text;
+    const u32 n_lines = dl.n_lines;
+    dp.n_lines = n_lines;
+    const u64 *line_start = dl.line_start;
+    u32 *bsum = dl.bsum, *d_cnt = dl.d_cnt;
 
     // ---- 2./3. per-line parse --------------------------------------------------------------------
     auto take_cols = [&](u32 n) {
@@ -747,57 +846,14 @@ static void tokenize_device(swg_ctx *c, const swg_paf &hp, DevPaf &dp) {
     if (n == 0) { SWG_CUDA(cudaStreamSynchronize(st)); return; }
 
     // ---- 4. names -> ids in first-appearance order ------------------------------------------------
-    u32 hcap = 1u << 16;
-    u64 *hk = nullptr, *hfirst = nullptr;
-    u32 D = 0;
-    while (true) {
-        hk = A.take<u64>(hcap);
-        hfirst = A.take<u64>(hcap);
-        SWG_CUDA(cudaMemsetAsync(hk, 0xFF, sizeof(u64) * hcap, st));
-        SWG_CUDA(cudaMemsetAsync(hfirst, 0xFF, sizeof(u64) * hcap, st));
-        SWG_CUDA(cudaMemsetAsync(tc + TC_DISTINCT, 0, 2 * sizeof(u64), st)); // TC_DISTINCT, TC_TABLE_FULL
-        k_name_insert<<<cdiv(n, 256), 256, 0, st>>>(R.qh, R.th, n, hk, hfirst, hcap - 1, tc);
-        lc.n++;
-        tok_read(c, tc, h_tc);
-        if (!h_tc[TC_TABLE_FULL]) { D = (u32)h_tc[TC_DISTINCT]; break; }
-        if (hcap >= (1u << 31)) throw FrontEndFallback{"too many distinct sequence names for the device table"};
-        hcap = hcap >= (1u << 27) ? hcap * 2 : hcap * 16;
-    }
-    // occupied slots ordered by first appearance
-    u64 *sk = A.take<u64>(D), *sk2 = A.take<u64>(D);
-    u32 *sv = A.take<u32>(D), *sv2 = A.take<u32>(D);
-    u32 *bsum2 = A.take<u32>(scan_temp_u32(hcap));
-    scan_apply([=] __device__(u32 s) -> u32 { return hk[s] != NONE64 ? 1u : 0u; },
-               [=] __device__(u32 s, u32 ex, u32 v) { if (v) { sk[ex] = hfirst[s]; sv[ex] = s; } }, hcap, bsum2, d_cnt, st, lc);
-    sort_pairs(c, sk, sk2, sv, sv2, D, bits_for(2ull * n + 1));
-    u32 *id_of_slot = A.take<u32>(hcap);
-    u64 *rep_off = A.take<u64>(D);
-    u32 *rep_len = A.take<u32>(D);
     {
-        const u64 *skc = sk;
-        const u32 *svc = sv;
-        launch_for<t_name_assign>(D, st, lc, [=] __device__(u32 j) {
-            id_of_slot[svc[j]] = j;
-            const u64 order = skc[j];
-            const u32 r = (u32)(order >> 1);
-            const bool side = order & 1;
-            rep_off[j] = R.off[r] + (side ? R.trel[r] : 0);
-            rep_len[j] = side ? R.tlen[r] : R.qlen[r];
-        });
+        NameTable nt = intern_names(c, text, hp.text, R, n, tc, d_cnt);
+        dp.qid = nt.qid;
+        dp.tid = nt.tid;
+        dp.n_seq = nt.n_seq;
+        dp.names.swap(nt.names);
     }
-    dp.qid = A.take<u32>(n);
-    dp.tid = A.take<u32>(n);
-    k_name_lookup<<<cdiv(n, 256), 256, 0, st>>>(text, R, n, hk, id_of_slot, hcap - 1, rep_off, rep_len, dp.qid, dp.tid, tc);
-    lc.n++;
-    std::vector<u64> h_off(D);
-    std::vector<u32> h_len(D);
-    SWG_CUDA(cudaMemcpyAsync(h_off.data(), rep_off, (size_t)D * 8, cudaMemcpyDeviceToHost, st));
-    SWG_CUDA(cudaMemcpyAsync(h_len.data(), rep_len, (size_t)D * 4, cudaMemcpyDeviceToHost, st));
-    tok_read(c, tc, h_tc);
-    if (h_tc[TC_COLLISION]) throw FrontEndFallback{"64-bit name hash collision"};
-    dp.n_seq = D;
-    dp.names.resize(D);
-    for (u32 j = 0; j < D; j++) dp.names[j].assign(hp.text + h_off[j], h_len[j]);
+    const u32 D = dp.n_seq;
     paf_prefix_ids(dp.names, &dp.hP, &dp.hP2);
     dp.P = A.take<u32>(D);
     dp.P2 = A.take<u32>(D);

@@ -47,6 +47,16 @@ struct PafLine {
 // `len` excludes the line terminator ("\n" or "\r\n").  SKIP: fewer than 11 fields.
 PafLine::Kind paf_parse_line(const char *line, size_t len, PafLine *out);
 
+// One PAF line the way calculate_ani_stats reads it (src/main.rs:412-460, :538-604): f64 matches / block length,
+// the FIRST dv:f: tag that parses overrides the matches.  false: the line is skipped ('#', empty, < 11 fields).
+struct AniLine {
+    const char *qname = nullptr, *tname = nullptr;
+    size_t qname_len = 0, tname_len = 0;
+    double matches = 0.0, block = 1.0;
+    uint64_t qlen = 0, tlen = 0;
+};
+bool paf_ani_line(const char *line, size_t len, AniLine *out);
+
 // Opens `path` (plain, .gz or .bgz) and fills text / text_len (mmap when possible); false + message on failure.
 bool paf_open_text(const char *path, swg_paf *p, std::string *err);
 

@@ -134,6 +134,45 @@ swg::PafLine::Kind swg::paf_parse_line(const char *line, size_t len, PafLine *ou
     return PafLine::OK;
 }
 
+bool swg::paf_ani_line(const char *line, size_t len, AniLine *out) {
+    if (len == 0 || line[0] == '#') return false; // main.rs:414-416
+    const char *fs[11];
+    size_t fl[11];
+    int nf = 0;
+    size_t a = 0;
+    while (nf < 11) {
+        const char *tab = (const char *)memchr(line + a, '\t', len - a);
+        size_t b = tab ? (size_t)(tab - line) : len;
+        fs[nf] = line + a;
+        fl[nf] = b - a;
+        nf++;
+        if (!tab) { a = len + 1; break; }
+        a = b + 1;
+    }
+    if (nf < 11) return false;
+    out->qname = fs[0]; out->qname_len = fl[0];
+    out->tname = fs[5]; out->tname_len = fl[5];
+    if (!rust_parse_u64(fs[1], fl[1], &out->qlen)) out->qlen = 0;
+    if (!rust_parse_u64(fs[6], fl[6], &out->tlen)) out->tlen = 0;
+    double m, b;
+    if (!rust_parse_f64(fs[9], fl[9], &m)) m = 0.0;
+    if (!rust_parse_f64(fs[10], fl[10], &b)) b = 1.0;
+    double fm = m;
+    while (a <= len) { // the first dv:f: tag that parses (main.rs:445-453)
+        const char *tab = a < len ? (const char *)memchr(line + a, '\t', len - a) : nullptr;
+        size_t e = tab ? (size_t)(tab - line) : len;
+        if (e - a >= 5 && memcmp(line + a, "dv:f:", 5) == 0) {
+            double dv;
+            if (rust_parse_f64(line + a + 5, e - a - 5, &dv)) { fm = (1.0 - dv) * b; break; }
+        }
+        if (!tab) break;
+        a = e + 1;
+    }
+    out->matches = fm;
+    out->block = b;
+    return true;
+}
+
 namespace {
 
 static void parse_chunk(const char *text, Chunk &c) {

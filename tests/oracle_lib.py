@@ -122,6 +122,21 @@ def parse_paf(path):
         _lib.orc_paf_free(h)
 
 
+_lib.orc_ani_stats.restype = C.c_int
+_lib.orc_ani_stats.argtypes = [C.c_char_p, C.c_int, C.c_double, C.c_int, f64p, u64p]
+
+
+def ani_stats(path, method, percentile=0.0, sort=1):
+    """Oracle calculate_ani_stats (src/main.rs:334-688) -> (ani50, n_pairs); raises ValueError where the reference panics."""
+    ani, npairs = C.c_double(), C.c_uint64()
+    rc = _lib.orc_ani_stats(os.fsencode(path), method, percentile, sort, C.byref(ani), C.byref(npairs))
+    if rc == -2:
+        raise ValueError("NaN (the reference panics)")
+    if rc != 0:
+        raise IOError(path)
+    return ani.value, int(npairs.value)
+
+
 def filter_paf(cfg, in_path, out_path):
     """Oracle PafFilter::filter_paf (parse + filter + tagged write) -> stats"""
     c = cfg.to_c()

@@ -190,3 +190,47 @@ def test_oracle_plane_sweep_core_vectors():
     assert sorted(oracle_lib.plane_sweep_core(iv, None, 0.95)) == [0, 1, 2]
     assert oracle_lib.plane_sweep_core([(0, 10, 1.0)], 1, 0.5) == [0]
     assert oracle_lib.plane_sweep_core([], 1, 0.5) == []
+
+
+ANI_PAF = "\n".join([
+    "A#1#c1\t1000\t0\t100\t+\tB#1#c1\t2000\t0\t100\t90\t100\t60",
+    "A#1#c1\t1000\t0\t100\t+\tB#1#c1\t2000\t0\t200\t150\t200\t60",
+    "A#1#c2\t500\t0\t100\t+\tC#1#c1\t3000\t0\t100\t50\t100\t60\ttp:A:P\tdv:f:bad\tdv:f:0.1\tdv:f:0.5",   # first dv that parses
+    "A#1#c1\t1000\t0\t10\t+\tA#1#c2\t500\t0\t10\t10\t10\t60",                                            # same genome: skipped
+    "# comment\twith\ttabs\t1\t2\t3\t4\t5\t6\t7\t8\t9",
+    "",
+    "short\tline",
+]) + "\n"
+
+
+def test_parse_ani_method_matches_reference_grammar():
+    """parse_ani_method, src/main.rs:296-331."""
+    P = swg.parse_ani_method
+    assert P("all") == (swg.ANI_ALL, 0.0, swg.NSORT_IDENTITY) and P("ALL")[0] == swg.ANI_ALL
+    assert P("orthogonal")[0] == swg.ANI_ORTHOGONAL and P("1:1")[0] == swg.ANI_ORTHOGONAL
+    assert P("n50") == (swg.ANI_NPERCENTILE, 50.0, swg.NSORT_IDENTITY)
+    assert P("N90-length") == (swg.ANI_NPERCENTILE, 90.0, swg.NSORT_LENGTH)
+    assert P("n100-score") == (swg.ANI_NPERCENTILE, 100.0, swg.NSORT_SCORE)
+    assert P("n12.5-identity-extra") == (swg.ANI_NPERCENTILE, 12.5, swg.NSORT_IDENTITY)
+    for bad in ("", "n", "n0", "n101", "n-5", "n50-foo", "nan", "ninf", "median", "n50-"):
+        assert P(bad) is None, bad
+
+
+def test_oracle_ani_stats_known_answers(tmp_path):
+    """calculate_ani_stats / calculate_ani_n_percentile (src/main.rs:334-688) on a hand-computed input (the reference has no
+    test of its own for this function: parity unpinned, the expected values below follow the source line by line)."""
+    p = tmp_path / "ani.paf"
+    p.write_text(ANI_PAF)
+    ab, ac = (90.0 + 150.0) / (100.0 + 200.0), ((1.0 - 0.1) * 100.0) / 100.0
+    assert oracle_lib.ani_stats(str(p), 0) == ((ab + ac) / 2.0, 2)
+    # genome size 1000 + 2000 + 500 + 3000 = 6500; n100 never reaches it: every alignment is used
+    assert oracle_lib.ani_stats(str(p), 2, 100.0, 1) == ((ab + ac) / 2.0, 2)
+    # n1: threshold 65, the first alignment of the sorted list crosses it
+    assert oracle_lib.ani_stats(str(p), 2, 1.0, 1) == (0.9, 1)      # identity order: 0.9 (line 1), 0.9 (line 3), 0.75
+    assert oracle_lib.ani_stats(str(p), 2, 1.0, 0) == (0.75, 1)     # length order: 200, 100, 100
+    # n4: threshold 260 -> identity order takes lines 1, 3 and 2 (100 + 100 + 200 >= 260 at the third)
+    assert oracle_lib.ani_stats(str(p), 2, 4.0, 1) == ((ab + ac) / 2.0, 2)
+    # n3: threshold 195 -> lines 1 and 3: pairs (A,B) = 0.9, (A,C) = 0.9
+    assert oracle_lib.ani_stats(str(p), 2, 3.0, 1) == ((0.9 + ac) / 2.0, 2)
+    (tmp_path / "none.paf").write_text("A#1#x\t1\t0\t1\t+\tA#1#y\t1\t0\t1\t1\t1\t60\n")
+    assert oracle_lib.ani_stats(str(tmp_path / "none.paf"), 0) == (0.0, 0)
