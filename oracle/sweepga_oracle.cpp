@@ -7,6 +7,9 @@
 // Parity status: PINNED against the reference's own known-answer tests
 // (tests/test_reference_vectors.py transcribes them with file:line), the Rust
 // reference itself cannot be compiled here (no cargo/rustc, un-vendored deps).
+// Exception: orc_ani_stats (the ANI pre-pass, src/main.rs:334-688) — PARITY UNPINNED:
+// the reference holds no test or vector for it; tests/test_host.py checks the
+// restatement against answers computed by hand from the source.
 //
 // Every function cites the reference file:line it restates
 // (paths relative to /root/reference).  Containers: BTreeSet -> std::set with
