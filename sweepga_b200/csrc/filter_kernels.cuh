@@ -609,16 +609,23 @@ __device__ __forceinline__ bool overlaps_more_than(u32 s1, u32 e1, u32 s2, u32 e
 }
 
 // ---------------------------------------------------------------------------------------------
-// General plane sweep over event-sorted groups, one warp per group
-// (plane_sweep_exact.rs:197-433: event loop + mark_good).  The active set is a rank-ordered
-// array (score desc, start asc, item asc) in a per-group slice of global scratch (L1/L2
-// resident for ordinary group sizes).  good/flagged follow the closed form
-// "kept <=> ever in the top-n at an evaluated position and never flagged overlapped".
+// General plane sweep (plane_sweep_exact.rs:197-433: event loop + mark_good) over groups whose items are sorted by
+// (start, item).  Only the Begins are sorted: the End events come out of the active set itself — the next event
+// position is min(next start, smallest end among the active items), which visits exactly the positions of the
+// reference's (position, Begin-before-End) event list, in the same order, with half the sort volume.
+// At a position: insert its Begins, remove every active item that ends there, then mark_good.
+// good/flagged follow the closed form "kept <=> ever in the top-n at an evaluated position and never flagged
+// overlapped".
 // ---------------------------------------------------------------------------------------------
+struct SweepItem { // per item, in (group, start, item) order, so that a group is one contiguous stream
+    u64 skey;  // score_desc_key of the item
+    u32 start; // axis interval of the item
+    u32 end;
+};
 struct ActEntry {
-    u64 skey;  // score_desc_key
-    u32 start; // axis start
-    u32 item;
+    u64 skey; // score_desc_key
+    u32 start, end;
+    u32 item, pad;
 };
 __device__ __forceinline__ bool act_less(const ActEntry &a, const ActEntry &b) {
     if (a.skey != b.skey) return a.skey < b.skey;
@@ -626,11 +633,12 @@ __device__ __forceinline__ bool act_less(const ActEntry &a, const ActEntry &b) {
     return a.item < b.item;
 }
 
+// One warp per group, for the groups whose pile is deeper than the per-thread array of k_sweep_small.  The active set
+// is a rank-ordered array (score desc, start asc, item asc) in a per-group slice of global scratch.
 __global__ void __launch_bounds__(128)
-k_sweep_groups(const u32 *__restrict__ eitem /* item * 2 + type, in (group, pos, type) order */, const u32 *__restrict__ gstart, u32 n_groups,
-               u32 n_events, const u32 *__restrict__ it_start, const u32 *__restrict__ it_end,
-               const double *__restrict__ it_score, u64 n_keep, double thr, ActEntry *act, u8 *good, u8 *flagged,
-               const u32 *__restrict__ work, const u32 *__restrict__ n_work_ptr, u32 *group_counter, u64 *ctr) {
+k_sweep_groups(const u32 *__restrict__ sitem, const SweepItem *__restrict__ sdata, const u32 *__restrict__ gstart, u32 n_groups, u32 n_sorted,
+               u64 n_keep, double thr, ActEntry *act, u8 *good, u8 *flagged, const u32 *__restrict__ work,
+               const u32 *__restrict__ n_work_ptr, u32 *group_counter, u64 *ctr) {
     const u32 full = 0xFFFFFFFFu;
     const u32 lane = lane_id();
     const u32 n_work = *n_work_ptr;
@@ -640,69 +648,72 @@ k_sweep_groups(const u32 *__restrict__ eitem /* item * 2 + type, in (group, pos,
         w = __shfl_sync(full, w, 0);
         if (w >= n_work) break;
         const u32 g = work[w];
-        const u32 es = gstart[g], ee = (g + 1 < n_groups) ? gstart[g + 1] : n_events;
-        const u32 items = (ee - es) >> 1;
-        if (items <= 1) { // plane_sweep_exact.rs:274-276
-            if (lane == 0) good[eitem[es] >> 1] = 1;
+        const u32 es = gstart[g], ee = (g + 1 < n_groups) ? gstart[g + 1] : n_sorted;
+        if (ee - es <= 1) { // plane_sweep_exact.rs:274-276
+            if (lane == 0) good[sitem[es]] = 1;
             continue;
         }
-        ActEntry *A = act + (es >> 1);
+        ActEntry *A = act + es;
         u32 size = 0;
         u32 e = es;
-        while (e < ee) {
-            // apply all events at this position: Begins (type 0) sort before Ends (type 1)
-            const u32 ev0 = eitem[e];
-            const u32 cur = (ev0 & 1) ? it_end[ev0 >> 1] : it_start[ev0 >> 1];
+        while (e < ee || size > 0) {
+            // the position of the next event
+            u32 mn = NONE32;
+            for (u32 b = lane; b < size; b += 32) mn = min(mn, A[b].end);
+            mn = __reduce_min_sync(full, mn);
+            u32 cur = mn;
+            if (e < ee) cur = min(cur, sdata[e].start);
+            bool ends_here = size > 0 && mn == cur;
+            // Begins at cur
             while (e < ee) {
-                const u32 ev = eitem[e];
-                const u32 item = ev >> 1;
-                const bool is_end = ev & 1;
-                if ((is_end ? it_end[item] : it_start[item]) != cur) break;
+                const SweepItem d = sdata[e];
+                if (d.start != cur) break;
                 ActEntry x;
-                x.skey = score_desc_key(it_score[item]);
-                x.start = it_start[item];
-                x.item = item;
+                x.skey = d.skey; x.start = d.start; x.end = d.end; x.item = sitem[e]; x.pad = 0;
+                ends_here |= d.end == cur;
                 // position of x in A: number of entries ordered before it
                 u32 cnt = 0;
                 for (u32 b = lane; b < size; b += 32) cnt += act_less(A[b], x) ? 1 : 0;
                 cnt = __reduce_add_sync(full, cnt);
-                if (!is_end) {
-                    // near-tie audit: neighbours whose score key differs by <= 2 ulp but is not equal
-                    if (lane == 0) {
-                        u32 near = 0;
-                        if (cnt > 0) { u64 d = x.skey - A[cnt - 1].skey; near += (d != 0 && d <= 2); }
-                        if (cnt < size) { u64 d = A[cnt].skey - x.skey; near += (d != 0 && d <= 2); }
-                        if (near) atomicAdd((unsigned long long *)&ctr[C_NEAR_TIES], (unsigned long long)near);
-                    }
-                    // shift [cnt, size) up by one, from the top, 32 at a time
-                    for (u32 hi = size; hi > cnt;) {
-                        u32 lo = hi > cnt + 32 ? hi - 32 : cnt;
-                        u32 b = lo + lane;
-                        ActEntry t;
-                        bool mv = b < hi;
-                        if (mv) t = A[b];
-                        __syncwarp();
-                        if (mv) A[b + 1] = t;
-                        __syncwarp();
-                        hi = lo;
-                    }
-                    if (lane == 0) A[cnt] = x;
-                    size++;
-                } else {
-                    // remove the entry at cnt (it is there: every End follows its Begin)
-                    for (u32 lo = cnt + 1; lo < size; lo += 32) {
-                        u32 b = lo + lane;
-                        ActEntry t;
-                        bool mv = b < size;
-                        if (mv) t = A[b];
-                        __syncwarp();
-                        if (mv) A[b - 1] = t;
-                        __syncwarp();
-                    }
-                    size--;
+                // near-tie audit: neighbours whose score key differs by <= 2 ulp but is not equal
+                if (lane == 0) {
+                    u32 near = 0;
+                    if (cnt > 0) { u64 df = x.skey - A[cnt - 1].skey; near += (df != 0 && df <= 2); }
+                    if (cnt < size) { u64 df = A[cnt].skey - x.skey; near += (df != 0 && df <= 2); }
+                    if (near) atomicAdd((unsigned long long *)&ctr[C_NEAR_TIES], (unsigned long long)near);
                 }
+                // shift [cnt, size) up by one, from the top, 32 at a time
+                for (u32 hi = size; hi > cnt;) {
+                    u32 lo = hi > cnt + 32 ? hi - 32 : cnt;
+                    u32 b = lo + lane;
+                    ActEntry t;
+                    bool mv = b < hi;
+                    if (mv) t = A[b];
+                    __syncwarp();
+                    if (mv) A[b + 1] = t;
+                    __syncwarp();
+                    hi = lo;
+                }
+                if (lane == 0) A[cnt] = x;
+                size++;
                 __syncwarp();
                 e++;
+            }
+            // Ends at cur: stable compaction of the entries that stay
+            if (ends_here) {
+                u32 out = 0;
+                for (u32 lo = 0; lo < size; lo += 32) {
+                    const u32 b = lo + lane;
+                    ActEntry t;
+                    const bool in = b < size;
+                    if (in) t = A[b];
+                    const bool kp = in && t.end != cur;
+                    const u32 m = __ballot_sync(full, kp);
+                    if (kp) A[out + __popc(m & lanemask_lt())] = t; // destination <= source, earlier chunks are consumed
+                    out += __popc(m);
+                    __syncwarp();
+                }
+                size = out;
             }
             if (size == 0) continue;
             // mark_good (plane_sweep_exact.rs:197-259)
@@ -710,12 +721,10 @@ k_sweep_groups(const u32 *__restrict__ eitem /* item * 2 + type, in (group, pos,
             for (u32 b = lane; b < top; b += 32) good[A[b].item] = 1;
             if (thr < 1.0 && top < size) {
                 for (u32 b = top + lane; b < size; b += 32) {
-                    const u32 m = A[b].item;
-                    if (flagged[m]) continue;
-                    const u32 ms = it_start[m], me = it_end[m];
+                    const ActEntry me = A[b];
+                    if (flagged[me.item]) continue;
                     for (u32 t = 0; t < top; t++) {
-                        const u32 k = A[t].item;
-                        if (overlaps_more_than(ms, me, it_start[k], it_end[k], thr)) { flagged[m] = 1; break; }
+                        if (overlaps_more_than(me.start, me.end, A[t].start, A[t].end, thr)) { flagged[me.item] = 1; break; }
                     }
                 }
             }
@@ -725,19 +734,13 @@ k_sweep_groups(const u32 *__restrict__ eitem /* item * 2 + type, in (group, pos,
     }
 }
 
-// Per-event copies of what the walker needs, in event order, so that a group is one contiguous stream
-struct SweepEvent {
-    u64 skey;  // score_desc_key of the item
-    u32 start; // axis interval of the item
-    u32 end;
-};
 // The same sweep, ONE THREAD PER GROUP, for the ordinary case (a (sequence, partner-genome) group of ~10^2 intervals
 // with a pile depth of a few): the active set lives in a small per-thread array; a group whose depth exceeds
 // SW_DEPTH is handed to the warp kernel above (good/flagged are monotone, so the redo is idempotent).
 constexpr int SW_DEPTH = 12;
 __global__ void __launch_bounds__(128)
-k_sweep_small(const u32 *__restrict__ eitem, const SweepEvent *__restrict__ edata, const u32 *__restrict__ gstart, u32 n_groups,
-              u32 n_events, u64 n_keep, double thr, u8 *good, u8 *flagged, u32 *big_list, u32 *big_count, u32 *group_counter, u64 *ctr) {
+k_sweep_small(const u32 *__restrict__ sitem, const SweepItem *__restrict__ sdata, const u32 *__restrict__ gstart, u32 n_groups, u32 n_sorted,
+              u64 n_keep, double thr, u8 *good, u8 *flagged, u32 *big_list, u32 *big_count, u32 *group_counter, u64 *ctr) {
     const u32 full = 0xFFFFFFFFu;
     bool active = false, exhausted = false;
     u32 g = 0, e = 0, ee = 0, size = 0;
@@ -755,54 +758,61 @@ k_sweep_small(const u32 *__restrict__ eitem, const SweepEvent *__restrict__ edat
                 if (g >= n_groups) exhausted = true;
                 else {
                     e = gstart[g];
-                    ee = (g + 1 < n_groups) ? gstart[g + 1] : n_events;
-                    if (ee - e <= 2) good[eitem[e] >> 1] = 1; // a single interval: kept (plane_sweep_exact.rs:274-276)
+                    ee = (g + 1 < n_groups) ? gstart[g + 1] : n_sorted;
+                    if (ee - e <= 1) good[sitem[e]] = 1; // a single interval: kept (plane_sweep_exact.rs:274-276)
                     else { active = true; size = 0; }
                 }
             }
         }
         if (__all_sync(full, exhausted && !active)) break;
         if (active) {
-            // one event position per iteration: apply its Begins then Ends, then mark_good
-            const u32 ev0 = eitem[e];
-            const SweepEvent d0 = edata[e];
-            const u32 cur = (ev0 & 1) ? d0.end : d0.start;
+            // one event position per iteration: min(next start, smallest active end); its Begins, its Ends, then mark_good
+            u32 mn = NONE32;
+#pragma unroll
+            for (int b = 0; b < SW_DEPTH; b++)
+                if ((u32)b < size) mn = min(mn, a_end[b]);
+            u32 cur = mn;
+            bool have = e < ee;
+            SweepItem d;
+            if (have) { d = sdata[e]; cur = min(cur, d.start); }
+            bool ends_here = size > 0 && mn == cur;
             bool overflow = false;
-            while (e < ee) {
-                const u32 ev = eitem[e];
-                const SweepEvent d = edata[e];
-                if (((ev & 1) ? d.end : d.start) != cur) break;
-                const u32 item = ev >> 1;
-                if (!(ev & 1)) { // Begin: insert in (score desc, start asc, item asc) order
-                    if (size == SW_DEPTH) { overflow = true; break; }
-                    u32 pos = size;
-                    while (pos > 0) {
-                        const u32 q = pos - 1;
-                        const bool less = a_key[q] < d.skey || (a_key[q] == d.skey && (a_start[q] < d.start || (a_start[q] == d.start && (a_item[q] >> 2) < item)));
-                        if (less) break;
-                        a_key[pos] = a_key[q]; a_start[pos] = a_start[q]; a_end[pos] = a_end[q]; a_item[pos] = a_item[q];
-                        pos--;
-                    }
-                    a_key[pos] = d.skey; a_start[pos] = d.start; a_end[pos] = d.end; a_item[pos] = item << 2;
-                    u32 near = 0; // near-tie audit: neighbours whose score key differs by <= 2 ulp but is not equal
-                    if (pos > 0) { const u64 df = d.skey - a_key[pos - 1]; near += (df != 0 && df <= 2); }
-                    if (pos < size) { const u64 df = a_key[pos + 1] - d.skey; near += (df != 0 && df <= 2); }
-                    if (near) atomicAdd((unsigned long long *)&ctr[C_NEAR_TIES], (unsigned long long)near);
-                    size++;
-                } else { // End: remove
-                    u32 pos = 0;
-                    while (pos < size && (a_item[pos] >> 2) != item) pos++;
-                    for (u32 q = pos; q + 1 < size; q++) {
-                        a_key[q] = a_key[q + 1]; a_start[q] = a_start[q + 1]; a_end[q] = a_end[q + 1]; a_item[q] = a_item[q + 1];
-                    }
-                    size--;
+            while (have && d.start == cur) { // Begin: insert in (score desc, start asc, item asc) order
+                if (size == SW_DEPTH) { overflow = true; break; }
+                const u32 item = sitem[e];
+                u32 pos = size;
+                while (pos > 0) {
+                    const u32 q = pos - 1;
+                    const bool less = a_key[q] < d.skey || (a_key[q] == d.skey && (a_start[q] < d.start || (a_start[q] == d.start && (a_item[q] >> 2) < item)));
+                    if (less) break;
+                    a_key[pos] = a_key[q]; a_start[pos] = a_start[q]; a_end[pos] = a_end[q]; a_item[pos] = a_item[q];
+                    pos--;
                 }
+                a_key[pos] = d.skey; a_start[pos] = d.start; a_end[pos] = d.end; a_item[pos] = item << 2;
+                u32 near = 0; // near-tie audit: neighbours whose score key differs by <= 2 ulp but is not equal
+                if (pos > 0) { const u64 df = d.skey - a_key[pos - 1]; near += (df != 0 && df <= 2); }
+                if (pos < size) { const u64 df = a_key[pos + 1] - d.skey; near += (df != 0 && df <= 2); }
+                if (near) atomicAdd((unsigned long long *)&ctr[C_NEAR_TIES], (unsigned long long)near);
+                size++;
+                ends_here |= d.end == cur;
                 e++;
+                have = e < ee;
+                if (have) d = sdata[e];
             }
             if (overflow) {
                 big_list[atomicAdd(big_count, 1u)] = g; // pile deeper than SW_DEPTH: the warp kernel redoes this group
                 active = false;
             } else {
+                if (ends_here) { // End: remove every entry that ends here, keeping the order of the others
+                    u32 o = 0;
+                    for (u32 b = 0; b < size; b++) {
+                        if (a_end[b] != cur) {
+                            if (o != b) { a_key[o] = a_key[b]; a_start[o] = a_start[b]; a_end[o] = a_end[b]; a_item[o] = a_item[b]; }
+                            o++;
+                        }
+                    }
+                    size = o;
+                }
                 if (size > 0) { // mark_good, plane_sweep_exact.rs:197-259
                     const u32 top = (u64)size <= n_keep ? size : (u32)n_keep;
                     for (u32 b = 0; b < top; b++)
@@ -820,7 +830,7 @@ k_sweep_small(const u32 *__restrict__ eitem, const SweepEvent *__restrict__ edat
                         }
                     }
                 }
-                if (e >= ee) active = false;
+                if (e >= ee && size == 0) active = false;
             }
         }
     }

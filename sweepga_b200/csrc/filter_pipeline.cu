@@ -191,91 +191,81 @@ static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 in
     SWG_CUDA(cudaMemsetAsync(keep, 0, n_items, st));
     if (n_items == 0) return;
     if (gb > 62) throw RangeError{"plane-sweep group key wider than 62 bits"};
-    if ((u64)n_items * 2 >= 0x7FFFFFF0ull) throw RangeError{"too many sweep events"};
-    u32 n_ev_all = n_items * 2;
-    u64 *ek = c->arena.take<u64>(n_ev_all), *ek2 = c->arena.take<u64>(n_ev_all);
-    u32 *ev = c->arena.take<u32>(n_ev_all), *ev2 = c->arena.take<u32>(n_ev_all);
+    u64 *ek = c->arena.take<u64>(n_items), *ek2 = c->arena.take<u64>(n_items);
+    u32 *ev = c->arena.take<u32>(n_items), *ev2 = c->arena.take<u32>(n_items);
     u64 *ctr = c->d_ctr;
     SWG_CUDA(cudaMemsetAsync(ctr + C_TMP0, 0, sizeof(u64), st));
-    stage_mark(c, "gs_events");
-    // events: payload = item * 2 + type; order = (group, position, Begin before End).  One sort when the key fits
-    // 64 bits, else two chained stable sorts (position|type first, then the group id).
-    const int pshift = pbits + 1; // position | type
-    const bool wide = (gb + pshift > 64) || (getenv("SWG_FORCE_WIDE_KEYS") != nullptr);
+    stage_mark(c, "gs_keys");
+    // items in (group, start, item) order; the End events come out of the active set (k_sweep_small).  One sort when
+    // the key fits 64 bits, else two chained stable sorts (start first, then the group id).
+    const bool wide = (gb + pbits > 64) || (getenv("SWG_FORCE_WIDE_KEYS") != nullptr);
     launch_for<t_events>(n_items, st, c->lc, [=] __device__(u32 i) {
-        bool inc = include ? (include[i] & include_mask) != 0 : true;
-        u64 k0 = NONE64, k1 = NONE64;
-        if (inc) {
-            const u64 g = wide ? 0 : (gkey[i] << pshift);
-            k0 = g | ((u64)it_start[i] << 1);
-            k1 = g | ((u64)it_end[i] << 1) | 1;
-        }
-        ek[2 * i] = k0; ev[2 * i] = 2 * i;
-        ek[2 * i + 1] = k1; ev[2 * i + 1] = 2 * i + 1;
+        const bool inc = include ? (include[i] & include_mask) != 0 : true;
+        ek[i] = inc ? ((wide ? 0 : (gkey[i] << pbits)) | (u64)it_start[i]) : NONE64;
+        ev[i] = i;
         u32 am = __activemask();
         u32 cnt = __popc(__ballot_sync(am, inc));
         if (cnt && (threadIdx.x & 31) == (u32)(__ffs(am) - 1)) atomicAdd((unsigned long long *)&ctr[C_TMP0], (unsigned long long)cnt);
     });
-    int eshift = pshift;
+    int eshift = pbits;
     stage_mark(c, "gs_sort");
     if (!wide) {
-        sort_pairs(c, ek, ek2, ev, ev2, n_ev_all, gb + pshift);
+        sort_pairs(c, ek, ek2, ev, ev2, n_items, gb + pbits);
     } else {
-        sort_pairs(c, ek, ek2, ev, ev2, n_ev_all, pshift);
+        sort_pairs(c, ek, ek2, ev, ev2, n_items, pbits);
         {
             u64 *kk = ek;
             const u32 *vv = ev;
-            launch_for<t_gather>(n_ev_all, st, c->lc, [=] __device__(u32 u) {
-                const u32 i = vv[u] >> 1;
+            launch_for<t_gather>(n_items, st, c->lc, [=] __device__(u32 u) {
+                const u32 i = vv[u];
                 const bool inc = include ? (include[i] & include_mask) != 0 : true;
                 kk[u] = inc ? gkey[i] : NONE64;
             });
         }
-        sort_pairs(c, ek, ek2, ev, ev2, n_ev_all, gb + 1);
+        sort_pairs(c, ek, ek2, ev, ev2, n_items, gb + 1);
         eshift = 0;
     }
     stage_mark(c, "gs_groups");
     read_counters(c);
-    u32 n_ev = (u32)(c->h_ctr[C_TMP0] * 2);
-    if (n_ev == 0) return;
-    u32 *gstart = c->arena.take<u32>(n_ev / 2 + 1);
-    u32 *bsum = c->arena.take<u32>(scan_temp_u32(n_ev));
+    const u32 n_inc = (u32)c->h_ctr[C_TMP0]; // the included items sort first
+    if (n_inc == 0) return;
+    u32 *gstart = c->arena.take<u32>(n_inc + 1);
+    u32 *bsum = c->arena.take<u32>(scan_temp_u32(n_inc));
     u32 *d_ng = c->arena.take<u32>(2);
     const u64 *ekc = ek;
     scan_apply([=] __device__(u32 u) -> u32 { return (u == 0 || (ekc[u] >> eshift) != (ekc[u - 1] >> eshift)) ? 1u : 0u; },
-               [=] __device__(u32 u, u32 ex, u32 v) { if (v) gstart[ex] = u; }, n_ev, bsum, d_ng, st, c->lc);
+               [=] __device__(u32 u, u32 ex, u32 v) { if (v) gstart[ex] = u; }, n_inc, bsum, d_ng, st, c->lc);
     u32 n_groups = read_u32(c, d_ng);
     u8 *good = c->arena.take<u8>(n_items), *flagged = c->arena.take<u8>(n_items);
     SWG_CUDA(cudaMemsetAsync(good, 0, n_items, st));
     SWG_CUDA(cudaMemsetAsync(flagged, 0, n_items, st));
-    // per-event copies (score key, axis interval) in event order: a group becomes one contiguous stream
-    SweepEvent *edata = c->arena.take<SweepEvent>(n_ev);
+    // per-item copies (score key, axis interval) in sorted order: a group becomes one contiguous stream
+    SweepItem *sdata = c->arena.take<SweepItem>(n_inc);
     {
         const u32 *evc = ev;
-        launch_for<t_sweep_gather>(n_ev, st, c->lc, [=] __device__(u32 u) {
-            const u32 i = evc[u] >> 1;
-            SweepEvent d;
+        launch_for<t_sweep_gather>(n_inc, st, c->lc, [=] __device__(u32 u) {
+            const u32 i = evc[u];
+            SweepItem d;
             d.skey = score_desc_key(it_score[i]);
             d.start = it_start[i];
             d.end = it_end[i];
-            edata[u] = d;
+            sdata[u] = d;
         });
     }
     u32 *big_list = c->arena.take<u32>(n_groups + 1);
     u32 *sw_ctr = c->arena.take<u32>(4); // [0] thread-kernel group counter, [1] deep groups, [2] warp-kernel work counter
     SWG_CUDA(cudaMemsetAsync(sw_ctr, 0, 4 * sizeof(u32), st));
     stage_mark(c, "gs_sweep");
-    k_sweep_small<<<(u32)c->sm_count * 4, 128, 0, st>>>(ev, edata, gstart, n_groups, n_ev, n_keep, thr, good, flagged, big_list, sw_ctr + 1,
+    k_sweep_small<<<(u32)c->sm_count * 4, 128, 0, st>>>(ev, sdata, gstart, n_groups, n_inc, n_keep, thr, good, flagged, big_list, sw_ctr + 1,
                                                        sw_ctr, ctr);
     // groups whose pile is deeper than the per-thread array: one warp each, active set in global scratch
-    ActEntry *act = c->arena.take<ActEntry>(n_ev / 2 + 1);
-    k_sweep_groups<<<(u32)c->sm_count * 4, 128, 0, st>>>(ev, gstart, n_groups, n_ev, it_start, it_end, it_score, n_keep, thr, act, good,
-                                                        flagged, big_list, sw_ctr + 1, sw_ctr + 2, ctr);
+    ActEntry *act = c->arena.take<ActEntry>(n_inc + 1);
+    k_sweep_groups<<<(u32)c->sm_count * 4, 128, 0, st>>>(ev, sdata, gstart, n_groups, n_inc, n_keep, thr, act, good, flagged, big_list,
+                                                        sw_ctr + 1, sw_ctr + 2, ctr);
     {
         const u32 *evc = ev;
-        launch_for<t_sweep_keep>(n_ev, st, c->lc, [=] __device__(u32 u) {
-            if (evc[u] & 1) return;
-            const u32 i = evc[u] >> 1;
+        launch_for<t_sweep_keep>(n_inc, st, c->lc, [=] __device__(u32 u) {
+            const u32 i = evc[u];
             keep[i] = (good[i] && !flagged[i]) ? 1 : 0;
         });
     }
