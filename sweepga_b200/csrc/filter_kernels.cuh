@@ -604,6 +604,14 @@ __device__ __forceinline__ bool overlaps_more_than(u32 s1, u32 e1, u32 s2, u32 e
     u32 os = max(s1, s2), oe = min(e1, e2);
     double ol = oe > os ? (double)(oe - os) : 0.0;
     double ml = fmin((double)(e1 - s1), (double)(e2 - s2));
+    // The reference compares RN(ol / ml) with thr.  ol and ml are exact integers, so whenever ol is outside
+    // thr * ml * (1 +- 2^-49) the rounded quotient is on the same side of thr as the exact one and the f64 division
+    // (the most expensive instruction sequence of the sweep) is not needed; only the band in between divides.
+    if (ml > 0.0 && thr >= 0.0 && thr < 1e300) {
+        const double p = __dmul_rn(thr, ml);
+        if (ol > __dmul_rn(p, 0x1.0000000000008p+0)) return true;
+        if (ol < __dmul_rn(p, 0x1.ffffffffffff0p-1)) return false;
+    }
     double ov = ml > 0.0 ? __ddiv_rn(ol, ml) : 0.0;
     return ov > thr;
 }
@@ -737,13 +745,18 @@ k_sweep_groups(const u32 *__restrict__ sitem, const SweepItem *__restrict__ sdat
 // The same sweep, ONE THREAD PER GROUP, for the ordinary case (a (sequence, partner-genome) group of ~10^2 intervals
 // with a pile depth of a few): the active set lives in a small per-thread array; a group whose depth exceeds
 // SW_DEPTH is handed to the warp kernel above (good/flagged are monotone, so the redo is idempotent).
-constexpr int SW_DEPTH = 12;
+#ifndef SWG_SW_DEPTH
+#define SWG_SW_DEPTH 12
+#endif
+constexpr int SW_DEPTH = SWG_SW_DEPTH;
 __global__ void __launch_bounds__(128)
 k_sweep_small(const u32 *__restrict__ sitem, const SweepItem *__restrict__ sdata, const u32 *__restrict__ gstart, u32 n_groups, u32 n_sorted,
               u64 n_keep, double thr, u8 *good, u8 *flagged, u32 *big_list, u32 *big_count, u32 *group_counter, u64 *ctr) {
     const u32 full = 0xFFFFFFFFu;
     bool active = false, exhausted = false;
     u32 g = 0, e = 0, ee = 0, size = 0;
+    u32 mn = NONE32; // smallest end among the active entries
+    u32 chk = 0;     // n_keep == 1: bit b = entry b has been compared with the current best entry (an overlap never changes)
     u64 a_key[SW_DEPTH];
     u32 a_start[SW_DEPTH], a_end[SW_DEPTH], a_item[SW_DEPTH]; // a_item: item * 4 | (flagged << 1) | good-written
     while (true) {
@@ -760,17 +773,13 @@ k_sweep_small(const u32 *__restrict__ sitem, const SweepItem *__restrict__ sdata
                     e = gstart[g];
                     ee = (g + 1 < n_groups) ? gstart[g + 1] : n_sorted;
                     if (ee - e <= 1) good[sitem[e]] = 1; // a single interval: kept (plane_sweep_exact.rs:274-276)
-                    else { active = true; size = 0; }
+                    else { active = true; size = 0; mn = NONE32; chk = 0; }
                 }
             }
         }
         if (__all_sync(full, exhausted && !active)) break;
         if (active) {
             // one event position per iteration: min(next start, smallest active end); its Begins, its Ends, then mark_good
-            u32 mn = NONE32;
-#pragma unroll
-            for (int b = 0; b < SW_DEPTH; b++)
-                if ((u32)b < size) mn = min(mn, a_end[b]);
             u32 cur = mn;
             bool have = e < ee;
             SweepItem d;
@@ -794,6 +803,8 @@ k_sweep_small(const u32 *__restrict__ sitem, const SweepItem *__restrict__ sdata
                 if (pos < size) { const u64 df = a_key[pos + 1] - d.skey; near += (df != 0 && df <= 2); }
                 if (near) atomicAdd((unsigned long long *)&ctr[C_NEAR_TIES], (unsigned long long)near);
                 size++;
+                chk = pos == 0 ? 0u : ((chk & ((1u << pos) - 1)) | ((chk >> pos) << (pos + 1)));
+                mn = min(mn, d.end);
                 ends_here |= d.end == cur;
                 e++;
                 have = e < ee;
@@ -804,13 +815,19 @@ k_sweep_small(const u32 *__restrict__ sitem, const SweepItem *__restrict__ sdata
                 active = false;
             } else {
                 if (ends_here) { // End: remove every entry that ends here, keeping the order of the others
-                    u32 o = 0;
+                    u32 o = 0, nchk = 0;
+                    mn = NONE32;
+                    const bool best_leaves = a_end[0] == cur;
                     for (u32 b = 0; b < size; b++) {
-                        if (a_end[b] != cur) {
-                            if (o != b) { a_key[o] = a_key[b]; a_start[o] = a_start[b]; a_end[o] = a_end[b]; a_item[o] = a_item[b]; }
+                        const u32 en = a_end[b];
+                        if (en != cur) {
+                            if (o != b) { a_key[o] = a_key[b]; a_start[o] = a_start[b]; a_end[o] = en; a_item[o] = a_item[b]; }
+                            nchk |= ((chk >> b) & 1u) << o;
+                            mn = min(mn, en);
                             o++;
                         }
                     }
+                    chk = best_leaves ? 0u : nchk;
                     size = o;
                 }
                 if (size > 0) { // mark_good, plane_sweep_exact.rs:197-259
@@ -818,13 +835,25 @@ k_sweep_small(const u32 *__restrict__ sitem, const SweepItem *__restrict__ sdata
                     for (u32 b = 0; b < top; b++)
                         if (!(a_item[b] & 1)) { good[a_item[b] >> 2] = 1; a_item[b] |= 1; }
                     if (thr < 1.0) {
-                        for (u32 b = top; b < size; b++) {
-                            if (a_item[b] & 2) continue;
-                            for (u32 t = 0; t < top; t++) {
-                                if (overlaps_more_than(a_start[b], a_end[b], a_start[t], a_end[t], thr)) {
+                        if (top == 1) { // every entry meets a given best entry once
+                            const u32 s0 = a_start[0], e0 = a_end[0];
+                            for (u32 b = 1; b < size; b++) {
+                                if ((a_item[b] & 2) || ((chk >> b) & 1u)) continue;
+                                chk |= 1u << b;
+                                if (overlaps_more_than(a_start[b], a_end[b], s0, e0, thr)) {
                                     flagged[a_item[b] >> 2] = 1;
                                     a_item[b] |= 2;
-                                    break;
+                                }
+                            }
+                        } else {
+                            for (u32 b = top; b < size; b++) {
+                                if (a_item[b] & 2) continue;
+                                for (u32 t = 0; t < top; t++) {
+                                    if (overlaps_more_than(a_start[b], a_end[b], a_start[t], a_end[t], thr)) {
+                                        flagged[a_item[b] >> 2] = 1;
+                                        a_item[b] |= 2;
+                                        break;
+                                    }
                                 }
                             }
                         }

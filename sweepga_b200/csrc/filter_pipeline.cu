@@ -256,7 +256,8 @@ static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 in
     u32 *sw_ctr = c->arena.take<u32>(4); // [0] thread-kernel group counter, [1] deep groups, [2] warp-kernel work counter
     SWG_CUDA(cudaMemsetAsync(sw_ctr, 0, 4 * sizeof(u32), st));
     stage_mark(c, "gs_sweep");
-    k_sweep_small<<<(u32)c->sm_count * 4, 128, 0, st>>>(ev, sdata, gstart, n_groups, n_inc, n_keep, thr, good, flagged, big_list, sw_ctr + 1,
+    static const int sweep_mult = getenv("SWG_SWEEP_MULT") ? atoi(getenv("SWG_SWEEP_MULT")) : 8;
+    k_sweep_small<<<(u32)c->sm_count * sweep_mult, 128, 0, st>>>(ev, sdata, gstart, n_groups, n_inc, n_keep, thr, good, flagged, big_list, sw_ctr + 1,
                                                        sw_ctr, ctr);
     // groups whose pile is deeper than the per-thread array: one warp each, active set in global scratch
     ActEntry *act = c->arena.take<ActEntry>(n_inc + 1);
