@@ -641,6 +641,22 @@ __device__ __forceinline__ bool act_less(const ActEntry &a, const ActEntry &b) {
     return a.item < b.item;
 }
 
+// sort keys of the included items: (group << pbits) | start, payload = item (pbits == 64: the start alone, the group id
+// is applied by a second stable sort); one counter atomic per CTA
+__global__ void __launch_bounds__(256) k_sweep_keys(u32 n_items, const u8 *__restrict__ include, u8 include_mask, const u64 *__restrict__ gkey,
+                                                    int pbits, const u32 *__restrict__ it_start, u64 *__restrict__ ek, u32 *__restrict__ ev,
+                                                    u64 *__restrict__ n_included) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool inc = false;
+    if (i < n_items) {
+        inc = include ? (include[i] & include_mask) != 0 : true;
+        ek[i] = inc ? ((pbits >= 64 ? 0 : (gkey[i] << pbits)) | (u64)it_start[i]) : NONE64;
+        ev[i] = i;
+    }
+    const u32 cnt = __syncthreads_count(inc);
+    if (threadIdx.x == 0 && cnt) atomicAdd((unsigned long long *)n_included, (unsigned long long)cnt);
+}
+
 // One warp per group, for the groups whose pile is deeper than the per-thread array of k_sweep_small.  The active set
 // is a rank-ordered array (score desc, start asc, item asc) in a per-group slice of global scratch.
 __global__ void __launch_bounds__(128)

@@ -199,14 +199,8 @@ static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 in
     // items in (group, start, item) order; the End events come out of the active set (k_sweep_small).  One sort when
     // the key fits 64 bits, else two chained stable sorts (start first, then the group id).
     const bool wide = (gb + pbits > 64) || (getenv("SWG_FORCE_WIDE_KEYS") != nullptr);
-    launch_for<t_events>(n_items, st, c->lc, [=] __device__(u32 i) {
-        const bool inc = include ? (include[i] & include_mask) != 0 : true;
-        ek[i] = inc ? ((wide ? 0 : (gkey[i] << pbits)) | (u64)it_start[i]) : NONE64;
-        ev[i] = i;
-        u32 am = __activemask();
-        u32 cnt = __popc(__ballot_sync(am, inc));
-        if (cnt && (threadIdx.x & 31) == (u32)(__ffs(am) - 1)) atomicAdd((unsigned long long *)&ctr[C_TMP0], (unsigned long long)cnt);
-    });
+    k_sweep_keys<<<cdiv(n_items, 256), 256, 0, st>>>(n_items, include, include_mask, gkey, wide ? 64 : pbits, it_start, ek, ev, ctr + C_TMP0);
+    c->lc.n++;
     int eshift = pbits;
     stage_mark(c, "gs_sort");
     if (!wide) {
@@ -645,7 +639,9 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                 u32 t = svc[u];
                 bool kept = t_keep ? t_keep[t] != 0 : true;
                 skw[u] = kept ? (u64)g2min[t] : ((1ull << ob) | 0); // dropped chains sort last
-                if (kept) atomicAdd((unsigned long long *)&ctr[C_KEPT_CHAINS], 1ull);
+                const u32 am = __activemask();
+                const u32 nk = __popc(__ballot_sync(am, kept));
+                if (nk && (threadIdx.x & 31) == (u32)(__ffs(am) - 1)) atomicAdd((unsigned long long *)&ctr[C_KEPT_CHAINS], (unsigned long long)nk);
             });
         }
         sort_pairs(c, sk, sk2, sv, sv2, C1, ob + 1);
@@ -698,7 +694,9 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                 ik[u] = f ? t_c2key[t] : NONE64;
                 iv[u] = u;
                 u_qs[u] = t_qs[t]; u_qe[u] = t_qe[t]; u_ts[u] = t_ts[t];
-                if (f) atomicAdd((unsigned long long *)&ctr[C_INV], 1ull);
+                const u32 am = __activemask();
+                const u32 nf = __popc(__ballot_sync(am, f));
+                if (nf && (threadIdx.x & 31) == (u32)(__ffs(am) - 1)) atomicAdd((unsigned long long *)&ctr[C_INV], (unsigned long long)nf);
             });
         }
         sort_pairs(c, ik, ik2, iv, iv2, C2, 2 * sb + 1);
