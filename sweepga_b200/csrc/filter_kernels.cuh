@@ -641,6 +641,94 @@ __device__ __forceinline__ bool act_less(const ActEntry &a, const ActEntry &b) {
     return a.item < b.item;
 }
 
+// n_keep == 1 (the 1:1 modes): the same result without walking a group sequentially — ONE THREAD PER ITEM.
+// After the events of a position p the active set is S(p) = { k : start_k <= p < end_k }.  Item m is marked good iff it
+// is the best of S(p) at some event position p in [start_m, end_m), and flagged iff at some such p it is not the best
+// and overlaps the best by more than thr.  Every member of S(p) for such p intersects m's span, so the thread only
+// looks at its neighbours in start order: to the right while start_k < end_m, to the left while an item could still
+// reach start_m (start_k + longest item of the group > start_m).  S(p) changes only at the starts and ends of those
+// neighbours.  Groups where a scan gets long (deep piles, one very long item) go to the warp-per-group kernel, which
+// redoes the whole group and k_sweep_keep_big overwrites the keep bytes of its items.
+constexpr u32 SWF_LEFT = 48, SWF_RIGHT = 48;
+__global__ void __launch_bounds__(256)
+k_sweep_flat1(const u32 *__restrict__ sitem, const SweepItem *__restrict__ sdata, const u32 *__restrict__ gid, const u32 *__restrict__ gstart,
+              const u32 *__restrict__ gmaxlen, u32 n_groups, u32 n_sorted, double thr, u8 *__restrict__ keep, u32 *gflag, u32 *big_list,
+              u32 *big_count, u64 *ctr) {
+    const u32 u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_sorted) return;
+    const u32 g = gid[u];
+    const u32 gs = gstart[g], ge = (g + 1 < n_groups) ? gstart[g + 1] : n_sorted;
+    const u32 item = sitem[u];
+    if (ge - gs <= 1) { keep[item] = 1; return; } // a single interval: kept (plane_sweep_exact.rs:274-276)
+    const SweepItem me = sdata[u];
+    if (me.end <= me.start) return; // zero length: its End follows its Begin at the same position, it is never evaluated (keep stays 0)
+    const u64 lmax = gmaxlen[g];
+    bool big = false;
+    u32 lo = u, hi = u;
+    for (u32 k = u, steps = 0; k > gs;) {
+        k--;
+        const SweepItem a = sdata[k];
+        if ((u64)a.start + lmax <= (u64)me.start) break; // nothing at or left of k reaches start_m
+        if (a.end > me.start) lo = k;
+        if (++steps > SWF_LEFT) { big = true; break; }
+    }
+    u32 near = 0;
+    for (u32 k = u + 1; k < ge && !big; k++) {
+        const SweepItem a = sdata[k];
+        if (a.start >= me.end) break;
+        hi = k;
+        const u64 df = a.skey > me.skey ? a.skey - me.skey : me.skey - a.skey; // near-tie audit, each co-active pair once
+        near += (df != 0 && df <= 2);
+        if (k - u > SWF_RIGHT) big = true;
+    }
+    if (big) {
+        if (atomicExch(&gflag[g], 1u) == 0) big_list[atomicAdd(big_count, 1u)] = g;
+        return;
+    }
+    if (near) atomicAdd((unsigned long long *)&ctr[C_NEAR_TIES], (unsigned long long)near);
+    bool is_good = false, is_flag = false;
+    const bool want_flag = thr < 1.0;
+    auto eval = [&](u32 p) {
+        u64 bkey = me.skey;
+        u32 bstart = me.start, bend = me.end, bpos = u;
+        for (u32 k = lo; k <= hi; k++) {
+            if (k == u) continue;
+            const SweepItem a = sdata[k];
+            if (a.start <= p && p < a.end) {
+                bool less = a.skey < bkey || (a.skey == bkey && a.start < bstart);
+                if (!less && a.skey == bkey && a.start == bstart) less = sitem[k] < sitem[bpos];
+                if (less) { bkey = a.skey; bstart = a.start; bend = a.end; bpos = k; }
+            }
+        }
+        if (bpos == u) is_good = true;
+        else if (want_flag && !is_flag) is_flag = overlaps_more_than(me.start, me.end, bstart, bend, thr);
+    };
+    eval(me.start);
+    for (u32 k = lo; k <= hi; k++) {
+        if (is_good && (is_flag || !want_flag)) break;
+        if (k == u) continue;
+        const SweepItem a = sdata[k];
+        if (k > u && a.start > me.start) eval(a.start);
+        if (a.end > me.start && a.end < me.end) eval(a.end);
+    }
+    if (is_good && !is_flag) keep[item] = 1;
+}
+
+// keep = good && !flagged for the items of the groups the warp kernel redid (n_keep == 1 path)
+__global__ void __launch_bounds__(128) k_sweep_keep_big(const u32 *__restrict__ sitem, const u32 *__restrict__ gstart, u32 n_groups, u32 n_sorted,
+                                                        const u32 *__restrict__ big_list, const u32 *__restrict__ big_count,
+                                                        const u8 *__restrict__ good, const u8 *__restrict__ flagged, u8 *__restrict__ keep) {
+    const u32 n_big = *big_count;
+    for (u32 w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_big; w += (gridDim.x * blockDim.x) >> 5) {
+        const u32 g = big_list[w];
+        const u32 gs = gstart[g], ge = (g + 1 < n_groups) ? gstart[g + 1] : n_sorted;
+        for (u32 k = gs + lane_id(); k < ge; k += 32) {
+            const u32 i = sitem[k];
+            keep[i] = (good[i] && !flagged[i]) ? 1 : 0;
+        }
+    }
+}
+
 // sort keys of the included items: (group << pbits) | start, payload = item (pbits == 64: the start alone, the group id
 // is applied by a second stable sort); one counter atomic per CTA
 __global__ void __launch_bounds__(256) k_sweep_keys(u32 n_items, const u8 *__restrict__ include, u8 include_mask, const u64 *__restrict__ gkey,

@@ -224,17 +224,25 @@ static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 in
     const u32 n_inc = (u32)c->h_ctr[C_TMP0]; // the included items sort first
     if (n_inc == 0) return;
     u32 *gstart = c->arena.take<u32>(n_inc + 1);
+    u32 *gid = c->arena.take<u32>(n_inc);
     u32 *bsum = c->arena.take<u32>(scan_temp_u32(n_inc));
     u32 *d_ng = c->arena.take<u32>(2);
     const u64 *ekc = ek;
     scan_apply([=] __device__(u32 u) -> u32 { return (u == 0 || (ekc[u] >> eshift) != (ekc[u - 1] >> eshift)) ? 1u : 0u; },
-               [=] __device__(u32 u, u32 ex, u32 v) { if (v) gstart[ex] = u; }, n_inc, bsum, d_ng, st, c->lc);
+               [=] __device__(u32 u, u32 ex, u32 v) {
+                   if (v) gstart[ex] = u;
+                   gid[u] = ex + v - 1;
+               },
+               n_inc, bsum, d_ng, st, c->lc);
     u32 n_groups = read_u32(c, d_ng);
     u8 *good = c->arena.take<u8>(n_items), *flagged = c->arena.take<u8>(n_items);
     SWG_CUDA(cudaMemsetAsync(good, 0, n_items, st));
     SWG_CUDA(cudaMemsetAsync(flagged, 0, n_items, st));
     // per-item copies (score key, axis interval) in sorted order: a group becomes one contiguous stream
     SweepItem *sdata = c->arena.take<SweepItem>(n_inc);
+    u32 *gmaxlen = c->arena.take<u32>(n_groups), *gflag = c->arena.take<u32>(n_groups);
+    SWG_CUDA(cudaMemsetAsync(gmaxlen, 0, sizeof(u32) * (size_t)n_groups, st));
+    SWG_CUDA(cudaMemsetAsync(gflag, 0, sizeof(u32) * (size_t)n_groups, st));
     {
         const u32 *evc = ev;
         launch_for<t_sweep_gather>(n_inc, st, c->lc, [=] __device__(u32 u) {
@@ -244,20 +252,34 @@ static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 in
             d.start = it_start[i];
             d.end = it_end[i];
             sdata[u] = d;
+            // longest item of the group (bounds the leftward scan of k_sweep_flat1): one atomic per group present in the warp
+            const u32 len = d.end - d.start, g = gid[u];
+            const u32 peers = __match_any_sync(__activemask(), g);
+            const u32 mx = __reduce_max_sync(peers, len);
+            if ((threadIdx.x & 31) == (u32)(__ffs(peers) - 1) && mx > gmaxlen[g]) atomicMax(&gmaxlen[g], mx);
         });
     }
     u32 *big_list = c->arena.take<u32>(n_groups + 1);
     u32 *sw_ctr = c->arena.take<u32>(4); // [0] thread-kernel group counter, [1] deep groups, [2] warp-kernel work counter
     SWG_CUDA(cudaMemsetAsync(sw_ctr, 0, 4 * sizeof(u32), st));
     stage_mark(c, "gs_sweep");
-    static const int sweep_mult = getenv("SWG_SWEEP_MULT") ? atoi(getenv("SWG_SWEEP_MULT")) : 8;
-    k_sweep_small<<<(u32)c->sm_count * sweep_mult, 128, 0, st>>>(ev, sdata, gstart, n_groups, n_inc, n_keep, thr, good, flagged, big_list, sw_ctr + 1,
-                                                       sw_ctr, ctr);
+    const bool no_flat = getenv("SWG_SWEEP_NO_FLAT") != nullptr; // testing aid (read per call): the sequential kernels for every n
+    if (n_keep == 1 && !no_flat) {
+        k_sweep_flat1<<<cdiv(n_inc, 256), 256, 0, st>>>(ev, sdata, gid, gstart, gmaxlen, n_groups, n_inc, thr, keep, gflag, big_list, sw_ctr + 1,
+                                                       ctr);
+    } else {
+        static const int sweep_mult = getenv("SWG_SWEEP_MULT") ? atoi(getenv("SWG_SWEEP_MULT")) : 8;
+        k_sweep_small<<<(u32)c->sm_count * sweep_mult, 128, 0, st>>>(ev, sdata, gstart, n_groups, n_inc, n_keep, thr, good, flagged, big_list,
+                                                                    sw_ctr + 1, sw_ctr, ctr);
+    }
     // groups whose pile is deeper than the per-thread array: one warp each, active set in global scratch
     ActEntry *act = c->arena.take<ActEntry>(n_inc + 1);
     k_sweep_groups<<<(u32)c->sm_count * 4, 128, 0, st>>>(ev, sdata, gstart, n_groups, n_inc, n_keep, thr, act, good, flagged, big_list,
                                                         sw_ctr + 1, sw_ctr + 2, ctr);
-    {
+    if (n_keep == 1 && !no_flat) {
+        k_sweep_keep_big<<<(u32)c->sm_count, 128, 0, st>>>(ev, gstart, n_groups, n_inc, big_list, sw_ctr + 1, good, flagged, keep);
+        c->lc.n++;
+    } else {
         const u32 *evc = ev;
         launch_for<t_sweep_keep>(n_inc, st, c->lc, [=] __device__(u32 u) {
             const u32 i = evc[u];
@@ -356,7 +378,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     S.n_stage1 = n_alive;
     const int sb = bits_for(in.n_seq);      // ids < n_seq <= 2^sb - 1: the all-ones pattern stays free for dead keys
     const int cb = bits_for(maxcoord);
-    const int pb = sb; // prefix ids are < n_seq
+    const int pb = bits_for(maxP); // genome-prefix ids of the partner: usually far fewer bits than a sequence id, and one sort pass less
 
     stage_mark(c, "primary_sweep");
     // ---- primary plane sweep (paf_filter.rs:972-1123) ----------------------------------------

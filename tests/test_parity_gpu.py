@@ -88,6 +88,15 @@ def test_yeast_configs(ctx, yeast, case):
     check(ctx, swg.FilterConfig.from_cli(**CLI_CASES[case]), yeast, case)
 
 
+@pytest.mark.parametrize("case", ["1:1_1:1", "mass0", "1:1_rescue"])
+def test_sequential_sweep_kernels_for_n1(ctx, yeast, case, monkeypatch):
+    """n = 1 normally runs the thread-per-item sweep (k_sweep_flat1); SWG_SWEEP_NO_FLAT routes it through the sequential
+    thread-per-group / warp-per-group kernels that every other n uses: both must agree with the oracle."""
+    monkeypatch.setenv("SWG_SWEEP_NO_FLAT", "1")
+    check(ctx, swg.FilterConfig.from_cli(**CLI_CASES[case]), yeast, case)
+    check(ctx, swg.FilterConfig.from_cli(**CLI_CASES[case]), synth.pansn(200_000, seed=8, n_hap=10), case)
+
+
 @pytest.mark.parametrize("case", ["defaults", "rescue100k", "1:1_1:1"])
 def test_pansn_400k(ctx, case):
     """configs[2]/[3] generator at a size the oracle finishes in seconds."""
