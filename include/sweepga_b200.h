@@ -233,6 +233,15 @@ int swg_parse_ani_method(const char *s, int *method, double *percentile, int *so
 int swg_ani_stats(swg_ctx *ctx, const char *paf_path, int method, double percentile, int sort, double *ani50,
                   uint64_t *n_pairs);
 
+/* apply_tree_filter_to_paf, src/tree_filter.rs:205-283 (`--sparsify tree:k[,f[,r]]` on an existing PAF): per genome
+ * pair (extract_genome_prefix, :15-25) identity = sum(matches) / sum(block length); every genome keeps its k_nearest
+ * and k_farthest neighbours, plus the pairs whose SipHash-1-3 is below random_fraction * 2^64 (select_tree_pairs,
+ * :84-164); the lines of the selected pairs are written verbatim, in input order.  Tokenising, the per-pair integer
+ * sums and the output assembly run on the GPU; the pair selection (thousands of pairs) on the host.  Ties in identity
+ * go by neighbour name (the reference leaves them to HashMap iteration order). */
+int swg_tree_filter_paf(swg_ctx *ctx, const char *in_path, const char *out_path, uint64_t k_nearest, uint64_t k_farthest,
+                        double random_fraction, uint64_t *n_kept, uint64_t *n_pairs_selected);
+
 /* src/pansn.rs:176-191, 207-225; has_avg = 0 => avg_seq_len None */
 uint64_t swg_round_nice(uint64_t v);
 void swg_clamp_scaffold_params(uint64_t user_jump, uint64_t user_mass, int has_avg, uint64_t avg_seq_len,

@@ -787,6 +787,113 @@ int orc_filter_paf(const swg_config *cfg, const char *in_path, const char *out_p
     return rc;
 }
 
+// SipHash-1-3 with a zero key over g1 || 0xFF || g2 || 0xFF: std's DefaultHasher::new() fed `str::hash` twice
+// (tree_filter.rs:147-151).  Restated from the SipHash specification; checked against CPython's siphash13 in tests/.
+uint64_t orc_siphash13(const uint8_t *msg, uint64_t len) {
+    auto rotl = [](uint64_t x, int b) { return (x << b) | (x >> (64 - b)); };
+    uint64_t v0 = 0x736f6d6570736575ull, v1 = 0x646f72616e646f6dull, v2 = 0x6c7967656e657261ull, v3 = 0x7465646279746573ull; // k0 = k1 = 0
+    auto round = [&]() {
+        v0 += v1; v1 = rotl(v1, 13); v1 ^= v0; v0 = rotl(v0, 32);
+        v2 += v3; v3 = rotl(v3, 16); v3 ^= v2;
+        v0 += v3; v3 = rotl(v3, 21); v3 ^= v0;
+        v2 += v1; v1 = rotl(v1, 17); v1 ^= v2; v2 = rotl(v2, 32);
+    };
+    uint64_t i = 0;
+    for (; i + 8 <= len; i += 8) {
+        uint64_t m = 0;
+        for (int k = 0; k < 8; k++) m |= (uint64_t)msg[i + k] << (8 * k);
+        v3 ^= m; round(); v0 ^= m;
+    }
+    uint64_t b = len << 56;
+    for (int k = 0; i + k < len; k++) b |= (uint64_t)msg[i + k] << (8 * k);
+    v3 ^= b; round(); v0 ^= b;
+    v2 ^= 0xff;
+    round(); round(); round();
+    return v0 ^ v1 ^ v2 ^ v3;
+}
+
+// apply_tree_filter_to_paf, src/tree_filter.rs:205-283 (build_identity_matrix :39-80, select_tree_pairs :84-164,
+// filter_tree_based :168-201).  The reference orders a genome's neighbours with a stable sort over HashMap iteration
+// order, so ties in identity are broken arbitrarily there; here (and in the product) ties go by neighbour name.
+// PARITY UNPINNED: the reference only tests extract_genome_prefix (tree_filter.rs:446-452).
+int orc_tree_filter_paf(const char *in_path, const char *out_path, uint64_t k_nearest, uint64_t k_farthest, double random_fraction,
+                        uint64_t *n_kept, uint64_t *n_selected) {
+    using namespace orc;
+    std::ifstream in(in_path, std::ios::binary);
+    if (!in) return -1;
+    struct Aln { std::string qg, tg; uint64_t m, b; };
+    std::vector<Aln> alns;
+    std::vector<std::string> lines;
+    std::string line;
+    while (std::getline(in, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (line.empty() || line[0] == '#') continue; // :221-223
+        std::vector<std::string> f;
+        size_t s = 0;
+        while (true) {
+            size_t t = line.find('\t', s);
+            if (t == std::string::npos) { f.push_back(line.substr(s)); break; }
+            f.push_back(line.substr(s, t - s));
+            s = t + 1;
+        }
+        if (f.size() < 11) continue;
+        uint64_t m = 0, b = 1;
+        if (!rust_parse_u64(f[9], m)) m = 0;
+        if (!rust_parse_u64(f[10], b)) b = 1;
+        alns.push_back(Aln{prefix_P2(f[0]), prefix_P2(f[5]), m, b}); // extract_genome_prefix :15-25 == the P2 rule
+        lines.push_back(line);
+    }
+    std::map<std::pair<std::string, std::string>, std::pair<double, double>> sums; // :39-80
+    for (const auto &a : alns) {
+        if (a.qg == a.tg) continue;
+        auto key = a.qg < a.tg ? std::make_pair(a.qg, a.tg) : std::make_pair(a.tg, a.qg);
+        auto &e = sums[key];
+        e.first += (double)a.m;
+        e.second += (double)a.b;
+    }
+    std::map<std::pair<std::string, std::string>, double> ident;
+    std::map<std::string, std::vector<std::pair<std::string, double>>> nb;
+    for (const auto &kv : sums) {
+        const double id = kv.second.second > 0.0 ? kv.second.first / kv.second.second : 0.0;
+        ident[kv.first] = id;
+        nb[kv.first.first].push_back({kv.first.second, id});
+        nb[kv.first.second].push_back({kv.first.first, id});
+    }
+    std::set<std::pair<std::string, std::string>> selected; // :84-164
+    for (auto &g : nb) {
+        auto &v = g.second;
+        for (auto &x : v) if (x.second != x.second) return -2; // partial_cmp().unwrap() panics on NaN
+        std::sort(v.begin(), v.end(), [](const auto &x, const auto &y) { return x.second != y.second ? x.second > y.second : x.first < y.first; });
+        auto add = [&](const std::string &o) { selected.insert(g.first < o ? std::make_pair(g.first, o) : std::make_pair(o, g.first)); };
+        for (size_t k = 0; k < v.size() && k < k_nearest; k++) add(v[k].first);
+        for (size_t k = 0; k < v.size() && k < k_farthest; k++) add(v[v.size() - 1 - k].first);
+    }
+    if (random_fraction > 0.0) {
+        const double t = random_fraction * 18446744073709551615.0;
+        const uint64_t thr = t >= 18446744073709551615.0 ? ~(uint64_t)0 : (t > 0.0 ? (uint64_t)t : 0); // `as u64` saturates
+        for (const auto &kv : ident) {
+            std::string msg = kv.first.first + "\xff" + kv.first.second + "\xff";
+            if (orc_siphash13((const uint8_t *)msg.data(), msg.size()) <= thr) selected.insert(kv.first);
+        }
+    }
+    FILE *out = fopen(out_path, "wb");
+    if (!out) return -1;
+    uint64_t kept = 0;
+    for (size_t i = 0; i < alns.size(); i++) { // :168-201
+        const auto &a = alns[i];
+        if (a.qg == a.tg) continue;
+        auto key = a.qg < a.tg ? std::make_pair(a.qg, a.tg) : std::make_pair(a.tg, a.qg);
+        if (!selected.count(key)) continue;
+        fwrite(lines[i].data(), 1, lines[i].size(), out);
+        fputc('\n', out);
+        kept++;
+    }
+    fclose(out);
+    if (n_kept) *n_kept = kept;
+    if (n_selected) *n_selected = selected.size();
+    return 0;
+}
+
 // calculate_ani_stats + calculate_ani_n_percentile, src/main.rs:334-688.
 // method 0 = All, 1 = Orthogonal (1:1 filter first, :346-383), 2 = NPercentile(percentile, sort); sort 0 = length,
 // 1 = identity, 2 = score.  Returns 0 and *ani50; -1: I/O; -2: the reference would panic (NaN in partial_cmp).

@@ -9,6 +9,6 @@ from .api import (ChainStatus, Context, FilterConfig, FilterMode, MappingTable, 
                   apply_paf_filter, clamp_scaffold_params, filter_config_from_align_cfg, filter_file, parse_filter_mode,
                   parse_filter_mode_cli, parse_identity_value, parse_metric_number, parse_paf, parse_scoring, prefix_P,
                   prefix_P2, prefix_ids, round_nice, shard_plan, ani_stats, parse_ani_method, ANI_ALL, ANI_ORTHOGONAL,
-                  ANI_NPERCENTILE, NSORT_LENGTH, NSORT_IDENTITY, NSORT_SCORE)
+                  ANI_NPERCENTILE, NSORT_LENGTH, NSORT_IDENTITY, NSORT_SCORE, apply_tree_filter_to_paf)
 
 __version__ = lib.swg_version().decode()

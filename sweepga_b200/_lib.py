@@ -93,6 +93,7 @@ SYMBOLS = [
     ("swg_paf_write", C.c_int, [_vp, C.c_char_p, u8p, u32p]),
     ("swg_parse_ani_method", C.c_int, [C.c_char_p, C.POINTER(C.c_int), f64p, C.POINTER(C.c_int)]),
     ("swg_ani_stats", C.c_int, [_vp, C.c_char_p, C.c_int, C.c_double, C.c_int, f64p, u64p]),
+    ("swg_tree_filter_paf", C.c_int, [_vp, C.c_char_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_double, u64p, u64p]),
     ("swg_paf_parse_device", _vp, [_vp, C.c_char_p]),
     ("swg_filter_paf", C.c_int, [_vp, _cfgp, C.c_char_p, C.c_char_p, _statp]),
     ("swg_filter_paf_host", C.c_int, [_vp, _cfgp, C.c_char_p, C.c_char_p, _statp]),

@@ -105,6 +105,15 @@ def ani_stats(ctx: "Context", paf_path: str, method="n100"):
     return ani.value, int(npairs.value)
 
 
+def apply_tree_filter_to_paf(ctx: "Context", input_path: str, output_path: str, k_nearest: int, k_farthest: int = 0,
+                             random_fraction: float = 0.0):
+    """apply_tree_filter_to_paf (src/tree_filter.rs:205-283) on the GPU -> (lines kept, genome pairs selected)."""
+    kept, sel = C.c_uint64(), C.c_uint64()
+    ctx._check(lib.swg_tree_filter_paf(ctx._h, os.fsencode(input_path), os.fsencode(output_path), int(k_nearest), int(k_farthest),
+                                       float(random_fraction), C.byref(kept), C.byref(sel)))
+    return int(kept.value), int(sel.value)
+
+
 def round_nice(v: int) -> int:
     return lib.swg_round_nice(v)
 

@@ -22,7 +22,7 @@ struct t_ani_pairs; struct t_ani_first; struct t_ani_sizes; struct t_ani_keys; s
 struct t_ani_tiles; struct t_ani_sortkeys;
 
 enum : u8 { AK_SKIP = 0, AK_OK = 1, AK_FIX = 2 };
-enum { AC_OK = 0, AC_NFIX, AC_NAN, AC_NONINT, AC_INTER, AC_COUNT };
+enum { AC_OK = 0, AC_NFIX, AC_NAN, AC_NONINT, AC_INTER, AC_MAXLEN, AC_COUNT };
 
 struct AniCols { // per line, then per record
     TokCols names;  // off, qh, th, qlen, trel, tlen are used
@@ -32,7 +32,10 @@ struct AniCols { // per line, then per record
 };
 struct AniPatch { u32 line; u32 kind; double m, b; u64 ql, tl; };
 
-// One thread per line (main.rs:412-460 / :538-604).
+// One thread per line.  MODE 0: the ANI reader (main.rs:412-460 / :538-604): columns 2 / 7 as u64 into ql / tl, columns
+// 10 / 11 as f64, the first dv:f: tag that parses.  MODE 1: the tree-filter reader (tree_filter.rs:219-245): columns
+// 10 / 11 as u64 (unwrap_or 0 / 1) into ql / tl, no tags; the line length is kept for the output.
+template <int MODE>
 __global__ void __launch_bounds__(256) k_ani_parse(const char *__restrict__ text, const u64 *__restrict__ line_start, u32 n_lines, AniCols L,
                                                    u32 *__restrict__ fix_list, u64 *__restrict__ ac) {
     const u32 l = blockIdx.x * blockDim.x + threadIdx.x;
@@ -63,7 +66,7 @@ __global__ void __launch_bounds__(256) k_ani_parse(const char *__restrict__ text
                     hh = name_hash_finish(hh, e - a);
                     if (nf == 0) { qh = hh; qlen = e - a; }
                     else { th = hh; trel = a; tlen = e - a; }
-                } else if (nf == 1 || nf == 6) { // parse::<u64>().unwrap_or(0)
+                } else if (MODE == 0 ? (nf == 1 || nf == 6) : (nf == 9 || nf == 10)) { // parse::<u64>().unwrap_or(0 | 1)
                     u64 v = 0;
                     u32 nd = 0;
                     bool bad = false;
@@ -77,12 +80,12 @@ __global__ void __launch_bounds__(256) k_ani_parse(const char *__restrict__ text
                         }
                         e++;
                     }
-                    if (bad || nd == 0) v = 0;
+                    if (bad || nd == 0) v = (MODE == 1 && nf == 10) ? 1 : 0;
                     else if (nd > 19) fix = true;
-                    if (nf == 1) ql = v; else tl = v;
+                    if (nf == 1 || nf == 9) ql = v; else tl = v;
                 } else {
                     while (e < len && line[e] != '\t') e++;
-                    if (nf == 9 || nf == 10) { // parse::<f64>().unwrap_or(0.0 / 1.0)
+                    if (MODE == 0 && (nf == 9 || nf == 10)) { // parse::<f64>().unwrap_or(0.0 / 1.0)
                         double v;
                         const int rc = tok_parse_f64(line + a, e - a, v);
                         if (rc == 2) fix = true;
@@ -98,7 +101,8 @@ __global__ void __launch_bounds__(256) k_ani_parse(const char *__restrict__ text
             }
             if (enough) {
                 double fm = m;
-                while (a <= len && !fix) { // the first dv:f: tag that parses
+                if (MODE == 1) L.names.len[l] = len;
+                while (MODE == 0 && a <= len && !fix) { // the first dv:f: tag that parses
                     u32 e = a;
                     while (e < len && line[e] != '\t') e++;
                     if (e - a >= 5 && line[a] == 'd' && line[a + 1] == 'v' && line[a + 2] == ':' && line[a + 3] == 'f' && line[a + 4] == ':') {
@@ -113,7 +117,8 @@ __global__ void __launch_bounds__(256) k_ani_parse(const char *__restrict__ text
                 L.names.off[l] = s;
                 L.names.qh[l] = qh; L.names.th[l] = th;
                 L.names.qlen[l] = qlen; L.names.trel[l] = trel; L.names.tlen[l] = tlen;
-                L.m[l] = fm; L.b[l] = b; L.ql[l] = ql; L.tl[l] = tl;
+                if (MODE == 0) { L.m[l] = fm; L.b[l] = b; }
+                L.ql[l] = ql; L.tl[l] = tl;
                 if (fix) {
                     kind = AK_FIX;
                     fix_list[atomicAdd((unsigned long long *)&ac[AC_NFIX], 1ull)] = l;
@@ -125,6 +130,12 @@ __global__ void __launch_bounds__(256) k_ani_parse(const char *__restrict__ text
     }
     const u32 nok = __syncthreads_count(ok);
     if (threadIdx.x == 0 && nok) atomicAdd((unsigned long long *)&ac[AC_OK], (unsigned long long)nok);
+    if (MODE == 1) { // the longest line sizes the output window of write_device
+        u32 mylen = 0;
+        if (l < n_lines) mylen = (u32)(line_start[l + 1] - 1 - line_start[l]);
+        const u32 mx = __reduce_max_sync(0xFFFFFFFFu, mylen);
+        if (lane_id() == 0 && mx > (u32)ac[AC_MAXLEN]) atomicMax((unsigned long long *)&ac[AC_MAXLEN], (unsigned long long)mx);
+    }
 }
 
 // one thread per genome pair: the pair's addends are contiguous and in the reference's order
@@ -181,7 +192,7 @@ static AniResult ani_device(swg_ctx *c, const swg_paf &hp, int method, double pe
     };
     SWG_CUDA(cudaMemsetAsync(ac, 0, sizeof(u64) * AC_COUNT, st));
     SWG_CUDA(cudaMemsetAsync(tc, 0, sizeof(u64) * TC_COUNT, st));
-    k_ani_parse<<<cdiv(n_lines, 256), 256, 0, st>>>(text, dl.line_start, n_lines, L, fix_list, ac);
+    k_ani_parse<0><<<cdiv(n_lines, 256), 256, 0, st>>>(text, dl.line_start, n_lines, L, fix_list, ac);
     lc.n++;
     read_ac();
     u64 n_ok = h_ac[AC_OK];
@@ -417,6 +428,216 @@ static AniResult ani_device(swg_ctx *c, const swg_paf &hp, int method, double pe
     const size_t mid = h_ani.size() / 2;
     res.ani50 = (h_ani.size() % 2 == 0 && h_ani.size() > 1) ? (h_ani[mid - 1] + h_ani[mid]) / 2.0 : h_ani[mid]; // main.rs:490-495
     res.n_pairs = n_pairs;
+    return res;
+}
+
+// ---- tree sparsification of an existing PAF (`--sparsify tree:k[,f[,r]]`) --------------------------------------
+//   tree_filter_device  <- apply_tree_filter_to_paf   (src/tree_filter.rs:205-283)
+// Per genome pair (the P2 prefix rule) Σ matches / Σ block length over u64 columns — integers, so the sums are
+// order-free: sort by pair, warp-segmented reduction, one atomic per (warp, pair).  The pair list (thousands) goes
+// to the host, select_tree_pairs picks the k nearest / k farthest / hashed-random pairs, the flags come back, and
+// the kept lines are assembled on the device in input order (write_device, verbatim lines).
+struct t_tree_keys; struct t_tree_sums; struct t_tree_status; struct t_tree_pairout;
+struct TreeResult { u64 n_kept = 0, n_selected = 0; };
+
+static TreeResult tree_filter_device(swg_ctx *c, const swg_paf &hp, const char *out_path, u64 k_nearest, u64 k_farthest, double random_fraction) {
+    cudaStream_t st = c->stream;
+    LaunchCounter &lc = c->lc;
+    Arena &A = c->io;
+    TreeResult res;
+    const DevLines dl = load_lines(c, hp);
+    DevPaf dp;
+    dp.text = dl.text;
+    dp.text_len = hp.text_len;
+    if (hp.text_len == 0) { write_device(c, dp, nullptr, nullptr, out_path); return res; }
+    const char *text = dl.text;
+    const u32 n_lines = dl.n_lines;
+    u32 *bsum = dl.bsum, *d_cnt = dl.d_cnt;
+    auto take_cols = [&](u32 n) {
+        AniCols L;
+        memset(&L, 0, sizeof L);
+        L.names.off = A.take<u64>(n); L.names.len = A.take<u32>(n);
+        L.names.qh = A.take<u64>(n); L.names.th = A.take<u64>(n);
+        L.names.qlen = A.take<u32>(n); L.names.trel = A.take<u32>(n); L.names.tlen = A.take<u32>(n);
+        L.ql = A.take<u64>(n); L.tl = A.take<u64>(n); // matches, block length
+        L.kind = A.take<u8>(n);
+        return L;
+    };
+    AniCols L = take_cols(n_lines);
+    u32 *fix_list = A.take<u32>(n_lines);
+    u64 *ac = A.take<u64>(AC_COUNT);
+    u64 *tc = A.take<u64>(TC_COUNT);
+    u64 h_ac[AC_COUNT];
+    auto read_ac = [&]() {
+        SWG_CUDA(cudaMemcpyAsync(h_ac, ac, sizeof(u64) * AC_COUNT, cudaMemcpyDeviceToHost, st));
+        SWG_CUDA(cudaStreamSynchronize(st));
+    };
+    SWG_CUDA(cudaMemsetAsync(ac, 0, sizeof(u64) * AC_COUNT, st));
+    SWG_CUDA(cudaMemsetAsync(tc, 0, sizeof(u64) * TC_COUNT, st));
+    k_ani_parse<1><<<cdiv(n_lines, 256), 256, 0, st>>>(text, dl.line_start, n_lines, L, fix_list, ac);
+    lc.n++;
+    read_ac();
+    u64 n_ok = h_ac[AC_OK];
+    if (h_ac[AC_MAXLEN] > ((u64)256 << 20)) throw FrontEndFallback{"a line longer than 256 MiB"};
+    c->tok_maxlen = (u32)h_ac[AC_MAXLEN];
+    if (h_ac[AC_NFIX]) { // integer columns with more than 19 digits: the host's line reader decides
+        const u32 nfix = (u32)h_ac[AC_NFIX];
+        std::vector<u32> lines(nfix);
+        u64 *d_off = A.take<u64>(2 * (size_t)nfix);
+        const u64 *ls = dl.line_start;
+        launch_for<t_ani_fixgather>(nfix, st, lc, [=] __device__(u32 i) { const u32 l = fix_list[i]; d_off[2 * i] = ls[l]; d_off[2 * i + 1] = ls[l + 1] - 1; });
+        std::vector<u64> se(2 * (size_t)nfix);
+        SWG_CUDA(cudaMemcpyAsync(lines.data(), fix_list, nfix * 4, cudaMemcpyDeviceToHost, st));
+        SWG_CUDA(cudaMemcpyAsync(se.data(), d_off, nfix * 16, cudaMemcpyDeviceToHost, st));
+        SWG_CUDA(cudaStreamSynchronize(st));
+        std::vector<AniPatch> patches(nfix);
+        for (u32 i = 0; i < nfix; i++) {
+            size_t len = (size_t)(se[2 * i + 1] - se[2 * i]);
+            const char *line = hp.text + se[2 * i];
+            if (len > 0 && line[len - 1] == '\r') len--;
+            AniLine al;
+            u64 m = 0, b = 1;
+            const bool ok = paf_tree_line(line, len, &al, &m, &b);
+            patches[i] = AniPatch{lines[i], ok ? (u32)AK_OK : (u32)AK_SKIP, 0.0, 0.0, m, b};
+            if (ok) n_ok++;
+        }
+        AniPatch *d_p = A.take<AniPatch>(nfix);
+        SWG_CUDA(cudaMemcpyAsync(d_p, patches.data(), sizeof(AniPatch) * nfix, cudaMemcpyHostToDevice, st));
+        launch_for<t_ani_patch>(nfix, st, lc, [=] __device__(u32 i) {
+            const AniPatch p = d_p[i];
+            L.kind[p.line] = (u8)p.kind;
+            L.ql[p.line] = p.ql; L.tl[p.line] = p.tl;
+        });
+        SWG_CUDA(cudaStreamSynchronize(st));
+    }
+    const u32 n = (u32)n_ok;
+    if (n == 0) { write_device(c, dp, nullptr, nullptr, out_path); return res; }
+    AniCols R = L;
+    if (n != n_lines) {
+        R = take_cols(n);
+        const AniCols Rc = R;
+        scan_apply([=] __device__(u32 l) -> u32 { return L.kind[l] == AK_OK ? 1u : 0u; },
+                   [=] __device__(u32 l, u32 r, u32 v) {
+                       if (!v) return;
+                       Rc.names.off[r] = L.names.off[l]; Rc.names.len[r] = L.names.len[l];
+                       Rc.names.qh[r] = L.names.qh[l]; Rc.names.th[r] = L.names.th[l];
+                       Rc.names.qlen[r] = L.names.qlen[l]; Rc.names.trel[r] = L.names.trel[l]; Rc.names.tlen[r] = L.names.tlen[l];
+                       Rc.ql[r] = L.ql[l]; Rc.tl[r] = L.tl[l];
+                       Rc.kind[r] = AK_OK;
+                   },
+                   n_lines, bsum, d_cnt, st, lc);
+    }
+    NameTable nt = intern_names(c, text, hp.text, R.names, n, tc, d_cnt);
+    const u32 n_seq = nt.n_seq;
+    // genome of every sequence under extract_genome_prefix (tree_filter.rs:15-25, the P2 rule), as its rank among the
+    // sorted distinct genomes
+    std::vector<u32> seq_rank(n_seq);
+    std::vector<std::string> genomes;
+    {
+        std::vector<std::string> pre(n_seq);
+        for (u32 s = 0; s < n_seq; s++) pre[s] = paf_prefix_P2(nt.names[s]);
+        genomes = pre;
+        std::sort(genomes.begin(), genomes.end());
+        genomes.erase(std::unique(genomes.begin(), genomes.end()), genomes.end());
+        for (u32 s = 0; s < n_seq; s++) seq_rank[s] = (u32)(std::lower_bound(genomes.begin(), genomes.end(), pre[s]) - genomes.begin());
+    }
+    const u64 nG = genomes.size();
+    u32 *d_rank = A.take<u32>(n_seq);
+    SWG_CUDA(cudaMemcpyAsync(d_rank, seq_rank.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, st));
+    const int pbits = bits_for(nG * nG) + 1;
+    if (pbits > 63) throw RangeError{"too many genomes for the pair key"};
+    const u64 dead = (1ull << pbits) - 1;
+    u64 *pk = A.take<u64>(n), *pk2 = A.take<u64>(n);
+    u32 *pv = A.take<u32>(n), *pv2 = A.take<u32>(n);
+    const u32 *qid = nt.qid, *tid = nt.tid;
+    SWG_CUDA(cudaMemsetAsync(ac, 0, sizeof(u64) * AC_COUNT, st));
+    {
+        u64 *k = pk;
+        u32 *v = pv;
+        launch_for<t_tree_keys>(n, st, lc, [=] __device__(u32 r) {
+            const u32 a = d_rank[qid[r]], b = d_rank[tid[r]];
+            const bool inter = a != b; // tree_filter.rs:46-48
+            k[r] = inter ? (u64)min(a, b) * nG + max(a, b) : dead;
+            v[r] = r;
+            const u32 am = __activemask();
+            const u32 cnt = __popc(__ballot_sync(am, inter));
+            if (cnt && (threadIdx.x & 31) == (u32)(__ffs(am) - 1)) atomicAdd((unsigned long long *)&ac[AC_INTER], (unsigned long long)cnt);
+        });
+    }
+    sort_pairs(c, pk, pk2, pv, pv2, n, pbits);
+    read_ac();
+    const u32 n_inter = (u32)h_ac[AC_INTER];
+    u8 *status = A.take<u8>(n);
+    u32 *chain = A.take<u32>(n);
+    SWG_CUDA(cudaMemsetAsync(status, 0, n, st));
+    SWG_CUDA(cudaMemsetAsync(chain, 0, sizeof(u32) * (size_t)n, st));
+    dp.n = n;
+    dp.rec = R.names;
+    if (n_inter == 0) { write_device(c, dp, status, chain, out_path); return res; }
+    u32 *gid = A.take<u32>(n_inter), *seg_start = A.take<u32>(n_inter);
+    {
+        const u64 *pkc = pk;
+        scan_apply([=] __device__(u32 k) -> u32 { return (k == 0 || pkc[k] != pkc[k - 1]) ? 1u : 0u; },
+                   [=] __device__(u32 k, u32 ex, u32 v) {
+                       if (v) seg_start[ex] = k;
+                       gid[k] = ex + v - 1;
+                   },
+                   n_inter, bsum, d_cnt, st, lc);
+    }
+    const u32 n_pairs = read_u32(c, d_cnt);
+    u64 *sums = A.take<u64>(2 * (size_t)n_pairs), *pkeys = A.take<u64>(n_pairs);
+    SWG_CUDA(cudaMemsetAsync(sums, 0, sizeof(u64) * 2 * (size_t)n_pairs, st));
+    {
+        const u32 *pvc = pv;
+        const u64 *pkc = pk;
+        launch_for<t_tree_sums>(n_inter, st, lc, [=] __device__(u32 k) {
+            const u32 r = pvc[k], p = gid[k];
+            u64 m = R.ql[r], b = R.tl[r];
+            // runs of one pair are contiguous: segmented reduction towards the first lane of each run
+            const u32 am = __activemask();
+            const u32 run = __match_any_sync(am, p);
+            const u32 lane = threadIdx.x & 31;
+            for (u32 off = 1; off < 32; off <<= 1) {
+                const u64 tm = __shfl_down_sync(am, m, off), tb = __shfl_down_sync(am, b, off);
+                if (lane + off < 32 && ((run >> (lane + off)) & 1u)) { m += tm; b += tb; }
+            }
+            if (lane == (u32)(__ffs(run) - 1)) {
+                atomicAdd((unsigned long long *)&sums[2 * (size_t)p], (unsigned long long)m);
+                atomicAdd((unsigned long long *)&sums[2 * (size_t)p + 1], (unsigned long long)b);
+            }
+        });
+        launch_for<t_tree_pairout>(n_pairs, st, lc, [=] __device__(u32 p) { pkeys[p] = pkc[seg_start[p]]; });
+    }
+    std::vector<u64> h_sums(2 * (size_t)n_pairs), h_keys(n_pairs);
+    SWG_CUDA(cudaMemcpyAsync(h_sums.data(), sums, sizeof(u64) * 2 * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+    SWG_CUDA(cudaMemcpyAsync(h_keys.data(), pkeys, sizeof(u64) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+    SWG_CUDA(cudaStreamSynchronize(st));
+    std::vector<u32> lo(n_pairs), hi(n_pairs);
+    std::vector<double> ident(n_pairs);
+    for (u32 p = 0; p < n_pairs; p++) {
+        lo[p] = (u32)(h_keys[p] / nG);
+        hi[p] = (u32)(h_keys[p] % nG);
+        const double tm = (double)h_sums[2 * (size_t)p], tb = (double)h_sums[2 * (size_t)p + 1]; // tree_filter.rs:58-59: f64 sums of integers, exact below 2^53
+        ident[p] = tb > 0.0 ? tm / tb : 0.0;
+    }
+    bool has_nan = false;
+    std::vector<uint8_t> sel = tree_select_pairs(genomes, lo, hi, ident, k_nearest, k_farthest, random_fraction, &has_nan);
+    if (has_nan) throw NanError{};
+    u8 *d_sel = A.take<u8>(n_pairs);
+    SWG_CUDA(cudaMemcpyAsync(d_sel, sel.data(), n_pairs, cudaMemcpyHostToDevice, st));
+    {
+        const u32 *pvc = pv;
+        launch_for<t_tree_status>(n_inter, st, lc, [=] __device__(u32 k) { status[pvc[k]] = d_sel[gid[k]] ? OUT_PLAIN : 0; });
+    }
+    SWG_CUDA(cudaStreamSynchronize(st)); // sel lives on this stack frame
+    for (u32 p = 0; p < n_pairs; p++) res.n_selected += sel[p];
+    write_device(c, dp, status, chain, out_path);
+    // kept lines: the records of the selected pairs
+    {
+        u32 *d_kept = d_cnt + 1;
+        scan_apply([=] __device__(u32 r) -> u32 { return status[r] == OUT_PLAIN ? 1u : 0u; }, [] __device__(u32, u32, u32) {}, n, bsum, d_kept, st, lc);
+        res.n_kept = read_u32(c, d_kept);
+    }
     return res;
 }
 

@@ -1446,4 +1446,32 @@ int swg_ani_stats(swg_ctx *c, const char *paf_path, int method, double percentil
     return SWG_OK;
 }
 
+// apply_tree_filter_to_paf (src/tree_filter.rs:205-283): tokenising, per-pair sums and the output on the GPU.
+int swg_tree_filter_paf(swg_ctx *c, const char *in_path, const char *out_path, uint64_t k_nearest, uint64_t k_farthest,
+                        double random_fraction, uint64_t *n_kept, uint64_t *n_pairs_selected) {
+    if (!c || !in_path || !out_path) return SWG_ERR_ARG;
+    swg_paf hp;
+    {
+        std::string err;
+        if (!paf_open_text(in_path, &hp, &err)) {
+            set_err(c, "swg_tree_filter_paf: " + err);
+            return access(in_path, R_OK) == 0 ? SWG_ERR_RANGE : SWG_ERR_IO;
+        }
+    }
+    struct Args { swg_ctx *c; const swg_paf *hp; const char *out; u64 kn, kf; double rf; TreeResult res; bool fallback, nan; } a{c, &hp, out_path, k_nearest, k_farthest, random_fraction, {}, false, false};
+    const int rc = guarded(c, "swg_tree_filter_paf", [](void *q) {
+        Args *a = (Args *)q;
+        SWG_CUDA(cudaSetDevice(a->c->device));
+        try { a->res = tree_filter_device(a->c, *a->hp, a->out, a->kn, a->kf, a->rf); }
+        catch (const FrontEndFallback &) { a->fallback = true; }
+        catch (const NanError &) { a->nan = true; }
+    }, &a);
+    if (rc != SWG_OK) return rc;
+    if (a.nan) { set_err(c, "swg_tree_filter_paf: NaN identity (the reference panics here)"); return SWG_ERR_RANGE; }
+    if (a.fallback) { set_err(c, "swg_tree_filter_paf: input not supported by the device front end (> 64 GiB, or a sequence-name hash collision)"); return SWG_ERR_UNSUPPORTED; }
+    if (n_kept) *n_kept = a.res.n_kept;
+    if (n_pairs_selected) *n_pairs_selected = a.res.n_selected;
+    return SWG_OK;
+}
+
 } // extern "C"

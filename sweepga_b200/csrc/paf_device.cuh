@@ -451,7 +451,9 @@ __device__ __forceinline__ u32 dec_digits(u32 v) {
     return v < 10 ? 1 : v < 100 ? 2 : v < 1000 ? 3 : v < 10000 ? 4 : v < 100000 ? 5 : v < 1000000 ? 6 : v < 10000000 ? 7 : v < 100000000 ? 8
            : v < 1000000000 ? 9 : 10;
 }
+constexpr u8 OUT_PLAIN = 4; // status value of write_device: the line as it is (tree filter), no tags
 __device__ __forceinline__ u32 out_suffix_len(u8 s, u32 chain) {
+    if (s == OUT_PLAIN) return 1;
     const u32 stl = s == 1 ? 8 : s == 2 ? 7 : 10; // scaffold / rescued / unassigned
     return (chain ? 12 + dec_digits(chain) : 0) + 6 + stl + 1;
 }
@@ -470,6 +472,10 @@ __global__ void __launch_bounds__(256) k_out_copy(const char *__restrict__ text,
     for (u32 j = lane; j < n; j += 32) dst[j] = src[j];
     dst += n;
     const u8 s = status[r];
+    if (s == OUT_PLAIN) {
+        if (lane == 0) dst[0] = '\n';
+        return;
+    }
     const u32 chain = chain_id[r];
     const u32 nd = chain ? dec_digits(chain) : 0, pre = chain ? 12 + nd : 0;
     const u32 stl = s == 1 ? 8 : s == 2 ? 7 : 10;
@@ -923,7 +929,7 @@ static void write_device(swg_ctx *c, const DevPaf &dp, const u8 *status, const u
         if (nrec == 0) continue;
         scan_apply([=] __device__(u32 w) -> u32 {
                        const u8 s = status[r0 + w];
-                       return (s == 0 || s > 3) ? 0u : len[r0 + w] + out_suffix_len(s, chain_id[r0 + w]);
+                       return (s == 0 || s > OUT_PLAIN) ? 0u : len[r0 + w] + out_suffix_len(s, chain_id[r0 + w]);
                    },
                    [=] __device__(u32 w, u32 ex, u32 v) { out_off[w] = v ? ex : NONE32; }, nrec, bsum, d_tot, st, lc);
         k_out_copy<<<cdiv((u64)nrec * 32, 256), 256, 0, st>>>(dp.text, dp.rec.off, len, status, chain_id, r0, nrec, out_off, out);

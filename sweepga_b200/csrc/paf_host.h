@@ -57,6 +57,20 @@ struct AniLine {
 };
 bool paf_ani_line(const char *line, size_t len, AniLine *out);
 
+// One PAF line the way apply_tree_filter_to_paf reads it (src/tree_filter.rs:219-245): u64 matches / block length
+// with unwrap_or(0 / 1).  false: skipped ('#', empty, < 11 fields).  Names come back in `out`.
+bool paf_tree_line(const char *line, size_t len, AniLine *out, uint64_t *matches, uint64_t *block);
+
+// SipHash-1-3 with a zero key — std's DefaultHasher::new(), which select_tree_pairs uses for its pseudo-random pairs.
+uint64_t siphash13_zero_key(const uint8_t *msg, size_t len);
+
+// select_tree_pairs (src/tree_filter.rs:84-164) over pairs (lo[i], hi[i]) of indices into `genomes`: every genome keeps
+// its k nearest and k farthest neighbours by identity, plus the pairs whose hash is below random_fraction * 2^64.
+// Ties in identity go by neighbour name (the reference leaves them to HashMap order).  *has_nan: the reference panics.
+std::vector<uint8_t> tree_select_pairs(const std::vector<std::string> &genomes, const std::vector<uint32_t> &lo,
+                                       const std::vector<uint32_t> &hi, const std::vector<double> &identity, uint64_t k_nearest,
+                                       uint64_t k_farthest, double random_fraction, bool *has_nan);
+
 // Opens `path` (plain, .gz or .bgz) and fills text / text_len (mmap when possible); false + message on failure.
 bool paf_open_text(const char *path, swg_paf *p, std::string *err);
 

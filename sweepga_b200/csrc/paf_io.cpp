@@ -173,6 +173,90 @@ bool swg::paf_ani_line(const char *line, size_t len, AniLine *out) {
     return true;
 }
 
+bool swg::paf_tree_line(const char *line, size_t len, AniLine *out, uint64_t *matches, uint64_t *block) {
+    if (len == 0 || line[0] == '#') return false; // tree_filter.rs:221-223
+    const char *fs[11];
+    size_t fl[11];
+    int nf = 0;
+    size_t a = 0;
+    while (nf < 11) {
+        const char *tab = (const char *)memchr(line + a, '\t', len - a);
+        size_t b = tab ? (size_t)(tab - line) : len;
+        fs[nf] = line + a;
+        fl[nf] = b - a;
+        nf++;
+        if (!tab) break;
+        a = b + 1;
+    }
+    if (nf < 11) return false;
+    out->qname = fs[0]; out->qname_len = fl[0];
+    out->tname = fs[5]; out->tname_len = fl[5];
+    if (!rust_parse_u64(fs[9], fl[9], matches)) *matches = 0;
+    if (!rust_parse_u64(fs[10], fl[10], block)) *block = 1;
+    return true;
+}
+
+uint64_t swg::siphash13_zero_key(const uint8_t *msg, size_t len) {
+    uint64_t v[4] = {0x736f6d6570736575ull, 0x646f72616e646f6dull, 0x6c7967656e657261ull, 0x7465646279746573ull};
+    auto rotl = [](uint64_t x, int b) { return (x << b) | (x >> (64 - b)); };
+    auto sipround = [&]() {
+        v[0] += v[1]; v[1] = rotl(v[1], 13); v[1] ^= v[0]; v[0] = rotl(v[0], 32);
+        v[2] += v[3]; v[3] = rotl(v[3], 16); v[3] ^= v[2];
+        v[0] += v[3]; v[3] = rotl(v[3], 21); v[3] ^= v[0];
+        v[2] += v[1]; v[1] = rotl(v[1], 17); v[1] ^= v[2]; v[2] = rotl(v[2], 32);
+    };
+    const size_t full = len & ~(size_t)7;
+    for (size_t i = 0; i < full; i += 8) {
+        uint64_t m;
+        memcpy(&m, msg + i, 8); // little endian host
+        v[3] ^= m;
+        sipround(); // c = 1
+        v[0] ^= m;
+    }
+    uint64_t last = (uint64_t)len << 56;
+    for (size_t i = full; i < len; i++) last |= (uint64_t)msg[i] << (8 * (i - full));
+    v[3] ^= last;
+    sipround();
+    v[0] ^= last;
+    v[2] ^= 0xff;
+    for (int r = 0; r < 3; r++) sipround(); // d = 3
+    return v[0] ^ v[1] ^ v[2] ^ v[3];
+}
+
+std::vector<uint8_t> swg::tree_select_pairs(const std::vector<std::string> &genomes, const std::vector<uint32_t> &lo,
+                                            const std::vector<uint32_t> &hi, const std::vector<double> &identity, uint64_t k_nearest,
+                                            uint64_t k_farthest, double random_fraction, bool *has_nan) {
+    const size_t np = lo.size();
+    std::vector<uint8_t> sel(np, 0);
+    *has_nan = false;
+    for (double v : identity)
+        if (v != v) { *has_nan = true; return sel; }
+    // adjacency: for every genome the (pair index, other genome) list
+    std::vector<std::vector<uint32_t>> adj(genomes.size());
+    for (size_t p = 0; p < np; p++) { adj[lo[p]].push_back((uint32_t)p); adj[hi[p]].push_back((uint32_t)p); }
+    for (size_t g = 0; g < genomes.size(); g++) {
+        auto &v = adj[g];
+        auto other = [&](uint32_t p) { return lo[p] == g ? hi[p] : lo[p]; };
+        // identity descending; `genomes` is sorted, so the index order of the other genome is its name order
+        std::sort(v.begin(), v.end(), [&](uint32_t x, uint32_t y) { return identity[x] != identity[y] ? identity[x] > identity[y] : other(x) < other(y); });
+        for (size_t k = 0; k < v.size() && k < k_nearest; k++) sel[v[k]] = 1;
+        for (size_t k = 0; k < v.size() && k < k_farthest; k++) sel[v[v.size() - 1 - k]] = 1;
+    }
+    if (random_fraction > 0.0) {
+        const double t = random_fraction * 18446744073709551616.0; // u64::MAX as f64
+        const uint64_t thr = t >= 18446744073709551616.0 ? ~(uint64_t)0 : (uint64_t)t; // `as u64` saturates
+        std::string msg;
+        for (size_t p = 0; p < np; p++) {
+            msg.assign(genomes[lo[p]]);
+            msg.push_back((char)0xff); // str::hash: the bytes, then 0xff
+            msg.append(genomes[hi[p]]);
+            msg.push_back((char)0xff);
+            if (siphash13_zero_key((const uint8_t *)msg.data(), msg.size()) <= thr) sel[p] = 1;
+        }
+    }
+    return sel;
+}
+
 namespace {
 
 static void parse_chunk(const char *text, Chunk &c) {

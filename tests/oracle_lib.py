@@ -137,6 +137,27 @@ def ani_stats(path, method, percentile=0.0, sort=1):
     return ani.value, int(npairs.value)
 
 
+_lib.orc_tree_filter_paf.restype = C.c_int
+_lib.orc_tree_filter_paf.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_double, u64p, u64p]
+_lib.orc_siphash13.restype = C.c_uint64
+_lib.orc_siphash13.argtypes = [C.c_char_p, C.c_uint64]
+
+
+def tree_filter_paf(in_path, out_path, k_nearest, k_farthest=0, random_fraction=0.0):
+    """Oracle apply_tree_filter_to_paf (src/tree_filter.rs:205-283) -> (lines kept, pairs selected)."""
+    kept, sel = C.c_uint64(), C.c_uint64()
+    rc = _lib.orc_tree_filter_paf(os.fsencode(in_path), os.fsencode(out_path), k_nearest, k_farthest, random_fraction, C.byref(kept), C.byref(sel))
+    if rc == -2:
+        raise ValueError("NaN (the reference panics)")
+    if rc != 0:
+        raise IOError(in_path)
+    return int(kept.value), int(sel.value)
+
+
+def siphash13(data: bytes) -> int:
+    return int(_lib.orc_siphash13(data, len(data)))
+
+
 def filter_paf(cfg, in_path, out_path):
     """Oracle PafFilter::filter_paf (parse + filter + tagged write) -> stats"""
     c = cfg.to_c()
