@@ -7,9 +7,11 @@
 // Parity status: PINNED against the reference's own known-answer tests
 // (tests/test_reference_vectors.py transcribes them with file:line), the Rust
 // reference itself cannot be compiled here (no cargo/rustc, un-vendored deps).
-// Exception: orc_ani_stats (the ANI pre-pass, src/main.rs:334-688) — PARITY UNPINNED:
-// the reference holds no test or vector for it; tests/test_host.py checks the
-// restatement against answers computed by hand from the source.
+// Exceptions: orc_ani_stats (the ANI pre-pass, src/main.rs:334-688) and
+// orc_tree_filter_paf (src/tree_filter.rs:205-283) — PARITY UNPINNED: the reference
+// holds no test or vector for them (beyond extract_genome_prefix); tests/test_host.py
+// and tests/test_tree_cpu.py check the restatements against answers computed by hand
+// from the source, and the SipHash-1-3 core against CPython's siphash13.
 //
 // Every function cites the reference file:line it restates
 // (paths relative to /root/reference).  Containers: BTreeSet -> std::set with
