@@ -473,7 +473,9 @@ k_chain_resolve_warp(const Cand *__restrict__ cand, const uint4 *__restrict__ sr
 
 // rough count of candidate evaluations the chaining will need (guards against an input that would run for hours)
 __global__ void __launch_bounds__(256)
-k_chain_work_estimate(const uint4 *__restrict__ srec, const u32 *__restrict__ gstart, u32 n_groups, u32 n_m, u64 G, u64 *ctr) {
+k_chain_work_estimate(const uint4 *__restrict__ srec, const u32 *__restrict__ gstart, const u32 *__restrict__ n_groups_ptr, u32 n_m, u64 G,
+                      u64 *ctr) {
+    const u32 n_groups = *n_groups_ptr; // the grid covers n_m >= n_groups: the host has not read the group count yet
     const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
     u64 est = 0;
     if (g < n_groups) {

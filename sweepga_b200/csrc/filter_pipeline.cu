@@ -358,7 +358,14 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     u32 *d_maxp = A.take<u32>(2);
     SWG_CUDA(cudaMemsetAsync(d_maxp, 0, 2 * sizeof(u32), st));
     launch_for<t_maxp>(in.n_seq, st, lc, [=] __device__(u32 s) { atomicMax(&d_maxp[0], in.P[s]); atomicMax(&d_maxp[1], in.P2[s]); });
-    const u32 maxP = read_u32(c, d_maxp), maxP2 = read_u32(c, d_maxp + 1);
+    u32 maxP, maxP2;
+    {   // both in one round trip
+        u32 *h = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
+        SWG_CUDA(cudaMemcpyAsync(h, d_maxp, 2 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+        SWG_CUDA(cudaStreamSynchronize(st));
+        maxP = h[0];
+        maxP2 = h[1];
+    }
     if (maxP >= in.n_seq || maxP2 >= in.n_seq) throw RangeError{"genome prefix id >= n_seq (prefix ids must be dense)"};
     u64 npairs = std::min<u64>((u64)N, (u64)(maxP + 1) * (maxP + 1));
     u32 hcap = 1024;
@@ -487,12 +494,15 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         srec[p] = __ldg(&rec4[i]);
         srec2[p] = make_uint2(__ldg(&in.blen[i]), __ldg(&in.matches[i]));
     });
-    const u32 n_groups = read_u32(c, d_tot);
+    u32 n_groups;
     {   // refuse inputs whose chaining would need an absurd number of candidate evaluations (e.g. one 50 M-mapping pile:
         // ~2e13; the reference is O(n * window) there as well) instead of occupying the GPU for hours
-        k_chain_work_estimate<<<cdiv(n_groups, 256), 256, 0, st>>>(srec, gstart, n_groups, n_m, cfg.scaffold_gap, ctr);
+        k_chain_work_estimate<<<cdiv(n_m, 256), 256, 0, st>>>(srec, gstart, d_tot, n_m, cfg.scaffold_gap, ctr);
         lc.n++;
+        u32 *h = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
+        SWG_CUDA(cudaMemcpyAsync(h, d_tot, sizeof(u32), cudaMemcpyDeviceToHost, st)); // group count and estimate in one round trip
         read_counters(c);
+        n_groups = *h;
         static const double max_evals = getenv("SWG_MAX_PAIR_EVALS") ? atof(getenv("SWG_MAX_PAIR_EVALS")) : 5e12;
         if ((double)c->h_ctr[C_WORK] > max_evals)
             throw RangeError{"chaining would need ~" + std::to_string((double)c->h_ctr[C_WORK]) +
@@ -597,10 +607,15 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     u32 *oval = A.take<u32>(C), *oval2 = A.take<u32>(C);
     scan_apply([=] __device__(u32 ci) -> u32 { return ct.pass[ci] ? 1u : 0u; },
                [=] __device__(u32 ci, u32 ex, u32 v) { if (v) { okey[ex] = okey_all[ci]; oval[ex] = ci; } }, C, bsum, d_tot + 3, st, lc);
-    const u32 C1 = read_u32(c, d_tot + 3);
-    sort_pairs(c, okey, okey2, oval, oval2, C1, 2 * nb); // stable: ties (same group) keep head-position order
-    read_counters(c);
+    u32 C1;
+    {   // the count and the counters in one round trip
+        u32 *h = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
+        SWG_CUDA(cudaMemcpyAsync(h, d_tot + 3, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        read_counters(c);
+        C1 = *h;
+    }
     const u64 pass_zero = c->h_ctr[C_PASS_ZEROSPAN];
+    sort_pairs(c, okey, okey2, oval, oval2, C1, 2 * nb); // stable: ties (same group) keep head-position order
     S.n_chains_after_mass = C1;
 
     stage_mark(c, "chain_order");
@@ -716,15 +731,11 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                 ik[u] = f ? t_c2key[t] : NONE64;
                 iv[u] = u;
                 u_qs[u] = t_qs[t]; u_qe[u] = t_qe[t]; u_ts[u] = t_ts[t];
-                const u32 am = __activemask();
-                const u32 nf = __popc(__ballot_sync(am, f));
-                if (nf && (threadIdx.x & 31) == (u32)(__ffs(am) - 1)) atomicAdd((unsigned long long *)&ctr[C_INV], (unsigned long long)nf);
             });
         }
         sort_pairs(c, ik, ik2, iv, iv2, C2, 2 * sb + 1);
-        read_counters(c);
-        const u32 Cf = (u32)c->h_ctr[C_INV];
-        if (Cf > 0) {
+        const u32 Cf = C2; // the other chains carry the all-ones key and sort behind every forward chain: no count (and no round trip) needed
+        {
             const u64 G = cfg.scaffold_gap;
             const u64 *ikc = ik;
             const u32 *ivc = iv;
