@@ -112,6 +112,7 @@ struct swg_ctx {
     cudaStream_t copy_stream = nullptr;          // second stream: the `matches` column is uploaded behind the kernels
     cudaEvent_t ev_copy[2] = {nullptr, nullptr};
     cudaEvent_t ev_sort[2] = {nullptr, nullptr}; // bracket the one-sweep passes of the record sort
+    cudaEvent_t ev_ctr = nullptr;                // marks an early copy of the counters (read while later kernels still run)
     int sort_passes = 0;
     u64 sort_pairs = 0;
     std::vector<cudaEvent_t> stage_ev;      // SWG_STAGE_TIMING=1: events at stage boundaries of the last call
@@ -164,6 +165,13 @@ static void read_counters(swg_ctx *c) {
     SWG_CUDA(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(u64) * C_COUNT, cudaMemcpyDeviceToHost, c->stream));
     SWG_CUDA(cudaStreamSynchronize(c->stream));
 }
+// The counters as they are at this point of the stream, without draining it: the copy is marked by an event, the host
+// waits for that event only, and kernels enqueued after the copy keep the GPU busy meanwhile.
+static void read_counters_begin(swg_ctx *c) {
+    SWG_CUDA(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(u64) * C_COUNT, cudaMemcpyDeviceToHost, c->stream));
+    SWG_CUDA(cudaEventRecord(c->ev_ctr, c->stream));
+}
+static void read_counters_end(swg_ctx *c) { SWG_CUDA(cudaEventSynchronize(c->ev_ctr)); }
 static u32 read_u32(swg_ctx *c, const u32 *d) {
     u32 *h = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
     SWG_CUDA(cudaMemcpyAsync(h, d, sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
@@ -439,7 +447,9 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     if (!wide) {
         k_chain_keys<<<cdiv(N, 256), 256, 0, st>>>(in, flags, keep_q, keep_t, sb, cb, keys, vals, ctr);
         lc.n++;
+        read_counters_begin(c); // the survivor count is final here; the host picks it up while the sort runs
         sort_pairs(c, keys, keys2, vals, vals2, N, 2 * sb + 1 + cb, true);
+        read_counters_end(c);
     } else {
         // key wider than 64 bits (hundreds of thousands of sequences): two chained stable sorts, least significant
         // field first: by query_start, then by the (query,target,strand) group id; skey then holds the group id alone
@@ -466,8 +476,8 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         }
         sort_pairs(c, keys, keys2, vals, vals2, N, 2 * sb + 2);
         gshift = 0;
+        read_counters(c);
     }
-    read_counters(c);
     const u32 n_m = (u32)c->h_ctr[C_KEPT_M];
     S.n_after_sweep = n_m;
     S.score_near_ties = c->h_ctr[C_NEAR_TIES];
@@ -547,20 +557,27 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         k_chain_resolve_warp<<<(u32)c->sm_count * 4, 128, 0, st>>>(cand, srec, skey, gstart, n_groups, n_m, work_big, bb_ctr + 2, gshift,
                                                                   cfg.scaffold_gap, bps, root, bb_ctr + 3);
         lc.n += 2;
-        k_chain_heads<<<cdiv(n_m, 256), 256, 0, st>>>(srec, srec2, sidx, gid, root, n_m, cs);
-        k_chain_members<<<cdiv(n_m, 256), 256, 0, st>>>(srec, srec2, root, n_m, cs);
-        lc.n += 3;
     }
-
-    stage_mark(c, "chain_table");
     // ---- K4: dense chain table + mass/identity filter + order key (A,B) ----------------------------
-    // upper bound on chains is n_m; the table is sized after counting heads
+    // upper bound on chains is n_m; the table is sized after counting heads.  The count only needs `root`, so it runs
+    // before the aggregate kernels and the host reads it (event, not a stream drain) while they execute.
     u32 *chain_of_pos = A.take<u32>(n_m);
     u32 *head_pos = A.take<u32>(n_m); // compacted head positions (C of them)
     u32 *d_nch = d_tot + 2;
     scan_apply([=] __device__(u32 p) -> u32 { return root[p] == p ? 1u : 0u; },
                [=] __device__(u32 p, u32 ex, u32 v) { if (v) { chain_of_pos[p] = ex; head_pos[ex] = p; } }, n_m, bsum, d_nch, st, lc);
-    const u32 C = read_u32(c, d_nch);
+    u32 C;
+    {
+        u32 *h = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
+        SWG_CUDA(cudaMemcpyAsync(h, d_nch, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        SWG_CUDA(cudaEventRecord(c->ev_ctr, st));
+        k_chain_heads<<<cdiv(n_m, 256), 256, 0, st>>>(srec, srec2, sidx, gid, root, n_m, cs);
+        k_chain_members<<<cdiv(n_m, 256), 256, 0, st>>>(srec, srec2, root, n_m, cs);
+        lc.n += 2;
+        SWG_CUDA(cudaEventSynchronize(c->ev_ctr));
+        C = *h;
+    }
+    stage_mark(c, "chain_table");
     S.n_chains = C;
     ChainTable ct;
     ct.pos = head_pos; ct.qid = A.take<u32>(C); ct.tid = A.take<u32>(C); ct.fwd = A.take<u8>(C);
@@ -681,8 +698,9 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                 if (nk && (threadIdx.x & 31) == (u32)(__ffs(am) - 1)) atomicAdd((unsigned long long *)&ctr[C_KEPT_CHAINS], (unsigned long long)nk);
             });
         }
+        read_counters_begin(c); // the kept-chain count is final here; the host picks it up while the sort runs
         sort_pairs(c, sk, sk2, sv, sv2, C1, ob + 1);
-        read_counters(c);
+        read_counters_end(c);
         C2 = (u32)c->h_ctr[C_KEPT_CHAINS];
         S.score_near_ties = c->h_ctr[C_NEAR_TIES];
         fin_t = sv;
@@ -1077,6 +1095,7 @@ swg_ctx *swg_create(int device) {
         for (auto &ev : c->ev_sort) SWG_CUDA(cudaEventCreate(&ev));
         SWG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         for (auto &ev : c->ev_copy) SWG_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        SWG_CUDA(cudaEventCreateWithFlags(&c->ev_ctr, cudaEventDisableTiming));
         SWG_CUDA(cudaMallocHost(&c->h_ctr, sizeof(u64) * (C_COUNT + 8)));
         SWG_CUDA(cudaMalloc(&c->d_ctr, sizeof(u64) * C_COUNT));
     } catch (const CudaError &e2) {
@@ -1103,6 +1122,7 @@ void swg_destroy(swg_ctx *c) {
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : c->ev_sort) if (ev) cudaEventDestroy(ev);
     for (auto &ev : c->ev_copy) if (ev) cudaEventDestroy(ev);
+    if (c->ev_ctr) cudaEventDestroy(c->ev_ctr);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
