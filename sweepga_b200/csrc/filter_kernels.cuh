@@ -475,17 +475,16 @@ k_chain_resolve_warp(const Cand *__restrict__ cand, const uint4 *__restrict__ sr
 __global__ void __launch_bounds__(256)
 k_chain_work_estimate(const uint4 *__restrict__ srec, const u32 *__restrict__ gstart, const u32 *__restrict__ n_groups_ptr, u32 n_m, u64 G,
                       u64 *ctr) {
-    const u32 n_groups = *n_groups_ptr; // the grid covers n_m >= n_groups: the host has not read the group count yet
-    const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 n_groups = *n_groups_ptr; // grid-stride: the host has not read the group count yet
     u64 est = 0;
-    if (g < n_groups) {
+    for (u32 g = blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += gridDim.x * blockDim.x) {
         const u32 s = gstart[g], e = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
         const u64 size = e - s;
         if (size > 1) {
             const u64 span = (u64)srec[e - 1].x - srec[s].x + 1;
             u64 win = size * G / span + 1; // expected candidates per step
             if (win > size) win = size;
-            est = size * win;
+            est += size * win;
         }
     }
 #pragma unroll

@@ -507,7 +507,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     u32 n_groups;
     {   // refuse inputs whose chaining would need an absurd number of candidate evaluations (e.g. one 50 M-mapping pile:
         // ~2e13; the reference is O(n * window) there as well) instead of occupying the GPU for hours
-        k_chain_work_estimate<<<cdiv(n_m, 256), 256, 0, st>>>(srec, gstart, d_tot, n_m, cfg.scaffold_gap, ctr);
+        k_chain_work_estimate<<<(u32)c->sm_count * 8, 256, 0, st>>>(srec, gstart, d_tot, n_m, cfg.scaffold_gap, ctr);
         lc.n++;
         u32 *h = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
         SWG_CUDA(cudaMemcpyAsync(h, d_tot, sizeof(u32), cudaMemcpyDeviceToHost, st)); // group count and estimate in one round trip
