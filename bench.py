@@ -137,6 +137,38 @@ def oracle_mt(cfg, table, threads):
     return time.perf_counter() - t0
 
 
+def paf_file_leg(ctx, cfg, n_lines):
+    """Extra, informational: PafFilter::filter_paf file to file (text tokenised and tagged output assembled on the GPU,
+    swg_filter_paf) and the same call with the host front end, on a synthetic PAF with cg:Z: tags.  Never fails the bench."""
+    import shutil
+    import tempfile
+    import sweepga_b200 as swg
+    from sweepga_b200 import synth
+    d = tempfile.mkdtemp(prefix="swg_bench_")
+    try:
+        t = synth.pansn(n_lines, seed=3, n_hap=40, with_names=True)
+        src, out = os.path.join(d, "in.paf"), os.path.join(d, "out.paf")
+        synth.write_paf_fast(t, src)
+        f = swg.PafFilter(cfg)
+        f._ctx = ctx
+        res = {}
+        for key, host in (("device_front_end", False), ("host_front_end", True)):
+            f.filter_paf(src, out, host_frontend=host)  # warm-up: page cache, arenas, pinned pieces
+            os.unlink(out)                               # a fresh output file (ext4 flushes a re-written truncated file at close)
+            t0 = time.time()
+            st = f.filter_paf(src, out, host_frontend=host)
+            dt = time.time() - t0
+            res[key] = {"wall_s": dt, "Mlines_per_s": t.n / dt / 1e6, "ms_upload": st.ms_h2d, "ms_tokenize": st.ms_tokenize,
+                        "ms_filter": st.ms_device, "ms_write": st.ms_write, "gpu_launches": int(st.gpu_launches), "kept": int(st.n_kept)}
+        res["lines"] = int(t.n)
+        res["input_bytes"] = os.path.getsize(src)
+        return res
+    except Exception as e:  # informational leg only
+        return {"error": repr(e)[:200]}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -144,6 +176,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--records", type=int, default=0, help="override the per-GPU record count (debug only)")
+    ap.add_argument("--paf-lines", type=int, default=2_000_000,
+                    help="N = 1 only: also time swg_filter_paf file to file on a synthetic PAF of this many lines (0 = skip)")
     ap.add_argument("--cpu-sample", type=int, default=20_000_000,
                     help="records of the workload the CPU oracle is timed on (~20 core-seconds at the default)")
     args = ap.parse_args()
@@ -301,6 +335,8 @@ def main():
                          "frac": achieved / peak if peak else None, "traffic": traffic,
                          "launch_ms": pass_ms, "pairs_per_launch": int(stats.n_sort_pairs)},
         }
+        if n_gpus == 1 and args.paf_lines > 0:
+            line["paf_e2e"] = paf_file_leg(ctx, cfg, args.paf_lines)
         if n_gpus == 1:
             sample = table.take(np.arange(min(n, args.cpu_sample)))
             cores = os.cpu_count() or 1

@@ -19,7 +19,7 @@
 namespace swg {
 
 struct t_ani_pairs; struct t_ani_first; struct t_ani_sizes; struct t_ani_keys; struct t_ani_gather; struct t_ani_fixgather; struct t_ani_patch;
-struct t_ani_tiles; struct t_ani_sortkeys;
+struct t_ani_tiles;
 
 enum : u8 { AK_SKIP = 0, AK_OK = 1, AK_FIX = 2 };
 enum { AC_OK = 0, AC_NFIX, AC_NAN, AC_NONINT, AC_INTER, AC_MAXLEN, AC_COUNT };

@@ -537,6 +537,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     {
         k_chain_candidates<<<cdiv(n_m, 256), 256, 0, st>>>(srec, skey, gid, gstart, n_groups, n_m, gshift, cfg.scaffold_gap, cand, bps, root, grp_has_cand);
         lc.n++;
+        stage_mark(c, "ch_worklists");
         // work lists: groups with at least one candidate, split into ordinary (thread per group) and large/dense
         // (warp per group: size > 4096 or an expected window > 64 candidates)
         const u64 Gj = cfg.scaffold_gap;
@@ -550,6 +551,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                    [=] __device__(u32 g, u32 ex, u32 v) { if (v) work[ex] = g; }, n_groups, bsum, bb_ctr, st, lc);
         scan_apply([=] __device__(u32 g) -> u32 { return (grp_has_cand[g] && is_big(g)) ? 1u : 0u; },
                    [=] __device__(u32 g, u32 ex, u32 v) { if (v) work_big[ex] = g; }, n_groups, bsum, bb_ctr + 2, st, lc);
+        stage_mark(c, "ch_resolve");
         // enough threads to hide the dependent-load latency of a step, few enough that every group's lines stay in L1/L2
         static const int resolve_mult = getenv("SWG_RESOLVE_MULT") ? atoi(getenv("SWG_RESOLVE_MULT")) : 4;
         k_chain_resolve<<<(u32)c->sm_count * resolve_mult, 128, 0, st>>>(cand, srec, skey, gstart, n_groups, n_m, work, bb_ctr, gshift, cfg.scaffold_gap,
@@ -558,6 +560,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                                                                   cfg.scaffold_gap, bps, root, bb_ctr + 3);
         lc.n += 2;
     }
+    stage_mark(c, "ch_aggregate");
     // ---- K4: dense chain table + mass/identity filter + order key (A,B) ----------------------------
     // upper bound on chains is n_m; the table is sized after counting heads.  The count only needs `root`, so it runs
     // before the aggregate kernels and the host reads it (event, not a stream drain) while they execute.

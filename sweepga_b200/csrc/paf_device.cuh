@@ -27,8 +27,7 @@
 
 namespace swg {
 
-struct t_tok_init; struct t_tok_fixgather; struct t_tok_patch; struct t_name_assign; struct t_name_lookup; struct t_out_bounds;
-struct t_tok_iota;
+struct t_tok_fixgather; struct t_tok_patch; struct t_name_assign; struct t_out_bounds;
 
 __constant__ double c_pow10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
                                    1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};

@@ -166,6 +166,23 @@ def skew(n_pile=50_000_000, n_tiny_groups=100_000, seed=5, window=6_000_000):
                         P, P2, None, names)
 
 
+def write_paf_fast(table: MappingTable, path: str):
+    """The same columns as write_paf plus a cg:Z: tag, built with vectorised numpy string ops (≈ 3 s per million
+    lines instead of a Python loop) — for file-level benchmarks."""
+    names = np.array(table.names)
+    t = table
+    cols = [names[t.query_id], (t.query_end.astype(np.int64) + 1000).astype(str), t.query_start.astype(str), t.query_end.astype(str),
+            np.where(t.strand == ord("+"), "+", "-"), names[t.target_id], (t.target_end.astype(np.int64) + 1000).astype(str),
+            t.target_start.astype(str), t.target_end.astype(str), t.matches.astype(str), t.block_length.astype(str), np.full(t.n, "60")]
+    lines = cols[0]
+    for c in cols[1:]:
+        lines = np.char.add(np.char.add(lines, "\t"), c)
+    tags = np.char.add(np.char.add(np.char.add("\tcg:Z:", t.matches.astype(str)), "="),
+                       np.char.add((t.block_length.astype(np.int64) - t.matches).astype(str), "X"))
+    with open(path, "w") as f:
+        f.write("\n".join(np.char.add(lines, tags).tolist()) + "\n")
+
+
 def write_paf(table: MappingTable, path: str, tags=True, seq_lengths=None):
     """Emit the table as PAF text (for the parse + filter + write path).  cols 10/11 reproduce
     matches/block_length, so the parser re-derives the same identity."""
