@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) k_ani_parse(const char *__restrict__ text
     bool ok = false;
     if (l < n_lines) {
         const u64 s = line_start[l];
-        u32 len = (u32)(line_start[l + 1] - 1 - s);
+        u32 len = (u32)min(line_start[l + 1] - 1 - s, (u64)0xFFFFFFF0u);
         const char *line = text + s;
         if (len > 0 && line[len - 1] == '\r') len--;
         u8 kind = AK_SKIP;
@@ -130,9 +130,9 @@ __global__ void __launch_bounds__(256) k_ani_parse(const char *__restrict__ text
     }
     const u32 nok = __syncthreads_count(ok);
     if (threadIdx.x == 0 && nok) atomicAdd((unsigned long long *)&ac[AC_OK], (unsigned long long)nok);
-    if (MODE == 1) { // the longest line sizes the output window of write_device
+    { // the longest line: sizes the output window of write_device (MODE 1); lines of 256 MiB and more are declined
         u32 mylen = 0;
-        if (l < n_lines) mylen = (u32)(line_start[l + 1] - 1 - line_start[l]);
+        if (l < n_lines) mylen = (u32)min(line_start[l + 1] - 1 - line_start[l], (u64)0xFFFFFFF0u);
         const u32 mx = __reduce_max_sync(0xFFFFFFFFu, mylen);
         if (lane_id() == 0 && mx > (u32)ac[AC_MAXLEN]) atomicMax((unsigned long long *)&ac[AC_MAXLEN], (unsigned long long)mx);
     }
@@ -195,6 +195,7 @@ static AniResult ani_device(swg_ctx *c, const swg_paf &hp, int method, double pe
     k_ani_parse<0><<<cdiv(n_lines, 256), 256, 0, st>>>(text, dl.line_start, n_lines, L, fix_list, ac);
     lc.n++;
     read_ac();
+    if (h_ac[AC_MAXLEN] > ((u64)256 << 20)) throw FrontEndFallback{"a line longer than 256 MiB"};
     u64 n_ok = h_ac[AC_OK];
     if (h_ac[AC_NFIX]) { // lines outside the plain number grammar: the host's line reader decides
         const u32 nfix = (u32)h_ac[AC_NFIX];

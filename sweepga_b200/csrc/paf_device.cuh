@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(256) k_tok_parse(const char *__restrict__ text
     if (l < n_lines) {
         const u64 s = line_start[l];
         const u64 e = line_start[l + 1] - 1;
-        len = (u32)(e - s);
+        len = (u32)min(e - s, (u64)0xFFFFFFF0u); // a line of 4 GiB trips the host's longest-line check (front-end fallback)
         const char *line = text + s;
         if (len > 0 && line[len - 1] == '\r') len--; // BufRead::lines strips "\r\n"
         L.off[l] = s;
