@@ -10,11 +10,17 @@
 
 namespace swg {
 
-constexpr int SC_THREADS = 256;
-constexpr int SC_ITEMS = 8;
+#ifndef SWG_SC_THREADS
+#define SWG_SC_THREADS 256
+#endif
+#ifndef SWG_SC_ITEMS
+#define SWG_SC_ITEMS 8
+#endif
+constexpr int SC_THREADS = SWG_SC_THREADS;
+constexpr int SC_ITEMS = SWG_SC_ITEMS;
 constexpr int SC_TILE = SC_THREADS * SC_ITEMS;
 
-__device__ __forceinline__ u32 block_exclusive_scan_256(u32 v, u32 *ws /*[8]*/, u32 &block_total) {
+__device__ __forceinline__ u32 block_exclusive_scan_256(u32 v, u32 *ws /*[SC_THREADS / 32]*/, u32 &block_total) {
     u32 x = v;
     u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -50,7 +56,7 @@ __device__ __forceinline__ void st_relaxed_u64(u64 *p, u64 v) {
 
 template <class In, class Out>
 __global__ void __launch_bounds__(SC_THREADS) sc_onepass_kernel(In in, Out out, u32 n, u64 *status, u32 *tile_counter, u32 *total_out) {
-    __shared__ u32 ws[8];
+    __shared__ u32 ws[SC_THREADS / 32];
     __shared__ u32 s_tile, s_excl;
     if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u); // in-order tile ids
     __syncthreads();
