@@ -216,6 +216,48 @@ def test_filter_paf_device_equals_host_and_oracle(ctx, tmp_path, flags):
     assert st.gpu_launches > 10 and st.ms_tokenize > 0
 
 
+def test_filter_file_and_apply_paf_filter(tmp_path):
+    """unified_filter::filter_file (src/unified_filter.rs:280-347) and library_api::apply_paf_filter
+    (src/library_api.rs:267-281): PAF input goes through filter_paf with the caller's keep_self / with keep_self = false;
+    a ONEcode container ("1 " magic) is reported as unsupported, never guessed."""
+    import os
+    from sweepga_b200 import _lib
+    t = synth.yeast_like(6000, seed=21)
+    src = tmp_path / "y.paf"
+    synth.write_paf(t, str(src))
+    # self mappings make keep_self observable
+    lines = src.read_text().split("\n")
+    extra = []
+    for k in range(0, 200, 7):
+        f = lines[k].split("\t")
+        f[5] = f[0]
+        extra.append("\t".join(f))
+    src.write_text("\n".join(extra + lines))
+    cfg = swg.FilterConfig.from_cli(scaffold_dist="20k")
+    outs = {}
+    for keep_self in (False, True):
+        out, ref = tmp_path / f"o{int(keep_self)}.paf", tmp_path / f"r{int(keep_self)}.paf"
+        swg.filter_file(str(src), str(out), cfg, keep_self=keep_self)
+        c2 = swg.FilterConfig(**vars(cfg))
+        c2.keep_self = keep_self
+        oracle_lib.filter_paf(c2, str(src), str(ref))
+        assert out.read_bytes() == ref.read_bytes(), keep_self
+        outs[keep_self] = out.read_bytes()
+    assert outs[False] != outs[True]
+    path = swg.apply_paf_filter(str(src), cfg)
+    try:
+        assert path.endswith(".filtered.paf") and open(path, "rb").read() == outs[False]
+    finally:
+        os.unlink(path)
+    aln = tmp_path / "x.1aln"
+    aln.write_bytes(b"1 3 aln\n2 3 seq\n")
+    with pytest.raises(swg.SwgError) as e:
+        swg.filter_file(str(aln), str(tmp_path / "o.1aln"), cfg)
+    assert e.value.code == _lib.ERR_UNSUPPORTED
+    with pytest.raises(swg.SwgError):
+        swg.filter_file(str(tmp_path / "missing.paf"), str(tmp_path / "o.paf"), cfg)
+
+
 def test_filter_paf_device_no_records_and_unwritable(ctx, tmp_path):
     (tmp_path / "junk.paf").write_bytes(b"\nnot a paf line\n")
     f = swg.PafFilter(swg.FilterConfig())
