@@ -399,38 +399,64 @@ __device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__
     bb_argmin(bd, bj);
     if (exhausted || lin_end >= e) return;
     const u32 jl = lin_end; // the rest of the window is [jl, ...)
+    // first position in [jl, e) whose start is >= query_end: 33-ary search, 32 probes in flight per round (a binary
+    // search pays one L2 round trip per halving: ~19 dependent loads in a 500 k-mapping group)
     u32 lo = jl, hi = e;
-    while (lo < hi) { // lane-uniform binary search (broadcast loads)
-        const u32 mid = (lo + hi) >> 1;
-        if (srec[mid].x < a.y) lo = mid + 1; else hi = mid;
+    while (hi - lo > 32) {
+        const u32 width = hi - lo;
+        const u32 p = lo + (u32)(((u64)(lane + 1) * width) / 33);
+        const u32 below = __popc(__ballot_sync(full, srec[p].x < a.y)); // monotone: the first `below` probes are < query_end
+        const u32 nlo = below ? lo + (u32)(((u64)below * width) / 33) + 1 : lo;
+        const u32 nhi = below < 32 ? lo + (u32)(((u64)(below + 1) * width) / 33) : hi;
+        lo = nlo;
+        hi = nhi;
+    }
+    {
+        const u32 p = lo + lane;
+        const u32 below = __popc(__ballot_sync(full, p < hi && srec[p].x < a.y));
+        lo += below;
     }
     const u32 c0 = lo;
-    for (u32 base = c0; base < e; base += 32) { // right side, q_gap >= 0 non-decreasing
+    // Four 32-wide chunks per round: their loads are independent, so a round costs one L2 round trip instead of four, and
+    // one warp arg-min.  The pruning test looks at the first candidate of the round only; candidates past the exact
+    // pruning point have d >= q_gap^2 > best d and cannot win, so reading a few more of them changes nothing.
+#ifndef SWG_RESCAN_WIDTH
+#define SWG_RESCAN_WIDTH 128
+#endif
+    constexpr u32 RW = SWG_RESCAN_WIDTH;
+    for (u32 base = c0; base < e; base += RW) { // right side, q_gap >= 0 non-decreasing
         const u64 qg0 = (u64)srec[base].x - a.y;
         if (qg0 > G || qg0 * qg0 > bd) break;
-        const u32 r = base + lane;
         u64 ld = NONE64;
         u32 lj = NONE32;
-        if (r < e) {
-            const uint4 b = srec[r];
-            const u64 qg = (u64)b.x - a.y;
-            u64 d;
-            if (qg <= G && bb_candidate(a, b, fwd, G, G5, d) && d < bps[r]) { ld = d; lj = r; }
+#pragma unroll
+        for (u32 k = 0; k < RW / 32; k++) {
+            const u32 r = base + k * 32 + lane;
+            if (r < e) {
+                const uint4 b = srec[r];
+                const u64 qg = (u64)b.x - a.y;
+                u64 d;
+                if (qg <= G && bb_candidate(a, b, fwd, G, G5, d) && d < bps[r] && d < ld) { ld = d; lj = r; } // r ascends: ties keep the smaller j
+            }
         }
         bb_argmin(ld, lj);
         if (ld < bd || (ld == bd && lj < bj)) { bd = ld; bj = lj; }
     }
-    for (u32 top = c0; top > jl;) { // left side, overlap > 0 non-decreasing going left; chunk = [top-32, top)
+    for (u32 top = c0; top > jl;) { // left side, overlap > 0 non-decreasing going left; round = [top-RW, top)
         const u64 ov0 = (u64)a.y - srec[top - 1].x;
         if (ov0 > G5 || ov0 * ov0 > bd) break;
-        const u32 cnt = min(32u, top - jl);
-        const u32 l = top - 1 - lane;
+        const u32 cnt = min(RW, top - jl);
         u64 ld = NONE64;
         u32 lj = NONE32;
-        if (lane < cnt) {
-            const uint4 b = srec[l];
-            u64 d;
-            if (bb_candidate(a, b, fwd, G, G5, d) && d < bps[l]) { ld = d; lj = l; }
+#pragma unroll
+        for (u32 k = 0; k < RW / 32; k++) {
+            const u32 off = k * 32 + lane;
+            if (off < cnt) {
+                const u32 l = top - 1 - off;
+                const uint4 b = srec[l];
+                u64 d;
+                if (bb_candidate(a, b, fwd, G, G5, d) && d < bps[l] && (d < ld || (d == ld && l < lj))) { ld = d; lj = l; }
+            }
         }
         bb_argmin(ld, lj);
         if (ld < bd || (ld == bd && lj < bj)) { bd = ld; bj = lj; }
@@ -453,20 +479,43 @@ k_chain_resolve_warp(const Cand *__restrict__ cand, const uint4 *__restrict__ sr
         const u32 g = work[w];
         const u32 s = gstart[g], e = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
         const bool fwd = ((skey[s] >> cb) & 1) == 0;
-        for (u32 i = s; i + 1 < e; i++) {
-            const Cand c = cand[i];
-            if (c.j == NONE32) continue;
-            const u32 ri = root[i];
-            if (c.d < bps[c.j]) {
-                if (lane == 0) { bps[c.j] = c.d; root[c.j] = ri; }
-            } else {
-                const uint4 a = srec[i];
-                u64 bd;
-                u32 bj;
-                bb_best_successor_warp(srec, bps, i, e, a, fwd, G, G5, bd, bj);
-                if (lane == 0 && bj != NONE32) { bps[bj] = bd; root[bj] = ri; }
+        // 32 steps per batch: lane k prefetches the candidate, the root and the current best_pred_score of step
+        // base + k in one round trip; the steps then run in order from registers.  A step that writes bps[j] / root[j]
+        // patches the prefetched copies of the later steps of the batch, so every step sees exactly the state the
+        // sequential walk would.
+        for (u32 base = s; base + 1 < e; base += 32) {
+            const u32 ik = base + lane;
+            Cand ck;
+            ck.d = 0; ck.j = NONE32;
+            u32 rk = 0;
+            u64 bk = 0;
+            if (ik + 1 < e) {
+                ck = cand[ik];
+                rk = root[ik];
+                if (ck.j != NONE32) bk = bps[ck.j];
             }
-            __syncwarp();
+            const u32 steps = min(32u, e - 1 - base);
+            for (u32 t = 0; t < steps; t++) {
+                const u32 cj = __shfl_sync(full, ck.j, t);
+                if (cj == NONE32) continue;
+                const u64 cd = __shfl_sync(full, ck.d, t);
+                const u64 bt = __shfl_sync(full, bk, t);
+                const u32 ri = __shfl_sync(full, rk, t);
+                u64 wd = NONE64; // what this step writes: bps[wj] = wd, root[wj] = ri
+                u32 wj = NONE32;
+                if (cd < bt) { wd = cd; wj = cj; }
+                else {
+                    const u32 i = base + t;
+                    const uint4 a = srec[i];
+                    bb_best_successor_warp(srec, bps, i, e, a, fwd, G, G5, wd, wj);
+                }
+                if (wj != NONE32) {
+                    if (lane == 0) { bps[wj] = wd; root[wj] = ri; }
+                    if (ck.j == wj) bk = wd;               // later steps of the batch that look at the same successor
+                    if (ik == wj) rk = ri;                 // the successor itself is a later step of the batch
+                    __syncwarp();
+                }
+            }
         }
     }
 }
