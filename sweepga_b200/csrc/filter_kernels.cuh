@@ -203,7 +203,8 @@ struct ChainSparse { // indexed by the sorted position of the chain head
 struct Cand { // unconstrained best successor of a position
     u64 d;    // squared gap distance
     u32 j;    // sorted position of the successor, NONE32 if the window holds no valid candidate
-    u32 pad;
+    u32 c0;   // first position past the linear phase whose query_start >= query_end (NONE32 if the search never got there):
+              // the origin of the outward scans, reused by the re-scans of the resolve
 };
 
 // gap rule of paf_filter.rs:799-833 (query axis and, strand-aware, target axis)
@@ -231,10 +232,11 @@ __device__ __forceinline__ bool bb_candidate(const uint4 &a, const uint4 &b, boo
 constexpr u32 BB_LINEAR = 48;
 template <bool ELIG>
 __device__ __forceinline__ void bb_best_successor(const uint4 *__restrict__ srec, const u64 *bps, u32 i, u32 e, const uint4 &a,
-                                                  bool fwd, u64 G, u64 G5, u64 &bd, u32 &bj) {
+                                                  bool fwd, u64 G, u64 G5, u64 &bd, u32 &bj, u32 *c0_out = nullptr) {
     const u64 bound = (u64)a.y + G;
     bd = NONE64;
     bj = NONE32;
+    if (c0_out) *c0_out = NONE32;
     u32 j = i + 1;
     const u32 lin_end = min(e, i + 1 + BB_LINEAR);
     for (; j < lin_end; j++) {
@@ -250,6 +252,7 @@ __device__ __forceinline__ void bb_best_successor(const uint4 *__restrict__ srec
         if (srec[mid].x < a.y) lo = mid + 1; else hi = mid;
     }
     const u32 c0 = lo;
+    if (c0_out) *c0_out = c0;
     for (u32 r = c0; r < e; r++) { // right: q_gap = qs - qe >= 0, non-decreasing
         const uint4 b = srec[r];
         const u64 qg = (u64)b.x - a.y;
@@ -280,9 +283,10 @@ k_chain_candidates(const uint4 *__restrict__ srec, const u64 *__restrict__ skey,
     const u32 e = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
     u64 bd;
     u32 bj;
-    bb_best_successor<false>(srec, nullptr, p, e, a, fwd, G, G / 5, bd, bj);
+    u32 c0;
+    bb_best_successor<false>(srec, nullptr, p, e, a, fwd, G, G / 5, bd, bj, &c0);
     Cand c;
-    c.d = bd; c.j = bj; c.pad = 0;
+    c.d = bd; c.j = bj; c.c0 = c0;
     cand[p] = c;
     bps[p] = NONE64;
     root[p] = p;
@@ -374,57 +378,103 @@ __device__ __forceinline__ void bb_argmin(u64 &bd, u32 &bj) { // smallest d, the
     bj = __reduce_min_sync(full, is ? bj : NONE32);
     bd = ((u64)mh << 32) | ml;
 }
-__device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__ srec, const u64 *bps, u32 i, u32 e, const uint4 &a,
-                                                       bool fwd, u64 G, u64 G5, u64 &bd, u32 &bj) {
-    const u32 full = 0xFFFFFFFFu;
-    const u32 lane = lane_id();
-    const u64 bound = (u64)a.y + G;
-    bd = NONE64;
-    bj = NONE32;
-    // linear phase: the first BB_LINEAR successors (two chunks)
-    u32 j0 = i + 1;
-    const u32 lin_end = min(e, i + 1 + 64);
-    bool exhausted = false;
-    for (; j0 < lin_end && !exhausted; j0 += 32) {
-        const u32 j = j0 + lane;
-        bool inwin = false;
-        if (j < lin_end) {
-            const uint4 b = srec[j];
-            inwin = (u64)b.x <= bound;
-            u64 d;
-            if (inwin && bb_candidate(a, b, fwd, G, G5, d) && d < bps[j] && (d < bd || (d == bd && j < bj))) { bd = d; bj = j; }
-        }
-        exhausted = !__all_sync(full, inwin || j >= lin_end) ;
-    }
-    bb_argmin(bd, bj);
-    if (exhausted || lin_end >= e) return;
-    const u32 jl = lin_end; // the rest of the window is [jl, ...)
-    // first position in [jl, e) whose start is >= query_end: 33-ary search, 32 probes in flight per round (a binary
-    // search pays one L2 round trip per halving: ~19 dependent loads in a 500 k-mapping group)
-    u32 lo = jl, hi = e;
-    while (hi - lo > 32) {
-        const u32 width = hi - lo;
-        const u32 p = lo + (u32)(((u64)(lane + 1) * width) / 33);
-        const u32 below = __popc(__ballot_sync(full, srec[p].x < a.y)); // monotone: the first `below` probes are < query_end
-        const u32 nlo = below ? lo + (u32)(((u64)below * width) / 33) + 1 : lo;
-        const u32 nhi = below < 32 ? lo + (u32)(((u64)(below + 1) * width) / 33) : hi;
-        lo = nlo;
-        hi = nhi;
-    }
-    {
-        const u32 p = lo + lane;
-        const u32 below = __popc(__ballot_sync(full, p < hi && srec[p].x < a.y));
-        lo += below;
-    }
-    const u32 c0 = lo;
-    // Four 32-wide chunks per round: their loads are independent, so a round costs one L2 round trip instead of four, and
-    // one warp arg-min.  The pruning test looks at the first candidate of the round only; candidates past the exact
-    // pruning point have d >= q_gap^2 > best d and cannot win, so reading a few more of them changes nothing.
 #ifndef SWG_RESCAN_WIDTH
 #define SWG_RESCAN_WIDTH 128
 #endif
-    constexpr u32 RW = SWG_RESCAN_WIDTH;
-    for (u32 base = c0; base < e; base += RW) { // right side, q_gap >= 0 non-decreasing
+__device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__ srec, const u64 *bps, u32 i, u32 e, const uint4 &a,
+                                                       bool fwd, u64 G, u64 G5, u64 &bd, u32 &bj, u32 c0_hint) {
+    const u32 full = 0xFFFFFFFFu;
+    const u32 lane = lane_id();
+    const u64 bound = (u64)a.y + G;
+    constexpr u32 RW = SWG_RESCAN_WIDTH; // candidates per outward round: four 32-wide chunks, loads independent, one warp arg-min
+    bd = NONE64;
+    bj = NONE32;
+    const u32 lin_end = min(e, i + 1 + 64);
+    const u32 jl = lin_end; // the outward scans cover [jl, e)
+    u32 rbase, ltop;        // where the outward rounds continue
+    if (c0_hint != NONE32 && lin_end < e) {
+        // The origin of the outward scans is known from the candidate pass (its linear phase is shorter: hence the max).
+        // First round: the 64 nearest successors, RW candidates to the right of the origin and RW to its left, all loads
+        // in flight together — one L2 round trip and one arg-min instead of three of each.  Every candidate is validated
+        // on its own (inside the window; gap rule), so evaluating this superset gives the same arg-min.
+        const u32 c0 = max(c0_hint, jl);
+        u64 ld = NONE64;
+        u32 lj = NONE32;
+#pragma unroll
+        for (u32 k = 0; k < 2; k++) {
+            const u32 j = i + 1 + k * 32 + lane;
+            if (j < lin_end) {
+                const uint4 b = srec[j];
+                u64 d;
+                if ((u64)b.x <= bound && bb_candidate(a, b, fwd, G, G5, d) && d < bps[j] && (d < ld || (d == ld && j < lj))) { ld = d; lj = j; }
+            }
+        }
+#pragma unroll
+        for (u32 k = 0; k < RW / 32; k++) {
+            const u32 r = c0 + k * 32 + lane;
+            if (r < e) {
+                const uint4 b = srec[r];
+                const u64 qg = (u64)b.x - a.y;
+                u64 d;
+                if (qg <= G && bb_candidate(a, b, fwd, G, G5, d) && d < bps[r] && (d < ld || (d == ld && r < lj))) { ld = d; lj = r; }
+            }
+        }
+        const u32 lcnt = min(RW, c0 - jl);
+#pragma unroll
+        for (u32 k = 0; k < RW / 32; k++) {
+            const u32 off = k * 32 + lane;
+            if (off < lcnt) {
+                const u32 l = c0 - 1 - off;
+                const uint4 b = srec[l];
+                u64 d;
+                if (bb_candidate(a, b, fwd, G, G5, d) && d < bps[l] && (d < ld || (d == ld && l < lj))) { ld = d; lj = l; }
+            }
+        }
+        bb_argmin(ld, lj);
+        bd = ld;
+        bj = lj;
+        rbase = c0 + RW;
+        ltop = c0 - lcnt;
+    } else {
+        // linear phase: the first 64 successors (two chunks)
+        u32 j0 = i + 1;
+        bool exhausted = false;
+        for (; j0 < lin_end && !exhausted; j0 += 32) {
+            const u32 j = j0 + lane;
+            bool inwin = false;
+            if (j < lin_end) {
+                const uint4 b = srec[j];
+                inwin = (u64)b.x <= bound;
+                u64 d;
+                if (inwin && bb_candidate(a, b, fwd, G, G5, d) && d < bps[j] && (d < bd || (d == bd && j < bj))) { bd = d; bj = j; }
+            }
+            exhausted = !__all_sync(full, inwin || j >= lin_end);
+        }
+        bb_argmin(bd, bj);
+        if (exhausted || lin_end >= e) return;
+        // first position in [jl, e) whose start is >= query_end: 33-ary search, 32 probes in flight per round (a binary
+        // search pays one L2 round trip per halving: ~19 dependent loads in a 500 k-mapping group)
+        u32 lo = jl, hi = e;
+        while (hi - lo > 32) {
+            const u32 width = hi - lo;
+            const u32 p = lo + (u32)(((u64)(lane + 1) * width) / 33);
+            const u32 below = __popc(__ballot_sync(full, srec[p].x < a.y)); // monotone: the first `below` probes are < query_end
+            const u32 nlo = below ? lo + (u32)(((u64)below * width) / 33) + 1 : lo;
+            const u32 nhi = below < 32 ? lo + (u32)(((u64)(below + 1) * width) / 33) : hi;
+            lo = nlo;
+            hi = nhi;
+        }
+        if (hi > lo) {
+            const u32 p = lo + lane;
+            const u32 below = __popc(__ballot_sync(full, p < hi && srec[p].x < a.y));
+            lo += below;
+        }
+        rbase = lo;
+        ltop = lo;
+    }
+    // Outward rounds.  The pruning test looks at the first candidate of a round only; candidates past the exact pruning
+    // point have d >= q_gap^2 > best d and cannot win, so reading a few more of them changes nothing.
+    for (u32 base = rbase; base < e; base += RW) { // right side, q_gap >= 0 non-decreasing
         const u64 qg0 = (u64)srec[base].x - a.y;
         if (qg0 > G || qg0 * qg0 > bd) break;
         u64 ld = NONE64;
@@ -442,7 +492,7 @@ __device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__
         bb_argmin(ld, lj);
         if (ld < bd || (ld == bd && lj < bj)) { bd = ld; bj = lj; }
     }
-    for (u32 top = c0; top > jl;) { // left side, overlap > 0 non-decreasing going left; round = [top-RW, top)
+    for (u32 top = ltop; top > jl;) { // left side, overlap > 0 non-decreasing going left; round = [top-RW, top)
         const u64 ov0 = (u64)a.y - srec[top - 1].x;
         if (ov0 > G5 || ov0 * ov0 > bd) break;
         const u32 cnt = min(RW, top - jl);
@@ -486,7 +536,7 @@ k_chain_resolve_warp(const Cand *__restrict__ cand, const uint4 *__restrict__ sr
         for (u32 base = s; base + 1 < e; base += 32) {
             const u32 ik = base + lane;
             Cand ck;
-            ck.d = 0; ck.j = NONE32;
+            ck.d = 0; ck.j = NONE32; ck.c0 = NONE32;
             u32 rk = 0;
             u64 bk = 0;
             if (ik + 1 < e) {
@@ -507,7 +557,7 @@ k_chain_resolve_warp(const Cand *__restrict__ cand, const uint4 *__restrict__ sr
                 else {
                     const u32 i = base + t;
                     const uint4 a = srec[i];
-                    bb_best_successor_warp(srec, bps, i, e, a, fwd, G, G5, wd, wj);
+                    bb_best_successor_warp(srec, bps, i, e, a, fwd, G, G5, wd, wj, __shfl_sync(full, ck.c0, t));
                 }
                 if (wj != NONE32) {
                     if (lane == 0) { bps[wj] = wd; root[wj] = ri; }
