@@ -392,6 +392,7 @@ __device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__
     const u32 lin_end = min(e, i + 1 + 64);
     const u32 jl = lin_end; // the outward scans cover [jl, e)
     u32 rbase, ltop;        // where the outward rounds continue
+    u64 rnext = NONE64, lnext = NONE64; // query_start of the first candidate of the next right / left round (NONE64: none)
     if (c0_hint != NONE32 && lin_end < e) {
         // The origin of the outward scans is known from the candidate pass (its linear phase is shorter: hence the max).
         // First round: the 64 nearest successors, RW candidates to the right of the origin and RW to its left, all loads
@@ -400,35 +401,39 @@ __device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__
         const u32 c0 = max(c0_hint, jl);
         u64 ld = NONE64;
         u32 lj = NONE32;
+        const u32 lcnt = min(RW, c0 - jl);
+        // every load of the round is issued before the first use (bps too: its address does not depend on the record)
+        uint4 rb[2 + 2 * (RW / 32)];
+        u64 rp[2 + 2 * (RW / 32)];
+        u32 rj[2 + 2 * (RW / 32)];
 #pragma unroll
         for (u32 k = 0; k < 2; k++) {
             const u32 j = i + 1 + k * 32 + lane;
-            if (j < lin_end) {
-                const uint4 b = srec[j];
-                u64 d;
-                if ((u64)b.x <= bound && bb_candidate(a, b, fwd, G, G5, d) && d < bps[j] && (d < ld || (d == ld && j < lj))) { ld = d; lj = j; }
-            }
+            rj[k] = j < lin_end ? j : NONE32;
         }
 #pragma unroll
         for (u32 k = 0; k < RW / 32; k++) {
             const u32 r = c0 + k * 32 + lane;
-            if (r < e) {
-                const uint4 b = srec[r];
-                const u64 qg = (u64)b.x - a.y;
-                u64 d;
-                if (qg <= G && bb_candidate(a, b, fwd, G, G5, d) && d < bps[r] && (d < ld || (d == ld && r < lj))) { ld = d; lj = r; }
-            }
-        }
-        const u32 lcnt = min(RW, c0 - jl);
-#pragma unroll
-        for (u32 k = 0; k < RW / 32; k++) {
+            rj[2 + k] = r < e ? r : NONE32;
             const u32 off = k * 32 + lane;
-            if (off < lcnt) {
-                const u32 l = c0 - 1 - off;
-                const uint4 b = srec[l];
-                u64 d;
-                if (bb_candidate(a, b, fwd, G, G5, d) && d < bps[l] && (d < ld || (d == ld && l < lj))) { ld = d; lj = l; }
-            }
+            rj[2 + RW / 32 + k] = off < lcnt ? c0 - 1 - off : NONE32;
+        }
+#pragma unroll
+        for (u32 k = 0; k < 2 + 2 * (RW / 32); k++) {
+            if (rj[k] != NONE32) { rb[k] = srec[rj[k]]; rp[k] = bps[rj[k]]; }
+        }
+        rnext = c0 + RW < e ? (u64)srec[c0 + RW].x : NONE64; // first candidate of the next right round (pruning test)
+        lnext = c0 - lcnt > jl ? (u64)srec[c0 - lcnt - 1].x : NONE64;
+#pragma unroll
+        for (u32 k = 0; k < 2 + 2 * (RW / 32); k++) {
+            if (rj[k] == NONE32) continue;
+            const uint4 b = rb[k];
+            bool inwin;
+            if (k < 2) inwin = (u64)b.x <= bound;                       // nearest successors: inside the window
+            else if (k < 2 + RW / 32) inwin = (u64)b.x - a.y <= G;      // right of the origin: q_gap <= G
+            else inwin = true;                                          // left of the origin: overlap, judged by the gap rule
+            u64 d;
+            if (inwin && bb_candidate(a, b, fwd, G, G5, d) && d < rp[k] && (d < ld || (d == ld && rj[k] < lj))) { ld = d; lj = rj[k]; }
         }
         bb_argmin(ld, lj);
         bd = ld;
@@ -471,31 +476,48 @@ __device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__
         }
         rbase = lo;
         ltop = lo;
+        rnext = rbase < e ? (u64)srec[rbase].x : NONE64;
+        lnext = ltop > jl ? (u64)srec[ltop - 1].x : NONE64;
     }
     // Outward rounds.  The pruning test looks at the first candidate of a round only; candidates past the exact pruning
     // point have d >= q_gap^2 > best d and cannot win, so reading a few more of them changes nothing.
     for (u32 base = rbase; base < e; base += RW) { // right side, q_gap >= 0 non-decreasing
-        const u64 qg0 = (u64)srec[base].x - a.y;
-        if (qg0 > G || qg0 * qg0 > bd) break;
+        const u64 qg0 = rnext - a.y;
+        if (rnext == NONE64 || qg0 > G || qg0 * qg0 > bd) break;
+        uint4 rb[RW / 32];
+        u64 rp[RW / 32];
+#pragma unroll
+        for (u32 k = 0; k < RW / 32; k++) {
+            const u32 r = base + k * 32 + lane;
+            if (r < e) { rb[k] = srec[r]; rp[k] = bps[r]; }
+        }
+        rnext = base + RW < e ? (u64)srec[base + RW].x : NONE64;
         u64 ld = NONE64;
         u32 lj = NONE32;
 #pragma unroll
         for (u32 k = 0; k < RW / 32; k++) {
             const u32 r = base + k * 32 + lane;
             if (r < e) {
-                const uint4 b = srec[r];
-                const u64 qg = (u64)b.x - a.y;
+                const u64 qg = (u64)rb[k].x - a.y;
                 u64 d;
-                if (qg <= G && bb_candidate(a, b, fwd, G, G5, d) && d < bps[r] && d < ld) { ld = d; lj = r; } // r ascends: ties keep the smaller j
+                if (qg <= G && bb_candidate(a, rb[k], fwd, G, G5, d) && d < rp[k] && d < ld) { ld = d; lj = r; } // r ascends: ties keep the smaller j
             }
         }
         bb_argmin(ld, lj);
         if (ld < bd || (ld == bd && lj < bj)) { bd = ld; bj = lj; }
     }
     for (u32 top = ltop; top > jl;) { // left side, overlap > 0 non-decreasing going left; round = [top-RW, top)
-        const u64 ov0 = (u64)a.y - srec[top - 1].x;
-        if (ov0 > G5 || ov0 * ov0 > bd) break;
+        const u64 ov0 = (u64)a.y - lnext;
+        if (lnext == NONE64 || ov0 > G5 || ov0 * ov0 > bd) break;
         const u32 cnt = min(RW, top - jl);
+        uint4 rb[RW / 32];
+        u64 rp[RW / 32];
+#pragma unroll
+        for (u32 k = 0; k < RW / 32; k++) {
+            const u32 off = k * 32 + lane;
+            if (off < cnt) { rb[k] = srec[top - 1 - off]; rp[k] = bps[top - 1 - off]; }
+        }
+        lnext = top - cnt > jl ? (u64)srec[top - cnt - 1].x : NONE64;
         u64 ld = NONE64;
         u32 lj = NONE32;
 #pragma unroll
@@ -503,9 +525,8 @@ __device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__
             const u32 off = k * 32 + lane;
             if (off < cnt) {
                 const u32 l = top - 1 - off;
-                const uint4 b = srec[l];
                 u64 d;
-                if (bb_candidate(a, b, fwd, G, G5, d) && d < bps[l] && (d < ld || (d == ld && l < lj))) { ld = d; lj = l; }
+                if (bb_candidate(a, rb[k], fwd, G, G5, d) && d < rp[k] && (d < ld || (d == ld && l < lj))) { ld = d; lj = l; }
             }
         }
         bb_argmin(ld, lj);
