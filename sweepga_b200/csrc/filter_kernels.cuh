@@ -294,6 +294,7 @@ k_chain_candidates(const uint4 *__restrict__ srec, const u64 *__restrict__ skey,
 }
 
 // P2: one thread per group that has at least one candidate; lanes refill from the work list as they finish.
+constexpr u32 RES_SMALL = 16;
 __global__ void __launch_bounds__(128)
 k_chain_resolve(const Cand *__restrict__ cand, const uint4 *__restrict__ srec, const u64 *__restrict__ skey,
                 const u32 *__restrict__ gstart, u32 n_groups, u32 n_m, const u32 *__restrict__ work, const u32 *__restrict__ n_work_ptr,
@@ -322,10 +323,46 @@ k_chain_resolve(const Cand *__restrict__ cand, const uint4 *__restrict__ srec, c
                     e = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
                     fwd = ((skey[i] >> cb) & 1) == 0;
                     active = true;
-                    c_cur = cand[i];
-                    c_next = (i + 1 < e) ? cand[i + 1] : Cand{0, NONE32, 0};
-                    b_cur = (c_cur.j != NONE32) ? bps[c_cur.j] : 0;
-                    r_cur = i; // the first position of a group has no predecessor
+                    const u32 n = e - i;
+                    if (n <= RES_SMALL) {
+                        // The whole state of a group is local to it (candidates point inside the group; bps starts at
+                        // "none" and root at the own position), so a small group is resolved from ONE burst of loads:
+                        // its candidates.  The walk below runs on per-thread copies; only `root` is written back.
+                        Cand cs[RES_SMALL];
+                        u32 rt[RES_SMALL];
+                        u64 bp[RES_SMALL];
+#pragma unroll
+                        for (u32 k = 0; k < RES_SMALL; k++) {
+                            if (k < n) cs[k] = cand[i + k];
+                            rt[k] = i + k;
+                            bp[k] = NONE64;
+                        }
+                        u32 k = 0;
+                        bool blocked = false;
+                        for (; k + 1 < n; k++) {
+                            const Cand c = cs[k];
+                            if (c.j == NONE32) continue;
+                            const u32 jj = c.j - i;
+                            if (c.d < bp[jj]) { bp[jj] = c.d; rt[jj] = rt[k]; }
+                            else { blocked = true; break; } // needs the arg-min over the eligible candidates: generic walk
+                        }
+                        if (!blocked) {
+                            for (u32 q = 0; q < n; q++) root[i + q] = rt[q];
+                            active = false;
+                        } else { // publish the state reached so far; the generic walk continues at step k
+                            for (u32 q = 0; q < n; q++) { bps[i + q] = bp[q]; root[i + q] = rt[q]; }
+                            c_cur = cs[k];
+                            c_next = (k + 1 < n) ? cs[k + 1] : Cand{0, NONE32, 0};
+                            b_cur = bp[c_cur.j - i];
+                            r_cur = rt[k];
+                            i += k;
+                        }
+                    } else {
+                        c_cur = cand[i];
+                        c_next = (i + 1 < e) ? cand[i + 1] : Cand{0, NONE32, 0};
+                        b_cur = (c_cur.j != NONE32) ? bps[c_cur.j] : 0;
+                        r_cur = i; // the first position of a group has no predecessor
+                    }
                 }
             }
         }
