@@ -194,12 +194,6 @@ __global__ void __launch_bounds__(256) k_count_status(u32 n, const u8 *__restric
 //   P3 k_chain_heads / k_chain_members  flat: bounding boxes and sums per chain (segmented warp
 //                          reduction, then one atomic set per run).
 // ---------------------------------------------------------------------------------------------
-struct ChainSparse { // indexed by the sorted position of the chain head
-    u32 *qmin, *qmax, *tmin, *tmax;
-    u64 *sum_matches, *sum_block;
-    u32 *group;       // group index of the chain (head slot)
-    u32 *grp_minidx;  // per GROUP: min original index over its members (first appearance of the group in M)
-};
 struct Cand { // unconstrained best successor of a position
     u64 d;    // squared gap distance
     u32 j;    // sorted position of the successor, NONE32 if the window holds no valid candidate
@@ -649,62 +643,54 @@ k_chain_work_estimate(const uint4 *__restrict__ srec, const u32 *__restrict__ gs
     if (lane_id() == 0 && est) atomicAdd((unsigned long long *)&ctr[C_WORK], (unsigned long long)est);
 }
 
-// P3a: chain heads seed their slot with their own record; every position feeds its group's min original index.
+// P3: per-chain aggregates (paf_filter.rs:875-894) into the dense chain table: bounding box by atomicMin / atomicMax, sums
+// by atomicAdd; runs of one chain inside a warp are reduced first (one set of atomics per run).  Every position also feeds
+// its group's min original index (the first appearance of the group in the input).  The table rows are pre-set to
+// (max, 0, max, 0, 0, 0).
+struct ChainDense {
+    u32 *qmin, *qmax, *tmin, *tmax; // = ChainTable qs / qe / ts / te
+    u64 *sum_matches, *sum_block;
+};
 __global__ void __launch_bounds__(256)
-k_chain_heads(const uint4 *__restrict__ srec, const uint2 *__restrict__ srec2, const u32 *__restrict__ sidx,
-              const u32 *__restrict__ gid, const u32 *__restrict__ root, u32 n_m, ChainSparse cs) {
+k_chain_aggregate(const uint4 *__restrict__ srec, const uint2 *__restrict__ srec2, const u32 *__restrict__ sidx, const u32 *__restrict__ gid,
+                  const u32 *__restrict__ root, const u32 *__restrict__ chain_of_pos, u32 n_m, ChainDense cd, u32 *__restrict__ grp_minidx) {
     const u32 full = 0xFFFFFFFFu;
+    const u32 lane = lane_id();
     const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
     const bool ok = p < n_m;
-    u32 g = NONE32, idx = NONE32;
+    u32 g = NONE32, idx = NONE32, ci = 0x80000000u | lane; // lanes past the end never match anything
+    uint4 a = make_uint4(NONE32, 0, NONE32, 0);
+    uint2 m = make_uint2(0, 0);
     if (ok) {
         g = gid[p];
         idx = sidx[p];
-        if (root[p] == p) {
-            const uint4 a = srec[p];
-            const uint2 m = srec2[p];
-            cs.qmin[p] = a.x; cs.qmax[p] = a.y; cs.tmin[p] = a.z; cs.tmax[p] = a.w;
-            cs.sum_matches[p] = m.y; cs.sum_block[p] = m.x; cs.group[p] = g;
-        }
+        ci = chain_of_pos[root[p]];
+        a = srec[p];
+        m = srec2[p];
     }
     // groups are contiguous: usually the whole warp shares one
     const u32 g0 = __shfl_sync(full, g, 0);
     if (__all_sync(full, g == g0)) {
         const u32 mn = __reduce_min_sync(full, idx);
-        if (lane_id() == 0 && g0 != NONE32) atomicMin(&cs.grp_minidx[g0], mn);
+        if (lane == 0 && g0 != NONE32) atomicMin(&grp_minidx[g0], mn);
     } else if (ok) {
-        atomicMin(&cs.grp_minidx[g], idx);
+        atomicMin(&grp_minidx[g], idx);
     }
-}
-
-// P3b: members fold into their head's slot (paf_filter.rs:875-894); runs of equal root are reduced in the warp first.
-__global__ void __launch_bounds__(256)
-k_chain_members(const uint4 *__restrict__ srec, const uint2 *__restrict__ srec2, const u32 *__restrict__ root, u32 n_m, ChainSparse cs) {
-    const u32 full = 0xFFFFFFFFu;
-    const u32 lane = lane_id();
-    const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool ok = p < n_m;
-    const u32 r = ok ? root[p] : NONE32;
-    const bool member = ok && r != p;
-    if (!__any_sync(full, member)) return;
-    uint4 a = member ? srec[p] : make_uint4(NONE32, 0, NONE32, 0);
-    uint2 m = member ? srec2[p] : make_uint2(0, 0);
     const u64 smv = m.y, sbk = m.x;
-    const u32 key = member ? r : (0x80000000u | lane) ; // non-members never match anything useful
-    const u32 peers = __match_any_sync(full, key);
+    const u32 peers = __match_any_sync(full, ci);
     const u32 leader = __ffs(peers) - 1;
-    if (member && __popc(peers) == 1) {
-        atomicMin(&cs.qmin[r], a.x); atomicMax(&cs.qmax[r], a.y);
-        atomicMin(&cs.tmin[r], a.z); atomicMax(&cs.tmax[r], a.w);
-        atomicAdd((unsigned long long *)&cs.sum_matches[r], (unsigned long long)smv);
-        atomicAdd((unsigned long long *)&cs.sum_block[r], (unsigned long long)sbk);
+    if (ok && __popc(peers) == 1) {
+        atomicMin(&cd.qmin[ci], a.x); atomicMax(&cd.qmax[ci], a.y);
+        atomicMin(&cd.tmin[ci], a.z); atomicMax(&cd.tmax[ci], a.w);
+        atomicAdd((unsigned long long *)&cd.sum_matches[ci], (unsigned long long)smv);
+        atomicAdd((unsigned long long *)&cd.sum_block[ci], (unsigned long long)sbk);
     }
-    u32 todo = __ballot_sync(full, member && __popc(peers) > 1 && lane == leader);
+    u32 todo = __ballot_sync(full, ok && __popc(peers) > 1 && lane == leader);
     while (todo) {
         const u32 Ld = __ffs(todo) - 1;
         todo &= todo - 1;
         const u32 pm = __shfl_sync(full, peers, Ld);
-        const u32 rr = __shfl_sync(full, r, Ld);
+        const u32 cc = __shfl_sync(full, ci, Ld);
         const bool in = (pm >> lane) & 1;
         const u32 vqmin = __reduce_min_sync(full, in ? a.x : NONE32), vqmax = __reduce_max_sync(full, in ? a.y : 0u);
         const u32 vtmin = __reduce_min_sync(full, in ? a.z : NONE32), vtmax = __reduce_max_sync(full, in ? a.w : 0u);
@@ -715,10 +701,10 @@ k_chain_members(const uint4 *__restrict__ srec, const uint2 *__restrict__ srec2,
             vsb += __shfl_down_sync(full, vsb, o);
         }
         if (lane == 0) {
-            atomicMin(&cs.qmin[rr], vqmin); atomicMax(&cs.qmax[rr], vqmax);
-            atomicMin(&cs.tmin[rr], vtmin); atomicMax(&cs.tmax[rr], vtmax);
-            atomicAdd((unsigned long long *)&cs.sum_matches[rr], (unsigned long long)vsm);
-            atomicAdd((unsigned long long *)&cs.sum_block[rr], (unsigned long long)vsb);
+            atomicMin(&cd.qmin[cc], vqmin); atomicMax(&cd.qmax[cc], vqmax);
+            atomicMin(&cd.tmin[cc], vtmin); atomicMax(&cd.tmax[cc], vtmax);
+            atomicAdd((unsigned long long *)&cd.sum_matches[cc], (unsigned long long)vsm);
+            atomicAdd((unsigned long long *)&cd.sum_block[cc], (unsigned long long)vsb);
         }
     }
 }

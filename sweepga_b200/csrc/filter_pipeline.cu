@@ -524,16 +524,13 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     u64 *bps = A.take<u64>(n_m);
     u32 *root = A.take<u32>(n_m);
     Cand *cand = A.take<Cand>(n_m);
-    ChainSparse cs;
-    cs.qmin = A.take<u32>(n_m); cs.qmax = A.take<u32>(n_m); cs.tmin = A.take<u32>(n_m); cs.tmax = A.take<u32>(n_m);
-    cs.sum_matches = A.take<u64>(n_m); cs.sum_block = A.take<u64>(n_m); cs.group = A.take<u32>(n_m);
-    cs.grp_minidx = A.take<u32>(n_groups);
+    u32 *grp_minidx = A.take<u32>(n_groups); // per GROUP: min original index over its members (first appearance of the group)
     u8 *grp_has_cand = A.take<u8>(n_groups);
     u32 *work = A.take<u32>(n_groups), *work_big = A.take<u32>(n_groups);
     u32 *bb_ctr = A.take<u32>(4); // [0] #ordinary groups, [1] their work counter, [2] #large/dense groups, [3] their work counter
     SWG_CUDA(cudaMemsetAsync(bb_ctr, 0, 4 * sizeof(u32), st));
     SWG_CUDA(cudaMemsetAsync(grp_has_cand, 0, n_groups, st));
-    SWG_CUDA(cudaMemsetAsync(cs.grp_minidx, 0xFF, sizeof(u32) * (size_t)n_groups, st));
+    SWG_CUDA(cudaMemsetAsync(grp_minidx, 0xFF, sizeof(u32) * (size_t)n_groups, st));
     {
         k_chain_candidates<<<cdiv(n_m, 256), 256, 0, st>>>(srec, skey, gid, gstart, n_groups, n_m, gshift, cfg.scaffold_gap, cand, bps, root, grp_has_cand);
         lc.n++;
@@ -562,24 +559,13 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     }
     stage_mark(c, "ch_aggregate");
     // ---- K4: dense chain table + mass/identity filter + order key (A,B) ----------------------------
-    // upper bound on chains is n_m; the table is sized after counting heads.  The count only needs `root`, so it runs
-    // before the aggregate kernels and the host reads it (event, not a stream drain) while they execute.
+    // upper bound on chains is n_m; the table is sized after counting heads
     u32 *chain_of_pos = A.take<u32>(n_m);
     u32 *head_pos = A.take<u32>(n_m); // compacted head positions (C of them)
     u32 *d_nch = d_tot + 2;
     scan_apply([=] __device__(u32 p) -> u32 { return root[p] == p ? 1u : 0u; },
                [=] __device__(u32 p, u32 ex, u32 v) { if (v) { chain_of_pos[p] = ex; head_pos[ex] = p; } }, n_m, bsum, d_nch, st, lc);
-    u32 C;
-    {
-        u32 *h = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
-        SWG_CUDA(cudaMemcpyAsync(h, d_nch, sizeof(u32), cudaMemcpyDeviceToHost, st));
-        SWG_CUDA(cudaEventRecord(c->ev_ctr, st));
-        k_chain_heads<<<cdiv(n_m, 256), 256, 0, st>>>(srec, srec2, sidx, gid, root, n_m, cs);
-        k_chain_members<<<cdiv(n_m, 256), 256, 0, st>>>(srec, srec2, root, n_m, cs);
-        lc.n += 2;
-        SWG_CUDA(cudaEventSynchronize(c->ev_ctr));
-        C = *h;
-    }
+    const u32 C = read_u32(c, d_nch);
     stage_mark(c, "chain_table");
     S.n_chains = C;
     ChainTable ct;
@@ -587,6 +573,18 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     ct.qs = A.take<u32>(C); ct.qe = A.take<u32>(C); ct.ts = A.take<u32>(C); ct.te = A.take<u32>(C);
     ct.wid = A.take<double>(C); ct.pass = A.take<u8>(C); ct.k = A.take<u32>(C);
     SWG_CUDA(cudaMemsetAsync(ct.k, 0, sizeof(u32) * (size_t)C, st));
+    // per-chain aggregates straight into the dense table (bounding box in ct.qs / qe / ts / te)
+    ChainDense cd;
+    cd.qmin = ct.qs; cd.qmax = ct.qe; cd.tmin = ct.ts; cd.tmax = ct.te;
+    cd.sum_matches = A.take<u64>(C); cd.sum_block = A.take<u64>(C);
+    SWG_CUDA(cudaMemsetAsync(cd.qmin, 0xFF, sizeof(u32) * (size_t)C, st));
+    SWG_CUDA(cudaMemsetAsync(cd.tmin, 0xFF, sizeof(u32) * (size_t)C, st));
+    SWG_CUDA(cudaMemsetAsync(cd.qmax, 0, sizeof(u32) * (size_t)C, st));
+    SWG_CUDA(cudaMemsetAsync(cd.tmax, 0, sizeof(u32) * (size_t)C, st));
+    SWG_CUDA(cudaMemsetAsync(cd.sum_matches, 0, sizeof(u64) * (size_t)C, st));
+    SWG_CUDA(cudaMemsetAsync(cd.sum_block, 0, sizeof(u64) * (size_t)C, st));
+    k_chain_aggregate<<<cdiv(n_m, 256), 256, 0, st>>>(srec, srec2, sidx, gid, root, chain_of_pos, n_m, cd, grp_minidx);
+    lc.n++;
     const int nb = bits_for(N);
     if (2 * nb > 63) throw RangeError{"too many records for the chain order key"};
     u64 *okey_all = A.take<u64>(C);
@@ -600,8 +598,8 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             u64 k = skey[p] >> gshift;
             u8 fwd = (k & 1) == 0;
             u32 tid = (u32)(k >> 1) & seqmask, qid = (u32)(k >> (1 + sb)) & seqmask;
-            u32 qmin = cs.qmin[p], qmax = cs.qmax[p], tmin = cs.tmin[p], tmax = cs.tmax[p];
-            u64 sm = cs.sum_matches[p], sbk = cs.sum_block[p];
+            u32 qmin = cd.qmin[ci], qmax = cd.qmax[ci], tmin = cd.tmin[ci], tmax = cd.tmax[ci];
+            u64 sm = cd.sum_matches[ci], sbk = cd.sum_block[ci];
             u64 total = (u64)(qmax - qmin);                         // paf_filter.rs:896
             u64 gap = total > sbk ? total - sbk : 0;                // saturating_sub, :901
             double lg = gap > 0 ? fmax(log((double)gap), 0.0) : 0.0; // :902-906
@@ -609,12 +607,11 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             double wid = eff > 0.0 ? __ddiv_rn((double)sm, eff) : 0.0;
             bool pass = total >= min_len && wid >= min_sid;         // :449-455
             ct.qid[ci] = qid; ct.tid[ci] = tid; ct.fwd[ci] = fwd;
-            ct.qs[ci] = qmin; ct.qe[ci] = qmax; ct.ts[ci] = tmin; ct.te[ci] = tmax;
-            ct.wid[ci] = wid; ct.pass[ci] = pass ? 1 : 0;
+            ct.wid[ci] = wid; ct.pass[ci] = pass ? 1 : 0; // ct.qs / qe / ts / te already hold the bounding box
             bool zero = false;
             if (pass) {
                 u32 Aidx = hash_lookup(hk, hv, hmask, ((u64)in.P[qid] << 32) | in.P[tid]);
-                okey_all[ci] = ((u64)Aidx << nb) | cs.grp_minidx[cs.group[p]];
+                okey_all[ci] = ((u64)Aidx << nb) | grp_minidx[gid[p]];
                 zero = qmax == qmin || tmax == tmin;
             }
             u32 am = __activemask();
