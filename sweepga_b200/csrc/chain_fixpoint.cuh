@@ -1,0 +1,328 @@
+// chain_fixpoint.cuh — best-buddy chaining of HUGE (query,target,strand) groups as a parallel fixed-point iteration.
+//
+// The reference (src/paf_filter.rs:784-851) walks the positions i of a group in order; position i picks the successor j
+// that minimises d(i,j) among the candidates with d(i,j) < best_pred_score[j], and best_pred_score[j] is the d of the LAST
+// position before i that picked j (every successful pick lowers it).  So
+//
+//     pick(i) = first arg-min_j { d(i,j) : d(i,j) < B(i,j) },   B(i,j) = min { d(i',j) : i' < i, pick(i') = j }      (*)
+//
+// and pick(i) depends only on the picks of smaller positions: (*) has exactly one solution, the reference's.  One thread
+// or warp walking a 25 M-mapping centromeric pile pays a memory round trip per step (k_chain_resolve_warp: ~1.3 us per
+// mapping); here ALL positions are evaluated against a snapshot of the picks and the evaluation is repeated until nothing
+// changes.  By induction on i the positions below the first wrong one stay correct and that one becomes correct in the
+// next round, so the iteration ends in the reference's picks; measured on the configs[4] piles it needs 6 rounds for a
+// 100 k group and 14 for a 500 k group, and the number of positions that have to be re-evaluated shrinks geometrically.
+//
+// A round:
+//   1. snapshot: picker lists per successor j (CSR: count, scan, fill) and minpd[j] = smallest d over all pickers of j
+//   2. k_fx_check (thread per position): position i must be re-evaluated iff its pick is now blocked (an earlier picker
+//      of the same j with d' <= d) or one of the candidates that rank BEFORE its pick — X(i), all of them ineligible when
+//      the pick was made, remembered explicitly — has become eligible.  This test is exact: a position whose pick stands
+//      and whose X(i) is still blocked would pick the same j again.
+//   3. k_fx_recompute (warp per listed position): the pruned window search of the sequential walk
+//      (bb_best_successor_warp) with eligibility against the snapshot, then a second pruned pass that collects X(i).
+// The first round starts from k_chain_candidates' unconstrained arg-min (X(i) is empty there by definition).
+// After the last round pred[j] = the last picker of j, roots by pointer jumping (union_find.rs:25-41: the root of a set is
+// its head), results scattered back to the sorted positions.  Everything runs in the compact index space k of the positions
+// that belong to huge groups (groups stay contiguous there, so successor offsets carry over).
+#pragma once
+
+namespace swg {
+
+struct t_fx_init; struct t_fx_count; struct t_fx_fill; struct t_fx_pred; struct t_fx_jump; struct t_fx_scatter;
+
+constexpr u32 FX_XCAP = 64;   // blocked candidates remembered per position; a position with more is re-evaluated every round
+constexpr u8 FX_XOVER = 0xFF; // xcnt value of such a position
+constexpr u32 FX_REV = 0x80000000u; // gend bit: the group is a '-' strand group
+
+struct FxArrays {
+    u32 n;             // positions in huge groups
+    uint4 *rec;        // (qs, qe, ts, te)
+    u32 *gend;         // end of the position's group (k-space) | FX_REV
+    u32 *c0;           // origin of the outward scans from the candidate pass, NONE32 if its window ended in the linear phase
+    u32 *pick;         // current pick (k-space), NONE32 = none
+    u64 *pd;           // d of the current pick
+    u32 *cnt, *off;    // picker lists: off[j] .. off[j+1]
+    u64 *minpd;        // smallest d over all pickers of j (NONE64: nobody picks j)
+    u32 *li;           // picker position
+    u64 *ld;           // picker d
+    u32 *xoff;         // X(i) lives at pool[xoff .. xoff + xcnt)
+    u8 *xcnt, *xcap;
+    u32 *pool, *pool_top;
+    u32 pool_cap;
+    u32 *list;         // positions to re-evaluate this round
+    u32 *ctrs;         // [0] list length, [1] picks changed this round, [2] recompute work counter, [3] slots refused (pool full)
+};
+
+// smallest d over the pickers of j that precede position i, compared with d: true iff d < B(i,j)
+__device__ __forceinline__ bool fx_eligible(const FxArrays &f, u32 i, u32 j, u64 d) {
+    const u32 a = f.off[j], b = f.off[j + 1];
+    for (u32 p = a; p < b; p++)
+        if (f.li[p] < i && f.ld[p] <= d) return false;
+    return true;
+}
+struct FxExtra {
+    FxArrays f;
+    u32 i;
+    __device__ __forceinline__ bool operator()(u32 j, u64 d) const { return fx_eligible(f, i, j, d); }
+};
+
+// step 2: does position k have to be re-evaluated against the new snapshot?
+__global__ void __launch_bounds__(256) k_fx_check(FxArrays f, u64 G) {
+    const u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    bool need = false;
+    if (k < f.n) {
+        const u8 xc = f.xcnt[k];
+        const u32 j = f.pick[k];
+        if (xc == FX_XOVER) need = true;
+        else {
+            if (j != NONE32 && f.off[j + 1] - f.off[j] > 1) need = !fx_eligible(f, k, j, f.pd[k]);
+            if (!need && xc) {
+                const uint4 a = f.rec[k];
+                const bool fwd = !(f.gend[k] & FX_REV);
+                const u32 *x = f.pool + f.xoff[k];
+                for (u32 q = 0; q < xc && !need; q++) {
+                    const u32 jx = x[q];
+                    u64 d;
+                    if (bb_candidate(a, f.rec[jx], fwd, G, G / 5, d)) need = d < f.minpd[jx] || fx_eligible(f, k, jx, d);
+                }
+            }
+        }
+    }
+    const u32 m = __ballot_sync(0xFFFFFFFFu, need);
+    if (m) {
+        u32 base = 0;
+        const u32 leader = __ffs(m) - 1;
+        if (lane_id() == leader) base = atomicAdd(&f.ctrs[0], (u32)__popc(m));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (need) f.list[base + __popc(m & lanemask_lt())] = k;
+    }
+}
+
+// X(i) = the valid candidates that rank before (bd, bj): appended to xs[0 .. FX_XCAP), returns how many there are
+__device__ __forceinline__ u32 fx_collect_chunk(const uint4 &a, bool fwd, u64 G, u64 G5, u64 bd, u32 bj, u32 j, bool inrange, const uint4 &b,
+                                                u32 *xs, u32 xn) {
+    u64 d;
+    const bool mem = inrange && bb_candidate(a, b, fwd, G, G5, d) && (d < bd || (d == bd && j < bj));
+    const u32 m = __ballot_sync(0xFFFFFFFFu, mem);
+    if (mem) {
+        const u32 o = xn + __popc(m & lanemask_lt());
+        if (o < FX_XCAP) xs[o] = j;
+    }
+    return xn + __popc(m);
+}
+__device__ __forceinline__ u32 fx_collect_blocked(const uint4 *__restrict__ rec, u32 i, u32 e, const uint4 &a, bool fwd, u64 G, u64 G5,
+                                                  u64 bd, u32 bj, u32 c0, u32 *xs) {
+    const u32 full = 0xFFFFFFFFu;
+    const u32 lane = lane_id();
+    u32 xn = 0;
+    // the nearest successors, evaluated one by one like the searches do (their origin may lie in here)
+    const u32 lin_end = min(e, i + 1 + 64);
+    const u64 bound = (u64)a.y + G;
+    for (u32 j0 = i + 1; j0 < lin_end; j0 += 32) {
+        const u32 j = j0 + lane;
+        uint4 b = make_uint4(0, 0, 0, 0);
+        bool in = false;
+        if (j < lin_end) { b = rec[j]; in = (u64)b.x <= bound; }
+        xn = fx_collect_chunk(a, fwd, G, G5, bd, bj, j, in, b, xs, xn);
+    }
+    if (c0 == NONE32 || lin_end >= e) return xn; // the window ended in there (k_chain_candidates' linear phase saw its end)
+    c0 = max(c0, lin_end);
+    for (u32 r0 = c0; r0 < e; r0 += 32) { // right of the origin: q_gap = qs - qe >= 0 grows; d >= q_gap^2
+        const u32 r = r0 + lane;
+        uint4 b = make_uint4(0, 0, 0, 0);
+        bool in = false;
+        if (r < e) {
+            b = rec[r];
+            const u64 qg = (u64)b.x - a.y;
+            in = qg <= G && qg * qg <= bd;
+        }
+        xn = fx_collect_chunk(a, fwd, G, G5, bd, bj, r, in, b, xs, xn);
+        if (!__shfl_sync(full, (int)in, 31)) break; // monotone: once the last lane is out, so is everything further right
+    }
+    for (u32 top = c0; top > lin_end;) { // left of the origin: overlap = qe - qs > 0 grows going left
+        const u32 cnt = min(32u, top - lin_end);
+        uint4 b = make_uint4(0, 0, 0, 0);
+        bool in = false;
+        const u32 l = top - 1 - lane;
+        if (lane < cnt) {
+            b = rec[l];
+            const u64 ov = (u64)a.y - b.x;
+            in = ov <= G5 && ov * ov <= bd;
+        }
+        xn = fx_collect_chunk(a, fwd, G, G5, bd, bj, l, in, b, xs, xn);
+        if (cnt < 32 || !__shfl_sync(full, (int)in, 31)) break;
+        top -= 32;
+    }
+    return xn;
+}
+
+// step 3: one warp per listed position
+__global__ void __launch_bounds__(128) k_fx_recompute(FxArrays f, u64 G) {
+    __shared__ u32 s_x[4][FX_XCAP];
+    const u32 full = 0xFFFFFFFFu;
+    const u32 lane = lane_id();
+    const u64 G5 = G / 5;
+    u32 *xs = s_x[threadIdx.x >> 5];
+    const u32 n_list = f.ctrs[0];
+    while (true) {
+        u32 w = 0;
+        if (lane == 0) w = atomicAdd(&f.ctrs[2], 1u);
+        w = __shfl_sync(full, w, 0);
+        if (w >= n_list) break;
+        const u32 i = f.list[w];
+        const uint4 a = f.rec[i];
+        const u32 ge = f.gend[i];
+        const u32 e = ge & ~FX_REV;
+        const bool fwd = !(ge & FX_REV);
+        const u32 c0 = f.c0[i];
+        u64 bd;
+        u32 bj;
+        FxExtra ex{f, i};
+        bb_best_successor_warp(f.rec, f.minpd, i, e, a, fwd, G, G5, bd, bj, c0, ex);
+        __syncwarp();
+        const u32 xn = fx_collect_blocked(f.rec, i, e, a, fwd, G, G5, bd, bj, c0, xs);
+        __syncwarp();
+        u32 xo = 0;
+        u8 xc = FX_XOVER;
+        if (lane == 0) {
+            if (bj != f.pick[i]) atomicAdd(&f.ctrs[1], 1u);
+            f.pick[i] = bj;
+            f.pd[i] = bd;
+            if (xn <= FX_XCAP) {
+                if (xn <= f.xcap[i]) { xo = f.xoff[i]; xc = (u8)xn; }
+                else { // a new slot (the old one is abandoned): capacity rounded up to a power of two >= 4, so X(i) can grow in place
+                    const u32 cap = xn <= 4 ? 4u : 1u << (32 - __clz(xn - 1));
+                    xo = atomicAdd(f.pool_top, cap);
+                    if (xo <= f.pool_cap && cap <= f.pool_cap - xo) { xc = (u8)xn; f.xoff[i] = xo; f.xcap[i] = (u8)cap; }
+                    else atomicAdd(&f.ctrs[3], 1u);
+                }
+            }
+            f.xcnt[i] = xc;
+        }
+        xo = __shfl_sync(full, xo, 0);
+        xc = (u8)__shfl_sync(full, (u32)xc, 0);
+        if (xc != FX_XOVER)
+            for (u32 q = lane; q < xn; q += 32) f.pool[xo + q] = xs[q];
+        __syncwarp();
+    }
+}
+
+// Resolve the huge groups.  hpos[k] = sorted position of k (ascending); gid / gstart / n_groups describe the groups in
+// sorted-position space; cand = k_chain_candidates' result there.  Writes root[] for the positions of huge groups.
+static void chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *srec, const u64 *skey, int cb, const u32 *gid, const u32 *gstart,
+                           u32 n_groups, u32 n_m, const Cand *cand, u64 G, u32 *root, u32 *bsum) {
+    cudaStream_t st = c->stream;
+    LaunchCounter &lc = c->lc;
+    Arena &A = c->arena;
+    static const bool verbose = getenv("SWG_STAGE_TIMING") != nullptr;
+    FxArrays f;
+    f.n = n_h;
+    f.rec = A.take<uint4>(n_h);
+    f.gend = A.take<u32>(n_h);
+    f.c0 = A.take<u32>(n_h);
+    f.pick = A.take<u32>(n_h);
+    f.pd = A.take<u64>(n_h);
+    f.cnt = A.take<u32>(n_h);
+    f.off = A.take<u32>((size_t)n_h + 1);
+    f.minpd = A.take<u64>(n_h);
+    f.li = A.take<u32>(n_h);
+    f.ld = A.take<u64>(n_h);
+    f.xoff = A.take<u32>(n_h);
+    f.xcnt = A.take<u8>(n_h);
+    f.xcap = A.take<u8>(n_h);
+    f.pool_cap = (u32)std::min<u64>((u64)n_h * 24 + 4096, 0xF0000000ull);
+    f.pool = A.take<u32>(f.pool_cap);
+    f.pool_top = A.take<u32>(1);
+    f.list = A.take<u32>(n_h);
+    f.ctrs = A.take<u32>(4);
+    u32 *scan_tot = A.take<u32>(1);
+    SWG_CUDA(cudaMemsetAsync(f.xcnt, 0, n_h, st));
+    SWG_CUDA(cudaMemsetAsync(f.xcap, 0, n_h, st));
+    SWG_CUDA(cudaMemsetAsync(f.pool_top, 0, sizeof(u32), st));
+    {
+        const FxArrays g = f;
+        launch_for<t_fx_init>(n_h, st, lc, [=] __device__(u32 k) {
+            const u32 p = hpos[k];
+            const u32 gr = gid[p];
+            const u32 e = (gr + 1 < n_groups) ? gstart[gr + 1] : n_m;
+            const bool fwd = ((skey[p] >> cb) & 1) == 0;
+            g.rec[k] = srec[p];
+            g.gend[k] = (k + (e - p)) | (fwd ? 0u : FX_REV);
+            const Cand cd = cand[p];
+            g.pick[k] = cd.j == NONE32 ? NONE32 : k + (cd.j - p);
+            g.pd[k] = cd.d;
+            g.c0[k] = cd.c0 == NONE32 ? NONE32 : k + (cd.c0 - p);
+        });
+    }
+    u32 *h = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
+    int rounds = 0;
+    u64 total_recomputed = 0;
+    auto t_round = std::chrono::steady_clock::now();
+    while (true) {
+        // 1. snapshot of the picks
+        const FxArrays g = f;
+        SWG_CUDA(cudaMemsetAsync(f.cnt, 0, sizeof(u32) * (size_t)n_h, st));
+        SWG_CUDA(cudaMemsetAsync(f.minpd, 0xFF, sizeof(u64) * (size_t)n_h, st));
+        SWG_CUDA(cudaMemsetAsync(f.ctrs, 0, 4 * sizeof(u32), st));
+        launch_for<t_fx_count>(n_h, st, lc, [=] __device__(u32 k) {
+            const u32 j = g.pick[k];
+            if (j != NONE32) {
+                atomicAdd(&g.cnt[j], 1u);
+                atomicMin((unsigned long long *)&g.minpd[j], (unsigned long long)g.pd[k]);
+            }
+        });
+        scan_apply([=] __device__(u32 k) -> u32 { return g.cnt[k]; },
+                   [=] __device__(u32 k, u32 ex, u32 v) {
+                       g.off[k] = ex;
+                       if (k + 1 == g.n) g.off[g.n] = ex + v;
+                   },
+                   n_h, bsum, scan_tot, st, lc);
+        launch_for<t_fx_fill>(n_h, st, lc, [=] __device__(u32 k) {
+            const u32 j = g.pick[k];
+            if (j != NONE32) {
+                const u32 slot = g.off[j] + atomicSub(&g.cnt[j], 1u) - 1;
+                g.li[slot] = k;
+                g.ld[slot] = g.pd[k];
+            }
+        });
+        // 2. + 3.
+        k_fx_check<<<cdiv(n_h, 256), 256, 0, st>>>(f, G);
+        k_fx_recompute<<<(u32)c->sm_count * 8, 128, 0, st>>>(f, G);
+        lc.n += 2;
+        SWG_CUDA(cudaMemcpyAsync(h, f.ctrs, 4 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+        if (verbose) SWG_CUDA(cudaMemcpyAsync(h + 4, f.pool_top, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        SWG_CUDA(cudaStreamSynchronize(st));
+        rounds++;
+        total_recomputed += h[0];
+        if (verbose) {
+            const auto t1 = std::chrono::steady_clock::now();
+            fprintf(stderr, "[swg fixpoint] round %d: %u of %u positions re-evaluated, %u picks changed, %.2f ms, pool %u of %u (%u refused)\n", rounds,
+                    h[0], n_h, h[1], std::chrono::duration<double, std::milli>(t1 - t_round).count(), h[4], f.pool_cap, h[3]);
+            t_round = t1;
+        }
+        if (h[1] == 0) break; // the snapshot of this round equals the picks: it is the fixed point
+    }
+    // pred[j] = the last picker of j; roots by pointer jumping (in place: a racing read sees an older or a newer
+    // ancestor, both valid), bits_for(n) + 1 rounds cover any chain length
+    {
+        const FxArrays g = f;
+        u32 *r = f.list;
+        launch_for<t_fx_pred>(n_h, st, lc, [=] __device__(u32 j) {
+            u32 m = NONE32;
+            for (u32 p = g.off[j]; p < g.off[j + 1]; p++) m = (m == NONE32 || g.li[p] > m) ? g.li[p] : m;
+            r[j] = m == NONE32 ? j : m;
+        });
+        for (int k = 0; k < bits_for(n_h) + 1; k++)
+            launch_for<t_fx_jump>(n_h, st, lc, [=] __device__(u32 j) {
+                const u32 a = r[j];
+                const u32 b = r[a];
+                if (b != a) r[j] = b;
+            });
+        launch_for<t_fx_scatter>(n_h, st, lc, [=] __device__(u32 k) { root[hpos[k]] = hpos[r[k]]; });
+    }
+    if (verbose) fprintf(stderr, "[swg fixpoint] %u positions in huge groups, %d rounds, %llu re-evaluations\n", n_h, rounds,
+                         (unsigned long long)total_recomputed);
+}
+
+} // namespace swg

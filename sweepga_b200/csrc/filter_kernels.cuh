@@ -18,7 +18,7 @@ constexpr u8 F_PREMEM = 8;  // member of a chain that passed the mass/identity f
 // counters (u64 each) shared with the host
 enum {
     C_ALIVE = 0, C_ZLQ, C_ZLT, C_MAXCOORD, C_BAD, C_KEPT_M, C_GROUPS, C_CHAINS, C_PASS, C_PASS_ZEROSPAN,
-    C_KEPT_CHAINS, C_ANCHORS, C_RESCUED, C_KEPT, C_NEAR_TIES, C_WORK, C_INV, C_TMP0, C_COUNT = 32
+    C_KEPT_CHAINS, C_ANCHORS, C_RESCUED, C_KEPT, C_NEAR_TIES, C_WORK, C_INV, C_HUGE, C_TMP0, C_COUNT = 32
 };
 
 struct DevIn {
@@ -412,8 +412,15 @@ __device__ __forceinline__ void bb_argmin(u64 &bd, u32 &bj) { // smallest d, the
 #ifndef SWG_RESCAN_WIDTH
 #define SWG_RESCAN_WIDTH 128
 #endif
+// `extra(j, d)` is consulted only for a candidate that fails the plain test d < bps[j]: the sequential walk passes BbNoExtra
+// (never eligible then); the fixed-point resolve (chain_fixpoint.cuh) passes bps = the smallest d over ALL current pickers
+// of j and decides the exact "smallest d over the pickers before i" there.
+struct BbNoExtra {
+    __device__ __forceinline__ bool operator()(u32, u64) const { return false; }
+};
+template <class Extra>
 __device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__ srec, const u64 *bps, u32 i, u32 e, const uint4 &a,
-                                                       bool fwd, u64 G, u64 G5, u64 &bd, u32 &bj, u32 c0_hint) {
+                                                       bool fwd, u64 G, u64 G5, u64 &bd, u32 &bj, u32 c0_hint, Extra extra) {
     const u32 full = 0xFFFFFFFFu;
     const u32 lane = lane_id();
     const u64 bound = (u64)a.y + G;
@@ -464,7 +471,7 @@ __device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__
             else if (k < 2 + RW / 32) inwin = (u64)b.x - a.y <= G;      // right of the origin: q_gap <= G
             else inwin = true;                                          // left of the origin: overlap, judged by the gap rule
             u64 d;
-            if (inwin && bb_candidate(a, b, fwd, G, G5, d) && d < rp[k] && (d < ld || (d == ld && rj[k] < lj))) { ld = d; lj = rj[k]; }
+            if (inwin && bb_candidate(a, b, fwd, G, G5, d) && (d < ld || (d == ld && rj[k] < lj)) && (d < rp[k] || extra(rj[k], d))) { ld = d; lj = rj[k]; }
         }
         bb_argmin(ld, lj);
         bd = ld;
@@ -482,7 +489,7 @@ __device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__
                 const uint4 b = srec[j];
                 inwin = (u64)b.x <= bound;
                 u64 d;
-                if (inwin && bb_candidate(a, b, fwd, G, G5, d) && d < bps[j] && (d < bd || (d == bd && j < bj))) { bd = d; bj = j; }
+                if (inwin && bb_candidate(a, b, fwd, G, G5, d) && (d < bd || (d == bd && j < bj)) && (d < bps[j] || extra(j, d))) { bd = d; bj = j; }
             }
             exhausted = !__all_sync(full, inwin || j >= lin_end);
         }
@@ -531,7 +538,7 @@ __device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__
             if (r < e) {
                 const u64 qg = (u64)rb[k].x - a.y;
                 u64 d;
-                if (qg <= G && bb_candidate(a, rb[k], fwd, G, G5, d) && d < rp[k] && d < ld) { ld = d; lj = r; } // r ascends: ties keep the smaller j
+                if (qg <= G && bb_candidate(a, rb[k], fwd, G, G5, d) && d < ld && (d < rp[k] || extra(r, d))) { ld = d; lj = r; } // r ascends: ties keep the smaller j
             }
         }
         bb_argmin(ld, lj);
@@ -557,7 +564,7 @@ __device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__
             if (off < cnt) {
                 const u32 l = top - 1 - off;
                 u64 d;
-                if (bb_candidate(a, rb[k], fwd, G, G5, d) && d < rp[k] && (d < ld || (d == ld && l < lj))) { ld = d; lj = l; }
+                if (bb_candidate(a, rb[k], fwd, G, G5, d) && (d < ld || (d == ld && l < lj)) && (d < rp[k] || extra(l, d))) { ld = d; lj = l; }
             }
         }
         bb_argmin(ld, lj);
@@ -609,7 +616,7 @@ k_chain_resolve_warp(const Cand *__restrict__ cand, const uint4 *__restrict__ sr
                 else {
                     const u32 i = base + t;
                     const uint4 a = srec[i];
-                    bb_best_successor_warp(srec, bps, i, e, a, fwd, G, G5, wd, wj, __shfl_sync(full, ck.c0, t));
+                    bb_best_successor_warp(srec, bps, i, e, a, fwd, G, G5, wd, wj, __shfl_sync(full, ck.c0, t), BbNoExtra{});
                 }
                 if (wj != NONE32) {
                     if (lane == 0) { bps[wj] = wd; root[wj] = ri; }
@@ -623,14 +630,18 @@ k_chain_resolve_warp(const Cand *__restrict__ cand, const uint4 *__restrict__ sr
 }
 
 // rough count of candidate evaluations the chaining will need (guards against an input that would run for hours)
+// Also counts the positions that belong to huge groups (size >= fx_min): those are chained by the fixed-point iteration
+// of chain_fixpoint.cuh instead of a sequential walk.
+constexpr u32 FX_MIN_GROUP = 16384;
 __global__ void __launch_bounds__(256)
 k_chain_work_estimate(const uint4 *__restrict__ srec, const u32 *__restrict__ gstart, const u32 *__restrict__ n_groups_ptr, u32 n_m, u64 G,
-                      u64 *ctr) {
+                      u32 fx_min, u64 *ctr) {
     const u32 n_groups = *n_groups_ptr; // grid-stride: the host has not read the group count yet
     u64 est = 0;
     for (u32 g = blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += gridDim.x * blockDim.x) {
         const u32 s = gstart[g], e = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
         const u64 size = e - s;
+        if (size >= fx_min) atomicAdd((unsigned long long *)&ctr[C_HUGE], (unsigned long long)size); // a handful of groups at most
         if (size > 1) {
             const u64 span = (u64)srec[e - 1].x - srec[s].x + 1;
             u64 win = size * G / span + 1; // expected candidates per step

@@ -318,6 +318,12 @@ static void segment_first(swg_ctx *c, const u64 *sk, const u32 *sv, u32 n, u32 *
     launch_for<t_segapply>(n, st, c->lc, [=] __device__(u32 u) { out[sv[u]] = segfirst[segof[u]]; });
 }
 
+} // namespace swg
+
+#include "chain_fixpoint.cuh"
+
+namespace swg {
+
 // ================================================================================================
 // the pipeline
 // ================================================================================================
@@ -505,9 +511,11 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         srec2[p] = make_uint2(__ldg(&in.blen[i]), __ldg(&in.matches[i]));
     });
     u32 n_groups;
+    // groups of at least fx_min positions are chained by the fixed-point iteration (SWG_NO_FIXPOINT=1: by the warp walk)
+    const u32 fx_min = getenv("SWG_NO_FIXPOINT") ? NONE32 : (getenv("SWG_FIXPOINT_MIN") ? (u32)atoi(getenv("SWG_FIXPOINT_MIN")) : FX_MIN_GROUP);
     {   // refuse inputs whose chaining would need an absurd number of candidate evaluations (e.g. one 50 M-mapping pile:
         // ~2e13; the reference is O(n * window) there as well) instead of occupying the GPU for hours
-        k_chain_work_estimate<<<(u32)c->sm_count * 8, 256, 0, st>>>(srec, gstart, d_tot, n_m, cfg.scaffold_gap, ctr);
+        k_chain_work_estimate<<<(u32)c->sm_count * 8, 256, 0, st>>>(srec, gstart, d_tot, n_m, cfg.scaffold_gap, fx_min, ctr);
         lc.n++;
         u32 *h = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
         SWG_CUDA(cudaMemcpyAsync(h, d_tot, sizeof(u32), cudaMemcpyDeviceToHost, st)); // group count and estimate in one round trip
@@ -542,9 +550,13 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             const u32 s0 = gstart[g], e0 = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
             const u64 size = e0 - s0;
             const u64 span = (u64)srec[e0 - 1].x - srec[s0].x + 1;
-            return size > 4096 || size * Gj > 64 * span;
+            return size < fx_min && (size > 4096 || size * Gj > 64 * span);
         };
-        scan_apply([=] __device__(u32 g) -> u32 { return (grp_has_cand[g] && !is_big(g)) ? 1u : 0u; },
+        auto is_huge = [=] __device__(u32 g) -> bool {
+            const u32 s0 = gstart[g], e0 = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
+            return e0 - s0 >= fx_min;
+        };
+        scan_apply([=] __device__(u32 g) -> u32 { return (grp_has_cand[g] && !is_big(g) && !is_huge(g)) ? 1u : 0u; },
                    [=] __device__(u32 g, u32 ex, u32 v) { if (v) work[ex] = g; }, n_groups, bsum, bb_ctr, st, lc);
         scan_apply([=] __device__(u32 g) -> u32 { return (grp_has_cand[g] && is_big(g)) ? 1u : 0u; },
                    [=] __device__(u32 g, u32 ex, u32 v) { if (v) work_big[ex] = g; }, n_groups, bsum, bb_ctr + 2, st, lc);
@@ -556,6 +568,14 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         k_chain_resolve_warp<<<(u32)c->sm_count * 4, 128, 0, st>>>(cand, srec, skey, gstart, n_groups, n_m, work_big, bb_ctr + 2, gshift,
                                                                   cfg.scaffold_gap, bps, root, bb_ctr + 3);
         lc.n += 2;
+        const u32 n_huge = (u32)c->h_ctr[C_HUGE];
+        if (n_huge) {
+            stage_mark(c, "ch_fixpoint");
+            u32 *hpos = A.take<u32>(n_huge);
+            scan_apply([=] __device__(u32 p) -> u32 { return is_huge(gid[p]) ? 1u : 0u; },
+                       [=] __device__(u32 p, u32 ex, u32 v) { if (v) hpos[ex] = p; }, n_m, bsum, d_tot + 3, st, lc);
+            chain_fixpoint(c, n_huge, hpos, srec, skey, gshift, gid, gstart, n_groups, n_m, cand, cfg.scaffold_gap, root, bsum);
+        }
     }
     stage_mark(c, "ch_aggregate");
     // ---- K4: dense chain table + mass/identity filter + order key (A,B) ----------------------------

@@ -139,6 +139,52 @@ def test_dense_windows(ctx, seed):
     check(ctx, cfg, t, f"dense{seed}")
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_fixpoint_dense_windows(ctx, seed, monkeypatch):
+    """The fixed-point chaining (chain_fixpoint.cuh) forced onto EVERY group: same inputs as test_dense_windows."""
+    monkeypatch.setenv("SWG_FIXPOINT_MIN", "2")
+    t = fuzz_table(500 + seed, 6000, n_genomes=1, n_chr=2, span=[4000, 20000][seed % 2], max_len=[400, 60][seed // 4 % 2],
+                   zero_len_frac=0.0)
+    cfg = swg.FilterConfig.from_cli(scaffold_jump=str([200, 1000, 3000, 50][seed % 4]), scaffold_mass=str([0, 300][seed % 2]),
+                                    scaffold_dist=str([0, 500][seed % 2]), keep_self=True)
+    check(ctx, cfg, t, f"fixpoint-dense{seed}")
+
+
+@pytest.mark.parametrize("what", ["yeast", "pansn400k", "skew20k", "fuzz"])
+def test_fixpoint_everywhere(ctx, yeast, what, monkeypatch):
+    """Ordinary inputs with every group of two or more mappings sent through the fixed-point chaining."""
+    monkeypatch.setenv("SWG_FIXPOINT_MIN", "2")
+    if what == "yeast":
+        check(ctx, swg.FilterConfig(), yeast, what)
+        check(ctx, swg.FilterConfig.from_cli(**CLI_CASES["1:1_rescue"]), yeast, what)
+    elif what == "pansn400k":
+        check(ctx, swg.FilterConfig(), synth.pansn(400_000, seed=3, n_hap=12), what)
+    elif what == "skew20k":
+        check(ctx, swg.FilterConfig(), synth.skew(n_pile=20_000, n_tiny_groups=3_000, seed=5, window=3_000_000), what)
+    else:
+        for seed in range(120, 132):
+            t = fuzz_table(seed, 5000)
+            cfg = swg.FilterConfig.from_cli(scaffold_jump=str([50, 200, 1000][seed % 3]), scaffold_mass=str([0, 100][seed % 2]), keep_self=True)
+            check(ctx, cfg, t, f"fixpoint-fuzz{seed}")
+
+
+def test_fixpoint_pile_200k(ctx):
+    """configs[4] at the largest size the oracle's O(n * window) chaining finishes in seconds: the two 100 k strand groups
+    of the pile are above the default threshold, so this is the fixed-point path as shipped."""
+    check(ctx, swg.FilterConfig(), synth.skew(n_pile=200_000, n_tiny_groups=20_000, seed=5), "pile200k")
+
+
+def test_fixpoint_equals_sequential_walk_2m(ctx, monkeypatch):
+    """Beyond the oracle's reach: a 2 M pile through the fixed point and through the sequential warp walk (same result)."""
+    t = synth.skew(n_pile=2_000_000, n_tiny_groups=50_000, seed=6)
+    cfg = swg.FilterConfig()
+    s1, c1, st1 = ctx.filter(cfg, t)
+    monkeypatch.setenv("SWG_NO_FIXPOINT", "1")
+    s2, c2, st2 = ctx.filter(cfg, t)
+    assert np.array_equal(s1, s2) and np.array_equal(c1, c2)
+    assert st1.n_chains == st2.n_chains and st1.n_kept == st2.n_kept
+
+
 def test_edge_cases(ctx):
     cfg = swg.FilterConfig.from_cli(scaffold_mass="0")
     names = ["A#1#c1", "B#1#c1"]
