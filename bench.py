@@ -169,6 +169,23 @@ def paf_file_leg(ctx, cfg, n_lines):
         shutil.rmtree(d, ignore_errors=True)
 
 
+def skew_leg(ctx, cfg, n_pile):
+    """Extra, informational: configs[4] (one centromeric pile + 100 k tiny groups) at --skew-pile mappings; the two strand
+    groups of the pile go through the fixed-point chaining.  Host buffers, wall clock.  Never fails the bench."""
+    try:
+        from sweepga_b200 import synth
+        t = synth.skew(n_pile=n_pile, n_tiny_groups=100_000, seed=5)
+        ctx.filter(cfg, t)
+        t0 = time.time()
+        _, _, st = ctx.filter(cfg, t)
+        dt = time.time() - t0
+        return {"workload": f"configs[4] at reduced scale: {n_pile} mappings on one chromosome pair (95 % inside 6 Mbp) + 100000 tiny groups",
+                "records": int(t.n), "wall_s": dt, "ms_device": float(st.ms_device), "Mmappings_per_s": t.n / dt / 1e6,
+                "gpu_launches": int(st.gpu_launches), "kept": int(st.n_kept), "chains": int(st.n_chains_kept)}
+    except Exception as e:  # informational leg only
+        return {"error": repr(e)[:200]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -178,6 +195,8 @@ def main():
     ap.add_argument("--records", type=int, default=0, help="override the per-GPU record count (debug only)")
     ap.add_argument("--paf-lines", type=int, default=2_000_000,
                     help="N = 1 only: also time swg_filter_paf file to file on a synthetic PAF of this many lines (0 = skip)")
+    ap.add_argument("--skew-pile", type=int, default=5_000_000,
+                    help="size of the configs[4] pile of the informational skew leg (0 = skip)")
     ap.add_argument("--cpu-sample", type=int, default=20_000_000,
                     help="records of the workload the CPU oracle is timed on (~20 core-seconds at the default)")
     args = ap.parse_args()
@@ -337,6 +356,8 @@ def main():
         }
         if n_gpus == 1 and args.paf_lines > 0:
             line["paf_e2e"] = paf_file_leg(ctx, cfg, args.paf_lines)
+        if n_gpus == 1 and args.skew_pile > 0:
+            line["skew"] = skew_leg(ctx, cfg, args.skew_pile)
         if n_gpus == 1:
             sample = table.take(np.arange(min(n, args.cpu_sample)))
             cores = os.cpu_count() or 1

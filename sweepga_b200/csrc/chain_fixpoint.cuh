@@ -29,10 +29,10 @@
 
 namespace swg {
 
-struct t_fx_init; struct t_fx_count; struct t_fx_fill; struct t_fx_pred; struct t_fx_jump; struct t_fx_scatter;
+struct t_fx_init; struct t_fx_count; struct t_fx_minpi; struct t_fx_fill; struct t_fx_pred; struct t_fx_jump; struct t_fx_scatter;
 
-constexpr u32 FX_XCAP = 64;   // blocked candidates remembered per position; a position with more is re-evaluated every round
-constexpr u8 FX_XOVER = 0xFF; // xcnt value of such a position
+constexpr u32 FX_XCAP = 1024;     // blocked candidates remembered per position; a position with more is re-evaluated every round
+constexpr u16 FX_XOVER = 0xFFFF; // xcnt value of such a position
 constexpr u32 FX_REV = 0x80000000u; // gend bit: the group is a '-' strand group
 
 struct FxArrays {
@@ -44,10 +44,11 @@ struct FxArrays {
     u64 *pd;           // d of the current pick
     u32 *cnt, *off;    // picker lists: off[j] .. off[j+1]
     u64 *minpd;        // smallest d over all pickers of j (NONE64: nobody picks j)
+    u32 *minpi;        // the first picker of j that has that d
     u32 *li;           // picker position
     u64 *ld;           // picker d
     u32 *xoff;         // X(i) lives at pool[xoff .. xoff + xcnt)
-    u8 *xcnt, *xcap;
+    u16 *xcnt, *xcap;
     u32 *pool, *pool_top;
     u32 pool_cap;
     u32 *list;         // positions to re-evaluate this round
@@ -55,16 +56,21 @@ struct FxArrays {
 };
 
 // smallest d over the pickers of j that precede position i, compared with d: true iff d < B(i,j)
-__device__ __forceinline__ bool fx_eligible(const FxArrays &f, u32 i, u32 j, u64 d) {
+// (callers have established d >= minpd[j]: if the picker that holds the minimum precedes i, that settles it)
+__device__ __forceinline__ bool fx_eligible(const FxArrays &f, u32 i, u32 j, u64 d, u32 mi /* = minpi[j] */) {
+    if (mi < i) return false;
+    if (mi == i) return true; // i itself holds the minimum and is the first to: every earlier picker has a larger d
     const u32 a = f.off[j], b = f.off[j + 1];
     for (u32 p = a; p < b; p++)
         if (f.li[p] < i && f.ld[p] <= d) return false;
     return true;
 }
 struct FxExtra {
+    static constexpr bool PREFETCH = true;
+    const u32 *pi; // = minpi
     FxArrays f;
     u32 i;
-    __device__ __forceinline__ bool operator()(u32 j, u64 d) const { return fx_eligible(f, i, j, d); }
+    __device__ __forceinline__ bool operator()(u32 j, u64 d, u32 mi) const { return fx_eligible(f, i, j, d, mi); }
 };
 
 // step 2: does position k have to be re-evaluated against the new snapshot?
@@ -72,11 +78,11 @@ __global__ void __launch_bounds__(256) k_fx_check(FxArrays f, u64 G) {
     const u32 k = blockIdx.x * blockDim.x + threadIdx.x;
     bool need = false;
     if (k < f.n) {
-        const u8 xc = f.xcnt[k];
+        const u16 xc = f.xcnt[k];
         const u32 j = f.pick[k];
         if (xc == FX_XOVER) need = true;
         else {
-            if (j != NONE32 && f.off[j + 1] - f.off[j] > 1) need = !fx_eligible(f, k, j, f.pd[k]);
+            if (j != NONE32 && f.off[j + 1] - f.off[j] > 1) need = !fx_eligible(f, k, j, f.pd[k], f.minpi[j]);
             if (!need && xc) {
                 const uint4 a = f.rec[k];
                 const bool fwd = !(f.gend[k] & FX_REV);
@@ -84,7 +90,7 @@ __global__ void __launch_bounds__(256) k_fx_check(FxArrays f, u64 G) {
                 for (u32 q = 0; q < xc && !need; q++) {
                     const u32 jx = x[q];
                     u64 d;
-                    if (bb_candidate(a, f.rec[jx], fwd, G, G / 5, d)) need = d < f.minpd[jx] || fx_eligible(f, k, jx, d);
+                    if (bb_candidate(a, f.rec[jx], fwd, G, G / 5, d)) need = d < f.minpd[jx] || fx_eligible(f, k, jx, d, f.minpi[jx]);
                 }
             }
         }
@@ -128,31 +134,49 @@ __device__ __forceinline__ u32 fx_collect_blocked(const uint4 *__restrict__ rec,
     }
     if (c0 == NONE32 || lin_end >= e) return xn; // the window ended in there (k_chain_candidates' linear phase saw its end)
     c0 = max(c0, lin_end);
-    for (u32 r0 = c0; r0 < e; r0 += 32) { // right of the origin: q_gap = qs - qe >= 0 grows; d >= q_gap^2
-        const u32 r = r0 + lane;
-        uint4 b = make_uint4(0, 0, 0, 0);
-        bool in = false;
-        if (r < e) {
-            b = rec[r];
-            const u64 qg = (u64)b.x - a.y;
-            in = qg <= G && qg * qg <= bd;
+    // four chunks per round, every load issued before the first use (one memory round trip per 128 candidates)
+    constexpr u32 CW = 4;
+    for (u32 r0 = c0; r0 < e; r0 += 32 * CW) { // right of the origin: q_gap = qs - qe >= 0 grows; d >= q_gap^2
+        uint4 b[CW];
+#pragma unroll
+        for (u32 k = 0; k < CW; k++) {
+            const u32 r = r0 + k * 32 + lane;
+            b[k] = r < e ? rec[r] : make_uint4(0, 0, 0, 0);
         }
-        xn = fx_collect_chunk(a, fwd, G, G5, bd, bj, r, in, b, xs, xn);
-        if (!__shfl_sync(full, (int)in, 31)) break; // monotone: once the last lane is out, so is everything further right
+        bool in = false;
+#pragma unroll
+        for (u32 k = 0; k < CW; k++) {
+            const u32 r = r0 + k * 32 + lane;
+            in = false;
+            if (r < e) {
+                const u64 qg = (u64)b[k].x - a.y;
+                in = qg <= G && qg * qg <= bd;
+            }
+            xn = fx_collect_chunk(a, fwd, G, G5, bd, bj, r, in, b[k], xs, xn);
+        }
+        if (!__shfl_sync(full, (int)in, 31)) break; // monotone: once the last candidate is out, so is everything further right
     }
     for (u32 top = c0; top > lin_end;) { // left of the origin: overlap = qe - qs > 0 grows going left
-        const u32 cnt = min(32u, top - lin_end);
-        uint4 b = make_uint4(0, 0, 0, 0);
-        bool in = false;
-        const u32 l = top - 1 - lane;
-        if (lane < cnt) {
-            b = rec[l];
-            const u64 ov = (u64)a.y - b.x;
-            in = ov <= G5 && ov * ov <= bd;
+        const u32 cnt = min(32u * CW, top - lin_end);
+        uint4 b[CW];
+#pragma unroll
+        for (u32 k = 0; k < CW; k++) {
+            const u32 off = k * 32 + lane;
+            b[k] = off < cnt ? rec[top - 1 - off] : make_uint4(0, 0, 0, 0);
         }
-        xn = fx_collect_chunk(a, fwd, G, G5, bd, bj, l, in, b, xs, xn);
-        if (cnt < 32 || !__shfl_sync(full, (int)in, 31)) break;
-        top -= 32;
+        bool in = false;
+#pragma unroll
+        for (u32 k = 0; k < CW; k++) {
+            const u32 off = k * 32 + lane;
+            in = false;
+            if (off < cnt) {
+                const u64 ov = (u64)a.y - b[k].x;
+                in = ov <= G5 && ov * ov <= bd;
+            }
+            xn = fx_collect_chunk(a, fwd, G, G5, bd, bj, top - 1 - off, in, b[k], xs, xn);
+        }
+        if (cnt < 32 * CW || !__shfl_sync(full, (int)in, 31)) break;
+        top -= 32 * CW;
     }
     return xn;
 }
@@ -178,30 +202,30 @@ __global__ void __launch_bounds__(128) k_fx_recompute(FxArrays f, u64 G) {
         const u32 c0 = f.c0[i];
         u64 bd;
         u32 bj;
-        FxExtra ex{f, i};
+        FxExtra ex{f.minpi, f, i};
         bb_best_successor_warp(f.rec, f.minpd, i, e, a, fwd, G, G5, bd, bj, c0, ex);
         __syncwarp();
         const u32 xn = fx_collect_blocked(f.rec, i, e, a, fwd, G, G5, bd, bj, c0, xs);
         __syncwarp();
         u32 xo = 0;
-        u8 xc = FX_XOVER;
+        u16 xc = FX_XOVER;
         if (lane == 0) {
             if (bj != f.pick[i]) atomicAdd(&f.ctrs[1], 1u);
             f.pick[i] = bj;
             f.pd[i] = bd;
             if (xn <= FX_XCAP) {
-                if (xn <= f.xcap[i]) { xo = f.xoff[i]; xc = (u8)xn; }
+                if (xn <= f.xcap[i]) { xo = f.xoff[i]; xc = (u16)xn; }
                 else { // a new slot (the old one is abandoned): capacity rounded up to a power of two >= 4, so X(i) can grow in place
                     const u32 cap = xn <= 4 ? 4u : 1u << (32 - __clz(xn - 1));
                     xo = atomicAdd(f.pool_top, cap);
-                    if (xo <= f.pool_cap && cap <= f.pool_cap - xo) { xc = (u8)xn; f.xoff[i] = xo; f.xcap[i] = (u8)cap; }
+                    if (xo <= f.pool_cap && cap <= f.pool_cap - xo) { xc = (u16)xn; f.xoff[i] = xo; f.xcap[i] = (u16)cap; }
                     else atomicAdd(&f.ctrs[3], 1u);
                 }
             }
             f.xcnt[i] = xc;
         }
         xo = __shfl_sync(full, xo, 0);
-        xc = (u8)__shfl_sync(full, (u32)xc, 0);
+        xc = (u16)__shfl_sync(full, (u32)xc, 0);
         if (xc != FX_XOVER)
             for (u32 q = lane; q < xn; q += 32) f.pool[xo + q] = xs[q];
         __syncwarp();
@@ -226,19 +250,26 @@ static void chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
     f.cnt = A.take<u32>(n_h);
     f.off = A.take<u32>((size_t)n_h + 1);
     f.minpd = A.take<u64>(n_h);
+    f.minpi = A.take<u32>(n_h);
     f.li = A.take<u32>(n_h);
     f.ld = A.take<u64>(n_h);
     f.xoff = A.take<u32>(n_h);
-    f.xcnt = A.take<u8>(n_h);
-    f.xcap = A.take<u8>(n_h);
-    f.pool_cap = (u32)std::min<u64>((u64)n_h * 24 + 4096, 0xF0000000ull);
+    f.xcnt = A.take<u16>(n_h);
+    f.xcap = A.take<u16>(n_h);
+    {   // X(i) pool: mean |X| grows with the density of the pile (about 9 on the '-' strand group of a 5 M pile, ten times
+        // that at 50 M); slots are powers of two and an outgrown slot is abandoned, so be generous where memory allows
+        size_t free_b = 0, total_b = 0;
+        SWG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const u64 want = (u64)n_h * 96 + 4096, fit = free_b / 2 / sizeof(u32);
+        f.pool_cap = (u32)std::min<u64>(std::min<u64>(want, std::max<u64>(fit, (u64)n_h * 8 + 4096)), 0xF0000000ull);
+    }
     f.pool = A.take<u32>(f.pool_cap);
     f.pool_top = A.take<u32>(1);
     f.list = A.take<u32>(n_h);
     f.ctrs = A.take<u32>(4);
     u32 *scan_tot = A.take<u32>(1);
-    SWG_CUDA(cudaMemsetAsync(f.xcnt, 0, n_h, st));
-    SWG_CUDA(cudaMemsetAsync(f.xcap, 0, n_h, st));
+    SWG_CUDA(cudaMemsetAsync(f.xcnt, 0, sizeof(u16) * (size_t)n_h, st));
+    SWG_CUDA(cudaMemsetAsync(f.xcap, 0, sizeof(u16) * (size_t)n_h, st));
     SWG_CUDA(cudaMemsetAsync(f.pool_top, 0, sizeof(u32), st));
     {
         const FxArrays g = f;
@@ -264,6 +295,7 @@ static void chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
         const FxArrays g = f;
         SWG_CUDA(cudaMemsetAsync(f.cnt, 0, sizeof(u32) * (size_t)n_h, st));
         SWG_CUDA(cudaMemsetAsync(f.minpd, 0xFF, sizeof(u64) * (size_t)n_h, st));
+        SWG_CUDA(cudaMemsetAsync(f.minpi, 0xFF, sizeof(u32) * (size_t)n_h, st));
         SWG_CUDA(cudaMemsetAsync(f.ctrs, 0, 4 * sizeof(u32), st));
         launch_for<t_fx_count>(n_h, st, lc, [=] __device__(u32 k) {
             const u32 j = g.pick[k];
@@ -271,6 +303,10 @@ static void chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
                 atomicAdd(&g.cnt[j], 1u);
                 atomicMin((unsigned long long *)&g.minpd[j], (unsigned long long)g.pd[k]);
             }
+        });
+        launch_for<t_fx_minpi>(n_h, st, lc, [=] __device__(u32 k) {
+            const u32 j = g.pick[k];
+            if (j != NONE32 && g.pd[k] == g.minpd[j]) atomicMin(&g.minpi[j], k);
         });
         scan_apply([=] __device__(u32 k) -> u32 { return g.cnt[k]; },
                    [=] __device__(u32 k, u32 ex, u32 v) {

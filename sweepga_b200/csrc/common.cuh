@@ -7,6 +7,7 @@
 namespace swg {
 
 typedef uint8_t u8;
+typedef uint16_t u16;
 typedef uint32_t u32;
 typedef uint64_t u64;
 typedef int64_t i64;

@@ -415,8 +415,12 @@ __device__ __forceinline__ void bb_argmin(u64 &bd, u32 &bj) { // smallest d, the
 // `extra(j, d)` is consulted only for a candidate that fails the plain test d < bps[j]: the sequential walk passes BbNoExtra
 // (never eligible then); the fixed-point resolve (chain_fixpoint.cuh) passes bps = the smallest d over ALL current pickers
 // of j and decides the exact "smallest d over the pickers before i" there.
+// An Extra with PREFETCH = true names a per-successor u32 column `pi` that is loaded together with bps[j] (same index, same
+// round trip) and handed to the call, so that the common verdicts need no dependent load.
 struct BbNoExtra {
-    __device__ __forceinline__ bool operator()(u32, u64) const { return false; }
+    static constexpr bool PREFETCH = false;
+    const u32 *pi = nullptr;
+    __device__ __forceinline__ bool operator()(u32, u64, u32) const { return false; }
 };
 template <class Extra>
 __device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__ srec, const u64 *bps, u32 i, u32 e, const uint4 &a,
@@ -444,6 +448,7 @@ __device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__
         uint4 rb[2 + 2 * (RW / 32)];
         u64 rp[2 + 2 * (RW / 32)];
         u32 rj[2 + 2 * (RW / 32)];
+        u32 rq[2 + 2 * (RW / 32)];
 #pragma unroll
         for (u32 k = 0; k < 2; k++) {
             const u32 j = i + 1 + k * 32 + lane;
@@ -458,7 +463,8 @@ __device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__
         }
 #pragma unroll
         for (u32 k = 0; k < 2 + 2 * (RW / 32); k++) {
-            if (rj[k] != NONE32) { rb[k] = srec[rj[k]]; rp[k] = bps[rj[k]]; }
+            rq[k] = 0;
+            if (rj[k] != NONE32) { rb[k] = srec[rj[k]]; rp[k] = bps[rj[k]]; if (Extra::PREFETCH) rq[k] = extra.pi[rj[k]]; }
         }
         rnext = c0 + RW < e ? (u64)srec[c0 + RW].x : NONE64; // first candidate of the next right round (pruning test)
         lnext = c0 - lcnt > jl ? (u64)srec[c0 - lcnt - 1].x : NONE64;
@@ -471,7 +477,7 @@ __device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__
             else if (k < 2 + RW / 32) inwin = (u64)b.x - a.y <= G;      // right of the origin: q_gap <= G
             else inwin = true;                                          // left of the origin: overlap, judged by the gap rule
             u64 d;
-            if (inwin && bb_candidate(a, b, fwd, G, G5, d) && (d < ld || (d == ld && rj[k] < lj)) && (d < rp[k] || extra(rj[k], d))) { ld = d; lj = rj[k]; }
+            if (inwin && bb_candidate(a, b, fwd, G, G5, d) && (d < ld || (d == ld && rj[k] < lj)) && (d < rp[k] || extra(rj[k], d, rq[k]))) { ld = d; lj = rj[k]; }
         }
         bb_argmin(ld, lj);
         bd = ld;
@@ -489,7 +495,7 @@ __device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__
                 const uint4 b = srec[j];
                 inwin = (u64)b.x <= bound;
                 u64 d;
-                if (inwin && bb_candidate(a, b, fwd, G, G5, d) && (d < bd || (d == bd && j < bj)) && (d < bps[j] || extra(j, d))) { bd = d; bj = j; }
+                if (inwin && bb_candidate(a, b, fwd, G, G5, d) && (d < bd || (d == bd && j < bj)) && (d < bps[j] || extra(j, d, Extra::PREFETCH ? extra.pi[j] : 0u))) { bd = d; bj = j; }
             }
             exhausted = !__all_sync(full, inwin || j >= lin_end);
         }
@@ -524,10 +530,12 @@ __device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__
         if (rnext == NONE64 || qg0 > G || qg0 * qg0 > bd) break;
         uint4 rb[RW / 32];
         u64 rp[RW / 32];
+        u32 rq[RW / 32];
 #pragma unroll
         for (u32 k = 0; k < RW / 32; k++) {
             const u32 r = base + k * 32 + lane;
-            if (r < e) { rb[k] = srec[r]; rp[k] = bps[r]; }
+            rq[k] = 0;
+            if (r < e) { rb[k] = srec[r]; rp[k] = bps[r]; if (Extra::PREFETCH) rq[k] = extra.pi[r]; }
         }
         rnext = base + RW < e ? (u64)srec[base + RW].x : NONE64;
         u64 ld = NONE64;
@@ -538,7 +546,7 @@ __device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__
             if (r < e) {
                 const u64 qg = (u64)rb[k].x - a.y;
                 u64 d;
-                if (qg <= G && bb_candidate(a, rb[k], fwd, G, G5, d) && d < ld && (d < rp[k] || extra(r, d))) { ld = d; lj = r; } // r ascends: ties keep the smaller j
+                if (qg <= G && bb_candidate(a, rb[k], fwd, G, G5, d) && d < ld && (d < rp[k] || extra(r, d, rq[k]))) { ld = d; lj = r; } // r ascends: ties keep the smaller j
             }
         }
         bb_argmin(ld, lj);
@@ -550,10 +558,12 @@ __device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__
         const u32 cnt = min(RW, top - jl);
         uint4 rb[RW / 32];
         u64 rp[RW / 32];
+        u32 rq[RW / 32];
 #pragma unroll
         for (u32 k = 0; k < RW / 32; k++) {
             const u32 off = k * 32 + lane;
-            if (off < cnt) { rb[k] = srec[top - 1 - off]; rp[k] = bps[top - 1 - off]; }
+            rq[k] = 0;
+            if (off < cnt) { rb[k] = srec[top - 1 - off]; rp[k] = bps[top - 1 - off]; if (Extra::PREFETCH) rq[k] = extra.pi[top - 1 - off]; }
         }
         lnext = top - cnt > jl ? (u64)srec[top - cnt - 1].x : NONE64;
         u64 ld = NONE64;
@@ -564,7 +574,7 @@ __device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__
             if (off < cnt) {
                 const u32 l = top - 1 - off;
                 u64 d;
-                if (bb_candidate(a, rb[k], fwd, G, G5, d) && (d < ld || (d == ld && l < lj)) && (d < rp[k] || extra(l, d))) { ld = d; lj = l; }
+                if (bb_candidate(a, rb[k], fwd, G, G5, d) && (d < ld || (d == ld && l < lj)) && (d < rp[k] || extra(l, d, rq[k]))) { ld = d; lj = l; }
             }
         }
         bb_argmin(ld, lj);

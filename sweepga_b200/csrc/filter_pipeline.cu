@@ -49,7 +49,7 @@ template <class Tag, class F> static inline void launch_for(u32 n, cudaStream_t 
 // tags: one per element-wise stage, so that the ncu launch list reads k_for<swg::t_assign, ...> etc.
 struct t_iota; struct t_maxp; struct t_scores; struct t_gkey; struct t_events; struct t_sweep_gather; struct t_sweep_keep;
 struct t_gather; struct t_chain_order; struct t_tspace; struct t_segapply; struct t_keys_c2min; struct t_keys_g2min;
-struct t_final_k; struct t_assign; struct t_invkeys; struct t_inversion; struct t_anchor_keys; struct t_rescue;
+struct t_final_k; struct t_assign; struct t_invkeys; struct t_invent; struct t_inversion; struct t_anchor_keys; struct t_rescue;
 
 // ---- grow-only HBM arena ----------------------------------------------------------------------
 // One block sized for the common path; a call that needs more (general sweeps, degenerate
@@ -527,6 +527,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                              " candidate evaluations (dense pile); raise SWG_MAX_PAIR_EVALS to run it anyway"};
     }
 
+    u32 n_huge = 0; // positions in huge groups (fixed-point chaining; also selects the bucketed inversion capture)
     stage_mark(c, "chaining");
     // ---- K3: best-buddy chaining (candidates -> sequential resolve -> aggregates) -------------------
     u64 *bps = A.take<u64>(n_m);
@@ -568,7 +569,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         k_chain_resolve_warp<<<(u32)c->sm_count * 4, 128, 0, st>>>(cand, srec, skey, gstart, n_groups, n_m, work_big, bb_ctr + 2, gshift,
                                                                   cfg.scaffold_gap, bps, root, bb_ctr + 3);
         lc.n += 2;
-        const u32 n_huge = (u32)c->h_ctr[C_HUGE];
+        n_huge = (u32)c->h_ctr[C_HUGE];
         if (n_huge) {
             stage_mark(c, "ch_fixpoint");
             u32 *hpos = A.take<u32>(n_huge);
@@ -771,6 +772,81 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                 u_qs[u] = t_qs[t]; u_qe[u] = t_qe[t]; u_ts[u] = t_ts[t];
             });
         }
+        // A chromosome pair that holds a huge group can hold 10^5..10^6 kept chains; walking all of them for every
+        // reverse mapping is O(n * chains).  Then (or with SWG_INV_GRID=1) chains and mappings meet in buckets of the query axis.
+        const int wb = std::max(17, bits_for(2 * cfg.scaffold_gap + 1)); // bucket width 2^wb > 2 * jump
+        const int bb = cb > wb ? cb - wb : 1;
+        const bool inv_grid = (n_huge > 0 || getenv("SWG_INV_GRID")) && !getenv("SWG_INV_NO_GRID") && 2 * sb + bb + 1 <= 64;
+        if (inv_grid) {
+            stage_mark(c, "inversion_grid");
+            const u64 G = cfg.scaffold_gap;
+            const u64 maxc = maxcoord;
+            // entries: every kept '+' chain once per bucket its extended query interval [qs - G, qe + G] touches
+            u32 *e_off = A.take<u32>(C2);
+            u32 *d_cnt = A.take<u32>(2); // [0] entries, [1] candidate mappings
+            auto first_b = [=] __device__(u32 u) -> u32 { const u64 a = u_qs[u]; return (u32)((a > G ? a - G : 0) >> wb); };
+            auto last_b = [=] __device__(u32 u) -> u32 { const u64 e = (u64)u_qe[u] + G; return (u32)((e < maxc ? e : maxc) >> wb); };
+            scan_apply([=] __device__(u32 u) -> u32 { return ik[u] != NONE64 ? last_b(u) - first_b(u) + 1 : 0u; },
+                       [=] __device__(u32 u, u32 ex, u32) { e_off[u] = ex; }, C2, bsum, d_cnt, st, lc);
+            u32 *inv_list = A.take<u32>(N);
+            scan_apply([=] __device__(u32 i) -> u32 { return ((flags[i] & F_ALIVE) && in.strand[i] != '+' && status[i] == 0) ? 1u : 0u; },
+                       [=] __device__(u32 i, u32 ex, u32 v) { if (v) inv_list[ex] = i; }, N, bsum, d_cnt + 1, st, lc);
+            u32 *h2 = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
+            SWG_CUDA(cudaMemcpyAsync(h2, d_cnt, 2 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+            SWG_CUDA(cudaStreamSynchronize(st));
+            const u32 n_ent = h2[0], n_inv = h2[1];
+            if (n_ent && n_inv) {
+                u64 *ek = A.take<u64>(n_ent), *ek2 = A.take<u64>(n_ent);
+                u32 *ev = A.take<u32>(n_ent), *ev2 = A.take<u32>(n_ent);
+                launch_for<t_invent>(C2, st, lc, [=] __device__(u32 u) {
+                    if (ik[u] == NONE64) return;
+                    const u32 b0 = first_b(u), b1 = last_b(u);
+                    u32 o = e_off[u];
+                    for (u32 b = b0; b <= b1; b++, o++) { ek[o] = (ik[u] << bb) | b; ev[o] = u; }
+                });
+                sort_pairs(c, ek, ek2, ev, ev2, n_ent, 2 * sb + bb); // stable: chains stay in k order inside a bucket
+                uint4 *ent = A.take<uint4>(n_ent);
+                {
+                    const u32 *evc = ev;
+                    launch_for<t_gather>(n_ent, st, lc, [=] __device__(u32 x) { const u32 u = evc[x]; ent[x] = make_uint4(u_qs[u], u_qe[u], u_ts[u], u); });
+                }
+                // the candidates ordered by (pair, first bucket): neighbouring threads walk the same entries
+                u64 *qk = A.take<u64>(n_inv), *qk2 = A.take<u64>(n_inv);
+                u32 *qv = A.take<u32>(n_inv), *qv2 = A.take<u32>(n_inv);
+                launch_for<t_invkeys>(n_inv, st, lc, [=] __device__(u32 x) {
+                    const u32 i = inv_list[x];
+                    qk[x] = (((((u64)in.qid[i] << sb) | in.tid[i])) << bb) | (in.qs[i] >> wb);
+                    qv[x] = i;
+                });
+                sort_pairs(c, qk, qk2, qv, qv2, n_inv, 2 * sb + bb);
+                const u64 *ekc = ek, *qkc = qk;
+                const u32 *qvc = qv;
+                launch_for<t_inversion>(n_inv, st, lc, [=] __device__(u32 x0) {
+                    const u32 i = qvc[x0];
+                    const u64 mqs = in.qs[i], mqe = in.qe[i], mts = in.ts[i], mte = in.te[i];
+                    const u64 qc = (mqs + mqe) / 2, tc = (mts + mte) / 2;
+                    const u64 pairkey = qkc[x0] >> bb;
+                    u32 best = NONE32; // smallest u = the first chain in the reference's order (paf_filter.rs:553-596)
+                    for (u64 b = mqs >> wb; b <= (mqe >> wb); b++) {
+                        const u64 key = (pairkey << bb) | b;
+                        u32 lo = 0, hi = n_ent;
+                        while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (ekc[mid] < key) lo = mid + 1; else hi = mid; }
+                        for (u32 x = lo; x < n_ent && ekc[x] == key; x++) {
+                            const uint4 ch = ent[x];
+                            if (ch.w >= best) break; // entries of a bucket ascend in u
+                            const u64 cqs = ch.x, cqe = ch.y, cts = ch.z;
+                            const u64 ext_s = cqs > G ? cqs - G : 0, ext_e = cqe + G;
+                            if (mqe < ext_s || mqs > ext_e) continue;
+                            const i64 dv = (i64)tc - (i64)qc - ((i64)cts - (i64)cqs);
+                            const u64 dev = dv < 0 ? (u64)(-dv) : (u64)dv;
+                            const u64 perp = (u64)__ddiv_rn((double)dev, 1.4142135623730951);
+                            if (perp <= G) { best = ch.w; break; }
+                        }
+                    }
+                    if (best != NONE32) { status[i] = 1; chain_id[i] = best + 1; }
+                });
+            }
+        } else {
         sort_pairs(c, ik, ik2, iv, iv2, C2, 2 * sb + 1);
         const u32 Cf = C2; // the other chains carry the all-ones key and sort behind every forward chain: no count (and no round trip) needed
         {
@@ -804,6 +880,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                 }
             });
         }
+        } // !inv_grid
 
         // ---- K7: rescue (paf_filter.rs:613-732) -----------------------------------------------------
         const u64 D = cfg.scaffold_max_deviation;

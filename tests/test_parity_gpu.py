@@ -185,6 +185,19 @@ def test_fixpoint_equals_sequential_walk_2m(ctx, monkeypatch):
     assert st1.n_chains == st2.n_chains and st1.n_kept == st2.n_kept
 
 
+@pytest.mark.parametrize("case", ["defaults", "1:1_1:1", "rescue100k", "tight_jump", "self", "mass0"])
+def test_inversion_grid_yeast(ctx, yeast, case, monkeypatch):
+    """Inversion capture through the bucketed path (taken on its own when a huge group exists), forced onto ordinary input."""
+    monkeypatch.setenv("SWG_INV_GRID", "1")
+    check(ctx, swg.FilterConfig.from_cli(**CLI_CASES[case]), yeast, "invgrid-" + case)
+
+
+@pytest.mark.parametrize("seed", range(0, 160, 4))
+def test_inversion_grid_fuzz(ctx, seed, monkeypatch):
+    monkeypatch.setenv("SWG_INV_GRID", "1")
+    test_fuzz_dense(ctx, seed)
+
+
 def test_edge_cases(ctx):
     cfg = swg.FilterConfig.from_cli(scaffold_mass="0")
     names = ["A#1#c1", "B#1#c1"]
