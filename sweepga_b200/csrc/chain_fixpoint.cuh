@@ -66,11 +66,20 @@ __device__ __forceinline__ bool fx_eligible(const FxArrays &f, u32 i, u32 j, u64
     return true;
 }
 struct FxExtra {
+    static constexpr u32 OUTWARD = 128; // wider rounds measured slower (256: 2.3x on the 8 M pile): most searches end within the first rounds
     static constexpr bool PREFETCH = true;
     const u32 *pi; // = minpi
     FxArrays f;
     u32 i;
-    __device__ __forceinline__ bool operator()(u32 j, u64 d, u32 mi) const { return fx_eligible(f, i, j, d, mi); }
+    u32 *seen, *n_seen; // shared memory of the warp: the blocked candidates met by the search (a superset of X(i))
+    __device__ __forceinline__ bool operator()(u32 j, u64 d, u32 mi) const {
+        const bool el = fx_eligible(f, i, j, d, mi);
+        if (!el) { // it beat the lane's best so far and is blocked: the only kind of candidate that can belong to X(i)
+            const u32 o = atomicAdd(n_seen, 1u);
+            if (o < FX_XCAP) seen[o] = j;
+        }
+        return el;
+    }
 };
 
 // step 2: does position k have to be re-evaluated against the new snapshot?
@@ -181,9 +190,33 @@ __device__ __forceinline__ u32 fx_collect_blocked(const uint4 *__restrict__ rec,
     return xn;
 }
 
+// X(i) out of the search's own record: keep the entries that rank before the final pick (compacted in place)
+__device__ __forceinline__ u32 fx_filter_seen(const uint4 *__restrict__ rec, const uint4 &a, bool fwd, u64 G, u64 G5, u64 bd, u32 bj, u32 *xs,
+                                              u32 seen) {
+    const u32 lane = lane_id();
+    u32 out = 0;
+    for (u32 q0 = 0; q0 < seen; q0 += 32) {
+        const u32 q = q0 + lane;
+        u32 j = NONE32;
+        bool mem = false;
+        if (q < seen) {
+            j = xs[q];
+            u64 d;
+            mem = bb_candidate(a, rec[j], fwd, G, G5, d) && (d < bd || (d == bd && j < bj));
+        }
+        __syncwarp(); // the chunk is in registers before anything is written (out <= q0)
+        const u32 m = __ballot_sync(0xFFFFFFFFu, mem);
+        if (mem) xs[out + __popc(m & lanemask_lt())] = j;
+        out += __popc(m);
+        __syncwarp();
+    }
+    return out;
+}
+
 // step 3: one warp per listed position
 __global__ void __launch_bounds__(128) k_fx_recompute(FxArrays f, u64 G) {
     __shared__ u32 s_x[4][FX_XCAP];
+    __shared__ u32 s_seen[4];
     const u32 full = 0xFFFFFFFFu;
     const u32 lane = lane_id();
     const u64 G5 = G / 5;
@@ -202,10 +235,16 @@ __global__ void __launch_bounds__(128) k_fx_recompute(FxArrays f, u64 G) {
         const u32 c0 = f.c0[i];
         u64 bd;
         u32 bj;
-        FxExtra ex{f.minpi, f, i};
+        u32 *n_seen = &s_seen[threadIdx.x >> 5];
+        if (lane == 0) *n_seen = 0;
+        __syncwarp();
+        FxExtra ex{f.minpi, f, i, xs, n_seen};
         bb_best_successor_warp(f.rec, f.minpd, i, e, a, fwd, G, G5, bd, bj, c0, ex);
         __syncwarp();
-        const u32 xn = fx_collect_blocked(f.rec, i, e, a, fwd, G, G5, bd, bj, c0, xs);
+        // X(i): normally out of the search's own record of blocked candidates; a separate pruned pass if that overflowed
+        const u32 seen = *n_seen;
+        const u32 xn = seen <= FX_XCAP ? fx_filter_seen(f.rec, a, fwd, G, G5, bd, bj, xs, seen)
+                                       : fx_collect_blocked(f.rec, i, e, a, fwd, G, G5, bd, bj, c0, xs);
         __syncwarp();
         u32 xo = 0;
         u16 xc = FX_XOVER;

@@ -202,18 +202,21 @@ struct Cand { // unconstrained best successor of a position
 };
 
 // gap rule of paf_filter.rs:799-833 (query axis and, strand-aware, target axis)
+// 32-bit arithmetic up to the squares: coordinates are u32 and the host refuses scaffold_gap >= 2^31, so every gap and
+// G + 1 fit (the reference computes the same values in u64).
 __device__ __forceinline__ bool bb_candidate(const uint4 &a, const uint4 &b, bool fwd, u64 G, u64 G5, u64 &d) {
-    u64 qgap, rgap;
+    const u32 g = (u32)G, g5 = (u32)G5;
+    u32 qgap, rgap;
     if (b.x >= a.y) qgap = b.x - a.y;
-    else { u64 ov = a.y - b.x; qgap = ov <= G5 ? ov : G + 1; }
+    else { const u32 ov = a.y - b.x; qgap = ov <= g5 ? ov : g + 1; }
     if (fwd) {
         if (b.z >= a.w) rgap = b.z - a.w;
-        else { u64 ov = a.w - b.z; rgap = ov <= G5 ? ov : G + 1; }
+        else { const u32 ov = a.w - b.z; rgap = ov <= g5 ? ov : g + 1; }
     } else {
         if (a.z >= b.w) rgap = a.z - b.w;
-        else { u64 ov = b.w - a.z; rgap = ov <= G5 ? ov : G + 1; }
+        else { const u32 ov = b.w - a.z; rgap = ov <= g5 ? ov : g + 1; }
     }
-    if (qgap <= G && rgap <= G) { d = qgap * qgap + rgap * rgap; return true; }
+    if (qgap <= g && rgap <= g) { d = (u64)qgap * qgap + (u64)rgap * rgap; return true; }
     return false;
 }
 
@@ -418,6 +421,7 @@ __device__ __forceinline__ void bb_argmin(u64 &bd, u32 &bj) { // smallest d, the
 // An Extra with PREFETCH = true names a per-successor u32 column `pi` that is loaded together with bps[j] (same index, same
 // round trip) and handed to the call, so that the common verdicts need no dependent load.
 struct BbNoExtra {
+    static constexpr u32 OUTWARD = SWG_RESCAN_WIDTH; // candidates per outward round
     static constexpr bool PREFETCH = false;
     const u32 *pi = nullptr;
     __device__ __forceinline__ bool operator()(u32, u64, u32) const { return false; }
@@ -525,23 +529,24 @@ __device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__
     }
     // Outward rounds.  The pruning test looks at the first candidate of a round only; candidates past the exact pruning
     // point have d >= q_gap^2 > best d and cannot win, so reading a few more of them changes nothing.
-    for (u32 base = rbase; base < e; base += RW) { // right side, q_gap >= 0 non-decreasing
+    constexpr u32 OW = Extra::OUTWARD; // outward rounds may be wider than the fused first round: one memory round trip per OW candidates
+    for (u32 base = rbase; base < e; base += OW) { // right side, q_gap >= 0 non-decreasing
         const u64 qg0 = rnext - a.y;
         if (rnext == NONE64 || qg0 > G || qg0 * qg0 > bd) break;
-        uint4 rb[RW / 32];
-        u64 rp[RW / 32];
-        u32 rq[RW / 32];
+        uint4 rb[OW / 32];
+        u64 rp[OW / 32];
+        u32 rq[OW / 32];
 #pragma unroll
-        for (u32 k = 0; k < RW / 32; k++) {
+        for (u32 k = 0; k < OW / 32; k++) {
             const u32 r = base + k * 32 + lane;
             rq[k] = 0;
             if (r < e) { rb[k] = srec[r]; rp[k] = bps[r]; if (Extra::PREFETCH) rq[k] = extra.pi[r]; }
         }
-        rnext = base + RW < e ? (u64)srec[base + RW].x : NONE64;
-        u64 ld = NONE64;
-        u32 lj = NONE32;
+        rnext = base + OW < e ? (u64)srec[base + OW].x : NONE64;
+        u64 ld = bd; // every lane starts from the best so far: only a candidate that beats it is tested for eligibility
+        u32 lj = bj;
 #pragma unroll
-        for (u32 k = 0; k < RW / 32; k++) {
+        for (u32 k = 0; k < OW / 32; k++) {
             const u32 r = base + k * 32 + lane;
             if (r < e) {
                 const u64 qg = (u64)rb[k].x - a.y;
@@ -550,26 +555,27 @@ __device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__
             }
         }
         bb_argmin(ld, lj);
-        if (ld < bd || (ld == bd && lj < bj)) { bd = ld; bj = lj; }
+        bd = ld;
+        bj = lj;
     }
-    for (u32 top = ltop; top > jl;) { // left side, overlap > 0 non-decreasing going left; round = [top-RW, top)
+    for (u32 top = ltop; top > jl;) { // left side, overlap > 0 non-decreasing going left; round = [top-OW, top)
         const u64 ov0 = (u64)a.y - lnext;
         if (lnext == NONE64 || ov0 > G5 || ov0 * ov0 > bd) break;
-        const u32 cnt = min(RW, top - jl);
-        uint4 rb[RW / 32];
-        u64 rp[RW / 32];
-        u32 rq[RW / 32];
+        const u32 cnt = min(OW, top - jl);
+        uint4 rb[OW / 32];
+        u64 rp[OW / 32];
+        u32 rq[OW / 32];
 #pragma unroll
-        for (u32 k = 0; k < RW / 32; k++) {
+        for (u32 k = 0; k < OW / 32; k++) {
             const u32 off = k * 32 + lane;
             rq[k] = 0;
             if (off < cnt) { rb[k] = srec[top - 1 - off]; rp[k] = bps[top - 1 - off]; if (Extra::PREFETCH) rq[k] = extra.pi[top - 1 - off]; }
         }
         lnext = top - cnt > jl ? (u64)srec[top - cnt - 1].x : NONE64;
-        u64 ld = NONE64;
-        u32 lj = NONE32;
+        u64 ld = bd;
+        u32 lj = bj;
 #pragma unroll
-        for (u32 k = 0; k < RW / 32; k++) {
+        for (u32 k = 0; k < OW / 32; k++) {
             const u32 off = k * 32 + lane;
             if (off < cnt) {
                 const u32 l = top - 1 - off;
@@ -578,7 +584,8 @@ __device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__
             }
         }
         bb_argmin(ld, lj);
-        if (ld < bd || (ld == bd && lj < bj)) { bd = ld; bj = lj; }
+        bd = ld;
+        bj = lj;
         top -= cnt;
     }
 }
