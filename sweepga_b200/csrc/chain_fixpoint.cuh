@@ -29,7 +29,7 @@
 
 namespace swg {
 
-struct t_fx_init; struct t_fx_count; struct t_fx_minpi; struct t_fx_fill; struct t_fx_pred; struct t_fx_jump; struct t_fx_scatter;
+struct t_fx_init; struct t_fx_count; struct t_fx_minpi; struct t_fx_all; struct t_fx_fill; struct t_fx_pred; struct t_fx_jump; struct t_fx_scatter;
 
 constexpr u32 FX_XCAP = 1024;     // blocked candidates remembered per position; a position with more is re-evaluated every round
 constexpr u16 FX_XOVER = 0xFFFF; // xcnt value of such a position
@@ -49,7 +49,8 @@ struct FxArrays {
     u64 *ld;           // picker d
     u32 *xoff;         // X(i) lives at pool[xoff .. xoff + xcnt)
     u16 *xcnt, *xcap;
-    u32 *pool, *pool_top;
+    u32 *pool;
+    unsigned long long *pool_top; // 64-bit: refused requests keep counting and must never wrap into live slots
     u32 pool_cap;
     u32 *list;         // positions to re-evaluate this round
     u32 *ctrs;         // [0] list length, [1] picks changed this round, [2] recompute work counter, [3] slots refused (pool full)
@@ -256,8 +257,8 @@ __global__ void __launch_bounds__(128) k_fx_recompute(FxArrays f, u64 G) {
                 if (xn <= f.xcap[i]) { xo = f.xoff[i]; xc = (u16)xn; }
                 else { // a new slot (the old one is abandoned): capacity rounded up to a power of two >= 4, so X(i) can grow in place
                     const u32 cap = xn <= 4 ? 4u : 1u << (32 - __clz(xn - 1));
-                    xo = atomicAdd(f.pool_top, cap);
-                    if (xo <= f.pool_cap && cap <= f.pool_cap - xo) { xc = (u16)xn; f.xoff[i] = xo; f.xcap[i] = (u16)cap; }
+                    const unsigned long long at = atomicAdd(f.pool_top, (unsigned long long)cap);
+                    if (at + cap <= (unsigned long long)f.pool_cap) { xo = (u32)at; xc = (u16)xn; f.xoff[i] = xo; f.xcap[i] = (u16)cap; }
                     else atomicAdd(&f.ctrs[3], 1u);
                 }
             }
@@ -303,13 +304,13 @@ static void chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
         f.pool_cap = (u32)std::min<u64>(std::min<u64>(want, std::max<u64>(fit, (u64)n_h * 8 + 4096)), 0xF0000000ull);
     }
     f.pool = A.take<u32>(f.pool_cap);
-    f.pool_top = A.take<u32>(1);
+    f.pool_top = A.take<unsigned long long>(1);
     f.list = A.take<u32>(n_h);
     f.ctrs = A.take<u32>(4);
     u32 *scan_tot = A.take<u32>(1);
     SWG_CUDA(cudaMemsetAsync(f.xcnt, 0, sizeof(u16) * (size_t)n_h, st));
     SWG_CUDA(cudaMemsetAsync(f.xcap, 0, sizeof(u16) * (size_t)n_h, st));
-    SWG_CUDA(cudaMemsetAsync(f.pool_top, 0, sizeof(u32), st));
+    SWG_CUDA(cudaMemsetAsync(f.pool_top, 0, sizeof(unsigned long long), st));
     {
         const FxArrays g = f;
         launch_for<t_fx_init>(n_h, st, lc, [=] __device__(u32 k) {
@@ -366,17 +367,34 @@ static void chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
         k_fx_recompute<<<(u32)c->sm_count * 8, 128, 0, st>>>(f, G);
         lc.n += 2;
         SWG_CUDA(cudaMemcpyAsync(h, f.ctrs, 4 * sizeof(u32), cudaMemcpyDeviceToHost, st));
-        if (verbose) SWG_CUDA(cudaMemcpyAsync(h + 4, f.pool_top, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        if (verbose) SWG_CUDA(cudaMemcpyAsync(h + 4, f.pool_top, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         SWG_CUDA(cudaStreamSynchronize(st));
         rounds++;
         total_recomputed += h[0];
         if (verbose) {
             const auto t1 = std::chrono::steady_clock::now();
-            fprintf(stderr, "[swg fixpoint] round %d: %u of %u positions re-evaluated, %u picks changed, %.2f ms, pool %u of %u (%u refused)\n", rounds,
-                    h[0], n_h, h[1], std::chrono::duration<double, std::milli>(t1 - t_round).count(), h[4], f.pool_cap, h[3]);
+            fprintf(stderr, "[swg fixpoint] round %d: %u of %u positions re-evaluated, %u picks changed, %.2f ms, pool %llu of %u (%u refused)\n", rounds,
+                    h[0], n_h, h[1], std::chrono::duration<double, std::milli>(t1 - t_round).count(),
+                    (unsigned long long)(h[4] | ((u64)h[5] << 32)), f.pool_cap, h[3]);
             t_round = t1;
         }
         if (h[1] == 0) break; // the snapshot of this round equals the picks: it is the fixed point
+    }
+    if (getenv("SWG_FIXPOINT_VERIFY")) {
+        // Self-check for sizes no oracle reaches: (*) has exactly one solution, so it suffices that EVERY position, evaluated
+        // from scratch against the final snapshot, reproduces its pick (this bypasses the X(i) bookkeeping of k_fx_check).
+        const FxArrays g = f;
+        SWG_CUDA(cudaMemsetAsync(f.ctrs, 0, 4 * sizeof(u32), st));
+        launch_for<t_fx_all>(n_h, st, lc, [=] __device__(u32 k) {
+            g.list[k] = k;
+            if (k == 0) g.ctrs[0] = g.n;
+        });
+        k_fx_recompute<<<(u32)c->sm_count * 8, 128, 0, st>>>(f, G);
+        lc.n++;
+        SWG_CUDA(cudaMemcpyAsync(h, f.ctrs, 4 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+        SWG_CUDA(cudaStreamSynchronize(st));
+        if (verbose) fprintf(stderr, "[swg fixpoint] verification: %u of %u positions would change their pick\n", h[1], n_h);
+        if (h[1] != 0) throw RangeError{"fixed-point chaining: verification failed (" + std::to_string(h[1]) + " positions)"};
     }
     // pred[j] = the last picker of j; roots by pointer jumping (in place: a racing read sees an older or a newer
     // ancestor, both valid), bits_for(n) + 1 rounds cover any chain length

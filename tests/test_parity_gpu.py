@@ -143,6 +143,7 @@ def test_dense_windows(ctx, seed):
 def test_fixpoint_dense_windows(ctx, seed, monkeypatch):
     """The fixed-point chaining (chain_fixpoint.cuh) forced onto EVERY group: same inputs as test_dense_windows."""
     monkeypatch.setenv("SWG_FIXPOINT_MIN", "2")
+    monkeypatch.setenv("SWG_FIXPOINT_VERIFY", "1")
     t = fuzz_table(500 + seed, 6000, n_genomes=1, n_chr=2, span=[4000, 20000][seed % 2], max_len=[400, 60][seed // 4 % 2],
                    zero_len_frac=0.0)
     cfg = swg.FilterConfig.from_cli(scaffold_jump=str([200, 1000, 3000, 50][seed % 4]), scaffold_mass=str([0, 300][seed % 2]),
@@ -154,6 +155,7 @@ def test_fixpoint_dense_windows(ctx, seed, monkeypatch):
 def test_fixpoint_everywhere(ctx, yeast, what, monkeypatch):
     """Ordinary inputs with every group of two or more mappings sent through the fixed-point chaining."""
     monkeypatch.setenv("SWG_FIXPOINT_MIN", "2")
+    monkeypatch.setenv("SWG_FIXPOINT_VERIFY", "1")
     if what == "yeast":
         check(ctx, swg.FilterConfig(), yeast, what)
         check(ctx, swg.FilterConfig.from_cli(**CLI_CASES["1:1_rescue"]), yeast, what)
@@ -175,10 +177,14 @@ def test_fixpoint_pile_200k(ctx):
 
 
 def test_fixpoint_equals_sequential_walk_2m(ctx, monkeypatch):
-    """Beyond the oracle's reach: a 2 M pile through the fixed point and through the sequential warp walk (same result)."""
+    """Beyond the oracle's reach: a 2 M pile through the fixed point and through the sequential warp walk (same result).
+    SWG_FIXPOINT_VERIFY=1 additionally re-evaluates every position from scratch against the final picks (the call fails if
+    one of them would choose differently): the size-independent property that pins the full 50 M configs[4] run."""
     t = synth.skew(n_pile=2_000_000, n_tiny_groups=50_000, seed=6)
     cfg = swg.FilterConfig()
+    monkeypatch.setenv("SWG_FIXPOINT_VERIFY", "1")
     s1, c1, st1 = ctx.filter(cfg, t)
+    monkeypatch.delenv("SWG_FIXPOINT_VERIFY")
     monkeypatch.setenv("SWG_NO_FIXPOINT", "1")
     s2, c2, st2 = ctx.filter(cfg, t)
     assert np.array_equal(s1, s2) and np.array_equal(c1, c2)
