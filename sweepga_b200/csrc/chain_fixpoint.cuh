@@ -273,8 +273,10 @@ __global__ void __launch_bounds__(128) k_fx_recompute(FxArrays f, u64 G) {
 }
 
 // Resolve the huge groups.  hpos[k] = sorted position of k (ascending); gid / gstart / n_groups describe the groups in
-// sorted-position space; cand = k_chain_candidates' result there.  Writes root[] for the positions of huge groups.
-static void chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *srec, const u64 *skey, int cb, const u32 *gid, const u32 *gstart,
+// sorted-position space; cand = k_chain_candidates' result there.  Writes root[] for the positions of huge groups and
+// returns true; returns false (root[] untouched) if the picks have not settled after SWG_FIXPOINT_MAX_ROUNDS rounds (default
+// 256): a dependency chain that long is walked faster sequentially, and the caller hands the groups to k_chain_resolve_warp.
+static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *srec, const u64 *skey, int cb, const u32 *gid, const u32 *gstart,
                            u32 n_groups, u32 n_m, const Cand *cand, u64 G, u32 *root, u32 *bsum) {
     cudaStream_t st = c->stream;
     LaunchCounter &lc = c->lc;
@@ -328,6 +330,7 @@ static void chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
     }
     u32 *h = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
     int rounds = 0;
+    const int max_rounds = getenv("SWG_FIXPOINT_MAX_ROUNDS") ? atoi(getenv("SWG_FIXPOINT_MAX_ROUNDS")) : 256;
     u64 total_recomputed = 0;
     auto t_round = std::chrono::steady_clock::now();
     while (true) {
@@ -379,6 +382,10 @@ static void chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
             t_round = t1;
         }
         if (h[1] == 0) break; // the snapshot of this round equals the picks: it is the fixed point
+        if (rounds >= max_rounds) {
+            if (verbose) fprintf(stderr, "[swg fixpoint] not settled after %d rounds (%u picks still changing): sequential walk instead\n", rounds, h[1]);
+            return false;
+        }
     }
     if (getenv("SWG_FIXPOINT_VERIFY")) {
         // Self-check for sizes no oracle reaches: (*) has exactly one solution, so it suffices that EVERY position, evaluated
@@ -416,6 +423,7 @@ static void chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
     }
     if (verbose) fprintf(stderr, "[swg fixpoint] %u positions in huge groups, %d rounds, %llu re-evaluations\n", n_h, rounds,
                          (unsigned long long)total_recomputed);
+    return true;
 }
 
 } // namespace swg

@@ -575,7 +575,16 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             u32 *hpos = A.take<u32>(n_huge);
             scan_apply([=] __device__(u32 p) -> u32 { return is_huge(gid[p]) ? 1u : 0u; },
                        [=] __device__(u32 p, u32 ex, u32 v) { if (v) hpos[ex] = p; }, n_m, bsum, d_tot + 3, st, lc);
-            chain_fixpoint(c, n_huge, hpos, srec, skey, gshift, gid, gstart, n_groups, n_m, cand, cfg.scaffold_gap, root, bsum);
+            if (!chain_fixpoint(c, n_huge, hpos, srec, skey, gshift, gid, gstart, n_groups, n_m, cand, cfg.scaffold_gap, root, bsum)) {
+                // a dependency chain longer than the round limit: the huge groups go through the sequential warp walk after all
+                // (bps / root still hold k_chain_candidates' initial state for them)
+                SWG_CUDA(cudaMemsetAsync(bb_ctr + 2, 0, 2 * sizeof(u32), st));
+                scan_apply([=] __device__(u32 g) -> u32 { return (grp_has_cand[g] && is_huge(g)) ? 1u : 0u; },
+                           [=] __device__(u32 g, u32 ex, u32 v) { if (v) work_big[ex] = g; }, n_groups, bsum, bb_ctr + 2, st, lc);
+                k_chain_resolve_warp<<<(u32)c->sm_count * 4, 128, 0, st>>>(cand, srec, skey, gstart, n_groups, n_m, work_big, bb_ctr + 2, gshift,
+                                                                          cfg.scaffold_gap, bps, root, bb_ctr + 3);
+                lc.n++;
+            }
         }
     }
     stage_mark(c, "ch_aggregate");

@@ -170,6 +170,15 @@ def test_fixpoint_everywhere(ctx, yeast, what, monkeypatch):
             check(ctx, cfg, t, f"fixpoint-fuzz{seed}")
 
 
+def test_fixpoint_round_limit_falls_back_to_the_walk(ctx, monkeypatch):
+    """Picks that have not settled after SWG_FIXPOINT_MAX_ROUNDS rounds: the groups go through the sequential warp walk."""
+    monkeypatch.setenv("SWG_FIXPOINT_MIN", "2")
+    monkeypatch.setenv("SWG_FIXPOINT_MAX_ROUNDS", "2")
+    check(ctx, swg.FilterConfig(), synth.skew(n_pile=20_000, n_tiny_groups=3_000, seed=5, window=3_000_000), "round-limit")
+    t = fuzz_table(503, 6000, n_genomes=1, n_chr=2, span=4000, max_len=400, zero_len_frac=0.0)
+    check(ctx, swg.FilterConfig.from_cli(scaffold_jump="1000", scaffold_mass="0", keep_self=True), t, "round-limit-dense")
+
+
 def test_fixpoint_pile_200k(ctx):
     """configs[4] at the largest size the oracle's O(n * window) chaining finishes in seconds: the two 100 k strand groups
     of the pile are above the default threshold, so this is the fixed-point path as shipped."""
