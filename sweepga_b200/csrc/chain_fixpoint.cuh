@@ -45,6 +45,7 @@ struct FxArrays {
     u32 *cnt, *off;    // picker lists: off[j] .. off[j+1]
     u64 *minpd;        // smallest d over all pickers of j (NONE64: nobody picks j)
     u32 *minpi;        // the first picker of j that has that d
+    u32 *firstp;       // the first picker of j at all (NONE32: nobody)
     u32 *li;           // picker position
     u64 *ld;           // picker d
     u32 *xoff;         // X(i) lives at pool[xoff .. xoff + xcnt)
@@ -61,6 +62,7 @@ struct FxArrays {
 __device__ __forceinline__ bool fx_eligible(const FxArrays &f, u32 i, u32 j, u64 d, u32 mi /* = minpi[j] */) {
     if (mi < i) return false;
     if (mi == i) return true; // i itself holds the minimum and is the first to: every earlier picker has a larger d
+    if (f.firstp[j] >= i) return true; // nobody picks j before i (ncu: the list walk below was 30 % of the stall samples of round 1)
     const u32 a = f.off[j], b = f.off[j + 1];
     for (u32 p = a; p < b; p++)
         if (f.li[p] < i && f.ld[p] <= d) return false;
@@ -293,6 +295,7 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
     f.off = A.take<u32>((size_t)n_h + 1);
     f.minpd = A.take<u64>(n_h);
     f.minpi = A.take<u32>(n_h);
+    f.firstp = A.take<u32>(n_h);
     f.li = A.take<u32>(n_h);
     f.ld = A.take<u64>(n_h);
     f.xoff = A.take<u32>(n_h);
@@ -339,12 +342,14 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
         SWG_CUDA(cudaMemsetAsync(f.cnt, 0, sizeof(u32) * (size_t)n_h, st));
         SWG_CUDA(cudaMemsetAsync(f.minpd, 0xFF, sizeof(u64) * (size_t)n_h, st));
         SWG_CUDA(cudaMemsetAsync(f.minpi, 0xFF, sizeof(u32) * (size_t)n_h, st));
+        SWG_CUDA(cudaMemsetAsync(f.firstp, 0xFF, sizeof(u32) * (size_t)n_h, st));
         SWG_CUDA(cudaMemsetAsync(f.ctrs, 0, 4 * sizeof(u32), st));
         launch_for<t_fx_count>(n_h, st, lc, [=] __device__(u32 k) {
             const u32 j = g.pick[k];
             if (j != NONE32) {
                 atomicAdd(&g.cnt[j], 1u);
                 atomicMin((unsigned long long *)&g.minpd[j], (unsigned long long)g.pd[k]);
+                atomicMin(&g.firstp[j], k);
             }
         });
         launch_for<t_fx_minpi>(n_h, st, lc, [=] __device__(u32 k) {
