@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """configs[4] (skew) at reduced scale: one dense pile + many tiny groups; times the GPU path and checks parity
-against the oracle.  Usage: python profiles/bench_skew.py n_pile n_tiny_groups [check_oracle]"""
+against the oracle.  Usage: python profiles/bench_skew.py n_pile n_tiny_groups [check_oracle] [scaffold_dist]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -11,7 +11,7 @@ import oracle_lib
 n_pile, n_tiny = int(sys.argv[1]), int(sys.argv[2])
 check = len(sys.argv) > 3 and sys.argv[3] == "1"
 t = synth.skew(n_pile=n_pile, n_tiny_groups=n_tiny, seed=5)
-cfg = swg.FilterConfig()
+cfg = swg.FilterConfig.from_cli(scaffold_dist=sys.argv[4]) if len(sys.argv) > 4 else swg.FilterConfig()
 ctx = swg.Context(0)
 if n_pile < 10_000_000:  # warm-up (arena growth, first-touch); skipped for the largest piles to keep the run short
     ctx.filter(cfg, t)

@@ -942,26 +942,37 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                 const u32 i = rlist[x0];
                 const u64 pair = ((u64)in.qid[i] << sb) | in.tid[i];
                 const u64 qc = ((u64)in.qs[i] + in.qe[i]) / 2, tc = ((u64)in.ts[i] + in.te[i]) / 2;
-                const u64 qlo = qc > D ? qc - D : 0;
+                // first anchor of the pair at or right of the query center; the scan runs outwards from there and stops once
+                // the query-axis distance alone exceeds the best distance found: dist = floor(sqrt(qd^2 + td^2)) >= qd - 1 (the f64
+                // square root of a rounded sum can fall one short), so nothing beyond qd > best + 1 can win or tie.  On a repeat pile
+                // (10^5..10^6 anchors inside +-D) that is a handful of anchors instead of all of them.
                 u32 lo = 0, hi = NA;
                 while (lo < hi) {
                     u32 mid = (lo + hi) >> 1;
                     const u64 mp = apair[mid];
-                    if (mp < pair || (mp == pair && (u64)aqc[mid] < qlo)) lo = mid + 1; else hi = mid;
+                    if (mp < pair || (mp == pair && (u64)aqc[mid] < qc)) lo = mid + 1; else hi = mid;
                 }
                 u64 best_d = NONE64;
                 u32 best_a = NONE32;
-                for (u32 x = lo; x < NA; x++) {
-                    if (apair[x] != pair) break;
-                    const u64 c_a = aqc[x];
-                    if (c_a > qc + D) break;
+                auto visit = [&](u32 x, u64 qd) {
                     const u32 a = avc[x];
-                    const u64 qd = c_a > qc ? c_a - qc : qc - c_a;
                     const u64 atc = ((u64)in.ts[a] + in.te[a]) / 2;
                     const u64 td = atc > tc ? atc - tc : tc - atc;
-                    if (td > D) continue; // then floor(sqrt(qd^2+td^2)) > D
+                    if (td > D) return; // then floor(sqrt(qd^2+td^2)) > D
                     const u64 dist = (u64)__dsqrt_rn((double)(qd * qd + td * td));
                     if (dist <= D && (dist < best_d || (dist == best_d && a < best_a))) { best_d = dist; best_a = a; }
+                };
+                for (u32 x = lo; x < NA && apair[x] == pair; x++) {
+                    const u64 qd = (u64)aqc[x] - qc;
+                    if (qd > D || (best_a != NONE32 && qd > best_d + 1)) break;
+                    visit(x, qd);
+                }
+                for (u32 x = lo; x > 0;) {
+                    x--;
+                    if (apair[x] != pair) break;
+                    const u64 qd = qc - (u64)aqc[x];
+                    if (qd > D || (best_a != NONE32 && qd > best_d + 1)) break;
+                    visit(x, qd);
                 }
                 if (best_a != NONE32) { status[i] = 2; chain_id[i] = chain_id[best_a]; }
             });
