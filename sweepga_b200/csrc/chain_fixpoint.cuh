@@ -11,16 +11,23 @@
 // mapping); here ALL positions are evaluated against a snapshot of the picks and the evaluation is repeated until nothing
 // changes.  By induction on i the positions below the first wrong one stay correct and that one becomes correct in the
 // next round, so the iteration ends in the reference's picks; measured on the configs[4] piles it needs 6 rounds for a
-// 100 k group and 14 for a 500 k group, and the number of positions that have to be re-evaluated shrinks geometrically.
+// 100 k group, 14 for a 500 k group and 56 for the two 25 M groups of the full configuration (13.8 s for the whole filter
+// call), and the number of positions that have to be re-evaluated shrinks geometrically.
 //
 // A round:
-//   1. snapshot: picker lists per successor j (CSR: count, scan, fill) and minpd[j] = smallest d over all pickers of j
+//   1. snapshot: picker lists per successor j (CSR: count, scan, fill), minpd[j] = smallest d over all pickers of j,
+//      minpi[j] = the first picker holding it, firstp[j] = the first picker at all: "d < B(i,j)?" is answered from these
+//      three words in all but a few cases, without walking the list
 //   2. k_fx_check (thread per position): position i must be re-evaluated iff its pick is now blocked (an earlier picker
 //      of the same j with d' <= d) or one of the candidates that rank BEFORE its pick — X(i), all of them ineligible when
 //      the pick was made, remembered explicitly — has become eligible.  This test is exact: a position whose pick stands
 //      and whose X(i) is still blocked would pick the same j again.
 //   3. k_fx_recompute (warp per listed position): the pruned window search of the sequential walk
-//      (bb_best_successor_warp) with eligibility against the snapshot, then a second pruned pass that collects X(i).
+//      (bb_best_successor_warp) with eligibility against the snapshot.  The blocked candidates the search meets while they
+//      still beat the lane's best are recorded in shared memory — a superset of X(i), filtered against the final pick
+//      (fx_filter_seen); only if that record overflows, a second pruned pass collects X(i) (fx_collect_blocked).
+// A huge group whose picks have not settled after SWG_FIXPOINT_MAX_ROUNDS rounds goes to the sequential walk after all;
+// SWG_FIXPOINT_VERIFY=1 re-evaluates every position from scratch against the final picks (0 of 50 M change on configs[4]).
 // The first round starts from k_chain_candidates' unconstrained arg-min (X(i) is empty there by definition).
 // After the last round pred[j] = the last picker of j, roots by pointer jumping (union_find.rs:25-41: the root of a set is
 // its head), results scattered back to the sorted positions.  Everything runs in the compact index space k of the positions
