@@ -179,6 +179,16 @@ def test_fixpoint_round_limit_falls_back_to_the_walk(ctx, monkeypatch):
     check(ctx, swg.FilterConfig.from_cli(scaffold_jump="1000", scaffold_mass="0", keep_self=True), t, "round-limit-dense")
 
 
+@pytest.mark.parametrize("case", ["defaults", "1:1_rescue", "tight_jump"])
+def test_fixpoint_and_inversion_grid_with_wide_keys(ctx, yeast, case, monkeypatch):
+    """The huge-group paths behind the two-stage (> 64-bit key) sorts: group ids without the strand bit position."""
+    monkeypatch.setenv("SWG_FORCE_WIDE_KEYS", "1")
+    monkeypatch.setenv("SWG_FIXPOINT_MIN", "2")
+    monkeypatch.setenv("SWG_FIXPOINT_VERIFY", "1")
+    monkeypatch.setenv("SWG_INV_GRID", "1")
+    check(ctx, swg.FilterConfig.from_cli(**CLI_CASES[case]), yeast, "wide-" + case)
+
+
 def test_fixpoint_pile_200k(ctx):
     """configs[4] at the largest size the oracle's O(n * window) chaining finishes in seconds: the two 100 k strand groups
     of the pile are above the default threshold, so this is the fixed-point path as shipped."""
