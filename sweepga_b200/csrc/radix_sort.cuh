@@ -19,7 +19,10 @@
 
 namespace swg {
 
-constexpr int RS_BITS = 8;
+#ifndef SWG_RS_BITS
+#define SWG_RS_BITS 8
+#endif
+constexpr int RS_BITS = SWG_RS_BITS; // digit width; 9 needs SWG_RS_THREADS >= 512 (one thread per digit in the scans)
 constexpr int RS_RADIX = 1 << RS_BITS;
 #ifndef SWG_RS_THREADS
 #define SWG_RS_THREADS 384
@@ -31,6 +34,7 @@ constexpr int RS_THREADS = SWG_RS_THREADS;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ITEMS = SWG_RS_ITEMS;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS; // 5376 pairs (384 threads x 14)
+static_assert(RS_RADIX <= RS_THREADS, "one thread per digit: the CTA must have at least 2^RS_BITS threads");
 constexpr int RS_MAX_PASSES = 8;
 #ifndef SWG_RS_LOOKBACK
 #define SWG_RS_LOOKBACK 8
@@ -84,7 +88,7 @@ __global__ void __launch_bounds__(512) rs_histogram_kernel(const u64 *__restrict
 
 // exclusive scan of each pass's 256 bins, in place (one block per pass, 256 threads)
 __global__ void rs_scan_hist_kernel(u32 *__restrict__ hist) {
-    __shared__ u32 ws[8];
+    __shared__ u32 ws[RS_RADIX / 32];
     u32 *h = hist + blockIdx.x * RS_RADIX;
     u32 v = h[threadIdx.x];
     u32 x = v;
