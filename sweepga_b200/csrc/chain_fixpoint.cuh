@@ -18,7 +18,9 @@
 //   1. snapshot: picker lists per successor j (CSR: count, scan, fill), minpd[j] = smallest d over all pickers of j,
 //      minpi[j] = the first picker holding it, firstp[j] = the first picker at all: "d < B(i,j)?" is answered from these
 //      three words in all but a few cases, without walking the list
-//   2. k_fx_check (thread per position): position i must be re-evaluated iff its pick is now blocked (an earlier picker
+//   2. k_fx_check (thread per position; a position is skipped outright when no picker list among the successors it can
+//      depend on — up to xhi[i] = max(pick(i), X(i)) — changed in the last round: dirty blocks of 512 successors and their
+//      prefix counts): position i must be re-evaluated iff its pick is now blocked (an earlier picker
 //      of the same j with d' <= d) or one of the candidates that rank BEFORE its pick — X(i), all of them ineligible when
 //      the pick was made, remembered explicitly — has become eligible.  This test is exact: a position whose pick stands
 //      and whose X(i) is still blocked would pick the same j again.
@@ -41,6 +43,7 @@ struct t_fx_init; struct t_fx_count; struct t_fx_minpi; struct t_fx_all; struct 
 constexpr u32 FX_XCAP = 1024;     // blocked candidates remembered per position; a position with more is re-evaluated every round
 constexpr u16 FX_XOVER = 0xFFFF; // xcnt value of such a position
 constexpr u32 FX_REV = 0x80000000u; // gend bit: the group is a '-' strand group
+constexpr int FX_DB = 9;            // dirty blocks of 512 successors
 
 struct FxArrays {
     u32 n;             // positions in huge groups
@@ -61,6 +64,9 @@ struct FxArrays {
     unsigned long long *pool_top; // 64-bit: refused requests keep counting and must never wrap into live slots
     u32 pool_cap;
     u32 *list;         // positions to re-evaluate this round
+    u32 *xhi;          // largest position in {pick(i)} U X(i) (i itself if there is none): how far i's verdict can depend
+    u32 *dirty, *dps;  // per block of successors: some picker list in it changed in the last round; prefix counts of that
+    u32 use_dirty;     // 0: check every position (first round, or the feature is off)
     u32 *ctrs;         // [0] list length, [1] picks changed this round, [2] recompute work counter, [3] slots refused (pool full)
 };
 
@@ -99,8 +105,13 @@ __global__ void __launch_bounds__(256) k_fx_check(FxArrays f, u64 G) {
     if (k < f.n) {
         const u16 xc = f.xcnt[k];
         const u32 j = f.pick[k];
+        bool untouched = false;
+        if (xc != FX_XOVER && f.use_dirty) { // no picker list this position depends on has changed since its last verdict
+            const u32 hi = f.xhi[k];
+            untouched = hi <= k || f.dps[(hi >> FX_DB) + 1] == f.dps[(k + 1) >> FX_DB];
+        }
         if (xc == FX_XOVER) need = true;
-        else {
+        else if (!untouched) {
             if (j != NONE32 && f.off[j + 1] - f.off[j] > 1) need = !fx_eligible(f, k, j, f.pd[k], f.minpi[j]);
             if (!need && xc) {
                 const uint4 a = f.rec[k];
@@ -258,8 +269,18 @@ __global__ void __launch_bounds__(128) k_fx_recompute(FxArrays f, u64 G) {
         __syncwarp();
         u32 xo = 0;
         u16 xc = FX_XOVER;
+        u32 hi = bj != NONE32 ? bj : i;
+        if (xn <= FX_XCAP)
+            for (u32 q = lane; q < xn; q += 32) hi = max(hi, xs[q]);
+        hi = __reduce_max_sync(full, hi);
         if (lane == 0) {
-            if (bj != f.pick[i]) atomicAdd(&f.ctrs[1], 1u);
+            const u32 old = f.pick[i];
+            if (bj != old) {
+                atomicAdd(&f.ctrs[1], 1u);
+                if (old != NONE32) f.dirty[old >> FX_DB] = 1; // the picker lists of both successors change
+                if (bj != NONE32) f.dirty[bj >> FX_DB] = 1;
+            }
+            f.xhi[i] = hi;
             f.pick[i] = bj;
             f.pd[i] = bd;
             if (xn <= FX_XCAP) {
@@ -318,6 +339,12 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
     f.pool = A.take<u32>(f.pool_cap);
     f.pool_top = A.take<unsigned long long>(1);
     f.list = A.take<u32>(n_h);
+    const u32 n_blk = (n_h >> FX_DB) + 1;
+    f.xhi = A.take<u32>(n_h);
+    f.dirty = A.take<u32>(n_blk);
+    f.dps = A.take<u32>((size_t)n_blk + 1);
+    f.use_dirty = 0;
+    const bool dirty_on = getenv("SWG_FX_NO_DIRTY") == nullptr; // testing aid: check every position in every round
     f.ctrs = A.take<u32>(4);
     u32 *scan_tot = A.take<u32>(1);
     SWG_CUDA(cudaMemsetAsync(f.xcnt, 0, sizeof(u16) * (size_t)n_h, st));
@@ -334,6 +361,7 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
             g.gend[k] = (k + (e - p)) | (fwd ? 0u : FX_REV);
             const Cand cd = cand[p];
             g.pick[k] = cd.j == NONE32 ? NONE32 : k + (cd.j - p);
+            g.xhi[k] = cd.j == NONE32 ? k : k + (cd.j - p);
             g.pd[k] = cd.d;
             g.c0[k] = cd.c0 == NONE32 ? NONE32 : k + (cd.c0 - p);
         });
@@ -344,6 +372,18 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
     u64 total_recomputed = 0;
     auto t_round = std::chrono::steady_clock::now();
     while (true) {
+        // 0. which blocks of successors saw a picker list change in the last round (prefix counts for k_fx_check)
+        if (dirty_on && rounds > 0) {
+            const FxArrays gd = f;
+            scan_apply([=] __device__(u32 b) -> u32 { return gd.dirty[b]; },
+                       [=] __device__(u32 b, u32 ex, u32 v) {
+                           gd.dps[b] = ex;
+                           if (b + 1 == n_blk) gd.dps[n_blk] = ex + v;
+                       },
+                       n_blk, bsum, scan_tot, st, lc);
+            f.use_dirty = 1;
+        }
+        SWG_CUDA(cudaMemsetAsync(f.dirty, 0, sizeof(u32) * (size_t)n_blk, st));
         // 1. snapshot of the picks
         const FxArrays g = f;
         SWG_CUDA(cudaMemsetAsync(f.cnt, 0, sizeof(u32) * (size_t)n_h, st));
