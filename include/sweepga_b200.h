@@ -111,7 +111,9 @@ typedef struct swg_mappings {
     const uint32_t *target_end;
     const uint32_t *block_length;
     const uint32_t *matches;
-    const double *identity;
+    const double *identity;       /* may be NULL: identity = matches / max(block_length, 1), the parser's value for a
+                                     record without dv:f: / cg:Z: tags (paf_filter.rs:322), derived on the device
+                                     (same IEEE division, same bits) — 8 B per record less to upload */
     const uint8_t *strand;        /* '+' is forward; any other byte is reverse (paf_filter.rs:311) */
     const double *score;          /* optional (may be NULL): caller-computed plane-sweep score,
                                      used instead of the device-computed one (glibc-log exactness) */
@@ -146,6 +148,11 @@ typedef struct swg_stats {
     uint64_t n_sort_pairs;        /* ... over how many (key,payload) pairs                      */
     double ms_tokenize;           /* swg_filter_paf: newline scan + parse + name interning on the device */
     double ms_write;              /* swg_filter_paf: output assembly on the device + download + write()  */
+    uint64_t exact_rerank;        /* 1: the call was redone with every logarithm taken from the HOST libm (near ties
+                                     on a host whose log() differs from the device's port, or SWG_EXACT_SCORES=always) */
+    uint64_t sort_bytes_per_pair; /* bytes one timed sort pass moves per pair (24: key+payload pairs, 16: packed words) */
+    uint64_t h2d_bytes, d2h_bytes;/* swg_filter: bytes copied host->device / device->host by this call        */
+    uint64_t reserved[4];
 } swg_stats;
 
 typedef struct swg_ctx swg_ctx;
@@ -185,6 +192,20 @@ int swg_download_result(swg_ctx *ctx, uint64_t n, const swg_result *dev_res, swg
 int swg_last_chain_keys(swg_ctx *ctx, uint64_t cap, uint32_t *first_index_genome_pair, uint32_t *first_index_group,
                         uint64_t *n_chains);
 
+/* Merging the chain numbering of shards needs less than the per-chain keys above: the kept chains of one genome-pair unit
+ * are numbered consecutively both on one GPU and in the merged numbering.  swg_last_chain_units reports, for the last
+ * call, the runs of chains that share a unit: the input index A of the unit's first stage-1 record and the (1-based) local
+ * number of the run's first chain, in chain order; *n_units receives the count (cap = 0: only the count).  The driver sorts
+ * all shards' runs by the GLOBAL index of A, takes the exclusive prefix sum of the run lengths and hands every shard its
+ * own runs' offsets: swg_renumber_chains_device adds unit_delta[r] to the chain number of every record whose chain belongs
+ * to run r (chain_id_dev: DEVICE array of n entries; the run arrays: HOST).  swg_pack_status_device packs status bytes
+ * into 2 bits per record (16 per u32, record i in bits 2*(i mod 16)) for the keep-bitmap gather; both arrays on the DEVICE. */
+int swg_last_chain_units(swg_ctx *ctx, uint64_t cap, uint32_t *unit_first_index, uint32_t *unit_first_chain,
+                         uint64_t *n_units);
+int swg_renumber_chains_device(swg_ctx *ctx, uint64_t n, uint32_t *chain_id_dev, uint64_t n_units,
+                               const uint32_t *unit_first_chain, const int64_t *unit_delta);
+int swg_pack_status_device(swg_ctx *ctx, uint64_t n, const uint8_t *status_dev, uint32_t *packed_dev);
+
 /* ---- primitives: plane_sweep_exact.rs:268-461 --------------------------- *
  * keep[i] = 1 iff local index i is in the Vec<usize> the reference returns.
  * n_keep = SWG_KEEP_ALL for usize::MAX.  HOST buffers.                          */
@@ -206,6 +227,23 @@ int swg_plane_sweep_both(swg_ctx *ctx, uint64_t n, const uint32_t *qs, const uin
  * that order unspecified).                                                                                     */
 int swg_plane_sweep_core(swg_ctx *ctx, uint64_t n, const uint32_t *begin, const uint32_t *end, const double *score,
                          uint64_t max_to_keep, double overlap_threshold, uint64_t *out_idx, uint64_t *n_out);
+
+/* ---- verification: the f64 expressions of the path, evaluated on the device ----------------------------------- *
+ * The plane sweeps rank by score_with_function (src/plane_sweep_exact.rs:29-86: identity * ln(query span) by default)
+ * and the chain filter compares weighted_identity = sum_matches / (sum_block + max(ln(gap), 0)) with a threshold
+ * (src/paf_filter.rs:896-913).  The device computes ln() with a port of glibc's log (csrc/glibc_log.cuh) so that these
+ * values carry the bits of the host's f64::ln; these entry points let a caller (and tests/test_scores_gpu.py) check that
+ * on any argument set.  HOST buffers in and out.                                                                   */
+int swg_score_column(swg_ctx *ctx, uint64_t n, const double *identity, const uint32_t *query_start,
+                     const uint32_t *query_end, int scoring, double *score_out);
+int swg_chain_identity(swg_ctx *ctx, uint64_t n, const uint64_t *total_length, const uint64_t *sum_block,
+                       const uint64_t *sum_matches, double *weighted_identity_out);
+/* 1 when swg_create found the device's ln() equal to the host libm's log() on its probe set (65 536 integer arguments),
+ * 0 when not: near ties seen by a sweep then make swg_filter redo the call with host-computed logarithms
+ * (swg_stats.exact_rerank; SWG_EXACT_SCORES=always|never overrides).                                               */
+int swg_log_matches_host(const swg_ctx *ctx);
+/* The port itself evaluated on the host (same operations, fma() from libm): lets a CPU-only test compare it with log(). */
+double swg_glibc_log_host(double x);
 
 /* ---- host-side mirrors of the flag parsers ------------------------------ */
 /* src/main.rs:244-293 (CLI grammar).  *mode, *per_query, *per_target (SWG_NO_LIMIT = None). */
@@ -284,6 +322,10 @@ int swg_filter_file(swg_ctx *ctx, const swg_config *cfg, const char *in_path, co
  * Size-balanced (LPT) assignment of genome-pair units (P(q),P(t)) to n_shards.
  * shard_of[i] receives the shard of record i.  Host only, no device needed.     */
 int swg_shard_plan(const swg_mappings *host_in, int n_shards, uint32_t *shard_of, uint64_t *shard_sizes);
+/* The same rule on unit sizes alone (largest unit first, ties by unit index, onto the least loaded shard, ties by the
+ * lowest shard): for drivers that know the unit sizes without holding the table (bench.py generates only its shard). */
+int swg_shard_plan_units(uint64_t n_units, const uint64_t *unit_sizes, int n_shards, uint32_t *shard_of_unit,
+                         uint64_t *shard_sizes);
 
 const char *swg_version(void);
 

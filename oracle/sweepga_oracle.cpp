@@ -720,6 +720,21 @@ double orc_score(uint64_t qs, uint64_t qe, double identity, int scoring) {
     return orc::score_of(m, scoring);
 }
 
+// score_with_function (plane_sweep_exact.rs:29-86) over columns
+void orc_score_column(uint64_t n, const uint32_t *qs, const uint32_t *qe, const double *identity, int scoring, double *out) {
+    for (uint64_t i = 0; i < n; i++) out[i] = orc_score(qs[i], qe[i], identity[i], scoring);
+}
+// weighted_identity of a chain from its aggregates (paf_filter.rs:896-913), the statement sequence of merge_chains above
+void orc_chain_identity(uint64_t n, const uint64_t *total_length, const uint64_t *sum_block, const uint64_t *sum_matches, double *out) {
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t total = total_length[i], sb = sum_block[i], sm = sum_matches[i];
+        uint64_t gap = total > sb ? total - sb : 0; // saturating_sub
+        double lg = gap > 0 ? std::max(std::log((double)gap), 0.0) : 0.0;
+        double eff = (double)sb + lg;
+        out[i] = eff > 0.0 ? (double)sm / eff : 0.0;
+    }
+}
+
 // returns the number kept; out_idx receives the kept indices in the reference's output order
 int orc_plane_sweep_core(uint64_t n, const uint32_t *begin, const uint32_t *end, const double *score,
                          uint64_t max_keep, double thr, uint64_t *out_idx) {

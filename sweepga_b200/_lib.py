@@ -51,7 +51,8 @@ class swg_stats(C.Structure):
         ("n_rescued", C.c_uint64), ("n_kept", C.c_uint64), ("score_near_ties", C.c_uint64), ("gpu_launches", C.c_uint64),
         ("ms_h2d", C.c_double), ("ms_device", C.c_double), ("ms_d2h", C.c_double),
         ("ms_sort_passes", C.c_double), ("n_sort_passes", C.c_uint64), ("n_sort_pairs", C.c_uint64),
-        ("ms_tokenize", C.c_double), ("ms_write", C.c_double),
+        ("ms_tokenize", C.c_double), ("ms_write", C.c_double), ("exact_rerank", C.c_uint64), ("sort_bytes_per_pair", C.c_uint64),
+        ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("reserved", C.c_uint64 * 4),
     ]
 
 
@@ -71,6 +72,10 @@ SYMBOLS = [
     ("swg_release", None, [_vp, _mapp, _resp]),
     ("swg_download_result", C.c_int, [_vp, C.c_uint64, _resp, _resp]),
     ("swg_last_chain_keys", C.c_int, [_vp, C.c_uint64, u32p, u32p, u64p]),
+    ("swg_score_column", C.c_int, [_vp, C.c_uint64, f64p, u32p, u32p, C.c_int, f64p]),
+    ("swg_chain_identity", C.c_int, [_vp, C.c_uint64, u64p, u64p, u64p, f64p]),
+    ("swg_log_matches_host", C.c_int, [_vp]),
+    ("swg_glibc_log_host", C.c_double, [C.c_double]),
     ("swg_plane_sweep_core", C.c_int, [_vp, C.c_uint64, u32p, u32p, f64p, C.c_uint64, C.c_double, u64p, u64p]),
     ("swg_plane_sweep_query", C.c_int, _sweep_args),
     ("swg_plane_sweep_target", C.c_int, _sweep_args),
@@ -99,6 +104,10 @@ SYMBOLS = [
     ("swg_filter_paf_host", C.c_int, [_vp, _cfgp, C.c_char_p, C.c_char_p, _statp]),
     ("swg_filter_file", C.c_int, [_vp, _cfgp, C.c_char_p, C.c_char_p, C.c_int, _statp]),
     ("swg_shard_plan", C.c_int, [_mapp, C.c_int, u32p, u64p]),
+    ("swg_shard_plan_units", C.c_int, [C.c_uint64, u64p, C.c_int, u32p, u64p]),
+    ("swg_last_chain_units", C.c_int, [_vp, C.c_uint64, u32p, u32p, u64p]),
+    ("swg_renumber_chains_device", C.c_int, [_vp, C.c_uint64, C.c_void_p, C.c_uint64, u32p, C.POINTER(C.c_int64)]),
+    ("swg_pack_status_device", C.c_int, [_vp, C.c_uint64, C.c_void_p, C.c_void_p]),
     ("swg_version", C.c_char_p, []),
 ]
 

@@ -20,6 +20,8 @@ from typing import Optional
 
 import numpy as np
 
+from workloads.table import Table, prefix_P, prefix_P2, prefix_ids  # noqa: F401  (pure numpy)
+
 from . import _lib
 from ._lib import lib
 
@@ -200,41 +202,10 @@ def filter_config_from_align_cfg(num_mappings="many:many", scaffold_filter="many
 
 
 # ------------------------------------------------------------------------------------------------
-@dataclass
-class MappingTable:
-    """The compact SoA that replaces Vec<RecordMeta> (include/sweepga_b200.h: swg_mappings)."""
-    query_id: np.ndarray
-    target_id: np.ndarray
-    query_start: np.ndarray
-    query_end: np.ndarray
-    target_start: np.ndarray
-    target_end: np.ndarray
-    block_length: np.ndarray
-    matches: np.ndarray
-    identity: np.ndarray
-    strand: np.ndarray              # uint8: ord('+') forward, anything else reverse
-    seq_genome_id: np.ndarray       # per sequence: id of P(name)
-    seq_genome2_id: np.ndarray      # per sequence: id of P2(name)
-    score: Optional[np.ndarray] = None
-    names: Optional[list] = None
-    rank: Optional[np.ndarray] = None  # PAF line number of each record (parse only)
-
-    def __post_init__(self):
-        for f in ("query_id", "target_id", "query_start", "query_end", "target_start", "target_end", "block_length", "matches",
-                  "seq_genome_id", "seq_genome2_id"):
-            setattr(self, f, np.ascontiguousarray(getattr(self, f), dtype=np.uint32))
-        self.identity = np.ascontiguousarray(self.identity, dtype=np.float64)
-        self.strand = np.ascontiguousarray(self.strand, dtype=np.uint8)
-        if self.score is not None:
-            self.score = np.ascontiguousarray(self.score, dtype=np.float64)
-
-    @property
-    def n(self):
-        return int(self.query_id.shape[0])
-
-    @property
-    def n_seq(self):
-        return int(self.seq_genome_id.shape[0])
+class MappingTable(Table):
+    """The compact SoA that replaces Vec<RecordMeta> (include/sweepga_b200.h: swg_mappings): the numpy column table of
+    `workloads.table.Table` plus its ctypes view.  `identity=None` leaves swg_mappings.identity NULL: the device then
+    derives matches / max(block_length, 1) itself (src/paf_filter.rs:322)."""
 
     def to_c(self) -> _lib.swg_mappings:
         m = _lib.swg_mappings()
@@ -242,55 +213,11 @@ class MappingTable:
         for f in ("query_id", "target_id", "query_start", "query_end", "target_start", "target_end", "block_length", "matches",
                   "seq_genome_id", "seq_genome2_id"):
             setattr(m, f, _ptr(getattr(self, f), C.c_uint32))
-        m.identity = _ptr(self.identity, C.c_double)
+        m.identity = _ptr(self.identity, C.c_double) if self.identity is not None else None
         m.strand = _ptr(self.strand, C.c_uint8)
         m.score = _ptr(self.score, C.c_double) if self.score is not None else None
         m.n_seq = self.n_seq
         return m
-
-    def take(self, idx):
-        """Sub-table of the given record indices (sequence table shared)."""
-        g = lambda a: a[idx]
-        return MappingTable(g(self.query_id), g(self.target_id), g(self.query_start), g(self.query_end), g(self.target_start),
-                            g(self.target_end), g(self.block_length), g(self.matches), g(self.identity), g(self.strand),
-                            self.seq_genome_id, self.seq_genome2_id, None if self.score is None else g(self.score), self.names)
-
-    @staticmethod
-    def from_names(qnames, tnames, qs, qe, ts, te, blen, matches, identity, strand):
-        """Intern names (first-appearance ids, one shared table) and derive P / P2 prefix ids."""
-        ids, names = {}, []
-        def iid(s):
-            if s not in ids:
-                ids[s] = len(names)
-                names.append(s)
-            return ids[s]
-        q = np.empty(len(qnames), np.uint32)
-        t = np.empty(len(qnames), np.uint32)
-        for i, (a, b) in enumerate(zip(qnames, tnames)):
-            q[i] = iid(a)
-            t[i] = iid(b)
-        P, P2 = prefix_ids(names)
-        st = np.array([ord("+") if s == "+" else ord("-") for s in strand], np.uint8)
-        return MappingTable(q, t, qs, qe, ts, te, blen, matches, identity, st, P, P2, None, names)
-
-
-def prefix_P(name: str) -> str:
-    """src/paf_filter.rs:1022-1030"""
-    p = name.rfind("#")
-    return name if p < 0 else name[: p + 1]
-
-
-def prefix_P2(name: str) -> str:
-    """src/plane_sweep_scaffold.rs:13-22"""
-    parts = name.split("#")
-    return f"{parts[0]}#{parts[1]}#" if len(parts) >= 2 else name
-
-
-def prefix_ids(names):
-    pid, p2id = {}, {}
-    P = np.array([pid.setdefault(prefix_P(n), len(pid)) for n in names], np.uint32)
-    P2 = np.array([p2id.setdefault(prefix_P2(n), len(p2id)) for n in names], np.uint32)
-    return P, P2
 
 
 # ------------------------------------------------------------------------------------------------
@@ -352,6 +279,26 @@ class Context:
         self._check(lib.swg_download_result(self._h, n, C.byref(dres), C.byref(res)))
         return status, chain_id
 
+    def score_column(self, identity, query_start, query_end, scoring=3):
+        """score_with_function (src/plane_sweep_exact.rs:29-86) of every row, evaluated on the device (swg_score_column)."""
+        idy = np.ascontiguousarray(identity, np.float64)
+        qs, qe = np.ascontiguousarray(query_start, np.uint32), np.ascontiguousarray(query_end, np.uint32)
+        out = np.empty(len(idy), np.float64)
+        self._check(lib.swg_score_column(self._h, len(idy), _ptr(idy, C.c_double), _ptr(qs, C.c_uint32), _ptr(qe, C.c_uint32), int(scoring),
+                                         _ptr(out, C.c_double)))
+        return out
+
+    def chain_identity(self, total_length, sum_block, sum_matches):
+        """weighted_identity of chains (src/paf_filter.rs:896-913), evaluated on the device (swg_chain_identity)."""
+        a = [np.ascontiguousarray(x, np.uint64) for x in (total_length, sum_block, sum_matches)]
+        out = np.empty(len(a[0]), np.float64)
+        self._check(lib.swg_chain_identity(self._h, len(a[0]), *[_ptr(x, C.c_uint64) for x in a], _ptr(out, C.c_double)))
+        return out
+
+    def log_matches_host(self) -> bool:
+        """True when the device's ln() produced the host libm's bits on the probe set of swg_create."""
+        return lib.swg_log_matches_host(self._h) == 1
+
     def last_chain_keys(self):
         """Order keys (A, B) of the chains kept by the last filter call on this context (swg_last_chain_keys)."""
         n = C.c_uint64()
@@ -362,6 +309,25 @@ class Context:
         a, b = np.zeros(k, np.uint32), np.zeros(k, np.uint32)
         self._check(lib.swg_last_chain_keys(self._h, k, _ptr(a, C.c_uint32), _ptr(b, C.c_uint32), C.byref(n)))
         return a, b
+
+    def last_chain_units(self):
+        """Runs of kept chains that share a genome-pair unit, for the last call (swg_last_chain_units):
+        (A = input index of the unit's first stage-1 record, first local chain number of the run), in chain order."""
+        n = C.c_uint64()
+        self._check(lib.swg_last_chain_units(self._h, 0, None, None, C.byref(n)))
+        k = int(n.value)
+        a, f = np.zeros(max(k, 1), np.uint32), np.zeros(max(k, 1), np.uint32)
+        if k:
+            self._check(lib.swg_last_chain_units(self._h, k, _ptr(a, C.c_uint32), _ptr(f, C.c_uint32), C.byref(n)))
+        return a[:k], f[:k]
+
+    def renumber_chains_device(self, n, chain_id_dev_ptr, unit_first_chain, unit_delta):
+        fk = np.ascontiguousarray(unit_first_chain, np.uint32)
+        dl = np.ascontiguousarray(unit_delta, np.int64)
+        self._check(lib.swg_renumber_chains_device(self._h, n, chain_id_dev_ptr, len(fk), _ptr(fk, C.c_uint32), _ptr(dl, C.c_int64)))
+
+    def pack_status_device(self, n, status_dev_ptr, packed_dev_ptr):
+        self._check(lib.swg_pack_status_device(self._h, n, status_dev_ptr, packed_dev_ptr))
 
     def release(self, dev, dres):
         lib.swg_release(self._h, C.byref(dev), C.byref(dres))
@@ -497,6 +463,17 @@ def apply_paf_filter(paf_path: str, filter_config: FilterConfig, device=0) -> st
     os.close(fd)
     PafFilter(filter_config, device).with_keep_self(False).filter_paf(paf_path, out)
     return out
+
+
+def shard_plan_units(unit_sizes, n_shards: int):
+    """swg_shard_plan_units: LPT of unit sizes -> (shard_of_unit, shard_sizes)."""
+    us = np.ascontiguousarray(unit_sizes, np.uint64)
+    so = np.zeros(len(us), np.uint32)
+    sizes = np.zeros(n_shards, np.uint64)
+    rc = lib.swg_shard_plan_units(len(us), _ptr(us, C.c_uint64), n_shards, _ptr(so, C.c_uint32), _ptr(sizes, C.c_uint64))
+    if rc != 0:
+        raise SwgError(rc, "swg_shard_plan_units")
+    return so, sizes
 
 
 def shard_plan(table: MappingTable, n_shards: int):

@@ -6,6 +6,8 @@
 // dense contraction; every kernel is HBM/L2 bound integer/byte work.
 #pragma once
 #include "common.cuh"
+#include "scan.cuh"
+#include "glibc_log.cuh"
 
 namespace swg {
 
@@ -76,6 +78,14 @@ template <int NC> __device__ __forceinline__ void block_count_add(u64 *ctr, cons
 // K0: stage-1 retain + range checks + genome-pair first appearance  (paf_filter.rs:384-388)
 // 33 B read + 1 B written per record.
 // ---------------------------------------------------------------------------------------------
+// identity column, or (identity == NULL) the parser's default matches / max(block_length, 1) (paf_filter.rs:322): one IEEE
+// division of two exactly converted integers, the same bits as the host's
+__device__ __forceinline__ double rec_identity(const DevIn &in, u32 i) {
+    if (in.identity) return in.identity[i];
+    const u32 b = in.blen[i];
+    return __ddiv_rn((double)in.matches[i], (double)(b > 1 ? b : 1));
+}
+
 __global__ void __launch_bounds__(256) k_prefilter(DevIn in, u64 min_len, double min_id, int keep_self, u8 *__restrict__ flags,
                                                    u64 *__restrict__ ctr, u64 *hk, u32 *hv, u32 hmask,
                                                    uint4 *__restrict__ rec4) {
@@ -86,16 +96,24 @@ __global__ void __launch_bounds__(256) k_prefilter(DevIn in, u64 min_len, double
     if (i < in.n) {
         u32 q = in.qid[i], t = in.tid[i];
         u32 qs = in.qs[i], qe = in.qe[i], ts = in.ts[i], te = in.te[i];
-        bad = q >= in.n_seq || t >= in.n_seq || qe < qs || te < ts;
-        double id = in.identity[i];
-        alive = !bad && (u64)in.blen[i] >= min_len && (keep_self || q != t) && id >= min_id;
+        const bool bad_id = q >= in.n_seq || t >= in.n_seq;
+        const bool bad_iv = qe < qs || te < ts; // the marshaller's mark for "does not fit the u32 SoA" as well (paf_io.cpp)
+        // without an identity column and with a threshold <= 0 the test is always true (matches / block >= 0): `matches`
+        // is then not read here and its upload overlaps this kernel and the sort
+        const bool id_ok = (!in.identity && min_id <= 0.0) ? true : rec_identity(in, i) >= min_id;
+        alive = !bad_id && (u64)in.blen[i] >= min_len && (keep_self || q != t) && id_ok;
+        // an impossible interval is an error only if the record survives the retain: the reference (u64, no check) would
+        // have dropped it here too (paf_filter.rs:384-388)
+        bad = bad_id || (alive && bad_iv);
+        if (bad) alive = false;
         zq = alive && qe == qs;
         zt = alive && te == ts;
-        maxc = max(qe, te);
+        maxc = alive ? max(qe, te) : 0u;
         if (alive) g = ((u64)in.P[q] << 32) | in.P[t];
         flags[i] = (u8)((alive ? F_ALIVE : 0) | (zq ? F_ZLQ : 0) | (zt ? F_ZLT : 0));
         // packed copy for the post-sort gather: one 16 B sector instead of four 4 B gathers.  `matches` is NOT touched
-        // here: it is first read by the gather after the sort, so its host-to-device copy can overlap K0 + sort.
+        // here (unless identity has to be derived from it): it is first read by the gather after the sort, so its
+        // host-to-device copy can overlap K0 + sort.
         if (rec4) rec4[i] = make_uint4(qs, qe, ts, te);
     }
     const u32 full = 0xFFFFFFFFu;
@@ -142,7 +160,10 @@ __global__ void __launch_bounds__(256) k_chain_keys(DevIn in, const u8 *__restri
     bool kept = false;
     if (i < in.n) {
         kept = (flags[i] & F_ALIVE) && (!keep_q || keep_q[i]) && (!keep_t || keep_t[i]);
-        u64 k = NONE64;
+        // dead records: all ones in the key's own 2*sb + 1 + cb bits (ids stay below 2^sb - 1, so they sort behind every
+        // live key) and zero above, so that the word still fits after the packed sort has shifted it
+        const int kb = 2 * sb + 1 + cb;
+        u64 k = kb >= 64 ? NONE64 : ((1ull << kb) - 1);
         if (kept) {
             u64 sbit = in.strand[i] == '+' ? 0 : 1;
             k = ((((u64)in.qid[i] << sb | in.tid[i]) << 1 | sbit) << cb) | in.qs[i];
@@ -267,11 +288,16 @@ __device__ __forceinline__ void bb_best_successor(const uint4 *__restrict__ srec
     }
 }
 
-// P1: 24 B read (+ window re-reads served by L1) and 28 B written per position.
+// P1: 24 B read (+ window re-reads served by L1) and 16 B written per position, plus one 32-bit exchange per candidate:
+// position p CLAIMS its unconstrained best successor, pred[j] = p.  If every successor of a group is claimed at most once,
+// the reference's loop does exactly that: best_pred_score[j] is still "none" when its only picker arrives, so the picker's
+// unconstrained arg-min is eligible and taken (paf_filter.rs:835-850).  A second claim on some j marks the whole group
+// dirty; dirty groups (rare on ordinary data) are redone by the sequential resolve below, which rewrites their pred[].
+// pred[] must be NONE32 everywhere on entry.
 __global__ void __launch_bounds__(256)
 k_chain_candidates(const uint4 *__restrict__ srec, const u64 *__restrict__ skey, const u32 *__restrict__ gid,
                    const u32 *__restrict__ gstart, u32 n_groups, u32 n_m, int cb, u64 G, Cand *__restrict__ cand,
-                   u64 *__restrict__ bps, u32 *__restrict__ root, u8 *__restrict__ grp_has_cand) {
+                   u32 *pred, u8 *__restrict__ grp_dirty) {
     const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_m) return;
     const uint4 a = srec[p]; // x=qs y=qe z=ts w=te
@@ -285,17 +311,20 @@ k_chain_candidates(const uint4 *__restrict__ srec, const u64 *__restrict__ skey,
     Cand c;
     c.d = bd; c.j = bj; c.c0 = c0;
     cand[p] = c;
-    bps[p] = NONE64;
-    root[p] = p;
-    if (bj != NONE32) grp_has_cand[g] = 1; // benign race: every writer stores 1
+    if (bj != NONE32 && atomicExch(&pred[bj], p) != NONE32) grp_dirty[g] = 1; // benign race: every writer stores 1
 }
 
-// P2: one thread per group that has at least one candidate; lanes refill from the work list as they finish.
+// P2: the reference's sequential loop for the DIRTY groups (some successor claimed twice), one thread per group; lanes
+// refill from the work list as they finish.  The whole state of a group is local to it (candidates point inside the
+// group), so the thread first resets the group's best_pred_score / pred and then walks it; a step is "does the
+// unconstrained arg-min still beat best_pred_score?" (then it is the reference's pick: the global arg-min is eligible, so
+// it is the arg-min over the eligible ones); only a blocked step re-scans its window with the eligibility test.
+// Result: pred[j] = best_pred_idx[j] (paf_filter.rs:847-850), NONE32 = no predecessor.
 constexpr u32 RES_SMALL = 16;
 __global__ void __launch_bounds__(128)
 k_chain_resolve(const Cand *__restrict__ cand, const uint4 *__restrict__ srec, const u64 *__restrict__ skey,
                 const u32 *__restrict__ gstart, u32 n_groups, u32 n_m, const u32 *__restrict__ work, const u32 *__restrict__ n_work_ptr,
-                int cb, u64 G, u64 *bps, u32 *root, u32 *work_counter) {
+                int cb, u64 G, u64 *bps, u32 *pred, u32 *work_counter) {
     const u32 full = 0xFFFFFFFFu;
     const u64 G5 = G / 5;
     const u32 n_work = *n_work_ptr;
@@ -303,7 +332,6 @@ k_chain_resolve(const Cand *__restrict__ cand, const uint4 *__restrict__ srec, c
     u32 e = 0, i = 0;
     Cand c_cur{0, NONE32, 0}, c_next{0, NONE32, 0};
     u64 b_cur = 0;
-    u32 r_cur = 0;
     while (true) {
         const u32 need = __ballot_sync(full, !active && !exhausted);
         if (need) {
@@ -322,16 +350,14 @@ k_chain_resolve(const Cand *__restrict__ cand, const uint4 *__restrict__ srec, c
                     active = true;
                     const u32 n = e - i;
                     if (n <= RES_SMALL) {
-                        // The whole state of a group is local to it (candidates point inside the group; bps starts at
-                        // "none" and root at the own position), so a small group is resolved from ONE burst of loads:
-                        // its candidates.  The walk below runs on per-thread copies; only `root` is written back.
+                        // a small group is resolved from ONE burst of loads (its candidates) on per-thread copies
                         Cand cs[RES_SMALL];
-                        u32 rt[RES_SMALL];
+                        u32 pr[RES_SMALL];
                         u64 bp[RES_SMALL];
 #pragma unroll
                         for (u32 k = 0; k < RES_SMALL; k++) {
                             if (k < n) cs[k] = cand[i + k];
-                            rt[k] = i + k;
+                            pr[k] = NONE32;
                             bp[k] = NONE64;
                         }
                         u32 k = 0;
@@ -340,36 +366,34 @@ k_chain_resolve(const Cand *__restrict__ cand, const uint4 *__restrict__ srec, c
                             const Cand c = cs[k];
                             if (c.j == NONE32) continue;
                             const u32 jj = c.j - i;
-                            if (c.d < bp[jj]) { bp[jj] = c.d; rt[jj] = rt[k]; }
+                            if (c.d < bp[jj]) { bp[jj] = c.d; pr[jj] = i + k; }
                             else { blocked = true; break; } // needs the arg-min over the eligible candidates: generic walk
                         }
+                        for (u32 q = 0; q < n; q++) pred[i + q] = pr[q];
                         if (!blocked) {
-                            for (u32 q = 0; q < n; q++) root[i + q] = rt[q];
                             active = false;
                         } else { // publish the state reached so far; the generic walk continues at step k
-                            for (u32 q = 0; q < n; q++) { bps[i + q] = bp[q]; root[i + q] = rt[q]; }
+                            for (u32 q = 0; q < n; q++) bps[i + q] = bp[q];
                             c_cur = cs[k];
                             c_next = (k + 1 < n) ? cs[k + 1] : Cand{0, NONE32, 0};
                             b_cur = bp[c_cur.j - i];
-                            r_cur = rt[k];
                             i += k;
                         }
                     } else {
+                        for (u32 q = i; q < e; q++) { bps[q] = NONE64; pred[q] = NONE32; }
                         c_cur = cand[i];
                         c_next = (i + 1 < e) ? cand[i + 1] : Cand{0, NONE32, 0};
-                        b_cur = (c_cur.j != NONE32) ? bps[c_cur.j] : 0;
-                        r_cur = i; // the first position of a group has no predecessor
+                        b_cur = NONE64;
                     }
                 }
             }
         }
         if (__all_sync(full, exhausted && !active)) break;
         if (active) {
-            // software pipeline: the loads of step i+1 (its candidate, that candidate's best_pred_score, its
-            // root) are issued before step i is decided; step i's own store is forwarded in registers.
+            // software pipeline: the loads of step i+1 (its candidate, that candidate's best_pred_score) are issued before
+            // step i is decided; step i's own store is forwarded in registers.
             const Cand c_nn = (i + 2 < e) ? cand[i + 2] : Cand{0, NONE32, 0}; // two steps ahead: its address is free
             u64 b_next = (c_next.j != NONE32) ? bps[c_next.j] : 0;             // c_next was loaded one step ago
-            u32 r_next = (i + 1 < e) ? root[i + 1] : 0;
             u32 chosen = NONE32;
             u64 chosen_d = 0;
             if (c_cur.j != NONE32) {
@@ -386,15 +410,13 @@ k_chain_resolve(const Cand *__restrict__ cand, const uint4 *__restrict__ srec, c
                 }
                 if (chosen != NONE32) {
                     bps[chosen] = chosen_d;
-                    root[chosen] = r_cur;
+                    pred[chosen] = i;
                     if (chosen == c_next.j) b_next = chosen_d; // supersedes the value prefetched above
-                    if (chosen == i + 1) r_next = r_cur;
                 }
             }
             c_cur = c_next;
             c_next = c_nn;
             b_cur = b_next;
-            r_cur = r_next;
             if (++i == e) active = false;
         }
     }
@@ -592,7 +614,7 @@ __device__ __forceinline__ void bb_best_successor_warp(const uint4 *__restrict__
 __global__ void __launch_bounds__(128)
 k_chain_resolve_warp(const Cand *__restrict__ cand, const uint4 *__restrict__ srec, const u64 *__restrict__ skey,
                      const u32 *__restrict__ gstart, u32 n_groups, u32 n_m, const u32 *__restrict__ work, const u32 *__restrict__ n_work_ptr,
-                     int cb, u64 G, u64 *bps, u32 *root, u32 *work_counter) {
+                     int cb, u64 G, u64 *bps, u32 *pred, u32 *work_counter) {
     const u32 full = 0xFFFFFFFFu;
     const u32 lane = lane_id();
     const u64 G5 = G / 5;
@@ -605,19 +627,18 @@ k_chain_resolve_warp(const Cand *__restrict__ cand, const uint4 *__restrict__ sr
         const u32 g = work[w];
         const u32 s = gstart[g], e = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
         const bool fwd = ((skey[s] >> cb) & 1) == 0;
-        // 32 steps per batch: lane k prefetches the candidate, the root and the current best_pred_score of step
-        // base + k in one round trip; the steps then run in order from registers.  A step that writes bps[j] / root[j]
-        // patches the prefetched copies of the later steps of the batch, so every step sees exactly the state the
-        // sequential walk would.
+        for (u32 q = s + lane; q < e; q += 32) { bps[q] = NONE64; pred[q] = NONE32; } // the group's state starts empty
+        __syncwarp();
+        // 32 steps per batch: lane k prefetches the candidate and the current best_pred_score of step base + k in one
+        // round trip; the steps then run in order from registers.  A step that writes bps[j] patches the prefetched
+        // copies of the later steps of the batch, so every step sees exactly the state the sequential walk would.
         for (u32 base = s; base + 1 < e; base += 32) {
             const u32 ik = base + lane;
             Cand ck;
             ck.d = 0; ck.j = NONE32; ck.c0 = NONE32;
-            u32 rk = 0;
             u64 bk = 0;
             if (ik + 1 < e) {
                 ck = cand[ik];
-                rk = root[ik];
                 if (ck.j != NONE32) bk = bps[ck.j];
             }
             const u32 steps = min(32u, e - 1 - base);
@@ -626,19 +647,17 @@ k_chain_resolve_warp(const Cand *__restrict__ cand, const uint4 *__restrict__ sr
                 if (cj == NONE32) continue;
                 const u64 cd = __shfl_sync(full, ck.d, t);
                 const u64 bt = __shfl_sync(full, bk, t);
-                const u32 ri = __shfl_sync(full, rk, t);
-                u64 wd = NONE64; // what this step writes: bps[wj] = wd, root[wj] = ri
+                u64 wd = NONE64; // what this step writes: bps[wj] = wd, pred[wj] = i
                 u32 wj = NONE32;
+                const u32 i = base + t;
                 if (cd < bt) { wd = cd; wj = cj; }
                 else {
-                    const u32 i = base + t;
                     const uint4 a = srec[i];
                     bb_best_successor_warp(srec, bps, i, e, a, fwd, G, G5, wd, wj, __shfl_sync(full, ck.c0, t), BbNoExtra{});
                 }
                 if (wj != NONE32) {
-                    if (lane == 0) { bps[wj] = wd; root[wj] = ri; }
+                    if (lane == 0) { bps[wj] = wd; pred[wj] = i; }
                     if (ck.j == wj) bk = wd;               // later steps of the batch that look at the same successor
-                    if (ik == wj) rk = ri;                 // the successor itself is a later step of the batch
                     __syncwarp();
                 }
             }
@@ -671,6 +690,121 @@ k_chain_work_estimate(const uint4 *__restrict__ srec, const u32 *__restrict__ gs
     if (lane_id() == 0 && est) atomicAdd((unsigned long long *)&ctr[C_WORK], (unsigned long long)est);
 }
 
+// P2c: union-find roots and dense chain numbers in ONE pass over pred[] (union_find.rs:25-41: every union hangs the
+// singleton j under find(pred[j]), so the root of a set is its head and pred[] is a forest of paths with pred[j] < j;
+// chains are numbered by ascending head position, union_find.rs:52-63).
+// A CTA takes a tile of 2048 consecutive sorted positions (tile ids in scheduling order): pointer jumping in shared memory
+// resolves every position to a head inside the tile or to an ancestor in an EARLIER tile; heads are numbered by a
+// decoupled look-back over the tiles' head counts; positions whose ancestor lies in an earlier tile wait for that
+// position's published chain number (its tile is resident or done: the wait only ever points backwards).
+// chain_of[] must be NONE32 everywhere on entry.  PRESET: root[] already holds the final root of some positions (huge
+// groups chained by the fixed-point iteration), NONE32 elsewhere.
+constexpr int CR_THREADS = 256, CR_ITEMS = 8, CR_TILE = CR_THREADS * CR_ITEMS;
+static_assert(CR_THREADS == SC_THREADS, "k_chain_number uses the 256-thread block scan of scan.cuh");
+template <bool PRESET>
+__global__ void __launch_bounds__(CR_THREADS)
+k_chain_number(const u32 *__restrict__ pred, const u32 *__restrict__ root_preset, u32 n_m, u32 *chain_of, u32 *__restrict__ head_pos,
+               u64 *status, u32 *tile_counter, u32 *n_chains_out) {
+    __shared__ u32 anc[CR_TILE];
+    __shared__ u32 ws[CR_THREADS / 32];
+    __shared__ u32 s_tile, s_excl;
+    const u32 tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u32 base = tile * CR_TILE;
+    // load (striped: coalesced), ancestor = predecessor or the position itself (a head)
+#pragma unroll
+    for (int k = 0; k < CR_ITEMS; k++) {
+        const u32 l = k * CR_THREADS + tid, p = base + l;
+        u32 a = p;
+        if (p < n_m) {
+            const u32 pr = pred[p];
+            if (pr != NONE32) a = pr;
+            if (PRESET) { const u32 r = root_preset[p]; if (r != NONE32) a = r; }
+        }
+        anc[l] = a;
+    }
+    __syncthreads();
+    // heads of the tile in position order (blocked), published before anything can wait
+    u32 hflag = 0, hcnt = 0;
+#pragma unroll
+    for (int k = 0; k < CR_ITEMS; k++) {
+        const u32 l = tid * CR_ITEMS + k, p = base + l;
+        const bool h = p < n_m && anc[l] == p;
+        hflag |= (h ? 1u : 0u) << k;
+        hcnt += h;
+    }
+    u32 tot;
+    const u32 ex_local = block_exclusive_scan_256(hcnt, ws, tot);
+    if (tid < 32) {
+        if (lane == 0) st_relaxed_u64(&status[tile], (tile == 0 ? SC_FLAG_INCL : SC_FLAG_AGG) | tot);
+        u32 excl = 0;
+        if (tile != 0) {
+            i64 t = (i64)tile - 1;
+            while (true) {
+                const i64 mine = t - lane;
+                const u64 w = mine >= 0 ? ld_relaxed_u64(&status[mine]) : SC_FLAG_INCL;
+                const u32 incl = __ballot_sync(0xFFFFFFFFu, (w & SC_FLAG_INCL) != 0);
+                const u32 ready = __ballot_sync(0xFFFFFFFFu, (w & (SC_FLAG_INCL | SC_FLAG_AGG)) != 0);
+                const u32 upto = incl ? (u32)(__ffs(incl) - 1) : 31u;
+                const u32 need = upto == 31 ? 0xFFFFFFFFu : ((2u << upto) - 1);
+                if ((ready & need) != need) continue;
+                excl += __reduce_add_sync(0xFFFFFFFFu, lane <= upto ? (u32)(w & SC_VAL_MASK) : 0u);
+                if (incl) break;
+                t -= 32;
+            }
+            if (lane == 0) st_relaxed_u64(&status[tile], SC_FLAG_INCL | (u64)(excl + tot));
+        }
+        if (lane == 0) {
+            s_excl = excl;
+            if ((u64)(tile + 1) * CR_TILE >= n_m) *n_chains_out = excl + tot;
+        }
+    }
+    // pointer jumping inside the tile (a racing read sees an older or a newer ancestor: both are ancestors)
+    while (true) {
+        bool changed = false;
+#pragma unroll
+        for (int k = 0; k < CR_ITEMS; k++) {
+            const u32 l = k * CR_THREADS + tid;
+            const u32 a = anc[l];
+            if (a >= base && a != base + l) {
+                const u32 a2 = anc[a - base];
+                if (a2 != a) { anc[l] = a2; changed = true; }
+            }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    // heads get their numbers (s_excl is visible: the loop above ended in a barrier)
+    {
+        u32 ex = s_excl + ex_local;
+#pragma unroll
+        for (int k = 0; k < CR_ITEMS; k++) {
+            if ((hflag >> k) & 1u) {
+                const u32 l = tid * CR_ITEMS + k;
+                head_pos[ex] = base + l;
+                anc[l] = 0x80000000u | ex; // marks "this entry now holds a chain number" (positions are < 2^31)
+                ex++;
+            }
+        }
+    }
+    __syncthreads();
+    // every position: chain number of its head (inside the tile) or of its ancestor in an earlier tile
+#pragma unroll
+    for (int k = 0; k < CR_ITEMS; k++) {
+        const u32 l = k * CR_THREADS + tid, p = base + l;
+        if (p >= n_m) continue;
+        const u32 a = anc[l];
+        u32 ci;
+        if (a & 0x80000000u) ci = a & 0x7FFFFFFFu;
+        else if (a >= base) ci = anc[a - base] & 0x7FFFFFFFu; // its head: numbered above
+        else {
+            do { ci = ld_volatile_u32(chain_of + a); } while (ci == NONE32);
+        }
+        st_volatile_u32(chain_of + p, ci);
+    }
+}
+
 // P3: per-chain aggregates (paf_filter.rs:875-894) into the dense chain table: bounding box by atomicMin / atomicMax, sums
 // by atomicAdd; runs of one chain inside a warp are reduced first (one set of atomics per run).  Every position also feeds
 // its group's min original index (the first appearance of the group in the input).  The table rows are pre-set to
@@ -679,9 +813,16 @@ struct ChainDense {
     u32 *qmin, *qmax, *tmin, *tmax; // = ChainTable qs / qe / ts / te
     u64 *sum_matches, *sum_block;
 };
+// sorted position -> input index: the payload column of a pairs sort, or the low bits of the packed words
+struct SortedIdx {
+    const u64 *w;
+    const u32 *v;
+    u64 mask;
+    __device__ __forceinline__ u32 operator[](u32 p) const { return w ? (u32)(w[p] & mask) : v[p]; }
+};
 __global__ void __launch_bounds__(256)
-k_chain_aggregate(const uint4 *__restrict__ srec, const uint2 *__restrict__ srec2, const u32 *__restrict__ sidx, const u32 *__restrict__ gid,
-                  const u32 *__restrict__ root, const u32 *__restrict__ chain_of_pos, u32 n_m, ChainDense cd, u32 *__restrict__ grp_minidx) {
+k_chain_aggregate(const uint4 *__restrict__ srec, const uint2 *__restrict__ srec2, SortedIdx sidx, const u32 *__restrict__ gid,
+                  const u32 *__restrict__ chain_of, u32 n_m, ChainDense cd, u32 *__restrict__ grp_minidx) {
     const u32 full = 0xFFFFFFFFu;
     const u32 lane = lane_id();
     const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -692,7 +833,7 @@ k_chain_aggregate(const uint4 *__restrict__ srec, const uint2 *__restrict__ srec
     if (ok) {
         g = gid[p];
         idx = sidx[p];
-        ci = chain_of_pos[root[p]];
+        ci = chain_of[p];
         a = srec[p];
         m = srec2[p];
     }
@@ -753,7 +894,10 @@ struct ChainTable {
 // ---------------------------------------------------------------------------------------------
 // score_with_function, plane_sweep_exact.rs:29-86 (length = QUERY span on both axes)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double score_fn(int scoring, double identity, u32 qs, u32 qe) {
+// `ln`: glibc_log (glibc_log.cuh: the host libm's bits) unless cuda_log is set (SWG_LOG_IMPL=cuda: CUDA's log(), a
+// testing aid that stands in for "a host whose libm differs from the port").
+__device__ __forceinline__ double ln_fn(double x, bool cuda_log) { return cuda_log ? log(x) : glibc_log(x); }
+__device__ __forceinline__ double score_fn(int scoring, double identity, u32 qs, u32 qe, bool cuda_log = false) {
     double length = (double)(qe - qs);
     const double ninf = __longlong_as_double(0xFFF0000000000000LL);
     switch (scoring) {
@@ -761,8 +905,16 @@ __device__ __forceinline__ double score_fn(int scoring, double identity, u32 qs,
     case 1: return length <= 0.0 ? ninf : length;
     case 2:
     case 4: return (length <= 0.0 || identity <= 0.0) ? ninf : __dmul_rn(length, identity);
-    default: return (length <= 0.0 || identity <= 0.0) ? ninf : __dmul_rn(identity, log(length));
+    default: return (length <= 0.0 || identity <= 0.0) ? ninf : __dmul_rn(identity, ln_fn(length, cuda_log));
     }
+}
+// weighted_identity of a chain, paf_filter.rs:896-913
+__device__ __forceinline__ double chain_identity_fn(u64 total_length, u64 sum_block, u64 sum_matches, bool cuda_log, const double *host_lg = nullptr) {
+    const u64 gap = total_length > sum_block ? total_length - sum_block : 0; // saturating_sub, :901
+    double lg = 0.0;
+    if (gap > 0) lg = host_lg ? *host_lg : fmax(ln_fn((double)gap, cuda_log), 0.0); // :902-906
+    const double eff = __dadd_rn((double)sum_block, lg);
+    return eff > 0.0 ? __ddiv_rn((double)sum_matches, eff) : 0.0;
 }
 // order-preserving map f64 -> u64, DESCENDING score = ascending key (MappingOrder::cmp, :183-194)
 __device__ __forceinline__ u64 score_desc_key(double s) {
@@ -797,6 +949,9 @@ __device__ __forceinline__ bool overlaps_more_than(u32 s1, u32 e1, u32 s2, u32 e
 // good/flagged follow the closed form "kept <=> ever in the top-n at an evaluated position and never flagged
 // overlapped".
 // ---------------------------------------------------------------------------------------------
+// Two scores this close can rank differently when the log comes from another libm (each side is within ~1 ulp of the
+// other in the log, one more rounding in the product): the audit band of swg_stats.score_near_ties.
+constexpr u64 NEAR_TIE_ULPS = 4;
 struct SweepItem { // per item, in (group, start, item) order, so that a group is one contiguous stream
     u64 skey;  // score_desc_key of the item
     u32 start; // axis interval of the item
@@ -850,7 +1005,7 @@ k_sweep_flat1(const u32 *__restrict__ sitem, const SweepItem *__restrict__ sdata
         if (a.start >= me.end) break;
         hi = k;
         const u64 df = a.skey > me.skey ? a.skey - me.skey : me.skey - a.skey; // near-tie audit, each co-active pair once
-        near += (df != 0 && df <= 2);
+        near += (df != 0 && df <= NEAR_TIE_ULPS);
         if (k - u > SWF_RIGHT) big = true;
     }
     if (big) {
@@ -962,8 +1117,8 @@ k_sweep_groups(const u32 *__restrict__ sitem, const SweepItem *__restrict__ sdat
                 // near-tie audit: neighbours whose score key differs by <= 2 ulp but is not equal
                 if (lane == 0) {
                     u32 near = 0;
-                    if (cnt > 0) { u64 df = x.skey - A[cnt - 1].skey; near += (df != 0 && df <= 2); }
-                    if (cnt < size) { u64 df = A[cnt].skey - x.skey; near += (df != 0 && df <= 2); }
+                    if (cnt > 0) { u64 df = x.skey - A[cnt - 1].skey; near += (df != 0 && df <= NEAR_TIE_ULPS); }
+                    if (cnt < size) { u64 df = A[cnt].skey - x.skey; near += (df != 0 && df <= NEAR_TIE_ULPS); }
                     if (near) atomicAdd((unsigned long long *)&ctr[C_NEAR_TIES], (unsigned long long)near);
                 }
                 // shift [cnt, size) up by one, from the top, 32 at a time
@@ -1075,8 +1230,8 @@ k_sweep_small(const u32 *__restrict__ sitem, const SweepItem *__restrict__ sdata
                 }
                 a_key[pos] = d.skey; a_start[pos] = d.start; a_end[pos] = d.end; a_item[pos] = item << 2;
                 u32 near = 0; // near-tie audit: neighbours whose score key differs by <= 2 ulp but is not equal
-                if (pos > 0) { const u64 df = d.skey - a_key[pos - 1]; near += (df != 0 && df <= 2); }
-                if (pos < size) { const u64 df = a_key[pos + 1] - d.skey; near += (df != 0 && df <= 2); }
+                if (pos > 0) { const u64 df = d.skey - a_key[pos - 1]; near += (df != 0 && df <= NEAR_TIE_ULPS); }
+                if (pos < size) { const u64 df = a_key[pos + 1] - d.skey; near += (df != 0 && df <= NEAR_TIE_ULPS); }
                 if (near) atomicAdd((unsigned long long *)&ctr[C_NEAR_TIES], (unsigned long long)near);
                 size++;
                 chk = pos == 0 ? 0u : ((chk & ((1u << pos) - 1)) | ((chk >> pos) << (pos + 1)));

@@ -14,6 +14,8 @@
 //   K7  rescue                                           paf_filter.rs:613-732
 #include <algorithm>
 #include <chrono>
+#include <cmath>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -102,6 +104,35 @@ struct Arena {
 
 } // namespace swg
 
+namespace swg {
+// Environment knobs (diagnostics and tests).  Read once per entry point, never cached across calls.
+struct Knobs {
+    bool force_wide = false, sweep_no_flat = false, no_fixpoint = false, inv_grid = false, inv_no_grid = false, cuda_log = false;
+    bool pairs_sort = false;   // SWG_SORT_PAIRS=1: the record sort keeps (key, payload) pairs through every pass
+    u32 fixpoint_min = 0;      // 0 = default
+    double max_pair_evals = 0; // 0 = no limit (SWG_MAX_PAIR_EVALS)
+    int sweep_mult = 8, resolve_mult = 4;
+    int exact_scores = 0;      // SWG_EXACT_SCORES: 0 auto, 1 always, 2 never
+};
+static Knobs read_knobs() {
+    Knobs k;
+    auto on = [](const char *n) { const char *v = getenv(n); return v != nullptr && *v && strcmp(v, "0") != 0; };
+    k.force_wide = on("SWG_FORCE_WIDE_KEYS");
+    k.sweep_no_flat = on("SWG_SWEEP_NO_FLAT");
+    k.no_fixpoint = on("SWG_NO_FIXPOINT");
+    k.inv_grid = on("SWG_INV_GRID");
+    k.inv_no_grid = on("SWG_INV_NO_GRID");
+    k.pairs_sort = on("SWG_SORT_PAIRS");
+    if (const char *v = getenv("SWG_LOG_IMPL")) k.cuda_log = strcmp(v, "cuda") == 0;
+    if (const char *v = getenv("SWG_FIXPOINT_MIN")) k.fixpoint_min = (u32)atoi(v);
+    if (const char *v = getenv("SWG_MAX_PAIR_EVALS")) k.max_pair_evals = atof(v);
+    if (const char *v = getenv("SWG_SWEEP_MULT")) k.sweep_mult = std::max(1, atoi(v));
+    if (const char *v = getenv("SWG_RESOLVE_MULT")) k.resolve_mult = std::max(1, atoi(v));
+    if (const char *v = getenv("SWG_EXACT_SCORES")) k.exact_scores = strcmp(v, "always") == 0 ? 1 : strcmp(v, "never") == 0 ? 2 : 0;
+    return k;
+}
+} // namespace swg
+
 using namespace swg;
 
 struct swg_ctx {
@@ -115,11 +146,18 @@ struct swg_ctx {
     cudaEvent_t ev_ctr = nullptr;                // marks an early copy of the counters (read while later kernels still run)
     int sort_passes = 0;
     u64 sort_pairs = 0;
+    u64 sort_bytes_per_pair = 24; // of the timed passes: 24 (pairs) or 16 (packed words)
     std::vector<cudaEvent_t> stage_ev;      // SWG_STAGE_TIMING=1: events at stage boundaries of the last call
     std::vector<const char *> stage_name;
     size_t stage_used = 0;
-    const u32 *last_keyA = nullptr, *last_keyB = nullptr; // order keys of the kept chains of the last call (arena memory)
+    const u32 *last_keyA = nullptr, *last_keyB = nullptr; // order keys of the kept chains of the last call (in `keys`, not in the scratch arena)
     u64 last_n_chains = 0;
+    Arena keys;       // owns last_keyA / last_keyB: they survive later calls that rewind the scratch arena
+    bool log_matches_host = false; // swg_create: the device's glibc_log agrees with the host libm's log on the probe set
+    bool cudalog_matches_host = false; // ... and CUDA's log() (SWG_LOG_IMPL=cuda) does
+    Knobs knobs;      // environment knobs, re-read at the start of every entry point (read_knobs)
+    std::vector<double> h_score;   // exact re-rank: host-computed score column
+    Arena score_arena;             // ... and its device copy
     Arena arena;      // per-call scratch
     Arena io;         // staging of host SoA for swg_filter
     u64 *h_ctr = nullptr; // pinned mirror of the counters
@@ -206,7 +244,7 @@ static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 in
     stage_mark(c, "gs_keys");
     // items in (group, start, item) order; the End events come out of the active set (k_sweep_small).  One sort when
     // the key fits 64 bits, else two chained stable sorts (start first, then the group id).
-    const bool wide = (gb + pbits > 64) || (getenv("SWG_FORCE_WIDE_KEYS") != nullptr);
+    const bool wide = (gb + pbits > 64) || c->knobs.force_wide;
     k_sweep_keys<<<cdiv(n_items, 256), 256, 0, st>>>(n_items, include, include_mask, gkey, wide ? 64 : pbits, it_start, ek, ev, ctr + C_TMP0);
     c->lc.n++;
     int eshift = pbits;
@@ -271,12 +309,12 @@ static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 in
     u32 *sw_ctr = c->arena.take<u32>(4); // [0] thread-kernel group counter, [1] deep groups, [2] warp-kernel work counter
     SWG_CUDA(cudaMemsetAsync(sw_ctr, 0, 4 * sizeof(u32), st));
     stage_mark(c, "gs_sweep");
-    const bool no_flat = getenv("SWG_SWEEP_NO_FLAT") != nullptr; // testing aid (read per call): the sequential kernels for every n
+    const bool no_flat = c->knobs.sweep_no_flat; // testing aid: the sequential kernels for every n
     if (n_keep == 1 && !no_flat) {
         k_sweep_flat1<<<cdiv(n_inc, 256), 256, 0, st>>>(ev, sdata, gid, gstart, gmaxlen, n_groups, n_inc, thr, keep, gflag, big_list, sw_ctr + 1,
                                                        ctr);
     } else {
-        static const int sweep_mult = getenv("SWG_SWEEP_MULT") ? atoi(getenv("SWG_SWEEP_MULT")) : 8;
+        const int sweep_mult = c->knobs.sweep_mult;
         k_sweep_small<<<(u32)c->sm_count * sweep_mult, 128, 0, st>>>(ev, sdata, gstart, n_groups, n_inc, n_keep, thr, good, flagged, big_list,
                                                                     sw_ctr + 1, sw_ctr, ctr);
     }
@@ -324,12 +362,29 @@ static void segment_first(swg_ctx *c, const u64 *sk, const u32 *sv, u32 n, u32 *
 
 namespace swg {
 
+// score_with_function on the host (plane_sweep_exact.rs:29-86) with the host libm: the exact re-rank's score column
+static inline double host_score(int scoring, double identity, u32 qs, u32 qe) {
+    const double length = (double)(qe - qs);
+    switch (scoring) {
+    case 0: return identity <= 0.0 ? -INFINITY : identity;
+    case 1: return length <= 0.0 ? -INFINITY : length;
+    case 2:
+    case 4: return (length <= 0.0 || identity <= 0.0) ? -INFINITY : length * identity;
+    default: return (length <= 0.0 || identity <= 0.0) ? -INFINITY : identity * std::log(length);
+    }
+}
+
 // ================================================================================================
 // the pipeline
 // ================================================================================================
+// exact_host: every logarithm on the path comes from the HOST libm (in.score carries the record scores; the chain-level
+// logs are computed on the host from small downloads) — the exact re-rank of DESIGN 4d, not the normal path.
 static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *status, u32 *chain_id, swg_stats *stats,
-                       cudaEvent_t ev_matches = nullptr /* recorded when in.matches has arrived (swg_filter overlaps that copy) */) {
+                       cudaEvent_t ev_matches = nullptr /* recorded when in.matches has arrived (swg_filter overlaps that copy) */,
+                       bool exact_host = false) {
     cudaStream_t st = c->stream;
+    const Knobs &K = c->knobs;
+    const bool cuda_log = K.cuda_log;
     LaunchCounter &lc = c->lc;
     const u32 N = in.n;
     u64 launches0 = lc.n;
@@ -340,6 +395,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     SWG_CUDA(cudaMemsetAsync(chain_id, 0, sizeof(u32) * (size_t)N, st));
     c->sort_passes = 0;
     c->sort_pairs = 0;
+    c->sort_bytes_per_pair = 24;
     c->stage_used = 0;
     c->last_n_chains = 0;
     c->last_keyA = c->last_keyB = nullptr;
@@ -353,6 +409,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             if (cudaEventElapsedTime(&ms, c->ev_sort[0], c->ev_sort[1]) == cudaSuccess) S.ms_sort_passes = ms;
             S.n_sort_passes = (u64)c->sort_passes;
             S.n_sort_pairs = c->sort_pairs;
+            S.sort_bytes_per_pair = c->sort_bytes_per_pair;
         }
         if (stats) *stats = S;
     };
@@ -390,10 +447,12 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     SWG_CUDA(cudaMemsetAsync(hv, 0xFF, sizeof(u32) * hcap, st));
     uint4 *rec4 = nullptr;
     if (cfg.scaffold_gap != 0) rec4 = A.take<uint4>(N);
+    if (ev_matches && !in.identity && !(cfg.min_identity <= 0.0)) SWG_CUDA(cudaStreamWaitEvent(st, ev_matches, 0)); // identity is derived from `matches`
     k_prefilter<<<cdiv(N, 256), 256, 0, st>>>(in, cfg.min_block_length, cfg.min_identity, cfg.keep_self, flags, ctr, hk, hv, hcap - 1, rec4);
     lc.n++;
     read_counters(c);
-    if (c->h_ctr[C_BAD]) throw RangeError{"record with end < start or sequence id >= n_seq"};
+    if (c->h_ctr[C_BAD])
+        throw RangeError{"a record that passes the length / self / identity retain has end < start, a coordinate beyond the u32 table, or a sequence id >= n_seq"};
     const u64 n_alive = c->h_ctr[C_ALIVE], zlq = c->h_ctr[C_ZLQ], zlt = c->h_ctr[C_ZLT];
     const u32 maxcoord = (u32)c->h_ctr[C_MAXCOORD];
     S.n_stage1 = n_alive;
@@ -416,8 +475,9 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     if (need_q || need_t) {
         rscore = A.take<double>(N);
         const int scoring = cfg.scoring_function;
+        if (ev_matches && !in.identity && !in.score) SWG_CUDA(cudaStreamWaitEvent(st, ev_matches, 0));
         launch_for<t_scores>(N, st, lc, [=] __device__(u32 i) {
-            rscore[i] = in.score ? in.score[i] : score_fn(scoring, in.identity[i], in.qs[i], in.qe[i]);
+            rscore[i] = in.score ? in.score[i] : score_fn(scoring, rec_identity(in, i), in.qs[i], in.qe[i], cuda_log);
         });
         u64 *gk = A.take<u64>(N);
         for (int axis = 0; axis < 2; axis++) {
@@ -449,12 +509,33 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     u64 *keys = A.take<u64>(N), *keys2 = A.take<u64>(N);
     u32 *vals = A.take<u32>(N), *vals2 = A.take<u32>(N);
     int gshift = cb; // group id of a sorted position = skey >> gshift
-    const bool wide = (2 * sb + 1 + cb > 64) || (getenv("SWG_FORCE_WIDE_KEYS") != nullptr);
+    const int kb = 2 * sb + 1 + cb;
+    const bool wide = kb > 64 || K.force_wide;
+    SortedIdx sidx{nullptr, nullptr, 0};
+    const u64 *skey = nullptr;
     if (!wide) {
         k_chain_keys<<<cdiv(N, 256), 256, 0, st>>>(in, flags, keep_q, keep_t, sb, cb, keys, vals, ctr);
         lc.n++;
         read_counters_begin(c); // the survivor count is final here; the host picks it up while the sort runs
-        sort_pairs(c, keys, keys2, vals, vals2, N, 2 * sb + 1 + cb, true);
+        const int ib = bits_for(N - 1);
+        if (K.pairs_sort) {
+            sort_pairs(c, keys, keys2, vals, vals2, N, kb, true);
+            skey = keys;
+            sidx.v = vals;
+        } else {
+            // the packed sort (radix_sort.cuh): once the key bits still to be sorted and the index fit one word, the passes
+            // move 8 B per record instead of 12 B; the result holds the index and the key from bit c0 upwards
+            RadixSortPlan p = rs_plan(N, 0, kb);
+            void *tmp = A.take<char>(p.temp_bytes);
+            const PackedSort ps = rs_sort_packed(N, kb, ib, keys, keys2, vals, vals2, tmp, p, st, c->sm_count, lc, c->ev_sort[0], c->ev_sort[1]);
+            c->sort_passes = ps.timed_passes; // the events bracket the packed-word passes
+            c->sort_pairs = N;
+            c->sort_bytes_per_pair = ps.timed_bytes_per_pair;
+            skey = ps.packed;
+            sidx.w = ps.packed;
+            sidx.mask = (1ull << ib) - 1;
+            gshift = ib + cb - ps.c0;
+        }
         read_counters_end(c);
     } else {
         // key wider than 64 bits (hundreds of thousands of sequences): two chained stable sorts, least significant
@@ -482,6 +563,8 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         }
         sort_pairs(c, keys, keys2, vals, vals2, N, 2 * sb + 2);
         gshift = 0;
+        skey = keys;
+        sidx.v = vals;
         read_counters(c);
     }
     const u32 n_m = (u32)c->h_ctr[C_KEPT_M];
@@ -489,62 +572,60 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     S.score_near_ties = c->h_ctr[C_NEAR_TIES];
     if (n_m == 0) { finish(); return; }
     stage_mark(c, "groups+gather");
-    const u64 *skey = keys;
-    const u32 *sidx = vals;
     uint4 *srec = A.take<uint4>(n_m);
     uint2 *srec2 = A.take<uint2>(n_m);
     u32 *gstart = A.take<u32>(n_m + 1);
     u32 *gid = A.take<u32>(n_m);
     u32 *bsum = A.take<u32>(scan_temp_u32(N));
     u32 *d_tot = A.take<u32>(4);
+    // group boundaries, and in the same pass the gather of the packed records into sorted order (a thread's eight gathers
+    // are independent loads in flight together)
+    if (ev_matches) SWG_CUDA(cudaStreamWaitEvent(st, ev_matches, 0)); // first use of in.matches
     scan_apply([=] __device__(u32 p) -> u32 { return (p == 0 || (skey[p] >> gshift) != (skey[p - 1] >> gshift)) ? 1u : 0u; },
                [=] __device__(u32 p, u32 ex, u32 v) {
                    if (v) gstart[ex] = p;
                    gid[p] = ex + v - 1;
+                   const u32 i = sidx[p];
+                   srec[p] = __ldg(&rec4[i]);
+                   srec2[p] = make_uint2(__ldg(&in.blen[i]), __ldg(&in.matches[i]));
                },
                n_m, bsum, d_tot, st, lc);
-    // post-sort gather of the packed records (flat, one thread per position: all gathers of a warp in flight at once)
-    if (ev_matches) SWG_CUDA(cudaStreamWaitEvent(st, ev_matches, 0)); // first use of in.matches
-    launch_for<t_gather>(n_m, st, lc, [=] __device__(u32 p) {
-        const u32 i = sidx[p];
-        srec[p] = __ldg(&rec4[i]);
-        srec2[p] = make_uint2(__ldg(&in.blen[i]), __ldg(&in.matches[i]));
-    });
     u32 n_groups;
     // groups of at least fx_min positions are chained by the fixed-point iteration (SWG_NO_FIXPOINT=1: by the warp walk)
-    const u32 fx_min = getenv("SWG_NO_FIXPOINT") ? NONE32 : (getenv("SWG_FIXPOINT_MIN") ? (u32)atoi(getenv("SWG_FIXPOINT_MIN")) : FX_MIN_GROUP);
-    {   // refuse inputs whose chaining would need an absurd number of candidate evaluations (e.g. one 50 M-mapping pile:
-        // ~2e13; the reference is O(n * window) there as well) instead of occupying the GPU for hours
+    const u32 fx_min = K.no_fixpoint ? NONE32 : (K.fixpoint_min ? K.fixpoint_min : FX_MIN_GROUP);
+    {   // group count, positions in huge groups and a rough count of the candidate evaluations ahead (SWG_MAX_PAIR_EVALS, if
+        // set, refuses an input beyond it; by default nothing is refused: the reference runs such piles to completion too)
         k_chain_work_estimate<<<(u32)c->sm_count * 8, 256, 0, st>>>(srec, gstart, d_tot, n_m, cfg.scaffold_gap, fx_min, ctr);
         lc.n++;
         u32 *h = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
         SWG_CUDA(cudaMemcpyAsync(h, d_tot, sizeof(u32), cudaMemcpyDeviceToHost, st)); // group count and estimate in one round trip
         read_counters(c);
         n_groups = *h;
-        static const double max_evals = getenv("SWG_MAX_PAIR_EVALS") ? atof(getenv("SWG_MAX_PAIR_EVALS")) : 5e12;
-        if ((double)c->h_ctr[C_WORK] > max_evals)
+        if (K.max_pair_evals > 0 && (double)c->h_ctr[C_WORK] > K.max_pair_evals)
             throw RangeError{"chaining would need ~" + std::to_string((double)c->h_ctr[C_WORK]) +
-                             " candidate evaluations (dense pile); raise SWG_MAX_PAIR_EVALS to run it anyway"};
+                             " candidate evaluations (dense pile), more than SWG_MAX_PAIR_EVALS"};
     }
 
     u32 n_huge = 0; // positions in huge groups (fixed-point chaining; also selects the bucketed inversion capture)
     stage_mark(c, "chaining");
-    // ---- K3: best-buddy chaining (candidates -> sequential resolve -> aggregates) -------------------
-    u64 *bps = A.take<u64>(n_m);
-    u32 *root = A.take<u32>(n_m);
+    // ---- K3: best-buddy chaining (claims -> sequential resolve of the dirty groups -> chain numbers -> aggregates) ----
+    u64 *bps = A.take<u64>(n_m);     // best_pred_score: only the dirty groups touch it
+    u32 *pred = A.take<u32>(n_m);    // best_pred_idx
     Cand *cand = A.take<Cand>(n_m);
     u32 *grp_minidx = A.take<u32>(n_groups); // per GROUP: min original index over its members (first appearance of the group)
-    u8 *grp_has_cand = A.take<u8>(n_groups);
+    u8 *grp_dirty = A.take<u8>(n_groups);
     u32 *work = A.take<u32>(n_groups), *work_big = A.take<u32>(n_groups);
-    u32 *bb_ctr = A.take<u32>(4); // [0] #ordinary groups, [1] their work counter, [2] #large/dense groups, [3] their work counter
+    u32 *bb_ctr = A.take<u32>(4); // [0] #ordinary dirty groups, [1] their work counter, [2] #large/dense dirty groups, [3] their work counter
+    u32 *root_preset = nullptr;   // roots of the positions of huge groups (fixed-point chaining), NONE32 elsewhere
     SWG_CUDA(cudaMemsetAsync(bb_ctr, 0, 4 * sizeof(u32), st));
-    SWG_CUDA(cudaMemsetAsync(grp_has_cand, 0, n_groups, st));
+    SWG_CUDA(cudaMemsetAsync(grp_dirty, 0, n_groups, st));
     SWG_CUDA(cudaMemsetAsync(grp_minidx, 0xFF, sizeof(u32) * (size_t)n_groups, st));
+    SWG_CUDA(cudaMemsetAsync(pred, 0xFF, sizeof(u32) * (size_t)n_m, st));
     {
-        k_chain_candidates<<<cdiv(n_m, 256), 256, 0, st>>>(srec, skey, gid, gstart, n_groups, n_m, gshift, cfg.scaffold_gap, cand, bps, root, grp_has_cand);
+        k_chain_candidates<<<cdiv(n_m, 256), 256, 0, st>>>(srec, skey, gid, gstart, n_groups, n_m, gshift, cfg.scaffold_gap, cand, pred, grp_dirty);
         lc.n++;
         stage_mark(c, "ch_worklists");
-        // work lists: groups with at least one candidate, split into ordinary (thread per group) and large/dense
+        // work lists: the dirty groups (a successor claimed twice), split into ordinary (thread per group) and large/dense
         // (warp per group: size > 4096 or an expected window > 64 candidates)
         const u64 Gj = cfg.scaffold_gap;
         auto is_big = [=] __device__(u32 g) -> bool {
@@ -557,44 +638,53 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             const u32 s0 = gstart[g], e0 = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
             return e0 - s0 >= fx_min;
         };
-        scan_apply([=] __device__(u32 g) -> u32 { return (grp_has_cand[g] && !is_big(g) && !is_huge(g)) ? 1u : 0u; },
+        scan_apply([=] __device__(u32 g) -> u32 { return (grp_dirty[g] && !is_big(g) && !is_huge(g)) ? 1u : 0u; },
                    [=] __device__(u32 g, u32 ex, u32 v) { if (v) work[ex] = g; }, n_groups, bsum, bb_ctr, st, lc);
-        scan_apply([=] __device__(u32 g) -> u32 { return (grp_has_cand[g] && is_big(g)) ? 1u : 0u; },
+        scan_apply([=] __device__(u32 g) -> u32 { return (grp_dirty[g] && is_big(g)) ? 1u : 0u; },
                    [=] __device__(u32 g, u32 ex, u32 v) { if (v) work_big[ex] = g; }, n_groups, bsum, bb_ctr + 2, st, lc);
         stage_mark(c, "ch_resolve");
         // enough threads to hide the dependent-load latency of a step, few enough that every group's lines stay in L1/L2
-        static const int resolve_mult = getenv("SWG_RESOLVE_MULT") ? atoi(getenv("SWG_RESOLVE_MULT")) : 4;
-        k_chain_resolve<<<(u32)c->sm_count * resolve_mult, 128, 0, st>>>(cand, srec, skey, gstart, n_groups, n_m, work, bb_ctr, gshift, cfg.scaffold_gap,
-                                                             bps, root, bb_ctr + 1);
+        k_chain_resolve<<<(u32)c->sm_count * K.resolve_mult, 128, 0, st>>>(cand, srec, skey, gstart, n_groups, n_m, work, bb_ctr, gshift, cfg.scaffold_gap,
+                                                                             bps, pred, bb_ctr + 1);
         k_chain_resolve_warp<<<(u32)c->sm_count * 4, 128, 0, st>>>(cand, srec, skey, gstart, n_groups, n_m, work_big, bb_ctr + 2, gshift,
-                                                                  cfg.scaffold_gap, bps, root, bb_ctr + 3);
+                                                                  cfg.scaffold_gap, bps, pred, bb_ctr + 3);
         lc.n += 2;
         n_huge = (u32)c->h_ctr[C_HUGE];
         if (n_huge) {
             stage_mark(c, "ch_fixpoint");
             u32 *hpos = A.take<u32>(n_huge);
+            root_preset = A.take<u32>(n_m);
+            SWG_CUDA(cudaMemsetAsync(root_preset, 0xFF, sizeof(u32) * (size_t)n_m, st));
             scan_apply([=] __device__(u32 p) -> u32 { return is_huge(gid[p]) ? 1u : 0u; },
                        [=] __device__(u32 p, u32 ex, u32 v) { if (v) hpos[ex] = p; }, n_m, bsum, d_tot + 3, st, lc);
-            if (!chain_fixpoint(c, n_huge, hpos, srec, skey, gshift, gid, gstart, n_groups, n_m, cand, cfg.scaffold_gap, root, bsum)) {
+            if (!chain_fixpoint(c, n_huge, hpos, srec, skey, gshift, gid, gstart, n_groups, n_m, cand, cfg.scaffold_gap, root_preset, bsum)) {
                 // a dependency chain longer than the round limit: the huge groups go through the sequential warp walk after all
-                // (bps / root still hold k_chain_candidates' initial state for them)
+                // (it resets the groups' pred / best_pred_score itself; root_preset is untouched)
                 SWG_CUDA(cudaMemsetAsync(bb_ctr + 2, 0, 2 * sizeof(u32), st));
-                scan_apply([=] __device__(u32 g) -> u32 { return (grp_has_cand[g] && is_huge(g)) ? 1u : 0u; },
+                scan_apply([=] __device__(u32 g) -> u32 { return is_huge(g) ? 1u : 0u; },
                            [=] __device__(u32 g, u32 ex, u32 v) { if (v) work_big[ex] = g; }, n_groups, bsum, bb_ctr + 2, st, lc);
                 k_chain_resolve_warp<<<(u32)c->sm_count * 4, 128, 0, st>>>(cand, srec, skey, gstart, n_groups, n_m, work_big, bb_ctr + 2, gshift,
-                                                                          cfg.scaffold_gap, bps, root, bb_ctr + 3);
+                                                                          cfg.scaffold_gap, bps, pred, bb_ctr + 3);
                 lc.n++;
             }
         }
     }
-    stage_mark(c, "ch_aggregate");
-    // ---- K4: dense chain table + mass/identity filter + order key (A,B) ----------------------------
-    // upper bound on chains is n_m; the table is sized after counting heads
-    u32 *chain_of_pos = A.take<u32>(n_m);
-    u32 *head_pos = A.take<u32>(n_m); // compacted head positions (C of them)
+    stage_mark(c, "ch_number");
+    // ---- roots + dense chain numbers in one pass (k_chain_number), then the chain table ---------------
+    u32 *chain_of = A.take<u32>(n_m);  // chain number of every sorted position
+    u32 *head_pos = A.take<u32>(n_m);  // compacted head positions (C of them)
     u32 *d_nch = d_tot + 2;
-    scan_apply([=] __device__(u32 p) -> u32 { return root[p] == p ? 1u : 0u; },
-               [=] __device__(u32 p, u32 ex, u32 v) { if (v) { chain_of_pos[p] = ex; head_pos[ex] = p; } }, n_m, bsum, d_nch, st, lc);
+    {
+        const u32 tiles = cdiv(n_m, CR_TILE);
+        u64 *cn_status = A.take<u64>(tiles + 1);
+        u32 *cn_ctr = A.take<u32>(2);
+        SWG_CUDA(cudaMemsetAsync(cn_status, 0, sizeof(u64) * (size_t)(tiles + 1), st));
+        SWG_CUDA(cudaMemsetAsync(cn_ctr, 0, 2 * sizeof(u32), st));
+        SWG_CUDA(cudaMemsetAsync(chain_of, 0xFF, sizeof(u32) * (size_t)n_m, st));
+        if (root_preset) k_chain_number<true><<<tiles, CR_THREADS, 0, st>>>(pred, root_preset, n_m, chain_of, head_pos, cn_status, cn_ctr, d_nch);
+        else k_chain_number<false><<<tiles, CR_THREADS, 0, st>>>(pred, nullptr, n_m, chain_of, head_pos, cn_status, cn_ctr, d_nch);
+        lc.n++;
+    }
     const u32 C = read_u32(c, d_nch);
     stage_mark(c, "chain_table");
     S.n_chains = C;
@@ -613,8 +703,27 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     SWG_CUDA(cudaMemsetAsync(cd.tmax, 0, sizeof(u32) * (size_t)C, st));
     SWG_CUDA(cudaMemsetAsync(cd.sum_matches, 0, sizeof(u64) * (size_t)C, st));
     SWG_CUDA(cudaMemsetAsync(cd.sum_block, 0, sizeof(u64) * (size_t)C, st));
-    k_chain_aggregate<<<cdiv(n_m, 256), 256, 0, st>>>(srec, srec2, sidx, gid, root, chain_of_pos, n_m, cd, grp_minidx);
+    k_chain_aggregate<<<cdiv(n_m, 256), 256, 0, st>>>(srec, srec2, sidx, gid, chain_of, n_m, cd, grp_minidx);
     lc.n++;
+    // exact re-rank: ln(gap) of every chain from the host libm (C values down, C values up)
+    double *host_lg = nullptr;
+    if (exact_host && C > 0) {
+        std::vector<u32> hq0(C), hq1(C);
+        std::vector<u64> hsb(C);
+        SWG_CUDA(cudaMemcpyAsync(hq0.data(), cd.qmin, sizeof(u32) * (size_t)C, cudaMemcpyDeviceToHost, st));
+        SWG_CUDA(cudaMemcpyAsync(hq1.data(), cd.qmax, sizeof(u32) * (size_t)C, cudaMemcpyDeviceToHost, st));
+        SWG_CUDA(cudaMemcpyAsync(hsb.data(), cd.sum_block, sizeof(u64) * (size_t)C, cudaMemcpyDeviceToHost, st));
+        SWG_CUDA(cudaStreamSynchronize(st));
+        std::vector<double> lg(C);
+        for (u32 ci = 0; ci < C; ci++) {
+            const u64 total = (u64)(hq1[ci] - hq0[ci]);
+            const u64 gap = total > hsb[ci] ? total - hsb[ci] : 0;
+            lg[ci] = gap > 0 ? std::max(std::log((double)gap), 0.0) : 0.0; // paf_filter.rs:902-906
+        }
+        host_lg = A.take<double>(C);
+        SWG_CUDA(cudaMemcpyAsync(host_lg, lg.data(), sizeof(double) * (size_t)C, cudaMemcpyHostToDevice, st));
+        SWG_CUDA(cudaStreamSynchronize(st)); // lg lives on this stack frame
+    }
     const int nb = bits_for(N);
     if (2 * nb > 63) throw RangeError{"too many records for the chain order key"};
     u64 *okey_all = A.take<u64>(C);
@@ -631,10 +740,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             u32 qmin = cd.qmin[ci], qmax = cd.qmax[ci], tmin = cd.tmin[ci], tmax = cd.tmax[ci];
             u64 sm = cd.sum_matches[ci], sbk = cd.sum_block[ci];
             u64 total = (u64)(qmax - qmin);                         // paf_filter.rs:896
-            u64 gap = total > sbk ? total - sbk : 0;                // saturating_sub, :901
-            double lg = gap > 0 ? fmax(log((double)gap), 0.0) : 0.0; // :902-906
-            double eff = __dadd_rn((double)sbk, lg);
-            double wid = eff > 0.0 ? __ddiv_rn((double)sm, eff) : 0.0;
+            double wid = chain_identity_fn(total, sbk, sm, cuda_log, host_lg ? host_lg + ci : nullptr); // :901-913
             bool pass = total >= min_len && wid >= min_sid;         // :449-455
             ct.qid[ci] = qid; ct.tid[ci] = tid; ct.fwd[ci] = fwd;
             ct.wid[ci] = wid; ct.pass[ci] = pass ? 1 : 0; // ct.qs / qe / ts / te already hold the bounding box
@@ -688,8 +794,21 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             t_c2key[t] = ((u64)q << sb) | tt;
             t_g2key[t] = ((u64)in.P2[q] << sb) | in.P2[tt];
             t_fwd[t] = ct.fwd[ci];
-            t_score[t] = score_fn(scoring, ct.wid[ci], ct.qs[ci], ct.qe[ci]);
+            t_score[t] = score_fn(scoring, ct.wid[ci], ct.qs[ci], ct.qe[ci], cuda_log);
         });
+        if (exact_host) { // exact re-rank: the chain scores from the host libm as well
+            std::vector<double> hw(C1), hs(C1);
+            std::vector<u32> hq0(C1), hq1(C1);
+            double *d_w = A.take<double>(C1);
+            launch_for<t_tspace>(C1, st, lc, [=] __device__(u32 t) { d_w[t] = ct.wid[oc_chain[t]]; });
+            SWG_CUDA(cudaMemcpyAsync(hw.data(), d_w, sizeof(double) * (size_t)C1, cudaMemcpyDeviceToHost, st));
+            SWG_CUDA(cudaMemcpyAsync(hq0.data(), t_qs, sizeof(u32) * (size_t)C1, cudaMemcpyDeviceToHost, st));
+            SWG_CUDA(cudaMemcpyAsync(hq1.data(), t_qe, sizeof(u32) * (size_t)C1, cudaMemcpyDeviceToHost, st));
+            SWG_CUDA(cudaStreamSynchronize(st));
+            for (u32 t = 0; t < C1; t++) hs[t] = host_score(scoring, hw[t], hq0[t], hq1[t]);
+            SWG_CUDA(cudaMemcpyAsync(t_score, hs.data(), sizeof(double) * (size_t)C1, cudaMemcpyHostToDevice, st));
+            SWG_CUDA(cudaStreamSynchronize(st)); // hs lives on this stack frame
+        }
         // first-appearance order of chromosome pairs and genome pairs over the filtered chains
         u32 *c2min = A.take<u32>(C1), *g2min = A.take<u32>(C1);
         u64 *sk = A.take<u64>(C1), *sk2 = A.take<u64>(C1);
@@ -738,7 +857,8 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             const u32 *fin = sv;
             // chain number + the order key of its genome-pair group (first-appearance indices A, B of the group's first
             // filtered chain): what a multi-GPU driver needs to merge the per-shard numberings (swg_last_chain_keys)
-            u32 *keyA = A.take<u32>(C2 + 1), *keyB = A.take<u32>(C2 + 1);
+            c->keys.reserve(((size_t)C2 + 1) * 8 + 1024); // context-owned: later calls that rewind the scratch arena do not touch it
+            u32 *keyA = c->keys.take<u32>(C2 + 1), *keyB = c->keys.take<u32>(C2 + 1);
             const u64 *okc = okey;
             const u64 bmask = (1ull << nb) - 1;
             launch_for<t_final_k>(C2, st, lc, [=] __device__(u32 u) {
@@ -758,7 +878,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     stage_mark(c, "assign+inversion+rescue");
     // ---- K5: anchors = members of kept chains (paf_filter.rs:517-528) ---------------------------------
     launch_for<t_assign>(n_m, st, lc, [=] __device__(u32 p) {
-        u32 ci = chain_of_pos[root[p]];
+        u32 ci = chain_of[p];
         u32 i = sidx[p];
         u32 kk = ct.k[ci];
         if (kk) { status[i] = 1; chain_id[i] = kk; }
@@ -785,7 +905,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         // reverse mapping is O(n * chains).  Then (or with SWG_INV_GRID=1) chains and mappings meet in buckets of the query axis.
         const int wb = std::max(17, bits_for(2 * cfg.scaffold_gap + 1)); // bucket width 2^wb > 2 * jump
         const int bb = cb > wb ? cb - wb : 1;
-        const bool inv_grid = (n_huge > 0 || getenv("SWG_INV_GRID")) && !getenv("SWG_INV_NO_GRID") && 2 * sb + bb + 1 <= 64;
+        const bool inv_grid = (n_huge > 0 || K.inv_grid) && !K.inv_no_grid && 2 * sb + bb + 1 <= 64;
         if (inv_grid) {
             stage_mark(c, "inversion_grid");
             const u64 G = cfg.scaffold_gap;
@@ -896,7 +1016,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         if (D > 0) {
             // anchor list (status == 1) ordered by (chromosome pair, query center); one sort when the key fits 64 bits,
             // else two chained stable sorts (center first, then the pair)
-            const bool wide_a = (2 * sb + cb > 63) || (getenv("SWG_FORCE_WIDE_KEYS") != nullptr);
+            const bool wide_a = (2 * sb + cb > 63) || K.force_wide;
             u64 *ak = A.take<u64>(N), *ak2 = A.take<u64>(N);
             u32 *av = A.take<u32>(N), *av2 = A.take<u32>(N);
             u32 *d_na = A.take<u32>(2);
@@ -991,12 +1111,102 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     finish();
 }
 
+// ---- does the device's ln() produce the host libm's bits? ------------------------------------------
+// 2^16 probe arguments: every integer up to 2^15 and pseudo-random integers up to 2^32 (spans and gaps are integers).
+struct t_probe;
+static bool probe_log(swg_ctx *c) {
+    const u32 n = 1u << 16;
+    c->arena.reserve((size_t)n * 32 + (1u << 20));
+    double *d = c->arena.take<double>(2 * (size_t)n);
+    launch_for<t_probe>(n, c->stream, c->lc, [=] __device__(u32 k) {
+        u64 x = k < (1u << 15) ? (u64)k + 1 : ((u64)k * 0x9E3779B97F4A7C15ull >> 32) + 2;
+        d[k] = ln_fn((double)x, false);
+        d[n + k] = ln_fn((double)x, true);
+    });
+    std::vector<double> h(2 * (size_t)n);
+    SWG_CUDA(cudaMemcpyAsync(h.data(), d, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, c->stream));
+    SWG_CUDA(cudaStreamSynchronize(c->stream));
+    bool port_ok = true, cuda_ok = true;
+    for (u32 k = 0; k < n; k++) {
+        const u64 x = k < (1u << 15) ? (u64)k + 1 : ((u64)k * 0x9E3779B97F4A7C15ull >> 32) + 2;
+        const double ref = std::log((double)x);
+        port_ok &= std::memcmp(&ref, &h[k], 8) == 0;
+        cuda_ok &= std::memcmp(&ref, &h[n + k], 8) == 0;
+    }
+    c->cudalog_matches_host = cuda_ok;
+    return port_ok;
+}
+
+// ---- the filter with the exact re-rank around it ---------------------------------------
+// Normal case: one run_filter.  If a sweep saw two scores within NEAR_TIE_ULPS of each other AND the device's ln() is not
+// known to equal the host libm's (another glibc, SWG_LOG_IMPL=cuda), a ranking could differ from the reference's by one
+// rounding: the call is redone with every logarithm computed by the HOST libm — the record scores as a column
+// (identity * ln(span), all host threads), the chain-level ones inside run_filter.  SWG_EXACT_SCORES=always / never.
+// host_*: the caller's host columns when it has them (swg_filter), else NULL (they are downloaded).
+static void run_filter_exact(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *status, u32 *chain_id, swg_stats *stats, cudaEvent_t ev_matches,
+                             const swg_mappings *host) {
+    const Knobs &K = c->knobs;
+    const bool log_ok = K.cuda_log ? c->cudalog_matches_host : c->log_matches_host;
+    const bool can = !in.score && in.n > 0;
+    swg_stats first;
+    std::memset(&first, 0, sizeof first);
+    if (!(can && K.exact_scores == 1)) {
+        run_filter(c, cfg, in, status, chain_id, &first, ev_matches);
+        if (stats) *stats = first;
+        if (!can || K.exact_scores == 2 || first.score_near_ties == 0 || log_ok) return;
+    }
+    const u32 n = in.n;
+    if (ev_matches) SWG_CUDA(cudaStreamWaitEvent(c->stream, ev_matches, 0));
+    std::vector<u32> hqs, hqe, hbl, hmt;
+    std::vector<double> hid;
+    const u32 *qs = host ? host->query_start : nullptr, *qe = host ? host->query_end : nullptr;
+    const u32 *bl = host ? host->block_length : nullptr, *mt = host ? host->matches : nullptr;
+    const double *id = host ? host->identity : nullptr;
+    if (!host) {
+        auto down = [&](auto &vec, const void *src, size_t bytes) { vec.resize(n); SWG_CUDA(cudaMemcpyAsync(vec.data(), src, bytes, cudaMemcpyDeviceToHost, c->stream)); };
+        down(hqs, in.qs, (size_t)n * 4); down(hqe, in.qe, (size_t)n * 4);
+        if (in.identity) down(hid, in.identity, (size_t)n * 8);
+        else { down(hbl, in.blen, (size_t)n * 4); down(hmt, in.matches, (size_t)n * 4); }
+        SWG_CUDA(cudaStreamSynchronize(c->stream));
+        qs = hqs.data(); qe = hqe.data();
+        id = in.identity ? hid.data() : nullptr;
+        bl = hbl.data(); mt = hmt.data();
+    }
+    c->h_score.resize(n);
+    {
+        const int scoring = cfg.scoring_function;
+        const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> th;
+        double *out = c->h_score.data();
+        for (unsigned t = 0; t < nt; t++)
+            th.emplace_back([=]() {
+                const size_t a = (size_t)n * t / nt, b = (size_t)n * (t + 1) / nt;
+                for (size_t i = a; i < b; i++) {
+                    const double idv = id ? id[i] : (double)mt[i] / (double)(bl[i] > 1 ? bl[i] : 1);
+                    out[i] = host_score(scoring, idv, qs[i], qe[i]);
+                }
+            });
+        for (auto &t : th) t.join();
+    }
+    c->score_arena.reserve((size_t)n * 8 + 1024);
+    double *d_score = c->score_arena.take<double>(n);
+    SWG_CUDA(cudaMemcpyAsync(d_score, c->h_score.data(), (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    DevIn in2 = in;
+    in2.score = d_score;
+    swg_stats second;
+    run_filter(c, cfg, in2, status, chain_id, &second, nullptr, true);
+    second.exact_rerank = 1;
+    second.gpu_launches += first.gpu_launches;
+    if (stats) *stats = second;
+}
+
 static int guarded(swg_ctx *c, const char *what, void (*fn)(void *), void *arg) {
     struct DrainCopies { // an error must not leave the caller's host buffers in use by an in-flight copy
         swg_ctx *c;
         ~DrainCopies() { if (c && c->copy_stream) cudaStreamSynchronize(c->copy_stream); }
     } drain{c};
     try {
+        if (c) c->knobs = read_knobs();
         fn(arg);
         return SWG_OK;
     } catch (const CudaError &e) {
@@ -1030,7 +1240,7 @@ static bool check_maps(swg_ctx *c, const swg_mappings *m) {
     if (m->n == 0) return true;
     if (m->n >= 0x7FFFFFF0ull) { set_err(c, "n too large (must be < 2^31 per context)"); return false; }
     if (!m->query_id || !m->target_id || !m->query_start || !m->query_end || !m->target_start || !m->target_end ||
-        !m->block_length || !m->matches || !m->identity || !m->strand || !m->seq_genome_id || !m->seq_genome2_id || m->n_seq == 0) {
+        !m->block_length || !m->matches || !m->strand || !m->seq_genome_id || !m->seq_genome2_id || m->n_seq == 0) { // identity may be NULL
         set_err(c, "swg_mappings has a NULL column or n_seq == 0");
         return false;
     }
@@ -1044,7 +1254,7 @@ static DevIn make_devin(const swg_mappings *m) {
     return d;
 }
 
-struct UploadArgs { swg_ctx *c; const swg_mappings *in; swg_mappings *dev; swg_result *res; Arena *arena; bool overlap_matches = false; };
+struct UploadArgs { swg_ctx *c; const swg_mappings *in; swg_mappings *dev; swg_result *res; Arena *arena; bool overlap_matches = false; size_t h2d_bytes = 0; };
 
 static void do_upload(void *p) {
     UploadArgs *a = (UploadArgs *)p;
@@ -1052,7 +1262,8 @@ static void do_upload(void *p) {
     const swg_mappings *h = a->in;
     SWG_CUDA(cudaSetDevice(c->device));
     size_t n = h->n;
-    size_t bytes = n * (8 * 4 + 8 + 1 + (h->score ? 8 : 0) + 1 + 4) + (size_t)h->n_seq * 8 + 64 * 256;
+    size_t bytes = n * (8 * 4 + (h->identity ? 8 : 0) + 1 + (h->score ? 8 : 0) + 1 + 4) + (size_t)h->n_seq * 8 + 64 * 256;
+    a->h2d_bytes = n * (8 * 4 + (h->identity ? 8 : 0) + 1 + (h->score ? 8 : 0)) + (size_t)h->n_seq * 8;
     a->arena->reserve(bytes);
     Arena &A = *a->arena;
     swg_mappings d = *h;
@@ -1062,7 +1273,7 @@ static void do_upload(void *p) {
     d.query_start = up32(h->query_start, n); d.query_end = up32(h->query_end, n);
     d.target_start = up32(h->target_start, n); d.target_end = up32(h->target_end, n);
     d.block_length = up32(h->block_length, n);
-    { double *dst = A.take<double>(n); SWG_CUDA(cudaMemcpyAsync(dst, h->identity, n * 8, cudaMemcpyHostToDevice, st)); d.identity = dst; }
+    if (h->identity) { double *dst = A.take<double>(n); SWG_CUDA(cudaMemcpyAsync(dst, h->identity, n * 8, cudaMemcpyHostToDevice, st)); d.identity = dst; }
     if (h->score) { double *dst = A.take<double>(n); SWG_CUDA(cudaMemcpyAsync(dst, h->score, n * 8, cudaMemcpyHostToDevice, st)); d.score = dst; }
     { u8 *dst = A.take<u8>(n); SWG_CUDA(cudaMemcpyAsync(dst, h->strand, n, cudaMemcpyHostToDevice, st)); d.strand = dst; }
     d.seq_genome_id = up32(h->seq_genome_id, h->n_seq);
@@ -1215,6 +1426,9 @@ swg_ctx *swg_create(int device) {
         SWG_CUDA(cudaEventCreateWithFlags(&c->ev_ctr, cudaEventDisableTiming));
         SWG_CUDA(cudaMallocHost(&c->h_ctr, sizeof(u64) * (C_COUNT + 8)));
         SWG_CUDA(cudaMalloc(&c->d_ctr, sizeof(u64) * C_COUNT));
+        rs_init_device(); // dynamic shared memory opt-in of the one-sweep kernels: a per-device attribute
+        c->knobs = read_knobs();
+        c->log_matches_host = probe_log(c);
     } catch (const CudaError &e2) {
         g_create_error = std::string("swg_create: CUDA error '") + cudaGetErrorString(e2.code) + "'";
         delete c;
@@ -1232,6 +1446,8 @@ void swg_destroy(swg_ctx *c) {
     cudaSetDevice(c->device);
     c->arena.release();
     c->io.release();
+    c->keys.release();
+    c->score_arena.release();
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     for (char *p : c->pin) cudaFreeHost(p);
     for (auto &ev : c->pin_ev) cudaEventDestroy(ev);
@@ -1259,7 +1475,9 @@ int swg_filter_device(swg_ctx *c, const swg_config *cfg, const swg_mappings *dev
         FilterDevArgs *a = (FilterDevArgs *)p;
         SWG_CUDA(cudaSetDevice(a->c->device));
         SWG_CUDA(cudaEventRecord(a->c->ev[1], a->c->stream));
-        run_filter(a->c, *a->cfg, make_devin(a->in), a->out->status, a->out->chain_id, a->stats);
+        swg_stats local;
+        run_filter_exact(a->c, *a->cfg, make_devin(a->in), a->out->status, a->out->chain_id, &local, nullptr, nullptr);
+        if (a->stats) *a->stats = local;
         SWG_CUDA(cudaEventRecord(a->c->ev[2], a->c->stream));
         SWG_CUDA(cudaStreamSynchronize(a->c->stream));
         if (a->stats) {
@@ -1287,7 +1505,7 @@ int swg_filter(swg_ctx *c, const swg_config *cfg, const swg_mappings *host_in, s
         swg_stats local;
         std::memset(&local, 0, sizeof local);
         if (a->in->n) {
-            run_filter(c, *a->cfg, make_devin(&dev), dres.status, dres.chain_id, &local, c->ev_copy[1]);
+            run_filter_exact(c, *a->cfg, make_devin(&dev), dres.status, dres.chain_id, &local, c->ev_copy[1], a->in);
             SWG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy[1], 0)); // early exits never touched `matches`: still wait for its copy
         }
         SWG_CUDA(cudaEventRecord(c->ev[2], c->stream));
@@ -1302,6 +1520,8 @@ int swg_filter(swg_ctx *c, const swg_config *cfg, const swg_mappings *host_in, s
         SWG_CUDA(cudaEventElapsedTime(&m1, c->ev[1], c->ev[2]));
         SWG_CUDA(cudaEventElapsedTime(&m2, c->ev[2], c->ev[3]));
         local.ms_h2d = m0; local.ms_device = m1; local.ms_d2h = m2;
+        local.h2d_bytes = ua.h2d_bytes;
+        local.d2h_bytes = a->in->n * 5;
         if (a->stats) *a->stats = local;
     }, &a);
 }
@@ -1354,6 +1574,144 @@ int swg_last_chain_keys(swg_ctx *c, uint64_t cap, uint32_t *first_index_genome_p
     }, &a);
 }
 
+// ---- multi-GPU merge helpers (shards are unions of whole genome-pair units) -------------------------------
+// The kept chains of one unit are numbered consecutively, on one GPU and in the merged numbering alike (order O3 sorts by the
+// unit's first index A first), so merging needs only (A, count) per unit: swg_last_chain_units reports the runs of equal A
+// among the kept chains of the last call (a few thousand values), swg_renumber_chains_device adds a per-run offset.
+struct t_units; struct t_renumber; struct t_pack;
+int swg_last_chain_units(swg_ctx *c, uint64_t cap, uint32_t *unit_first_index, uint32_t *unit_first_chain, uint64_t *n_units) {
+    if (!c || !n_units) return SWG_ERR_ARG;
+    struct Args { swg_ctx *c; u64 cap; u32 *a, *k; u64 *n; } a{c, cap, unit_first_index, unit_first_chain, n_units};
+    return guarded(c, "swg_last_chain_units", [](void *p) {
+        Args *a = (Args *)p;
+        swg_ctx *c = a->c;
+        *a->n = 0;
+        const u32 C2 = (u32)c->last_n_chains;
+        if (C2 == 0) return;
+        SWG_CUDA(cudaSetDevice(c->device));
+        // runs of equal A in chain order; the list lives behind the keys in the context-owned arena
+        u32 *run_k = c->keys.take<u32>(C2), *bsum = c->keys.take<u32>(scan_temp_u32(C2)), *tot = c->keys.take<u32>(1);
+        const u32 *kA = c->last_keyA;
+        scan_apply([=] __device__(u32 u) -> u32 { return (u == 0 || kA[u] != kA[u - 1]) ? 1u : 0u; },
+                   [=] __device__(u32 u, u32 ex, u32 v) { if (v) run_k[ex] = u; }, C2, bsum, tot, c->stream, c->lc);
+        const u32 nu = read_u32(c, tot);
+        *a->n = nu;
+        if (a->cap < nu || !a->a || !a->k) { if (a->cap == 0) return; throw RangeError{"capacity too small"}; }
+        std::vector<u32> hk(nu);
+        SWG_CUDA(cudaMemcpyAsync(hk.data(), run_k, sizeof(u32) * nu, cudaMemcpyDeviceToHost, c->stream));
+        u32 *d_a = c->keys.take<u32>(nu);
+        launch_for<t_units>(nu, c->stream, c->lc, [=] __device__(u32 r) { d_a[r] = kA[run_k[r]]; });
+        SWG_CUDA(cudaMemcpyAsync(a->a, d_a, sizeof(u32) * nu, cudaMemcpyDeviceToHost, c->stream));
+        SWG_CUDA(cudaStreamSynchronize(c->stream));
+        for (u32 r = 0; r < nu; r++) a->k[r] = hk[r] + 1; // chain numbers are 1-based
+    }, &a);
+}
+// chain_id[i] += delta[run of chain_id[i]] for every record with a chain (runs given by their first local chain number,
+// ascending); chain_id is a DEVICE array of n entries, the two run arrays are HOST arrays.
+int swg_renumber_chains_device(swg_ctx *c, uint64_t n, uint32_t *chain_id_dev, uint64_t n_units, const uint32_t *unit_first_chain,
+                               const int64_t *unit_delta) {
+    if (!c || (n && !chain_id_dev) || (n_units && (!unit_first_chain || !unit_delta)) || n >= 0x7FFFFFF0ull) return SWG_ERR_ARG;
+    struct Args { swg_ctx *c; u32 n; u32 *ch; u32 nu; const u32 *fk; const int64_t *dl; } a{c, (u32)n, chain_id_dev, (u32)n_units, unit_first_chain, unit_delta};
+    return guarded(c, "swg_renumber_chains_device", [](void *p) {
+        Args *a = (Args *)p;
+        swg_ctx *c = a->c;
+        if (a->n == 0 || a->nu == 0) return;
+        SWG_CUDA(cudaSetDevice(c->device));
+        const u32 nu = a->nu;
+        c->score_arena.reserve((size_t)nu * 16 + 1024); // small, context-owned (the scratch arena may hold the caller's data)
+        u32 *fk = c->score_arena.take<u32>(nu);
+        i64 *dl = c->score_arena.take<i64>(nu);
+        SWG_CUDA(cudaMemcpyAsync(fk, a->fk, sizeof(u32) * nu, cudaMemcpyHostToDevice, c->stream));
+        SWG_CUDA(cudaMemcpyAsync(dl, a->dl, sizeof(i64) * nu, cudaMemcpyHostToDevice, c->stream));
+        u32 *ch = a->ch;
+        launch_for<t_renumber>(a->n, c->stream, c->lc, [=] __device__(u32 i) {
+            const u32 k = ch[i];
+            if (k == 0) return;
+            u32 lo = 0, hi = nu; // last run whose first chain number is <= k
+            while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (fk[mid] <= k) lo = mid; else hi = mid; }
+            ch[i] = (u32)((i64)k + dl[lo]);
+        });
+        SWG_CUDA(cudaStreamSynchronize(c->stream));
+    }, &a);
+}
+// status bytes (0..3) -> 2 bits per record, 16 records per u32 (record i in bits 2*(i%16)); both DEVICE arrays
+int swg_pack_status_device(swg_ctx *c, uint64_t n, const uint8_t *status_dev, uint32_t *packed_dev) {
+    if (!c || (n && (!status_dev || !packed_dev)) || n >= 0x7FFFFFF0ull) return SWG_ERR_ARG;
+    struct Args { swg_ctx *c; u32 n; const u8 *s; u32 *o; } a{c, (u32)n, status_dev, packed_dev};
+    return guarded(c, "swg_pack_status_device", [](void *p) {
+        Args *a = (Args *)p;
+        swg_ctx *c = a->c;
+        if (a->n == 0) return;
+        SWG_CUDA(cudaSetDevice(c->device));
+        const u32 n = a->n, nw = cdiv(n, 16);
+        const u8 *st = a->s;
+        u32 *out = a->o;
+        launch_for<t_pack>(nw, c->stream, c->lc, [=] __device__(u32 w) {
+            u32 v = 0;
+            if ((u64)w * 16 + 16 <= n && ((size_t)(st + (size_t)w * 16) & 15) == 0) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(st + (size_t)w * 16);
+                const u32 x[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) v |= ((x[k] >> (8 * b)) & 3u) << (2 * (4 * k + b));
+            } else {
+                for (u32 k = 0; k < 16 && (u64)w * 16 + k < n; k++) v |= ((u32)st[(size_t)w * 16 + k] & 3u) << (2 * k);
+            }
+            out[w] = v;
+        });
+        SWG_CUDA(cudaStreamSynchronize(c->stream));
+    }, &a);
+}
+
+// ---- verification entry points: the f64 expressions of the path, evaluated on the device ------------------------
+struct t_verify;
+int swg_score_column(swg_ctx *c, uint64_t n, const double *identity, const uint32_t *qs, const uint32_t *qe, int scoring, double *out) {
+    if (!c || (n && (!identity || !qs || !qe || !out)) || scoring < 0 || scoring > 4 || n >= 0x7FFFFFF0ull) return SWG_ERR_ARG;
+    struct Args { swg_ctx *c; u32 n; const double *id; const u32 *qs, *qe; int scoring; double *out; } a{c, (u32)n, identity, qs, qe, scoring, out};
+    return guarded(c, "swg_score_column", [](void *p) {
+        Args *a = (Args *)p;
+        swg_ctx *c = a->c;
+        const u32 n = a->n;
+        if (n == 0) return;
+        SWG_CUDA(cudaSetDevice(c->device));
+        c->arena.reserve((size_t)n * 24 + (1u << 20));
+        double *id = c->arena.take<double>(n), *sc = c->arena.take<double>(n);
+        u32 *qs = c->arena.take<u32>(n), *qe = c->arena.take<u32>(n);
+        SWG_CUDA(cudaMemcpyAsync(id, a->id, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        SWG_CUDA(cudaMemcpyAsync(qs, a->qs, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        SWG_CUDA(cudaMemcpyAsync(qe, a->qe, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        const int scoring = a->scoring;
+        const bool cuda_log = c->knobs.cuda_log;
+        launch_for<t_verify>(n, c->stream, c->lc, [=] __device__(u32 i) { sc[i] = score_fn(scoring, id[i], qs[i], qe[i], cuda_log); });
+        SWG_CUDA(cudaMemcpyAsync(a->out, sc, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+        SWG_CUDA(cudaStreamSynchronize(c->stream));
+    }, &a);
+}
+int swg_chain_identity(swg_ctx *c, uint64_t n, const uint64_t *total_length, const uint64_t *sum_block, const uint64_t *sum_matches, double *out) {
+    if (!c || (n && (!total_length || !sum_block || !sum_matches || !out)) || n >= 0x7FFFFFF0ull) return SWG_ERR_ARG;
+    struct Args { swg_ctx *c; u32 n; const u64 *tl, *sb, *sm; double *out; } a{c, (u32)n, total_length, sum_block, sum_matches, out};
+    return guarded(c, "swg_chain_identity", [](void *p) {
+        Args *a = (Args *)p;
+        swg_ctx *c = a->c;
+        const u32 n = a->n;
+        if (n == 0) return;
+        SWG_CUDA(cudaSetDevice(c->device));
+        c->arena.reserve((size_t)n * 32 + (1u << 20));
+        u64 *tl = c->arena.take<u64>(n), *sb = c->arena.take<u64>(n), *sm = c->arena.take<u64>(n);
+        double *w = c->arena.take<double>(n);
+        SWG_CUDA(cudaMemcpyAsync(tl, a->tl, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        SWG_CUDA(cudaMemcpyAsync(sb, a->sb, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        SWG_CUDA(cudaMemcpyAsync(sm, a->sm, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        const bool cuda_log = c->knobs.cuda_log;
+        launch_for<t_verify>(n, c->stream, c->lc, [=] __device__(u32 i) { w[i] = chain_identity_fn(tl[i], sb[i], sm[i], cuda_log); });
+        SWG_CUDA(cudaMemcpyAsync(a->out, w, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+        SWG_CUDA(cudaStreamSynchronize(c->stream));
+    }, &a);
+}
+int swg_log_matches_host(const swg_ctx *c) { return c ? (c->log_matches_host ? 1 : 0) : SWG_ERR_ARG; }
+double swg_glibc_log_host(double x) { return glibc_log(x); }
+
 // Tuning aid (not part of the public header): sort n pseudo-random (key,payload) pairs over `bits` key bits, `reps`
 // times, and report the mean CUDA-event time of ONE one-sweep pass in *ms_per_pass.  Returns 0 and checks sortedness.
 int swg__bench_sort(swg_ctx *c, uint64_t n, int bits, int reps, double *ms_per_pass, int *sorted_ok) {
@@ -1404,6 +1762,70 @@ int swg__bench_sort(swg_ctx *c, uint64_t n, int bits, int reps, double *ms_per_p
             }
         }
         *a->ms = total / a->reps / passes;
+    }, &a);
+}
+
+// The same for the packed sort (rs_sort_packed): *ms_per_pass = mean time of one packed-word pass (8 B read + 8 B written per
+// element), *ms_total = the whole sort incl. histogram, pairs passes and the packing pass.  Checks that the result is the
+// stable order of the full keys and that every word carries its key's high bits.
+int swg__bench_sort_packed(swg_ctx *c, uint64_t n, int key_bits, int reps, double *ms_per_pass, double *ms_total, int *sorted_ok) {
+    if (!c || !ms_per_pass || n == 0 || n >= 0x7FFFFFF0ull || key_bits > 64) return SWG_ERR_ARG;
+    struct Args { swg_ctx *c; u32 n; int bits, reps; double *ms, *tot; int *ok; } a{c, (u32)n, key_bits, reps, ms_per_pass, ms_total, sorted_ok};
+    return guarded(c, "swg__bench_sort_packed", [](void *p) {
+        Args *a = (Args *)p;
+        swg_ctx *c = a->c;
+        SWG_CUDA(cudaSetDevice(c->device));
+        const u32 n = a->n;
+        c->arena.reserve((size_t)n * 40 + (64u << 20));
+        u64 *src = c->arena.take<u64>(n), *k = c->arena.take<u64>(n), *k2 = c->arena.take<u64>(n);
+        u32 *v = c->arena.take<u32>(n), *v2 = c->arena.take<u32>(n);
+        u64 *bad = c->arena.take<u64>(1);
+        const int bits = a->bits, ib = bits_for(n - 1);
+        launch_for<t_iota>(n, c->stream, c->lc, [=] __device__(u32 i) {
+            u64 x = (u64)i * 0x9E3779B97F4A7C15ull + 0x7F4A7C15ull;
+            x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
+            src[i] = bits >= 64 ? x : (x & ((1ull << bits) - 1));
+        });
+        double total = 0, whole = 0;
+        PackedSort ps;
+        for (int r = 0; r < a->reps; r++) {
+            SWG_CUDA(cudaMemcpyAsync(k, src, sizeof(u64) * n, cudaMemcpyDeviceToDevice, c->stream));
+            launch_for<t_gather>(n, c->stream, c->lc, [=] __device__(u32 i) { v[i] = i; });
+            Arena::Mark mk = c->arena.mark();
+            RadixSortPlan p = rs_plan(n, 0, bits);
+            void *tmp = c->arena.take<char>(p.temp_bytes);
+            SWG_CUDA(cudaEventRecord(c->ev[0], c->stream));
+            ps = rs_sort_packed(n, bits, ib, k, k2, v, v2, tmp, p, c->stream, c->sm_count, c->lc, c->ev_sort[0], c->ev_sort[1]);
+            SWG_CUDA(cudaEventRecord(c->ev[1], c->stream));
+            SWG_CUDA(cudaStreamSynchronize(c->stream));
+            c->arena.rewind(mk);
+            float ms = 0, ms2 = 0;
+            SWG_CUDA(cudaEventElapsedTime(&ms, c->ev_sort[0], c->ev_sort[1]));
+            SWG_CUDA(cudaEventElapsedTime(&ms2, c->ev[0], c->ev[1]));
+            total += ms / ps.timed_passes;
+            whole += ms2;
+        }
+        if (a->ok) {
+            SWG_CUDA(cudaMemsetAsync(bad, 0, sizeof(u64), c->stream));
+            const u64 *w = ps.packed;
+            const u64 mask = (1ull << ib) - 1;
+            const int c0 = ps.c0;
+            launch_for<t_maxp>(n, c->stream, c->lc, [=] __device__(u32 i) {
+                const u32 a0 = (u32)(w[i] & mask);
+                bool b = a0 >= n || (w[i] >> ib) != (src[a0 < n ? a0 : 0] >> c0);
+                if (!b && i + 1 < n) {
+                    const u32 a1 = (u32)(w[i + 1] & mask);
+                    if (a1 < n) b = src[a0] > src[a1] || (src[a0] == src[a1] && a0 > a1);
+                }
+                if (b) atomicAdd((unsigned long long *)bad, 1ull);
+            });
+            u64 hb = 1;
+            SWG_CUDA(cudaMemcpyAsync(&hb, bad, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+            SWG_CUDA(cudaStreamSynchronize(c->stream));
+            *a->ok = hb == 0;
+        }
+        *a->ms = total / a->reps;
+        if (a->tot) *a->tot = whole / a->reps;
     }, &a);
 }
 
@@ -1522,7 +1944,7 @@ int swg_filter_paf(swg_ctx *c, const swg_config *cfg, const char *in_path, const
         u32 *chain = c->io.take<u32>(std::max<u32>(dp.n, 1));
         if (dp.n) {
             SWG_CUDA(cudaEventRecord(c->ev[1], c->stream));
-            run_filter(c, *a->cfg, devin_of(dp), status, chain, &local);
+            run_filter_exact(c, *a->cfg, devin_of(dp), status, chain, &local, nullptr, nullptr);
             SWG_CUDA(cudaEventRecord(c->ev[2], c->stream));
             SWG_CUDA(cudaStreamSynchronize(c->stream));
             float ms = 0;

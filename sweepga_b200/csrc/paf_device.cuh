@@ -195,16 +195,17 @@ __device__ __forceinline__ void tok_store(const TokCols &L, u32 l, const TokHead
     if (r.fix || h.fix) {
         kind = TK_FIX;
         fix_list[atomicAdd((unsigned long long *)&tc[TC_NFIX], 1ull)] = l;
-    } else if (h.qs > LIM || h.qe > LIM || h.ts > LIM || h.te > LIM || h.bl > LIM || r.exact > LIM) kind = TK_ERR_RANGE;
-    else if (h.qe < h.qs || h.te < h.ts) kind = TK_ERR_ORDER;
-    else kind = TK_OK;
-    if (kind == TK_ERR_RANGE || kind == TK_ERR_ORDER) atomicMin((unsigned long long *)&tc[TC_ERRLINE], (unsigned long long)l);
+    } else kind = TK_OK;
+    // values beyond the u32 SoA / end < start: the record stays, with an impossible interval (same rule as paf_parse_line);
+    // the filter raises SWG_ERR_RANGE only if it survives the stage-1 retain
+    const bool over = h.qs > LIM || h.qe > LIM || h.ts > LIM || h.te > LIM || h.bl > LIM || r.exact > LIM;
+    auto sat = [LIM](u64 v) { return (u32)(v > LIM ? LIM : v); };
     L.kind[l] = kind;
     L.qh[l] = h.qh; L.th[l] = h.th;
     L.qlen[l] = h.qlen; L.trel[l] = h.trel; L.tlen[l] = h.tlen;
     if (kind == TK_OK) {
-        L.qs[l] = (u32)h.qs; L.qe[l] = (u32)h.qe; L.ts[l] = (u32)h.ts; L.te[l] = (u32)h.te;
-        L.blen[l] = (u32)h.bl; L.matches[l] = (u32)r.exact;
+        L.qs[l] = over ? 0xFFFFFFFFu : (u32)h.qs; L.qe[l] = over ? 0u : (u32)h.qe; L.ts[l] = sat(h.ts); L.te[l] = sat(h.te);
+        L.blen[l] = sat(h.bl); L.matches[l] = sat(r.exact);
         L.identity[l] = r.identity;
         L.strand[l] = h.plus ? '+' : '-';
     }
@@ -773,8 +774,6 @@ static void tokenize_device(swg_ctx *c, const swg_paf &hp, DevPaf &dp) {
         tok_read(c, tc, h_tc);
     }
     u64 n_ok = h_tc[TC_OK];
-    u64 err_line = h_tc[TC_ERRLINE];
-    bool err_is_order = false;
     // ---- lines the device does not decide: the host's reference-exact parser patches them -----------
     if (h_tc[TC_NFIX]) {
         const u32 nfix = (u32)h_tc[TC_NFIX];
@@ -796,10 +795,9 @@ static void tokenize_device(swg_ctx *c, const swg_paf &hp, DevPaf &dp) {
             p.line = lines[i];
             p.qs = pl.qs; p.qe = pl.qe; p.ts = pl.ts; p.te = pl.te; p.blen = pl.blen; p.matches = pl.matches;
             p.identity = pl.identity;
-            u8 kind = k == PafLine::OK ? TK_OK : k == PafLine::SKIP ? TK_SKIP : k == PafLine::ERR_RANGE ? TK_ERR_RANGE : TK_ERR_ORDER;
+            u8 kind = k == PafLine::SKIP ? TK_SKIP : TK_OK; // range / order problems ride along as impossible intervals
             p.kind_strand = (u32)kind | ((u32)pl.strand << 8);
             if (kind == TK_OK) n_ok++;
-            if ((kind == TK_ERR_RANGE || kind == TK_ERR_ORDER) && lines[i] < err_line) err_line = lines[i];
         }
         Patch *d_p = A.take<Patch>(nfix);
         SWG_CUDA(cudaMemcpyAsync(d_p, patches.data(), sizeof(Patch) * nfix, cudaMemcpyHostToDevice, st));
@@ -812,14 +810,6 @@ static void tokenize_device(swg_ctx *c, const swg_paf &hp, DevPaf &dp) {
             L.strand[l] = (u8)(p.kind_strand >> 8);
         });
         SWG_CUDA(cudaStreamSynchronize(st)); // patches lives on this stack frame
-    }
-    if (err_line != NONE64) {
-        u8 k = 0;
-        SWG_CUDA(cudaMemcpyAsync(&k, L.kind + err_line, 1, cudaMemcpyDeviceToHost, st));
-        SWG_CUDA(cudaStreamSynchronize(st));
-        err_is_order = k == TK_ERR_ORDER;
-        throw RangeError{(err_is_order ? std::string("record with end < start at line ") : std::string("coordinate / length does not fit the u32 SoA at line ")) +
-                         std::to_string(err_line)};
     }
     if (h_tc[TC_MAXLEN] > ((u64)256 << 20)) throw FrontEndFallback{"a line longer than 256 MiB"};
     c->tok_maxlen = (u32)h_tc[TC_MAXLEN];

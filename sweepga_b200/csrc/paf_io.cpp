@@ -122,16 +122,24 @@ swg::PafLine::Kind swg::paf_parse_line(const char *line, size_t len, PafLine *ou
         if (!tab) break;
         a = b + 1;
     }
+    // A value beyond the u32 SoA, or end < start, does not reject the file here: the reference parses u64 and lets such a
+    // record through to its stage-1 retain (paf_filter.rs:384-388), so the record is kept with an impossible interval
+    // (query_start = 2^32 - 1 > query_end = 0 when a value had to be saturated; the original values when only the order is
+    // wrong) and the filter raises SWG_ERR_RANGE only if it survives that retain (k_prefilter).  identity uses the exact u64s.
     const uint64_t LIM = 0xFFFFFFFFull;
-    if (qs > LIM || qe > LIM || ts > LIM || te > LIM || bl > LIM || exact > LIM) return PafLine::ERR_RANGE;
-    if (qe < qs || te < ts) return PafLine::ERR_ORDER;
+    PafLine::Kind kind = PafLine::OK;
+    if (qs > LIM || qe > LIM || ts > LIM || te > LIM || bl > LIM || exact > LIM) {
+        kind = PafLine::ERR_RANGE;
+        qs = LIM; qe = 0;
+        ts = ts > LIM ? LIM : ts; te = te > LIM ? LIM : te; bl = bl > LIM ? LIM : bl; exact = exact > LIM ? LIM : exact;
+    } else if (qe < qs || te < ts) kind = PafLine::ERR_ORDER;
     out->qname = fs[0]; out->qname_len = fl[0];
     out->tname = fs[5]; out->tname_len = fl[5];
     out->qs = (uint32_t)qs; out->qe = (uint32_t)qe; out->ts = (uint32_t)ts; out->te = (uint32_t)te;
     out->blen = (uint32_t)bl; out->matches = (uint32_t)exact;
     out->identity = identity;
     out->strand = (fl[4] == 1 && fs[4][0] == '+') ? '+' : '-';
-    return PafLine::OK;
+    return kind;
 }
 
 bool swg::paf_ani_line(const char *line, size_t len, AniLine *out) {
@@ -289,11 +297,7 @@ static void parse_chunk(const char *text, Chunk &c) {
         uint64_t this_ln = ln++;
         size_t next = nl ? eol + 1 : c.end;
         const swg::PafLine::Kind kind = swg::paf_parse_line(text + pos, len, &L);
-        if (kind == swg::PafLine::ERR_RANGE) {
-            if (c.error.empty()) c.error = "coordinate / length does not fit the u32 SoA at chunk line " + std::to_string(this_ln);
-        } else if (kind == swg::PafLine::ERR_ORDER) {
-            if (c.error.empty()) c.error = "record with end < start at chunk line " + std::to_string(this_ln);
-        } else if (kind == swg::PafLine::OK) {
+        if (kind != swg::PafLine::SKIP) { // ERR_RANGE / ERR_ORDER lines are records with an impossible interval (see paf_parse_line)
             uint32_t q = intern(L.qname, L.qname_len, last_q, last_qid, have_q);
             uint32_t t = intern(L.tname, L.tname_len, last_t, last_tid, have_t);
             c.rank_local.push_back(this_ln);
@@ -643,18 +647,26 @@ int swg_shard_plan(const swg_mappings *m, int n_shards, uint32_t *shard_of, uint
         unit_size[u]++;
         unit_of[i] = u;
     }
-    std::vector<uint32_t> order(unit_size.size());
-    for (uint32_t u = 0; u < order.size(); u++) order[u] = u;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return unit_size[a] > unit_size[b]; });
-    std::vector<uint64_t> load(n_shards, 0);
     std::vector<uint32_t> unit_shard(unit_size.size());
+    const int rc = swg_shard_plan_units(unit_size.size(), unit_size.data(), n_shards, unit_shard.data(), shard_sizes);
+    if (rc != SWG_OK) return rc;
+    for (uint64_t i = 0; i < m->n; i++) shard_of[i] = unit_shard[unit_of[i]];
+    return SWG_OK;
+}
+
+// LPT: largest unit first (ties by unit index), onto the least loaded shard (ties by the lowest shard)
+int swg_shard_plan_units(uint64_t n_units, const uint64_t *unit_sizes, int n_shards, uint32_t *shard_of_unit, uint64_t *shard_sizes) {
+    if (n_shards < 1 || (n_units && (!unit_sizes || !shard_of_unit))) return SWG_ERR_ARG;
+    std::vector<uint32_t> order(n_units);
+    for (uint32_t u = 0; u < order.size(); u++) order[u] = u;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return unit_sizes[a] > unit_sizes[b]; });
+    std::vector<uint64_t> load(n_shards, 0);
     for (uint32_t u : order) {
         int best = 0;
         for (int s = 1; s < n_shards; s++) if (load[s] < load[best]) best = s;
-        unit_shard[u] = (uint32_t)best;
-        load[best] += unit_size[u];
+        shard_of_unit[u] = (uint32_t)best;
+        load[best] += unit_sizes[u];
     }
-    for (uint64_t i = 0; i < m->n; i++) shard_of[i] = unit_shard[unit_of[i]];
     if (shard_sizes) for (int s = 0; s < n_shards; s++) shard_sizes[s] = load[s];
     return SWG_OK;
 }

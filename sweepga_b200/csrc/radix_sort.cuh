@@ -105,19 +105,35 @@ __global__ void rs_scan_hist_kernel(u32 *__restrict__ hist) {
 }
 
 // ---- one pass ---------------------------------------------------------------------------
-struct RsSmem {
+// Three formats of one element:
+//   RS_PAIRS   (u64 key, u32 payload) in, the same out                       12 B read + 12 B written
+//   RS_PACK    (u64 key, u32 payload) in, ONE u64 out                        12 B read +  8 B written
+//   RS_PACKED  one u64 in, one u64 out                                        8 B read +  8 B written
+// An LSD sort never looks at a digit again once its pass is done, and the callers of the packed sort read the payload and
+// the HIGH key bits of the result only (group id; positions are re-gathered from the records).  So as soon as the key
+// bits still to be sorted plus the payload bits fit one word — packed = ((key >> c0) << ib) | payload after c0 low key
+// bits have been consumed — the remaining passes move 8 B per element instead of 12 B.  RS_PACK is the pass that consumes
+// key bits [c0 - 8, c0) and writes the packed word (its own digit is gone from the word, so the digit is staged as a byte).
+enum { RS_PAIRS = 0, RS_PACK = 1, RS_PACKED = 2 };
+
+template <int MODE> struct RsSmemT {
     u32 warp_hist[RS_WARPS][RS_RADIX]; // 16 KB: per-warp digit counts, later exclusive-over-warps offsets
     u64 stage_k[RS_TILE];              // 48 KB
-    u32 stage_v[RS_TILE];              // 24 KB
+    u32 stage_v[MODE == RS_PAIRS ? RS_TILE : 1]; // 24 KB (pairs only)
+    u8 stage_d[MODE == RS_PACK ? RS_TILE : 4];  // the digit of the pass that packs
     u32 digit_excl[RS_RADIX];          // tile-local exclusive digit offsets
     u32 global_base[RS_RADIX];         // global output index of staged position 0 of each digit run
     u32 wsum[RS_WARPS];
     u32 tile;
 };
+typedef RsSmemT<RS_PAIRS> RsSmem;
 
-template <bool FULL>
-__device__ __forceinline__ void rs_onesweep_tile(RsSmem &s, const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out,
+// shift: bit position of this pass's digit in the INPUT word (RS_PACKED: inside the packed word).
+// RS_PACK: pack_drop = c0 (low key bits dropped), pack_ib = payload bits.
+template <bool FULL, int MODE>
+__device__ __forceinline__ void rs_onesweep_tile(RsSmemT<MODE> &s, const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out,
                                                  const u32 *__restrict__ vals_in, u32 *__restrict__ vals_out, u32 n, int shift,
+                                                 int pack_drop, int pack_ib,
                                                  const u32 *__restrict__ digit_base, u32 *tile_status, u32 tile) {
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u64 tile_base = (u64)tile * RS_TILE;
@@ -125,7 +141,7 @@ __device__ __forceinline__ void rs_onesweep_tile(RsSmem &s, const u64 *__restric
     const u32 warp_n = FULL ? 32 * RS_ITEMS : (u32)min((u64)(32 * RS_ITEMS), n > warp_base ? (u64)n - warp_base : (u64)0);
 
     u64 key[RS_ITEMS];
-    u32 val[RS_ITEMS];
+    u32 val[MODE == RS_PACKED ? 1 : RS_ITEMS];
     u32 rnk[RS_ITEMS];
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
@@ -133,7 +149,7 @@ __device__ __forceinline__ void rs_onesweep_tile(RsSmem &s, const u64 *__restric
         key[i] = ok ? keys_in[warp_base + i * 32 + lane] : NONE64;
     }
     // warp-level multi-split ranking (stable: items ascending, lanes ascending).
-    // pass A: all the match_any's back to back (independent); pass B: the sequential warp-histogram update.
+    // pass A: all the peer masks back to back (independent); pass B: the sequential warp-histogram update.
     const u32 lt = lanemask_lt();
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
@@ -167,10 +183,12 @@ __device__ __forceinline__ void rs_onesweep_tile(RsSmem &s, const u64 *__restric
         __syncwarp();
     }
     // payloads are only needed for staging: issue their loads now so the latency hides behind the scans/barriers
+    if (MODE != RS_PACKED) {
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; i++) {
-        const bool ok = FULL || (u32)(i * 32 + lane) < warp_n;
-        val[i] = ok ? vals_in[warp_base + i * 32 + lane] : 0u;
+        for (int i = 0; i < RS_ITEMS; i++) {
+            const bool ok = FULL || (u32)(i * 32 + lane) < warp_n;
+            val[MODE == RS_PACKED ? 0 : i] = ok ? vals_in[warp_base + i * 32 + lane] : 0u;
+        }
     }
     __syncthreads();
 
@@ -212,8 +230,15 @@ __device__ __forceinline__ void rs_onesweep_tile(RsSmem &s, const u64 *__restric
         if (ok) {
             u32 d = (u32)(key[i] >> shift) & (RS_RADIX - 1);
             u32 pos = s.digit_excl[d] + s.warp_hist[warp][d] + rnk[i];
-            s.stage_k[pos] = key[i];
-            s.stage_v[pos] = val[i];
+            if (MODE == RS_PAIRS) {
+                s.stage_k[pos] = key[i];
+                s.stage_v[pos] = val[MODE == RS_PACKED ? 0 : i];
+            } else if (MODE == RS_PACK) {
+                s.stage_k[pos] = ((key[i] >> pack_drop) << pack_ib) | (u64)val[MODE == RS_PACKED ? 0 : i];
+                s.stage_d[pos] = (u8)d;
+            } else {
+                s.stage_k[pos] = key[i];
+            }
         }
     }
 
@@ -247,20 +272,18 @@ __device__ __forceinline__ void rs_onesweep_tile(RsSmem &s, const u64 *__restric
         for (int it = 0; it < RS_ITEMS; it++) {
             const u32 j = it * RS_THREADS + tid;
             const u64 k = s.stage_k[j];
-#ifdef SWG_RS_DEBUG_LINEAR_OUT
-            const u32 g = (u32)tile_base + j + (s.global_base[(u32)(k >> shift) & (RS_RADIX - 1)] & 0); // timing experiment only
-#else
-            const u32 g = s.global_base[(u32)(k >> shift) & (RS_RADIX - 1)] + j;
-#endif
+            const u32 d = MODE == RS_PACK ? (u32)s.stage_d[MODE == RS_PACK ? j : 0] : ((u32)(k >> shift) & (RS_RADIX - 1));
+            const u32 g = s.global_base[d] + j;
             keys_out[g] = k;
-            vals_out[g] = s.stage_v[j];
+            if (MODE == RS_PAIRS) vals_out[g] = s.stage_v[MODE == RS_PAIRS ? j : 0];
         }
     } else {
         for (u32 j = tid; j < tile_n; j += RS_THREADS) {
             const u64 k = s.stage_k[j];
-            const u32 g = s.global_base[(u32)(k >> shift) & (RS_RADIX - 1)] + j;
+            const u32 d = MODE == RS_PACK ? (u32)s.stage_d[MODE == RS_PACK ? j : 0] : ((u32)(k >> shift) & (RS_RADIX - 1));
+            const u32 g = s.global_base[d] + j;
             keys_out[g] = k;
-            vals_out[g] = s.stage_v[j];
+            if (MODE == RS_PAIRS) vals_out[g] = s.stage_v[MODE == RS_PAIRS ? j : 0];
         }
     }
 }
@@ -268,22 +291,36 @@ __device__ __forceinline__ void rs_onesweep_tile(RsSmem &s, const u64 *__restric
 #ifndef SWG_RS_MINBLOCKS
 #define SWG_RS_MINBLOCKS 2
 #endif
-__global__ void __launch_bounds__(RS_THREADS, SWG_RS_MINBLOCKS)
+#ifndef SWG_RS_MINBLOCKS_PACKED
+#define SWG_RS_MINBLOCKS_PACKED 2
+#endif
+template <int MODE>
+__global__ void __launch_bounds__(RS_THREADS, MODE == RS_PACKED ? SWG_RS_MINBLOCKS_PACKED : SWG_RS_MINBLOCKS)
 rs_onesweep_kernel(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out, const u32 *__restrict__ vals_in,
-                   u32 *__restrict__ vals_out, u32 n, int shift, const u32 *__restrict__ digit_base,
+                   u32 *__restrict__ vals_out, u32 n, int shift, int pack_drop, int pack_ib, const u32 *__restrict__ digit_base,
                    u32 *tile_status /*[tiles][256]*/, u32 *tile_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    RsSmem &s = *reinterpret_cast<RsSmem *>(smem_raw);
+    RsSmemT<MODE> &s = *reinterpret_cast<RsSmemT<MODE> *>(smem_raw);
     const u32 tid = threadIdx.x;
     if (tid == 0) s.tile = atomicAdd(tile_counter, 1u); // in-order tile ids: look-back never waits on an unscheduled tile
     for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&s.warp_hist[0][0])[i] = 0;
     __syncthreads();
     const u32 tile = s.tile;
-    if ((u64)(tile + 1) * RS_TILE <= (u64)n) rs_onesweep_tile<true>(s, keys_in, keys_out, vals_in, vals_out, n, shift, digit_base, tile_status, tile);
-    else rs_onesweep_tile<false>(s, keys_in, keys_out, vals_in, vals_out, n, shift, digit_base, tile_status, tile);
+    if ((u64)(tile + 1) * RS_TILE <= (u64)n)
+        rs_onesweep_tile<true, MODE>(s, keys_in, keys_out, vals_in, vals_out, n, shift, pack_drop, pack_ib, digit_base, tile_status, tile);
+    else
+        rs_onesweep_tile<false, MODE>(s, keys_in, keys_out, vals_in, vals_out, n, shift, pack_drop, pack_ib, digit_base, tile_status, tile);
 }
 
 // ---- host driver --------------------------------------------------------------------------
+// The one-sweep tile needs more dynamic shared memory than the 48 KB default; the opt-in is a per-DEVICE function
+// attribute, so every context sets it for its own device (swg_create, after cudaSetDevice).
+static inline void rs_init_device() {
+    SWG_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<RS_PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmemT<RS_PAIRS>)));
+    SWG_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<RS_PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmemT<RS_PACK>)));
+    SWG_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<RS_PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmemT<RS_PACKED>)));
+}
+
 struct RadixSortPlan {
     u32 n = 0;
     int begin_bit = 0, passes = 0;
@@ -314,26 +351,86 @@ static inline void rs_sort_pairs(const RadixSortPlan &p, u64 *&keys, u64 *&keys_
     u32 *counters = hist + RS_MAX_PASSES * RS_RADIX;
     u32 *status = counters + 16;
     SWG_CUDA(cudaMemsetAsync(temp, 0, p.temp_bytes, st));
-    static bool attr_set = false;
-    if (!attr_set) {
-        SWG_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
-        attr_set = true;
-    }
     u32 hgrid = (u32)min((u64)sm_count * 4, (u64)cdiv(p.n / 2 + 1, 512));
     rs_histogram_kernel<<<hgrid, 512, 0, st>>>(keys, p.n, p.begin_bit, p.passes, hist);
     rs_scan_hist_kernel<<<p.passes, RS_RADIX, 0, st>>>(hist);
     lc.n += 2;
     if (ev_begin) SWG_CUDA(cudaEventRecord(ev_begin, st));
     for (int pass = 0; pass < p.passes; pass++) {
-        rs_onesweep_kernel<<<p.tiles, RS_THREADS, sizeof(RsSmem), st>>>(keys, keys_alt, vals, vals_alt, p.n,
-                                                                        p.begin_bit + pass * RS_BITS, hist + pass * RS_RADIX,
-                                                                        status + (size_t)pass * p.tiles * RS_RADIX, counters + pass);
+        rs_onesweep_kernel<RS_PAIRS><<<p.tiles, RS_THREADS, sizeof(RsSmem), st>>>(keys, keys_alt, vals, vals_alt, p.n,
+                                                                                  p.begin_bit + pass * RS_BITS, 0, 0, hist + pass * RS_RADIX,
+                                                                                  status + (size_t)pass * p.tiles * RS_RADIX, counters + pass);
         lc.n += 1;
         u64 *tk = keys; keys = keys_alt; keys_alt = tk;
         u32 *tv = vals; vals = vals_alt; vals_alt = tv;
     }
     if (ev_end) SWG_CUDA(cudaEventRecord(ev_end, st));
     SWG_CUDA(cudaGetLastError());
+}
+
+// ---- packed sort ---------------------------------------------------------------------------
+// Sort (key, payload) pairs by key bits [0, key_bits) (begin bit 0) where the caller only needs, of the result, the payload
+// and the key bits from `c0` upwards: returns ONE array of words ((key >> c0) << ib) | payload in sorted order.
+// c0 = the smallest multiple of the digit width with key_bits - c0 + ib <= 64 (0: the words are packed by the first pass).
+struct PackedSort {
+    const u64 *packed = nullptr; // sorted words
+    int c0 = 0, ib = 0;          // payload = word & ((1 << ib) - 1); key >> c0 = word >> ib
+    int passes = 0, pack_pass = -1;
+    int timed_passes = 0, timed_bytes_per_pair = 16; // what [ev_begin, ev_end] bracket: the packed-word passes (all passes if there is none)
+};
+static inline int rs_packed_c0(int key_bits, int ib) {
+    int c0 = 0;
+    while (key_bits - c0 + ib > 64) c0 += RS_BITS;
+    return c0;
+}
+// keys/keys_alt: n u64 each; vals/vals_alt: n u32 each (vals_alt is unused when the first pass packs).  Needs
+// payload < 2^ib and key_bits <= RS_MAX_PASSES * RS_BITS.  ev[2k], ev[2k+1] (optional): events around pass k.
+static inline PackedSort rs_sort_packed(u32 n, int key_bits, int ib, u64 *keys, u64 *keys_alt, u32 *vals, u32 *vals_alt, void *temp,
+                                        const RadixSortPlan &p, cudaStream_t st, int sm_count, LaunchCounter &lc,
+                                        cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_end = nullptr) {
+    PackedSort r;
+    r.ib = ib;
+    r.c0 = rs_packed_c0(key_bits, ib);
+    r.passes = p.passes;
+    if (n == 0) return r;
+    u32 *hist = (u32 *)temp;
+    u32 *counters = hist + RS_MAX_PASSES * RS_RADIX;
+    u32 *status = counters + 16;
+    SWG_CUDA(cudaMemsetAsync(temp, 0, p.temp_bytes, st));
+    u32 hgrid = (u32)min((u64)sm_count * 4, (u64)cdiv(p.n / 2 + 1, 512));
+    rs_histogram_kernel<<<hgrid, 512, 0, st>>>(keys, p.n, 0, p.passes, hist);
+    rs_scan_hist_kernel<<<p.passes, RS_RADIX, 0, st>>>(hist);
+    lc.n += 2;
+    // passes [0, pk) move pairs, pass pk packs, the rest move packed words.  c0 == 0: a pass "-1" would pack, so the first
+    // pass packs without dropping anything and keeps its own digit in the word (read back from it at write-out: RS_PACK
+    // stages the digit byte either way).
+    const int pk = r.c0 == 0 ? 0 : r.c0 / RS_BITS - 1;
+    r.pack_pass = pk;
+    r.timed_passes = p.passes - pk - 1;
+    if (r.timed_passes <= 0) { r.timed_passes = p.passes; r.timed_bytes_per_pair = pk == 0 ? 20 : 24; }
+    const int first_timed = r.timed_passes == p.passes ? 0 : pk + 1;
+    for (int pass = 0; pass < p.passes; pass++) {
+        if (pass == first_timed && ev_begin) SWG_CUDA(cudaEventRecord(ev_begin, st));
+        const u32 *db = hist + pass * RS_RADIX;
+        u32 *stt = status + (size_t)pass * p.tiles * RS_RADIX;
+        if (pass < pk) {
+            rs_onesweep_kernel<RS_PAIRS><<<p.tiles, RS_THREADS, sizeof(RsSmemT<RS_PAIRS>), st>>>(keys, keys_alt, vals, vals_alt, n, pass * RS_BITS, 0, 0,
+                                                                                              db, stt, counters + pass);
+            u32 *tv = vals; vals = vals_alt; vals_alt = tv;
+        } else if (pass == pk) {
+            rs_onesweep_kernel<RS_PACK><<<p.tiles, RS_THREADS, sizeof(RsSmemT<RS_PACK>), st>>>(keys, keys_alt, vals, nullptr, n, pass * RS_BITS, r.c0, ib,
+                                                                                            db, stt, counters + pass);
+        } else {
+            rs_onesweep_kernel<RS_PACKED><<<p.tiles, RS_THREADS, sizeof(RsSmemT<RS_PACKED>), st>>>(keys, keys_alt, nullptr, nullptr, n,
+                                                                                                ib + pass * RS_BITS - r.c0, 0, 0, db, stt, counters + pass);
+        }
+        lc.n += 1;
+        u64 *tk = keys; keys = keys_alt; keys_alt = tk;
+    }
+    if (ev_end) SWG_CUDA(cudaEventRecord(ev_end, st));
+    SWG_CUDA(cudaGetLastError());
+    r.packed = keys;
+    return r;
 }
 
 } // namespace swg

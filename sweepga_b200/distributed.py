@@ -83,3 +83,43 @@ def gpu_local_filter(ctx):
         ka, kb = ctx.last_chain_keys()
         return st, ch, ka, kb
     return f
+
+
+# ---- the cheaper merge: (A, count) per genome-pair unit instead of two keys per chain --------------------------------
+def chain_runs(key_a):
+    """Runs of equal A in a shard's chain order -> (A per run, first local chain number per run (1-based), run lengths).
+    What swg_last_chain_units reports, from the per-chain keys (for fallbacks and tests)."""
+    key_a = np.asarray(key_a)
+    if len(key_a) == 0:
+        z = np.zeros(0, np.int64)
+        return z, z, z
+    first = np.nonzero(np.concatenate(([True], key_a[1:] != key_a[:-1])))[0]
+    return key_a[first].astype(np.int64), (first + 1).astype(np.int64), np.diff(np.concatenate((first, [len(key_a)]))).astype(np.int64)
+
+
+def unit_offsets(all_runs):
+    """all_runs[s] = (A_global per run, run length per run) of shard s, each in that shard's chain order.
+    Returns delta[s][r] = (global number of the run's first chain) - (its local number): the kept chains of one
+    genome-pair unit are consecutive in the local and in the merged numbering (order O3 sorts by A first), so a shard's
+    chain k of run r becomes k + delta[s][r]."""
+    a = np.concatenate([np.asarray(r[0], np.int64) for r in all_runs]) if all_runs else np.zeros(0, np.int64)
+    n = np.concatenate([np.asarray(r[1], np.int64) for r in all_runs]) if all_runs else np.zeros(0, np.int64)
+    order = np.argsort(a, kind="stable")
+    excl = np.zeros(len(a), np.int64)
+    excl[order] = np.cumsum(n[order]) - n[order]
+    out, off = [], 0
+    for r in all_runs:
+        k = len(r[0])
+        local_first = np.cumsum(np.asarray(r[1], np.int64)) - np.asarray(r[1], np.int64)  # 0-based
+        out.append(excl[off:off + k] - local_first)
+        off += k
+    return out
+
+
+def gather_runs(dist, a_global, counts, world, device=None, group=None):
+    """all_gather of every rank's (A_global, count) runs -> list over ranks (tiny: one pair per genome-pair unit)."""
+    import torch
+    dev = device or torch.device("cpu")
+    t = torch.from_numpy(np.stack([np.asarray(a_global, np.int64), np.asarray(counts, np.int64)], axis=1).reshape(-1)).to(dev)
+    parts = _pad_gather(dist, t, world, group)
+    return [(p.cpu().numpy().reshape(-1, 2)[:, 0], p.cpu().numpy().reshape(-1, 2)[:, 1]) for p in parts]

@@ -1,6 +1,9 @@
 """ctypes binding of oracle/liboracle.so — the CPU restatement of the reference filter.
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs.
+It does NOT import the product package: the two POD layouts it needs (swg_config, swg_stats of
+include/sweepga_b200.h) are declared here, so that a process that only runs the oracle (bench.py --impl reference)
+never maps libsweepga_b200.so.  tests/test_host.py checks the two declarations against the product binding's.
 """
 import ctypes as C
 import os
@@ -11,12 +14,56 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _PATH = os.path.join(ROOT, "oracle", "liboracle.so")
 _lib = C.CDLL(_PATH)
 
-from sweepga_b200._lib import swg_config, swg_stats  # POD layouts only
+NO_LIMIT = (1 << 64) - 1
+
+
+class swg_config(C.Structure):  # include/sweepga_b200.h: swg_config
+    _fields_ = [
+        ("min_block_length", C.c_uint64), ("mapping_max_per_query", C.c_uint64), ("mapping_max_per_target", C.c_uint64),
+        ("scaffold_max_per_query", C.c_uint64), ("scaffold_max_per_target", C.c_uint64), ("scaffold_gap", C.c_uint64),
+        ("min_scaffold_length", C.c_uint64), ("scaffold_max_deviation", C.c_uint64),
+        ("overlap_threshold", C.c_double), ("scaffold_overlap_threshold", C.c_double),
+        ("min_identity", C.c_double), ("min_scaffold_identity", C.c_double),
+        ("mapping_filter_mode", C.c_uint8), ("scaffold_filter_mode", C.c_uint8), ("scoring_function", C.c_uint8),
+        ("keep_self", C.c_uint8), ("scaffolds_only", C.c_uint8), ("reserved", C.c_uint8 * 3),
+    ]
+
+
+class swg_stats(C.Structure):  # include/sweepga_b200.h: swg_stats
+    _fields_ = [
+        ("n_input", C.c_uint64), ("n_stage1", C.c_uint64), ("n_after_sweep", C.c_uint64), ("n_chains", C.c_uint64),
+        ("n_chains_after_mass", C.c_uint64), ("n_chains_kept", C.c_uint64), ("n_anchors", C.c_uint64),
+        ("n_rescued", C.c_uint64), ("n_kept", C.c_uint64), ("score_near_ties", C.c_uint64), ("gpu_launches", C.c_uint64),
+        ("ms_h2d", C.c_double), ("ms_device", C.c_double), ("ms_d2h", C.c_double),
+        ("ms_sort_passes", C.c_double), ("n_sort_passes", C.c_uint64), ("n_sort_pairs", C.c_uint64),
+        ("ms_tokenize", C.c_double), ("ms_write", C.c_double), ("exact_rerank", C.c_uint64), ("sort_bytes_per_pair", C.c_uint64),
+        ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("reserved", C.c_uint64 * 4),
+    ]
+
+
+class Config:
+    """Stand-alone config for oracle-only processes: CLI defaults (src/cli.rs:204-276) unless overridden by keyword
+    (field names of swg_config; None = no limit)."""
+
+    def __init__(self, **kw):
+        c = swg_config()
+        c.mapping_max_per_query = c.mapping_max_per_target = c.scaffold_max_per_query = c.scaffold_max_per_target = NO_LIMIT
+        c.scaffold_gap, c.min_scaffold_length, c.scaffold_max_deviation = 50_000, 10_000, 0
+        c.overlap_threshold, c.scaffold_overlap_threshold = 0.95, 0.5
+        c.mapping_filter_mode = c.scaffold_filter_mode = 2
+        c.scoring_function = 3
+        for k, v in kw.items():
+            setattr(c, k, NO_LIMIT if v is None else v)
+        self._c = c
+
+    def to_c(self):
+        return self._c
+
 
 u8p, u32p, u64p, f64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_double)
 _lib.orc_apply_filters.restype = C.c_int
-_lib.orc_apply_filters.argtypes = [C.POINTER(swg_config), C.c_uint64, u32p, u32p, u64p, u64p, u64p, u64p, u64p, u64p, f64p, u8p,
-                                   u32p, u32p, u8p, u32p, C.POINTER(swg_stats), u32p, u32p]
+_lib.orc_apply_filters.argtypes = [C.c_void_p, C.c_uint64, u32p, u32p, u64p, u64p, u64p, u64p, u64p, u64p, f64p, u8p,
+                                   u32p, u32p, u8p, u32p, C.c_void_p, u32p, u32p]
 _lib.orc_plane_sweep.restype = C.c_int
 _lib.orc_plane_sweep.argtypes = [C.c_int, C.c_uint64, u64p, u64p, u64p, u64p, f64p, C.c_uint64, C.c_uint64, C.c_double, C.c_int, u8p]
 _lib.orc_score.restype = C.c_double
@@ -42,7 +89,7 @@ _lib.orc_paf_strand.argtypes = [C.c_void_p]
 _lib.orc_paf_write.restype = C.c_int
 _lib.orc_paf_write.argtypes = [C.c_void_p, C.c_char_p, u8p, u32p]
 _lib.orc_filter_paf.restype = C.c_int
-_lib.orc_filter_paf.argtypes = [C.POINTER(swg_config), C.c_char_p, C.c_char_p, C.POINTER(swg_stats)]
+_lib.orc_filter_paf.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p]
 
 USIZE_MAX = (1 << 64) - 1
 
@@ -86,6 +133,29 @@ def plane_sweep(axis, mappings, n_keep, thr, scoring=3, n_keep2=None):
 
 def score(qs, qe, identity, scoring=3):
     return _lib.orc_score(qs, qe, identity, scoring)
+
+
+_lib.orc_score_column.restype = None
+_lib.orc_score_column.argtypes = [C.c_uint64, u32p, u32p, f64p, C.c_int, f64p]
+_lib.orc_chain_identity.restype = None
+_lib.orc_chain_identity.argtypes = [C.c_uint64, u64p, u64p, u64p, f64p]
+
+
+def score_column(qs, qe, identity, scoring=3):
+    """score_with_function over columns (host libm)."""
+    qs, qe = np.ascontiguousarray(qs, np.uint32), np.ascontiguousarray(qe, np.uint32)
+    identity = np.ascontiguousarray(identity, np.float64)
+    out = np.empty(len(qs), np.float64)
+    _lib.orc_score_column(len(qs), _p(qs, C.c_uint32), _p(qe, C.c_uint32), _p(identity, C.c_double), scoring, _p(out, C.c_double))
+    return out
+
+
+def chain_identity(total_length, sum_block, sum_matches):
+    """weighted_identity (paf_filter.rs:896-913) over columns (host libm)."""
+    a = [np.ascontiguousarray(x, np.uint64) for x in (total_length, sum_block, sum_matches)]
+    out = np.empty(len(a[0]), np.float64)
+    _lib.orc_chain_identity(len(a[0]), *[_p(x, C.c_uint64) for x in a], _p(out, C.c_double))
+    return out
 
 
 def plane_sweep_core(intervals, max_keep, thr):

@@ -34,10 +34,34 @@ def test_library_exports_every_declared_symbol():
     assert declared <= bound, f"not bound in _lib.py: {sorted(declared - bound)}"
 
 
+def _header_layout(structs):
+    """sizeof / offsetof of every field of the given structs of include/sweepga_b200.h, as gcc lays them out."""
+    import subprocess
+    import tempfile
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "sweepga_b200.h"', 'int main(void) {']
+    for name, fields in structs.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for f in fields:
+            lines.append(f'  printf("{name}.{f} %zu\\n", offsetof({name}, {f}));')
+    lines += ['  return 0;', '}']
+    with tempfile.TemporaryDirectory() as d:
+        src, exe = os.path.join(d, "l.c"), os.path.join(d, "l")
+        open(src, "w").write("\n".join(lines))
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
+        out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    return {k: int(v) for k, v in (l.split() for l in out.splitlines())}
+
+
 def test_struct_layouts_match_header():
-    assert C.sizeof(_lib.swg_config) == 8 * 8 + 4 * 8 + 8
-    assert C.sizeof(_lib.swg_stats) == 11 * 8 + 3 * 8 + 3 * 8 + 2 * 8
-    assert C.sizeof(_lib.swg_mappings) == 8 + 10 * 8 + 8 + 8 + 8 + 8  # n, 10 ptr, score, n_seq(+pad), 2 ptr
+    """Every ctypes mirror (the product binding's and the oracle binding's own copies) has the header's size and offsets."""
+    mirrors = {"swg_config": [_lib.swg_config, oracle_lib.swg_config], "swg_stats": [_lib.swg_stats, oracle_lib.swg_stats],
+               "swg_mappings": [_lib.swg_mappings], "swg_result": [_lib.swg_result]}
+    want = _header_layout({name: [f for f, _ in cls[0]._fields_] for name, cls in mirrors.items()})
+    for name, classes in mirrors.items():
+        for cls in classes:
+            assert C.sizeof(cls) == want[name], (name, cls)
+            for f, _ in cls._fields_:
+                assert getattr(cls, f).offset == want[f"{name}.{f}"], (name, f, cls)
 
 
 def test_config_default_matches_cli_defaults():
@@ -135,10 +159,19 @@ def test_paf_gz_and_bgz_inputs(tmp_path):
 
 
 def test_paf_range_error(tmp_path):
+    """A value beyond the u32 table (or end < start) does not reject the file at parse time: the record is kept with an
+    impossible interval (query_start = 2^32 - 1 > query_end = 0) so that the filter can drop it in the stage-1 retain like
+    the reference would (paf_filter.rs:384-388), and fails only if it survives (tests/test_parity_gpu.py)."""
     p = tmp_path / "big.paf"
-    p.write_text("a\t1\t0\t5000000000\t+\tb\t1\t0\t10\t5\t10\t60\n")
-    with pytest.raises(swg.SwgError):
-        swg.parse_paf(str(p))
+    p.write_text("a\t1\t0\t5000000000\t+\tb\t1\t0\t10\t5\t10\t60\n"
+                 "a\t1\t500\t200\t+\tb\t1\t0\t10\t5\t10\t60\n"
+                 "a\t1\t0\t100\t+\tb\t1\t0\t10\t5\t10\t60\n")
+    t = swg.parse_paf(str(p))
+    assert t.n == 3
+    assert (int(t.query_start[0]), int(t.query_end[0])) == (0xFFFFFFFF, 0)  # beyond u32: marked
+    assert (int(t.query_start[1]), int(t.query_end[1])) == (500, 200)       # end < start: passed through
+    assert (int(t.query_start[2]), int(t.query_end[2])) == (0, 100)
+    assert t.identity[0] == 0.5
     with pytest.raises(swg.SwgError):
         swg.parse_paf(str(tmp_path / "missing.paf"))
 

@@ -254,9 +254,34 @@ def test_range_errors(ctx):
     with pytest.raises(swg.SwgError) as e:
         ctx.filter(swg.FilterConfig(), t)
     assert e.value.code == -2
+    # ... but only if the record survives the stage-1 retain (the reference, u64 and unchecked, drops it there too)
+    for flags in (dict(min_aln_length="1k"), dict(min_aln_identity="0.95")):
+        status, chain, _ = ctx.filter(swg.FilterConfig.from_cli(**flags), t)
+        assert status.tolist() == [0] and chain.tolist() == [0]
     t = swg.MappingTable(z(0), z(7), z(10), z(500), z(10), z(500), z(490), z(480), np.array([0.9]), np.array([43], np.uint8), P, P2)
     with pytest.raises(swg.SwgError):
         ctx.filter(swg.FilterConfig(), t)
+
+
+def test_range_marked_records_through_the_file_front_ends(ctx, tmp_path):
+    """A PAF line beyond the u32 table or with end < start is an error only if it passes the retain."""
+    good = "q#1#c\t9000\t0\t5000\t+\tt#1#c\t9000\t0\t5000\t4900\t5000\t60\n" * 2
+    bad = ("q#1#c\t1\t0\t5000000000\t+\tt#1#c\t1\t0\t10\t5\t10\t60\n"      # beyond u32, block length 10
+           "q#1#c\t1\t500\t200\t+\tt#1#c\t1\t0\t10\t5\t10\t60\n")           # end < start, block length 10
+    src, out, ref = tmp_path / "in.paf", tmp_path / "out.paf", tmp_path / "ref.paf"
+    src.write_text(good + bad + good)
+    f = swg.PafFilter(swg.FilterConfig.from_cli(min_aln_length="1k", scaffold_jump="0"))
+    f._ctx = ctx
+    for host in (False, True):
+        f.filter_paf(str(src), str(out), host_frontend=host)
+        oracle_lib.filter_paf(f.config, str(src), str(ref))
+        assert out.read_bytes() == ref.read_bytes() and out.read_bytes().count(b"\n") == 4
+    f2 = swg.PafFilter(swg.FilterConfig.from_cli(scaffold_jump="0"))
+    f2._ctx = ctx
+    for host in (False, True):
+        with pytest.raises(swg.SwgError) as e:
+            f2.filter_paf(str(src), str(out), host_frontend=host)
+        assert e.value.code == -2
 
 
 def test_paf_front_end_matches_oracle(ctx, tmp_path):

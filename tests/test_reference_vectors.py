@@ -517,6 +517,155 @@ def test_overlap_penalty(eng, tmp_path):  # tests/test_chaining_stability.rs:248
 
 
 # ---------------------------------------------------------------------------------------------
+# tests/test_chain_monotonicity.rs:128-345 (CLI runs on synthetic PAFs; flags -> FilterConfig.from_cli)
+# ---------------------------------------------------------------------------------------------
+def _cg_row(qs, ident_pm, qlen=100000, strand="+", ts=None, ln=1000, name_q="query", name_t="target"):
+    m = ln * ident_pm // 1000
+    ts = qs if ts is None else ts
+    return (name_q, qlen, qs, qs + ln, strand, name_t, qlen, ts, ts + ln, m, ln, 60, f"NM:i:{ln - m}", f"cg:Z:{m}={ln - m}X")
+
+
+def test_simple_collinear_chaining(eng, tmp_path):  # tests/test_chain_monotonicity.rs:128-164 (PAF :19-37)
+    text = paf(*[_cg_row(qs, 950) for qs in (0, 2000, 8000, 20000, 50000)])
+    for gap in (2_000, 10_000, 30_000, 100_000):
+        out = run_paf(eng, tmp_path, text, scaffold_jump=str(gap), min_aln_identity="0.90", scaffold_mass="0")
+        assert len(out) == 5, gap
+
+
+def test_mixed_identity_chaining(eng, tmp_path):  # tests/test_chain_monotonicity.rs:166-208 (PAF :41-66)
+    text = paf(*([_cg_row(qs, 980, 200000) for qs in (0, 2000, 5000, 8000, 11000)] +
+                 [_cg_row(qs, 900, 200000) for qs in (50000, 80000, 120000, 160000, 195000)]))
+    for gap, thr, expected in ((10_000, "0.95", 5), (100_000, "0.95", 0), (10_000, "0.85", 10), (100_000, "0.85", 10)):
+        out = run_paf(eng, tmp_path, text, scaffold_jump=str(gap), min_scaffold_identity=thr, scaffold_mass="0")
+        assert len(out) == expected, (gap, thr)
+
+
+def test_fragmented_chaining_coverage(eng, tmp_path):  # tests/test_chain_monotonicity.rs:210-249 (PAF :70-93)
+    text = paf(*[_cg_row(i * 3000, 950 + (i % 3) * 10) for i in range(20)])
+    for gap in (5_000, 50_000, 500_000):
+        assert len(run_paf(eng, tmp_path, text, scaffold_jump=str(gap), min_aln_identity="0.90", scaffold_mass="0")) == 20, gap
+
+
+def test_centromere_inversion_filtering(eng, tmp_path):  # tests/test_chain_monotonicity.rs:251-345
+    text = paf(*[_cg_row(qs, 760, 200000000, "-", ts, 1000000) for qs, ts in
+                 ((129000000, 132000000), (130000000, 133000000), (131000000, 134000000))])
+    flags = dict(scaffold_jump="10000", scaffold_mass="0")
+    assert len(run_paf(eng, tmp_path, text, min_aln_identity="0.80", **flags)) == 0   # 76 % < 80 %
+    assert len(run_paf(eng, tmp_path, text, min_aln_identity="0.75", **flags)) > 0    # 76 % >= 75 %
+    assert len(run_paf(eng, tmp_path, text, min_aln_identity="0", **flags)) > 0
+
+
+def test_chaining_monotonicity_property(eng, tmp_path):
+    """tests/test_chaining_stability.rs:52-94 runs the aligner on data/scerevisiae8.fa.gz (absent here: FASTA blob and FastGA
+    missing).  Its assertion — the number of chain members never decreases as --scaffold-jump grows — on the yeast-shaped
+    synthetic PAF instead."""
+    from sweepga_b200 import synth
+    src = tmp_path / "y.paf"
+    synth.write_paf(synth.yeast_like(6000, seed=33), str(src))
+    text = src.read_text()
+    counts = []
+    for gap in (10_000, 50_000, 100_000, 500_000, 1_000_000):
+        ch = _chains(run_paf(eng, tmp_path, text, scaffold_jump=str(gap), min_aln_identity="0"))
+        counts.append(sum(len(v) for v in ch.values()))
+    assert counts == sorted(counts) and counts[0] > 0, counts
+
+
+# ---------------------------------------------------------------------------------------------
+# tests/test_error_handling.rs:46-366 (the PAF-level cases; the CLI's own messages are out of scope)
+# ---------------------------------------------------------------------------------------------
+GOOD12 = "seq1\t1000\t{qs}\t{qe}\t{strand}\tseq2\t2000\t100\t300\t150\t200\t60\n"
+
+
+def test_malformed_paf_lines(eng, tmp_path):  # :46-77 — "rejected or produce no output"
+    assert run_paf(eng, tmp_path, "seq1\t100\t200\n") == []
+
+
+def test_invalid_paf_numbers(eng, tmp_path):  # :80-112 — a non-numeric field parses as 0 (paf_filter.rs:308-317); no output
+    assert run_paf(eng, tmp_path, GOOD12.format(qs="NOT_A_NUMBER", qe=200, strand="+")) == []
+
+
+def test_missing_file_error(eng, tmp_path):  # :115-144
+    with pytest.raises((IOError, swg.SwgError)):
+        eng.filter_paf(swg.FilterConfig(), str(tmp_path / "this_file_definitely_does_not_exist_12345.paf"), str(tmp_path / "o.paf"))
+
+
+def test_invalid_coordinate_ranges(eng, tmp_path):  # :149-180 — start > end "currently passes them through"
+    """The reference neither validates nor crashes (release build: wrapping u64 arithmetic).  The u32 table cannot hold a
+    wrapped span, so the drop-in states the difference: such a record is an error only if it SURVIVES the
+    stage-1 retain, and then a clean one (SWG_ERR_RANGE, context still usable); if the retain drops it, nothing happens."""
+    text = GOOD12.format(qs=500, qe=200, strand="+")
+    assert run_paf(eng, tmp_path, text, min_aln_length="1k") == []
+    if eng.name == "gpu":
+        with pytest.raises(swg.SwgError) as e:
+            run_paf(eng, tmp_path, text)
+        assert e.value.code == -2 and "end < start" in str(e.value)
+        assert run_paf(eng, tmp_path, GOOD12.format(qs=0, qe=200, strand="+"), scaffold_jump="0") != []
+    else:
+        run_paf(eng, tmp_path, text)  # must not crash
+
+
+def test_unsupported_format(eng, tmp_path):  # :183-218 — binary garbage: no record, no output (the CLI's message is its own)
+    src, dst = tmp_path / "binary.bin", tmp_path / "o.paf"
+    src.write_bytes(bytes([0xFF, 0xFE, 0xFD, 0xFC, 0x00, 0x01]))
+    eng.filter_paf(swg.FilterConfig(), str(src), str(dst))
+    assert dst.read_bytes() == b""
+
+
+def test_partial_valid_paf(eng, tmp_path):  # :221-263
+    text = ("seq1\t100\t0\t50\t+\tseq2\t200\t0\t50\t40\t50\t60\n"
+            "INVALID LINE WITH GARBAGE\n"
+            "seq3\t300\t0\t100\t+\tseq4\t400\t0\t100\t90\t100\t60\n"
+            "too\tfew\tfields\n"
+            "seq5\t500\t0\t150\t+\tseq6\t600\t0\t150\t140\t150\t60\n")
+    out = run_paf(eng, tmp_path, text, scaffold_jump="0")
+    assert len(out) == 3 and all(l.endswith("st:Z:unassigned") for l in out)
+
+
+def test_negative_coordinates(eng, tmp_path):  # :266-295 — "-100" does not parse as u64 -> 0; the 200 bp mapping is below the scaffold mass
+    assert run_paf(eng, tmp_path, GOOD12.format(qs=-100, qe=200, strand="+")) == []
+
+
+def test_overflow_coordinates(eng, tmp_path):  # :298-327 — the overflowing number sits in the (unused) length column
+    assert run_paf(eng, tmp_path, "seq1\t999999999999999999999\t0\t100\t+\tseq2\t2000\t0\t100\t90\t100\t60\n") == []
+
+
+def test_invalid_strand(eng, tmp_path):  # :330-366 — any strand other than "+" is reverse (paf_filter.rs:311); no crash
+    out = run_paf(eng, tmp_path, GOOD12.format(qs=0, qe=100, strand="X"), scaffold_jump="0")
+    assert len(out) == 1
+
+
+def test_empty_file(eng, tmp_path):  # :11-43 — the CLI refuses an empty input itself; the filter writes an empty output
+    assert run_paf(eng, tmp_path, "") == []
+
+
+# ---------------------------------------------------------------------------------------------
+# tests/unit_tests.rs:148-208
+# ---------------------------------------------------------------------------------------------
+def test_cigar_extended_format(eng, tmp_path):  # :148-188 — the example CIGARs through parse_cigar_counts (src/paf.rs:32-64)
+    examples = {"10=": 10, "5=2X3=": 8, "10=5I10=": 20, "10=5D10=": 20, "3=1X2=1I4=1D": 9}
+    text = paf(*[("q", 1000, 0, 100, "+", "t", 1000, 0, 100, 1, 100, 60, f"cg:Z:{cg}") for cg in examples])
+    src = tmp_path / "cg.paf"
+    src.write_text(text)
+    t = oracle_lib.parse_paf(str(src)) if eng.name == "oracle" else swg.parse_paf(str(src), eng.ctx)
+    assert [int(x) for x in t.matches] == list(examples.values())
+    assert t.identity.tolist() == [m / 100 for m in examples.values()]
+
+
+def test_scaffold_annotations(eng, tmp_path):  # :190-208 — ch:Z:chain_<k> / st:Z:<status> as written by write_filtered_output
+    text = paf(*[_cg_row(qs, 950) for qs in (0, 12000, 24000)], _cg_row(40000, 950, strand="-", ts=39000))
+    out = run_paf(eng, tmp_path, text, scaffold_dist="100k")
+    assert out
+    for l in out:
+        tags = [x for x in l.split("\t")[12:] if x[:5] in ("ch:Z:", "st:Z:")]
+        assert len(tags) == 2
+        for ann in tags:
+            parts = ann.split(":")
+            assert len(parts) == 3 and parts[0] in ("ch", "st") and parts[1] == "Z" and parts[2]
+        assert tags[0].startswith("ch:Z:chain_") and tags[0][11:].isdigit()
+        assert tags[1] in ("st:Z:scaffold", "st:Z:rescued")
+
+
+# ---------------------------------------------------------------------------------------------
 # src/pansn.rs:317-342, src/cli.rs parsers, src/main.rs:244-293 / src/library_api.rs:31-63 (host logic; no GPU)
 # ---------------------------------------------------------------------------------------------
 def test_round_nice():  # src/pansn.rs:300-315
