@@ -340,7 +340,7 @@ def main():
     import torch
     import torch.distributed as dist
     import sweepga_b200 as swg
-    from sweepga_b200.distributed import gather_runs, unit_offsets
+    from sweepga_b200.distributed import unit_offsets
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -379,14 +379,32 @@ def main():
         d_res.status = C.cast(status_t.data_ptr(), C.POINTER(C.c_uint8))
         d_res.chain_id = C.cast(chain_t.data_ptr(), C.POINTER(C.c_uint32))
 
+    if world > 1:
+        n_mine = len(units["mine"])
+        max_units = torch.tensor([n_mine], dtype=torch.int64, device=dev)
+        dist.all_reduce(max_units, op=dist.ReduceOp.MAX)
+        max_units = int(max_units.item())
+        runs_send = torch.zeros(max_units * 2 + 1, dtype=torch.int64, device=dev)     # [count, A..., n...]
+        runs_recv = torch.zeros((max_units * 2 + 1) * world, dtype=torch.int64, device=dev)
+        runs_host = torch.zeros(max_units * 2 + 1, dtype=torch.int64, pin_memory=True)
+
     def make_global(res_chain_ptr, n_ch):
-        """chain_N of the shard -> chain_N of the whole table; 2-bit status planes of every shard to every rank.
-        Returns the number of kernels of ours launched here."""
-        a_loc, first_k = ctx.last_chain_units()
+        """chain_N of the shard -> chain_N of the whole table: one (A, count) pair per genome-pair unit is exchanged (one
+        fixed-size all-gather of a few thousand integers), sorted by the global index of A, prefix-summed, and every rank adds
+        its runs' offsets on the device.  Returns the number of kernels of ours launched here."""
+        a_loc, first_k = ctx.last_chain_units(n_mine)
+        k = len(a_loc)
         cnt = np.diff(np.concatenate((first_k.astype(np.int64), [n_ch + 1])))
         u = np.searchsorted(loff, a_loc, side="right") - 1
         a_glob = goff[units["mine"][u]] + (a_loc.astype(np.int64) - loff[u])
-        runs = gather_runs(dist, a_glob, cnt, world, device=dev)
+        h = runs_host.numpy()
+        h[0] = k
+        h[1:1 + k] = a_glob
+        h[1 + max_units:1 + max_units + k] = cnt
+        runs_send.copy_(runs_host, non_blocking=True)
+        dist.all_gather_into_tensor(runs_recv, runs_send)
+        allr = runs_recv.cpu().numpy().reshape(world, -1)
+        runs = [(allr[r, 1:1 + int(allr[r, 0])], allr[r, 1 + max_units:1 + max_units + int(allr[r, 0])]) for r in range(world)]
         delta = unit_offsets(runs)[rank]
         ctx.renumber_chains_device(n, res_chain_ptr, first_k, delta)
         return 3
@@ -536,7 +554,7 @@ def main():
                        "pipeline_fraction_of_hbm_roofline": (n * desc["b_alg"] / (t_filter / args.steps)) / 1e9 / peak,
                        "log_matches_host": ctx.log_matches_host(),
                        "stats": {k: int(getattr(stats, k)) for k in ("n_stage1", "n_after_sweep", "n_chains", "n_chains_after_mass",
-                                                                     "n_chains_kept", "n_anchors", "n_rescued", "n_kept", "exact_rerank")}},
+                                                                     "n_chains_kept", "n_anchors", "n_rescued", "n_kept", "exact_rerank", "n_dirty_groups")}},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_v, "unit": "Mmappings/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": t_e2e * 1e3 / args.steps, "wall_ms_per_step": wall_e2e * 1e3 / args.steps,

@@ -152,7 +152,9 @@ typedef struct swg_stats {
                                      on a host whose log() differs from the device's port, or SWG_EXACT_SCORES=always) */
     uint64_t sort_bytes_per_pair; /* bytes one timed sort pass moves per pair (24: key+payload pairs, 16: packed words) */
     uint64_t h2d_bytes, d2h_bytes;/* swg_filter: bytes copied host->device / device->host by this call        */
-    uint64_t reserved[4];
+    uint64_t n_dirty_groups;      /* (query,target,strand) groups in which some mapping was claimed as successor twice:
+                                     chained by the sequential walk instead of the one-pass claims (diagnostic)       */
+    uint64_t reserved[3];
 } swg_stats;
 
 typedef struct swg_ctx swg_ctx;

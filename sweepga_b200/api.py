@@ -310,15 +310,18 @@ class Context:
         self._check(lib.swg_last_chain_keys(self._h, k, _ptr(a, C.c_uint32), _ptr(b, C.c_uint32), C.byref(n)))
         return a, b
 
-    def last_chain_units(self):
+    def last_chain_units(self, max_units=0):
         """Runs of kept chains that share a genome-pair unit, for the last call (swg_last_chain_units):
-        (A = input index of the unit's first stage-1 record, first local chain number of the run), in chain order."""
+        (A = input index of the unit's first stage-1 record, first local chain number of the run), in chain order.
+        max_units: an upper bound on the number of runs if the caller knows one (one round trip instead of two)."""
         n = C.c_uint64()
-        self._check(lib.swg_last_chain_units(self._h, 0, None, None, C.byref(n)))
+        if not max_units:
+            self._check(lib.swg_last_chain_units(self._h, 0, None, None, C.byref(n)))
+            max_units = int(n.value)
+        a, f = np.zeros(max(max_units, 1), np.uint32), np.zeros(max(max_units, 1), np.uint32)
+        if max_units:
+            self._check(lib.swg_last_chain_units(self._h, max_units, _ptr(a, C.c_uint32), _ptr(f, C.c_uint32), C.byref(n)))
         k = int(n.value)
-        a, f = np.zeros(max(k, 1), np.uint32), np.zeros(max(k, 1), np.uint32)
-        if k:
-            self._check(lib.swg_last_chain_units(self._h, k, _ptr(a, C.c_uint32), _ptr(f, C.c_uint32), C.byref(n)))
         return a[:k], f[:k]
 
     def renumber_chains_device(self, n, chain_id_dev_ptr, unit_first_chain, unit_delta):

@@ -16,6 +16,8 @@ constexpr u8 F_ALIVE = 1;   // passed the stage-1 retain (paf_filter.rs:384-388)
 constexpr u8 F_ZLQ = 2;     // zero-length query interval
 constexpr u8 F_ZLT = 4;     // zero-length target interval
 constexpr u8 F_PREMEM = 8;  // member of a chain that passed the mass/identity filter (pre_sweep_scaffold_members)
+constexpr u8 F_REV = 16;    // reverse strand (any strand byte other than '+', paf_filter.rs:311)
+constexpr u8 F_ANCHOR = 32; // status == scaffold: member of a kept chain or captured inversion (set by t_assign / t_inversion)
 
 // counters (u64 each) shared with the host
 enum {
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(256) k_prefilter(DevIn in, u64 min_len, double
         zt = alive && te == ts;
         maxc = alive ? max(qe, te) : 0u;
         if (alive) g = ((u64)in.P[q] << 32) | in.P[t];
-        flags[i] = (u8)((alive ? F_ALIVE : 0) | (zq ? F_ZLQ : 0) | (zt ? F_ZLT : 0));
+        flags[i] = (u8)((alive ? F_ALIVE : 0) | (zq ? F_ZLQ : 0) | (zt ? F_ZLT : 0) | (in.strand[i] != '+' ? F_REV : 0));
         // packed copy for the post-sort gather: one 16 B sector instead of four 4 B gathers.  `matches` is NOT touched
         // here (unless identity has to be derived from it): it is first read by the gather after the sort, so its
         // host-to-device copy can overlap K0 + sort.
@@ -159,13 +161,14 @@ __global__ void __launch_bounds__(256) k_chain_keys(DevIn in, const u8 *__restri
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     bool kept = false;
     if (i < in.n) {
-        kept = (flags[i] & F_ALIVE) && (!keep_q || keep_q[i]) && (!keep_t || keep_t[i]);
+        const u8 fl = flags[i];
+        kept = (fl & F_ALIVE) && (!keep_q || keep_q[i]) && (!keep_t || keep_t[i]);
         // dead records: all ones in the key's own 2*sb + 1 + cb bits (ids stay below 2^sb - 1, so they sort behind every
         // live key) and zero above, so that the word still fits after the packed sort has shifted it
         const int kb = 2 * sb + 1 + cb;
         u64 k = kb >= 64 ? NONE64 : ((1ull << kb) - 1);
         if (kept) {
-            u64 sbit = in.strand[i] == '+' ? 0 : 1;
+            u64 sbit = (fl & F_REV) ? 1 : 0;
             k = ((((u64)in.qid[i] << sb | in.tid[i]) << 1 | sbit) << cb) | in.qs[i];
         }
         keys[i] = k;
@@ -215,6 +218,13 @@ __global__ void __launch_bounds__(256) k_count_status(u32 n, const u8 *__restric
 //   P3 k_chain_heads / k_chain_members  flat: bounding boxes and sums per chain (segmented warp
 //                          reduction, then one atomic set per run).
 // ---------------------------------------------------------------------------------------------
+// sorted position -> input index: the payload column of a pairs sort, or the low bits of the packed words
+struct SortedIdx {
+    const u64 *w;
+    const u32 *v;
+    u64 mask;
+    __device__ __forceinline__ u32 operator[](u32 p) const { return w ? (u32)(w[p] & mask) : v[p]; }
+};
 struct Cand { // unconstrained best successor of a position
     u64 d;    // squared gap distance
     u32 j;    // sorted position of the successor, NONE32 if the window holds no valid candidate
@@ -294,24 +304,51 @@ __device__ __forceinline__ void bb_best_successor(const uint4 *__restrict__ srec
 // unconstrained arg-min is eligible and taken (paf_filter.rs:835-850).  A second claim on some j marks the whole group
 // dirty; dirty groups (rare on ordinary data) are redone by the sequential resolve below, which rewrites their pred[].
 // pred[] must be NONE32 everywhere on entry.
+// LIST = false: one thread per position, claims only (the 16 B candidate record is not written: clean groups never read it).
+// LIST = true: grid-stride over a list of positions (those of the dirty and huge groups), writes their candidate records
+// for the resolve kernels / the fixed-point iteration; no claims.
+template <bool LIST>
 __global__ void __launch_bounds__(256)
 k_chain_candidates(const uint4 *__restrict__ srec, const u64 *__restrict__ skey, const u32 *__restrict__ gid,
                    const u32 *__restrict__ gstart, u32 n_groups, u32 n_m, int cb, u64 G, Cand *__restrict__ cand,
-                   u32 *pred, u8 *__restrict__ grp_dirty) {
-    const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_m) return;
-    const uint4 a = srec[p]; // x=qs y=qe z=ts w=te
-    const bool fwd = ((skey[p] >> cb) & 1) == 0;
-    const u32 g = gid[p];
-    const u32 e = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
-    u64 bd;
-    u32 bj;
-    u32 c0;
-    bb_best_successor<false>(srec, nullptr, p, e, a, fwd, G, G / 5, bd, bj, &c0);
-    Cand c;
-    c.d = bd; c.j = bj; c.c0 = c0;
-    cand[p] = c;
-    if (bj != NONE32 && atomicExch(&pred[bj], p) != NONE32) grp_dirty[g] = 1; // benign race: every writer stores 1
+                   u32 *pred, u8 *__restrict__ grp_dirty, const u32 *__restrict__ list, const u32 *__restrict__ n_list_ptr) {
+    const u32 n_items = LIST ? *n_list_ptr : n_m;
+    for (u32 x = blockIdx.x * blockDim.x + threadIdx.x; x < n_items; x += gridDim.x * blockDim.x) {
+        const u32 p = LIST ? list[x] : x;
+        const uint4 a = srec[p]; // x=qs y=qe z=ts w=te
+        const bool fwd = ((skey[p] >> cb) & 1) == 0;
+        const u32 g = gid[p];
+        const u32 e = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
+        u64 bd;
+        u32 bj;
+        u32 c0;
+        bb_best_successor<false>(srec, nullptr, p, e, a, fwd, G, G / 5, bd, bj, &c0);
+        if (LIST) {
+            Cand c;
+            c.d = bd; c.j = bj; c.c0 = c0;
+            cand[p] = c;
+        } else if (bj != NONE32 && atomicExch(&pred[bj], p) != NONE32) grp_dirty[g] = 1; // benign race: every writer stores 1
+    }
+}
+
+// The candidate records of the positions of LISTED GROUPS (the dirty ones), one warp per group, lanes over its positions.
+__global__ void __launch_bounds__(256)
+k_chain_candidates_groups(const uint4 *__restrict__ srec, const u64 *__restrict__ skey, const u32 *__restrict__ gstart, u32 n_groups, u32 n_m, int cb,
+                          u64 G, Cand *__restrict__ cand, const u32 *__restrict__ glist_a, const u32 *__restrict__ n_a, const u32 *__restrict__ glist_b,
+                          const u32 *__restrict__ n_b) {
+    const u32 na = *n_a, nb = *n_b;
+    const u32 lane = lane_id();
+    for (u32 w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < na + nb; w += (gridDim.x * blockDim.x) >> 5) {
+        const u32 g = w < na ? glist_a[w] : glist_b[w - na];
+        const u32 s0 = gstart[g], e = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
+        const bool fwd = ((skey[s0] >> cb) & 1) == 0;
+        for (u32 p = s0 + lane; p < e; p += 32) {
+            const uint4 a = srec[p];
+            Cand c;
+            bb_best_successor<false>(srec, nullptr, p, e, a, fwd, G, G / 5, c.d, c.j, &c.c0);
+            cand[p] = c;
+        }
+    }
 }
 
 // P2: the reference's sequential loop for the DIRTY groups (some successor claimed twice), one thread per group; lanes
@@ -321,6 +358,7 @@ k_chain_candidates(const uint4 *__restrict__ srec, const u64 *__restrict__ skey,
 // it is the arg-min over the eligible ones); only a blocked step re-scans its window with the eligibility test.
 // Result: pred[j] = best_pred_idx[j] (paf_filter.rs:847-850), NONE32 = no predecessor.
 constexpr u32 RES_SMALL = 16;
+constexpr u32 RES_THREAD_MAX = 48; // dirty groups up to this size are walked by one thread, larger ones by a warp
 __global__ void __launch_bounds__(128)
 k_chain_resolve(const Cand *__restrict__ cand, const uint4 *__restrict__ srec, const u64 *__restrict__ skey,
                 const u32 *__restrict__ gstart, u32 n_groups, u32 n_m, const u32 *__restrict__ work, const u32 *__restrict__ n_work_ptr,
@@ -670,8 +708,8 @@ k_chain_resolve_warp(const Cand *__restrict__ cand, const uint4 *__restrict__ sr
 // of chain_fixpoint.cuh instead of a sequential walk.
 constexpr u32 FX_MIN_GROUP = 16384;
 __global__ void __launch_bounds__(256)
-k_chain_work_estimate(const uint4 *__restrict__ srec, const u32 *__restrict__ gstart, const u32 *__restrict__ n_groups_ptr, u32 n_m, u64 G,
-                      u32 fx_min, u64 *ctr) {
+k_chain_work_estimate(const uint4 *__restrict__ rec4, SortedIdx sidx, const u32 *__restrict__ gstart, const u32 *__restrict__ n_groups_ptr, u32 n_m,
+                      u64 G, u32 fx_min, u64 *ctr) {
     const u32 n_groups = *n_groups_ptr; // grid-stride: the host has not read the group count yet
     u64 est = 0;
     for (u32 g = blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += gridDim.x * blockDim.x) {
@@ -679,7 +717,7 @@ k_chain_work_estimate(const uint4 *__restrict__ srec, const u32 *__restrict__ gs
         const u64 size = e - s;
         if (size >= fx_min) atomicAdd((unsigned long long *)&ctr[C_HUGE], (unsigned long long)size); // a handful of groups at most
         if (size > 1) {
-            const u64 span = (u64)srec[e - 1].x - srec[s].x + 1;
+            const u64 span = (u64)rec4[sidx[e - 1]].x - rec4[sidx[s]].x + 1; // (runs before the gather: two reads per group)
             u64 win = size * G / span + 1; // expected candidates per step
             if (win > size) win = size;
             est += size * win;
@@ -699,12 +737,17 @@ k_chain_work_estimate(const uint4 *__restrict__ srec, const u32 *__restrict__ gs
 // position's published chain number (its tile is resident or done: the wait only ever points backwards).
 // chain_of[] must be NONE32 everywhere on entry.  PRESET: root[] already holds the final root of some positions (huge
 // groups chained by the fixed-point iteration), NONE32 elsewhere.
+struct ChainDense { // per-chain aggregates, rows indexed by chain number
+    u32 *qmin, *qmax, *tmin, *tmax; // = ChainTable qs / qe / ts / te
+    u64 *sum_matches, *sum_block;
+    u32 *k;                         // chain_N of the chain (0 = not kept): cleared with the row
+};
 constexpr int CR_THREADS = 256, CR_ITEMS = 8, CR_TILE = CR_THREADS * CR_ITEMS;
 static_assert(CR_THREADS == SC_THREADS, "k_chain_number uses the 256-thread block scan of scan.cuh");
 template <bool PRESET>
 __global__ void __launch_bounds__(CR_THREADS)
 k_chain_number(const u32 *__restrict__ pred, const u32 *__restrict__ root_preset, u32 n_m, u32 *chain_of, u32 *__restrict__ head_pos,
-               u64 *status, u32 *tile_counter, u32 *n_chains_out) {
+               u64 *status, u32 *tile_counter, u32 *n_chains_out, ChainDense cd) {
     __shared__ u32 anc[CR_TILE];
     __shared__ u32 ws[CR_THREADS / 32];
     __shared__ u32 s_tile, s_excl;
@@ -788,6 +831,12 @@ k_chain_number(const u32 *__restrict__ pred, const u32 *__restrict__ root_preset
             }
         }
     }
+    // the tile's chains are the consecutive rows s_excl .. s_excl + tot of the aggregate table: they start empty (the host does
+    // not know the chain count yet, so nobody else can clear them)
+    for (u32 r = s_excl + tid, r_end = s_excl + tot; r < r_end; r += CR_THREADS) {
+        cd.qmin[r] = NONE32; cd.qmax[r] = 0; cd.tmin[r] = NONE32; cd.tmax[r] = 0;
+        cd.sum_matches[r] = 0; cd.sum_block[r] = 0; cd.k[r] = 0;
+    }
     __syncthreads();
     // every position: chain number of its head (inside the tile) or of its ancestor in an earlier tile
 #pragma unroll
@@ -809,20 +858,9 @@ k_chain_number(const u32 *__restrict__ pred, const u32 *__restrict__ root_preset
 // by atomicAdd; runs of one chain inside a warp are reduced first (one set of atomics per run).  Every position also feeds
 // its group's min original index (the first appearance of the group in the input).  The table rows are pre-set to
 // (max, 0, max, 0, 0, 0).
-struct ChainDense {
-    u32 *qmin, *qmax, *tmin, *tmax; // = ChainTable qs / qe / ts / te
-    u64 *sum_matches, *sum_block;
-};
-// sorted position -> input index: the payload column of a pairs sort, or the low bits of the packed words
-struct SortedIdx {
-    const u64 *w;
-    const u32 *v;
-    u64 mask;
-    __device__ __forceinline__ u32 operator[](u32 p) const { return w ? (u32)(w[p] & mask) : v[p]; }
-};
 __global__ void __launch_bounds__(256)
-k_chain_aggregate(const uint4 *__restrict__ srec, const uint2 *__restrict__ srec2, SortedIdx sidx, const u32 *__restrict__ gid,
-                  const u32 *__restrict__ chain_of, u32 n_m, ChainDense cd, u32 *__restrict__ grp_minidx) {
+k_chain_aggregate(const uint4 *__restrict__ srec, const u32 *__restrict__ blen, const u32 *__restrict__ matches, SortedIdx sidx,
+                  const u32 *__restrict__ gid, const u32 *__restrict__ chain_of, u32 n_m, ChainDense cd, u32 *__restrict__ grp_minidx) {
     const u32 full = 0xFFFFFFFFu;
     const u32 lane = lane_id();
     const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -835,7 +873,7 @@ k_chain_aggregate(const uint4 *__restrict__ srec, const uint2 *__restrict__ srec
         idx = sidx[p];
         ci = chain_of[p];
         a = srec[p];
-        m = srec2[p];
+        m = make_uint2(__ldg(&blen[idx]), __ldg(&matches[idx])); // gathered by input index (a separate sorted copy cost 16 B more per record)
     }
     // groups are contiguous: usually the whole warp shares one
     const u32 g0 = __shfl_sync(full, g, 0);
@@ -952,6 +990,12 @@ __device__ __forceinline__ bool overlaps_more_than(u32 s1, u32 e1, u32 s2, u32 e
 // Two scores this close can rank differently when the log comes from another libm (each side is within ~1 ulp of the
 // other in the log, one more rounding in the product): the audit band of swg_stats.score_near_ties.
 constexpr u64 NEAR_TIE_ULPS = 4;
+// An exact tie counts too unless the two items also share the interval (duplicate records: same inputs, same score under
+// any libm): equal device scores of DIFFERENT items may be unequal on the host.
+__device__ __forceinline__ bool near_tie(u64 key_a, u32 start_a, u32 end_a, u64 key_b, u32 start_b, u32 end_b) {
+    const u64 df = key_a > key_b ? key_a - key_b : key_b - key_a;
+    return df <= NEAR_TIE_ULPS && !(df == 0 && start_a == start_b && end_a == end_b);
+}
 struct SweepItem { // per item, in (group, start, item) order, so that a group is one contiguous stream
     u64 skey;  // score_desc_key of the item
     u32 start; // axis interval of the item
@@ -1004,8 +1048,7 @@ k_sweep_flat1(const u32 *__restrict__ sitem, const SweepItem *__restrict__ sdata
         const SweepItem a = sdata[k];
         if (a.start >= me.end) break;
         hi = k;
-        const u64 df = a.skey > me.skey ? a.skey - me.skey : me.skey - a.skey; // near-tie audit, each co-active pair once
-        near += (df != 0 && df <= NEAR_TIE_ULPS);
+        near += near_tie(a.skey, a.start, a.end, me.skey, me.start, me.end); // near-tie audit, each co-active pair once
         if (k - u > SWF_RIGHT) big = true;
     }
     if (big) {
@@ -1117,8 +1160,8 @@ k_sweep_groups(const u32 *__restrict__ sitem, const SweepItem *__restrict__ sdat
                 // near-tie audit: neighbours whose score key differs by <= 2 ulp but is not equal
                 if (lane == 0) {
                     u32 near = 0;
-                    if (cnt > 0) { u64 df = x.skey - A[cnt - 1].skey; near += (df != 0 && df <= NEAR_TIE_ULPS); }
-                    if (cnt < size) { u64 df = A[cnt].skey - x.skey; near += (df != 0 && df <= NEAR_TIE_ULPS); }
+                    if (cnt > 0) near += near_tie(x.skey, x.start, x.end, A[cnt - 1].skey, A[cnt - 1].start, A[cnt - 1].end);
+                    if (cnt < size) near += near_tie(x.skey, x.start, x.end, A[cnt].skey, A[cnt].start, A[cnt].end);
                     if (near) atomicAdd((unsigned long long *)&ctr[C_NEAR_TIES], (unsigned long long)near);
                 }
                 // shift [cnt, size) up by one, from the top, 32 at a time
@@ -1230,8 +1273,8 @@ k_sweep_small(const u32 *__restrict__ sitem, const SweepItem *__restrict__ sdata
                 }
                 a_key[pos] = d.skey; a_start[pos] = d.start; a_end[pos] = d.end; a_item[pos] = item << 2;
                 u32 near = 0; // near-tie audit: neighbours whose score key differs by <= 2 ulp but is not equal
-                if (pos > 0) { const u64 df = d.skey - a_key[pos - 1]; near += (df != 0 && df <= NEAR_TIE_ULPS); }
-                if (pos < size) { const u64 df = a_key[pos + 1] - d.skey; near += (df != 0 && df <= NEAR_TIE_ULPS); }
+                if (pos > 0) near += near_tie(d.skey, d.start, d.end, a_key[pos - 1], a_start[pos - 1], a_end[pos - 1]);
+                if (pos < size) near += near_tie(d.skey, d.start, d.end, a_key[pos + 1], a_start[pos + 1], a_end[pos + 1]);
                 if (near) atomicAdd((unsigned long long *)&ctr[C_NEAR_TIES], (unsigned long long)near);
                 size++;
                 chk = pos == 0 ? 0u : ((chk & ((1u << pos) - 1)) | ((chk >> pos) << (pos + 1)));

@@ -48,6 +48,15 @@ template <class Tag, class F> static inline void launch_for(u32 n, cudaStream_t 
     k_for<Tag, F><<<cdiv(n, 256), 256, 0, st>>>(n, f);
     lc.n++;
 }
+// the same over a count that lives on the device (no host round trip): fixed grid, grid-stride
+template <class Tag, class F> __global__ void __launch_bounds__(256) k_for_dev(const u32 *n_ptr, F f) {
+    const u32 n = *n_ptr;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) f(i);
+}
+template <class Tag, class F> static inline void launch_for_dev(const u32 *n_ptr, int sm_count, cudaStream_t st, LaunchCounter &lc, F f) {
+    k_for_dev<Tag, F><<<(u32)sm_count * 8, 256, 0, st>>>(n_ptr, f);
+    lc.n++;
+}
 // tags: one per element-wise stage, so that the ncu launch list reads k_for<swg::t_assign, ...> etc.
 struct t_iota; struct t_maxp; struct t_scores; struct t_gkey; struct t_events; struct t_sweep_gather; struct t_sweep_keep;
 struct t_gather; struct t_chain_order; struct t_tspace; struct t_segapply; struct t_keys_c2min; struct t_keys_g2min;
@@ -274,7 +283,7 @@ static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 in
     u32 *bsum = c->arena.take<u32>(scan_temp_u32(n_inc));
     u32 *d_ng = c->arena.take<u32>(2);
     const u64 *ekc = ek;
-    scan_apply([=] __device__(u32 u) -> u32 { return (u == 0 || (ekc[u] >> eshift) != (ekc[u - 1] >> eshift)) ? 1u : 0u; },
+    scan_flags([=] __device__(u32 u) -> u32 { return (u == 0 || (ekc[u] >> eshift) != (ekc[u - 1] >> eshift)) ? 1u : 0u; },
                [=] __device__(u32 u, u32 ex, u32 v) {
                    if (v) gstart[ex] = u;
                    gid[u] = ex + v - 1;
@@ -350,7 +359,7 @@ static void segment_first(swg_ctx *c, const u64 *sk, const u32 *sv, u32 n, u32 *
     cudaStream_t st = c->stream;
     u32 *segof = c->arena.take<u32>(n), *segfirst = c->arena.take<u32>(n);
     u32 *bsum = c->arena.take<u32>(scan_temp_u32(n)), *tot = c->arena.take<u32>(1);
-    scan_apply([=] __device__(u32 u) -> u32 { return (u == 0 || sk[u] != sk[u - 1]) ? 1u : 0u; },
+    scan_flags([=] __device__(u32 u) -> u32 { return (u == 0 || sk[u] != sk[u - 1]) ? 1u : 0u; },
                [=] __device__(u32 u, u32 ex, u32 v) { u32 s = ex + v - 1; segof[u] = s; if (v) segfirst[s] = sv[u]; }, n, bsum, tot,
                st, c->lc);
     launch_for<t_segapply>(n, st, c->lc, [=] __device__(u32 u) { out[sv[u]] = segfirst[segof[u]]; });
@@ -391,8 +400,6 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     swg_stats S;
     std::memset(&S, 0, sizeof S);
     S.n_input = N;
-    SWG_CUDA(cudaMemsetAsync(status, 0, N, st));
-    SWG_CUDA(cudaMemsetAsync(chain_id, 0, sizeof(u32) * (size_t)N, st));
     c->sort_passes = 0;
     c->sort_pairs = 0;
     c->sort_bytes_per_pair = 24;
@@ -414,6 +421,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         if (stats) *stats = S;
     };
     if (N == 0) { SWG_CUDA(cudaStreamSynchronize(st)); finish(); return; }
+    // (status / chain_id are cleared below, while the host waits for the first small read)
     if (cfg.scaffold_gap >= (1ull << 31) || cfg.scaffold_max_deviation >= (1ull << 31))
         throw RangeError{"scaffold_gap / scaffold_max_deviation must be < 2^31"};
 
@@ -430,10 +438,13 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     SWG_CUDA(cudaMemsetAsync(d_maxp, 0, 2 * sizeof(u32), st));
     launch_for<t_maxp>(in.n_seq, st, lc, [=] __device__(u32 s) { atomicMax(&d_maxp[0], in.P[s]); atomicMax(&d_maxp[1], in.P2[s]); });
     u32 maxP, maxP2;
-    {   // both in one round trip
+    {   // both in one round trip; the result arrays are cleared while the host waits for it
         u32 *h = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
         SWG_CUDA(cudaMemcpyAsync(h, d_maxp, 2 * sizeof(u32), cudaMemcpyDeviceToHost, st));
-        SWG_CUDA(cudaStreamSynchronize(st));
+        SWG_CUDA(cudaEventRecord(c->ev_ctr, st));
+        SWG_CUDA(cudaMemsetAsync(status, 0, N, st));
+        SWG_CUDA(cudaMemsetAsync(chain_id, 0, sizeof(u32) * (size_t)N, st));
+        SWG_CUDA(cudaEventSynchronize(c->ev_ctr));
         maxP = h[0];
         maxP2 = h[1];
     }
@@ -573,33 +584,32 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     if (n_m == 0) { finish(); return; }
     stage_mark(c, "groups+gather");
     uint4 *srec = A.take<uint4>(n_m);
-    uint2 *srec2 = A.take<uint2>(n_m);
     u32 *gstart = A.take<u32>(n_m + 1);
     u32 *gid = A.take<u32>(n_m);
     u32 *bsum = A.take<u32>(scan_temp_u32(N));
     u32 *d_tot = A.take<u32>(4);
-    // group boundaries, and in the same pass the gather of the packed records into sorted order (a thread's eight gathers
-    // are independent loads in flight together)
-    if (ev_matches) SWG_CUDA(cudaStreamWaitEvent(st, ev_matches, 0)); // first use of in.matches
-    scan_apply([=] __device__(u32 p) -> u32 { return (p == 0 || (skey[p] >> gshift) != (skey[p - 1] >> gshift)) ? 1u : 0u; },
+    scan_flags([=] __device__(u32 p) -> u32 { return (p == 0 || (skey[p] >> gshift) != (skey[p - 1] >> gshift)) ? 1u : 0u; },
                [=] __device__(u32 p, u32 ex, u32 v) {
                    if (v) gstart[ex] = p;
                    gid[p] = ex + v - 1;
-                   const u32 i = sidx[p];
-                   srec[p] = __ldg(&rec4[i]);
-                   srec2[p] = make_uint2(__ldg(&in.blen[i]), __ldg(&in.matches[i]));
                },
                n_m, bsum, d_tot, st, lc);
     u32 n_groups;
     // groups of at least fx_min positions are chained by the fixed-point iteration (SWG_NO_FIXPOINT=1: by the warp walk)
     const u32 fx_min = K.no_fixpoint ? NONE32 : (K.fixpoint_min ? K.fixpoint_min : FX_MIN_GROUP);
     {   // group count, positions in huge groups and a rough count of the candidate evaluations ahead (SWG_MAX_PAIR_EVALS, if
-        // set, refuses an input beyond it; by default nothing is refused: the reference runs such piles to completion too)
-        k_chain_work_estimate<<<(u32)c->sm_count * 8, 256, 0, st>>>(srec, gstart, d_tot, n_m, cfg.scaffold_gap, fx_min, ctr);
+        // set, refuses an input beyond it; by default nothing is refused: the reference runs such piles to completion too).
+        // The host picks the numbers up while the gather below runs.
+        k_chain_work_estimate<<<(u32)c->sm_count * 8, 256, 0, st>>>(rec4, sidx, gstart, d_tot, n_m, cfg.scaffold_gap, fx_min, ctr);
         lc.n++;
         u32 *h = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
         SWG_CUDA(cudaMemcpyAsync(h, d_tot, sizeof(u32), cudaMemcpyDeviceToHost, st)); // group count and estimate in one round trip
-        read_counters(c);
+        read_counters_begin(c);
+        // post-sort gather of the packed coordinates (flat, one thread per position: all gathers of a warp in flight at once;
+        // fused into the scan above it ran 5x slower: a scan thread owns eight CONSECUTIVE positions, so neither side coalesces).
+        // block_length / matches are not copied: the aggregate pass gathers them itself.
+        launch_for<t_gather>(n_m, st, lc, [=] __device__(u32 p) { srec[p] = __ldg(&rec4[sidx[p]]); });
+        read_counters_end(c);
         n_groups = *h;
         if (K.max_pair_evals > 0 && (double)c->h_ctr[C_WORK] > K.max_pair_evals)
             throw RangeError{"chaining would need ~" + std::to_string((double)c->h_ctr[C_WORK]) +
@@ -611,7 +621,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     // ---- K3: best-buddy chaining (claims -> sequential resolve of the dirty groups -> chain numbers -> aggregates) ----
     u64 *bps = A.take<u64>(n_m);     // best_pred_score: only the dirty groups touch it
     u32 *pred = A.take<u32>(n_m);    // best_pred_idx
-    Cand *cand = A.take<Cand>(n_m);
+    Cand *cand = nullptr;            // unconstrained arg-min of every position of the groups that are redone (dirty / huge)
     u32 *grp_minidx = A.take<u32>(n_groups); // per GROUP: min original index over its members (first appearance of the group)
     u8 *grp_dirty = A.take<u8>(n_groups);
     u32 *work = A.take<u32>(n_groups), *work_big = A.take<u32>(n_groups);
@@ -622,7 +632,8 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     SWG_CUDA(cudaMemsetAsync(grp_minidx, 0xFF, sizeof(u32) * (size_t)n_groups, st));
     SWG_CUDA(cudaMemsetAsync(pred, 0xFF, sizeof(u32) * (size_t)n_m, st));
     {
-        k_chain_candidates<<<cdiv(n_m, 256), 256, 0, st>>>(srec, skey, gid, gstart, n_groups, n_m, gshift, cfg.scaffold_gap, cand, pred, grp_dirty);
+        k_chain_candidates<false><<<cdiv(n_m, 256), 256, 0, st>>>(srec, skey, gid, gstart, n_groups, n_m, gshift, cfg.scaffold_gap, nullptr, pred, grp_dirty,
+                                                                   nullptr, nullptr);
         lc.n++;
         stage_mark(c, "ch_worklists");
         // work lists: the dirty groups (a successor claimed twice), split into ordinary (thread per group) and large/dense
@@ -632,16 +643,24 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             const u32 s0 = gstart[g], e0 = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
             const u64 size = e0 - s0;
             const u64 span = (u64)srec[e0 - 1].x - srec[s0].x + 1;
-            return size < fx_min && (size > 4096 || size * Gj > 64 * span);
+            // a thread walking a group pays one memory round trip per step: beyond a few dozen steps the warp walk (32 steps
+            // prefetched per batch) is the faster one, and with only the dirty groups on the list the longest walk IS the kernel time
+            return size < fx_min && (size > RES_THREAD_MAX || size * Gj > 64 * span);
         };
         auto is_huge = [=] __device__(u32 g) -> bool {
             const u32 s0 = gstart[g], e0 = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
             return e0 - s0 >= fx_min;
         };
-        scan_apply([=] __device__(u32 g) -> u32 { return (grp_dirty[g] && !is_big(g) && !is_huge(g)) ? 1u : 0u; },
+        scan_flags([=] __device__(u32 g) -> u32 { return (grp_dirty[g] && !is_big(g) && !is_huge(g)) ? 1u : 0u; },
                    [=] __device__(u32 g, u32 ex, u32 v) { if (v) work[ex] = g; }, n_groups, bsum, bb_ctr, st, lc);
-        scan_apply([=] __device__(u32 g) -> u32 { return (grp_dirty[g] && is_big(g)) ? 1u : 0u; },
+        scan_flags([=] __device__(u32 g) -> u32 { return (grp_dirty[g] && is_big(g)) ? 1u : 0u; },
                    [=] __device__(u32 g, u32 ex, u32 v) { if (v) work_big[ex] = g; }, n_groups, bsum, bb_ctr + 2, st, lc);
+        // the redone groups need their candidate records: a second candidate pass over the listed groups only (ordinary data: a
+        // few hundred groups; writing all 16 B records in the first pass cost more than it saved)
+        cand = A.take<Cand>(n_m);
+        k_chain_candidates_groups<<<(u32)c->sm_count * 4, 256, 0, st>>>(srec, skey, gstart, n_groups, n_m, gshift, cfg.scaffold_gap, cand, work, bb_ctr,
+                                                                       work_big, bb_ctr + 2);
+        lc.n++;
         stage_mark(c, "ch_resolve");
         // enough threads to hide the dependent-load latency of a step, few enough that every group's lines stay in L1/L2
         k_chain_resolve<<<(u32)c->sm_count * K.resolve_mult, 128, 0, st>>>(cand, srec, skey, gstart, n_groups, n_m, work, bb_ctr, gshift, cfg.scaffold_gap,
@@ -655,13 +674,16 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             u32 *hpos = A.take<u32>(n_huge);
             root_preset = A.take<u32>(n_m);
             SWG_CUDA(cudaMemsetAsync(root_preset, 0xFF, sizeof(u32) * (size_t)n_m, st));
-            scan_apply([=] __device__(u32 p) -> u32 { return is_huge(gid[p]) ? 1u : 0u; },
+            scan_flags([=] __device__(u32 p) -> u32 { return is_huge(gid[p]) ? 1u : 0u; },
                        [=] __device__(u32 p, u32 ex, u32 v) { if (v) hpos[ex] = p; }, n_m, bsum, d_tot + 3, st, lc);
+            k_chain_candidates<true><<<(u32)c->sm_count * 16, 256, 0, st>>>(srec, skey, gid, gstart, n_groups, n_m, gshift, cfg.scaffold_gap, cand, nullptr,
+                                                                             nullptr, hpos, d_tot + 3); // their candidate records (position-parallel)
+            lc.n++;
             if (!chain_fixpoint(c, n_huge, hpos, srec, skey, gshift, gid, gstart, n_groups, n_m, cand, cfg.scaffold_gap, root_preset, bsum)) {
                 // a dependency chain longer than the round limit: the huge groups go through the sequential warp walk after all
                 // (it resets the groups' pred / best_pred_score itself; root_preset is untouched)
                 SWG_CUDA(cudaMemsetAsync(bb_ctr + 2, 0, 2 * sizeof(u32), st));
-                scan_apply([=] __device__(u32 g) -> u32 { return is_huge(g) ? 1u : 0u; },
+                scan_flags([=] __device__(u32 g) -> u32 { return is_huge(g) ? 1u : 0u; },
                            [=] __device__(u32 g, u32 ex, u32 v) { if (v) work_big[ex] = g; }, n_groups, bsum, bb_ctr + 2, st, lc);
                 k_chain_resolve_warp<<<(u32)c->sm_count * 4, 128, 0, st>>>(cand, srec, skey, gstart, n_groups, n_m, work_big, bb_ctr + 2, gshift,
                                                                           cfg.scaffold_gap, bps, pred, bb_ctr + 3);
@@ -671,9 +693,18 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     }
     stage_mark(c, "ch_number");
     // ---- roots + dense chain numbers in one pass (k_chain_number), then the chain table ---------------
+    // The table is sized for the worst case (every position its own chain) and each row is cleared by the kernel that numbers
+    // its chain, so the aggregate pass can start before the host knows the chain count (it reads it while that pass runs).
     u32 *chain_of = A.take<u32>(n_m);  // chain number of every sorted position
     u32 *head_pos = A.take<u32>(n_m);  // compacted head positions (C of them)
     u32 *d_nch = d_tot + 2;
+    ChainTable ct;
+    ct.pos = head_pos; ct.qid = A.take<u32>(n_m); ct.tid = A.take<u32>(n_m); ct.fwd = A.take<u8>(n_m);
+    ct.qs = A.take<u32>(n_m); ct.qe = A.take<u32>(n_m); ct.ts = A.take<u32>(n_m); ct.te = A.take<u32>(n_m);
+    ct.wid = A.take<double>(n_m); ct.pass = A.take<u8>(n_m); ct.k = A.take<u32>(n_m);
+    ChainDense cd;
+    cd.qmin = ct.qs; cd.qmax = ct.qe; cd.tmin = ct.ts; cd.tmax = ct.te; cd.k = ct.k;
+    cd.sum_matches = A.take<u64>(n_m); cd.sum_block = A.take<u64>(n_m);
     {
         const u32 tiles = cdiv(n_m, CR_TILE);
         u64 *cn_status = A.take<u64>(tiles + 1);
@@ -681,30 +712,28 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         SWG_CUDA(cudaMemsetAsync(cn_status, 0, sizeof(u64) * (size_t)(tiles + 1), st));
         SWG_CUDA(cudaMemsetAsync(cn_ctr, 0, 2 * sizeof(u32), st));
         SWG_CUDA(cudaMemsetAsync(chain_of, 0xFF, sizeof(u32) * (size_t)n_m, st));
-        if (root_preset) k_chain_number<true><<<tiles, CR_THREADS, 0, st>>>(pred, root_preset, n_m, chain_of, head_pos, cn_status, cn_ctr, d_nch);
-        else k_chain_number<false><<<tiles, CR_THREADS, 0, st>>>(pred, nullptr, n_m, chain_of, head_pos, cn_status, cn_ctr, d_nch);
+        if (root_preset) k_chain_number<true><<<tiles, CR_THREADS, 0, st>>>(pred, root_preset, n_m, chain_of, head_pos, cn_status, cn_ctr, d_nch, cd);
+        else k_chain_number<false><<<tiles, CR_THREADS, 0, st>>>(pred, nullptr, n_m, chain_of, head_pos, cn_status, cn_ctr, d_nch, cd);
         lc.n++;
     }
-    const u32 C = read_u32(c, d_nch);
+    {   // the chain count (and, as diagnostics, how many groups had to be redone sequentially) travels while the aggregate runs
+        u32 *h = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
+        SWG_CUDA(cudaMemcpyAsync(h, d_nch, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        SWG_CUDA(cudaMemcpyAsync(h + 2, bb_ctr, 4 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+        SWG_CUDA(cudaEventRecord(c->ev_ctr, st));
+    }
+    if (ev_matches) SWG_CUDA(cudaStreamWaitEvent(st, ev_matches, 0)); // first use of in.matches
+    k_chain_aggregate<<<cdiv(n_m, 256), 256, 0, st>>>(srec, in.blen, in.matches, sidx, gid, chain_of, n_m, cd, grp_minidx);
+    lc.n++;
+    SWG_CUDA(cudaEventSynchronize(c->ev_ctr));
+    u32 C;
+    {
+        const u32 *h = reinterpret_cast<const u32 *>(c->h_ctr + C_COUNT);
+        C = h[0];
+        S.n_dirty_groups = (u64)h[2] + h[4];
+    }
     stage_mark(c, "chain_table");
     S.n_chains = C;
-    ChainTable ct;
-    ct.pos = head_pos; ct.qid = A.take<u32>(C); ct.tid = A.take<u32>(C); ct.fwd = A.take<u8>(C);
-    ct.qs = A.take<u32>(C); ct.qe = A.take<u32>(C); ct.ts = A.take<u32>(C); ct.te = A.take<u32>(C);
-    ct.wid = A.take<double>(C); ct.pass = A.take<u8>(C); ct.k = A.take<u32>(C);
-    SWG_CUDA(cudaMemsetAsync(ct.k, 0, sizeof(u32) * (size_t)C, st));
-    // per-chain aggregates straight into the dense table (bounding box in ct.qs / qe / ts / te)
-    ChainDense cd;
-    cd.qmin = ct.qs; cd.qmax = ct.qe; cd.tmin = ct.ts; cd.tmax = ct.te;
-    cd.sum_matches = A.take<u64>(C); cd.sum_block = A.take<u64>(C);
-    SWG_CUDA(cudaMemsetAsync(cd.qmin, 0xFF, sizeof(u32) * (size_t)C, st));
-    SWG_CUDA(cudaMemsetAsync(cd.tmin, 0xFF, sizeof(u32) * (size_t)C, st));
-    SWG_CUDA(cudaMemsetAsync(cd.qmax, 0, sizeof(u32) * (size_t)C, st));
-    SWG_CUDA(cudaMemsetAsync(cd.tmax, 0, sizeof(u32) * (size_t)C, st));
-    SWG_CUDA(cudaMemsetAsync(cd.sum_matches, 0, sizeof(u64) * (size_t)C, st));
-    SWG_CUDA(cudaMemsetAsync(cd.sum_block, 0, sizeof(u64) * (size_t)C, st));
-    k_chain_aggregate<<<cdiv(n_m, 256), 256, 0, st>>>(srec, srec2, sidx, gid, chain_of, n_m, cd, grp_minidx);
-    lc.n++;
     // exact re-rank: ln(gap) of every chain from the host libm (C values down, C values up)
     double *host_lg = nullptr;
     if (exact_host && C > 0) {
@@ -758,7 +787,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     // only the chains that pass the mass/identity filter take part in the ordering
     u64 *okey = A.take<u64>(C), *okey2 = A.take<u64>(C);
     u32 *oval = A.take<u32>(C), *oval2 = A.take<u32>(C);
-    scan_apply([=] __device__(u32 ci) -> u32 { return ct.pass[ci] ? 1u : 0u; },
+    scan_flags([=] __device__(u32 ci) -> u32 { return ct.pass[ci] ? 1u : 0u; },
                [=] __device__(u32 ci, u32 ex, u32 v) { if (v) { okey[ex] = okey_all[ci]; oval[ex] = ci; } }, C, bsum, d_tot + 3, st, lc);
     u32 C1;
     {   // the count and the counters in one round trip
@@ -787,14 +816,28 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         t_fwd = A.take<u8>(C1);
         double *t_score = A.take<double>(C1);
         const int scoring = cfg.scoring_function;
+        // first appearance (smallest t) of every chromosome pair and genome pair among the filtered chains: two open-addressing
+        // tables with atomicMin (one insert per chain; round 1 sorted the chains twice for this)
+        u32 hcap2 = 1024;
+        while ((u64)hcap2 < (u64)C1 * 2) hcap2 <<= 1;
+        u64 *hk2 = A.take<u64>(hcap2), *hk3 = A.take<u64>(hcap2);
+        u32 *hv2 = A.take<u32>(hcap2), *hv3 = A.take<u32>(hcap2);
+        SWG_CUDA(cudaMemsetAsync(hk2, 0xFF, sizeof(u64) * hcap2, st));
+        SWG_CUDA(cudaMemsetAsync(hk3, 0xFF, sizeof(u64) * hcap2, st));
+        SWG_CUDA(cudaMemsetAsync(hv2, 0xFF, sizeof(u32) * hcap2, st));
+        SWG_CUDA(cudaMemsetAsync(hv3, 0xFF, sizeof(u32) * hcap2, st));
+        const u32 hmask2 = hcap2 - 1;
         launch_for<t_tspace>(C1, st, lc, [=] __device__(u32 t) {
             u32 ci = oc_chain[t];
             u32 q = ct.qid[ci], tt = ct.tid[ci];
             t_qs[t] = ct.qs[ci]; t_qe[t] = ct.qe[ci]; t_ts[t] = ct.ts[ci]; t_te[t] = ct.te[ci];
-            t_c2key[t] = ((u64)q << sb) | tt;
-            t_g2key[t] = ((u64)in.P2[q] << sb) | in.P2[tt];
+            const u64 c2 = ((u64)q << sb) | tt, g2 = ((u64)in.P2[q] << sb) | in.P2[tt];
+            t_c2key[t] = c2;
+            t_g2key[t] = g2;
             t_fwd[t] = ct.fwd[ci];
             t_score[t] = score_fn(scoring, ct.wid[ci], ct.qs[ci], ct.qe[ci], cuda_log);
+            hash_insert_min(hk2, hv2, hmask2, c2, t);
+            hash_insert_min(hk3, hv3, hmask2, g2, t);
         });
         if (exact_host) { // exact re-rank: the chain scores from the host libm as well
             std::vector<double> hw(C1), hs(C1);
@@ -809,16 +852,9 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             SWG_CUDA(cudaMemcpyAsync(t_score, hs.data(), sizeof(double) * (size_t)C1, cudaMemcpyHostToDevice, st));
             SWG_CUDA(cudaStreamSynchronize(st)); // hs lives on this stack frame
         }
-        // first-appearance order of chromosome pairs and genome pairs over the filtered chains
-        u32 *c2min = A.take<u32>(C1), *g2min = A.take<u32>(C1);
+        u32 *g2min = A.take<u32>(C1);
         u64 *sk = A.take<u64>(C1), *sk2 = A.take<u64>(C1);
         u32 *sv = A.take<u32>(C1), *sv2 = A.take<u32>(C1);
-        for (int which = 0; which < 2; which++) {
-            const u64 *src = which == 0 ? t_c2key : t_g2key;
-            launch_for<t_iota>(C1, st, lc, [=] __device__(u32 t) { sk[t] = src[t]; sv[t] = t; });
-            sort_pairs(c, sk, sk2, sv, sv2, C1, 2 * sb);
-            segment_first(c, sk, sv, C1, which == 0 ? c2min : g2min);
-        }
         // scaffold plane sweep (plane_sweep_scaffold.rs:47-251)
         u8 *t_keep = nullptr;
         u64 nq, nt;
@@ -831,24 +867,25 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             general_sweep(c, C1, nullptr, 0, t_c2key, 2 * sb, cb, t_qs, t_qe, t_score, nq, cfg.scaffold_overlap_threshold, k1);
             general_sweep(c, C1, k1, 1, t_c2key, 2 * sb, cb, t_ts, t_te, t_score, nt, cfg.scaffold_overlap_threshold, t_keep);
         }
-        // final order: (g2min, c2min, t): two stable sorts, least significant first (t is the input order)
+        // final order: (g2min, c2min, t) in ONE stable sort (t is the input order); dropped chains sort last
         const int ob = bits_for(C1);
-        launch_for<t_keys_c2min>(C1, st, lc, [=] __device__(u32 t) { sk[t] = c2min[t]; sv[t] = t; });
-        sort_pairs(c, sk, sk2, sv, sv2, C1, ob);
+        if (2 * ob + 1 > 64) throw RangeError{"too many chains for the final order key"};
         {
-            const u32 *svc = sv;
             u64 *skw = sk;
-            launch_for<t_keys_g2min>(C1, st, lc, [=] __device__(u32 u) {
-                u32 t = svc[u];
-                bool kept = t_keep ? t_keep[t] != 0 : true;
-                skw[u] = kept ? (u64)g2min[t] : ((1ull << ob) | 0); // dropped chains sort last
+            u32 *svw = sv;
+            launch_for<t_keys_g2min>(C1, st, lc, [=] __device__(u32 t) {
+                const bool kept = t_keep ? t_keep[t] != 0 : true;
+                const u32 gm = hash_lookup(hk3, hv3, hmask2, t_g2key[t]), cm = hash_lookup(hk2, hv2, hmask2, t_c2key[t]);
+                g2min[t] = gm;
+                skw[t] = kept ? (((u64)gm << ob) | cm) : (1ull << (2 * ob));
+                svw[t] = t;
                 const u32 am = __activemask();
                 const u32 nk = __popc(__ballot_sync(am, kept));
                 if (nk && (threadIdx.x & 31) == (u32)(__ffs(am) - 1)) atomicAdd((unsigned long long *)&ctr[C_KEPT_CHAINS], (unsigned long long)nk);
             });
         }
         read_counters_begin(c); // the kept-chain count is final here; the host picks it up while the sort runs
-        sort_pairs(c, sk, sk2, sv, sv2, C1, ob + 1);
+        sort_pairs(c, sk, sk2, sv, sv2, C1, 2 * ob + 1);
         read_counters_end(c);
         C2 = (u32)c->h_ctr[C_KEPT_CHAINS];
         S.score_near_ties = c->h_ctr[C_NEAR_TIES];
@@ -882,23 +919,37 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         u32 i = sidx[p];
         u32 kk = ct.k[ci];
         if (kk) { status[i] = 1; chain_id[i] = kk; }
-        if (ct.pass[ci]) flags[i] |= F_PREMEM;
+        const u8 add = (u8)((kk ? F_ANCHOR : 0) | (ct.pass[ci] ? F_PREMEM : 0));
+        if (add) flags[i] |= add;
     });
 
     if (!cfg.scaffolds_only && C2 > 0) {
         // ---- K6: inversion capture (paf_filter.rs:535-597) ------------------------------------------
-        // kept '+' chains ordered by (chromosome pair, k)
+        // kept chains in chain_N order u; ik[u] = chromosome pair of a '+' chain, NONE64 for a '-' chain; u_c2[u] = the pair of
+        // either.  The final order groups the chains by chromosome pair, so a pair's chains are one run of u: the table below
+        // maps a pair to the start of its run (atomicMin of u).
         u64 *ik = A.take<u64>(C2), *ik2 = A.take<u64>(C2);
         u32 *iv = A.take<u32>(C2), *iv2 = A.take<u32>(C2);
         u32 *u_qs = A.take<u32>(C2), *u_qe = A.take<u32>(C2), *u_ts = A.take<u32>(C2);
+        u64 *u_c2 = A.take<u64>(C2);
+        u32 hcap4 = 1024;
+        while ((u64)hcap4 < (u64)C2 * 2) hcap4 <<= 1;
+        u64 *hk4 = A.take<u64>(hcap4);
+        u32 *hv4 = A.take<u32>(hcap4);
+        const u32 hmask4 = hcap4 - 1;
+        SWG_CUDA(cudaMemsetAsync(hk4, 0xFF, sizeof(u64) * hcap4, st));
+        SWG_CUDA(cudaMemsetAsync(hv4, 0xFF, sizeof(u32) * hcap4, st));
         {
             const u32 *fin = fin_t;
             launch_for<t_invkeys>(C2, st, lc, [=] __device__(u32 u) {
                 u32 t = fin[u];
                 bool f = t_fwd[t] != 0;
-                ik[u] = f ? t_c2key[t] : NONE64;
+                const u64 c2 = t_c2key[t];
+                ik[u] = f ? c2 : NONE64;
                 iv[u] = u;
+                u_c2[u] = c2;
                 u_qs[u] = t_qs[t]; u_qe[u] = t_qe[t]; u_ts[u] = t_ts[t];
+                hash_insert_min(hk4, hv4, hmask4, c2, u);
             });
         }
         // A chromosome pair that holds a huge group can hold 10^5..10^6 kept chains; walking all of them for every
@@ -918,7 +969,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             scan_apply([=] __device__(u32 u) -> u32 { return ik[u] != NONE64 ? last_b(u) - first_b(u) + 1 : 0u; },
                        [=] __device__(u32 u, u32 ex, u32) { e_off[u] = ex; }, C2, bsum, d_cnt, st, lc);
             u32 *inv_list = A.take<u32>(N);
-            scan_apply([=] __device__(u32 i) -> u32 { return ((flags[i] & F_ALIVE) && in.strand[i] != '+' && status[i] == 0) ? 1u : 0u; },
+            scan_flags([=] __device__(u32 i) -> u32 { return (flags[i] & (F_ALIVE | F_REV | F_ANCHOR)) == (F_ALIVE | F_REV) ? 1u : 0u; },
                        [=] __device__(u32 i, u32 ex, u32 v) { if (v) inv_list[ex] = i; }, N, bsum, d_cnt + 1, st, lc);
             u32 *h2 = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
             SWG_CUDA(cudaMemcpyAsync(h2, d_cnt, 2 * sizeof(u32), cudaMemcpyDeviceToHost, st));
@@ -972,40 +1023,37 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                             if (perp <= G) { best = ch.w; break; }
                         }
                     }
-                    if (best != NONE32) { status[i] = 1; chain_id[i] = best + 1; }
+                    if (best != NONE32) { status[i] = 1; chain_id[i] = best + 1; flags[i] |= F_ANCHOR; }
                 });
             }
         } else {
-        sort_pairs(c, ik, ik2, iv, iv2, C2, 2 * sb + 1);
-        const u32 Cf = C2; // the other chains carry the all-ones key and sort behind every forward chain: no count (and no round trip) needed
         {
+            // the candidates (reverse strand, alive, not yet an anchor: a few per cent of the records) are compacted first, in
+            // no particular order (each is judged on its own); a candidate looks its chromosome pair up and walks the pair's run
+            // of chains in chain_N order — the reference's loop over the kept '+' chains "in order", first hit wins
+            // (paf_filter.rs:553-596)
             const u64 G = cfg.scaffold_gap;
             const u64 *ikc = ik;
-            const u32 *ivc = iv;
-            // compact the candidates first (reverse-strand, alive, not yet an anchor): the binary searches then run
-            // in dense warps instead of stalling every warp that holds a single candidate
             u32 *inv_list = A.take<u32>(N);
             u32 *d_ninv = A.take<u32>(1);
-            scan_apply([=] __device__(u32 i) -> u32 { return ((flags[i] & F_ALIVE) && in.strand[i] != '+' && status[i] == 0) ? 1u : 0u; },
-                       [=] __device__(u32 i, u32 ex, u32 v) { if (v) inv_list[ex] = i; }, N, bsum, d_ninv, st, lc);
-            launch_for<t_inversion>(N, st, lc, [=] __device__(u32 x0) {
-                if (x0 >= *d_ninv) return;
+            scan_flags([=] __device__(u32 i) -> bool { return (flags[i] & (F_ALIVE | F_REV | F_ANCHOR)) == (F_ALIVE | F_REV); },
+                       [=] __device__(u32 i, u32 slot, u32 v) { if (v) inv_list[slot] = i; }, N, bsum, d_ninv, st, lc);
+            launch_for_dev<t_inversion>(d_ninv, c->sm_count, st, lc, [=] __device__(u32 x0) {
                 const u32 i = inv_list[x0];
-                u64 key = ((u64)in.qid[i] << sb) | in.tid[i];
-                u32 lo = 0, hi = Cf;
-                while (lo < hi) { u32 mid = (lo + hi) >> 1; if (ikc[mid] < key) lo = mid + 1; else hi = mid; }
-                if (lo >= Cf || ikc[lo] != key) return;
+                const u64 key = ((u64)in.qid[i] << sb) | in.tid[i];
+                const u32 u0 = hash_lookup(hk4, hv4, hmask4, key);
+                if (u0 == NONE32) return;
                 u64 mqs = in.qs[i], mqe = in.qe[i], mts = in.ts[i], mte = in.te[i];
                 u64 qc = (mqs + mqe) / 2, tc = (mts + mte) / 2;
-                for (u32 x = lo; x < Cf && ikc[x] == key; x++) {
-                    u32 u = ivc[x];
+                for (u32 u = u0; u < C2 && u_c2[u] == key; u++) {
+                    if (ikc[u] == NONE64) continue; // a '-' chain
                     u64 cqs = u_qs[u], cqe = u_qe[u], cts = u_ts[u];
                     u64 ext_s = cqs > G ? cqs - G : 0, ext_e = cqe + G;
                     if (mqe < ext_s || mqs > ext_e) continue;
                     i64 dv = (i64)tc - (i64)qc - ((i64)cts - (i64)cqs);
                     u64 dev = dv < 0 ? (u64)(-dv) : (u64)dv;
                     u64 perp = (u64)__ddiv_rn((double)dev, 1.4142135623730951);
-                    if (perp <= G) { status[i] = 1; chain_id[i] = u + 1; break; }
+                    if (perp <= G) { status[i] = 1; chain_id[i] = u + 1; flags[i] |= F_ANCHOR; break; }
                 }
             });
         }
@@ -1020,7 +1068,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             u64 *ak = A.take<u64>(N), *ak2 = A.take<u64>(N);
             u32 *av = A.take<u32>(N), *av2 = A.take<u32>(N);
             u32 *d_na = A.take<u32>(2);
-            scan_apply([=] __device__(u32 i) -> u32 { return status[i] == 1 ? 1u : 0u; },
+            scan_flags([=] __device__(u32 i) -> bool { return (flags[i] & F_ANCHOR) != 0; },
                        [=] __device__(u32 i, u32 ex, u32 v) {
                            if (!v) return;
                            u64 qc = ((u64)in.qs[i] + in.qe[i]) / 2;
@@ -1053,12 +1101,11 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             }
             // candidates (alive, not an anchor, not a member of a swept-away scaffold), compacted so the searches run dense
             u32 *rlist = A.take<u32>(N);
-            scan_apply([=] __device__(u32 i) -> u32 { return ((flags[i] & F_ALIVE) && status[i] == 0 && !(flags[i] & F_PREMEM)) ? 1u : 0u; },
-                       [=] __device__(u32 i, u32 ex, u32 v) { if (v) rlist[ex] = i; }, N, bsum, d_na + 1, st, lc);
+            scan_flags([=] __device__(u32 i) -> bool { return (flags[i] & (F_ALIVE | F_ANCHOR | F_PREMEM)) == F_ALIVE; },
+                       [=] __device__(u32 i, u32 slot, u32 v) { if (v) rlist[slot] = i; }, N, bsum, d_na + 1, st, lc);
             const u32 *avc = av;
             const u32 *d_nr = d_na + 1;
-            launch_for<t_rescue>(N, st, lc, [=] __device__(u32 x0) {
-                if (x0 >= *d_nr) return;
+            launch_for_dev<t_rescue>(d_nr, c->sm_count, st, lc, [=] __device__(u32 x0) {
                 const u32 i = rlist[x0];
                 const u64 pair = ((u64)in.qid[i] << sb) | in.tid[i];
                 const u64 qc = ((u64)in.qs[i] + in.qe[i]) / 2, tc = ((u64)in.ts[i] + in.te[i]) / 2;
@@ -1367,7 +1414,7 @@ static void do_sweep_core(void *p) {
     c->lc.n++;
     // marked set in ascending index order
     u32 *list = A.take<u32>(n), *bsum = A.take<u32>(scan_temp_u32(n)), *d_cnt = A.take<u32>(2);
-    scan_apply([=] __device__(u32 i) -> u32 { return marked[i] ? 1u : 0u; }, [=] __device__(u32 i, u32 ex, u32 v) { if (v) list[ex] = i; },
+    scan_flags([=] __device__(u32 i) -> u32 { return marked[i] ? 1u : 0u; }, [=] __device__(u32 i, u32 ex, u32 v) { if (v) list[ex] = i; },
                n, bsum, d_cnt, st, c->lc);
     u32 nk = read_u32(c, d_cnt);
     std::vector<u32> host(nk);
@@ -1589,21 +1636,23 @@ int swg_last_chain_units(swg_ctx *c, uint64_t cap, uint32_t *unit_first_index, u
         const u32 C2 = (u32)c->last_n_chains;
         if (C2 == 0) return;
         SWG_CUDA(cudaSetDevice(c->device));
-        // runs of equal A in chain order; the list lives behind the keys in the context-owned arena
-        u32 *run_k = c->keys.take<u32>(C2), *bsum = c->keys.take<u32>(scan_temp_u32(C2)), *tot = c->keys.take<u32>(1);
+        // runs of equal A in chain order; the lists live behind the keys in the context-owned arena.  One round trip: the count
+        // and the first min(cap, C2) entries of both lists travel together.
+        u32 *run_k = c->keys.take<u32>(C2), *run_a = c->keys.take<u32>(C2), *bsum = c->keys.take<u32>(scan_temp_u32(C2)), *tot = c->keys.take<u32>(1);
         const u32 *kA = c->last_keyA;
-        scan_apply([=] __device__(u32 u) -> u32 { return (u == 0 || kA[u] != kA[u - 1]) ? 1u : 0u; },
-                   [=] __device__(u32 u, u32 ex, u32 v) { if (v) run_k[ex] = u; }, C2, bsum, tot, c->stream, c->lc);
-        const u32 nu = read_u32(c, tot);
-        *a->n = nu;
-        if (a->cap < nu || !a->a || !a->k) { if (a->cap == 0) return; throw RangeError{"capacity too small"}; }
-        std::vector<u32> hk(nu);
-        SWG_CUDA(cudaMemcpyAsync(hk.data(), run_k, sizeof(u32) * nu, cudaMemcpyDeviceToHost, c->stream));
-        u32 *d_a = c->keys.take<u32>(nu);
-        launch_for<t_units>(nu, c->stream, c->lc, [=] __device__(u32 r) { d_a[r] = kA[run_k[r]]; });
-        SWG_CUDA(cudaMemcpyAsync(a->a, d_a, sizeof(u32) * nu, cudaMemcpyDeviceToHost, c->stream));
+        scan_flags([=] __device__(u32 u) -> bool { return u == 0 || kA[u] != kA[u - 1]; },
+                   [=] __device__(u32 u, u32 ex, u32 v) { if (v) { run_k[ex] = u + 1; run_a[ex] = kA[u]; } }, C2, bsum, tot, c->stream, c->lc);
+        u32 *h = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
+        SWG_CUDA(cudaMemcpyAsync(h, tot, sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+        const u32 take = (u32)std::min<u64>(a->cap, C2);
+        if (take && a->a && a->k) {
+            SWG_CUDA(cudaMemcpyAsync(a->k, run_k, sizeof(u32) * take, cudaMemcpyDeviceToHost, c->stream)); // chain numbers are 1-based
+            SWG_CUDA(cudaMemcpyAsync(a->a, run_a, sizeof(u32) * take, cudaMemcpyDeviceToHost, c->stream));
+        }
         SWG_CUDA(cudaStreamSynchronize(c->stream));
-        for (u32 r = 0; r < nu; r++) a->k[r] = hk[r] + 1; // chain numbers are 1-based
+        const u32 nu = *h;
+        *a->n = nu;
+        if (a->cap != 0 && (a->cap < nu || !a->a || !a->k)) throw RangeError{"capacity too small"};
     }, &a);
 }
 // chain_id[i] += delta[run of chain_id[i]] for every record with a chain (runs given by their first local chain number,

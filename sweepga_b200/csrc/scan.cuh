@@ -110,6 +110,127 @@ __global__ void __launch_bounds__(SC_THREADS) sc_onepass_kernel(In in, Out out, 
     }
 }
 
+// ---- 0/1 flags: the same one-pass scan with a STRIPED tile (element k*256 + t of the tile belongs to thread t): every load
+// and store of the functors is coalesced, and the in-tile scan is eight ballots + one 64-entry scan instead of a shuffle scan
+// per thread.  in(i) -> bool; out(i, exclusive_prefix, flag).  Used for every stream compaction and head-flag numbering.
+template <class In, class Out>
+__global__ void __launch_bounds__(SC_THREADS) sc_flags_kernel(In in, Out out, u32 n, u64 *status, u32 *tile_counter, u32 *total_out) {
+    static_assert(SC_THREADS == 256 && SC_ITEMS == 8, "striped flag scan: 8 warps x 8 items");
+    __shared__ u32 s_cnt[64]; // [item][warp] counts, then exclusive prefixes in element order
+    __shared__ u32 s_tile, s_excl;
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u); // in-order tile ids
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 base = tile * SC_TILE;
+    u32 m[SC_ITEMS];
+    u32 fbits = 0;
+#pragma unroll
+    for (int k = 0; k < SC_ITEMS; k++) {
+        const u32 i = base + k * SC_THREADS + threadIdx.x;
+        const bool f = i < n && in(i);
+        fbits |= (f ? 1u : 0u) << k;
+        m[k] = __ballot_sync(0xFFFFFFFFu, f);
+        if (lane == 0) s_cnt[k * 8 + warp] = __popc(m[k]);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) { // 64 counts -> exclusive prefixes (two per lane), tile total, look-back
+        const u32 a = s_cnt[2 * lane], b = s_cnt[2 * lane + 1];
+        u32 x = a + b;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 t = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= (u32)o) x += t;
+        }
+        const u32 tot = __shfl_sync(0xFFFFFFFFu, x, 31);
+        s_cnt[2 * lane] = x - a - b;
+        s_cnt[2 * lane + 1] = x - b;
+        if (lane == 0) st_relaxed_u64(&status[tile], (tile == 0 ? SC_FLAG_INCL : SC_FLAG_AGG) | tot);
+        u32 excl = 0;
+        if (tile != 0) {
+            i64 t = (i64)tile - 1;
+            while (true) {
+                const i64 mine = t - lane;
+                const u64 w = mine >= 0 ? ld_relaxed_u64(&status[mine]) : SC_FLAG_INCL;
+                const u32 incl = __ballot_sync(0xFFFFFFFFu, (w & SC_FLAG_INCL) != 0);
+                const u32 ready = __ballot_sync(0xFFFFFFFFu, (w & (SC_FLAG_INCL | SC_FLAG_AGG)) != 0);
+                const u32 upto = incl ? (u32)(__ffs(incl) - 1) : 31u;
+                const u32 need = upto == 31 ? 0xFFFFFFFFu : ((2u << upto) - 1);
+                if ((ready & need) != need) continue;
+                excl += __reduce_add_sync(0xFFFFFFFFu, lane <= upto ? (u32)(w & SC_VAL_MASK) : 0u);
+                if (incl) break;
+                t -= 32;
+            }
+            if (lane == 0) st_relaxed_u64(&status[tile], SC_FLAG_INCL | (u64)(excl + tot));
+        }
+        if (lane == 0) {
+            s_excl = excl;
+            if ((u64)(tile + 1) * SC_TILE >= n) *total_out = excl + tot;
+        }
+    }
+    __syncthreads();
+    const u32 lt = (1u << lane) - 1;
+    const u32 tile_excl = s_excl;
+#pragma unroll
+    for (int k = 0; k < SC_ITEMS; k++) {
+        const u32 i = base + k * SC_THREADS + threadIdx.x;
+        if (i < n) out(i, tile_excl + s_cnt[k * 8 + warp] + __popc(m[k] & lt), (fbits >> k) & 1u);
+    }
+}
+template <class In, class Out>
+static inline void scan_flags(In in, Out out, u32 n, u32 *temp, u32 *total_out, cudaStream_t st, LaunchCounter &lc) {
+    if (n == 0) {
+        SWG_CUDA(cudaMemsetAsync(total_out, 0, sizeof(u32), st));
+        return;
+    }
+    u32 nb = cdiv(n, SC_TILE);
+    SWG_CUDA(cudaMemsetAsync(temp, 0, sizeof(u32) * (2 * (size_t)nb + 4), st));
+    u64 *status = reinterpret_cast<u64 *>(temp);
+    u32 *counter = temp + 2 * (size_t)nb + 2;
+    sc_flags_kernel<<<nb, SC_THREADS, 0, st>>>(in, out, n, status, counter, total_out);
+    lc.n += 1;
+    SWG_CUDA(cudaGetLastError());
+}
+
+// ---- unordered compaction: the elements with pred(i) appended to list[] in no particular order (one counter atomic per
+// 1024-element block).  For lists whose consumers treat every entry independently (candidate lists): ~3x cheaper than the
+// ordered scan above.  *counter must be zero on entry.
+template <class Pred, class Out>
+__global__ void __launch_bounds__(256) k_compact_unordered(Pred pred, Out out, u32 n, u32 *counter) {
+    __shared__ u32 s_w[8][4];
+    __shared__ u32 s_base;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 base = blockIdx.x * 1024;
+    bool f[4];
+    u32 m[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const u32 i = base + k * 256 + threadIdx.x;
+        f[k] = i < n && pred(i);
+        m[k] = __ballot_sync(0xFFFFFFFFu, f[k]);
+        if (lane == 0) s_w[warp][k] = __popc(m[k]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 tot = 0;
+        for (int k = 0; k < 4; k++)
+            for (int w = 0; w < 8; w++) { const u32 t = s_w[w][k]; s_w[w][k] = tot; tot += t; }
+        s_base = tot ? atomicAdd(counter, tot) : 0;
+    }
+    __syncthreads();
+    const u32 lt = (1u << lane) - 1;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (f[k]) out(base + k * 256 + threadIdx.x, s_base + s_w[warp][k] + __popc(m[k] & lt));
+}
+// out(i, slot) is called once per selected element with its slot in [0, *counter)
+template <class Pred, class Out> static inline void compact_unordered(Pred pred, Out out, u32 n, u32 *counter, cudaStream_t st, LaunchCounter &lc) {
+    SWG_CUDA(cudaMemsetAsync(counter, 0, sizeof(u32), st));
+    if (n == 0) return;
+    k_compact_unordered<<<cdiv(n, 1024), 256, 0, st>>>(pred, out, n, counter);
+    lc.n += 1;
+}
+
 // temp: scan_temp_u32(n) u32 (tile status words + tile counter); total_out: device u32
 template <class In, class Out>
 static inline void scan_apply(In in, Out out, u32 n, u32 *temp, u32 *total_out, cudaStream_t st, LaunchCounter &lc) {
