@@ -224,6 +224,12 @@ def pinned_copy(table, with_identity):
         cols[f] = v
         keep.append(t)
     t2 = swg.MappingTable(**cols)
+    if table.n_seq <= 65536:  # 16-bit sequence ids on the wire (swg_mappings.query_id16 / target_id16)
+        def alloc(a):
+            v, t = pin(a)
+            keep.append(t)
+            return v
+        t2 = swg.with_ids16(t2, alloc)
     t2._pins = keep
     st = torch.empty(max(table.n, 1), dtype=torch.uint8, pin_memory=True)
     ch = torch.empty(max(table.n, 1), dtype=torch.int32, pin_memory=True)
@@ -470,6 +476,20 @@ def main():
         wall_e2e = time.perf_counter() - t0
     clk.rows += clk2.rows
     h2d, d2h = int(st2.h2d_bytes), int(st2.d2h_bytes)
+    # the same call with PAGEABLE buffers (what a Rust Vec or a plain numpy array is): pinned staging inside the library
+    pageable_ms = None
+    if world == 1:
+        import copy
+        tp = copy.copy(table)
+        if identity_is_default:
+            tp.identity = None
+        ps, pc = np.zeros(n, np.uint8), np.zeros(n, np.uint32)
+        ctx.filter(cfg, tp, ps, pc)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ctx.filter(cfg, tp, ps, pc)
+        pageable_ms = (time.perf_counter() - t0) / 3 * 1e3
+        assert np.array_equal(ps, out_s) and np.array_equal(pc, out_c), "pageable-buffer call differs"
     if world == 1:
         assert np.array_equal(out_s, status_dev) and np.array_equal(out_c, chain_dev), "e2e and device-resident results differ"
     else:  # the e2e call returns shard-local chain numbers; the device-resident step has renumbered them
@@ -558,7 +578,8 @@ def main():
             "clocks": clk.summary(),
             "e2e": {"value": e2e_v, "unit": "Mmappings/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": t_e2e * 1e3 / args.steps, "wall_ms_per_step": wall_e2e * 1e3 / args.steps,
-                    "identity_column_uploaded": not identity_is_default,
+                    "identity_column_uploaded": not identity_is_default, "ids_16bit": bool(table.n_seq <= 65536),
+                    "pageable_buffers_wall_ms_per_step": pageable_ms,
                     "h2d_gbs_per_rank": h2d / max(st2.ms_h2d, 1e-9) / 1e6},
             "gpu_launches": int(launches),
             "roofline": {"kernel": ("rs_onesweep_kernel<RS_PACKED> (record sort pass on packed words, 8 B read + 8 B written per record)"

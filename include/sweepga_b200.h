@@ -120,6 +120,10 @@ typedef struct swg_mappings {
     uint32_t n_seq;
     const uint32_t *seq_genome_id;
     const uint32_t *seq_genome2_id;
+    /* Optional 16-bit id columns, read when query_id and target_id are both NULL and n_seq <= 65536 (HOST tables only:
+     * swg_filter / swg_upload widen them on the device; swg_filter_device takes 32-bit ids): 2 B instead of 4 B per id. */
+    const uint16_t *query_id16;
+    const uint16_t *target_id16;
 } swg_mappings;
 
 /* Result, replaces HashMap<rank, RecordMeta{chain_id, chain_status}>.
@@ -328,6 +332,20 @@ int swg_shard_plan(const swg_mappings *host_in, int n_shards, uint32_t *shard_of
  * lowest shard): for drivers that know the unit sizes without holding the table (bench.py generates only its shard). */
 int swg_shard_plan_units(uint64_t n_units, const uint64_t *unit_sizes, int n_shards, uint32_t *shard_of_unit,
                          uint64_t *shard_sizes);
+
+/* ---- several GPUs behind one call ----------------------------------------- *
+ * One handle owns a context per device.  swg_multi_filter partitions the HOST table by genome-pair unit (swg_shard_plan),
+ * filters every shard on its device from its own host thread (swg_filter), and merges the shard results into the caller's
+ * arrays with the chain numbers of a single-GPU run (one (A, count) run per unit is all that has to be reconciled, see
+ * swg_last_chain_units).  Results do not depend on the number of devices.  NULL + swg_last_error(NULL) when a device
+ * cannot be initialised.                                                                                              */
+typedef struct swg_multi swg_multi;
+swg_multi *swg_multi_create(const int *devices, int n_devices);
+void swg_multi_destroy(swg_multi *m);
+const char *swg_multi_last_error(const swg_multi *m);
+int swg_multi_device_count(const swg_multi *m);
+int swg_multi_filter(swg_multi *m, const swg_config *cfg, const swg_mappings *host_in, swg_result *host_out,
+                     swg_stats *stats);
 
 const char *swg_version(void);
 

@@ -36,7 +36,7 @@ class swg_mappings(C.Structure):
         ("n", C.c_uint64), ("query_id", u32p), ("target_id", u32p), ("query_start", u32p), ("query_end", u32p),
         ("target_start", u32p), ("target_end", u32p), ("block_length", u32p), ("matches", u32p),
         ("identity", f64p), ("strand", u8p), ("score", f64p), ("n_seq", C.c_uint32),
-        ("seq_genome_id", u32p), ("seq_genome2_id", u32p),
+        ("seq_genome_id", u32p), ("seq_genome2_id", u32p), ("query_id16", C.POINTER(C.c_uint16)), ("target_id16", C.POINTER(C.c_uint16)),
     ]
 
 
@@ -108,6 +108,11 @@ SYMBOLS = [
     ("swg_last_chain_units", C.c_int, [_vp, C.c_uint64, u32p, u32p, u64p]),
     ("swg_renumber_chains_device", C.c_int, [_vp, C.c_uint64, C.c_void_p, C.c_uint64, u32p, C.POINTER(C.c_int64)]),
     ("swg_pack_status_device", C.c_int, [_vp, C.c_uint64, C.c_void_p, C.c_void_p]),
+    ("swg_multi_create", _vp, [C.POINTER(C.c_int), C.c_int]),
+    ("swg_multi_destroy", None, [_vp]),
+    ("swg_multi_last_error", C.c_char_p, [_vp]),
+    ("swg_multi_device_count", C.c_int, [_vp]),
+    ("swg_multi_filter", C.c_int, [_vp, _cfgp, _mapp, _resp, _statp]),
     ("swg_version", C.c_char_p, []),
 ]
 

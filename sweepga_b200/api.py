@@ -213,6 +213,9 @@ class MappingTable(Table):
         for f in ("query_id", "target_id", "query_start", "query_end", "target_start", "target_end", "block_length", "matches",
                   "seq_genome_id", "seq_genome2_id"):
             setattr(m, f, _ptr(getattr(self, f), C.c_uint32))
+        if getattr(self, "ids16", None) is not None:  # (query_id16, target_id16): 2 B per id on the wire (n_seq <= 65536)
+            m.query_id, m.target_id = None, None
+            m.query_id16, m.target_id16 = _ptr(self.ids16[0], C.c_uint16), _ptr(self.ids16[1], C.c_uint16)
         m.identity = _ptr(self.identity, C.c_double) if self.identity is not None else None
         m.strand = _ptr(self.strand, C.c_uint8)
         m.score = _ptr(self.score, C.c_double) if self.score is not None else None
@@ -221,6 +224,17 @@ class MappingTable(Table):
 
 
 # ------------------------------------------------------------------------------------------------
+def with_ids16(table: "MappingTable", alloc=None) -> "MappingTable":
+    """A copy of the table whose swg_mappings view carries 16-bit id columns (n_seq <= 65536).  alloc(array) -> array lets the
+    caller place the two columns (e.g. in pinned memory)."""
+    import copy
+    assert table.n_seq <= 65536
+    t = copy.copy(table)
+    q, tt = table.query_id.astype(np.uint16), table.target_id.astype(np.uint16)
+    t.ids16 = (alloc(q), alloc(tt)) if alloc else (q, tt)
+    return t
+
+
 class Context:
     """swg_ctx: one per GPU.  Raises (never falls back) when no sm_100 device is usable."""
 
@@ -368,6 +382,38 @@ class Context:
         self._check(lib.swg_plane_sweep_core(self._h, n, _ptr(b, C.c_uint32), _ptr(e, C.c_uint32), _ptr(s, C.c_double), _n(max_to_keep),
                                              overlap_threshold, _ptr(out, C.c_uint64), C.byref(cnt)))
         return [int(x) for x in out[: cnt.value]]
+
+
+class MultiContext:
+    """swg_multi: one context per listed GPU behind one call; results identical to a single-GPU call (chain numbers too)."""
+
+    def __init__(self, devices):
+        arr = (C.c_int * len(devices))(*devices)
+        self._h = lib.swg_multi_create(arr, len(devices))
+        if not self._h:
+            raise SwgError(_lib.ERR_CUDA, (lib.swg_last_error(None) or b"").decode())
+
+    def close(self):
+        if self._h:
+            lib.swg_multi_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def filter(self, cfg: FilterConfig, table: MappingTable):
+        n = table.n
+        status, chain_id = np.zeros(n, np.uint8), np.zeros(n, np.uint32)
+        res = _lib.swg_result(_ptr(status, C.c_uint8), _ptr(chain_id, C.c_uint32))
+        stats = _lib.swg_stats()
+        cm, cc = table.to_c(), cfg.to_c()
+        rc = lib.swg_multi_filter(self._h, C.byref(cc), C.byref(cm), C.byref(res), C.byref(stats))
+        if rc != 0:
+            raise SwgError(rc, (lib.swg_multi_last_error(self._h) or b"").decode())
+        return status, chain_id, stats
 
 
 USIZE_MAX = (1 << 64) - 1

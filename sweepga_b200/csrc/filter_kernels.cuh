@@ -307,11 +307,14 @@ __device__ __forceinline__ void bb_best_successor(const uint4 *__restrict__ srec
 // LIST = false: one thread per position, claims only (the 16 B candidate record is not written: clean groups never read it).
 // LIST = true: grid-stride over a list of positions (those of the dirty and huge groups), writes their candidate records
 // for the resolve kernels / the fixed-point iteration; no claims.
+constexpr u32 RES_SMALL = 16;
+constexpr u32 RES_THREAD_MAX = 48; // dirty groups up to this size are walked by one thread, larger ones by a warp
 template <bool LIST>
 __global__ void __launch_bounds__(256)
 k_chain_candidates(const uint4 *__restrict__ srec, const u64 *__restrict__ skey, const u32 *__restrict__ gid,
                    const u32 *__restrict__ gstart, u32 n_groups, u32 n_m, int cb, u64 G, Cand *__restrict__ cand,
-                   u32 *pred, u8 *__restrict__ grp_dirty, const u32 *__restrict__ list, const u32 *__restrict__ n_list_ptr) {
+                   u32 *pred, u32 *grp_dirty, const u32 *__restrict__ list, const u32 *__restrict__ n_list_ptr, u32 fx_min = 0,
+                   u32 *work = nullptr, u32 *work_big = nullptr, u32 *bb_ctr = nullptr) {
     const u32 n_items = LIST ? *n_list_ptr : n_m;
     for (u32 x = blockIdx.x * blockDim.x + threadIdx.x; x < n_items; x += gridDim.x * blockDim.x) {
         const u32 p = LIST ? list[x] : x;
@@ -327,7 +330,20 @@ k_chain_candidates(const uint4 *__restrict__ srec, const u64 *__restrict__ skey,
             Cand c;
             c.d = bd; c.j = bj; c.c0 = c0;
             cand[p] = c;
-        } else if (bj != NONE32 && atomicExch(&pred[bj], p) != NONE32) grp_dirty[g] = 1; // benign race: every writer stores 1
+        } else if (bj != NONE32 && atomicExch(&pred[bj], p) != NONE32 && atomicExch(&grp_dirty[g], 1u) == 0) {
+            // first conflict seen in this group: it goes on a work list of the sequential resolve — the thread walk for small
+            // groups, the warp walk for larger or dense ones (a thread pays one memory round trip per step; with only the dirty
+            // groups listed, the longest walk is the kernel time).  Huge groups have their own path.  The order of a list does
+            // not matter: every group is resolved on its own.
+            const u32 s0 = gstart[g];
+            const u64 size = e - s0;
+            if (size < fx_min) {
+                const u64 span = (u64)srec[e - 1].x - srec[s0].x + 1;
+                const bool big = size > RES_THREAD_MAX || size * G > 64 * span;
+                if (big) work_big[atomicAdd(&bb_ctr[2], 1u)] = g;
+                else work[atomicAdd(&bb_ctr[0], 1u)] = g;
+            }
+        }
     }
 }
 
@@ -357,8 +373,6 @@ k_chain_candidates_groups(const uint4 *__restrict__ srec, const u64 *__restrict_
 // unconstrained arg-min still beat best_pred_score?" (then it is the reference's pick: the global arg-min is eligible, so
 // it is the arg-min over the eligible ones); only a blocked step re-scans its window with the eligibility test.
 // Result: pred[j] = best_pred_idx[j] (paf_filter.rs:847-850), NONE32 = no predecessor.
-constexpr u32 RES_SMALL = 16;
-constexpr u32 RES_THREAD_MAX = 48; // dirty groups up to this size are walked by one thread, larger ones by a warp
 __global__ void __launch_bounds__(128)
 k_chain_resolve(const Cand *__restrict__ cand, const uint4 *__restrict__ srec, const u64 *__restrict__ skey,
                 const u32 *__restrict__ gstart, u32 n_groups, u32 n_m, const u32 *__restrict__ work, const u32 *__restrict__ n_work_ptr,

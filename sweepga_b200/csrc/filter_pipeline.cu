@@ -13,6 +13,7 @@
 //   K6  inversion capture                                paf_filter.rs:535-597
 //   K7  rescue                                           paf_filter.rs:613-732
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <thread>
@@ -623,38 +624,25 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     u32 *pred = A.take<u32>(n_m);    // best_pred_idx
     Cand *cand = nullptr;            // unconstrained arg-min of every position of the groups that are redone (dirty / huge)
     u32 *grp_minidx = A.take<u32>(n_groups); // per GROUP: min original index over its members (first appearance of the group)
-    u8 *grp_dirty = A.take<u8>(n_groups);
+    u32 *grp_dirty = A.take<u32>(n_groups);
     u32 *work = A.take<u32>(n_groups), *work_big = A.take<u32>(n_groups);
     u32 *bb_ctr = A.take<u32>(4); // [0] #ordinary dirty groups, [1] their work counter, [2] #large/dense dirty groups, [3] their work counter
     u32 *root_preset = nullptr;   // roots of the positions of huge groups (fixed-point chaining), NONE32 elsewhere
     SWG_CUDA(cudaMemsetAsync(bb_ctr, 0, 4 * sizeof(u32), st));
-    SWG_CUDA(cudaMemsetAsync(grp_dirty, 0, n_groups, st));
+    SWG_CUDA(cudaMemsetAsync(grp_dirty, 0, sizeof(u32) * (size_t)n_groups, st));
     SWG_CUDA(cudaMemsetAsync(grp_minidx, 0xFF, sizeof(u32) * (size_t)n_groups, st));
     SWG_CUDA(cudaMemsetAsync(pred, 0xFF, sizeof(u32) * (size_t)n_m, st));
     {
+        // claims; a group with a conflict puts itself on a work list: ordinary (thread per group) or large/dense (warp per group:
+        // more than RES_THREAD_MAX positions or an expected window > 64 candidates)
         k_chain_candidates<false><<<cdiv(n_m, 256), 256, 0, st>>>(srec, skey, gid, gstart, n_groups, n_m, gshift, cfg.scaffold_gap, nullptr, pred, grp_dirty,
-                                                                   nullptr, nullptr);
+                                                                   nullptr, nullptr, fx_min, work, work_big, bb_ctr);
         lc.n++;
         stage_mark(c, "ch_worklists");
-        // work lists: the dirty groups (a successor claimed twice), split into ordinary (thread per group) and large/dense
-        // (warp per group: size > 4096 or an expected window > 64 candidates)
-        const u64 Gj = cfg.scaffold_gap;
-        auto is_big = [=] __device__(u32 g) -> bool {
-            const u32 s0 = gstart[g], e0 = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
-            const u64 size = e0 - s0;
-            const u64 span = (u64)srec[e0 - 1].x - srec[s0].x + 1;
-            // a thread walking a group pays one memory round trip per step: beyond a few dozen steps the warp walk (32 steps
-            // prefetched per batch) is the faster one, and with only the dirty groups on the list the longest walk IS the kernel time
-            return size < fx_min && (size > RES_THREAD_MAX || size * Gj > 64 * span);
-        };
         auto is_huge = [=] __device__(u32 g) -> bool {
             const u32 s0 = gstart[g], e0 = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
             return e0 - s0 >= fx_min;
         };
-        scan_flags([=] __device__(u32 g) -> u32 { return (grp_dirty[g] && !is_big(g) && !is_huge(g)) ? 1u : 0u; },
-                   [=] __device__(u32 g, u32 ex, u32 v) { if (v) work[ex] = g; }, n_groups, bsum, bb_ctr, st, lc);
-        scan_flags([=] __device__(u32 g) -> u32 { return (grp_dirty[g] && is_big(g)) ? 1u : 0u; },
-                   [=] __device__(u32 g, u32 ex, u32 v) { if (v) work_big[ex] = g; }, n_groups, bsum, bb_ctr + 2, st, lc);
         // the redone groups need their candidate records: a second candidate pass over the listed groups only (ordinary data: a
         // few hundred groups; writing all 16 B records in the first pass cost more than it saved)
         cand = A.take<Cand>(n_m);
@@ -1286,7 +1274,8 @@ static bool check_maps(swg_ctx *c, const swg_mappings *m) {
     if (!m) { set_err(c, "NULL swg_mappings"); return false; }
     if (m->n == 0) return true;
     if (m->n >= 0x7FFFFFF0ull) { set_err(c, "n too large (must be < 2^31 per context)"); return false; }
-    if (!m->query_id || !m->target_id || !m->query_start || !m->query_end || !m->target_start || !m->target_end ||
+    const bool ids32 = m->query_id && m->target_id, ids16 = !m->query_id && !m->target_id && m->query_id16 && m->target_id16 && m->n_seq <= 65536;
+    if (!(ids32 || ids16) || !m->query_start || !m->query_end || !m->target_start || !m->target_end ||
         !m->block_length || !m->matches || !m->strand || !m->seq_genome_id || !m->seq_genome2_id || m->n_seq == 0) { // identity may be NULL
         set_err(c, "swg_mappings has a NULL column or n_seq == 0");
         return false;
@@ -1301,45 +1290,172 @@ static DevIn make_devin(const swg_mappings *m) {
     return d;
 }
 
-struct UploadArgs { swg_ctx *c; const swg_mappings *in; swg_mappings *dev; swg_result *res; Arena *arena; bool overlap_matches = false; size_t h2d_bytes = 0; };
+// ---- host <-> device copies through pinned pieces (pageable caller memory, file text) --------------------------------------
+// cudaMemcpyAsync from PAGEABLE memory is staged by the driver on one thread (a few GB/s, and it blocks); a Rust Vec or a numpy
+// array is pageable.  Here a team of threads copies 8 MiB pieces into pinned buffers and queues one DMA per piece, so the link
+// stays busy: the path swg_filter takes whenever a caller's column is not page-locked.
+static constexpr size_t PIN_PIECE = (size_t)8 << 20;
+static constexpr int PIN_COUNT = 12;
 
+static void ensure_pinned(swg_ctx *c) {
+    if (!c->pin.empty()) return;
+    for (int i = 0; i < PIN_COUNT; i++) {
+        char *p = nullptr;
+        SWG_CUDA(cudaMallocHost(&p, PIN_PIECE));
+        c->pin.push_back(p);
+        cudaEvent_t e;
+        SWG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->pin_ev.push_back(e);
+    }
+}
+struct CopyJob { const char *src; char *dst; size_t bytes; int fd; }; // fd >= 0: the source is that file (pread), src its mapping
+
+// host -> device on c->copy_stream; returns when every piece is QUEUED (the last DMAs may still be in flight)
+static void staged_h2d(swg_ctx *c, const std::vector<CopyJob> &jobs) {
+    ensure_pinned(c);
+    struct Piece { const CopyJob *j; size_t off, len; };
+    std::vector<Piece> pieces;
+    for (const CopyJob &j : jobs)
+        for (size_t o = 0; o < j.bytes; o += PIN_PIECE) pieces.push_back(Piece{&j, o, std::min(PIN_PIECE, j.bytes - o)});
+    std::atomic<size_t> next{0};
+    std::atomic<int> failed{0};
+    auto worker = [&](int t) {
+        cudaSetDevice(c->device);
+        while (!failed.load()) {
+            const size_t k = next.fetch_add(1);
+            if (k >= pieces.size()) break;
+            const Piece &pc = pieces[k];
+            if (cudaEventSynchronize(c->pin_ev[t]) != cudaSuccess) { failed = 1; break; }
+            bool filled = false;
+            if (pc.j->fd >= 0) { // plain file: pread skips the page-table work of touching a fresh mapping
+                size_t got = 0;
+                while (got < pc.len) {
+                    const ssize_t r = pread(pc.j->fd, c->pin[t] + got, pc.len - got, (off_t)(pc.off + got));
+                    if (r <= 0) break;
+                    got += (size_t)r;
+                }
+                filled = got == pc.len;
+            }
+            if (!filled) memcpy(c->pin[t], pc.j->src + pc.off, pc.len);
+            if (cudaMemcpyAsync(pc.j->dst + pc.off, c->pin[t], pc.len, cudaMemcpyHostToDevice, c->copy_stream) != cudaSuccess ||
+                cudaEventRecord(c->pin_ev[t], c->copy_stream) != cudaSuccess) { failed = 1; break; }
+        }
+    };
+    std::vector<std::thread> th;
+    const int nt = (int)std::min<size_t>(PIN_COUNT, pieces.size());
+    for (int t = 1; t < nt; t++) th.emplace_back(worker, t);
+    if (nt > 0) worker(0);
+    for (auto &t : th) t.join();
+    if (failed.load()) { cudaGetLastError(); throw CudaError{cudaErrorUnknown, __FILE__, __LINE__}; }
+}
+// host text -> device, through the pinned pieces, one reader thread per piece buffer
+static void upload_text(swg_ctx *c, const char *src, int fd, size_t bytes, char *dst) {
+    staged_h2d(c, std::vector<CopyJob>{CopyJob{src, dst, bytes, fd}});
+}
+// device -> pageable host memory: DMA per piece into a pinned buffer, the team copies the pieces out; returns when done.
+// The device data must be complete on c->copy_stream's view (the caller makes copy_stream wait for the producing stream).
+static void staged_d2h(swg_ctx *c, const std::vector<CopyJob> &jobs /* src = device, dst = host */) {
+    ensure_pinned(c);
+    struct Piece { const CopyJob *j; size_t off, len; };
+    std::vector<Piece> pieces;
+    for (const CopyJob &j : jobs)
+        for (size_t o = 0; o < j.bytes; o += PIN_PIECE) pieces.push_back(Piece{&j, o, std::min(PIN_PIECE, j.bytes - o)});
+    std::atomic<size_t> next{0};
+    std::atomic<int> failed{0};
+    auto worker = [&](int t) {
+        cudaSetDevice(c->device);
+        while (!failed.load()) {
+            const size_t k = next.fetch_add(1);
+            if (k >= pieces.size()) break;
+            const Piece &pc = pieces[k];
+            if (cudaMemcpyAsync(c->pin[t], pc.j->src + pc.off, pc.len, cudaMemcpyDeviceToHost, c->copy_stream) != cudaSuccess ||
+                cudaEventRecord(c->pin_ev[t], c->copy_stream) != cudaSuccess || cudaEventSynchronize(c->pin_ev[t]) != cudaSuccess) { failed = 1; break; }
+            memcpy(pc.j->dst + pc.off, c->pin[t], pc.len);
+        }
+    };
+    std::vector<std::thread> th;
+    const int nt = (int)std::min<size_t>(PIN_COUNT, pieces.size());
+    for (int t = 1; t < nt; t++) th.emplace_back(worker, t);
+    if (nt > 0) worker(0);
+    for (auto &t : th) t.join();
+    if (failed.load()) { cudaGetLastError(); throw CudaError{cudaErrorUnknown, __FILE__, __LINE__}; }
+}
+static bool is_pageable(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+struct UploadArgs { swg_ctx *c; const swg_mappings *in; swg_mappings *dev; swg_result *res; Arena *arena; bool overlap_matches = false; size_t h2d_bytes = 0; bool pageable = false; };
+
+struct t_widen;
 static void do_upload(void *p) {
     UploadArgs *a = (UploadArgs *)p;
     swg_ctx *c = a->c;
     const swg_mappings *h = a->in;
     SWG_CUDA(cudaSetDevice(c->device));
     size_t n = h->n;
-    size_t bytes = n * (8 * 4 + (h->identity ? 8 : 0) + 1 + (h->score ? 8 : 0) + 1 + 4) + (size_t)h->n_seq * 8 + 64 * 256;
-    a->h2d_bytes = n * (8 * 4 + (h->identity ? 8 : 0) + 1 + (h->score ? 8 : 0)) + (size_t)h->n_seq * 8;
+    const bool id16 = h->query_id == nullptr; // 16-bit id columns (n_seq <= 65536): 2 B instead of 4 B per id on the wire
+    const size_t idb = id16 ? 2 : 4;
+    size_t bytes = n * (8 * 4 + (id16 ? 4 + 8 : 0) + (h->identity ? 8 : 0) + 1 + (h->score ? 8 : 0) + 1 + 4) + (size_t)h->n_seq * 8 + 64 * 256;
+    a->h2d_bytes = n * (6 * 4 + 2 * idb + (h->identity ? 8 : 0) + 1 + (h->score ? 8 : 0)) + (size_t)h->n_seq * 8;
     a->arena->reserve(bytes);
     Arena &A = *a->arena;
     swg_mappings d = *h;
     cudaStream_t st = c->stream;
-    auto up32 = [&](const u32 *src, size_t cnt) { u32 *dst = A.take<u32>(cnt); SWG_CUDA(cudaMemcpyAsync(dst, src, cnt * 4, cudaMemcpyHostToDevice, st)); return (const u32 *)dst; };
-    d.query_id = up32(h->query_id, n); d.target_id = up32(h->target_id, n);
-    d.query_start = up32(h->query_start, n); d.query_end = up32(h->query_end, n);
-    d.target_start = up32(h->target_start, n); d.target_end = up32(h->target_end, n);
-    d.block_length = up32(h->block_length, n);
-    if (h->identity) { double *dst = A.take<double>(n); SWG_CUDA(cudaMemcpyAsync(dst, h->identity, n * 8, cudaMemcpyHostToDevice, st)); d.identity = dst; }
-    if (h->score) { double *dst = A.take<double>(n); SWG_CUDA(cudaMemcpyAsync(dst, h->score, n * 8, cudaMemcpyHostToDevice, st)); d.score = dst; }
-    { u8 *dst = A.take<u8>(n); SWG_CUDA(cudaMemcpyAsync(dst, h->strand, n, cudaMemcpyHostToDevice, st)); d.strand = dst; }
-    d.seq_genome_id = up32(h->seq_genome_id, h->n_seq);
-    d.seq_genome2_id = up32(h->seq_genome2_id, h->n_seq);
+    // the columns the first kernels need, then `matches` (first read after the sort): with overlap_matches it travels behind the
+    // others on the copy stream, so prefilter, key build and sort run while it is still on the wire
+    std::vector<CopyJob> first, last;
+    auto col = [&](const void *src, size_t cnt, size_t elem, std::vector<CopyJob> &jobs) {
+        char *dst = A.take<char>(cnt * elem);
+        jobs.push_back(CopyJob{(const char *)src, dst, cnt * elem, -1});
+        return (void *)dst;
+    };
+    u16 *q16 = nullptr, *t16 = nullptr;
+    if (id16) { q16 = (u16 *)col(h->query_id16, n, 2, first); t16 = (u16 *)col(h->target_id16, n, 2, first); }
+    else { d.query_id = (const u32 *)col(h->query_id, n, 4, first); d.target_id = (const u32 *)col(h->target_id, n, 4, first); }
+    d.query_start = (const u32 *)col(h->query_start, n, 4, first); d.query_end = (const u32 *)col(h->query_end, n, 4, first);
+    d.target_start = (const u32 *)col(h->target_start, n, 4, first); d.target_end = (const u32 *)col(h->target_end, n, 4, first);
+    d.block_length = (const u32 *)col(h->block_length, n, 4, first);
+    if (h->identity) d.identity = (const double *)col(h->identity, n, 8, first);
+    if (h->score) d.score = (const double *)col(h->score, n, 8, first);
+    d.strand = (const u8 *)col(h->strand, n, 1, first);
+    d.seq_genome_id = (const u32 *)col(h->seq_genome_id, h->n_seq, 4, first);
+    d.seq_genome2_id = (const u32 *)col(h->seq_genome2_id, h->n_seq, 4, first);
     a->res->status = A.take<u8>(n);
     a->res->chain_id = A.take<u32>(n);
-    {   // `matches` goes last; with overlap_matches it travels on the copy stream behind the other columns, so the
-        // kernels that do not need it (prefilter, key build, sort) run while it is still on the wire
-        u32 *dst = A.take<u32>(n);
+    d.matches = (const u32 *)col(h->matches, n, 4, last);
+    bool pageable = false;
+    for (const CopyJob &j : first) pageable |= j.bytes >= (1u << 20) && is_pageable(j.src);
+    pageable |= is_pageable(last[0].src) && last[0].bytes >= (1u << 20);
+    if (pageable) {
+        // pinned pieces on the copy stream (behind whatever the main stream has queued), the main stream waits for them
+        SWG_CUDA(cudaEventRecord(c->ev_copy[0], st));
+        SWG_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_copy[0], 0));
+        staged_h2d(c, first);
+        SWG_CUDA(cudaEventRecord(c->ev_copy[0], c->copy_stream));
+        SWG_CUDA(cudaStreamWaitEvent(st, c->ev_copy[0], 0));
+        staged_h2d(c, last);
+        SWG_CUDA(cudaEventRecord(c->ev_copy[1], c->copy_stream));
+        if (!a->overlap_matches) SWG_CUDA(cudaStreamWaitEvent(st, c->ev_copy[1], 0));
+    } else {
+        for (const CopyJob &j : first) SWG_CUDA(cudaMemcpyAsync(j.dst, j.src, j.bytes, cudaMemcpyHostToDevice, st));
         cudaStream_t cs = st;
         if (a->overlap_matches) {
             SWG_CUDA(cudaEventRecord(c->ev_copy[0], st));
             SWG_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_copy[0], 0));
             cs = c->copy_stream;
         }
-        SWG_CUDA(cudaMemcpyAsync(dst, h->matches, n * 4, cudaMemcpyHostToDevice, cs));
+        SWG_CUDA(cudaMemcpyAsync(last[0].dst, last[0].src, last[0].bytes, cudaMemcpyHostToDevice, cs));
         if (a->overlap_matches) SWG_CUDA(cudaEventRecord(c->ev_copy[1], cs));
-        d.matches = dst;
     }
+    if (id16) { // widen on the device: every kernel reads 32-bit ids
+        u32 *q32 = A.take<u32>(n), *t32 = A.take<u32>(n);
+        launch_for<t_widen>((u32)n, st, c->lc, [=] __device__(u32 i) { q32[i] = q16[i]; t32[i] = t16[i]; });
+        d.query_id = q32;
+        d.target_id = t32;
+    }
+    a->pageable = pageable;
     *a->dev = d;
 }
 
@@ -1557,8 +1673,16 @@ int swg_filter(swg_ctx *c, const swg_config *cfg, const swg_mappings *host_in, s
         }
         SWG_CUDA(cudaEventRecord(c->ev[2], c->stream));
         if (a->in->n) {
-            SWG_CUDA(cudaMemcpyAsync(a->out->status, dres.status, a->in->n, cudaMemcpyDeviceToHost, c->stream));
-            SWG_CUDA(cudaMemcpyAsync(a->out->chain_id, dres.chain_id, a->in->n * 4, cudaMemcpyDeviceToHost, c->stream));
+            if (a->in->n * 5 >= (1u << 20) && (is_pageable(a->out->status) || is_pageable(a->out->chain_id))) {
+                SWG_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev[2], 0));
+                staged_d2h(c, std::vector<CopyJob>{CopyJob{(const char *)dres.status, (char *)a->out->status, (size_t)a->in->n, -1},
+                                                    CopyJob{(const char *)dres.chain_id, (char *)a->out->chain_id, (size_t)a->in->n * 4, -1}});
+                SWG_CUDA(cudaEventRecord(c->ev_copy[0], c->copy_stream));
+                SWG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy[0], 0));
+            } else {
+                SWG_CUDA(cudaMemcpyAsync(a->out->status, dres.status, a->in->n, cudaMemcpyDeviceToHost, c->stream));
+                SWG_CUDA(cudaMemcpyAsync(a->out->chain_id, dres.chain_id, a->in->n * 4, cudaMemcpyDeviceToHost, c->stream));
+            }
         }
         SWG_CUDA(cudaEventRecord(c->ev[3], c->stream));
         SWG_CUDA(cudaStreamSynchronize(c->stream));

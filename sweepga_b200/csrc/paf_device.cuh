@@ -525,57 +525,6 @@ struct DevPaf {
 struct Patch { u32 line, qs, qe, ts, te, blen, matches; u32 kind_strand; double identity; }; // a line re-parsed by the host
 struct FrontEndFallback { std::string why; }; // the device front end declines: the caller uses the host front end
 
-static constexpr size_t PIN_PIECE = (size_t)8 << 20;
-static constexpr int PIN_COUNT = 12;
-
-static void ensure_pinned(swg_ctx *c) {
-    if (!c->pin.empty()) return;
-    for (int i = 0; i < PIN_COUNT; i++) {
-        char *p = nullptr;
-        SWG_CUDA(cudaMallocHost(&p, PIN_PIECE));
-        c->pin.push_back(p);
-        cudaEvent_t e;
-        SWG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        c->pin_ev.push_back(e);
-    }
-}
-
-// host text -> device, through the pinned pieces, one reader thread per piece buffer
-static void upload_text(swg_ctx *c, const char *src, int fd, size_t bytes, char *dst) {
-    ensure_pinned(c);
-    const size_t npieces = (bytes + PIN_PIECE - 1) / PIN_PIECE;
-    std::atomic<size_t> next{0};
-    std::atomic<int> failed{0};
-    auto worker = [&](int t) {
-        cudaSetDevice(c->device);
-        while (!failed.load()) {
-            const size_t k = next.fetch_add(1);
-            if (k >= npieces) break;
-            const size_t o = k * PIN_PIECE, len = std::min(PIN_PIECE, bytes - o);
-            if (cudaEventSynchronize(c->pin_ev[t]) != cudaSuccess) { failed = 1; break; }
-            bool filled = false;
-            if (fd >= 0) { // plain file: pread skips the page-table work of touching a fresh mapping
-                size_t got = 0;
-                while (got < len) {
-                    const ssize_t r = pread(fd, c->pin[t] + got, len - got, (off_t)(o + got));
-                    if (r <= 0) break;
-                    got += (size_t)r;
-                }
-                filled = got == len;
-            }
-            if (!filled) memcpy(c->pin[t], src + o, len);
-            if (cudaMemcpyAsync(dst + o, c->pin[t], len, cudaMemcpyHostToDevice, c->copy_stream) != cudaSuccess ||
-                cudaEventRecord(c->pin_ev[t], c->copy_stream) != cudaSuccess) { failed = 1; break; }
-        }
-    };
-    std::vector<std::thread> th;
-    const int nt = (int)std::min<size_t>(PIN_COUNT, npieces);
-    for (int t = 1; t < nt; t++) th.emplace_back(worker, t);
-    if (nt > 0) worker(0);
-    for (auto &t : th) t.join();
-    if (failed.load()) { cudaGetLastError(); throw CudaError{cudaErrorUnknown, __FILE__, __LINE__}; }
-}
-
 static void tok_read(swg_ctx *c, const u64 *d_tc, u64 *h) {
     SWG_CUDA(cudaMemcpyAsync(h, d_tc, sizeof(u64) * TC_COUNT, cudaMemcpyDeviceToHost, c->stream));
     SWG_CUDA(cudaStreamSynchronize(c->stream));

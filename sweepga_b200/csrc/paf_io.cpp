@@ -617,7 +617,7 @@ int swg_filter_file(swg_ctx *ctx, const swg_config *cfg, const char *in_path, co
 // of the filter: (P(q),P(t)) for the primary sweep and (P2(q),P2(t)) for the scaffold sweep / chain numbering, so
 // sequences are first merged into classes that share a P id OR a P2 id (for 3-field PanSN names P == P2).
 int swg_shard_plan(const swg_mappings *m, int n_shards, uint32_t *shard_of, uint64_t *shard_sizes) {
-    if (!m || n_shards < 1 || (m->n && !shard_of)) return SWG_ERR_ARG;
+    if (!m || n_shards < 1 || (m->n && (!shard_of || !m->query_id || !m->target_id))) return SWG_ERR_ARG; // 32-bit id columns only
     const uint32_t ns = m->n_seq;
     std::vector<uint32_t> cls(ns);
     {

@@ -115,3 +115,35 @@ def test_two_nccl_ranks_reproduce_the_single_gpu_run(tmp_path):
         got_s[idx], got_c[idx] = d["status"], d["chain"]
     assert np.array_equal(got_s, ref_s) and np.array_equal(got_c, ref_c)
     assert int((ref_c > 0).sum()) > 10000
+
+
+@pytest.mark.gpu
+@needs2
+@pytest.mark.parametrize("flags", [{}, dict(num_mappings="1:1", scaffold_filter="1:1"), dict(scaffold_dist="50k")])
+def test_swg_multi_filter_equals_single_gpu(flags):
+    """Several GPUs behind ONE C-ABI call (swg_multi_filter): same status and chain numbers as one GPU."""
+    import sweepga_b200 as swg
+    from sweepga_b200 import synth
+    t = synth.pansn(300_000, seed=17, n_hap=8, with_names=True)
+    cfg = swg.FilterConfig.from_cli(**flags)
+    with swg.Context(0) as ctx:
+        ref_s, ref_c, ref_st = ctx.filter(cfg, t)
+    with swg.MultiContext([0, 1]) as mc:
+        for _ in range(2):
+            s, c, st = mc.filter(cfg, t)
+            assert np.array_equal(s, ref_s) and np.array_equal(c, ref_c)
+            assert st.n_kept == ref_st.n_kept and st.n_chains_kept == ref_st.n_chains_kept
+
+
+@pytest.mark.gpu
+def test_swg_multi_filter_one_device():
+    """The same entry point with a single device (runs on the 1-GPU test box): the split / merge path with one shard."""
+    import oracle_lib
+    import sweepga_b200 as swg
+    from sweepga_b200 import synth
+    t = synth.yeast_like(20000, seed=5)
+    cfg = swg.FilterConfig.from_cli(scaffold_dist="20k")
+    ref = oracle_lib.apply_filters(cfg, t)
+    with swg.MultiContext([0]) as mc:
+        s, c, _ = mc.filter(cfg, t)
+    assert np.array_equal(s, ref[0]) and np.array_equal(c, ref[1])
