@@ -6,8 +6,13 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import sweepga_b200 as swg
 from sweepga_b200 import synth
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 20_000_000
+n = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 20_000_000
 t = synth.pansn(n, seed=3)
+if "--shuffle" in sys.argv:  # the generator emits records grouped by genome pair and position-ordered, like an aligner; this
+    # is the same table in random row order (sort scatter, gathers and first-appearance tables lose their locality)
+    t = t.take(np.random.default_rng(11).permutation(t.n))
+    print("rows shuffled")
+n = t.n
 ctx = swg.Context(0)
 dev, dres = ctx.upload(t)
 for name, flags in (("defaults", {}), ("rescue 100k", dict(scaffold_dist="100k")), ("1:1 / 1:1", dict(num_mappings="1:1", scaffold_filter="1:1")),

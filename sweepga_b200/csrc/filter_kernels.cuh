@@ -88,9 +88,16 @@ __device__ __forceinline__ double rec_identity(const DevIn &in, u32 i) {
     return __ddiv_rn((double)in.matches[i], (double)(b > 1 ? b : 1));
 }
 
+// KEYS: also writes the chain sort key of every record in the "gap layout" ((query, target, strand) << 32 | query_start) —
+// the width of the coordinate field is only known after this kernel (rs_squeeze closes the gap inside the sort) — and the
+// payload (the record index): the key pass of k_chain_keys without a second read of the columns.  Valid when the primary
+// sweep is the closed form and no alive record has an empty interval (kept == alive); the host falls back to k_chain_keys
+// otherwise.
+template <bool KEYS>
 __global__ void __launch_bounds__(256) k_prefilter(DevIn in, u64 min_len, double min_id, int keep_self, u8 *__restrict__ flags,
                                                    u64 *__restrict__ ctr, u64 *hk, u32 *hv, u32 hmask,
-                                                   uint4 *__restrict__ rec4) {
+                                                   uint4 *__restrict__ rec4, int sb = 0, u64 *__restrict__ keys = nullptr,
+                                                   u32 *__restrict__ vals = nullptr) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     bool alive = false, zq = false, zt = false, bad = false;
     u32 maxc = 0;
@@ -112,7 +119,13 @@ __global__ void __launch_bounds__(256) k_prefilter(DevIn in, u64 min_len, double
         zt = alive && te == ts;
         maxc = alive ? max(qe, te) : 0u;
         if (alive) g = ((u64)in.P[q] << 32) | in.P[t];
-        flags[i] = (u8)((alive ? F_ALIVE : 0) | (zq ? F_ZLQ : 0) | (zt ? F_ZLT : 0) | (in.strand[i] != '+' ? F_REV : 0));
+        const bool rev = in.strand[i] != '+';
+        flags[i] = (u8)((alive ? F_ALIVE : 0) | (zq ? F_ZLQ : 0) | (zt ? F_ZLT : 0) | (rev ? F_REV : 0));
+        if (KEYS) {
+            const u64 grp = alive ? ((((u64)q << sb) | t) << 1 | (rev ? 1 : 0)) : ((1ull << (2 * sb + 1)) - 1); // dead: all ones, sorts last
+            keys[i] = (grp << 32) | (alive ? qs : 0xFFFFFFFFu);
+            vals[i] = i;
+        }
         // packed copy for the post-sort gather: one 16 B sector instead of four 4 B gathers.  `matches` is NOT touched
         // here (unless identity has to be derived from it): it is first read by the gather after the sort, so its
         // host-to-device copy can overlap K0 + sort.
@@ -308,7 +321,7 @@ __device__ __forceinline__ void bb_best_successor(const uint4 *__restrict__ srec
 // LIST = true: grid-stride over a list of positions (those of the dirty and huge groups), writes their candidate records
 // for the resolve kernels / the fixed-point iteration; no claims.
 constexpr u32 RES_SMALL = 16;
-constexpr u32 RES_THREAD_MAX = 48; // dirty groups up to this size are walked by one thread, larger ones by a warp
+constexpr u32 RES_THREAD_MAX = 16; // dirty groups up to this size are walked by one thread (from registers), larger ones by a warp
 template <bool LIST>
 __global__ void __launch_bounds__(256)
 k_chain_candidates(const uint4 *__restrict__ srec, const u64 *__restrict__ skey, const u32 *__restrict__ gid,
@@ -322,6 +335,8 @@ k_chain_candidates(const uint4 *__restrict__ srec, const u64 *__restrict__ skey,
         const bool fwd = ((skey[p] >> cb) & 1) == 0;
         const u32 g = gid[p];
         const u32 e = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
+        if (!LIST && fx_min != NONE32 && e - gstart[g] >= fx_min) continue; // huge group: the fixed-point iteration searches itself
+                                                                              // (the host passes NONE32 when no group is huge)
         u64 bd;
         u32 bj;
         u32 c0;
@@ -721,6 +736,9 @@ k_chain_resolve_warp(const Cand *__restrict__ cand, const uint4 *__restrict__ sr
 // Also counts the positions that belong to huge groups (size >= fx_min): those are chained by the fixed-point iteration
 // of chain_fixpoint.cuh instead of a sequential walk.
 constexpr u32 FX_MIN_GROUP = 16384;
+// ESTIMATE = false: only the huge-group count (two coalesced reads per group); the work estimate needs two gathers per group
+// and is computed only when SWG_MAX_PAIR_EVALS asks for it.
+template <bool ESTIMATE>
 __global__ void __launch_bounds__(256)
 k_chain_work_estimate(const uint4 *__restrict__ rec4, SortedIdx sidx, const u32 *__restrict__ gstart, const u32 *__restrict__ n_groups_ptr, u32 n_m,
                       u64 G, u32 fx_min, u64 *ctr) {
@@ -730,7 +748,7 @@ k_chain_work_estimate(const uint4 *__restrict__ rec4, SortedIdx sidx, const u32 
         const u32 s = gstart[g], e = (g + 1 < n_groups) ? gstart[g + 1] : n_m;
         const u64 size = e - s;
         if (size >= fx_min) atomicAdd((unsigned long long *)&ctr[C_HUGE], (unsigned long long)size); // a handful of groups at most
-        if (size > 1) {
+        if (ESTIMATE && size > 1) {
             const u64 span = (u64)rec4[sidx[e - 1]].x - rec4[sidx[s]].x + 1; // (runs before the gather: two reads per group)
             u64 win = size * G / span + 1; // expected candidates per step
             if (win > size) win = size;

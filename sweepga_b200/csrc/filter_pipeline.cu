@@ -119,6 +119,7 @@ namespace swg {
 struct Knobs {
     bool force_wide = false, sweep_no_flat = false, no_fixpoint = false, inv_grid = false, inv_no_grid = false, cuda_log = false;
     bool pairs_sort = false;   // SWG_SORT_PAIRS=1: the record sort keeps (key, payload) pairs through every pass
+    bool no_fused_keys = false; // SWG_NO_FUSED_KEYS=1: the chain sort keys always come from k_chain_keys
     u32 fixpoint_min = 0;      // 0 = default
     double max_pair_evals = 0; // 0 = no limit (SWG_MAX_PAIR_EVALS)
     int sweep_mult = 8, resolve_mult = 4;
@@ -133,6 +134,7 @@ static Knobs read_knobs() {
     k.inv_grid = on("SWG_INV_GRID");
     k.inv_no_grid = on("SWG_INV_NO_GRID");
     k.pairs_sort = on("SWG_SORT_PAIRS");
+    k.no_fused_keys = on("SWG_NO_FUSED_KEYS");
     if (const char *v = getenv("SWG_LOG_IMPL")) k.cuda_log = strcmp(v, "cuda") == 0;
     if (const char *v = getenv("SWG_FIXPOINT_MIN")) k.fixpoint_min = (u32)atoi(v);
     if (const char *v = getenv("SWG_MAX_PAIR_EVALS")) k.max_pair_evals = atof(v);
@@ -460,7 +462,22 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     uint4 *rec4 = nullptr;
     if (cfg.scaffold_gap != 0) rec4 = A.take<uint4>(N);
     if (ev_matches && !in.identity && !(cfg.min_identity <= 0.0)) SWG_CUDA(cudaStreamWaitEvent(st, ev_matches, 0)); // identity is derived from `matches`
-    k_prefilter<<<cdiv(N, 256), 256, 0, st>>>(in, cfg.min_block_length, cfg.min_identity, cfg.keep_self, flags, ctr, hk, hv, hcap - 1, rec4);
+    // The chain sort keys can be written by the same pass when the primary sweep is the closed form (no per-axis limit): then
+    // kept == alive unless an alive record has an empty interval (checked below; k_chain_keys redoes the keys in that case).
+    const int sb0 = bits_for(in.n_seq);
+    u64 qlim0, tlim0;
+    switch (cfg.mapping_filter_mode) {
+    case SWG_ONE_TO_ONE: qlim0 = tlim0 = 1; break;
+    case SWG_ONE_TO_MANY: qlim0 = cfg.mapping_max_per_query != SWG_NO_LIMIT ? cfg.mapping_max_per_query : 1; tlim0 = cfg.mapping_max_per_target; break;
+    default: qlim0 = cfg.mapping_max_per_query; tlim0 = cfg.mapping_max_per_target;
+    }
+    bool fused_keys = cfg.scaffold_gap != 0 && qlim0 == SWG_KEEP_ALL && tlim0 == SWG_KEEP_ALL && !K.force_wide && !K.pairs_sort &&
+                      2 * sb0 + 1 <= 32 && !K.no_fused_keys;
+    u64 *keys = nullptr, *keys2 = nullptr;
+    u32 *vals = nullptr, *vals2 = nullptr;
+    if (cfg.scaffold_gap != 0) { keys = A.take<u64>(N); keys2 = A.take<u64>(N); vals = A.take<u32>(N); vals2 = A.take<u32>(N); }
+    if (fused_keys) k_prefilter<true><<<cdiv(N, 256), 256, 0, st>>>(in, cfg.min_block_length, cfg.min_identity, cfg.keep_self, flags, ctr, hk, hv, hcap - 1, rec4, sb0, keys, vals);
+    else k_prefilter<false><<<cdiv(N, 256), 256, 0, st>>>(in, cfg.min_block_length, cfg.min_identity, cfg.keep_self, flags, ctr, hk, hv, hcap - 1, rec4);
     lc.n++;
     read_counters(c);
     if (c->h_ctr[C_BAD])
@@ -518,18 +535,21 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
 
     // ---- K1 + sort + K2: group by (q,t,strand), stable order by query_start ------------------------
     stage_mark(c, "keys+sort");
-    u64 *keys = A.take<u64>(N), *keys2 = A.take<u64>(N);
-    u32 *vals = A.take<u32>(N), *vals2 = A.take<u32>(N);
     int gshift = cb; // group id of a sorted position = skey >> gshift
     const int kb = 2 * sb + 1 + cb;
     const bool wide = kb > 64 || K.force_wide;
     SortedIdx sidx{nullptr, nullptr, 0};
     const u64 *skey = nullptr;
     if (!wide) {
-        k_chain_keys<<<cdiv(N, 256), 256, 0, st>>>(in, flags, keep_q, keep_t, sb, cb, keys, vals, ctr);
-        lc.n++;
-        read_counters_begin(c); // the survivor count is final here; the host picks it up while the sort runs
         const int ib = bits_for(N - 1);
+        // the keys written by k_prefilter<true> stand if no sweep ran (kept == alive) and every digit consumed up to the packing
+        // pass lies inside the coordinate field (the gap of the layout is closed by the packing pass)
+        fused_keys = fused_keys && !keep_q && !keep_t && zlq == 0 && zlt == 0 && rs_packed_c0(kb, ib) > 0 && rs_packed_c0(kb, ib) <= cb;
+        if (!fused_keys) {
+            k_chain_keys<<<cdiv(N, 256), 256, 0, st>>>(in, flags, keep_q, keep_t, sb, cb, keys, vals, ctr);
+            lc.n++;
+        }
+        read_counters_begin(c); // the survivor count is final here; the host picks it up while the sort runs
         if (K.pairs_sort) {
             sort_pairs(c, keys, keys2, vals, vals2, N, kb, true);
             skey = keys;
@@ -539,7 +559,8 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             // move 8 B per record instead of 12 B; the result holds the index and the key from bit c0 upwards
             RadixSortPlan p = rs_plan(N, 0, kb);
             void *tmp = A.take<char>(p.temp_bytes);
-            const PackedSort ps = rs_sort_packed(N, kb, ib, keys, keys2, vals, vals2, tmp, p, st, c->sm_count, lc, c->ev_sort[0], c->ev_sort[1]);
+            const PackedSort ps = rs_sort_packed(N, kb, ib, keys, keys2, vals, vals2, tmp, p, st, c->sm_count, lc, c->ev_sort[0], c->ev_sort[1],
+                                                 fused_keys ? cb : 0);
             c->sort_passes = ps.timed_passes; // the events bracket the packed-word passes
             c->sort_pairs = N;
             c->sort_bytes_per_pair = ps.timed_bytes_per_pair;
@@ -567,6 +588,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                 if (cnt && (threadIdx.x & 31) == (u32)(__ffs(am) - 1)) atomicAdd((unsigned long long *)&ctr[C_KEPT_M], (unsigned long long)cnt);
             });
         }
+        fused_keys = false;
         sort_pairs(c, keys, keys2, vals, vals2, N, cb, true);
         {
             u64 *kk = keys;
@@ -579,7 +601,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         sidx.v = vals;
         read_counters(c);
     }
-    const u32 n_m = (u32)c->h_ctr[C_KEPT_M];
+    const u32 n_m = fused_keys ? (u32)n_alive : (u32)c->h_ctr[C_KEPT_M]; // fused keys: kept == alive (k_chain_keys did not count)
     S.n_after_sweep = n_m;
     S.score_near_ties = c->h_ctr[C_NEAR_TIES];
     if (n_m == 0) { finish(); return; }
@@ -601,7 +623,8 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     {   // group count, positions in huge groups and a rough count of the candidate evaluations ahead (SWG_MAX_PAIR_EVALS, if
         // set, refuses an input beyond it; by default nothing is refused: the reference runs such piles to completion too).
         // The host picks the numbers up while the gather below runs.
-        k_chain_work_estimate<<<(u32)c->sm_count * 8, 256, 0, st>>>(rec4, sidx, gstart, d_tot, n_m, cfg.scaffold_gap, fx_min, ctr);
+        if (K.max_pair_evals > 0) k_chain_work_estimate<true><<<(u32)c->sm_count * 8, 256, 0, st>>>(rec4, sidx, gstart, d_tot, n_m, cfg.scaffold_gap, fx_min, ctr);
+        else k_chain_work_estimate<false><<<(u32)c->sm_count * 8, 256, 0, st>>>(rec4, sidx, gstart, d_tot, n_m, cfg.scaffold_gap, fx_min, ctr);
         lc.n++;
         u32 *h = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
         SWG_CUDA(cudaMemcpyAsync(h, d_tot, sizeof(u32), cudaMemcpyDeviceToHost, st)); // group count and estimate in one round trip
@@ -636,7 +659,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         // claims; a group with a conflict puts itself on a work list: ordinary (thread per group) or large/dense (warp per group:
         // more than RES_THREAD_MAX positions or an expected window > 64 candidates)
         k_chain_candidates<false><<<cdiv(n_m, 256), 256, 0, st>>>(srec, skey, gid, gstart, n_groups, n_m, gshift, cfg.scaffold_gap, nullptr, pred, grp_dirty,
-                                                                   nullptr, nullptr, fx_min, work, work_big, bb_ctr);
+                                                                   nullptr, nullptr, c->h_ctr[C_HUGE] ? fx_min : NONE32, work, work_big, bb_ctr);
         lc.n++;
         stage_mark(c, "ch_worklists");
         auto is_huge = [=] __device__(u32 g) -> bool {

@@ -46,8 +46,12 @@ constexpr u32 RS_FLAG_INCL = 2u << 30; // inclusive prefix available
 constexpr u32 RS_VAL_MASK = (1u << 30) - 1;
 
 // ---- histogram of all passes in one read --------------------------------------------------
+// gap_cb != 0: the keys are in the "gap layout" (high field << 32) | (low field < 2^gap_cb) — written before the width of the
+// low field was known — and are squeezed to (high << gap_cb) | low on the fly (rs_squeeze); the sort then behaves as if the
+// contiguous key had been stored.
+__device__ __forceinline__ u64 rs_squeeze(u64 k, int gap_cb) { return ((k >> 32) << gap_cb) | (u64)(u32)k; }
 __global__ void __launch_bounds__(512) rs_histogram_kernel(const u64 *__restrict__ keys, u32 n, int begin_bit, int passes,
-                                                           u32 *__restrict__ hist /*[passes][256]*/) {
+                                                           u32 *__restrict__ hist /*[passes][256]*/, int gap_cb = 0) {
     __shared__ u32 sh[RS_MAX_PASSES * RS_RADIX];
     for (int i = threadIdx.x; i < passes * RS_RADIX; i += blockDim.x) sh[i] = 0;
     __syncthreads();
@@ -60,6 +64,7 @@ __global__ void __launch_bounds__(512) rs_histogram_kernel(const u64 *__restrict
         const u32 i = wbase + lane;
         const bool ok = i < n2;
         ulonglong2 v = ok ? k2[i] : make_ulonglong2(0, 0);
+        if (gap_cb) { v.x = rs_squeeze(v.x, gap_cb); v.y = rs_squeeze(v.y, gap_cb); }
         u64 a = v.x >> begin_bit, b = v.y >> begin_bit;
 #pragma unroll
         for (int p = 0; p < RS_MAX_PASSES; p++) {
@@ -78,7 +83,7 @@ __global__ void __launch_bounds__(512) rs_histogram_kernel(const u64 *__restrict
         }
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-        u64 a = keys[n - 1] >> begin_bit;
+        u64 a = (gap_cb ? rs_squeeze(keys[n - 1], gap_cb) : keys[n - 1]) >> begin_bit;
         for (int p = 0; p < passes; p++) atomicAdd(&sh[p * RS_RADIX + ((u32)(a >> (p * RS_BITS)) & (RS_RADIX - 1))], 1u);
     }
     __syncthreads();
@@ -133,7 +138,7 @@ typedef RsSmemT<RS_PAIRS> RsSmem;
 template <bool FULL, int MODE>
 __device__ __forceinline__ void rs_onesweep_tile(RsSmemT<MODE> &s, const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out,
                                                  const u32 *__restrict__ vals_in, u32 *__restrict__ vals_out, u32 n, int shift,
-                                                 int pack_drop, int pack_ib,
+                                                 int pack_drop, int pack_ib, int pack_gap,
                                                  const u32 *__restrict__ digit_base, u32 *tile_status, u32 tile) {
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u64 tile_base = (u64)tile * RS_TILE;
@@ -234,7 +239,8 @@ __device__ __forceinline__ void rs_onesweep_tile(RsSmemT<MODE> &s, const u64 *__
                 s.stage_k[pos] = key[i];
                 s.stage_v[pos] = val[MODE == RS_PACKED ? 0 : i];
             } else if (MODE == RS_PACK) {
-                s.stage_k[pos] = ((key[i] >> pack_drop) << pack_ib) | (u64)val[MODE == RS_PACKED ? 0 : i];
+                const u64 kk = pack_gap ? rs_squeeze(key[i], pack_gap) : key[i]; // (digits consumed so far lie below the gap)
+                s.stage_k[pos] = ((kk >> pack_drop) << pack_ib) | (u64)val[MODE == RS_PACKED ? 0 : i];
                 s.stage_d[pos] = (u8)d;
             } else {
                 s.stage_k[pos] = key[i];
@@ -297,7 +303,7 @@ __device__ __forceinline__ void rs_onesweep_tile(RsSmemT<MODE> &s, const u64 *__
 template <int MODE>
 __global__ void __launch_bounds__(RS_THREADS, MODE == RS_PACKED ? SWG_RS_MINBLOCKS_PACKED : SWG_RS_MINBLOCKS)
 rs_onesweep_kernel(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out, const u32 *__restrict__ vals_in,
-                   u32 *__restrict__ vals_out, u32 n, int shift, int pack_drop, int pack_ib, const u32 *__restrict__ digit_base,
+                   u32 *__restrict__ vals_out, u32 n, int shift, int pack_drop, int pack_ib, int pack_gap, const u32 *__restrict__ digit_base,
                    u32 *tile_status /*[tiles][256]*/, u32 *tile_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RsSmemT<MODE> &s = *reinterpret_cast<RsSmemT<MODE> *>(smem_raw);
@@ -307,9 +313,9 @@ rs_onesweep_kernel(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out, 
     __syncthreads();
     const u32 tile = s.tile;
     if ((u64)(tile + 1) * RS_TILE <= (u64)n)
-        rs_onesweep_tile<true, MODE>(s, keys_in, keys_out, vals_in, vals_out, n, shift, pack_drop, pack_ib, digit_base, tile_status, tile);
+        rs_onesweep_tile<true, MODE>(s, keys_in, keys_out, vals_in, vals_out, n, shift, pack_drop, pack_ib, pack_gap, digit_base, tile_status, tile);
     else
-        rs_onesweep_tile<false, MODE>(s, keys_in, keys_out, vals_in, vals_out, n, shift, pack_drop, pack_ib, digit_base, tile_status, tile);
+        rs_onesweep_tile<false, MODE>(s, keys_in, keys_out, vals_in, vals_out, n, shift, pack_drop, pack_ib, pack_gap, digit_base, tile_status, tile);
 }
 
 // ---- host driver --------------------------------------------------------------------------
@@ -358,7 +364,7 @@ static inline void rs_sort_pairs(const RadixSortPlan &p, u64 *&keys, u64 *&keys_
     if (ev_begin) SWG_CUDA(cudaEventRecord(ev_begin, st));
     for (int pass = 0; pass < p.passes; pass++) {
         rs_onesweep_kernel<RS_PAIRS><<<p.tiles, RS_THREADS, sizeof(RsSmem), st>>>(keys, keys_alt, vals, vals_alt, p.n,
-                                                                                  p.begin_bit + pass * RS_BITS, 0, 0, hist + pass * RS_RADIX,
+                                                                                  p.begin_bit + pass * RS_BITS, 0, 0, 0, hist + pass * RS_RADIX,
                                                                                   status + (size_t)pass * p.tiles * RS_RADIX, counters + pass);
         lc.n += 1;
         u64 *tk = keys; keys = keys_alt; keys_alt = tk;
@@ -387,7 +393,7 @@ static inline int rs_packed_c0(int key_bits, int ib) {
 // payload < 2^ib and key_bits <= RS_MAX_PASSES * RS_BITS.  ev[2k], ev[2k+1] (optional): events around pass k.
 static inline PackedSort rs_sort_packed(u32 n, int key_bits, int ib, u64 *keys, u64 *keys_alt, u32 *vals, u32 *vals_alt, void *temp,
                                         const RadixSortPlan &p, cudaStream_t st, int sm_count, LaunchCounter &lc,
-                                        cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_end = nullptr) {
+                                        cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_end = nullptr, int gap_cb = 0) {
     PackedSort r;
     r.ib = ib;
     r.c0 = rs_packed_c0(key_bits, ib);
@@ -398,7 +404,7 @@ static inline PackedSort rs_sort_packed(u32 n, int key_bits, int ib, u64 *keys, 
     u32 *status = counters + 16;
     SWG_CUDA(cudaMemsetAsync(temp, 0, p.temp_bytes, st));
     u32 hgrid = (u32)min((u64)sm_count * 4, (u64)cdiv(p.n / 2 + 1, 512));
-    rs_histogram_kernel<<<hgrid, 512, 0, st>>>(keys, p.n, 0, p.passes, hist);
+    rs_histogram_kernel<<<hgrid, 512, 0, st>>>(keys, p.n, 0, p.passes, hist, gap_cb);
     rs_scan_hist_kernel<<<p.passes, RS_RADIX, 0, st>>>(hist);
     lc.n += 2;
     // passes [0, pk) move pairs, pass pk packs, the rest move packed words.  c0 == 0: a pass "-1" would pack, so the first
@@ -414,15 +420,15 @@ static inline PackedSort rs_sort_packed(u32 n, int key_bits, int ib, u64 *keys, 
         const u32 *db = hist + pass * RS_RADIX;
         u32 *stt = status + (size_t)pass * p.tiles * RS_RADIX;
         if (pass < pk) {
-            rs_onesweep_kernel<RS_PAIRS><<<p.tiles, RS_THREADS, sizeof(RsSmemT<RS_PAIRS>), st>>>(keys, keys_alt, vals, vals_alt, n, pass * RS_BITS, 0, 0,
+            rs_onesweep_kernel<RS_PAIRS><<<p.tiles, RS_THREADS, sizeof(RsSmemT<RS_PAIRS>), st>>>(keys, keys_alt, vals, vals_alt, n, pass * RS_BITS, 0, 0, 0,
                                                                                               db, stt, counters + pass);
             u32 *tv = vals; vals = vals_alt; vals_alt = tv;
         } else if (pass == pk) {
             rs_onesweep_kernel<RS_PACK><<<p.tiles, RS_THREADS, sizeof(RsSmemT<RS_PACK>), st>>>(keys, keys_alt, vals, nullptr, n, pass * RS_BITS, r.c0, ib,
-                                                                                            db, stt, counters + pass);
+                                                                                            gap_cb, db, stt, counters + pass);
         } else {
             rs_onesweep_kernel<RS_PACKED><<<p.tiles, RS_THREADS, sizeof(RsSmemT<RS_PACKED>), st>>>(keys, keys_alt, nullptr, nullptr, n,
-                                                                                                ib + pass * RS_BITS - r.c0, 0, 0, db, stt, counters + pass);
+                                                                                                ib + pass * RS_BITS - r.c0, 0, 0, 0, db, stt, counters + pass);
         }
         lc.n += 1;
         u64 *tk = keys; keys = keys_alt; keys_alt = tk;

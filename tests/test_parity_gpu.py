@@ -318,3 +318,20 @@ def test_wide_key_paths(ctx, yeast, case, monkeypatch):
         t = fuzz_table(seed, 400)
         check(ctx, swg.FilterConfig.from_cli(num_mappings="1:1", scaffold_filter="2:2", scaffold_jump="200", scaffold_mass="0",
                                             scaffold_dist="300"), t, f"wide fuzz{seed}")
+
+
+@pytest.mark.parametrize("knob", ["SWG_SORT_PAIRS", "SWG_NO_FUSED_KEYS", None])
+def test_record_sort_variants(ctx, yeast, knob, monkeypatch):
+    """The three forms of the record sort give the same result: (default) keys written by the prefilter pass in the gap layout
+    and packed into one word by the third pass; keys from k_chain_keys, packed; key + payload pairs through every pass.
+    The default only takes the fused-key path when the key plus the index exceed 64 bits, i.e. on a large table: the PanSN
+    table below (12 + 12 + 1 + 28 key bits, 21 index bits) qualifies, the yeast table exercises the other branch."""
+    if knob:
+        monkeypatch.setenv(knob, "1")
+    big = synth.pansn(1_200_000, seed=29, with_names=False)
+    for cfg in (swg.FilterConfig(), swg.FilterConfig.from_cli(scaffold_dist="100k"), swg.FilterConfig.from_cli(scaffold_filter="1:1")):
+        check(ctx, cfg, big, f"pansn 1.2M {knob}")
+    check(ctx, swg.FilterConfig(), yeast, f"yeast {knob}")
+    # zero-length intervals among the alive records: the fused keys are discarded and rebuilt after the sweep
+    t = fuzz_table(5, 3000)
+    check(ctx, swg.FilterConfig.from_cli(scaffold_jump="200", scaffold_mass="0"), t, f"fuzz {knob}")
