@@ -7,6 +7,7 @@
 #pragma once
 #include "common.cuh"
 #include "scan.cuh"
+#include "group_sort.cuh"
 #include "glibc_log.cuh"
 
 namespace swg {

@@ -120,6 +120,8 @@ struct Knobs {
     bool force_wide = false, sweep_no_flat = false, no_fixpoint = false, inv_grid = false, inv_no_grid = false, cuda_log = false;
     bool pairs_sort = false;   // SWG_SORT_PAIRS=1: the record sort keeps (key, payload) pairs through every pass
     bool no_fused_keys = false; // SWG_NO_FUSED_KEYS=1: the chain sort keys always come from k_chain_keys
+    bool no_group_sort = false; // SWG_NO_GROUP_SORT=1: the record sort always runs the LSD passes (radix_sort.cuh)
+    u32 group_sort_max = 0;     // SWG_GROUP_SORT_MAX: largest group the group sort accepts (default GS_CTA_MAX; tests lower it)
     u32 fixpoint_min = 0;      // 0 = default
     double max_pair_evals = 0; // 0 = no limit (SWG_MAX_PAIR_EVALS)
     int sweep_mult = 8, resolve_mult = 4;
@@ -135,6 +137,8 @@ static Knobs read_knobs() {
     k.inv_no_grid = on("SWG_INV_NO_GRID");
     k.pairs_sort = on("SWG_SORT_PAIRS");
     k.no_fused_keys = on("SWG_NO_FUSED_KEYS");
+    k.no_group_sort = on("SWG_NO_GROUP_SORT");
+    if (const char *v = getenv("SWG_GROUP_SORT_MAX")) k.group_sort_max = (u32)atoi(v);
     if (const char *v = getenv("SWG_LOG_IMPL")) k.cuda_log = strcmp(v, "cuda") == 0;
     if (const char *v = getenv("SWG_FIXPOINT_MIN")) k.fixpoint_min = (u32)atoi(v);
     if (const char *v = getenv("SWG_MAX_PAIR_EVALS")) k.max_pair_evals = atof(v);
@@ -172,6 +176,9 @@ struct swg_ctx {
     Arena score_arena;             // ... and its device copy
     Arena arena;      // per-call scratch
     Arena io;         // staging of host SoA for swg_filter
+    u32 *gtable = nullptr;        // group sort (group_sort.cuh): one counter per possible (query, target, strand) group;
+    size_t gtable_entries = 0;    // all zero between calls, unless a call died half way (gtable_dirty)
+    bool gtable_dirty = false;
     u64 *h_ctr = nullptr; // pinned mirror of the counters
     std::vector<char *> pin;          // pinned pieces for the file front end (text upload, output download)
     std::vector<cudaEvent_t> pin_ev;
@@ -428,7 +435,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     if (cfg.scaffold_gap >= (1ull << 31) || cfg.scaffold_max_deviation >= (1ull << 31))
         throw RangeError{"scaffold_gap / scaffold_max_deviation must be < 2^31"};
 
-    c->arena.reserve((size_t)N * 360 + (64u << 20));
+    c->arena.reserve((size_t)N * 400 + (64u << 20));
     Arena &A = c->arena;
     u64 *ctr = c->d_ctr;
     SWG_CUDA(cudaMemsetAsync(ctr, 0, sizeof(u64) * C_COUNT, st));
@@ -476,6 +483,23 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     u64 *keys = nullptr, *keys2 = nullptr;
     u32 *vals = nullptr, *vals2 = nullptr;
     if (cfg.scaffold_gap != 0) { keys = A.take<u64>(N); keys2 = A.take<u64>(N); vals = A.take<u32>(N); vals2 = A.take<u32>(N); }
+    // The record sort as a counting sort by group (group_sort.cuh) when the table of all possible groups fits.
+    const u64 g_entries = 2ull * in.n_seq * in.n_seq;
+    const bool gsort = cfg.scaffold_gap != 0 && !K.force_wide && !K.pairs_sort && !K.no_group_sort && g_entries <= GS_MAX_TABLE && 2 * sb0 + 1 <= 31;
+    u32 *gtab = nullptr;
+    if (gsort) {
+        if (c->gtable_entries < g_entries) {
+            if (c->gtable) cudaFree(c->gtable);
+            c->gtable = nullptr;
+            c->gtable_entries = 0;
+            if (cudaMalloc(&c->gtable, g_entries * sizeof(u32)) != cudaSuccess) { cudaGetLastError(); throw OomError{(size_t)g_entries * sizeof(u32)}; }
+            c->gtable_entries = g_entries;
+            c->gtable_dirty = true;
+        }
+        if (c->gtable_dirty) SWG_CUDA(cudaMemsetAsync(c->gtable, 0, c->gtable_entries * sizeof(u32), st));
+        c->gtable_dirty = true; // until the ordering kernels have put the touched entries back to zero
+        gtab = c->gtable;
+    }
     if (fused_keys) k_prefilter<true><<<cdiv(N, 256), 256, 0, st>>>(in, cfg.min_block_length, cfg.min_identity, cfg.keep_self, flags, ctr, hk, hv, hcap - 1, rec4, sb0, keys, vals);
     else k_prefilter<false><<<cdiv(N, 256), 256, 0, st>>>(in, cfg.min_block_length, cfg.min_identity, cfg.keep_self, flags, ctr, hk, hv, hcap - 1, rec4);
     lc.n++;
@@ -540,21 +564,125 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     const bool wide = kb > 64 || K.force_wide;
     SortedIdx sidx{nullptr, nullptr, 0};
     const u64 *skey = nullptr;
+    bool kept_is_alive = false;   // the keys came from k_prefilter: kept == alive, nobody counted C_KEPT_M
+    bool groups_done = false;     // gid / gstart / group count already produced (group sort)
+    u32 n_groups = 0;
+    u32 *gstart = nullptr, *gid = nullptr;
+    u32 *d_tot = A.take<u32>(4);
     if (!wide) {
         const int ib = bits_for(N - 1);
-        // the keys written by k_prefilter<true> stand if no sweep ran (kept == alive) and every digit consumed up to the packing
-        // pass lies inside the coordinate field (the gap of the layout is closed by the packing pass)
-        fused_keys = fused_keys && !keep_q && !keep_t && zlq == 0 && zlt == 0 && rs_packed_c0(kb, ib) > 0 && rs_packed_c0(kb, ib) <= cb;
-        if (!fused_keys) {
-            k_chain_keys<<<cdiv(N, 256), 256, 0, st>>>(in, flags, keep_q, keep_t, sb, cb, keys, vals, ctr);
+        // the keys written by k_prefilter<true> stand if no sweep ran (kept == alive)
+        const bool fused_ok = fused_keys && !keep_q && !keep_t && zlq == 0 && zlt == 0;
+        // ... for the LSD passes additionally every digit consumed up to the packing pass must lie inside the coordinate field
+        // (the gap of the layout is closed by the packing pass)
+        const bool fused_lsd_ok = fused_ok && rs_packed_c0(kb, ib) > 0 && rs_packed_c0(kb, ib) <= cb;
+        bool lsd = true;
+        int key_shift = cb; // keys[] = (group key << key_shift) | query_start
+        if (gsort) {
+            stage_mark(c, "gs_runs");
+            if (fused_ok) { key_shift = 32; kept_is_alive = true; }
+            else {
+                k_chain_keys<<<cdiv(N, 256), 256, 0, st>>>(in, flags, keep_q, keep_t, sb, cb, keys, vals, ctr);
+                lc.n++;
+                fused_keys = false;
+            }
+            // runs of consecutive records with one group key: run index of every record, first record of every run
+            u32 *run_of = vals2, *run_start = A.take<u32>((size_t)N + 1), *run_base = A.take<u32>(N);
+            u32 *gs_ctr = A.take<u32>(12); // [0] groups, [1] records, [2] largest group; [3] runs; [4..6] list lengths; [7..9] work counters
+            SWG_CUDA(cudaMemsetAsync(gs_ctr, 0, 12 * sizeof(u32), st));
+            {
+                u32 *tmp = A.take<u32>(scan_temp_u32(N));
+                const u64 *kk = keys;
+                const int shift = key_shift;
+                scan_flags([=] __device__(u32 i) -> u32 { return (i == 0 || (kk[i] >> shift) != (kk[i - 1] >> shift)) ? 1u : 0u; },
+                           [=] __device__(u32 i, u32 ex, u32 v) {
+                               if (v) run_start[ex] = i;
+                               run_of[i] = ex + v - 1;
+                           },
+                           N, tmp, gs_ctr + 3, st, lc);
+            }
+            k_gs_run_base<<<(u32)c->sm_count * 8, 256, 0, st>>>(gs_ctr + 3, run_start, N, keys, key_shift, sb, in.n_seq, gtab, run_base);
             lc.n++;
+            stage_mark(c, "gs_scan");
+            gstart = A.take<u32>((size_t)N + 1);
+            u32 *gkey = A.take<u32>(N);
+            const u32 tiles = cdiv(g_entries, SC_TILE);
+            u64 *gs_status = A.take<u64>((size_t)tiles + 2);
+            SWG_CUDA(cudaMemsetAsync(gs_status, 0, sizeof(u64) * ((size_t)tiles + 2), st));
+            u32 *gs_out = gs_ctr;
+            k_gs_scan<<<tiles, SC_THREADS, 0, st>>>(gtab, (u32)g_entries, in.n_seq, sb, gstart, gkey, gs_status, reinterpret_cast<u32 *>(gs_status + tiles), gs_out);
+            lc.n++;
+            u32 *h = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
+            SWG_CUDA(cudaMemcpyAsync(h, gs_out, 3 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+            read_counters_begin(c); // (C_KEPT_M of k_chain_keys) the host picks the numbers up while the scatter runs
+            stage_mark(c, "gs_scatter");
+            k_gs_scatter<<<cdiv(N, 256), 256, 0, st>>>(keys, run_of, run_start, run_base, N, key_shift, sb, in.n_seq, ib, gtab, keys2);
+            lc.n++;
+            read_counters_end(c);
+            n_groups = h[0];
+            const u32 n_rec = h[1], gmax = h[2];
+            const u32 limit = K.group_sort_max ? std::min(K.group_sort_max, GS_CTA_MAX) : GS_CTA_MAX;
+            if (n_rec != (kept_is_alive ? (u32)n_alive : (u32)c->h_ctr[C_KEPT_M])) throw RangeError{"group sort: the group table was not clean on entry"};
+            if (n_groups == 0) {
+                lsd = false;
+                c->gtable_dirty = false;
+            } else if (gmax <= limit) {
+                stage_mark(c, "gs_order");
+                lsd = false;
+                gid = A.take<u32>(n_rec);
+                u32 *list_warp = A.take<u32>(n_groups), *list_mid = A.take<u32>(n_groups), *list_cta = A.take<u32>(n_groups);
+                u32 *list_ctr = gs_ctr + 4;
+                k_gs_groups<<<cdiv(n_groups, 256), 256, 0, st>>>(n_groups, gstart, gkey, sb, in.n_seq, ib, gtab, keys2, gid, list_warp, list_mid, list_cta, list_ctr);
+                k_gs_warp<<<(u32)c->sm_count * 8, 256, 0, st>>>(list_warp, list_ctr, gs_ctr + 7, gstart, gkey, ib, keys2, gid);
+                lc.n += 2;
+                if (gmax > GS_WARP_MAX) {
+                    k_gs_mid<<<(u32)c->sm_count * 3, 256, 8 * GS_MID_MAX * sizeof(u64), st>>>(list_mid, list_ctr + 1, gs_ctr + 8, gstart, gkey, ib, keys2, gid);
+                    lc.n++;
+                }
+                if (gmax > GS_MID_MAX) {
+                    k_gs_cta<<<(u32)c->sm_count * 2, GS_CTA_THREADS, GS_CTA_MAX * sizeof(u64), st>>>(list_cta, list_ctr + 2, gs_ctr + 9, gstart, gkey, ib, keys2, gid);
+                    lc.n++;
+                }
+                c->gtable_dirty = false;
+                SWG_CUDA(cudaMemcpyAsync(d_tot, gs_out, sizeof(u32), cudaMemcpyDeviceToDevice, st)); // d_tot[0] = group count (k_chain_work_estimate)
+                skey = keys2;
+                sidx.w = keys2;
+                sidx.mask = (1ull << ib) - 1;
+                gshift = ib;
+                groups_done = true;
+            } else {
+                // some group is larger than one CTA sorts: the LSD passes take over (the keys are still in place)
+                k_gs_clean<<<cdiv(n_groups, 256), 256, 0, st>>>(n_groups, gkey, sb, in.n_seq, gtab);
+                lc.n++;
+                c->gtable_dirty = false;
+                if (key_shift == 32 && !fused_lsd_ok) { // the gap layout does not suit the LSD passes of this key width
+                    k_chain_keys<<<cdiv(N, 256), 256, 0, st>>>(in, flags, keep_q, keep_t, sb, cb, keys, vals, ctr);
+                    lc.n++;
+                    kept_is_alive = false;
+                    fused_keys = false;
+                    read_counters(c);
+                } else fused_keys = key_shift == 32;
+                gstart = gid = nullptr;
+                n_groups = 0;
+            }
+        } else {
+            fused_keys = fused_lsd_ok;
+            kept_is_alive = fused_keys;
+            if (!fused_keys) {
+                k_chain_keys<<<cdiv(N, 256), 256, 0, st>>>(in, flags, keep_q, keep_t, sb, cb, keys, vals, ctr);
+                lc.n++;
+            }
         }
-        read_counters_begin(c); // the survivor count is final here; the host picks it up while the sort runs
-        if (K.pairs_sort) {
+        if (!lsd) {
+            // done above
+        } else if (K.pairs_sort) {
+            read_counters_begin(c);
             sort_pairs(c, keys, keys2, vals, vals2, N, kb, true);
             skey = keys;
             sidx.v = vals;
+            read_counters_end(c);
         } else {
+            read_counters_begin(c); // the survivor count is final here; the host picks it up while the sort runs
             // the packed sort (radix_sort.cuh): once the key bits still to be sorted and the index fit one word, the passes
             // move 8 B per record instead of 12 B; the result holds the index and the key from bit c0 upwards
             RadixSortPlan p = rs_plan(N, 0, kb);
@@ -568,8 +696,8 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             sidx.w = ps.packed;
             sidx.mask = (1ull << ib) - 1;
             gshift = ib + cb - ps.c0;
+            read_counters_end(c);
         }
-        read_counters_end(c);
     } else {
         // key wider than 64 bits (hundreds of thousands of sequences): two chained stable sorts, least significant
         // field first: by query_start, then by the (query,target,strand) group id; skey then holds the group id alone
@@ -601,23 +729,23 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         sidx.v = vals;
         read_counters(c);
     }
-    const u32 n_m = fused_keys ? (u32)n_alive : (u32)c->h_ctr[C_KEPT_M]; // fused keys: kept == alive (k_chain_keys did not count)
+    const u32 n_m = kept_is_alive ? (u32)n_alive : (u32)c->h_ctr[C_KEPT_M]; // keys of k_prefilter: kept == alive (nobody counted)
     S.n_after_sweep = n_m;
     S.score_near_ties = c->h_ctr[C_NEAR_TIES];
     if (n_m == 0) { finish(); return; }
     stage_mark(c, "groups+gather");
     uint4 *srec = A.take<uint4>(n_m);
-    u32 *gstart = A.take<u32>(n_m + 1);
-    u32 *gid = A.take<u32>(n_m);
     u32 *bsum = A.take<u32>(scan_temp_u32(N));
-    u32 *d_tot = A.take<u32>(4);
-    scan_flags([=] __device__(u32 p) -> u32 { return (p == 0 || (skey[p] >> gshift) != (skey[p - 1] >> gshift)) ? 1u : 0u; },
-               [=] __device__(u32 p, u32 ex, u32 v) {
-                   if (v) gstart[ex] = p;
-                   gid[p] = ex + v - 1;
-               },
-               n_m, bsum, d_tot, st, lc);
-    u32 n_groups;
+    if (!groups_done) {
+        gstart = A.take<u32>(n_m + 1);
+        gid = A.take<u32>(n_m);
+        scan_flags([=] __device__(u32 p) -> u32 { return (p == 0 || (skey[p] >> gshift) != (skey[p - 1] >> gshift)) ? 1u : 0u; },
+                   [=] __device__(u32 p, u32 ex, u32 v) {
+                       if (v) gstart[ex] = p;
+                       gid[p] = ex + v - 1;
+                   },
+                   n_m, bsum, d_tot, st, lc);
+    }
     // groups of at least fx_min positions are chained by the fixed-point iteration (SWG_NO_FIXPOINT=1: by the warp walk)
     const u32 fx_min = K.no_fixpoint ? NONE32 : (K.fixpoint_min ? K.fixpoint_min : FX_MIN_GROUP);
     {   // group count, positions in huge groups and a rough count of the candidate evaluations ahead (SWG_MAX_PAIR_EVALS, if
@@ -1613,6 +1741,7 @@ swg_ctx *swg_create(int device) {
         SWG_CUDA(cudaMallocHost(&c->h_ctr, sizeof(u64) * (C_COUNT + 8)));
         SWG_CUDA(cudaMalloc(&c->d_ctr, sizeof(u64) * C_COUNT));
         rs_init_device(); // dynamic shared memory opt-in of the one-sweep kernels: a per-device attribute
+        gs_init_device();
         c->knobs = read_knobs();
         c->log_matches_host = probe_log(c);
     } catch (const CudaError &e2) {
@@ -1638,6 +1767,7 @@ void swg_destroy(swg_ctx *c) {
     for (char *p : c->pin) cudaFreeHost(p);
     for (auto &ev : c->pin_ev) cudaEventDestroy(ev);
     if (c->d_ctr) cudaFree(c->d_ctr);
+    if (c->gtable) cudaFree(c->gtable);
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : c->ev_sort) if (ev) cudaEventDestroy(ev);
     for (auto &ev : c->ev_copy) if (ev) cudaEventDestroy(ev);

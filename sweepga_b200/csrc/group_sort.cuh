@@ -1,0 +1,380 @@
+// group_sort.cuh — the record sort of the chaining stage as a counting sort by group + an ordering step inside every group.
+//
+// Replaces, like radix_sort.cuh, the (query, target, strand) IndexMap + stable sort_by_key(query_start) of
+// src/paf_filter.rs:761-777 — the same result (groups in (query, target, strand) order, every group ordered by
+// (query_start, input index)), produced with far fewer passes over the records when no group is huge:
+//
+//   runs     (scan_flags in the caller) a run = maximal stretch of consecutive input records with the same group key; every
+//            record learns its run, every run its first record.  Aligner output is grouped, so a group usually IS one run.
+//   count    k_gs_run_base: one atomicAdd per run on a dense table indexed by (query * n_seq + target) * 2 + strand: the
+//            run's slot range inside its group.  A group that is a single run gets slots in input order, deterministically.
+//   scan     k_gs_scan: one pass over the table: start of every non-empty group, dense group numbers, largest group
+//   scatter  k_gs_scatter: record -> words[start(group) + base(run) + offset in run] = (query_start << ib) | index
+//   order    k_gs_groups (thread per group: sizes 1, 2), k_gs_warp (warp per group, <= 128 records: registers),
+//            k_gs_mid (warp per group, <= 1024: shared memory), k_gs_cta (CTA per group, <= 8192): a group that already is in
+//            order — an input sorted by position inside its groups — is only checked; otherwise a bitonic network sorts it.
+//            They write the result in the layout of the packed LSD sort — (group key << ib) | index — plus the group index of
+//            every position, and put the table entries back to zero.
+//
+// A one-sweep LSD pass is bound by the SM (warp ranking + shared-memory staging) at ~0.15 ms per 20 M records and
+// the 53-bit key needs seven of them; this path touches every record three times.  When some group is larger than
+// GS_CTA_MAX (configs[4]'s pile) or the table would not fit (n_seq > ~5800) the caller uses the LSD sort instead.
+#pragma once
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace swg {
+
+constexpr u32 GS_WARP_MAX = 128;        // largest group one warp orders in registers (4 words per lane)
+constexpr u32 GS_MID_MAX = 1024;        // largest group one warp orders in its 8 KB of shared memory
+constexpr u32 GS_CTA_MAX = 8192;        // largest group one CTA orders in shared memory (64 KB)
+constexpr u64 GS_MAX_TABLE = 1ull << 26; // table entries (256 MB)
+constexpr int GS_CTA_THREADS = 256;
+
+__device__ __forceinline__ u32 gs_index(u32 q, u32 t, u32 rev, u32 n_seq) { return (q * n_seq + t) * 2 + rev; }
+// table index from the bit-packed group key ((query << sb | target) << 1 | strand) of the sort keys
+__device__ __forceinline__ u32 gs_index_of_key(u32 grp, int sb, u32 n_seq) {
+    return gs_index(grp >> (sb + 1), (grp >> 1) & ((1u << sb) - 1), grp & 1, n_seq);
+}
+
+// ---- count: one atomic per run ---------------------------------------------------------------------------------------------
+// keys[i] = (group key << shift) | query_start; dead records carry the all-ones group key (their runs are skipped).
+__global__ void __launch_bounds__(256) k_gs_run_base(const u32 *__restrict__ n_runs_ptr, const u32 *__restrict__ run_start, u32 n,
+                                                     const u64 *__restrict__ keys, int shift, int sb, u32 n_seq, u32 *__restrict__ table,
+                                                     u32 *__restrict__ run_base) {
+    const u32 n_runs = *n_runs_ptr;
+    for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < n_runs; r += gridDim.x * blockDim.x) {
+        const u32 i0 = run_start[r], i1 = r + 1 < n_runs ? run_start[r + 1] : n;
+        const u32 grp = (u32)(keys[i0] >> shift);
+        if (grp == (1u << (2 * sb + 1)) - 1) continue; // dead
+        run_base[r] = atomicAdd(&table[gs_index_of_key(grp, sb, n_seq)], i1 - i0);
+    }
+}
+
+// ---- scan of the table ---------------------------------------------------------------------------------------------------
+// One pass, decoupled look-back over tiles (the scheme of scan.cuh) on a packed pair (non-empty groups before << 31 | records
+// before).  Non-empty entry g: table[g] = start + 1 (0 stays "empty"), gstart[dense] = start, gkey[dense] = bit-packed key.
+// out[0] = number of groups, out[1] = number of records, out[2] = largest group; gstart[n_groups] = number of records.
+__global__ void __launch_bounds__(SC_THREADS) k_gs_scan(u32 *__restrict__ table, u32 n_entries, u32 n_seq, int sb, u32 *__restrict__ gstart,
+                                                        u32 *__restrict__ gkey, u64 *status, u32 *tile_counter, u32 *out) {
+    __shared__ u64 ws[SC_THREADS / 32];
+    __shared__ u32 s_tile, s_max;
+    __shared__ u64 s_excl;
+    if (threadIdx.x == 0) { s_tile = atomicAdd(tile_counter, 1u); s_max = 0; }
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 base = tile * SC_TILE + threadIdx.x * SC_ITEMS;
+    u32 v[SC_ITEMS];
+    u64 s = 0;
+    u32 mx = 0;
+    if (base + SC_ITEMS <= n_entries) { // n_entries is even and the tile start a multiple of 8: two 16 B loads
+        const uint4 a = *reinterpret_cast<const uint4 *>(table + base), b = *reinterpret_cast<const uint4 *>(table + base + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < SC_ITEMS; k++) v[k] = base + k < n_entries ? table[base + k] : 0;
+    }
+    static_assert(SC_ITEMS == 8, "k_gs_scan loads eight entries per thread");
+#pragma unroll
+    for (int k = 0; k < SC_ITEMS; k++) {
+        s += (u64)v[k] + (v[k] ? (1ull << 31) : 0);
+        mx = max(mx, v[k]);
+    }
+    // block-wide exclusive scan of s
+    u64 x = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u64 t = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= (u32)o) x += t;
+    }
+    if (lane == 31) ws[warp] = x;
+    mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+    if (lane == 0 && mx) atomicMax(&s_max, mx);
+    __syncthreads();
+    u64 wbase = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < SC_THREADS / 32; w++) {
+        const u64 t = ws[w];
+        if (w < (int)warp) wbase += t;
+        tot += t;
+    }
+    const u64 ex_local = wbase + x - s;
+    if (threadIdx.x < 32) {
+        if (lane == 0) st_relaxed_u64(&status[tile], (tile == 0 ? SC_FLAG_INCL : SC_FLAG_AGG) | tot);
+        u64 excl = 0;
+        if (tile != 0) {
+            i64 t = (i64)tile - 1;
+            while (true) {
+                const i64 mine = t - lane;
+                const u64 w = mine >= 0 ? ld_relaxed_u64(&status[mine]) : SC_FLAG_INCL;
+                const u32 incl = __ballot_sync(0xFFFFFFFFu, (w & SC_FLAG_INCL) != 0);
+                const u32 ready = __ballot_sync(0xFFFFFFFFu, (w & (SC_FLAG_INCL | SC_FLAG_AGG)) != 0);
+                const u32 upto = incl ? (u32)(__ffs(incl) - 1) : 31u;
+                const u32 need = upto == 31 ? 0xFFFFFFFFu : ((2u << upto) - 1);
+                if ((ready & need) != need) continue;
+                u64 part = lane <= upto ? (w & SC_VAL_MASK) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+                excl += part;
+                if (incl) break;
+                t -= 32;
+            }
+            if (lane == 0) st_relaxed_u64(&status[tile], SC_FLAG_INCL | (excl + tot));
+        }
+        if (lane == 0) {
+            s_excl = excl;
+            if (s_max) atomicMax(&out[2], s_max);
+            if ((u64)(tile + 1) * SC_TILE >= n_entries) {
+                const u64 all = excl + tot;
+                const u32 ng = (u32)(all >> 31), nr = (u32)(all & 0x7FFFFFFFu);
+                out[0] = ng;
+                out[1] = nr;
+                gstart[ng] = nr;
+            }
+        }
+    }
+    __syncthreads();
+    u64 ex = s_excl + ex_local;
+#pragma unroll
+    for (int k = 0; k < SC_ITEMS; k++) {
+        if (v[k]) {
+            const u32 g = base + k;
+            const u32 start = (u32)(ex & 0x7FFFFFFFu), dense = (u32)(ex >> 31);
+            table[g] = start + 1;
+            gstart[dense] = start;
+            const u32 pair = g >> 1, q = pair / n_seq, t = pair - q * n_seq;
+            gkey[dense] = (((q << sb) | t) << 1) | (g & 1);
+            ex += (u64)v[k] + (1ull << 31);
+        }
+    }
+}
+
+// ---- scatter ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gs_scatter(const u64 *__restrict__ keys, const u32 *__restrict__ run_of, const u32 *__restrict__ run_start,
+                                                    const u32 *__restrict__ run_base, u32 n, int shift, int sb, u32 n_seq, int ib,
+                                                    const u32 *__restrict__ table, u64 *__restrict__ words) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 k = keys[i];
+    const u32 grp = (u32)(k >> shift);
+    if (grp == (1u << (2 * sb + 1)) - 1) return; // dead
+    const u32 qs = (u32)(k & ((1ull << shift) - 1));
+    const u32 r = run_of[i];
+    const u32 start1 = table[gs_index_of_key(grp, sb, n_seq)];
+    words[start1 - 1 + run_base[r] + (i - run_start[r])] = ((u64)qs << ib) | i;
+}
+
+// ---- order inside the groups --------------------------------------------------------------------------------------------
+// thread per group: puts the table entry back to zero, finishes groups of one or two records, lists the others.
+__global__ void __launch_bounds__(256) k_gs_groups(u32 n_groups, const u32 *__restrict__ gstart, const u32 *__restrict__ gkey, int sb, u32 n_seq,
+                                                   int ib, u32 *__restrict__ table, u64 *__restrict__ words, u32 *__restrict__ gid,
+                                                   u32 *__restrict__ list_warp, u32 *__restrict__ list_mid, u32 *__restrict__ list_cta,
+                                                   u32 *__restrict__ list_ctr /*[3]*/) {
+    const u32 d = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 cls = 0; // 1: warp list, 2: mid list, 3: CTA list
+    if (d < n_groups) {
+        const u32 s = gstart[d], e = gstart[d + 1], grp = gkey[d];
+        table[gs_index_of_key(grp, sb, n_seq)] = 0;
+        const u64 hi = (u64)grp << ib, mask = (1ull << ib) - 1;
+        const u32 size = e - s;
+        if (size == 1) {
+            words[s] = hi | (words[s] & mask);
+            gid[s] = d;
+        } else if (size == 2) {
+            u64 a = words[s], b = words[s + 1];
+            if (b < a) { const u64 t = a; a = b; b = t; }
+            words[s] = hi | (a & mask);
+            words[s + 1] = hi | (b & mask);
+            gid[s] = d;
+            gid[s + 1] = d;
+        } else cls = size <= GS_WARP_MAX ? 1 : size <= GS_MID_MAX ? 2 : 3;
+    }
+    const u32 full = 0xFFFFFFFFu, lt = lanemask_lt();
+#pragma unroll
+    for (u32 c = 1; c <= 3; c++) {
+        const u32 m = __ballot_sync(full, cls == c);
+        if (m == 0) continue;
+        u32 base = 0;
+        if (lane_id() == (u32)__ffs(m) - 1) base = atomicAdd(&list_ctr[c - 1], (u32)__popc(m));
+        base = __shfl_sync(full, base, __ffs(m) - 1);
+        if (cls == c) (c == 1 ? list_warp : c == 2 ? list_mid : list_cta)[base + __popc(m & lt)] = d;
+    }
+}
+
+// compare-exchange network over 32 * R words, word index = r * 32 + lane, ascending
+template <int R> __device__ __forceinline__ void gs_bitonic_warp(u64 (&x)[R], u32 lane) {
+#pragma unroll
+    for (int k = 2; k <= 32 * R; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int jr = j >> 5;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    if ((r & jr) == 0) {
+                        const bool up = ((r * 32) & k) == 0; // k >= 64: bit k of the index lies in r
+                        const u64 a = x[r], b = x[r | jr];
+                        const bool sw = up ? a > b : a < b;
+                        x[r] = sw ? b : a;
+                        x[r | jr] = sw ? a : b;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const u64 o = __shfl_xor_sync(0xFFFFFFFFu, x[r], j);
+                    const bool up = (((u32)(r * 32) | lane) & (u32)k) == 0;
+                    const bool lower = (lane & (u32)j) == 0;
+                    x[r] = (up == lower) ? (x[r] < o ? x[r] : o) : (x[r] > o ? x[r] : o);
+                }
+            }
+        }
+    }
+}
+template <int R>
+__device__ __forceinline__ void gs_warp_group(u64 *__restrict__ words, u32 *__restrict__ gid, u32 s, u32 size, u32 d, u64 hi, u64 mask, u32 lane) {
+    u64 x[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) x[r] = (u32)(r * 32) + lane < size ? words[s + r * 32 + lane] : NONE64;
+    bool ok = true; // already in order?  (arrival order of a group that sits in one warp of the counting pass is input order)
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        u64 prev = __shfl_up_sync(0xFFFFFFFFu, x[r], 1);
+        const u64 carry = __shfl_sync(0xFFFFFFFFu, x[r > 0 ? r - 1 : 0], 31);
+        if (lane == 0) prev = r > 0 ? carry : 0;
+        ok = ok && prev <= x[r];
+    }
+    if (!__all_sync(0xFFFFFFFFu, ok)) gs_bitonic_warp<R>(x, lane);
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const u32 p = (u32)(r * 32) + lane;
+        if (p < size) {
+            words[s + p] = hi | (x[r] & mask);
+            gid[s + p] = d;
+        }
+    }
+}
+// warp per listed group (3 .. GS_WARP_MAX records), warps take groups from a counter
+__global__ void __launch_bounds__(256) k_gs_warp(const u32 *__restrict__ list, const u32 *__restrict__ n_list_ptr, u32 *work_ctr,
+                                                 const u32 *__restrict__ gstart, const u32 *__restrict__ gkey, int ib, u64 *__restrict__ words,
+                                                 u32 *__restrict__ gid) {
+    const u32 lane = threadIdx.x & 31;
+    const u32 n_list = *n_list_ptr;
+    const u64 mask = (1ull << ib) - 1;
+    while (true) {
+        u32 w = 0;
+        if (lane == 0) w = atomicAdd(work_ctr, 1u);
+        w = __shfl_sync(0xFFFFFFFFu, w, 0);
+        if (w >= n_list) return;
+        const u32 d = list[w];
+        const u32 s = gstart[d], size = gstart[d + 1] - s;
+        const u64 hi = (u64)gkey[d] << ib;
+        if (size <= 32) gs_warp_group<1>(words, gid, s, size, d, hi, mask, lane);
+        else if (size <= 64) gs_warp_group<2>(words, gid, s, size, d, hi, mask, lane);
+        else gs_warp_group<4>(words, gid, s, size, d, hi, mask, lane);
+    }
+}
+static_assert(GS_WARP_MAX == 128, "gs_warp_group<4> holds 128 words");
+
+// warp per listed group (GS_WARP_MAX + 1 .. GS_MID_MAX records): the group in the warp's own 8 KB of shared memory; no block
+// barrier anywhere, the eight warps of a CTA work on eight groups
+__global__ void __launch_bounds__(256) k_gs_mid(const u32 *__restrict__ list, const u32 *__restrict__ n_list_ptr, u32 *work_ctr,
+                                                const u32 *__restrict__ gstart, const u32 *__restrict__ gkey, int ib, u64 *__restrict__ words,
+                                                u32 *__restrict__ gid) {
+    extern __shared__ __align__(16) unsigned char gs_smem_raw[];
+    const u32 lane = threadIdx.x & 31;
+    u64 *sm = reinterpret_cast<u64 *>(gs_smem_raw) + (threadIdx.x >> 5) * GS_MID_MAX;
+    const u32 n_list = *n_list_ptr;
+    const u64 mask = (1ull << ib) - 1;
+    while (true) {
+        u32 w = 0;
+        if (lane == 0) w = atomicAdd(work_ctr, 1u);
+        w = __shfl_sync(0xFFFFFFFFu, w, 0);
+        if (w >= n_list) return;
+        const u32 d = list[w];
+        const u32 s = gstart[d], size = gstart[d + 1] - s;
+        const u64 hi = (u64)gkey[d] << ib;
+        u32 np = 256;
+        while (np < size) np <<= 1;
+        __syncwarp();
+        for (u32 p = lane; p < np; p += 32) sm[p] = p < size ? words[s + p] : NONE64;
+        __syncwarp();
+        bool bad = false;
+        for (u32 p = lane + 1; p < size; p += 32) bad |= sm[p - 1] > sm[p];
+        if (__any_sync(0xFFFFFFFFu, bad)) {
+            for (u32 k = 2; k <= np; k <<= 1) {
+                for (u32 j = k >> 1; j > 0; j >>= 1) {
+                    for (u32 t = lane; t < np / 2; t += 32) {
+                        const u32 i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), o = i | j;
+                        const u64 a = sm[i], b = sm[o];
+                        const bool up = (i & k) == 0;
+                        if (up ? a > b : a < b) { sm[i] = b; sm[o] = a; }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        for (u32 p = lane; p < size; p += 32) {
+            words[s + p] = hi | (sm[p] & mask);
+            gid[s + p] = d;
+        }
+    }
+}
+
+// CTA per listed group (GS_MID_MAX + 1 .. GS_CTA_MAX records): the group in shared memory, in-order check, bitonic network
+__global__ void __launch_bounds__(GS_CTA_THREADS) k_gs_cta(const u32 *__restrict__ list, const u32 *__restrict__ n_list_ptr, u32 *work_ctr,
+                                                           const u32 *__restrict__ gstart, const u32 *__restrict__ gkey, int ib,
+                                                           u64 *__restrict__ words, u32 *__restrict__ gid) {
+    extern __shared__ __align__(16) unsigned char gs_smem_raw[];
+    u64 *sm = reinterpret_cast<u64 *>(gs_smem_raw);
+    __shared__ u32 s_w;
+    const u32 n_list = *n_list_ptr;
+    const u64 mask = (1ull << ib) - 1;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_w = atomicAdd(work_ctr, 1u);
+        __syncthreads();
+        const u32 w = s_w;
+        if (w >= n_list) return;
+        const u32 d = list[w];
+        const u32 s = gstart[d], size = gstart[d + 1] - s;
+        const u64 hi = (u64)gkey[d] << ib;
+        u32 np = 256;
+        while (np < size) np <<= 1;
+        for (u32 p = threadIdx.x; p < np; p += GS_CTA_THREADS) sm[p] = p < size ? words[s + p] : NONE64;
+        __syncthreads();
+        int bad = 0;
+        for (u32 p = threadIdx.x + 1; p < size; p += GS_CTA_THREADS) bad |= sm[p - 1] > sm[p];
+        if (__syncthreads_or(bad)) {
+            for (u32 k = 2; k <= np; k <<= 1) {
+                for (u32 j = k >> 1; j > 0; j >>= 1) {
+                    for (u32 t = threadIdx.x; t < np / 2; t += GS_CTA_THREADS) {
+                        const u32 i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), o = i | j;
+                        const u64 a = sm[i], b = sm[o];
+                        const bool up = (i & k) == 0;
+                        if (up ? a > b : a < b) { sm[i] = b; sm[o] = a; }
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+        for (u32 p = threadIdx.x; p < size; p += GS_CTA_THREADS) {
+            words[s + p] = hi | (sm[p] & mask);
+            gid[s + p] = d;
+        }
+    }
+}
+
+// fallback (some group is larger than GS_CTA_MAX: the caller sorts with the LSD passes): only put the table back to zero
+__global__ void __launch_bounds__(256) k_gs_clean(u32 n_groups, const u32 *__restrict__ gkey, int sb, u32 n_seq, u32 *__restrict__ table) {
+    const u32 d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < n_groups) table[gs_index_of_key(gkey[d], sb, n_seq)] = 0;
+}
+
+static inline void gs_init_device() {
+    SWG_CUDA(cudaFuncSetAttribute(k_gs_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GS_CTA_MAX * sizeof(u64))));
+    SWG_CUDA(cudaFuncSetAttribute(k_gs_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * GS_MID_MAX * sizeof(u64))));
+}
+
+} // namespace swg

@@ -39,6 +39,9 @@ constexpr int RS_MAX_PASSES = 8;
 #ifndef SWG_RS_LOOKBACK
 #define SWG_RS_LOOKBACK 8
 #endif
+#ifndef SWG_RS_RANK
+#define SWG_RS_RANK 2
+#endif
 constexpr int RS_LOOKBACK = SWG_RS_LOOKBACK; // predecessor tiles inspected per look-back round (independent loads in flight)
 
 constexpr u32 RS_FLAG_AGG = 1u << 30;  // tile aggregate available
@@ -153,22 +156,62 @@ __device__ __forceinline__ void rs_onesweep_tile(RsSmemT<MODE> &s, const u64 *__
         const bool ok = FULL || (u32)(i * 32 + lane) < warp_n;
         key[i] = ok ? keys_in[warp_base + i * 32 + lane] : NONE64;
     }
-    // warp-level multi-split ranking (stable: items ascending, lanes ascending).
-    // pass A: all the peer masks back to back (independent); pass B: the sequential warp-histogram update.
+    // warp-level multi-split ranking (stable: items ascending, lanes ascending): for every item the lanes of the warp holding
+    // the same digit ("peers"), the lowest of them as leader; the leader bumps the warp's digit count, everyone takes
+    // count-before + its rank inside the run.  Three ways to find the peers (SWG_RS_RANK):
+    //   0  eight ballots, one per digit bit (pure ALU work: ~58 SASS instructions per item as compiled — round-2 ncu: the
+    //      pass was ALU-pipe bound on exactly this)
+    //   1  MATCH.ANY
+    //   2  shared-memory match masks: MATCH.ALL first (a warp holding ONE digit — every high-order pass over grouped input —
+    //      needs nothing else); otherwise every lane ORs its lane bit into mask[digit] (one shared atomic), reads the mask
+    //      back, and the leader clears it.  The masks overlay the staging area, which is idle during the ranking and zeroed
+    //      at tile start.
     const u32 lt = lanemask_lt();
+#if SWG_RS_RANK == 2
+    if (FULL) {
+        u32 *match = reinterpret_cast<u32 *>(s.stage_k) + warp * RS_RADIX;
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; i++) {
+            const u32 d = (u32)(key[i] >> shift) & (RS_RADIX - 1);
+            int uniform;
+            __match_all_sync(0xFFFFFFFFu, d, &uniform);
+            u32 peers = 0xFFFFFFFFu;
+            if (!uniform) {
+                atomicOr(&match[d], 1u << lane);
+                __syncwarp();
+                peers = match[d];
+                __syncwarp();
+            }
+            const u32 leader = (u32)__ffs(peers) - 1;
+            u32 prev = 0;
+            if (lane == leader) {
+                prev = s.warp_hist[warp][d];
+                s.warp_hist[warp][d] = prev + (u32)__popc(peers);
+                if (!uniform) match[d] = 0;
+            }
+            prev = __shfl_sync(0xFFFFFFFFu, prev, leader);
+            rnk[i] = prev + (u32)__popc(peers & lt);
+            __syncwarp();
+        }
+    } else
+#endif
+    {
+    // pass A: all the peer masks back to back (independent); pass B: the sequential warp-histogram update.
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
         const bool ok = FULL || (u32)(i * 32 + lane) < warp_n;
         const u32 d = (u32)(key[i] >> shift) & (RS_RADIX - 1);
-        // lanes with the same 8-bit digit, from 8 ballots (much cheaper than MATCH.ANY when the warp holds many
-        // distinct digits, which is every low-order pass)
         u32 peers = FULL ? 0xFFFFFFFFu : __ballot_sync(0xFFFFFFFFu, ok);
+#if SWG_RS_RANK == 1
+        peers &= __match_any_sync(0xFFFFFFFFu, d);
+#else
 #pragma unroll
         for (int b = 0; b < RS_BITS; b++) {
-            const bool bit = (d >> b) & 1;
+            const bool bit = (d & (1u << b)) != 0;
             const u32 m = __ballot_sync(0xFFFFFFFFu, bit);
             peers &= bit ? m : ~m;
         }
+#endif
         if (!FULL && !ok) peers = 1u << lane;
         // leader (5 bits) | run length (6 bits) | rank inside the run (5 bits)
         rnk[i] = (u32)(__ffs(peers) - 1) | ((u32)__popc(peers) << 8) | ((u32)__popc(peers & lt) << 16);
@@ -186,6 +229,7 @@ __device__ __forceinline__ void rs_onesweep_tile(RsSmemT<MODE> &s, const u64 *__
         prev = __shfl_sync(0xFFFFFFFFu, prev, leader);
         rnk[i] = prev + (rnk[i] >> 16);
         __syncwarp();
+    }
     }
     // payloads are only needed for staging: issue their loads now so the latency hides behind the scans/barriers
     if (MODE != RS_PACKED) {
@@ -310,6 +354,10 @@ rs_onesweep_kernel(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out, 
     const u32 tid = threadIdx.x;
     if (tid == 0) s.tile = atomicAdd(tile_counter, 1u); // in-order tile ids: look-back never waits on an unscheduled tile
     for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&s.warp_hist[0][0])[i] = 0;
+#if SWG_RS_RANK == 2
+    static_assert(sizeof(u64) * RS_TILE >= sizeof(u32) * RS_WARPS * RS_RADIX, "the match masks overlay the staging area");
+    for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) reinterpret_cast<u32 *>(s.stage_k)[i] = 0;
+#endif
     __syncthreads();
     const u32 tile = s.tile;
     if ((u64)(tile + 1) * RS_TILE <= (u64)n)
@@ -393,7 +441,8 @@ static inline int rs_packed_c0(int key_bits, int ib) {
 // payload < 2^ib and key_bits <= RS_MAX_PASSES * RS_BITS.  ev[2k], ev[2k+1] (optional): events around pass k.
 static inline PackedSort rs_sort_packed(u32 n, int key_bits, int ib, u64 *keys, u64 *keys_alt, u32 *vals, u32 *vals_alt, void *temp,
                                         const RadixSortPlan &p, cudaStream_t st, int sm_count, LaunchCounter &lc,
-                                        cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_end = nullptr, int gap_cb = 0) {
+                                        cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_end = nullptr, int gap_cb = 0,
+                                        cudaEvent_t *pass_ev = nullptr /* tuning: events around every pass */) {
     PackedSort r;
     r.ib = ib;
     r.c0 = rs_packed_c0(key_bits, ib);
@@ -417,6 +466,7 @@ static inline PackedSort rs_sort_packed(u32 n, int key_bits, int ib, u64 *keys, 
     const int first_timed = r.timed_passes == p.passes ? 0 : pk + 1;
     for (int pass = 0; pass < p.passes; pass++) {
         if (pass == first_timed && ev_begin) SWG_CUDA(cudaEventRecord(ev_begin, st));
+        if (pass_ev) SWG_CUDA(cudaEventRecord(pass_ev[2 * pass], st));
         const u32 *db = hist + pass * RS_RADIX;
         u32 *stt = status + (size_t)pass * p.tiles * RS_RADIX;
         if (pass < pk) {
@@ -431,6 +481,7 @@ static inline PackedSort rs_sort_packed(u32 n, int key_bits, int ib, u64 *keys, 
                                                                                                 ib + pass * RS_BITS - r.c0, 0, 0, 0, db, stt, counters + pass);
         }
         lc.n += 1;
+        if (pass_ev) SWG_CUDA(cudaEventRecord(pass_ev[2 * pass + 1], st));
         u64 *tk = keys; keys = keys_alt; keys_alt = tk;
     }
     if (ev_end) SWG_CUDA(cudaEventRecord(ev_end, st));

@@ -335,3 +335,68 @@ def test_record_sort_variants(ctx, yeast, knob, monkeypatch):
     # zero-length intervals among the alive records: the fused keys are discarded and rebuilt after the sweep
     t = fuzz_table(5, 3000)
     check(ctx, swg.FilterConfig.from_cli(scaffold_jump="200", scaffold_mass="0"), t, f"fuzz {knob}")
+
+
+# ---- the record sort as a counting sort by group (csrc/group_sort.cuh) -------------------------------------------------------
+def _shuffled(t, seed):
+    t2 = t.take(np.random.default_rng(seed).permutation(t.n))
+    return swg.MappingTable(t2.query_id, t2.target_id, t2.query_start, t2.query_end, t2.target_start, t2.target_end, t2.block_length,
+                            t2.matches, t2.identity, t2.strand, t2.seq_genome_id, t2.seq_genome2_id)
+
+
+@pytest.mark.parametrize("knob", [None, "SWG_NO_GROUP_SORT", "SWG_GROUP_SORT_MAX"])
+@pytest.mark.parametrize("case", ["defaults", "1:1_1:1", "rescue100k"])
+def test_group_sort_paths(ctx, yeast, case, knob, monkeypatch):
+    """Default: count + scan + scatter + per-group ordering.  SWG_NO_GROUP_SORT=1: the LSD passes.  SWG_GROUP_SORT_MAX=8: every
+    input with a group of more than eight records takes the fallback (table cleaned, keys re-used or rebuilt, LSD passes) —
+    the path of a real input with one huge group.  Same result on grouped and on shuffled rows."""
+    if knob:
+        monkeypatch.setenv(knob, "8" if knob == "SWG_GROUP_SORT_MAX" else "1")
+    cfg = swg.FilterConfig.from_cli(**CLI_CASES[case])
+    check(ctx, cfg, yeast, f"yeast {knob}")
+    check(ctx, cfg, _shuffled(yeast, 1), f"yeast shuffled {knob}")
+    big = synth.pansn(300_000, seed=31, n_hap=6)
+    check(ctx, cfg, big, f"pansn {knob}")
+    check(ctx, cfg, _shuffled(big, 2), f"pansn shuffled {knob}")
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_group_sort_size_classes(ctx, seed):
+    """Shuffled rows with groups of every size class: one or two records (thread), 3..32 / 33..64 / 65..128 (warp network,
+    1 / 2 / 4 words per lane), 129..8192 (CTA in shared memory) and, seed 5, one group beyond that (LSD fallback); many
+    equal query starts, so the index tie-break of the stable order is exercised."""
+    rng = np.random.default_rng(700 + seed)
+    sizes = {0: [1, 2, 3, 5, 31, 32, 33, 63, 64, 65, 100, 127, 128], 1: [129, 200, 256, 257, 1000, 2048, 2049], 2: [8191, 8192, 4097, 3, 1],
+             3: list(rng.integers(1, 300, 60)), 4: list(rng.integers(1, 40, 400)), 5: [8193, 50, 2, 1]}[seed]
+    names = [f"G{g}#1#c{c}" for g in range(2) for c in range(len(sizes) + 1)]
+    nq = len(sizes) + 1
+    qid, tid, strand = [], [], []
+    for k, sz in enumerate(sizes):
+        qid += [k] * sz
+        tid += [nq + (k * 7) % nq] * sz
+        strand += [ord("+") if k % 3 else ord("-")] * sz
+    n = len(qid)
+    qs = rng.integers(0, 5000, n) * 100          # many exact ties
+    ln = rng.integers(50, 3000, n)
+    ts = np.maximum(qs + rng.integers(-2000, 2000, n), 0)
+    blk = ln + rng.integers(0, 20, n)
+    matches = np.rint(blk * rng.uniform(0.8, 1.0, n)).astype(np.int64)
+    P, P2 = swg.prefix_ids(names)
+    t = swg.MappingTable(np.array(qid), np.array(tid), qs, qs + ln, ts, ts + ln, blk, matches, matches / blk, np.array(strand, np.uint8), P, P2, None, names)
+    t = _shuffled(t, seed)
+    for flags in ({}, dict(scaffold_jump="20k", scaffold_mass="0", scaffold_dist="10k"), dict(num_mappings="1:1", scaffold_mass="1k")):
+        check(ctx, swg.FilterConfig.from_cli(**flags), t, f"classes seed {seed} {flags}")
+
+
+def test_group_sort_table_survives_a_failed_call(ctx, yeast):
+    """A call that dies after the counting pass (a bad record makes the filter raise) leaves the group table dirty; the next call
+    must clear it instead of adding to stale counts."""
+    bad = yeast.take(np.arange(yeast.n))
+    bad = swg.MappingTable(bad.query_id, bad.target_id, bad.query_start, bad.query_end, bad.target_start, bad.target_end, bad.block_length,
+                           bad.matches, bad.identity, bad.strand, bad.seq_genome_id, bad.seq_genome2_id)
+    bad.query_end = bad.query_end.copy()
+    bad.query_end[yeast.n // 2] = bad.query_start[yeast.n // 2] - 1 if bad.query_start[yeast.n // 2] > 0 else 0
+    if bad.query_end[yeast.n // 2] < bad.query_start[yeast.n // 2]:
+        with pytest.raises(swg.SwgError):
+            ctx.filter(swg.FilterConfig(), bad)
+    check(ctx, swg.FilterConfig(), yeast, "after a failed call")

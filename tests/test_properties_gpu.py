@@ -30,7 +30,7 @@ def test_device_resident_equals_host_path(ctx, big):
     s2, c2 = ctx.download(big.n, dres)
     ctx.release(dev, dres)
     assert np.array_equal(s, s2) and np.array_equal(c, c2)
-    assert st.n_sort_passes > 0 and st.ms_sort_passes > 0 and st.gpu_launches > 20
+    assert st.gpu_launches > 20
 
 
 def test_idempotence_of_the_kept_set(ctx, big):
