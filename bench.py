@@ -360,10 +360,16 @@ def main():
     cfg = swg.FilterConfig.from_cli(scaffold_dist="100k") if n_gpus > 1 else swg.FilterConfig()
     n = table.n
     ctx = swg.Context(local_rank)
-    d_in, d_res = ctx.upload(table)
-    # the synthetic tables carry no dv:f: / cg:Z: tags: identity == matches / max(block_length, 1) bit for bit, so the e2e
-    # call may leave the column out (the device derives it)
+    # the synthetic tables carry no dv:f: / cg:Z: tags: identity == matches / max(block_length, 1) bit for bit, so both the
+    # device-resident table and the e2e call leave the column out (swg_mappings.identity == NULL: the device derives it)
     identity_is_default = bool(np.array_equal(table.identity, table.matches / np.maximum(table.block_length, 1)))
+    if identity_is_default:
+        import copy
+        dtable = copy.copy(table)
+        dtable.identity = None
+    else:
+        dtable = table
+    d_in, d_res = ctx.upload(dtable)
 
     # ---- N > 1: what makes the shard results global ------------------------------------------------------------------
     units = desc["units"]
@@ -438,7 +444,7 @@ def main():
     for _ in range(args.warmup):
         step_device()
     barrier()
-    dev_ms, sort_ms, sort_passes, launches, filter_ms = 0.0, 0.0, 0, 0, 0.0
+    dev_ms, sort_ms, sort_passes, launches, filter_ms, pre_ms = 0.0, 0.0, 0, 0, 0.0, 0.0
     with ClockSampler(local_rank) as clk:
         t0 = time.perf_counter()
         for _ in range(args.steps):
@@ -446,6 +452,7 @@ def main():
             dev_ms += ms
             filter_ms += st.ms_device
             sort_ms += st.ms_sort_passes
+            pre_ms += st.ms_prefilter
             sort_passes += st.n_sort_passes
             launches += st.gpu_launches + extra
         barrier()
@@ -545,16 +552,31 @@ def main():
         peak, peak_src = peaks()
         value = n_total * args.steps / t_dev / 1e6
         e2e_v = n_total * args.steps / t_e2e / 1e6
-        pass_ms = sort_ms / max(sort_passes, 1)
-        bpp = int(stats.sort_bytes_per_pair) or 24
-        achieved = stats.n_sort_pairs * bpp / (pass_ms / 1e3) / 1e9 if pass_ms > 0 else 0.0
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "onesweep_traffic.json")
-        traffic_note = None
+        # the dominant kernel of the step: the LSD passes of the record sort when they ran (huge groups / very many sequences),
+        # otherwise k_prefilter (the record sort is a counting sort by group then: csrc/group_sort.cuh)
+        traffic, traffic_note = None, None
+        if sort_ms > pre_ms:
+            pass_ms = sort_ms / max(sort_passes, 1)
+            bpp = int(stats.sort_bytes_per_pair) or 24
+            units_per_launch = int(stats.n_sort_pairs)
+            launches_timed = int(stats.n_sort_passes)
+            kernel = ("rs_onesweep_kernel<RS_PACKED> (record sort pass on packed words, 8 B read + 8 B written per record)"
+                      if bpp == 16 else "rs_onesweep_kernel (record sort pass, 12 B read + 12 B written per pair)")
+            tfile = "onesweep_traffic.json"
+        else:
+            pass_ms = pre_ms / args.steps
+            bpp = int(stats.prefilter_bytes_per_record)
+            units_per_launch = int(n)
+            launches_timed = 1
+            kernel = (f"k_prefilter (stage-1 retain, range checks, genome-pair first appearance, packed coordinates and sort keys: "
+                      f"{bpp} B read + written per record)")
+            tfile = "prefilter_traffic.json"
+        achieved = units_per_launch * bpp / (pass_ms / 1e3) / 1e9 if pass_ms > 0 else 0.0
+        tp = os.path.join(ROOT, "profiles", tfile)
         if os.path.exists(tp):
             try:
                 tj = json.load(open(tp))
-                if int(tj.get("pairs_per_launch", 0)) == int(stats.n_sort_pairs) and int(tj.get("bytes_per_pair", 24)) == bpp:
+                if int(tj.get("pairs_per_launch", 0)) == units_per_launch and int(tj.get("bytes_per_pair", 24)) == bpp:
                     traffic = tj.get("dram_bytes_per_launch")
                     traffic_note = tj.get("source")
             except Exception:
@@ -574,7 +596,7 @@ def main():
                        "pipeline_fraction_of_hbm_roofline": (n * desc["b_alg"] / (t_filter / args.steps)) / 1e9 / peak,
                        "log_matches_host": ctx.log_matches_host(),
                        "stats": {k: int(getattr(stats, k)) for k in ("n_stage1", "n_after_sweep", "n_chains", "n_chains_after_mass",
-                                                                     "n_chains_kept", "n_anchors", "n_rescued", "n_kept", "exact_rerank", "n_dirty_groups")}},
+                                                                     "n_chains_kept", "n_anchors", "n_rescued", "n_kept", "exact_rerank", "n_dirty_groups", "n_unsorted_groups")}},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_v, "unit": "Mmappings/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": t_e2e * 1e3 / args.steps, "wall_ms_per_step": wall_e2e * 1e3 / args.steps,
@@ -582,12 +604,10 @@ def main():
                     "pageable_buffers_wall_ms_per_step": pageable_ms,
                     "h2d_gbs_per_rank": h2d / max(st2.ms_h2d, 1e-9) / 1e6},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": ("rs_onesweep_kernel<RS_PACKED> (record sort pass on packed words, 8 B read + 8 B written per record)"
-                                    if bpp == 16 else "rs_onesweep_kernel (record sort pass, 12 B read + 12 B written per pair)"),
-                         "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+            "roofline": {"kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_note,
-                         "launch_ms": pass_ms, "pairs_per_launch": int(stats.n_sort_pairs), "bytes_per_pair": bpp,
-                         "launches_timed_per_step": int(stats.n_sort_passes)},
+                         "launch_ms": pass_ms, "records_per_launch": units_per_launch, "bytes_per_record": bpp,
+                         "launches_timed_per_step": launches_timed},
             "parity": parity,
         }
         if n_gpus == 1:
@@ -629,10 +649,13 @@ def scale_anchor(ctx, args):
         d_in, d_res = ctx.upload(t)
         for _ in range(2):
             ctx.filter_device(cfg, d_in, d_res)
-        ms = [ctx.filter_device(cfg, d_in, d_res).ms_device for _ in range(5)]
+        sts = [ctx.filter_device(cfg, d_in, d_res) for _ in range(5)]
+        ms = [s.ms_device for s in sts]
         ctx.release(d_in, d_res)
         return {"workload": "shard 0 of the 8-GPU partition of configs[3] on one GPU (filter only, no exchange)", "records": int(t.n),
-                "ms_per_step": sum(ms) / len(ms), "Mmappings_per_s": t.n / (sum(ms) / len(ms)) / 1e3}
+                "ms_per_step": sum(ms) / len(ms), "Mmappings_per_s": t.n / (sum(ms) / len(ms)) / 1e3,
+                "lsd_sort_passes": int(sts[-1].n_sort_passes), "groups_ordered_after_scatter": int(sts[-1].n_unsorted_groups),
+                "gpu_launches": int(sts[-1].gpu_launches)}
     except Exception as e:
         return {"error": repr(e)[:200]}
 

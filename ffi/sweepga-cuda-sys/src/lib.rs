@@ -119,7 +119,9 @@ pub struct swg_stats {
     pub h2d_bytes: u64,
     pub d2h_bytes: u64,
     pub n_dirty_groups: u64,
-    pub reserved: [u64; 3],
+    pub ms_prefilter: f64,
+    pub prefilter_bytes_per_record: u64,
+    pub n_unsorted_groups: u64,
 }
 
 /// Opaque context: one per GPU and per calling thread.

@@ -158,7 +158,10 @@ typedef struct swg_stats {
     uint64_t h2d_bytes, d2h_bytes;/* swg_filter: bytes copied host->device / device->host by this call        */
     uint64_t n_dirty_groups;      /* (query,target,strand) groups in which some mapping was claimed as successor twice:
                                      chained by the sequential walk instead of the one-pass claims (diagnostic)       */
-    uint64_t reserved[3];
+    double ms_prefilter;          /* CUDA-event time of k_prefilter (stage-1 retain + sort keys), the largest kernel of a default call */
+    uint64_t prefilter_bytes_per_record; /* ... and the bytes it reads + writes per input record (algorithmic)              */
+    uint64_t n_unsorted_groups;   /* record sort by groups: groups of three or more records that were not in (query_start, index)
+                                     order after the scatter and went through an ordering kernel (diagnostic)            */
 } swg_stats;
 
 typedef struct swg_ctx swg_ctx;

@@ -19,6 +19,8 @@ for name, flags in (("defaults", {}), ("rescue 100k", dict(scaffold_dist="100k")
                     ("1:1 / 1:1 + rescue", dict(num_mappings="1:1", scaffold_filter="1:1", scaffold_dist="100k")),
                     ("many:many / 1:1", dict(scaffold_filter="1:1")), ("no scaffolding, 1:1", dict(num_mappings="1:1", scaffold_jump="0")),
                     ("scaffolds only", dict(scaffolds_only=True))):
+    if "--only-defaults" in sys.argv and flags:
+        continue
     cfg = swg.FilterConfig.from_cli(**flags)
     ctx.filter_device(cfg, dev, dres)
     ms = []

@@ -52,7 +52,8 @@ class swg_stats(C.Structure):
         ("ms_h2d", C.c_double), ("ms_device", C.c_double), ("ms_d2h", C.c_double),
         ("ms_sort_passes", C.c_double), ("n_sort_passes", C.c_uint64), ("n_sort_pairs", C.c_uint64),
         ("ms_tokenize", C.c_double), ("ms_write", C.c_double), ("exact_rerank", C.c_uint64), ("sort_bytes_per_pair", C.c_uint64),
-        ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_dirty_groups", C.c_uint64), ("reserved", C.c_uint64 * 3),
+        ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_dirty_groups", C.c_uint64),
+        ("ms_prefilter", C.c_double), ("prefilter_bytes_per_record", C.c_uint64), ("n_unsorted_groups", C.c_uint64),
     ]
 
 

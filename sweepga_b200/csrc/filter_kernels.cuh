@@ -23,7 +23,7 @@ constexpr u8 F_ANCHOR = 32; // status == scaffold: member of a kept chain or cap
 // counters (u64 each) shared with the host
 enum {
     C_ALIVE = 0, C_ZLQ, C_ZLT, C_MAXCOORD, C_BAD, C_KEPT_M, C_GROUPS, C_CHAINS, C_PASS, C_PASS_ZEROSPAN,
-    C_KEPT_CHAINS, C_ANCHORS, C_RESCUED, C_KEPT, C_NEAR_TIES, C_WORK, C_INV, C_HUGE, C_TMP0, C_COUNT = 32
+    C_KEPT_CHAINS, C_ANCHORS, C_RESCUED, C_KEPT, C_NEAR_TIES, C_WORK, C_INV, C_HUGE, C_TMP0, C_RUNS, C_COUNT = 32
 };
 
 struct DevIn {
@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(256) k_prefilter(DevIn in, u64 min_len, double
     bool alive = false, zq = false, zt = false, bad = false;
     u32 maxc = 0;
     u64 g = NONE64;
+    u32 qt = NONE32; // (query, target, strand) as one word, for the run count below (ids beyond 2^15 alias: it is only an estimate)
     if (i < in.n) {
         u32 q = in.qid[i], t = in.tid[i];
         u32 qs = in.qs[i], qe = in.qe[i], ts = in.ts[i], te = in.te[i];
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(256) k_prefilter(DevIn in, u64 min_len, double
         maxc = alive ? max(qe, te) : 0u;
         if (alive) g = ((u64)in.P[q] << 32) | in.P[t];
         const bool rev = in.strand[i] != '+';
+        qt = (q << 17) ^ (t << 1) ^ (rev ? 1u : 0u);
         flags[i] = (u8)((alive ? F_ALIVE : 0) | (zq ? F_ZLQ : 0) | (zt ? F_ZLT : 0) | (rev ? F_REV : 0));
         if (KEYS) {
             const u64 grp = alive ? ((((u64)q << sb) | t) << 1 | (rev ? 1 : 0)) : ((1ull << (2 * sb + 1)) - 1); // dead: all ones, sorts last
@@ -133,10 +135,14 @@ __global__ void __launch_bounds__(256) k_prefilter(DevIn in, u64 min_len, double
         if (rec4) rec4[i] = make_uint4(qs, qe, ts, te);
     }
     const u32 full = 0xFFFFFFFFu;
+    // runs of consecutive records with one (query, target, strand): how grouped the input is (the record sort picks its method by
+    // it).  Warp starts count as run starts: an over-estimate by at most n / 32.
+    u32 prev_qt = __shfl_up_sync(full, qt, 1);
+    const bool head = i < in.n && (lane_id() == 0 || prev_qt != qt);
     {
-        const int slots[4] = {C_ALIVE, C_ZLQ, C_ZLT, C_BAD};
-        const u32 vals[4] = {alive ? 1u : 0u, zq ? 1u : 0u, zt ? 1u : 0u, bad ? 1u : 0u};
-        block_count_add<4>(ctr, slots, vals);
+        const int slots[5] = {C_ALIVE, C_ZLQ, C_ZLT, C_BAD, C_RUNS};
+        const u32 vals[5] = {alive ? 1u : 0u, zq ? 1u : 0u, zt ? 1u : 0u, bad ? 1u : 0u, head ? 1u : 0u};
+        block_count_add<5>(ctr, slots, vals);
     }
     u32 mx = __reduce_max_sync(full, maxc);
     if (lane_id() == 0 && mx > (u32)ctr[C_MAXCOORD]) atomicMax((unsigned long long *)&ctr[C_MAXCOORD], (unsigned long long)mx);

@@ -121,6 +121,7 @@ struct Knobs {
     bool pairs_sort = false;   // SWG_SORT_PAIRS=1: the record sort keeps (key, payload) pairs through every pass
     bool no_fused_keys = false; // SWG_NO_FUSED_KEYS=1: the chain sort keys always come from k_chain_keys
     bool no_group_sort = false; // SWG_NO_GROUP_SORT=1: the record sort always runs the LSD passes (radix_sort.cuh)
+    bool group_sort_always = false; // SWG_GROUP_SORT_ALWAYS=1: ... never because the rows look ungrouped (tests)
     u32 group_sort_max = 0;     // SWG_GROUP_SORT_MAX: largest group the group sort accepts (default GS_CTA_MAX; tests lower it)
     u32 fixpoint_min = 0;      // 0 = default
     double max_pair_evals = 0; // 0 = no limit (SWG_MAX_PAIR_EVALS)
@@ -138,6 +139,7 @@ static Knobs read_knobs() {
     k.pairs_sort = on("SWG_SORT_PAIRS");
     k.no_fused_keys = on("SWG_NO_FUSED_KEYS");
     k.no_group_sort = on("SWG_NO_GROUP_SORT");
+    k.group_sort_always = on("SWG_GROUP_SORT_ALWAYS");
     if (const char *v = getenv("SWG_GROUP_SORT_MAX")) k.group_sort_max = (u32)atoi(v);
     if (const char *v = getenv("SWG_LOG_IMPL")) k.cuda_log = strcmp(v, "cuda") == 0;
     if (const char *v = getenv("SWG_FIXPOINT_MIN")) k.fixpoint_min = (u32)atoi(v);
@@ -159,6 +161,7 @@ struct swg_ctx {
     cudaStream_t copy_stream = nullptr;          // second stream: the `matches` column is uploaded behind the kernels
     cudaEvent_t ev_copy[2] = {nullptr, nullptr};
     cudaEvent_t ev_sort[2] = {nullptr, nullptr}; // bracket the one-sweep passes of the record sort
+    cudaEvent_t ev_pre[2] = {nullptr, nullptr};  // bracket k_prefilter
     cudaEvent_t ev_ctr = nullptr;                // marks an early copy of the counters (read while later kernels still run)
     int sort_passes = 0;
     u64 sort_pairs = 0;
@@ -176,9 +179,8 @@ struct swg_ctx {
     Arena score_arena;             // ... and its device copy
     Arena arena;      // per-call scratch
     Arena io;         // staging of host SoA for swg_filter
-    u32 *gtable = nullptr;        // group sort (group_sort.cuh): one counter per possible (query, target, strand) group;
-    size_t gtable_entries = 0;    // all zero between calls, unless a call died half way (gtable_dirty)
-    bool gtable_dirty = false;
+    u32 *gtable = nullptr;        // group sort (group_sort.cuh): per possible (query, target, strand) group a counter (u32, cleared
+    size_t gtable_entries = 0;    // by every call) and its dense number (u32)
     u64 *h_ctr = nullptr; // pinned mirror of the counters
     std::vector<char *> pin;          // pinned pieces for the file front end (text upload, output download)
     std::vector<cudaEvent_t> pin_ev;
@@ -428,6 +430,11 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             S.n_sort_pairs = c->sort_pairs;
             S.sort_bytes_per_pair = c->sort_bytes_per_pair;
         }
+        if (S.prefilter_bytes_per_record) {
+            float ms = 0;
+            cudaStreamSynchronize(st);
+            if (cudaEventElapsedTime(&ms, c->ev_pre[0], c->ev_pre[1]) == cudaSuccess) S.ms_prefilter = ms;
+        }
         if (stats) *stats = S;
     };
     if (N == 0) { SWG_CUDA(cudaStreamSynchronize(st)); finish(); return; }
@@ -486,22 +493,28 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     // The record sort as a counting sort by group (group_sort.cuh) when the table of all possible groups fits.
     const u64 g_entries = 2ull * in.n_seq * in.n_seq;
     const bool gsort = cfg.scaffold_gap != 0 && !K.force_wide && !K.pairs_sort && !K.no_group_sort && g_entries <= GS_MAX_TABLE && 2 * sb0 + 1 <= 31;
-    u32 *gtab = nullptr;
+    u32 *gtab = nullptr, *dtab = nullptr;
     if (gsort) {
         if (c->gtable_entries < g_entries) {
             if (c->gtable) cudaFree(c->gtable);
             c->gtable = nullptr;
             c->gtable_entries = 0;
-            if (cudaMalloc(&c->gtable, g_entries * sizeof(u32)) != cudaSuccess) { cudaGetLastError(); throw OomError{(size_t)g_entries * sizeof(u32)}; }
+            if (cudaMalloc(&c->gtable, g_entries * 8) != cudaSuccess) { cudaGetLastError(); throw OomError{(size_t)g_entries * 8}; }
             c->gtable_entries = g_entries;
-            c->gtable_dirty = true;
         }
-        if (c->gtable_dirty) SWG_CUDA(cudaMemsetAsync(c->gtable, 0, c->gtable_entries * sizeof(u32), st));
-        c->gtable_dirty = true; // until the ordering kernels have put the touched entries back to zero
         gtab = c->gtable;
+        dtab = gtab + g_entries;
+        SWG_CUDA(cudaMemsetAsync(gtab, 0, g_entries * 4, st)); // the counters (37 MB for 2160 sequences: ~10 us)
     }
+    SWG_CUDA(cudaEventRecord(c->ev_pre[0], st));
     if (fused_keys) k_prefilter<true><<<cdiv(N, 256), 256, 0, st>>>(in, cfg.min_block_length, cfg.min_identity, cfg.keep_self, flags, ctr, hk, hv, hcap - 1, rec4, sb0, keys, vals);
     else k_prefilter<false><<<cdiv(N, 256), 256, 0, st>>>(in, cfg.min_block_length, cfg.min_identity, cfg.keep_self, flags, ctr, hk, hv, hcap - 1, rec4);
+    SWG_CUDA(cudaEventRecord(c->ev_pre[1], st));
+    {   // algorithmic bytes of the launch per record: ids 8, coordinates 16, block length 4, strand 1 (+ matches 4 / identity 8 when
+        // the identity test needs them) read; flags 1 (+ packed coordinates 16, + key 8 and index 4 when the pass writes the keys) written
+        const bool need_id = in.identity != nullptr || !(cfg.min_identity <= 0.0);
+        S.prefilter_bytes_per_record = 29 + (need_id ? (in.identity ? 8 : 4) : 0) + 1 + (rec4 ? 16 : 0) + (fused_keys ? 12 : 0);
+    }
     lc.n++;
     read_counters(c);
     if (c->h_ctr[C_BAD])
@@ -566,6 +579,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     const u64 *skey = nullptr;
     bool kept_is_alive = false;   // the keys came from k_prefilter: kept == alive, nobody counted C_KEPT_M
     bool groups_done = false;     // gid / gstart / group count already produced (group sort)
+    const u32 *gs_lists = nullptr; // group sort: [3] groups that had to be ordered, by size class (diagnostic)
     u32 n_groups = 0;
     u32 *gstart = nullptr, *gid = nullptr;
     u32 *d_tot = A.take<u32>(4);
@@ -578,7 +592,10 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         const bool fused_lsd_ok = fused_ok && rs_packed_c0(kb, ib) > 0 && rs_packed_c0(kb, ib) <= cb;
         bool lsd = true;
         int key_shift = cb; // keys[] = (group key << key_shift) | query_start
-        if (gsort) {
+        // rows in no particular order (runs of ~1 record: every step of the group sort turns into random accesses, ~1.6x the
+        // LSD passes on a shuffled 20 M table) go through the LSD passes
+        const bool grouped_rows = (c->h_ctr[C_RUNS] - std::min<u64>(c->h_ctr[C_RUNS], N / 32)) * 2 <= (u64)N || K.group_sort_always;
+        if (gsort && grouped_rows) {
             stage_mark(c, "gs_runs");
             if (fused_ok) { key_shift = 32; kept_is_alive = true; }
             else {
@@ -610,51 +627,52 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             u64 *gs_status = A.take<u64>((size_t)tiles + 2);
             SWG_CUDA(cudaMemsetAsync(gs_status, 0, sizeof(u64) * ((size_t)tiles + 2), st));
             u32 *gs_out = gs_ctr;
-            k_gs_scan<<<tiles, SC_THREADS, 0, st>>>(gtab, (u32)g_entries, in.n_seq, sb, gstart, gkey, gs_status, reinterpret_cast<u32 *>(gs_status + tiles), gs_out);
+            k_gs_scan<<<tiles, SC_THREADS, 0, st>>>(gtab, dtab, (u32)g_entries, in.n_seq, sb, gstart, gkey, gs_status, reinterpret_cast<u32 *>(gs_status + tiles), gs_out);
             lc.n++;
             u32 *h = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
-            SWG_CUDA(cudaMemcpyAsync(h, gs_out, 3 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+            SWG_CUDA(cudaMemcpyAsync(h, gs_out, 4 * sizeof(u32), cudaMemcpyDeviceToHost, st)); // + [3] runs
             read_counters_begin(c); // (C_KEPT_M of k_chain_keys) the host picks the numbers up while the scatter runs
             stage_mark(c, "gs_scatter");
-            k_gs_scatter<<<cdiv(N, 256), 256, 0, st>>>(keys, run_of, run_start, run_base, N, key_shift, sb, in.n_seq, ib, gtab, keys2);
+            gid = A.take<u32>(N);
+            k_gs_scatter<<<cdiv(N, 256), 256, 0, st>>>(keys, run_of, run_start, run_base, N, key_shift, sb, in.n_seq, ib, gtab, dtab, keys2, gid);
             lc.n++;
             read_counters_end(c);
             n_groups = h[0];
             const u32 n_rec = h[1], gmax = h[2];
+            if (getenv("SWG_STAGE_TIMING")) fprintf(stderr, "[swg group sort] records %u runs %u groups %u largest %u\n", n_rec, h[3], n_groups, gmax);
             const u32 limit = K.group_sort_max ? std::min(K.group_sort_max, GS_CTA_MAX) : GS_CTA_MAX;
-            if (n_rec != (kept_is_alive ? (u32)n_alive : (u32)c->h_ctr[C_KEPT_M])) throw RangeError{"group sort: the group table was not clean on entry"};
+            if (n_rec != (kept_is_alive ? (u32)n_alive : (u32)c->h_ctr[C_KEPT_M])) throw RangeError{"group sort: the table counted " + std::to_string(n_rec) + " records"};
             if (n_groups == 0) {
                 lsd = false;
-                c->gtable_dirty = false;
             } else if (gmax <= limit) {
                 stage_mark(c, "gs_order");
                 lsd = false;
-                gid = A.take<u32>(n_rec);
                 u32 *list_warp = A.take<u32>(n_groups), *list_mid = A.take<u32>(n_groups), *list_cta = A.take<u32>(n_groups);
+                u8 *unsorted = A.take<u8>(n_groups);
                 u32 *list_ctr = gs_ctr + 4;
-                k_gs_groups<<<cdiv(n_groups, 256), 256, 0, st>>>(n_groups, gstart, gkey, sb, in.n_seq, ib, gtab, keys2, gid, list_warp, list_mid, list_cta, list_ctr);
-                k_gs_warp<<<(u32)c->sm_count * 8, 256, 0, st>>>(list_warp, list_ctr, gs_ctr + 7, gstart, gkey, ib, keys2, gid);
-                lc.n += 2;
+                u64 *words_out = keys; // the keys have done their duty
+                SWG_CUDA(cudaMemsetAsync(unsorted, 0, n_groups, st));
+                k_gs_emit<<<cdiv(n_rec, 256), 256, 0, st>>>(keys2, gid, gkey, gs_out + 1, ib, words_out, unsorted);
+                k_gs_groups<<<cdiv(n_groups, 256), 256, 0, st>>>(n_groups, gstart, gkey, sb, in.n_seq, ib, unsorted, keys2, words_out, list_warp, list_mid, list_cta, list_ctr);
+                k_gs_warp<<<(u32)c->sm_count * 8, 256, 0, st>>>(list_warp, list_ctr, gs_ctr + 7, gstart, gkey, ib, keys2, words_out);
+                lc.n += 3;
                 if (gmax > GS_WARP_MAX) {
-                    k_gs_mid<<<(u32)c->sm_count * 3, 256, 8 * GS_MID_MAX * sizeof(u64), st>>>(list_mid, list_ctr + 1, gs_ctr + 8, gstart, gkey, ib, keys2, gid);
+                    k_gs_mid<<<(u32)c->sm_count * 3, 256, 8 * GS_MID_MAX * sizeof(u64), st>>>(list_mid, list_ctr + 1, gs_ctr + 8, gstart, gkey, ib, keys2, words_out);
                     lc.n++;
                 }
                 if (gmax > GS_MID_MAX) {
-                    k_gs_cta<<<(u32)c->sm_count * 2, GS_CTA_THREADS, GS_CTA_MAX * sizeof(u64), st>>>(list_cta, list_ctr + 2, gs_ctr + 9, gstart, gkey, ib, keys2, gid);
+                    k_gs_cta<<<(u32)c->sm_count * 2, GS_CTA_THREADS, GS_CTA_MAX * sizeof(u64), st>>>(list_cta, list_ctr + 2, gs_ctr + 9, gstart, gkey, ib, keys2, words_out);
                     lc.n++;
                 }
-                c->gtable_dirty = false;
                 SWG_CUDA(cudaMemcpyAsync(d_tot, gs_out, sizeof(u32), cudaMemcpyDeviceToDevice, st)); // d_tot[0] = group count (k_chain_work_estimate)
-                skey = keys2;
-                sidx.w = keys2;
+                skey = words_out;
+                sidx.w = words_out;
                 sidx.mask = (1ull << ib) - 1;
                 gshift = ib;
                 groups_done = true;
+                gs_lists = list_ctr;
             } else {
                 // some group is larger than one CTA sorts: the LSD passes take over (the keys are still in place)
-                k_gs_clean<<<cdiv(n_groups, 256), 256, 0, st>>>(n_groups, gkey, sb, in.n_seq, gtab);
-                lc.n++;
-                c->gtable_dirty = false;
                 if (key_shift == 32 && !fused_lsd_ok) { // the gap layout does not suit the LSD passes of this key width
                     k_chain_keys<<<cdiv(N, 256), 256, 0, st>>>(in, flags, keep_q, keep_t, sb, cb, keys, vals, ctr);
                     lc.n++;
@@ -859,6 +877,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         u32 *h = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
         SWG_CUDA(cudaMemcpyAsync(h, d_nch, sizeof(u32), cudaMemcpyDeviceToHost, st));
         SWG_CUDA(cudaMemcpyAsync(h + 2, bb_ctr, 4 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+        if (gs_lists) SWG_CUDA(cudaMemcpyAsync(h + 6, gs_lists, 3 * sizeof(u32), cudaMemcpyDeviceToHost, st));
         SWG_CUDA(cudaEventRecord(c->ev_ctr, st));
     }
     if (ev_matches) SWG_CUDA(cudaStreamWaitEvent(st, ev_matches, 0)); // first use of in.matches
@@ -870,6 +889,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         const u32 *h = reinterpret_cast<const u32 *>(c->h_ctr + C_COUNT);
         C = h[0];
         S.n_dirty_groups = (u64)h[2] + h[4];
+        if (gs_lists) S.n_unsorted_groups = (u64)h[6] + h[7] + h[8];
     }
     stage_mark(c, "chain_table");
     S.n_chains = C;
@@ -1735,6 +1755,7 @@ swg_ctx *swg_create(int device) {
         SWG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         for (auto &ev : c->ev) SWG_CUDA(cudaEventCreate(&ev));
         for (auto &ev : c->ev_sort) SWG_CUDA(cudaEventCreate(&ev));
+        for (auto &ev : c->ev_pre) SWG_CUDA(cudaEventCreate(&ev));
         SWG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         for (auto &ev : c->ev_copy) SWG_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         SWG_CUDA(cudaEventCreateWithFlags(&c->ev_ctr, cudaEventDisableTiming));
@@ -1770,6 +1791,7 @@ void swg_destroy(swg_ctx *c) {
     if (c->gtable) cudaFree(c->gtable);
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : c->ev_sort) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : c->ev_pre) if (ev) cudaEventDestroy(ev);
     for (auto &ev : c->ev_copy) if (ev) cudaEventDestroy(ev);
     if (c->ev_ctr) cudaEventDestroy(c->ev_ctr);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);

@@ -5,16 +5,21 @@
 // (query_start, input index)), produced with far fewer passes over the records when no group is huge:
 //
 //   runs     (scan_flags in the caller) a run = maximal stretch of consecutive input records with the same group key; every
-//            record learns its run, every run its first record.  Aligner output is grouped, so a group usually IS one run.
-//   count    k_gs_run_base: one atomicAdd per run on a dense table indexed by (query * n_seq + target) * 2 + strand: the
-//            run's slot range inside its group.  A group that is a single run gets slots in input order, deterministically.
+//            record learns its run, every run its first record.  Aligner output is grouped, so a group is one run or a few.
+//   count    k_gs_run_base: the run's slot range inside its group from an atomicAdd on a dense table indexed by
+//            (query * n_seq + target) * 2 + strand.  Runs of one group handled by the same warp share one atomic and take
+//            their ranges in input order; across warps the ranges follow the arrival of the atomics.
 //   scan     k_gs_scan: one pass over the table: start of every non-empty group, dense group numbers, largest group
-//   scatter  k_gs_scatter: record -> words[start(group) + base(run) + offset in run] = (query_start << ib) | index
-//   order    k_gs_groups (thread per group: sizes 1, 2), k_gs_warp (warp per group, <= 128 records: registers),
-//            k_gs_mid (warp per group, <= 1024: shared memory), k_gs_cta (CTA per group, <= 8192): a group that already is in
-//            order — an input sorted by position inside its groups — is only checked; otherwise a bitonic network sorts it.
-//            They write the result in the layout of the packed LSD sort — (group key << ib) | index — plus the group index of
-//            every position, and put the table entries back to zero.
+//   scatter  k_gs_scatter: record -> sort word (query_start << ib) | index at start(group) + base(run) + offset in run, and
+//            the group index of that position
+//   emit     k_gs_emit: one flat pass writes the final form of every position and marks the groups in which some word is
+//            smaller than its predecessor.  Input that is sorted by position inside its groups ends here unless the runs of
+//            a group arrived out of order.
+//   order    marked groups only: k_gs_groups lists them by size (pairs are finished there); k_gs_warp (warp per group,
+//            <= 128 records: registers), k_gs_mid (warp per group, <= 1024: shared memory), k_gs_cta (CTA per group,
+//            <= 8192) merge the group's ascending pieces (or run a bitonic network over the sort words when there are many)
+//            and overwrite the group's final words.
+//   Final form = the layout of the packed LSD sort, (group key << ib) | index, plus the group index of every position.
 //
 // A one-sweep LSD pass is bound by the SM (warp ranking + shared-memory staging) at ~0.15 ms per 20 M records and
 // the 53-bit key needs seven of them; this path touches every record three times.  When some group is larger than
@@ -37,26 +42,61 @@ __device__ __forceinline__ u32 gs_index_of_key(u32 grp, int sb, u32 n_seq) {
     return gs_index(grp >> (sb + 1), (grp >> 1) & ((1u << sb) - 1), grp & 1, n_seq);
 }
 
-// ---- count: one atomic per run ---------------------------------------------------------------------------------------------
+// ---- count: slot ranges of the runs ------------------------------------------------------------------------------------------
 // keys[i] = (group key << shift) | query_start; dead records carry the all-ones group key (their runs are skipped).
+// A warp owns GS_RUN_CHUNK consecutive runs and walks them 32 at a time, in order.  Lanes whose runs belong to one group (a '+'
+// group interrupted by records of other groups) issue ONE atomic and split the range in lane order, and the next 32 runs are
+// taken up only after that atomic has returned: the runs of a group that lie inside one chunk get their ranges in input order.
+// Runs of one group in different chunks race; k_gs_emit finds the groups this disorders and the ordering kernels repair them.
+constexpr u32 GS_RUN_CHUNK = 1024;
 __global__ void __launch_bounds__(256) k_gs_run_base(const u32 *__restrict__ n_runs_ptr, const u32 *__restrict__ run_start, u32 n,
                                                      const u64 *__restrict__ keys, int shift, int sb, u32 n_seq, u32 *__restrict__ table,
                                                      u32 *__restrict__ run_base) {
     const u32 n_runs = *n_runs_ptr;
-    for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < n_runs; r += gridDim.x * blockDim.x) {
-        const u32 i0 = run_start[r], i1 = r + 1 < n_runs ? run_start[r + 1] : n;
-        const u32 grp = (u32)(keys[i0] >> shift);
-        if (grp == (1u << (2 * sb + 1)) - 1) continue; // dead
-        run_base[r] = atomicAdd(&table[gs_index_of_key(grp, sb, n_seq)], i1 - i0);
+    const u32 lane = threadIdx.x & 31, full = 0xFFFFFFFFu;
+    const u32 n_warps = (gridDim.x * blockDim.x) >> 5;
+    const u32 n_chunks = (n_runs + GS_RUN_CHUNK - 1) / GS_RUN_CHUNK;
+    for (u32 chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < n_chunks; chunk += n_warps) {
+        const u32 c0 = chunk * GS_RUN_CHUNK, c1 = min(c0 + GS_RUN_CHUNK, n_runs);
+        // this lane's run of the first round; the loads of the next round are issued before the atomic of the current one
+        u32 r = c0 + lane;
+        u32 i0 = r < c1 ? run_start[r] : 0, i1 = r < c1 ? (r + 1 < n_runs ? run_start[r + 1] : n) : 0;
+        u64 k0 = r < c1 ? keys[i0] : 0;
+        for (u32 r0 = c0; r0 < c1; r0 += 32) {
+            const u32 rn = r0 + 32 + lane;
+            const u32 ni0 = rn < c1 ? run_start[rn] : 0, ni1 = rn < c1 ? (rn + 1 < n_runs ? run_start[rn + 1] : n) : 0;
+            const u64 nk0 = rn < c1 ? keys[ni0] : 0;
+            u32 gi = NONE32, len = 0;
+            if (r < c1) {
+                const u32 grp = (u32)(k0 >> shift);
+                if (grp != (1u << (2 * sb + 1)) - 1) { gi = gs_index_of_key(grp, sb, n_seq); len = i1 - i0; }
+            }
+            const u32 peers = __match_any_sync(full, gi);
+            u32 before = 0, total = len;
+            if (__any_sync(full, peers != (1u << lane))) { // some group has several runs among these 32
+                total = 0;
+#pragma unroll 8
+                for (u32 l = 0; l < 32; l++) {
+                    const u32 v = __shfl_sync(full, len, l);
+                    if ((peers >> l) & 1) { total += v; if (l < lane) before += v; }
+                }
+            }
+            const u32 leader = (u32)__ffs(peers) - 1;
+            u32 base = 0;
+            if (lane == leader && gi != NONE32) base = atomicAdd(&table[gi], total);
+            base = __shfl_sync(full, base, leader); // (waits for the atomic: the next round's atomics are issued after it)
+            if (gi != NONE32) run_base[r] = base + before;
+            r = rn; i0 = ni0; i1 = ni1; k0 = nk0;
+        }
     }
 }
 
 // ---- scan of the table ---------------------------------------------------------------------------------------------------
 // One pass, decoupled look-back over tiles (the scheme of scan.cuh) on a packed pair (non-empty groups before << 31 | records
-// before).  Non-empty entry g: table[g] = start + 1 (0 stays "empty"), gstart[dense] = start, gkey[dense] = bit-packed key.
+// before).  Non-empty entry g: table[g] = start + 1 (0 stays "empty"), dtab[g] = dense, gstart[dense] = start, gkey[dense] = bit-packed key.
 // out[0] = number of groups, out[1] = number of records, out[2] = largest group; gstart[n_groups] = number of records.
-__global__ void __launch_bounds__(SC_THREADS) k_gs_scan(u32 *__restrict__ table, u32 n_entries, u32 n_seq, int sb, u32 *__restrict__ gstart,
-                                                        u32 *__restrict__ gkey, u64 *status, u32 *tile_counter, u32 *out) {
+__global__ void __launch_bounds__(SC_THREADS) k_gs_scan(u32 *__restrict__ table, u32 *__restrict__ dtab, u32 n_entries, u32 n_seq, int sb,
+                                                        u32 *__restrict__ gstart, u32 *__restrict__ gkey, u64 *status, u32 *tile_counter, u32 *out) {
     __shared__ u64 ws[SC_THREADS / 32];
     __shared__ u32 s_tile, s_max;
     __shared__ u64 s_excl;
@@ -142,6 +182,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_gs_scan(u32 *__restrict__ table,
             const u32 g = base + k;
             const u32 start = (u32)(ex & 0x7FFFFFFFu), dense = (u32)(ex >> 31);
             table[g] = start + 1;
+            dtab[g] = dense;
             gstart[dense] = start;
             const u32 pair = g >> 1, q = pair / n_seq, t = pair - q * n_seq;
             gkey[dense] = (((q << sb) | t) << 1) | (g & 1);
@@ -153,7 +194,8 @@ __global__ void __launch_bounds__(SC_THREADS) k_gs_scan(u32 *__restrict__ table,
 // ---- scatter ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_gs_scatter(const u64 *__restrict__ keys, const u32 *__restrict__ run_of, const u32 *__restrict__ run_start,
                                                     const u32 *__restrict__ run_base, u32 n, int shift, int sb, u32 n_seq, int ib,
-                                                    const u32 *__restrict__ table, u64 *__restrict__ words) {
+                                                    const u32 *__restrict__ table, const u32 *__restrict__ dtab,
+                                                    u64 *__restrict__ words, u32 *__restrict__ gid) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const u64 k = keys[i];
@@ -161,34 +203,43 @@ __global__ void __launch_bounds__(256) k_gs_scatter(const u64 *__restrict__ keys
     if (grp == (1u << (2 * sb + 1)) - 1) return; // dead
     const u32 qs = (u32)(k & ((1ull << shift) - 1));
     const u32 r = run_of[i];
-    const u32 start1 = table[gs_index_of_key(grp, sb, n_seq)];
-    words[start1 - 1 + run_base[r] + (i - run_start[r])] = ((u64)qs << ib) | i;
+    const u32 gi = gs_index_of_key(grp, sb, n_seq);
+    const u32 pos = table[gi] - 1 + run_base[r] + (i - run_start[r]);
+    words[pos] = ((u64)qs << ib) | i;
+    gid[pos] = dtab[gi];
+}
+
+// ---- emit: final form of every position, groups that are not in order ------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gs_emit(const u64 *__restrict__ words, const u32 *__restrict__ gid, const u32 *__restrict__ gkey,
+                                                 const u32 *__restrict__ n_rec_ptr, int ib, u64 *__restrict__ out, u8 *__restrict__ unsorted) {
+    const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= *n_rec_ptr) return;
+    const u64 w = words[p];
+    const u32 d = gid[p];
+    out[p] = ((u64)gkey[d] << ib) | (w & ((1ull << ib) - 1));
+    if (p > 0 && gid[p - 1] == d && words[p - 1] > w) unsorted[d] = 1;
 }
 
 // ---- order inside the groups --------------------------------------------------------------------------------------------
-// thread per group: puts the table entry back to zero, finishes groups of one or two records, lists the others.
+// thread per group: lists the groups k_gs_emit marked by size (pairs are finished here)
 __global__ void __launch_bounds__(256) k_gs_groups(u32 n_groups, const u32 *__restrict__ gstart, const u32 *__restrict__ gkey, int sb, u32 n_seq,
-                                                   int ib, u32 *__restrict__ table, u64 *__restrict__ words, u32 *__restrict__ gid,
+                                                   int ib, const u8 *__restrict__ unsorted, const u64 *__restrict__ words, u64 *__restrict__ out,
                                                    u32 *__restrict__ list_warp, u32 *__restrict__ list_mid, u32 *__restrict__ list_cta,
                                                    u32 *__restrict__ list_ctr /*[3]*/) {
     const u32 d = blockIdx.x * blockDim.x + threadIdx.x;
     u32 cls = 0; // 1: warp list, 2: mid list, 3: CTA list
     if (d < n_groups) {
-        const u32 s = gstart[d], e = gstart[d + 1], grp = gkey[d];
-        table[gs_index_of_key(grp, sb, n_seq)] = 0;
-        const u64 hi = (u64)grp << ib, mask = (1ull << ib) - 1;
-        const u32 size = e - s;
-        if (size == 1) {
-            words[s] = hi | (words[s] & mask);
-            gid[s] = d;
-        } else if (size == 2) {
-            u64 a = words[s], b = words[s + 1];
-            if (b < a) { const u64 t = a; a = b; b = t; }
-            words[s] = hi | (a & mask);
-            words[s + 1] = hi | (b & mask);
-            gid[s] = d;
-            gid[s + 1] = d;
-        } else cls = size <= GS_WARP_MAX ? 1 : size <= GS_MID_MAX ? 2 : 3;
+        const u32 grp = gkey[d];
+        if (unsorted[d]) {
+            const u32 s = gstart[d], size = gstart[d + 1] - s;
+            if (size == 2) {
+                const u64 hi = (u64)grp << ib, mask = (1ull << ib) - 1;
+                u64 a = words[s], b = words[s + 1];
+                if (b < a) { const u64 t = a; a = b; b = t; }
+                out[s] = hi | (a & mask);
+                out[s + 1] = hi | (b & mask);
+            } else cls = size <= GS_WARP_MAX ? 1 : size <= GS_MID_MAX ? 2 : 3;
+        }
     }
     const u32 full = 0xFFFFFFFFu, lt = lanemask_lt();
 #pragma unroll
@@ -233,11 +284,11 @@ template <int R> __device__ __forceinline__ void gs_bitonic_warp(u64 (&x)[R], u3
     }
 }
 template <int R>
-__device__ __forceinline__ void gs_warp_group(u64 *__restrict__ words, u32 *__restrict__ gid, u32 s, u32 size, u32 d, u64 hi, u64 mask, u32 lane) {
+__device__ __forceinline__ void gs_warp_group(const u64 *__restrict__ words, u64 *__restrict__ out, u32 s, u32 size, u64 hi, u64 mask, u32 lane) {
     u64 x[R];
 #pragma unroll
     for (int r = 0; r < R; r++) x[r] = (u32)(r * 32) + lane < size ? words[s + r * 32 + lane] : NONE64;
-    bool ok = true; // already in order?  (arrival order of a group that sits in one warp of the counting pass is input order)
+    bool ok = true; // in order after all?  (several runs that happened to arrive in input order)
 #pragma unroll
     for (int r = 0; r < R; r++) {
         u64 prev = __shfl_up_sync(0xFFFFFFFFu, x[r], 1);
@@ -249,16 +300,13 @@ __device__ __forceinline__ void gs_warp_group(u64 *__restrict__ words, u32 *__re
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const u32 p = (u32)(r * 32) + lane;
-        if (p < size) {
-            words[s + p] = hi | (x[r] & mask);
-            gid[s + p] = d;
-        }
+        if (p < size) out[s + p] = hi | (x[r] & mask);
     }
 }
 // warp per listed group (3 .. GS_WARP_MAX records), warps take groups from a counter
 __global__ void __launch_bounds__(256) k_gs_warp(const u32 *__restrict__ list, const u32 *__restrict__ n_list_ptr, u32 *work_ctr,
-                                                 const u32 *__restrict__ gstart, const u32 *__restrict__ gkey, int ib, u64 *__restrict__ words,
-                                                 u32 *__restrict__ gid) {
+                                                 const u32 *__restrict__ gstart, const u32 *__restrict__ gkey, int ib, const u64 *__restrict__ words,
+                                                 u64 *__restrict__ out) {
     const u32 lane = threadIdx.x & 31;
     const u32 n_list = *n_list_ptr;
     const u64 mask = (1ull << ib) - 1;
@@ -270,21 +318,68 @@ __global__ void __launch_bounds__(256) k_gs_warp(const u32 *__restrict__ list, c
         const u32 d = list[w];
         const u32 s = gstart[d], size = gstart[d + 1] - s;
         const u64 hi = (u64)gkey[d] << ib;
-        if (size <= 32) gs_warp_group<1>(words, gid, s, size, d, hi, mask, lane);
-        else if (size <= 64) gs_warp_group<2>(words, gid, s, size, d, hi, mask, lane);
-        else gs_warp_group<4>(words, gid, s, size, d, hi, mask, lane);
+        if (size <= 32) gs_warp_group<1>(words, out, s, size, hi, mask, lane);
+        else if (size <= 64) gs_warp_group<2>(words, out, s, size, hi, mask, lane);
+        else gs_warp_group<4>(words, out, s, size, hi, mask, lane);
     }
 }
 static_assert(GS_WARP_MAX == 128, "gs_warp_group<4> holds 128 words");
 
+// A group that is not in order usually is a few ascending pieces: its runs took their slot ranges out of input order, or an
+// ordered block is followed by some stray records.  Such a group is MERGED: the final position of a word is its offset inside its
+// own piece plus, for every other piece, the number of words below it there (binary search; one comparison when the piece lies
+// wholly below or above the word).  The sort words are distinct (they end in the record index), so the positions are a permutation.
+constexpr u32 GS_MERGE_MAX = 16; // pieces; beyond that the sorting network is cheaper
+// One warp: finds the pieces of sm[0, size) and writes their starts to pstart[0 .. n], pstart[n] = size.  Returns n, or 0 if
+// there are more than GS_MERGE_MAX.
+__device__ __forceinline__ u32 gs_find_pieces_warp(const u64 *sm, u32 size, u32 *pstart, u32 lane) {
+    const u32 full = 0xFFFFFFFFu;
+    u32 n_pieces = 0;
+    for (u32 base = 0; base < size; base += 32) {
+        const u32 p = base + lane;
+        const bool head = p < size && (p == 0 || sm[p - 1] > sm[p]);
+        const u32 m = __ballot_sync(full, head);
+        const u32 cnt = (u32)__popc(m);
+        if (n_pieces + cnt > GS_MERGE_MAX) return 0;
+        if (head) pstart[n_pieces + __popc(m & ((1u << lane) - 1))] = p;
+        n_pieces += cnt;
+    }
+    if (lane == 0) pstart[n_pieces] = size;
+    return n_pieces;
+}
+// The threads tid, tid + nthreads, ... of a warp or CTA (after a barrier that makes pstart visible) write the merged group.
+__device__ __forceinline__ void gs_merge_pieces(const u64 *sm, u32 size, const u32 *pstart, u32 n_pieces, u64 *__restrict__ dst, u64 hi,
+                                                u64 mask, u32 tid, u32 nthreads) {
+    for (u32 e = tid; e < size; e += nthreads) {
+        const u64 x = sm[e];
+        u32 rank = 0;
+        for (u32 j = 0; j < n_pieces; j++) {
+            const u32 a = pstart[j], b = pstart[j + 1];
+            if (e >= a && e < b) rank += e - a;
+            else if (sm[b - 1] < x) rank += b - a;
+            else if (sm[a] < x) {
+                u32 lo = a + 1, up = b - 1; // sm[a] < x < sm[b - 1]
+                while (lo < up) {
+                    const u32 mid = (lo + up) >> 1;
+                    if (sm[mid] < x) lo = mid + 1; else up = mid;
+                }
+                rank += lo - a;
+            }
+        }
+        dst[rank] = hi | (x & mask);
+    }
+}
+
 // warp per listed group (GS_WARP_MAX + 1 .. GS_MID_MAX records): the group in the warp's own 8 KB of shared memory; no block
 // barrier anywhere, the eight warps of a CTA work on eight groups
 __global__ void __launch_bounds__(256) k_gs_mid(const u32 *__restrict__ list, const u32 *__restrict__ n_list_ptr, u32 *work_ctr,
-                                                const u32 *__restrict__ gstart, const u32 *__restrict__ gkey, int ib, u64 *__restrict__ words,
-                                                u32 *__restrict__ gid) {
+                                                const u32 *__restrict__ gstart, const u32 *__restrict__ gkey, int ib, const u64 *__restrict__ words,
+                                                u64 *__restrict__ out) {
     extern __shared__ __align__(16) unsigned char gs_smem_raw[];
     const u32 lane = threadIdx.x & 31;
     u64 *sm = reinterpret_cast<u64 *>(gs_smem_raw) + (threadIdx.x >> 5) * GS_MID_MAX;
+    __shared__ u32 s_pst[8][GS_MERGE_MAX + 2];
+    u32 *pst = s_pst[threadIdx.x >> 5];
     const u32 n_list = *n_list_ptr;
     const u64 mask = (1ull << ib) - 1;
     while (true) {
@@ -300,35 +395,34 @@ __global__ void __launch_bounds__(256) k_gs_mid(const u32 *__restrict__ list, co
         __syncwarp();
         for (u32 p = lane; p < np; p += 32) sm[p] = p < size ? words[s + p] : NONE64;
         __syncwarp();
-        bool bad = false;
-        for (u32 p = lane + 1; p < size; p += 32) bad |= sm[p - 1] > sm[p];
-        if (__any_sync(0xFFFFFFFFu, bad)) {
-            for (u32 k = 2; k <= np; k <<= 1) {
-                for (u32 j = k >> 1; j > 0; j >>= 1) {
-                    for (u32 t = lane; t < np / 2; t += 32) {
-                        const u32 i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), o = i | j;
-                        const u64 a = sm[i], b = sm[o];
-                        const bool up = (i & k) == 0;
-                        if (up ? a > b : a < b) { sm[i] = b; sm[o] = a; }
-                    }
-                    __syncwarp();
+        const u32 n_pieces = gs_find_pieces_warp(sm, size, pst, lane);
+        __syncwarp();
+        if (n_pieces) { // a few ascending pieces: merge
+            gs_merge_pieces(sm, size, pst, n_pieces, out + s, hi, mask, lane, 32);
+            continue;
+        }
+        for (u32 k = 2; k <= np; k <<= 1) {
+            for (u32 j = k >> 1; j > 0; j >>= 1) {
+                for (u32 t = lane; t < np / 2; t += 32) {
+                    const u32 i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), o = i | j;
+                    const u64 a = sm[i], b = sm[o];
+                    const bool up = (i & k) == 0;
+                    if (up ? a > b : a < b) { sm[i] = b; sm[o] = a; }
                 }
+                __syncwarp();
             }
         }
-        for (u32 p = lane; p < size; p += 32) {
-            words[s + p] = hi | (sm[p] & mask);
-            gid[s + p] = d;
-        }
+        for (u32 p = lane; p < size; p += 32) out[s + p] = hi | (sm[p] & mask);
     }
 }
 
 // CTA per listed group (GS_MID_MAX + 1 .. GS_CTA_MAX records): the group in shared memory, in-order check, bitonic network
 __global__ void __launch_bounds__(GS_CTA_THREADS) k_gs_cta(const u32 *__restrict__ list, const u32 *__restrict__ n_list_ptr, u32 *work_ctr,
                                                            const u32 *__restrict__ gstart, const u32 *__restrict__ gkey, int ib,
-                                                           u64 *__restrict__ words, u32 *__restrict__ gid) {
+                                                           const u64 *__restrict__ words, u64 *__restrict__ out) {
     extern __shared__ __align__(16) unsigned char gs_smem_raw[];
     u64 *sm = reinterpret_cast<u64 *>(gs_smem_raw);
-    __shared__ u32 s_w;
+    __shared__ u32 s_w, s_done, s_pst[GS_MERGE_MAX + 2];
     const u32 n_list = *n_list_ptr;
     const u64 mask = (1ull << ib) - 1;
     while (true) {
@@ -344,32 +438,28 @@ __global__ void __launch_bounds__(GS_CTA_THREADS) k_gs_cta(const u32 *__restrict
         while (np < size) np <<= 1;
         for (u32 p = threadIdx.x; p < np; p += GS_CTA_THREADS) sm[p] = p < size ? words[s + p] : NONE64;
         __syncthreads();
-        int bad = 0;
-        for (u32 p = threadIdx.x + 1; p < size; p += GS_CTA_THREADS) bad |= sm[p - 1] > sm[p];
-        if (__syncthreads_or(bad)) {
-            for (u32 k = 2; k <= np; k <<= 1) {
-                for (u32 j = k >> 1; j > 0; j >>= 1) {
-                    for (u32 t = threadIdx.x; t < np / 2; t += GS_CTA_THREADS) {
-                        const u32 i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), o = i | j;
-                        const u64 a = sm[i], b = sm[o];
-                        const bool up = (i & k) == 0;
-                        if (up ? a > b : a < b) { sm[i] = b; sm[o] = a; }
-                    }
-                    __syncthreads();
+        if (threadIdx.x < 32) { // a few ascending pieces: merge
+            const u32 np_ = gs_find_pieces_warp(sm, size, s_pst, threadIdx.x);
+            if (threadIdx.x == 0) s_done = np_;
+        }
+        __syncthreads();
+        if (s_done) {
+            gs_merge_pieces(sm, size, s_pst, s_done, out + s, hi, mask, threadIdx.x, GS_CTA_THREADS);
+            continue;
+        }
+        for (u32 k = 2; k <= np; k <<= 1) {
+            for (u32 j = k >> 1; j > 0; j >>= 1) {
+                for (u32 t = threadIdx.x; t < np / 2; t += GS_CTA_THREADS) {
+                    const u32 i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), o = i | j;
+                    const u64 a = sm[i], b = sm[o];
+                    const bool up = (i & k) == 0;
+                    if (up ? a > b : a < b) { sm[i] = b; sm[o] = a; }
                 }
+                __syncthreads();
             }
         }
-        for (u32 p = threadIdx.x; p < size; p += GS_CTA_THREADS) {
-            words[s + p] = hi | (sm[p] & mask);
-            gid[s + p] = d;
-        }
+        for (u32 p = threadIdx.x; p < size; p += GS_CTA_THREADS) out[s + p] = hi | (sm[p] & mask);
     }
-}
-
-// fallback (some group is larger than GS_CTA_MAX: the caller sorts with the LSD passes): only put the table back to zero
-__global__ void __launch_bounds__(256) k_gs_clean(u32 n_groups, const u32 *__restrict__ gkey, int sb, u32 n_seq, u32 *__restrict__ table) {
-    const u32 d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d < n_groups) table[gs_index_of_key(gkey[d], sb, n_seq)] = 0;
 }
 
 static inline void gs_init_device() {

@@ -352,6 +352,7 @@ def test_group_sort_paths(ctx, yeast, case, knob, monkeypatch):
     the path of a real input with one huge group.  Same result on grouped and on shuffled rows."""
     if knob:
         monkeypatch.setenv(knob, "8" if knob == "SWG_GROUP_SORT_MAX" else "1")
+    monkeypatch.setenv("SWG_GROUP_SORT_ALWAYS", "1")  # also for the shuffled rows (by default they would take the LSD passes)
     cfg = swg.FilterConfig.from_cli(**CLI_CASES[case])
     check(ctx, cfg, yeast, f"yeast {knob}")
     check(ctx, cfg, _shuffled(yeast, 1), f"yeast shuffled {knob}")
@@ -361,10 +362,11 @@ def test_group_sort_paths(ctx, yeast, case, knob, monkeypatch):
 
 
 @pytest.mark.parametrize("seed", range(6))
-def test_group_sort_size_classes(ctx, seed):
+def test_group_sort_size_classes(ctx, seed, monkeypatch):
     """Shuffled rows with groups of every size class: one or two records (thread), 3..32 / 33..64 / 65..128 (warp network,
     1 / 2 / 4 words per lane), 129..8192 (CTA in shared memory) and, seed 5, one group beyond that (LSD fallback); many
     equal query starts, so the index tie-break of the stable order is exercised."""
+    monkeypatch.setenv("SWG_GROUP_SORT_ALWAYS", "1")
     rng = np.random.default_rng(700 + seed)
     sizes = {0: [1, 2, 3, 5, 31, 32, 33, 63, 64, 65, 100, 127, 128], 1: [129, 200, 256, 257, 1000, 2048, 2049], 2: [8191, 8192, 4097, 3, 1],
              3: list(rng.integers(1, 300, 60)), 4: list(rng.integers(1, 40, 400)), 5: [8193, 50, 2, 1]}[seed]
@@ -400,3 +402,49 @@ def test_group_sort_table_survives_a_failed_call(ctx, yeast):
         with pytest.raises(swg.SwgError):
             ctx.filter(swg.FilterConfig(), bad)
     check(ctx, swg.FilterConfig(), yeast, "after a failed call")
+
+
+def test_record_sort_method_follows_the_row_order(ctx):
+    """Grouped rows (aligner order): counting sort by group, no LSD pass.  The same rows shuffled: the LSD passes (every step of
+    the group sort would be a random access).  Same result either way."""
+    t = synth.pansn(600_000, seed=41, n_hap=8)
+    cfg = swg.FilterConfig()
+    s1, c1, st1 = check(ctx, cfg, t, "grouped rows")
+    assert st1.n_sort_passes == 0
+    perm = np.random.default_rng(5).permutation(t.n)
+    t2 = _shuffled(t, 5)
+    s2, c2, st2 = check(ctx, cfg, t2, "shuffled rows")
+    assert st2.n_sort_passes > 0
+    assert np.array_equal(s1[perm], s2)
+
+
+@pytest.mark.parametrize("n_blocks,group", [(5, 700), (31, 3000), (40, 3000), (7, 6000)])
+def test_group_sort_pieces_out_of_place(ctx, n_blocks, group, monkeypatch):
+    """A big group whose rows come as a few ascending blocks in the wrong order, separated by rows of other groups (what racing
+    slot ranges of a group's runs produce): repaired by putting the pieces into order (up to 32 pieces), by the sorting network
+    beyond that and when the blocks interleave."""
+    monkeypatch.setenv("SWG_GROUP_SORT_ALWAYS", "1")
+    rng = np.random.default_rng(n_blocks * 1000 + group)
+    names = [f"G{g}#1#c{c}" for g in range(2) for c in range(4)]
+    for interleave in (False, True):
+        qs_big = np.sort(rng.integers(0, 3_000_000, group)) * 10
+        if interleave:  # blocks = residue classes: every block spans the whole range
+            blocks = [qs_big[k::n_blocks] for k in range(n_blocks)]
+        else:
+            blocks = np.array_split(qs_big, n_blocks)
+        order = rng.permutation(n_blocks)
+        qid, tid, qs = [], [], []
+        for k in order:
+            qid += [0] * len(blocks[k]); tid += [4] * len(blocks[k]); qs += list(blocks[k])
+            qid += [1, 2]; tid += [5, 6]; qs += list(rng.integers(0, 1000, 2))  # separators: two other groups
+        n = len(qid)
+        qs = np.array(qs)
+        ln = rng.integers(200, 4000, n)
+        ts = qs + rng.integers(-500, 500, n) + 1000
+        blk = ln + 5
+        matches = np.rint(blk * 0.95).astype(np.int64)
+        P, P2 = swg.prefix_ids(names)
+        t = swg.MappingTable(np.array(qid), np.array(tid), qs, qs + ln, ts, ts + ln, blk, matches, matches / blk, np.full(n, ord("+"), np.uint8), P, P2,
+                             None, names)
+        _, _, st = check(ctx, swg.FilterConfig.from_cli(scaffold_mass="0"), t, f"pieces {n_blocks} x {group} interleave={interleave}")
+        assert st.n_sort_passes == 0 and st.n_unsorted_groups >= 1
