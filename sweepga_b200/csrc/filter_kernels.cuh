@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) k_prefilter(DevIn in, u64 min_len, double
         // without an identity column and with a threshold <= 0 the test is always true (matches / block >= 0): `matches`
         // is then not read here and its upload overlaps this kernel and the sort
         const bool id_ok = (!in.identity && min_id <= 0.0) ? true : rec_identity(in, i) >= min_id;
-        alive = !bad_id && (u64)in.blen[i] >= min_len && (keep_self || q != t) && id_ok;
+        alive = !bad_id && (min_len == 0 || (u64)in.blen[i] >= min_len) && (keep_self || q != t) && id_ok; // (min_len 0: block_length not read)
         // an impossible interval is an error only if the record survives the retain: the reference (u64, no check) would
         // have dropped it here too (paf_filter.rs:384-388)
         bad = bad_id || (alive && bad_iv);

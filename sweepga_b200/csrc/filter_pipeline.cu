@@ -475,7 +475,9 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     SWG_CUDA(cudaMemsetAsync(hv, 0xFF, sizeof(u32) * hcap, st));
     uint4 *rec4 = nullptr;
     if (cfg.scaffold_gap != 0) rec4 = A.take<uint4>(N);
-    if (ev_matches && !in.identity && !(cfg.min_identity <= 0.0)) SWG_CUDA(cudaStreamWaitEvent(st, ev_matches, 0)); // identity is derived from `matches`
+    // swg_filter sends `matches` — and `block_length`, when the retain does not test it — behind the other columns: k_prefilter waits
+    // for them only if it derives the identity from them
+    if (ev_matches && !in.identity && !(cfg.min_identity <= 0.0)) SWG_CUDA(cudaStreamWaitEvent(st, ev_matches, 0));
     // The chain sort keys can be written by the same pass when the primary sweep is the closed form (no per-axis limit): then
     // kept == alive unless an alive record has an empty interval (checked below; k_chain_keys redoes the keys in that case).
     const int sb0 = bits_for(in.n_seq);
@@ -1557,7 +1559,8 @@ static bool is_pageable(const void *p) {
     return at.type == cudaMemoryTypeUnregistered;
 }
 
-struct UploadArgs { swg_ctx *c; const swg_mappings *in; swg_mappings *dev; swg_result *res; Arena *arena; bool overlap_matches = false; size_t h2d_bytes = 0; bool pageable = false; };
+struct UploadArgs { swg_ctx *c; const swg_mappings *in; swg_mappings *dev; swg_result *res; Arena *arena; bool overlap_matches = false; size_t h2d_bytes = 0; bool pageable = false;
+                    bool late_blen = false; /* block_length travels with `matches` (the retain does not test it: min_block_length == 0) */ };
 
 struct t_widen;
 static void do_upload(void *p) {
@@ -1587,7 +1590,7 @@ static void do_upload(void *p) {
     else { d.query_id = (const u32 *)col(h->query_id, n, 4, first); d.target_id = (const u32 *)col(h->target_id, n, 4, first); }
     d.query_start = (const u32 *)col(h->query_start, n, 4, first); d.query_end = (const u32 *)col(h->query_end, n, 4, first);
     d.target_start = (const u32 *)col(h->target_start, n, 4, first); d.target_end = (const u32 *)col(h->target_end, n, 4, first);
-    d.block_length = (const u32 *)col(h->block_length, n, 4, first);
+    if (!(a->overlap_matches && a->late_blen)) d.block_length = (const u32 *)col(h->block_length, n, 4, first);
     if (h->identity) d.identity = (const double *)col(h->identity, n, 8, first);
     if (h->score) d.score = (const double *)col(h->score, n, 8, first);
     d.strand = (const u8 *)col(h->strand, n, 1, first);
@@ -1596,9 +1599,10 @@ static void do_upload(void *p) {
     a->res->status = A.take<u8>(n);
     a->res->chain_id = A.take<u32>(n);
     d.matches = (const u32 *)col(h->matches, n, 4, last);
+    if (a->overlap_matches && a->late_blen) d.block_length = (const u32 *)col(h->block_length, n, 4, last);
     bool pageable = false;
     for (const CopyJob &j : first) pageable |= j.bytes >= (1u << 20) && is_pageable(j.src);
-    pageable |= is_pageable(last[0].src) && last[0].bytes >= (1u << 20);
+    for (const CopyJob &j : last) pageable |= j.bytes >= (1u << 20) && is_pageable(j.src);
     if (pageable) {
         // pinned pieces on the copy stream (behind whatever the main stream has queued), the main stream waits for them
         SWG_CUDA(cudaEventRecord(c->ev_copy[0], st));
@@ -1617,7 +1621,7 @@ static void do_upload(void *p) {
             SWG_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_copy[0], 0));
             cs = c->copy_stream;
         }
-        SWG_CUDA(cudaMemcpyAsync(last[0].dst, last[0].src, last[0].bytes, cudaMemcpyHostToDevice, cs));
+        for (const CopyJob &j : last) SWG_CUDA(cudaMemcpyAsync(j.dst, j.src, j.bytes, cudaMemcpyHostToDevice, cs));
         if (a->overlap_matches) SWG_CUDA(cudaEventRecord(c->ev_copy[1], cs));
     }
     if (id16) { // widen on the device: every kernel reads 32-bit ids
@@ -1837,6 +1841,7 @@ int swg_filter(swg_ctx *c, const swg_config *cfg, const swg_mappings *host_in, s
         swg_mappings dev;
         swg_result dres;
         UploadArgs ua{c, a->in, &dev, &dres, &c->io, true};
+        ua.late_blen = a->cfg->min_block_length == 0;
         SWG_CUDA(cudaEventRecord(c->ev[0], c->stream));
         if (a->in->n) do_upload(&ua);
         SWG_CUDA(cudaEventRecord(c->ev[1], c->stream));
