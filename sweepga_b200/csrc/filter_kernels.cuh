@@ -1055,14 +1055,15 @@ __device__ __forceinline__ bool act_less(const ActEntry &a, const ActEntry &b) {
 // After the events of a position p the active set is S(p) = { k : start_k <= p < end_k }.  Item m is marked good iff it
 // is the best of S(p) at some event position p in [start_m, end_m), and flagged iff at some such p it is not the best
 // and overlaps the best by more than thr.  Every member of S(p) for such p intersects m's span, so the thread only
-// looks at its neighbours in start order: to the right while start_k < end_m, to the left while an item could still
-// reach start_m (start_k + longest item of the group > start_m).  S(p) changes only at the starts and ends of those
-// neighbours.  Groups where a scan gets long (deep piles, one very long item) go to the warp-per-group kernel, which
+// looks at its neighbours in start order: to the right while start_k < end_m, to the left while some item at or left of k
+// still reaches start_m — one load of the group's running maximum of the interval ends (pmax[k] = max end over the group's
+// items up to k, scan_segmax): on collinear data the scan stops after a step or two however long the longest item of the group
+// is.  S(p) changes only at the starts and ends of those neighbours.  Groups where a scan gets long (deep piles, one very long item) go to the warp-per-group kernel, which
 // redoes the whole group and k_sweep_keep_big overwrites the keep bytes of its items.
 constexpr u32 SWF_LEFT = 48, SWF_RIGHT = 48;
 __global__ void __launch_bounds__(256)
 k_sweep_flat1(const u32 *__restrict__ sitem, const SweepItem *__restrict__ sdata, const u32 *__restrict__ gid, const u32 *__restrict__ gstart,
-              const u32 *__restrict__ gmaxlen, u32 n_groups, u32 n_sorted, double thr, u8 *__restrict__ keep, u32 *gflag, u32 *big_list,
+              const u32 *__restrict__ pmax, u32 n_groups, u32 n_sorted, double thr, u8 *__restrict__ keep, u32 *gflag, u32 *big_list,
               u32 *big_count, u64 *ctr) {
     const u32 u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_sorted) return;
@@ -1072,13 +1073,12 @@ k_sweep_flat1(const u32 *__restrict__ sitem, const SweepItem *__restrict__ sdata
     if (ge - gs <= 1) { keep[item] = 1; return; } // a single interval: kept (plane_sweep_exact.rs:274-276)
     const SweepItem me = sdata[u];
     if (me.end <= me.start) return; // zero length: its End follows its Begin at the same position, it is never evaluated (keep stays 0)
-    const u64 lmax = gmaxlen[g];
     bool big = false;
     u32 lo = u, hi = u;
     for (u32 k = u, steps = 0; k > gs;) {
         k--;
+        if (pmax[k] <= me.start) break; // nothing at or left of k reaches start_m
         const SweepItem a = sdata[k];
-        if ((u64)a.start + lmax <= (u64)me.start) break; // nothing at or left of k reaches start_m
         if (a.end > me.start) lo = k;
         if (++steps > SWF_LEFT) { big = true; break; }
     }
@@ -1143,15 +1143,16 @@ __global__ void __launch_bounds__(128) k_sweep_keep_big(const u32 *__restrict__ 
 __global__ void __launch_bounds__(256) k_sweep_keys(u32 n_items, const u8 *__restrict__ include, u8 include_mask, const u64 *__restrict__ gkey,
                                                     int pbits, const u32 *__restrict__ it_start, u64 *__restrict__ ek, u32 *__restrict__ ev,
                                                     u64 *__restrict__ n_included) {
-    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool inc = false;
-    if (i < n_items) {
-        inc = include ? (include[i] & include_mask) != 0 : true;
+    u32 mine = 0; // grid-stride: one counter atomic per CTA of a grid of a few thousand (78 k same-address atomics cost ~80 us)
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
+        const bool inc = include ? (include[i] & include_mask) != 0 : true;
         ek[i] = inc ? ((pbits >= 64 ? 0 : (gkey[i] << pbits)) | (u64)it_start[i]) : NONE64;
         ev[i] = i;
+        mine += inc ? 1u : 0u;
     }
-    const u32 cnt = __syncthreads_count(inc);
-    if (threadIdx.x == 0 && cnt) atomicAdd((unsigned long long *)n_included, (unsigned long long)cnt);
+    const int slots[1] = {0};
+    const u32 vals[1] = {mine};
+    block_count_add<1>(n_included, slots, vals);
 }
 
 // One warp per group, for the groups whose pile is deeper than the per-thread array of k_sweep_small.  The active set

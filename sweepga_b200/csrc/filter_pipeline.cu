@@ -179,6 +179,7 @@ struct swg_ctx {
     Arena score_arena;             // ... and its device copy
     Arena arena;      // per-call scratch
     Arena io;         // staging of host SoA for swg_filter
+    bool rows_grouped = false;    // last k_prefilter: the rows come in runs of one (query, target, strand) (aligner order)
     u32 *gtable = nullptr;        // group sort (group_sort.cuh): per possible (query, target, strand) group a counter (u32, cleared
     size_t gtable_entries = 0;    // by every call) and its dense number (u32)
     u64 *h_ctr = nullptr; // pinned mirror of the counters
@@ -250,6 +251,98 @@ static void sort_pairs(swg_ctx *c, u64 *&k, u64 *&k2, u32 *&v, u32 *&v2, u32 n, 
     }
 }
 
+// ---- the group sort (csrc/group_sort.cuh) as one call ---------------------------------------------------------------------
+// keys[i] = (group key << shift) | secondary key (< 2^shift); excluded items carry the group key `dead`.  Orders the items by
+// (group key, secondary key, index).  On success: out[p] = (group key << ib) | index for the sorted positions p < n_rec,
+// gid[p] / gstart[g] / gkey[g] = group of a position, first position and key of a group.  Returns done = false — nothing usable
+// written, keys[] untouched — when some group is larger than `limit` (the caller sorts with the LSD passes).
+// scratch: n words (sort words); out: n words (may be keys itself); run_of: n u32.  The host reads the counts while the scatter runs;
+// with_counters copies the shared counters in the same round trip.
+struct GroupSorted {
+    bool done = false;
+    u32 n_groups = 0, n_rec = 0, n_runs = 0, gmax = 0;
+    u32 *gid = nullptr, *gstart = nullptr, *gkey = nullptr;
+    const u32 *lists = nullptr; // [3] groups that went through a repair kernel, by size class (device)
+    const u32 *d_n_groups = nullptr;
+};
+static u32 *group_table(swg_ctx *c, u64 entries) { // counters (cleared per use) + dense numbers
+    if (c->gtable_entries < entries) {
+        if (c->gtable) cudaFree(c->gtable);
+        c->gtable = nullptr;
+        c->gtable_entries = 0;
+        if (cudaMalloc(&c->gtable, entries * 8) != cudaSuccess) { cudaGetLastError(); throw OomError{(size_t)entries * 8}; }
+        c->gtable_entries = entries;
+    }
+    return c->gtable;
+}
+static GroupSorted group_sort(swg_ctx *c, const u64 *keys, u64 *scratch, u64 *out, u32 *run_of, u32 n, int shift, GsIndex ix, u32 dead,
+                              u64 table_entries, int ib, u32 limit, bool with_counters) {
+    cudaStream_t st = c->stream;
+    Arena &A = c->arena;
+    LaunchCounter &lc = c->lc;
+    GroupSorted r;
+    u32 *gtab = group_table(c, table_entries), *dtab = gtab + table_entries;
+    SWG_CUDA(cudaMemsetAsync(gtab, 0, table_entries * 4, st)); // the counters (37 MB for the pairs of 2160 sequences: ~10 us)
+    stage_mark(c, "gs_runs");
+    // runs of consecutive items with one group key: run index of every item, first item of every run
+    u32 *run_start = A.take<u32>((size_t)n + 1), *run_base = A.take<u32>(n);
+    u32 *gs_ctr = A.take<u32>(12); // [0] groups, [1] records, [2] largest group; [3] runs; [4..6] list lengths; [7..9] work counters
+    SWG_CUDA(cudaMemsetAsync(gs_ctr, 0, 12 * sizeof(u32), st));
+    {
+        u32 *tmp = A.take<u32>(scan_temp_u32(n));
+        scan_flags([=] __device__(u32 i) -> u32 { return (i == 0 || (keys[i] >> shift) != (keys[i - 1] >> shift)) ? 1u : 0u; },
+                   [=] __device__(u32 i, u32 ex, u32 v) {
+                       if (v) run_start[ex] = i;
+                       run_of[i] = ex + v - 1;
+                   },
+                   n, tmp, gs_ctr + 3, st, lc);
+    }
+    k_gs_run_base<<<(u32)c->sm_count * 8, 256, 0, st>>>(gs_ctr + 3, run_start, n, keys, shift, ix, dead, gtab, run_base);
+    lc.n++;
+    stage_mark(c, "gs_scan");
+    r.gstart = A.take<u32>((size_t)n + 1);
+    r.gkey = A.take<u32>(n);
+    r.gid = A.take<u32>(n);
+    const u32 tiles = cdiv(table_entries, SC_TILE);
+    u64 *gs_status = A.take<u64>((size_t)tiles + 2);
+    SWG_CUDA(cudaMemsetAsync(gs_status, 0, sizeof(u64) * ((size_t)tiles + 2), st));
+    k_gs_scan<<<tiles, SC_THREADS, 0, st>>>(gtab, dtab, (u32)table_entries, ix, r.gstart, r.gkey, gs_status, reinterpret_cast<u32 *>(gs_status + tiles), gs_ctr);
+    lc.n++;
+    u32 *h = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
+    SWG_CUDA(cudaMemcpyAsync(h, gs_ctr, 4 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    if (with_counters) read_counters_begin(c); // the host picks the numbers up while the scatter runs
+    else SWG_CUDA(cudaEventRecord(c->ev_ctr, st));
+    stage_mark(c, "gs_scatter");
+    k_gs_scatter<<<cdiv(n, 256), 256, 0, st>>>(keys, run_of, run_start, run_base, n, shift, ix, dead, ib, gtab, dtab, scratch, r.gid);
+    lc.n++;
+    read_counters_end(c);
+    r.n_groups = h[0]; r.n_rec = h[1]; r.gmax = h[2]; r.n_runs = h[3];
+    r.d_n_groups = gs_ctr;
+    if (getenv("SWG_STAGE_TIMING")) fprintf(stderr, "[swg group sort] records %u runs %u groups %u largest %u\n", r.n_rec, r.n_runs, r.n_groups, r.gmax);
+    if (r.n_groups == 0) { r.done = true; return r; }
+    if (r.gmax > limit) return r;
+    stage_mark(c, "gs_order");
+    u32 *list_warp = A.take<u32>(r.n_groups), *list_mid = A.take<u32>(r.n_groups), *list_cta = A.take<u32>(r.n_groups);
+    u8 *unsorted = A.take<u8>(r.n_groups);
+    u32 *list_ctr = gs_ctr + 4;
+    SWG_CUDA(cudaMemsetAsync(unsorted, 0, r.n_groups, st));
+    k_gs_emit<<<cdiv(r.n_rec, 256), 256, 0, st>>>(scratch, r.gid, r.gkey, gs_ctr + 1, ib, out, unsorted);
+    k_gs_groups<<<cdiv(r.n_groups, 256), 256, 0, st>>>(r.n_groups, r.gstart, r.gkey, ib, unsorted, scratch, out, list_warp, list_mid, list_cta, list_ctr);
+    k_gs_warp<<<(u32)c->sm_count * 8, 256, 0, st>>>(list_warp, list_ctr, gs_ctr + 7, r.gstart, r.gkey, ib, scratch, out);
+    lc.n += 3;
+    if (r.gmax > GS_WARP_MAX) {
+        k_gs_mid<<<(u32)c->sm_count * 3, 256, 8 * GS_MID_MAX * sizeof(u64), st>>>(list_mid, list_ctr + 1, gs_ctr + 8, r.gstart, r.gkey, ib, scratch, out);
+        lc.n++;
+    }
+    if (r.gmax > GS_MID_MAX) {
+        k_gs_cta<<<(u32)c->sm_count * 2, GS_CTA_THREADS, GS_CTA_MAX * sizeof(u64), st>>>(list_cta, list_ctr + 2, gs_ctr + 9, r.gstart, r.gkey, ib, scratch, out);
+        lc.n++;
+    }
+    r.lists = list_ctr;
+    r.done = true;
+    return r;
+}
+
 // ---- general plane sweep over arbitrary items (records or chains) ----------------------------
 // include == nullptr: all items.  gkey < 2^gb - 1.  keep[] is fully overwritten (0 for excluded).
 static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 include_mask, const u64 *gkey, int gb, int pbits,
@@ -266,11 +359,21 @@ static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 in
     // items in (group, start, item) order; the End events come out of the active set (k_sweep_small).  One sort when
     // the key fits 64 bits, else two chained stable sorts (start first, then the group id).
     const bool wide = (gb + pbits > 64) || c->knobs.force_wide;
-    k_sweep_keys<<<cdiv(n_items, 256), 256, 0, st>>>(n_items, include, include_mask, gkey, wide ? 64 : pbits, it_start, ek, ev, ctr + C_TMP0);
+    k_sweep_keys<<<std::min<u32>(cdiv(n_items, 256), (u32)c->sm_count * 16), 256, 0, st>>>(n_items, include, include_mask, gkey, wide ? 64 : pbits, it_start, ek, ev, ctr + C_TMP0);
     c->lc.n++;
     int eshift = pbits;
     stage_mark(c, "gs_sort");
-    if (!wide) {
+    // big grouped inputs (the primary sweeps of a record table in aligner order): the group sort instead of the LSD passes
+    const int ib = bits_for(n_items - 1);
+    GroupSorted gs;
+    if (!wide && !c->knobs.no_group_sort && gb <= 22 && pbits <= 32 && pbits + ib <= 64 && gb + ib <= 64 && n_items >= (1u << 18) &&
+        (c->rows_grouped || c->knobs.group_sort_always)) {
+        const u32 limit = c->knobs.group_sort_max ? std::min(c->knobs.group_sort_max, GS_CTA_MAX) : GS_CTA_MAX;
+        gs = group_sort(c, ek, ek2, ek, ev2, n_items, pbits, GsIndex{0, 0, 0}, 0xFFFFFFFFu, 1ull << gb, ib, limit, true);
+    }
+    if (gs.done) {
+        // (sorted item indices: the low bits of ek; t_sweep_gather below writes them to ev)
+    } else if (!wide) {
         sort_pairs(c, ek, ek2, ev, ev2, n_items, gb + pbits);
     } else {
         sort_pairs(c, ek, ek2, ev, ev2, n_items, pbits);
@@ -287,52 +390,71 @@ static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 in
         eshift = 0;
     }
     stage_mark(c, "gs_groups");
-    read_counters(c);
-    const u32 n_inc = (u32)c->h_ctr[C_TMP0]; // the included items sort first
-    if (n_inc == 0) return;
-    u32 *gstart = c->arena.take<u32>(n_inc + 1);
-    u32 *gid = c->arena.take<u32>(n_inc);
-    u32 *bsum = c->arena.take<u32>(scan_temp_u32(n_inc));
-    u32 *d_ng = c->arena.take<u32>(2);
-    const u64 *ekc = ek;
-    scan_flags([=] __device__(u32 u) -> u32 { return (u == 0 || (ekc[u] >> eshift) != (ekc[u - 1] >> eshift)) ? 1u : 0u; },
-               [=] __device__(u32 u, u32 ex, u32 v) {
-                   if (v) gstart[ex] = u;
-                   gid[u] = ex + v - 1;
-               },
-               n_inc, bsum, d_ng, st, c->lc);
-    u32 n_groups = read_u32(c, d_ng);
+    u32 n_inc, n_groups;
+    u32 *gstart, *gid;
+    SortedIdx sidx{nullptr, ev, 0};
+    if (gs.done) {
+        n_inc = gs.n_rec;
+        if (n_inc != (u32)c->h_ctr[C_TMP0]) throw RangeError{"group sort (sweep): the table counted " + std::to_string(n_inc) + " items"};
+        if (n_inc == 0) return;
+        n_groups = gs.n_groups;
+        gstart = gs.gstart;
+        gid = gs.gid;
+        sidx = SortedIdx{ek, nullptr, (1ull << ib) - 1};
+    } else {
+        read_counters(c);
+        n_inc = (u32)c->h_ctr[C_TMP0]; // the included items sort first
+        if (n_inc == 0) return;
+        gstart = c->arena.take<u32>(n_inc + 1);
+        gid = c->arena.take<u32>(n_inc);
+        u32 *bsum = c->arena.take<u32>(scan_temp_u32(n_inc));
+        u32 *d_ng = c->arena.take<u32>(2);
+        const u64 *ekc = ek;
+        scan_flags([=] __device__(u32 u) -> u32 { return (u == 0 || (ekc[u] >> eshift) != (ekc[u - 1] >> eshift)) ? 1u : 0u; },
+                   [=] __device__(u32 u, u32 ex, u32 v) {
+                       if (v) gstart[ex] = u;
+                       gid[u] = ex + v - 1;
+                   },
+                   n_inc, bsum, d_ng, st, c->lc);
+        n_groups = read_u32(c, d_ng);
+    }
+    const bool no_flat = c->knobs.sweep_no_flat; // testing aid: the sequential kernels for every n
+    u32 *ends = (n_keep == 1 && !no_flat) ? c->arena.take<u32>(n_inc) : nullptr; // interval ends in sorted order (for the running maximum)
     u8 *good = c->arena.take<u8>(n_items), *flagged = c->arena.take<u8>(n_items);
     SWG_CUDA(cudaMemsetAsync(good, 0, n_items, st));
     SWG_CUDA(cudaMemsetAsync(flagged, 0, n_items, st));
     // per-item copies (score key, axis interval) in sorted order: a group becomes one contiguous stream
     SweepItem *sdata = c->arena.take<SweepItem>(n_inc);
-    u32 *gmaxlen = c->arena.take<u32>(n_groups), *gflag = c->arena.take<u32>(n_groups);
-    SWG_CUDA(cudaMemsetAsync(gmaxlen, 0, sizeof(u32) * (size_t)n_groups, st));
+    u32 *gflag = c->arena.take<u32>(n_groups);
     SWG_CUDA(cudaMemsetAsync(gflag, 0, sizeof(u32) * (size_t)n_groups, st));
     {
-        const u32 *evc = ev;
+        u32 *evw = gs.done ? ev : nullptr;
         launch_for<t_sweep_gather>(n_inc, st, c->lc, [=] __device__(u32 u) {
-            const u32 i = evc[u];
+            const u32 i = sidx[u];
+            if (evw) evw[u] = i;
+            if (ends) ends[u] = it_end[i];
             SweepItem d;
             d.skey = score_desc_key(it_score[i]);
             d.start = it_start[i];
             d.end = it_end[i];
             sdata[u] = d;
-            // longest item of the group (bounds the leftward scan of k_sweep_flat1): one atomic per group present in the warp
-            const u32 len = d.end - d.start, g = gid[u];
-            const u32 peers = __match_any_sync(__activemask(), g);
-            const u32 mx = __reduce_max_sync(peers, len);
-            if ((threadIdx.x & 31) == (u32)(__ffs(peers) - 1) && mx > gmaxlen[g]) atomicMax(&gmaxlen[g], mx);
         });
+    }
+    u32 *pmax = nullptr;
+    if (n_keep == 1 && !no_flat) { // running maximum of the interval ends inside every group (bounds the leftward scan of k_sweep_flat1)
+        pmax = c->arena.take<u32>(n_inc);
+        u32 *tmp = c->arena.take<u32>(scan_temp_u32(n_inc));
+        const u32 *gidc = gid;
+        scan_segmax([=] __device__(u32 u) -> bool { return u == 0 || gidc[u] != gidc[u - 1]; },
+                    [=] __device__(u32 u) -> u32 { return ends[u]; },
+                    [=] __device__(u32 u, u32 m) { pmax[u] = m; }, n_inc, tmp, st, c->lc);
     }
     u32 *big_list = c->arena.take<u32>(n_groups + 1);
     u32 *sw_ctr = c->arena.take<u32>(4); // [0] thread-kernel group counter, [1] deep groups, [2] warp-kernel work counter
     SWG_CUDA(cudaMemsetAsync(sw_ctr, 0, 4 * sizeof(u32), st));
     stage_mark(c, "gs_sweep");
-    const bool no_flat = c->knobs.sweep_no_flat; // testing aid: the sequential kernels for every n
     if (n_keep == 1 && !no_flat) {
-        k_sweep_flat1<<<cdiv(n_inc, 256), 256, 0, st>>>(ev, sdata, gid, gstart, gmaxlen, n_groups, n_inc, thr, keep, gflag, big_list, sw_ctr + 1,
+        k_sweep_flat1<<<cdiv(n_inc, 256), 256, 0, st>>>(ev, sdata, gid, gstart, pmax, n_groups, n_inc, thr, keep, gflag, big_list, sw_ctr + 1,
                                                        ctr);
     } else {
         const int sweep_mult = c->knobs.sweep_mult;
@@ -495,19 +617,6 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     // The record sort as a counting sort by group (group_sort.cuh) when the table of all possible groups fits.
     const u64 g_entries = 2ull * in.n_seq * in.n_seq;
     const bool gsort = cfg.scaffold_gap != 0 && !K.force_wide && !K.pairs_sort && !K.no_group_sort && g_entries <= GS_MAX_TABLE && 2 * sb0 + 1 <= 31;
-    u32 *gtab = nullptr, *dtab = nullptr;
-    if (gsort) {
-        if (c->gtable_entries < g_entries) {
-            if (c->gtable) cudaFree(c->gtable);
-            c->gtable = nullptr;
-            c->gtable_entries = 0;
-            if (cudaMalloc(&c->gtable, g_entries * 8) != cudaSuccess) { cudaGetLastError(); throw OomError{(size_t)g_entries * 8}; }
-            c->gtable_entries = g_entries;
-        }
-        gtab = c->gtable;
-        dtab = gtab + g_entries;
-        SWG_CUDA(cudaMemsetAsync(gtab, 0, g_entries * 4, st)); // the counters (37 MB for 2160 sequences: ~10 us)
-    }
     SWG_CUDA(cudaEventRecord(c->ev_pre[0], st));
     if (fused_keys) k_prefilter<true><<<cdiv(N, 256), 256, 0, st>>>(in, cfg.min_block_length, cfg.min_identity, cfg.keep_self, flags, ctr, hk, hv, hcap - 1, rec4, sb0, keys, vals);
     else k_prefilter<false><<<cdiv(N, 256), 256, 0, st>>>(in, cfg.min_block_length, cfg.min_identity, cfg.keep_self, flags, ctr, hk, hv, hcap - 1, rec4);
@@ -522,6 +631,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     if (c->h_ctr[C_BAD])
         throw RangeError{"a record that passes the length / self / identity retain has end < start, a coordinate beyond the u32 table, or a sequence id >= n_seq"};
     const u64 n_alive = c->h_ctr[C_ALIVE], zlq = c->h_ctr[C_ZLQ], zlt = c->h_ctr[C_ZLT];
+    c->rows_grouped = (c->h_ctr[C_RUNS] - std::min<u64>(c->h_ctr[C_RUNS], N / 32)) * 2 <= (u64)N;
     const u32 maxcoord = (u32)c->h_ctr[C_MAXCOORD];
     S.n_stage1 = n_alive;
     const int sb = bits_for(in.n_seq);      // ids < n_seq <= 2^sb - 1: the all-ones pattern stays free for dead keys
@@ -596,83 +706,32 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         int key_shift = cb; // keys[] = (group key << key_shift) | query_start
         // rows in no particular order (runs of ~1 record: every step of the group sort turns into random accesses, ~1.6x the
         // LSD passes on a shuffled 20 M table) go through the LSD passes
-        const bool grouped_rows = (c->h_ctr[C_RUNS] - std::min<u64>(c->h_ctr[C_RUNS], N / 32)) * 2 <= (u64)N || K.group_sort_always;
+        const bool grouped_rows = c->rows_grouped || K.group_sort_always;
         if (gsort && grouped_rows) {
-            stage_mark(c, "gs_runs");
             if (fused_ok) { key_shift = 32; kept_is_alive = true; }
             else {
                 k_chain_keys<<<cdiv(N, 256), 256, 0, st>>>(in, flags, keep_q, keep_t, sb, cb, keys, vals, ctr);
                 lc.n++;
                 fused_keys = false;
             }
-            // runs of consecutive records with one group key: run index of every record, first record of every run
-            u32 *run_of = vals2, *run_start = A.take<u32>((size_t)N + 1), *run_base = A.take<u32>(N);
-            u32 *gs_ctr = A.take<u32>(12); // [0] groups, [1] records, [2] largest group; [3] runs; [4..6] list lengths; [7..9] work counters
-            SWG_CUDA(cudaMemsetAsync(gs_ctr, 0, 12 * sizeof(u32), st));
-            {
-                u32 *tmp = A.take<u32>(scan_temp_u32(N));
-                const u64 *kk = keys;
-                const int shift = key_shift;
-                scan_flags([=] __device__(u32 i) -> u32 { return (i == 0 || (kk[i] >> shift) != (kk[i - 1] >> shift)) ? 1u : 0u; },
-                           [=] __device__(u32 i, u32 ex, u32 v) {
-                               if (v) run_start[ex] = i;
-                               run_of[i] = ex + v - 1;
-                           },
-                           N, tmp, gs_ctr + 3, st, lc);
-            }
-            k_gs_run_base<<<(u32)c->sm_count * 8, 256, 0, st>>>(gs_ctr + 3, run_start, N, keys, key_shift, sb, in.n_seq, gtab, run_base);
-            lc.n++;
-            stage_mark(c, "gs_scan");
-            gstart = A.take<u32>((size_t)N + 1);
-            u32 *gkey = A.take<u32>(N);
-            const u32 tiles = cdiv(g_entries, SC_TILE);
-            u64 *gs_status = A.take<u64>((size_t)tiles + 2);
-            SWG_CUDA(cudaMemsetAsync(gs_status, 0, sizeof(u64) * ((size_t)tiles + 2), st));
-            u32 *gs_out = gs_ctr;
-            k_gs_scan<<<tiles, SC_THREADS, 0, st>>>(gtab, dtab, (u32)g_entries, in.n_seq, sb, gstart, gkey, gs_status, reinterpret_cast<u32 *>(gs_status + tiles), gs_out);
-            lc.n++;
-            u32 *h = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
-            SWG_CUDA(cudaMemcpyAsync(h, gs_out, 4 * sizeof(u32), cudaMemcpyDeviceToHost, st)); // + [3] runs
-            read_counters_begin(c); // (C_KEPT_M of k_chain_keys) the host picks the numbers up while the scatter runs
-            stage_mark(c, "gs_scatter");
-            gid = A.take<u32>(N);
-            k_gs_scatter<<<cdiv(N, 256), 256, 0, st>>>(keys, run_of, run_start, run_base, N, key_shift, sb, in.n_seq, ib, gtab, dtab, keys2, gid);
-            lc.n++;
-            read_counters_end(c);
-            n_groups = h[0];
-            const u32 n_rec = h[1], gmax = h[2];
-            if (getenv("SWG_STAGE_TIMING")) fprintf(stderr, "[swg group sort] records %u runs %u groups %u largest %u\n", n_rec, h[3], n_groups, gmax);
             const u32 limit = K.group_sort_max ? std::min(K.group_sort_max, GS_CTA_MAX) : GS_CTA_MAX;
-            if (n_rec != (kept_is_alive ? (u32)n_alive : (u32)c->h_ctr[C_KEPT_M])) throw RangeError{"group sort: the table counted " + std::to_string(n_rec) + " records"};
-            if (n_groups == 0) {
+            const GroupSorted gs = group_sort(c, keys, keys2, keys /* the keys have done their duty by then */, vals2, N, key_shift,
+                                              GsIndex{1, sb, in.n_seq}, (1u << (2 * sb + 1)) - 1, g_entries, ib, limit, true);
+            if (gs.n_rec != (kept_is_alive ? (u32)n_alive : (u32)c->h_ctr[C_KEPT_M])) throw RangeError{"group sort: the table counted " + std::to_string(gs.n_rec) + " records"};
+            if (gs.done) {
                 lsd = false;
-            } else if (gmax <= limit) {
-                stage_mark(c, "gs_order");
-                lsd = false;
-                u32 *list_warp = A.take<u32>(n_groups), *list_mid = A.take<u32>(n_groups), *list_cta = A.take<u32>(n_groups);
-                u8 *unsorted = A.take<u8>(n_groups);
-                u32 *list_ctr = gs_ctr + 4;
-                u64 *words_out = keys; // the keys have done their duty
-                SWG_CUDA(cudaMemsetAsync(unsorted, 0, n_groups, st));
-                k_gs_emit<<<cdiv(n_rec, 256), 256, 0, st>>>(keys2, gid, gkey, gs_out + 1, ib, words_out, unsorted);
-                k_gs_groups<<<cdiv(n_groups, 256), 256, 0, st>>>(n_groups, gstart, gkey, sb, in.n_seq, ib, unsorted, keys2, words_out, list_warp, list_mid, list_cta, list_ctr);
-                k_gs_warp<<<(u32)c->sm_count * 8, 256, 0, st>>>(list_warp, list_ctr, gs_ctr + 7, gstart, gkey, ib, keys2, words_out);
-                lc.n += 3;
-                if (gmax > GS_WARP_MAX) {
-                    k_gs_mid<<<(u32)c->sm_count * 3, 256, 8 * GS_MID_MAX * sizeof(u64), st>>>(list_mid, list_ctr + 1, gs_ctr + 8, gstart, gkey, ib, keys2, words_out);
-                    lc.n++;
+                if (gs.n_groups) {
+                    SWG_CUDA(cudaMemcpyAsync(d_tot, gs.d_n_groups, sizeof(u32), cudaMemcpyDeviceToDevice, st)); // d_tot[0] = group count (k_chain_work_estimate)
+                    n_groups = gs.n_groups;
+                    gstart = gs.gstart;
+                    gid = gs.gid;
+                    skey = keys;
+                    sidx.w = keys;
+                    sidx.mask = (1ull << ib) - 1;
+                    gshift = ib;
+                    groups_done = true;
+                    gs_lists = gs.lists;
                 }
-                if (gmax > GS_MID_MAX) {
-                    k_gs_cta<<<(u32)c->sm_count * 2, GS_CTA_THREADS, GS_CTA_MAX * sizeof(u64), st>>>(list_cta, list_ctr + 2, gs_ctr + 9, gstart, gkey, ib, keys2, words_out);
-                    lc.n++;
-                }
-                SWG_CUDA(cudaMemcpyAsync(d_tot, gs_out, sizeof(u32), cudaMemcpyDeviceToDevice, st)); // d_tot[0] = group count (k_chain_work_estimate)
-                skey = words_out;
-                sidx.w = words_out;
-                sidx.mask = (1ull << ib) - 1;
-                gshift = ib;
-                groups_done = true;
-                gs_lists = list_ctr;
             } else {
                 // some group is larger than one CTA sorts: the LSD passes take over (the keys are still in place)
                 if (key_shift == 32 && !fused_lsd_ok) { // the gap layout does not suit the LSD passes of this key width
@@ -682,8 +741,6 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                     fused_keys = false;
                     read_counters(c);
                 } else fused_keys = key_shift == 32;
-                gstart = gid = nullptr;
-                n_groups = 0;
             }
         } else {
             fused_keys = fused_lsd_ok;

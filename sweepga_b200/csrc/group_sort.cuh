@@ -36,21 +36,32 @@ constexpr u32 GS_CTA_MAX = 8192;        // largest group one CTA orders in share
 constexpr u64 GS_MAX_TABLE = 1ull << 26; // table entries (256 MB)
 constexpr int GS_CTA_THREADS = 256;
 
-__device__ __forceinline__ u32 gs_index(u32 q, u32 t, u32 rev, u32 n_seq) { return (q * n_seq + t) * 2 + rev; }
-// table index from the bit-packed group key ((query << sb | target) << 1 | strand) of the sort keys
-__device__ __forceinline__ u32 gs_index_of_key(u32 grp, int sb, u32 n_seq) {
-    return gs_index(grp >> (sb + 1), (grp >> 1) & ((1u << sb) - 1), grp & 1, n_seq);
-}
+// Table entry of a group key, and back.  dense: the key is the bit-packed ((query << sb | target) << 1 | strand) of the chaining
+// sort and the table is indexed by (query * n_seq + target) * 2 + strand (2 * n_seq^2 entries instead of 2^(2 sb + 1)); otherwise
+// the key itself indexes the table (the sweeps' (sequence, partner genome) keys: a few hundred thousand entries).
+struct GsIndex {
+    int dense, sb;
+    u32 n_seq;
+    __device__ __forceinline__ u32 operator()(u32 grp) const {
+        if (!dense) return grp;
+        return ((grp >> (sb + 1)) * n_seq + ((grp >> 1) & ((1u << sb) - 1))) * 2 + (grp & 1);
+    }
+    __device__ __forceinline__ u32 key_of(u32 entry) const {
+        if (!dense) return entry;
+        const u32 pair = entry >> 1, q = pair / n_seq, t = pair - q * n_seq;
+        return (((q << sb) | t) << 1) | (entry & 1);
+    }
+};
 
 // ---- count: slot ranges of the runs ------------------------------------------------------------------------------------------
-// keys[i] = (group key << shift) | query_start; dead records carry the all-ones group key (their runs are skipped).
+// keys[i] = (group key << shift) | query_start; excluded records carry the group key `dead` (their runs are skipped).
 // A warp owns GS_RUN_CHUNK consecutive runs and walks them 32 at a time, in order.  Lanes whose runs belong to one group (a '+'
 // group interrupted by records of other groups) issue ONE atomic and split the range in lane order, and the next 32 runs are
 // taken up only after that atomic has returned: the runs of a group that lie inside one chunk get their ranges in input order.
 // Runs of one group in different chunks race; k_gs_emit finds the groups this disorders and the ordering kernels repair them.
 constexpr u32 GS_RUN_CHUNK = 1024;
 __global__ void __launch_bounds__(256) k_gs_run_base(const u32 *__restrict__ n_runs_ptr, const u32 *__restrict__ run_start, u32 n,
-                                                     const u64 *__restrict__ keys, int shift, int sb, u32 n_seq, u32 *__restrict__ table,
+                                                     const u64 *__restrict__ keys, int shift, GsIndex ix, u32 dead, u32 *__restrict__ table,
                                                      u32 *__restrict__ run_base) {
     const u32 n_runs = *n_runs_ptr;
     const u32 lane = threadIdx.x & 31, full = 0xFFFFFFFFu;
@@ -69,7 +80,7 @@ __global__ void __launch_bounds__(256) k_gs_run_base(const u32 *__restrict__ n_r
             u32 gi = NONE32, len = 0;
             if (r < c1) {
                 const u32 grp = (u32)(k0 >> shift);
-                if (grp != (1u << (2 * sb + 1)) - 1) { gi = gs_index_of_key(grp, sb, n_seq); len = i1 - i0; }
+                if (grp != dead) { gi = ix(grp); len = i1 - i0; }
             }
             const u32 peers = __match_any_sync(full, gi);
             u32 before = 0, total = len;
@@ -95,7 +106,7 @@ __global__ void __launch_bounds__(256) k_gs_run_base(const u32 *__restrict__ n_r
 // One pass, decoupled look-back over tiles (the scheme of scan.cuh) on a packed pair (non-empty groups before << 31 | records
 // before).  Non-empty entry g: table[g] = start + 1 (0 stays "empty"), dtab[g] = dense, gstart[dense] = start, gkey[dense] = bit-packed key.
 // out[0] = number of groups, out[1] = number of records, out[2] = largest group; gstart[n_groups] = number of records.
-__global__ void __launch_bounds__(SC_THREADS) k_gs_scan(u32 *__restrict__ table, u32 *__restrict__ dtab, u32 n_entries, u32 n_seq, int sb,
+__global__ void __launch_bounds__(SC_THREADS) k_gs_scan(u32 *__restrict__ table, u32 *__restrict__ dtab, u32 n_entries, GsIndex ix,
                                                         u32 *__restrict__ gstart, u32 *__restrict__ gkey, u64 *status, u32 *tile_counter, u32 *out) {
     __shared__ u64 ws[SC_THREADS / 32];
     __shared__ u32 s_tile, s_max;
@@ -184,8 +195,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_gs_scan(u32 *__restrict__ table,
             table[g] = start + 1;
             dtab[g] = dense;
             gstart[dense] = start;
-            const u32 pair = g >> 1, q = pair / n_seq, t = pair - q * n_seq;
-            gkey[dense] = (((q << sb) | t) << 1) | (g & 1);
+            gkey[dense] = ix.key_of(g);
             ex += (u64)v[k] + (1ull << 31);
         }
     }
@@ -193,17 +203,17 @@ __global__ void __launch_bounds__(SC_THREADS) k_gs_scan(u32 *__restrict__ table,
 
 // ---- scatter ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_gs_scatter(const u64 *__restrict__ keys, const u32 *__restrict__ run_of, const u32 *__restrict__ run_start,
-                                                    const u32 *__restrict__ run_base, u32 n, int shift, int sb, u32 n_seq, int ib,
+                                                    const u32 *__restrict__ run_base, u32 n, int shift, GsIndex ix, u32 dead, int ib,
                                                     const u32 *__restrict__ table, const u32 *__restrict__ dtab,
                                                     u64 *__restrict__ words, u32 *__restrict__ gid) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const u64 k = keys[i];
     const u32 grp = (u32)(k >> shift);
-    if (grp == (1u << (2 * sb + 1)) - 1) return; // dead
+    if (grp == dead) return;
     const u32 qs = (u32)(k & ((1ull << shift) - 1));
     const u32 r = run_of[i];
-    const u32 gi = gs_index_of_key(grp, sb, n_seq);
+    const u32 gi = ix(grp);
     const u32 pos = table[gi] - 1 + run_base[r] + (i - run_start[r]);
     words[pos] = ((u64)qs << ib) | i;
     gid[pos] = dtab[gi];
@@ -222,7 +232,7 @@ __global__ void __launch_bounds__(256) k_gs_emit(const u64 *__restrict__ words, 
 
 // ---- order inside the groups --------------------------------------------------------------------------------------------
 // thread per group: lists the groups k_gs_emit marked by size (pairs are finished here)
-__global__ void __launch_bounds__(256) k_gs_groups(u32 n_groups, const u32 *__restrict__ gstart, const u32 *__restrict__ gkey, int sb, u32 n_seq,
+__global__ void __launch_bounds__(256) k_gs_groups(u32 n_groups, const u32 *__restrict__ gstart, const u32 *__restrict__ gkey,
                                                    int ib, const u8 *__restrict__ unsorted, const u64 *__restrict__ words, u64 *__restrict__ out,
                                                    u32 *__restrict__ list_warp, u32 *__restrict__ list_mid, u32 *__restrict__ list_cta,
                                                    u32 *__restrict__ list_ctr /*[3]*/) {
@@ -252,78 +262,6 @@ __global__ void __launch_bounds__(256) k_gs_groups(u32 n_groups, const u32 *__re
         if (cls == c) (c == 1 ? list_warp : c == 2 ? list_mid : list_cta)[base + __popc(m & lt)] = d;
     }
 }
-
-// compare-exchange network over 32 * R words, word index = r * 32 + lane, ascending
-template <int R> __device__ __forceinline__ void gs_bitonic_warp(u64 (&x)[R], u32 lane) {
-#pragma unroll
-    for (int k = 2; k <= 32 * R; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j >= 32) {
-                const int jr = j >> 5;
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    if ((r & jr) == 0) {
-                        const bool up = ((r * 32) & k) == 0; // k >= 64: bit k of the index lies in r
-                        const u64 a = x[r], b = x[r | jr];
-                        const bool sw = up ? a > b : a < b;
-                        x[r] = sw ? b : a;
-                        x[r | jr] = sw ? a : b;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    const u64 o = __shfl_xor_sync(0xFFFFFFFFu, x[r], j);
-                    const bool up = (((u32)(r * 32) | lane) & (u32)k) == 0;
-                    const bool lower = (lane & (u32)j) == 0;
-                    x[r] = (up == lower) ? (x[r] < o ? x[r] : o) : (x[r] > o ? x[r] : o);
-                }
-            }
-        }
-    }
-}
-template <int R>
-__device__ __forceinline__ void gs_warp_group(const u64 *__restrict__ words, u64 *__restrict__ out, u32 s, u32 size, u64 hi, u64 mask, u32 lane) {
-    u64 x[R];
-#pragma unroll
-    for (int r = 0; r < R; r++) x[r] = (u32)(r * 32) + lane < size ? words[s + r * 32 + lane] : NONE64;
-    bool ok = true; // in order after all?  (several runs that happened to arrive in input order)
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-        u64 prev = __shfl_up_sync(0xFFFFFFFFu, x[r], 1);
-        const u64 carry = __shfl_sync(0xFFFFFFFFu, x[r > 0 ? r - 1 : 0], 31);
-        if (lane == 0) prev = r > 0 ? carry : 0;
-        ok = ok && prev <= x[r];
-    }
-    if (!__all_sync(0xFFFFFFFFu, ok)) gs_bitonic_warp<R>(x, lane);
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-        const u32 p = (u32)(r * 32) + lane;
-        if (p < size) out[s + p] = hi | (x[r] & mask);
-    }
-}
-// warp per listed group (3 .. GS_WARP_MAX records), warps take groups from a counter
-__global__ void __launch_bounds__(256) k_gs_warp(const u32 *__restrict__ list, const u32 *__restrict__ n_list_ptr, u32 *work_ctr,
-                                                 const u32 *__restrict__ gstart, const u32 *__restrict__ gkey, int ib, const u64 *__restrict__ words,
-                                                 u64 *__restrict__ out) {
-    const u32 lane = threadIdx.x & 31;
-    const u32 n_list = *n_list_ptr;
-    const u64 mask = (1ull << ib) - 1;
-    while (true) {
-        u32 w = 0;
-        if (lane == 0) w = atomicAdd(work_ctr, 1u);
-        w = __shfl_sync(0xFFFFFFFFu, w, 0);
-        if (w >= n_list) return;
-        const u32 d = list[w];
-        const u32 s = gstart[d], size = gstart[d + 1] - s;
-        const u64 hi = (u64)gkey[d] << ib;
-        if (size <= 32) gs_warp_group<1>(words, out, s, size, hi, mask, lane);
-        else if (size <= 64) gs_warp_group<2>(words, out, s, size, hi, mask, lane);
-        else gs_warp_group<4>(words, out, s, size, hi, mask, lane);
-    }
-}
-static_assert(GS_WARP_MAX == 128, "gs_warp_group<4> holds 128 words");
 
 // A group that is not in order usually is a few ascending pieces: its runs took their slot ranges out of input order, or an
 // ordered block is followed by some stray records.  Such a group is MERGED: the final position of a word is its offset inside its
@@ -369,6 +307,85 @@ __device__ __forceinline__ void gs_merge_pieces(const u64 *sm, u32 size, const u
         dst[rank] = hi | (x & mask);
     }
 }
+
+// compare-exchange network over 32 * R words, word index = r * 32 + lane, ascending
+template <int R> __device__ __forceinline__ void gs_bitonic_warp(u64 (&x)[R], u32 lane) {
+#pragma unroll
+    for (int k = 2; k <= 32 * R; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int jr = j >> 5;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    if ((r & jr) == 0) {
+                        const bool up = ((r * 32) & k) == 0; // k >= 64: bit k of the index lies in r
+                        const u64 a = x[r], b = x[r | jr];
+                        const bool sw = up ? a > b : a < b;
+                        x[r] = sw ? b : a;
+                        x[r | jr] = sw ? a : b;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const u64 o = __shfl_xor_sync(0xFFFFFFFFu, x[r], j);
+                    const bool up = (((u32)(r * 32) | lane) & (u32)k) == 0;
+                    const bool lower = (lane & (u32)j) == 0;
+                    x[r] = (up == lower) ? (x[r] < o ? x[r] : o) : (x[r] > o ? x[r] : o);
+                }
+            }
+        }
+    }
+}
+template <int R>
+__device__ __forceinline__ void gs_warp_group(const u64 *__restrict__ words, u64 *__restrict__ out, u32 s, u32 size, u64 hi, u64 mask, u32 lane,
+                                              u64 *sm /*[32 * R], this warp's*/, u32 *pst) {
+    u64 x[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        x[r] = (u32)(r * 32) + lane < size ? words[s + r * 32 + lane] : NONE64;
+        sm[r * 32 + lane] = x[r];
+    }
+    __syncwarp();
+    // a few ascending pieces (the usual shape: an ordered block and some stray records): merge them; else the network
+    const u32 n_pieces = gs_find_pieces_warp(sm, size, pst, lane);
+    __syncwarp();
+    if (n_pieces) {
+        gs_merge_pieces(sm, size, pst, n_pieces, out + s, hi, mask, lane, 32);
+        __syncwarp();
+        return;
+    }
+    gs_bitonic_warp<R>(x, lane);
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const u32 p = (u32)(r * 32) + lane;
+        if (p < size) out[s + p] = hi | (x[r] & mask);
+    }
+}
+// warp per listed group (3 .. GS_WARP_MAX records), warps take groups from a counter
+__global__ void __launch_bounds__(256) k_gs_warp(const u32 *__restrict__ list, const u32 *__restrict__ n_list_ptr, u32 *work_ctr,
+                                                 const u32 *__restrict__ gstart, const u32 *__restrict__ gkey, int ib, const u64 *__restrict__ words,
+                                                 u64 *__restrict__ out) {
+    __shared__ u64 s_sm[8][GS_WARP_MAX];
+    __shared__ u32 s_pst[8][GS_MERGE_MAX + 2];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 n_list = *n_list_ptr;
+    const u64 mask = (1ull << ib) - 1;
+    while (true) {
+        u32 w = 0;
+        if (lane == 0) w = atomicAdd(work_ctr, 1u);
+        w = __shfl_sync(0xFFFFFFFFu, w, 0);
+        if (w >= n_list) return;
+        const u32 d = list[w];
+        const u32 s = gstart[d], size = gstart[d + 1] - s;
+        const u64 hi = (u64)gkey[d] << ib;
+        if (size <= 32) gs_warp_group<1>(words, out, s, size, hi, mask, lane, s_sm[warp], s_pst[warp]);
+        else if (size <= 64) gs_warp_group<2>(words, out, s, size, hi, mask, lane, s_sm[warp], s_pst[warp]);
+        else gs_warp_group<4>(words, out, s, size, hi, mask, lane, s_sm[warp], s_pst[warp]);
+    }
+}
+static_assert(GS_WARP_MAX == 128, "gs_warp_group<4> holds 128 words");
 
 // warp per listed group (GS_WARP_MAX + 1 .. GS_MID_MAX records): the group in the warp's own 8 KB of shared memory; no block
 // barrier anywhere, the eight warps of a CTA work on eight groups

@@ -192,6 +192,91 @@ static inline void scan_flags(In in, Out out, u32 n, u32 *temp, u32 *total_out, 
     SWG_CUDA(cudaGetLastError());
 }
 
+// ---- segmented inclusive max-scan (u32), one pass ---------------------------------------------------------------------------
+// out(i, m): m = max of val(j) over the j <= i of i's segment (head(i): i starts a segment).  The running maximum of the interval
+// ends of a group in start order: "does anything at or left of k reach position p" is one load (the halo test of the plane sweeps).
+// Same tiling and decoupled look-back as sc_onepass_kernel; a predecessor tile that holds a segment head ends the look-back like
+// one that holds an inclusive value.  Tile status: flags | has_head << 32 | max.
+template <class Head, class Val, class Out>
+__global__ void __launch_bounds__(SC_THREADS) sc_segmax_kernel(Head head, Val val, Out out, u32 n, u64 *status, u32 *tile_counter) {
+    __shared__ u32 wv[SC_THREADS / 32], wf[SC_THREADS / 32];
+    __shared__ u32 s_tile, s_carry;
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 base = tile * SC_TILE + threadIdx.x * SC_ITEMS;
+    u32 v[SC_ITEMS];
+    u32 fbits = 0, run = 0;
+#pragma unroll
+    for (int k = 0; k < SC_ITEMS; k++) {
+        const u32 i = base + k;
+        if (i < n) {
+            const u32 x = val(i);
+            if (head(i)) { run = x; fbits |= 1u << k; } else run = max(run, x);
+        }
+        v[k] = run;
+    }
+    // warp-level segmented inclusive scan of the thread aggregates (a: max since the last head, f: a head seen)
+    u32 a = run, f = fbits ? 1u : 0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 ta = __shfl_up_sync(0xFFFFFFFFu, a, o), tf = __shfl_up_sync(0xFFFFFFFFu, f, o);
+        if (lane >= (u32)o) { if (!f) a = max(a, ta); f |= tf; }
+    }
+    u32 ea = __shfl_up_sync(0xFFFFFFFFu, a, 1), ef = __shfl_up_sync(0xFFFFFFFFu, f, 1); // exclusive, inside the warp
+    if (lane == 0) { ea = 0; ef = 0; }
+    if (lane == 31) { wv[warp] = a; wf[warp] = f; }
+    __syncthreads();
+    u32 ca = 0, cf = 0, ta_ = 0, tf_ = 0; // carry of the warps before this one; aggregate of the whole tile
+#pragma unroll
+    for (int w = 0; w < SC_THREADS / 32; w++) {
+        const u32 x = wv[w], h = wf[w];
+        if (w < (int)warp) { if (h) { ca = x; cf = 1; } else ca = max(ca, x); }
+        if (h) { ta_ = x; tf_ = 1; } else ta_ = max(ta_, x);
+    }
+    const u32 xa = ef ? ea : max(ca, ea), xf = ef | cf; // exclusive carry of this thread inside the tile
+    if (threadIdx.x < 32) {
+        if (lane == 0) st_relaxed_u64(&status[tile], (tile == 0 ? SC_FLAG_INCL : SC_FLAG_AGG) | ((u64)tf_ << 32) | ta_);
+        u32 excl = 0;
+        if (tile != 0) {
+            i64 t = (i64)tile - 1;
+            while (true) {
+                const i64 mine = t - lane;
+                const u64 w = mine >= 0 ? ld_relaxed_u64(&status[mine]) : SC_FLAG_INCL;
+                const u32 term = __ballot_sync(0xFFFFFFFFu, (w & SC_FLAG_INCL) != 0 || ((w & SC_FLAG_AGG) != 0 && ((w >> 32) & 1)));
+                const u32 ready = __ballot_sync(0xFFFFFFFFu, (w & (SC_FLAG_INCL | SC_FLAG_AGG)) != 0);
+                const u32 upto = term ? (u32)(__ffs(term) - 1) : 31u;
+                const u32 need = upto == 31 ? 0xFFFFFFFFu : ((2u << upto) - 1);
+                if ((ready & need) != need) continue;
+                excl = max(excl, __reduce_max_sync(0xFFFFFFFFu, lane <= upto ? (u32)w : 0u));
+                if (term) break;
+                t -= 32;
+            }
+            if (lane == 0) st_relaxed_u64(&status[tile], SC_FLAG_INCL | (tf_ ? ta_ : max(excl, ta_)));
+        }
+        if (lane == 0) s_carry = excl;
+    }
+    __syncthreads();
+    const u32 carry = xf ? xa : max(xa, s_carry); // max over the segment's items before this thread's first item
+#pragma unroll
+    for (int k = 0; k < SC_ITEMS; k++) {
+        const u32 i = base + k;
+        if (i < n) out(i, (fbits & ((2u << k) - 1)) ? v[k] : max(v[k], carry));
+    }
+}
+template <class Head, class Val, class Out>
+static inline void scan_segmax(Head head, Val val, Out out, u32 n, u32 *temp, cudaStream_t st, LaunchCounter &lc) {
+    if (n == 0) return;
+    u32 nb = cdiv(n, SC_TILE);
+    SWG_CUDA(cudaMemsetAsync(temp, 0, sizeof(u32) * (2 * (size_t)nb + 4), st));
+    u64 *status = reinterpret_cast<u64 *>(temp);
+    u32 *counter = temp + 2 * (size_t)nb + 2;
+    sc_segmax_kernel<<<nb, SC_THREADS, 0, st>>>(head, val, out, n, status, counter);
+    lc.n += 1;
+    SWG_CUDA(cudaGetLastError());
+}
+
 // ---- unordered compaction: the elements with pred(i) appended to list[] in no particular order (one counter atomic per
 // 1024-element block).  For lists whose consumers treat every entry independently (candidate lists): ~3x cheaper than the
 // ordered scan above.  *counter must be zero on entry.
