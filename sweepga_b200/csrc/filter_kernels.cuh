@@ -1064,7 +1064,7 @@ constexpr u32 SWF_LEFT = 48, SWF_RIGHT = 48;
 __global__ void __launch_bounds__(256)
 k_sweep_flat1(const u32 *__restrict__ sitem, const SweepItem *__restrict__ sdata, const u32 *__restrict__ gid, const u32 *__restrict__ gstart,
               const u32 *__restrict__ pmax, u32 n_groups, u32 n_sorted, double thr, u8 *__restrict__ keep, u32 *gflag, u32 *big_list,
-              u32 *big_count, u64 *ctr) {
+              u32 *big_count, u64 *ctr, u32 scan_limit /* SWF_LEFT; 0: every group of two or more items counts as a pile (tests) */) {
     const u32 u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_sorted) return;
     const u32 g = gid[u];
@@ -1073,14 +1073,14 @@ k_sweep_flat1(const u32 *__restrict__ sitem, const SweepItem *__restrict__ sdata
     if (ge - gs <= 1) { keep[item] = 1; return; } // a single interval: kept (plane_sweep_exact.rs:274-276)
     const SweepItem me = sdata[u];
     if (me.end <= me.start) return; // zero length: its End follows its Begin at the same position, it is never evaluated (keep stays 0)
-    bool big = false;
+    bool big = scan_limit == 0;
     u32 lo = u, hi = u;
-    for (u32 k = u, steps = 0; k > gs;) {
+    for (u32 k = u, steps = 0; k > gs && !big;) {
         k--;
         if (pmax[k] <= me.start) break; // nothing at or left of k reaches start_m
         const SweepItem a = sdata[k];
         if (a.end > me.start) lo = k;
-        if (++steps > SWF_LEFT) { big = true; break; }
+        if (++steps > scan_limit) { big = true; break; }
     }
     u32 near = 0;
     for (u32 k = u + 1; k < ge && !big; k++) {
@@ -1088,7 +1088,7 @@ k_sweep_flat1(const u32 *__restrict__ sitem, const SweepItem *__restrict__ sdata
         if (a.start >= me.end) break;
         hi = k;
         near += near_tie(a.skey, a.start, a.end, me.skey, me.start, me.end); // near-tie audit, each co-active pair once
-        if (k - u > SWF_RIGHT) big = true;
+        if (k - u > scan_limit) big = true;
     }
     if (big) {
         if (atomicExch(&gflag[g], 1u) == 0) big_list[atomicAdd(big_count, 1u)] = g;

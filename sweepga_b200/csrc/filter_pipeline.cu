@@ -29,6 +29,7 @@
 #include "radix_sort.cuh"
 #include "scan.cuh"
 #include "filter_kernels.cuh"
+#include "sweep_tree.cuh"
 #include "paf_host.h"
 
 #include <unistd.h>
@@ -121,6 +122,7 @@ struct Knobs {
     bool pairs_sort = false;   // SWG_SORT_PAIRS=1: the record sort keeps (key, payload) pairs through every pass
     bool no_fused_keys = false; // SWG_NO_FUSED_KEYS=1: the chain sort keys always come from k_chain_keys
     bool no_group_sort = false; // SWG_NO_GROUP_SORT=1: the record sort always runs the LSD passes (radix_sort.cuh)
+    bool sweep_no_tree = false, sweep_tree_all = false; // SWG_SWEEP_NO_TREE=1: piles of an n = 1 sweep go through the warp walk; SWG_SWEEP_TREE_ALL=1: every group through the tree (tests)
     bool group_sort_always = false; // SWG_GROUP_SORT_ALWAYS=1: ... never because the rows look ungrouped (tests)
     u32 group_sort_max = 0;     // SWG_GROUP_SORT_MAX: largest group the group sort accepts (default GS_CTA_MAX; tests lower it)
     u32 fixpoint_min = 0;      // 0 = default
@@ -140,6 +142,8 @@ static Knobs read_knobs() {
     k.no_fused_keys = on("SWG_NO_FUSED_KEYS");
     k.no_group_sort = on("SWG_NO_GROUP_SORT");
     k.group_sort_always = on("SWG_GROUP_SORT_ALWAYS");
+    k.sweep_no_tree = on("SWG_SWEEP_NO_TREE");
+    k.sweep_tree_all = on("SWG_SWEEP_TREE_ALL");
     if (const char *v = getenv("SWG_GROUP_SORT_MAX")) k.group_sort_max = (u32)atoi(v);
     if (const char *v = getenv("SWG_LOG_IMPL")) k.cuda_log = strcmp(v, "cuda") == 0;
     if (const char *v = getenv("SWG_FIXPOINT_MIN")) k.fixpoint_min = (u32)atoi(v);
@@ -343,6 +347,81 @@ static GroupSorted group_sort(swg_ctx *c, const u64 *keys, u64 *scratch, u64 *ou
     return r;
 }
 
+// ---- n = 1 sweep of the piles (csrc/sweep_tree.cuh) -----------------------------------------------------------------------------
+struct t_pile_rank; struct t_pile_grp;
+static void sweep_piles_n1(swg_ctx *c, const u32 *sitem, const SweepItem *sdata, const u32 *gstart, u32 n_groups, u32 n_sorted,
+                           const u32 *big_list, u32 n_big, double thr, u8 *keep) {
+    cudaStream_t st = c->stream;
+    Arena &A = c->arena;
+    LaunchCounter &lc = c->lc;
+    stage_mark(c, "pile_events");
+    // items of the pile groups
+    u32 *boff = A.take<u32>(n_big + 1), *d_tot = A.take<u32>(4);
+    u32 *tmp = A.take<u32>(scan_temp_u32(std::max(n_big, 1u)));
+    scan_apply([=] __device__(u32 b) -> u32 { const u32 g = big_list[b]; return ((g + 1 < n_groups) ? gstart[g + 1] : n_sorted) - gstart[g]; },
+               [=] __device__(u32 b, u32 ex, u32) { boff[b] = ex; }, n_big, tmp, d_tot, st, lc);
+    const u32 nb = read_u32(c, d_tot);
+    if (nb == 0) return;
+    if (nb >= (1u << 30)) throw RangeError{"plane sweep: more than 2^30 mappings in deep piles"};
+    u32 *bitem = A.take<u32>(nb), *bgrp = A.take<u32>(nb);
+    k_pile_expand<<<cdiv(nb, 256), 256, 0, st>>>(big_list, boff, n_big, nb, gstart, bitem, bgrp);
+    u64 *ek = A.take<u64>(2 * (size_t)nb), *ek2 = A.take<u64>(2 * (size_t)nb), *rk = A.take<u64>(nb), *rk2 = A.take<u64>(nb);
+    u32 *ev = A.take<u32>(2 * (size_t)nb), *ev2 = A.take<u32>(2 * (size_t)nb), *rv = A.take<u32>(nb), *rv2 = A.take<u32>(nb);
+    k_pile_events<<<cdiv(nb, 256), 256, 0, st>>>(bitem, bgrp, sdata, nb, ek, ev, rk, rv);
+    lc.n += 2;
+    const int bb = bits_for(n_big);
+    sort_pairs(c, ek, ek2, ev, ev2, 2 * nb, 32 + bb);
+    // index of every event's position among the distinct (group, position) values
+    u32 *upos = A.take<u32>(2 * (size_t)nb);
+    {
+        u32 *tmp2 = A.take<u32>(scan_temp_u32(2 * nb));
+        const u64 *ekc = ek;
+        const u32 *evc = ev;
+        scan_flags([=] __device__(u32 e) -> u32 { return (ekc[e] != NONE64 && (e == 0 || ekc[e] != ekc[e - 1])) ? 1u : 0u; },
+                   [=] __device__(u32 e, u32 ex, u32 v) { upos[evc[e]] = ekc[e] == NONE64 ? NONE32 : ex + v - 1; }, 2 * nb, tmp2, d_tot + 1, st, lc);
+    }
+    stage_mark(c, "pile_ranks");
+    // ranks: stable by score key over items that already are in (group, start, index) order, then stable by group
+    sort_pairs(c, rk, rk2, rv, rv2, nb, 64);
+    if (n_big > 1) {
+        u64 *kk = rk;
+        const u32 *vv = rv;
+        launch_for<t_pile_grp>(nb, st, lc, [=] __device__(u32 r) { kk[r] = bgrp[vv[r]]; });
+        sort_pairs(c, rk, rk2, rv, rv2, nb, bb);
+    }
+    u32 *rank_of = A.take<u32>(nb);
+    {
+        const u32 *vv = rv;
+        launch_for<t_pile_rank>(nb, st, lc, [=] __device__(u32 r) { rank_of[vv[r]] = r; });
+    }
+    const u32 *item_of_rank = rv;
+    stage_mark(c, "pile_tree");
+    u32 size = 1;
+    while (size < 2 * nb) size <<= 1;
+    u32 *tree = A.take<u32>(2 * (size_t)size), *best = A.take<u32>(2 * (size_t)nb);
+    SWG_CUDA(cudaMemsetAsync(tree, 0xFF, sizeof(u32) * 2 * (size_t)size, st));
+    k_pile_paint<<<cdiv(nb, 256), 256, 0, st>>>(upos, rank_of, nb, size, tree);
+    k_pile_best<<<cdiv(2 * nb, 256), 256, 0, st>>>(tree, 2 * nb, size, best);
+    lc.n += 2;
+    // runs of one best item
+    u32 *run_id = A.take<u32>(2 * (size_t)nb), *run_first = A.take<u32>(2 * (size_t)nb), *run_best = A.take<u32>(2 * (size_t)nb);
+    {
+        u32 *tmp3 = A.take<u32>(scan_temp_u32(2 * nb));
+        scan_flags([=] __device__(u32 i) -> u32 { return (i == 0 || best[i] != best[i - 1]) ? 1u : 0u; },
+                   [=] __device__(u32 i, u32 ex, u32 v) {
+                       const u32 r = ex + v - 1;
+                       run_id[i] = r;
+                       if (v) { run_first[r] = i; run_best[r] = best[i]; }
+                   },
+                   2 * nb, tmp3, d_tot + 2, st, lc);
+    }
+    stage_mark(c, "pile_verdict");
+    k_pile_verdict<<<cdiv(nb, 256), 256, 0, st>>>(bitem, sitem, sdata, upos, rank_of, item_of_rank, run_id, run_first, run_best, d_tot + 2, nb, thr, keep,
+                                                   c->d_ctr);
+    lc.n++;
+    SWG_CUDA(cudaGetLastError());
+}
+
 // ---- general plane sweep over arbitrary items (records or chains) ----------------------------
 // include == nullptr: all items.  gkey < 2^gb - 1.  keep[] is fully overwritten (0 for excluded).
 static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 include_mask, const u64 *gkey, int gb, int pbits,
@@ -455,27 +534,35 @@ static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 in
     stage_mark(c, "gs_sweep");
     if (n_keep == 1 && !no_flat) {
         k_sweep_flat1<<<cdiv(n_inc, 256), 256, 0, st>>>(ev, sdata, gid, gstart, pmax, n_groups, n_inc, thr, keep, gflag, big_list, sw_ctr + 1,
-                                                       ctr);
+                                                       ctr, c->knobs.sweep_tree_all ? 0u : SWF_LEFT);
     } else {
         const int sweep_mult = c->knobs.sweep_mult;
         k_sweep_small<<<(u32)c->sm_count * sweep_mult, 128, 0, st>>>(ev, sdata, gstart, n_groups, n_inc, n_keep, thr, good, flagged, big_list,
                                                                     sw_ctr + 1, sw_ctr, ctr);
     }
-    // groups whose pile is deeper than the per-thread array: one warp each, active set in global scratch
-    ActEntry *act = c->arena.take<ActEntry>(n_inc + 1);
-    k_sweep_groups<<<(u32)c->sm_count * 4, 128, 0, st>>>(ev, sdata, gstart, n_groups, n_inc, n_keep, thr, act, good, flagged, big_list,
-                                                        sw_ctr + 1, sw_ctr + 2, ctr);
-    if (n_keep == 1 && !no_flat) {
-        k_sweep_keep_big<<<(u32)c->sm_count, 128, 0, st>>>(ev, gstart, n_groups, n_inc, big_list, sw_ctr + 1, good, flagged, keep);
-        c->lc.n++;
+    const bool tree = n_keep == 1 && !no_flat && !c->knobs.sweep_no_tree;
+    if (tree) {
+        // n = 1: the groups whose neighbour scans got long (piles) go through the position-parallel tree sweep (sweep_tree.cuh)
+        const u32 n_big = read_u32(c, sw_ctr + 1);
+        if (n_big) sweep_piles_n1(c, ev, sdata, gstart, n_groups, n_inc, big_list, n_big, thr, keep);
     } else {
-        const u32 *evc = ev;
-        launch_for<t_sweep_keep>(n_inc, st, c->lc, [=] __device__(u32 u) {
-            const u32 i = evc[u];
-            keep[i] = (good[i] && !flagged[i]) ? 1 : 0;
-        });
+        // groups whose pile is deeper than the per-thread array: one warp each, active set in global scratch
+        ActEntry *act = c->arena.take<ActEntry>(n_inc + 1);
+        k_sweep_groups<<<(u32)c->sm_count * 4, 128, 0, st>>>(ev, sdata, gstart, n_groups, n_inc, n_keep, thr, act, good, flagged, big_list,
+                                                            sw_ctr + 1, sw_ctr + 2, ctr);
+        if (n_keep == 1 && !no_flat) {
+            k_sweep_keep_big<<<(u32)c->sm_count, 128, 0, st>>>(ev, gstart, n_groups, n_inc, big_list, sw_ctr + 1, good, flagged, keep);
+            c->lc.n++;
+        } else {
+            const u32 *evc = ev;
+            launch_for<t_sweep_keep>(n_inc, st, c->lc, [=] __device__(u32 u) {
+                const u32 i = evc[u];
+                keep[i] = (good[i] && !flagged[i]) ? 1 : 0;
+            });
+        }
+        c->lc.n += 1;
     }
-    c->lc.n += 2;
+    c->lc.n += 1;
     stage_mark(c, "gs_done");
     SWG_CUDA(cudaGetLastError());
 }

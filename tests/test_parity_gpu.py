@@ -448,3 +448,35 @@ def test_group_sort_pieces_out_of_place(ctx, n_blocks, group, monkeypatch):
                              None, names)
         _, _, st = check(ctx, swg.FilterConfig.from_cli(scaffold_mass="0"), t, f"pieces {n_blocks} x {group} interleave={interleave}")
         assert st.n_sort_passes == 0 and st.n_unsorted_groups >= 1
+
+
+# ---- the n = 1 plane sweep of deep piles through the segment tree (csrc/sweep_tree.cuh) ---------------------------------------
+@pytest.mark.parametrize("case", ["1:1_1:1", "1:1_rescue", "no_scaffold_1:1", "identity_scoring", "length_scoring", "mass0"])
+def test_tree_sweep_everywhere_yeast(ctx, yeast, case, monkeypatch):
+    """SWG_SWEEP_TREE_ALL=1: every group of two or more items of an n = 1 sweep is treated as a pile (positions, ranks, segment
+    tree, runs of one best item, verdict per item) instead of the neighbour scans of k_sweep_flat1."""
+    monkeypatch.setenv("SWG_SWEEP_TREE_ALL", "1")
+    check(ctx, swg.FilterConfig.from_cli(**CLI_CASES[case]), yeast, f"tree sweep {case}")
+
+
+@pytest.mark.parametrize("seed", range(0, 160, 3))
+def test_tree_sweep_everywhere_fuzz(ctx, seed, monkeypatch):
+    """Dense, tie-rich fuzz tables (zero-length intervals, equal scores, equal starts) with every n = 1 sweep through the tree."""
+    monkeypatch.setenv("SWG_SWEEP_TREE_ALL", "1")
+    rng = np.random.default_rng(3000 + seed)
+    n = int(rng.integers(2, 600)) if seed < 120 else int(rng.integers(2000, 8000))
+    t = fuzz_table(seed, n, hashless=bool(seed % 5 == 0))
+    cfg = swg.FilterConfig.from_cli(
+        num_mappings=["1:1", "1", "many:1", "1:many"][seed % 4], scaffold_filter=["1:1", "many:many", "1:many"][(seed // 3) % 3],
+        overlap=[0.0, 0.5, 0.95, 1.0][seed % 4], scaffold_overlap=[0.5, 0.0, 1.0][seed % 3],
+        scaffold_jump=str([0, 50, 200, 1000][(seed // 2) % 4]), scaffold_mass=str([0, 100, 500][seed % 3]),
+        scaffold_dist=str([0, 100, 1000][(seed // 5) % 3]), keep_self=bool(seed % 2),
+        scoring=["log-length-ani", "ani", "length", "length-ani", "matches"][seed % 5])
+    check(ctx, cfg, t, f"tree fuzz{seed}")
+
+
+@pytest.mark.parametrize("case", ["1:1_1:1", "no_scaffold_1:1"])
+def test_tree_sweep_pile(ctx, case):
+    """configs[4] shape at a size the oracle finishes: the pile's groups leave the neighbour scans by themselves."""
+    t = synth.skew(n_pile=20_000, n_tiny_groups=3_000, seed=5, window=3_000_000)
+    check(ctx, swg.FilterConfig.from_cli(**CLI_CASES[case]), t, f"pile {case}")
