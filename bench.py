@@ -286,6 +286,32 @@ def skew_leg(ctx, cfg, n_pile):
         return {"error": repr(e)[:200]}
 
 
+def modes_leg(ctx, d_in, d_res, n):
+    """Extra, informational: the 1:1 / 1:1 mode (both plane sweeps fully exercised: configs[1]'s flags) on the resident configs[2]
+    table, and --num-mappings 1:1 on a configs[4]-shaped pile of 1 M mappings (deep piles take the segment-tree sweep)."""
+    try:
+        import sweepga_b200 as swg
+        from sweepga_b200 import synth
+        out = {}
+        cfg = swg.FilterConfig.from_cli(num_mappings="1:1", scaffold_filter="1:1")
+        ctx.filter_device(cfg, d_in, d_res)
+        sts = [ctx.filter_device(cfg, d_in, d_res) for _ in range(3)]
+        ms = min(s.ms_device for s in sts)
+        out["1:1/1:1 on the 20 M table"] = {"ms_device": ms, "Mmappings_per_s": n / ms / 1e3, "gpu_launches": int(sts[-1].gpu_launches),
+                                            "kept": int(sts[-1].n_kept), "pipeline_algorithmic_bytes_per_mapping": 1134}
+        t = synth.skew(n_pile=1_000_000, n_tiny_groups=100_000, seed=5)
+        p_in, p_res = ctx.upload(t)
+        cfg = swg.FilterConfig.from_cli(num_mappings="1:1", scaffold_jump="0")
+        ctx.filter_device(cfg, p_in, p_res)
+        st = ctx.filter_device(cfg, p_in, p_res)
+        ctx.release(p_in, p_res)
+        out["--num-mappings 1:1 on a 1 M pile + 100000 tiny groups"] = {"records": int(t.n), "ms_device": float(st.ms_device),
+                                                                         "gpu_launches": int(st.gpu_launches), "kept": int(st.n_kept)}
+        return out
+    except Exception as e:
+        return {"error": repr(e)[:200]}
+
+
 def small_leg(ctx):
     """configs[0] / configs[1]: the yeast-shaped table (~30 k records), defaults and 1:1 / 1:1 — latency-bound calls;
     device-resident, CUDA-event time per call, mean of 20 after 3 warm-ups."""
@@ -611,6 +637,7 @@ def main():
             "parity": parity,
         }
         if n_gpus == 1:
+            line["modes"] = modes_leg(ctx, d_in, d_res, n)
             line["small"] = small_leg(ctx)
         if n_gpus == 1 and args.paf_lines > 0:
             line["paf_e2e"] = paf_file_leg(ctx, cfg, args.paf_lines)

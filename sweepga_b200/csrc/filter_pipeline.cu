@@ -280,7 +280,7 @@ static u32 *group_table(swg_ctx *c, u64 entries) { // counters (cleared per use)
     return c->gtable;
 }
 static GroupSorted group_sort(swg_ctx *c, const u64 *keys, u64 *scratch, u64 *out, u32 *run_of, u32 n, int shift, GsIndex ix, u32 dead,
-                              u64 table_entries, int ib, u32 limit, bool with_counters) {
+                              u64 table_entries, int ib, u32 limit, bool with_counters, u32 *sec_out = nullptr /* n u32: the secondary keys in sorted order */) {
     cudaStream_t st = c->stream;
     Arena &A = c->arena;
     LaunchCounter &lc = c->lc;
@@ -330,16 +330,16 @@ static GroupSorted group_sort(swg_ctx *c, const u64 *keys, u64 *scratch, u64 *ou
     u8 *unsorted = A.take<u8>(r.n_groups);
     u32 *list_ctr = gs_ctr + 4;
     SWG_CUDA(cudaMemsetAsync(unsorted, 0, r.n_groups, st));
-    k_gs_emit<<<cdiv(r.n_rec, 256), 256, 0, st>>>(scratch, r.gid, r.gkey, gs_ctr + 1, ib, out, unsorted);
-    k_gs_groups<<<cdiv(r.n_groups, 256), 256, 0, st>>>(r.n_groups, r.gstart, r.gkey, ib, unsorted, scratch, out, list_warp, list_mid, list_cta, list_ctr);
-    k_gs_warp<<<(u32)c->sm_count * 8, 256, 0, st>>>(list_warp, list_ctr, gs_ctr + 7, r.gstart, r.gkey, ib, scratch, out);
+    k_gs_emit<<<cdiv(r.n_rec, 256), 256, 0, st>>>(scratch, r.gid, r.gkey, gs_ctr + 1, ib, out, unsorted, sec_out);
+    k_gs_groups<<<cdiv(r.n_groups, 256), 256, 0, st>>>(r.n_groups, r.gstart, r.gkey, ib, unsorted, scratch, out, sec_out, list_warp, list_mid, list_cta, list_ctr);
+    k_gs_warp<<<(u32)c->sm_count * 8, 256, 0, st>>>(list_warp, list_ctr, gs_ctr + 7, r.gstart, r.gkey, ib, scratch, out, sec_out);
     lc.n += 3;
     if (r.gmax > GS_WARP_MAX) {
-        k_gs_mid<<<(u32)c->sm_count * 3, 256, 8 * GS_MID_MAX * sizeof(u64), st>>>(list_mid, list_ctr + 1, gs_ctr + 8, r.gstart, r.gkey, ib, scratch, out);
+        k_gs_mid<<<(u32)c->sm_count * 3, 256, 8 * GS_MID_MAX * sizeof(u64), st>>>(list_mid, list_ctr + 1, gs_ctr + 8, r.gstart, r.gkey, ib, scratch, out, sec_out);
         lc.n++;
     }
     if (r.gmax > GS_MID_MAX) {
-        k_gs_cta<<<(u32)c->sm_count * 2, GS_CTA_THREADS, GS_CTA_MAX * sizeof(u64), st>>>(list_cta, list_ctr + 2, gs_ctr + 9, r.gstart, r.gkey, ib, scratch, out);
+        k_gs_cta<<<(u32)c->sm_count * 2, GS_CTA_THREADS, GS_CTA_MAX * sizeof(u64), st>>>(list_cta, list_ctr + 2, gs_ctr + 9, r.gstart, r.gkey, ib, scratch, out, sec_out);
         lc.n++;
     }
     r.lists = list_ctr;
@@ -1373,6 +1373,38 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             u64 *ak = A.take<u64>(N), *ak2 = A.take<u64>(N);
             u32 *av = A.take<u32>(N), *av2 = A.take<u32>(N);
             u32 *d_na = A.take<u32>(2);
+            u32 NA = 0;
+            u64 *apair = nullptr;
+            u32 *aqc = nullptr;
+            bool a_done = false;
+            const int ibN = bits_for(N - 1);
+            if (gsort && !wide_a && c->rows_grouped && cb + ibN <= 64 && 2 * sb + 1 + ibN <= 64) {
+                // the group sort with the chromosome pair as group (the strand bit of the table index stays 0) and the query centre as
+                // secondary key: anchors come grouped like the records and nearly in centre order
+                const u32 dead = (1u << (2 * sb + 1)) - 1;
+                {
+                    u64 *kk = ak;
+                    launch_for<t_anchor_keys>(N, st, lc, [=] __device__(u32 i) {
+                        const bool anchor = (flags[i] & F_ANCHOR) != 0;
+                        const u64 qc = ((u64)in.qs[i] + in.qe[i]) / 2;
+                        kk[i] = anchor ? ((((((u64)in.qid[i] << sb) | in.tid[i]) << 1) << cb) | qc) : (((u64)dead << cb) | ((1ull << cb) - 1));
+                    });
+                }
+                aqc = A.take<u32>((size_t)N + 1);
+                const u32 limit = K.group_sort_max ? std::min(K.group_sort_max, GS_CTA_MAX) : GS_CTA_MAX;
+                const GroupSorted gs = group_sort(c, ak, ak2, ak, av2, N, cb, GsIndex{1, sb, in.n_seq}, dead, g_entries, ibN, limit, false, aqc);
+                if (gs.done) {
+                    a_done = true;
+                    NA = gs.n_rec;
+                    apair = A.take<u64>((size_t)NA + 1);
+                    const u64 *w = ak;
+                    const u64 imask = (1ull << ibN) - 1;
+                    u64 *ap = apair;
+                    u32 *avw = av;
+                    launch_for<t_gather>(NA, st, lc, [=] __device__(u32 x) { ap[x] = w[x] >> (ibN + 1); avw[x] = (u32)(w[x] & imask); });
+                }
+            }
+            if (!a_done) {
             scan_flags([=] __device__(u32 i) -> bool { return (flags[i] & F_ANCHOR) != 0; },
                        [=] __device__(u32 i, u32 ex, u32 v) {
                            if (!v) return;
@@ -1381,7 +1413,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                            av[ex] = i;
                        },
                        N, bsum, d_na, st, lc);
-            const u32 NA = read_u32(c, d_na);
+            NA = read_u32(c, d_na);
             if (!wide_a) {
                 sort_pairs(c, ak, ak2, av, av2, NA, 2 * sb + cb);
             } else {
@@ -1393,16 +1425,19 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                 }
                 sort_pairs(c, ak, ak2, av, av2, NA, 2 * sb);
             }
-            u64 *apair = A.take<u64>(NA + 1);
-            u32 *aqc = A.take<u32>(NA + 1);
+            apair = A.take<u64>(NA + 1);
+            aqc = A.take<u32>(NA + 1);
             {
                 const u64 *akc = ak;
                 const u32 *avc = av;
                 const u64 cmask = (1ull << cb) - 1;
+                u64 *ap = apair;
+                u32 *aq = aqc;
                 launch_for<t_anchor_keys>(NA, st, lc, [=] __device__(u32 x) {
-                    if (wide_a) { const u32 i = avc[x]; apair[x] = akc[x]; aqc[x] = (u32)(((u64)in.qs[i] + in.qe[i]) / 2); }
-                    else { apair[x] = akc[x] >> cb; aqc[x] = (u32)(akc[x] & cmask); }
+                    if (wide_a) { const u32 i = avc[x]; ap[x] = akc[x]; aq[x] = (u32)(((u64)in.qs[i] + in.qe[i]) / 2); }
+                    else { ap[x] = akc[x] >> cb; aq[x] = (u32)(akc[x] & cmask); }
                 });
+            }
             }
             // candidates (alive, not an anchor, not a member of a swept-away scaffold), compacted so the searches run dense
             u32 *rlist = A.take<u32>(N);

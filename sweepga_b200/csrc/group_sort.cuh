@@ -221,12 +221,14 @@ __global__ void __launch_bounds__(256) k_gs_scatter(const u64 *__restrict__ keys
 
 // ---- emit: final form of every position, groups that are not in order ------------------------------------------------------
 __global__ void __launch_bounds__(256) k_gs_emit(const u64 *__restrict__ words, const u32 *__restrict__ gid, const u32 *__restrict__ gkey,
-                                                 const u32 *__restrict__ n_rec_ptr, int ib, u64 *__restrict__ out, u8 *__restrict__ unsorted) {
+                                                 const u32 *__restrict__ n_rec_ptr, int ib, u64 *__restrict__ out, u8 *__restrict__ unsorted,
+                                                 u32 *__restrict__ sec /* optional: the secondary key of every position */) {
     const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= *n_rec_ptr) return;
     const u64 w = words[p];
     const u32 d = gid[p];
     out[p] = ((u64)gkey[d] << ib) | (w & ((1ull << ib) - 1));
+    if (sec) sec[p] = (u32)(w >> ib);
     if (p > 0 && gid[p - 1] == d && words[p - 1] > w) unsorted[d] = 1;
 }
 
@@ -234,6 +236,7 @@ __global__ void __launch_bounds__(256) k_gs_emit(const u64 *__restrict__ words, 
 // thread per group: lists the groups k_gs_emit marked by size (pairs are finished here)
 __global__ void __launch_bounds__(256) k_gs_groups(u32 n_groups, const u32 *__restrict__ gstart, const u32 *__restrict__ gkey,
                                                    int ib, const u8 *__restrict__ unsorted, const u64 *__restrict__ words, u64 *__restrict__ out,
+                                                   u32 *__restrict__ sec,
                                                    u32 *__restrict__ list_warp, u32 *__restrict__ list_mid, u32 *__restrict__ list_cta,
                                                    u32 *__restrict__ list_ctr /*[3]*/) {
     const u32 d = blockIdx.x * blockDim.x + threadIdx.x;
@@ -248,6 +251,7 @@ __global__ void __launch_bounds__(256) k_gs_groups(u32 n_groups, const u32 *__re
                 if (b < a) { const u64 t = a; a = b; b = t; }
                 out[s] = hi | (a & mask);
                 out[s + 1] = hi | (b & mask);
+                if (sec) { sec[s] = (u32)(a >> ib); sec[s + 1] = (u32)(b >> ib); }
             } else cls = size <= GS_WARP_MAX ? 1 : size <= GS_MID_MAX ? 2 : 3;
         }
     }
@@ -287,7 +291,7 @@ __device__ __forceinline__ u32 gs_find_pieces_warp(const u64 *sm, u32 size, u32 
 }
 // The threads tid, tid + nthreads, ... of a warp or CTA (after a barrier that makes pstart visible) write the merged group.
 __device__ __forceinline__ void gs_merge_pieces(const u64 *sm, u32 size, const u32 *pstart, u32 n_pieces, u64 *__restrict__ dst, u64 hi,
-                                                u64 mask, u32 tid, u32 nthreads) {
+                                                u64 mask, u32 tid, u32 nthreads, u32 *__restrict__ sec /* or NULL */, int ib) {
     for (u32 e = tid; e < size; e += nthreads) {
         const u64 x = sm[e];
         u32 rank = 0;
@@ -305,6 +309,7 @@ __device__ __forceinline__ void gs_merge_pieces(const u64 *sm, u32 size, const u
             }
         }
         dst[rank] = hi | (x & mask);
+        if (sec) sec[rank] = (u32)(x >> ib);
     }
 }
 
@@ -340,7 +345,7 @@ template <int R> __device__ __forceinline__ void gs_bitonic_warp(u64 (&x)[R], u3
 }
 template <int R>
 __device__ __forceinline__ void gs_warp_group(const u64 *__restrict__ words, u64 *__restrict__ out, u32 s, u32 size, u64 hi, u64 mask, u32 lane,
-                                              u64 *sm /*[32 * R], this warp's*/, u32 *pst) {
+                                              u64 *sm /*[32 * R], this warp's*/, u32 *pst, u32 *__restrict__ sec, int ib) {
     u64 x[R];
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -352,7 +357,7 @@ __device__ __forceinline__ void gs_warp_group(const u64 *__restrict__ words, u64
     const u32 n_pieces = gs_find_pieces_warp(sm, size, pst, lane);
     __syncwarp();
     if (n_pieces) {
-        gs_merge_pieces(sm, size, pst, n_pieces, out + s, hi, mask, lane, 32);
+        gs_merge_pieces(sm, size, pst, n_pieces, out + s, hi, mask, lane, 32, sec ? sec + s : nullptr, ib);
         __syncwarp();
         return;
     }
@@ -360,13 +365,16 @@ __device__ __forceinline__ void gs_warp_group(const u64 *__restrict__ words, u64
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const u32 p = (u32)(r * 32) + lane;
-        if (p < size) out[s + p] = hi | (x[r] & mask);
+        if (p < size) {
+            out[s + p] = hi | (x[r] & mask);
+            if (sec) sec[s + p] = (u32)(x[r] >> ib);
+        }
     }
 }
 // warp per listed group (3 .. GS_WARP_MAX records), warps take groups from a counter
 __global__ void __launch_bounds__(256) k_gs_warp(const u32 *__restrict__ list, const u32 *__restrict__ n_list_ptr, u32 *work_ctr,
                                                  const u32 *__restrict__ gstart, const u32 *__restrict__ gkey, int ib, const u64 *__restrict__ words,
-                                                 u64 *__restrict__ out) {
+                                                 u64 *__restrict__ out, u32 *__restrict__ sec) {
     __shared__ u64 s_sm[8][GS_WARP_MAX];
     __shared__ u32 s_pst[8][GS_MERGE_MAX + 2];
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -380,9 +388,9 @@ __global__ void __launch_bounds__(256) k_gs_warp(const u32 *__restrict__ list, c
         const u32 d = list[w];
         const u32 s = gstart[d], size = gstart[d + 1] - s;
         const u64 hi = (u64)gkey[d] << ib;
-        if (size <= 32) gs_warp_group<1>(words, out, s, size, hi, mask, lane, s_sm[warp], s_pst[warp]);
-        else if (size <= 64) gs_warp_group<2>(words, out, s, size, hi, mask, lane, s_sm[warp], s_pst[warp]);
-        else gs_warp_group<4>(words, out, s, size, hi, mask, lane, s_sm[warp], s_pst[warp]);
+        if (size <= 32) gs_warp_group<1>(words, out, s, size, hi, mask, lane, s_sm[warp], s_pst[warp], sec, ib);
+        else if (size <= 64) gs_warp_group<2>(words, out, s, size, hi, mask, lane, s_sm[warp], s_pst[warp], sec, ib);
+        else gs_warp_group<4>(words, out, s, size, hi, mask, lane, s_sm[warp], s_pst[warp], sec, ib);
     }
 }
 static_assert(GS_WARP_MAX == 128, "gs_warp_group<4> holds 128 words");
@@ -391,7 +399,7 @@ static_assert(GS_WARP_MAX == 128, "gs_warp_group<4> holds 128 words");
 // barrier anywhere, the eight warps of a CTA work on eight groups
 __global__ void __launch_bounds__(256) k_gs_mid(const u32 *__restrict__ list, const u32 *__restrict__ n_list_ptr, u32 *work_ctr,
                                                 const u32 *__restrict__ gstart, const u32 *__restrict__ gkey, int ib, const u64 *__restrict__ words,
-                                                u64 *__restrict__ out) {
+                                                u64 *__restrict__ out, u32 *__restrict__ sec) {
     extern __shared__ __align__(16) unsigned char gs_smem_raw[];
     const u32 lane = threadIdx.x & 31;
     u64 *sm = reinterpret_cast<u64 *>(gs_smem_raw) + (threadIdx.x >> 5) * GS_MID_MAX;
@@ -415,7 +423,7 @@ __global__ void __launch_bounds__(256) k_gs_mid(const u32 *__restrict__ list, co
         const u32 n_pieces = gs_find_pieces_warp(sm, size, pst, lane);
         __syncwarp();
         if (n_pieces) { // a few ascending pieces: merge
-            gs_merge_pieces(sm, size, pst, n_pieces, out + s, hi, mask, lane, 32);
+            gs_merge_pieces(sm, size, pst, n_pieces, out + s, hi, mask, lane, 32, sec ? sec + s : nullptr, ib);
             continue;
         }
         for (u32 k = 2; k <= np; k <<= 1) {
@@ -429,14 +437,17 @@ __global__ void __launch_bounds__(256) k_gs_mid(const u32 *__restrict__ list, co
                 __syncwarp();
             }
         }
-        for (u32 p = lane; p < size; p += 32) out[s + p] = hi | (sm[p] & mask);
+        for (u32 p = lane; p < size; p += 32) {
+            out[s + p] = hi | (sm[p] & mask);
+            if (sec) sec[s + p] = (u32)(sm[p] >> ib);
+        }
     }
 }
 
 // CTA per listed group (GS_MID_MAX + 1 .. GS_CTA_MAX records): the group in shared memory, in-order check, bitonic network
 __global__ void __launch_bounds__(GS_CTA_THREADS) k_gs_cta(const u32 *__restrict__ list, const u32 *__restrict__ n_list_ptr, u32 *work_ctr,
                                                            const u32 *__restrict__ gstart, const u32 *__restrict__ gkey, int ib,
-                                                           const u64 *__restrict__ words, u64 *__restrict__ out) {
+                                                           const u64 *__restrict__ words, u64 *__restrict__ out, u32 *__restrict__ sec) {
     extern __shared__ __align__(16) unsigned char gs_smem_raw[];
     u64 *sm = reinterpret_cast<u64 *>(gs_smem_raw);
     __shared__ u32 s_w, s_done, s_pst[GS_MERGE_MAX + 2];
@@ -461,7 +472,7 @@ __global__ void __launch_bounds__(GS_CTA_THREADS) k_gs_cta(const u32 *__restrict
         }
         __syncthreads();
         if (s_done) {
-            gs_merge_pieces(sm, size, s_pst, s_done, out + s, hi, mask, threadIdx.x, GS_CTA_THREADS);
+            gs_merge_pieces(sm, size, s_pst, s_done, out + s, hi, mask, threadIdx.x, GS_CTA_THREADS, sec ? sec + s : nullptr, ib);
             continue;
         }
         for (u32 k = 2; k <= np; k <<= 1) {
@@ -475,7 +486,10 @@ __global__ void __launch_bounds__(GS_CTA_THREADS) k_gs_cta(const u32 *__restrict
                 __syncthreads();
             }
         }
-        for (u32 p = threadIdx.x; p < size; p += GS_CTA_THREADS) out[s + p] = hi | (sm[p] & mask);
+        for (u32 p = threadIdx.x; p < size; p += GS_CTA_THREADS) {
+            out[s + p] = hi | (sm[p] & mask);
+            if (sec) sec[s + p] = (u32)(sm[p] >> ib);
+        }
     }
 }
 
