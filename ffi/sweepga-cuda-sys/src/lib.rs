@@ -148,6 +148,8 @@ extern "C" {
     pub fn swg_filter(ctx: *mut swg_ctx, cfg: *const swg_config, host_in: *const swg_mappings, host_out: *mut swg_result, stats: *mut swg_stats) -> c_int;
     pub fn swg_filter_device(ctx: *mut swg_ctx, cfg: *const swg_config, dev_in: *const swg_mappings, dev_out: *mut swg_result, stats: *mut swg_stats) -> c_int;
     pub fn swg_stream(ctx: *mut swg_ctx) -> *mut c_void;
+    pub fn swg_prefetch(ctx: *mut swg_ctx, host_in: *const swg_mappings) -> c_int;
+    pub fn swg_prefetch_drop(ctx: *mut swg_ctx);
     pub fn swg_upload(ctx: *mut swg_ctx, host_in: *const swg_mappings, dev_out: *mut swg_mappings, dev_res: *mut swg_result) -> c_int;
     pub fn swg_release(ctx: *mut swg_ctx, dev: *mut swg_mappings, dev_res: *mut swg_result);
     pub fn swg_download_result(ctx: *mut swg_ctx, n: u64, dev_res: *const swg_result, host_out: *mut swg_result) -> c_int;

@@ -186,6 +186,16 @@ int swg_filter_device(swg_ctx *ctx, const swg_config *cfg, const swg_mappings *d
 /* Raw stream handle (cudaStream_t) the context launches on — for event timing. */
 void *swg_stream(swg_ctx *ctx);
 
+/* Streaming hint for a caller that filters many tables back to back (one PAF per sample, per chromosome, per batch):
+ * swg_prefetch() starts the host->device copy of `host_in` on the copy engine and returns at once; a later
+ * swg_filter() called with a table of the SAME n and column pointers finds it on the device (oldest first) and skips its
+ * own upload, so the upload of table k+1 overlaps the kernels and the result download of table k.  Up to two prefetched
+ * tables per context; the host columns must stay valid and unchanged until the swg_filter call that consumes them
+ * returns.  Pinned host memory overlaps; pageable memory is staged at once (no overlap).  swg_filter on any other
+ * table uploads as usual.  swg_prefetch_drop() forgets the outstanding prefetches.                                      */
+int swg_prefetch(swg_ctx *ctx, const swg_mappings *host_in);
+void swg_prefetch_drop(swg_ctx *ctx);
+
 /* Upload a host table once / free it; lets a caller time swg_filter_device on
  * resident data without touching CUDA itself.                                   */
 int swg_upload(swg_ctx *ctx, const swg_mappings *host_in, swg_mappings *dev_out, swg_result *dev_res);

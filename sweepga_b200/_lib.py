@@ -69,6 +69,8 @@ SYMBOLS = [
     ("swg_filter", C.c_int, [_vp, _cfgp, _mapp, _resp, _statp]),
     ("swg_filter_device", C.c_int, [_vp, _cfgp, _mapp, _resp, _statp]),
     ("swg_stream", _vp, [_vp]),
+    ("swg_prefetch", C.c_int, [_vp, _mapp]),
+    ("swg_prefetch_drop", None, [_vp]),
     ("swg_upload", C.c_int, [_vp, _mapp, _mapp, _resp]),
     ("swg_release", None, [_vp, _mapp, _resp]),
     ("swg_download_result", C.c_int, [_vp, C.c_uint64, _resp, _resp]),

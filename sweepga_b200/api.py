@@ -275,6 +275,14 @@ class Context:
         self._check(lib.swg_filter(self._h, C.byref(cc), C.byref(cm), C.byref(res), C.byref(stats)))
         return status, chain_id, stats
 
+    def prefetch(self, table: MappingTable):
+        """Start uploading `table` now (swg_prefetch); the next filter() of the same table (same arrays) finds it on the device."""
+        cm = table.to_c()
+        self._check(lib.swg_prefetch(self._h, C.byref(cm)))
+
+    def prefetch_drop(self):
+        lib.swg_prefetch_drop(self._h)
+
     def upload(self, table: MappingTable):
         dev, dres = _lib.swg_mappings(), _lib.swg_result()
         cm = table.to_c()

@@ -183,6 +183,11 @@ struct swg_ctx {
     Arena score_arena;             // ... and its device copy
     Arena arena;      // per-call scratch
     Arena io;         // staging of host SoA for swg_filter
+    // swg_prefetch: up to two tables already (being) uploaded, oldest first
+    struct Prefetched { bool valid = false; swg_mappings key; swg_mappings dev; swg_result dres; cudaEvent_t ready = nullptr; size_t h2d_bytes = 0; Arena arena; };
+    Prefetched pf[2];
+    int pf_head = 0, pf_count = 0;
+    cudaStream_t up_stream = nullptr;
     bool rows_grouped = false;    // last k_prefilter: the rows come in runs of one (query, target, strand) (aligner order)
     u32 *gtable = nullptr;        // group sort (group_sort.cuh): per possible (query, target, strand) group a counter (u32, cleared
     size_t gtable_entries = 0;    // by every call) and its dense number (u32)
@@ -1739,6 +1744,7 @@ static bool is_pageable(const void *p) {
 }
 
 struct UploadArgs { swg_ctx *c; const swg_mappings *in; swg_mappings *dev; swg_result *res; Arena *arena; bool overlap_matches = false; size_t h2d_bytes = 0; bool pageable = false;
+                    cudaStream_t stream = nullptr; /* NULL: the context's main stream */
                     bool late_blen = false; /* block_length travels with `matches` (the retain does not test it: min_block_length == 0) */ };
 
 struct t_widen;
@@ -1755,7 +1761,7 @@ static void do_upload(void *p) {
     a->arena->reserve(bytes);
     Arena &A = *a->arena;
     swg_mappings d = *h;
-    cudaStream_t st = c->stream;
+    cudaStream_t st = a->stream ? a->stream : c->stream;
     // the columns the first kernels need, then `matches` (first read after the sort): with overlap_matches it travels behind the
     // others on the copy stream, so prefilter, key build and sort run while it is still on the wire
     std::vector<CopyJob> first, last;
@@ -1940,6 +1946,8 @@ swg_ctx *swg_create(int device) {
         for (auto &ev : c->ev_sort) SWG_CUDA(cudaEventCreate(&ev));
         for (auto &ev : c->ev_pre) SWG_CUDA(cudaEventCreate(&ev));
         SWG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        SWG_CUDA(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
+        for (auto &p : c->pf) SWG_CUDA(cudaEventCreateWithFlags(&p.ready, cudaEventDisableTiming));
         for (auto &ev : c->ev_copy) SWG_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         SWG_CUDA(cudaEventCreateWithFlags(&c->ev_ctr, cudaEventDisableTiming));
         SWG_CUDA(cudaMallocHost(&c->h_ctr, sizeof(u64) * (C_COUNT + 8)));
@@ -1978,6 +1986,8 @@ void swg_destroy(swg_ctx *c) {
     for (auto &ev : c->ev_copy) if (ev) cudaEventDestroy(ev);
     if (c->ev_ctr) cudaEventDestroy(c->ev_ctr);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->up_stream) { cudaStreamSynchronize(c->up_stream); cudaStreamDestroy(c->up_stream); }
+    for (auto &p : c->pf) { if (p.ready) cudaEventDestroy(p.ready); p.arena.release(); }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -2022,13 +2032,29 @@ int swg_filter(swg_ctx *c, const swg_config *cfg, const swg_mappings *host_in, s
         UploadArgs ua{c, a->in, &dev, &dres, &c->io, true};
         ua.late_blen = a->cfg->min_block_length == 0;
         SWG_CUDA(cudaEventRecord(c->ev[0], c->stream));
-        if (a->in->n) do_upload(&ua);
+        // a table swg_prefetch already put (or is putting) on the device: same n, same column pointers, oldest first
+        swg_ctx::Prefetched *pf = nullptr;
+        if (a->in->n && c->pf_count > 0) {
+            swg_ctx::Prefetched &p = c->pf[c->pf_head];
+            const swg_mappings &k = p.key, &m = *a->in;
+            if (p.valid && k.n == m.n && k.n_seq == m.n_seq && k.query_id == m.query_id && k.target_id == m.target_id && k.query_id16 == m.query_id16 &&
+                k.target_id16 == m.target_id16 && k.query_start == m.query_start && k.query_end == m.query_end && k.target_start == m.target_start &&
+                k.target_end == m.target_end && k.block_length == m.block_length && k.matches == m.matches && k.identity == m.identity &&
+                k.strand == m.strand && k.score == m.score && k.seq_genome_id == m.seq_genome_id && k.seq_genome2_id == m.seq_genome2_id)
+                pf = &p;
+        }
+        if (pf) {
+            dev = pf->dev;
+            dres = pf->dres;
+            ua.h2d_bytes = pf->h2d_bytes;
+            SWG_CUDA(cudaStreamWaitEvent(c->stream, pf->ready, 0));
+        } else if (a->in->n) do_upload(&ua);
         SWG_CUDA(cudaEventRecord(c->ev[1], c->stream));
         swg_stats local;
         std::memset(&local, 0, sizeof local);
         if (a->in->n) {
-            run_filter_exact(c, *a->cfg, make_devin(&dev), dres.status, dres.chain_id, &local, c->ev_copy[1], a->in);
-            SWG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy[1], 0)); // early exits never touched `matches`: still wait for its copy
+            run_filter_exact(c, *a->cfg, make_devin(&dev), dres.status, dres.chain_id, &local, pf ? nullptr : c->ev_copy[1], a->in);
+            if (!pf) SWG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy[1], 0)); // early exits never touched `matches`: still wait for its copy
         }
         SWG_CUDA(cudaEventRecord(c->ev[2], c->stream));
         if (a->in->n) {
@@ -2052,8 +2078,37 @@ int swg_filter(swg_ctx *c, const swg_config *cfg, const swg_mappings *host_in, s
         local.ms_h2d = m0; local.ms_device = m1; local.ms_d2h = m2;
         local.h2d_bytes = ua.h2d_bytes;
         local.d2h_bytes = a->in->n * 5;
+        if (pf) { pf->valid = false; c->pf_head ^= 1; c->pf_count--; }
         if (a->stats) *a->stats = local;
     }, &a);
+}
+
+int swg_prefetch(swg_ctx *c, const swg_mappings *host_in) {
+    if (!c) return SWG_ERR_ARG;
+    if (!check_maps(c, host_in) || host_in->n == 0) return SWG_ERR_ARG;
+    if (c->pf_count >= 2) { set_err(c, "swg_prefetch: two tables are already outstanding"); return SWG_ERR_ARG; }
+    struct Args { swg_ctx *c; const swg_mappings *in; } a{c, host_in};
+    return guarded(c, "swg_prefetch", [](void *p) {
+        Args *a = (Args *)p;
+        swg_ctx *c = a->c;
+        SWG_CUDA(cudaSetDevice(c->device));
+        swg_ctx::Prefetched &slot = c->pf[(c->pf_head + c->pf_count) & 1];
+        UploadArgs ua{c, a->in, &slot.dev, &slot.dres, &slot.arena, false};
+        ua.stream = c->up_stream;
+        do_upload(&ua);
+        SWG_CUDA(cudaEventRecord(slot.ready, c->up_stream));
+        slot.key = *a->in;
+        slot.h2d_bytes = ua.h2d_bytes;
+        slot.valid = true;
+        c->pf_count++;
+    }, &a);
+}
+void swg_prefetch_drop(swg_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->up_stream) cudaStreamSynchronize(c->up_stream);
+    for (auto &p : c->pf) p.valid = false;
+    c->pf_head = c->pf_count = 0;
 }
 
 int swg_upload(swg_ctx *c, const swg_mappings *host_in, swg_mappings *dev_out, swg_result *dev_res) {

@@ -93,3 +93,30 @@ def test_many_sequences_wide_keys(ctx):
         s, c, _ = ctx.filter(cfg, t)
         os_, oc, _ = oracle_lib.apply_filters(cfg, t)
         assert np.array_equal(s, os_) and np.array_equal(c, oc)
+
+
+def test_prefetch_gives_the_same_result(ctx, big):
+    """swg_prefetch: a table uploaded ahead of its swg_filter call gives the same result; a filter call on other arrays ignores
+    the prefetched table; at most two are outstanding; swg_prefetch_drop forgets them."""
+    cfg = swg.FilterConfig.from_cli(scaffold_dist="100k")
+    s0, c0, st0 = ctx.filter(cfg, big)
+    ctx.prefetch(big)
+    s1, c1, st1 = ctx.filter(cfg, big)            # consumes the prefetched copy
+    assert np.array_equal(s0, s1) and np.array_equal(c0, c1) and st1.h2d_bytes == st0.h2d_bytes
+    ctx.prefetch(big)
+    ctx.prefetch(big)
+    with pytest.raises(swg.SwgError):
+        ctx.prefetch(big)                         # a third one
+    other = big.take(np.arange(big.n // 2))
+    other = swg.MappingTable(other.query_id, other.target_id, other.query_start, other.query_end, other.target_start, other.target_end,
+                             other.block_length, other.matches, other.identity, other.strand, other.seq_genome_id, other.seq_genome2_id)
+    so, co, _ = ctx.filter(cfg, other)            # different arrays: uploaded as usual, the prefetched tables stay
+    s2, c2, _ = ctx.filter(cfg, big)
+    s3, c3, _ = ctx.filter(cfg, big)
+    assert np.array_equal(s0, s2) and np.array_equal(c0, c2) and np.array_equal(s0, s3) and np.array_equal(c0, c3)
+    so2, co2, _ = ctx.filter(cfg, other)
+    assert np.array_equal(so, so2) and np.array_equal(co, co2)
+    ctx.prefetch(big)
+    ctx.prefetch_drop()
+    s4, c4, _ = ctx.filter(cfg, big)
+    assert np.array_equal(s0, s4) and np.array_equal(c0, c4)
