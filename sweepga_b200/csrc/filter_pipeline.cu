@@ -784,6 +784,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     bool kept_is_alive = false;   // the keys came from k_prefilter: kept == alive, nobody counted C_KEPT_M
     bool groups_done = false;     // gid / gstart / group count already produced (group sort)
     const u32 *gs_lists = nullptr; // group sort: [3] groups that had to be ordered, by size class (diagnostic)
+    u32 gs_gmax = 0;               // ... its largest group
     u32 n_groups = 0;
     u32 *gstart = nullptr, *gid = nullptr;
     u32 *d_tot = A.take<u32>(4);
@@ -823,6 +824,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                     gshift = ib;
                     groups_done = true;
                     gs_lists = gs.lists;
+                    gs_gmax = gs.gmax;
                 }
             } else {
                 // some group is larger than one CTA sorts: the LSD passes take over (the keys are still in place)
@@ -917,7 +919,11 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     }
     // groups of at least fx_min positions are chained by the fixed-point iteration (SWG_NO_FIXPOINT=1: by the warp walk)
     const u32 fx_min = K.no_fixpoint ? NONE32 : (K.fixpoint_min ? K.fixpoint_min : FX_MIN_GROUP);
-    {   // group count, positions in huge groups and a rough count of the candidate evaluations ahead (SWG_MAX_PAIR_EVALS, if
+    if (groups_done && gs_gmax < fx_min && !(K.max_pair_evals > 0)) {
+        // the group sort has told the host the group count and the largest group: no huge group, nothing to estimate, no round trip
+        launch_for<t_gather>(n_m, st, lc, [=] __device__(u32 p) { srec[p] = __ldg(&rec4[sidx[p]]); });
+    } else {
+        // group count, positions in huge groups and a rough count of the candidate evaluations ahead (SWG_MAX_PAIR_EVALS, if
         // set, refuses an input beyond it; by default nothing is refused: the reference runs such piles to completion too).
         // The host picks the numbers up while the gather below runs.
         if (K.max_pair_evals > 0) k_chain_work_estimate<true><<<(u32)c->sm_count * 8, 256, 0, st>>>(rec4, sidx, gstart, d_tot, n_m, cfg.scaffold_gap, fx_min, ctr);
