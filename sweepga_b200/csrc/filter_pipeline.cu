@@ -579,18 +579,6 @@ static void general_sweep(swg_ctx *c, u32 n_items, const u8 *include, u8 include
     c->arena.rewind(mk);
 }
 
-// segment-first: for keys sorted ascending with payload vals (n rows), out[vals[u]] = vals[first row of u's segment]
-static void segment_first(swg_ctx *c, const u64 *sk, const u32 *sv, u32 n, u32 *out) {
-    if (n == 0) return;
-    cudaStream_t st = c->stream;
-    u32 *segof = c->arena.take<u32>(n), *segfirst = c->arena.take<u32>(n);
-    u32 *bsum = c->arena.take<u32>(scan_temp_u32(n)), *tot = c->arena.take<u32>(1);
-    scan_flags([=] __device__(u32 u) -> u32 { return (u == 0 || sk[u] != sk[u - 1]) ? 1u : 0u; },
-               [=] __device__(u32 u, u32 ex, u32 v) { u32 s = ex + v - 1; segof[u] = s; if (v) segfirst[s] = sv[u]; }, n, bsum, tot,
-               st, c->lc);
-    launch_for<t_segapply>(n, st, c->lc, [=] __device__(u32 u) { out[sv[u]] = segfirst[segof[u]]; });
-}
-
 } // namespace swg
 
 #include "chain_fixpoint.cuh"
