@@ -1061,18 +1061,14 @@ __device__ __forceinline__ bool act_less(const ActEntry &a, const ActEntry &b) {
 // is.  S(p) changes only at the starts and ends of those neighbours.  Groups where a scan gets long (deep piles, one very long item) go to the warp-per-group kernel, which
 // redoes the whole group and k_sweep_keep_big overwrites the keep bytes of its items.
 constexpr u32 SWF_LEFT = 48, SWF_RIGHT = 48;
-__global__ void __launch_bounds__(256)
-k_sweep_flat1(const u32 *__restrict__ sitem, const SweepItem *__restrict__ sdata, const u32 *__restrict__ gid, const u32 *__restrict__ gstart,
-              const u32 *__restrict__ pmax, u32 n_groups, u32 n_sorted, double thr, u8 *__restrict__ keep, u32 *gflag, u32 *big_list,
-              u32 *big_count, u64 *ctr, u32 scan_limit /* SWF_LEFT; 0: every group of two or more items counts as a pile (tests) */) {
-    const u32 u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= n_sorted) return;
+// the verdict of one item (sorted position u): everything k_sweep_flat1's header describes
+__device__ __forceinline__ void sweep_flat1_item(u32 u, const u32 *__restrict__ sitem, const SweepItem *__restrict__ sdata, const u32 *__restrict__ gid,
+                                                 const u32 *__restrict__ gstart, const u32 *__restrict__ pmax, u32 n_groups, u32 n_sorted, double thr,
+                                                 u8 *__restrict__ keep, u32 *gflag, u32 *big_list, u32 *big_count, u64 *ctr, u32 scan_limit) {
     const u32 g = gid[u];
     const u32 gs = gstart[g], ge = (g + 1 < n_groups) ? gstart[g + 1] : n_sorted;
     const u32 item = sitem[u];
-    if (ge - gs <= 1) { keep[item] = 1; return; } // a single interval: kept (plane_sweep_exact.rs:274-276)
     const SweepItem me = sdata[u];
-    if (me.end <= me.start) return; // zero length: its End follows its Begin at the same position, it is never evaluated (keep stays 0)
     bool big = scan_limit == 0;
     u32 lo = u, hi = u;
     for (u32 k = u, steps = 0; k > gs && !big;) {
@@ -1113,14 +1109,68 @@ k_sweep_flat1(const u32 *__restrict__ sitem, const SweepItem *__restrict__ sdata
         else if (want_flag && !is_flag) is_flag = overlaps_more_than(me.start, me.end, bstart, bend, thr);
     };
     eval(me.start);
-    for (u32 k = lo; k <= hi; k++) {
-        if (is_good && (is_flag || !want_flag)) break;
+    for (u32 k = lo; k <= hi && !is_flag; k++) {
+        if (is_good && !want_flag) break;
         if (k == u) continue;
         const SweepItem a = sdata[k];
         if (k > u && a.start > me.start) eval(a.start);
         if (a.end > me.start && a.end < me.end) eval(a.end);
     }
     if (is_good && !is_flag) keep[item] = 1;
+}
+// First pass, 1024 items per CTA: an item alone in its span — nothing to its left reaches its start, its right neighbour starts at
+// or after its end: nine in ten on collinear data — is the best of every active set it is in: kept, no neighbour scan.  The others
+// are LISTED (one counter atomic per CTA) and judged by k_sweep_flat1_rest with all lanes busy (judging them in place ran at 12 of
+// 32 threads per instruction).
+__global__ void __launch_bounds__(256)
+k_sweep_flat1(const u32 *__restrict__ sitem, const SweepItem *__restrict__ sdata, const u32 *__restrict__ gid, const u32 *__restrict__ gstart,
+              const u32 *__restrict__ pmax, u32 n_groups, u32 n_sorted, u8 *__restrict__ keep, u32 *__restrict__ rest, u32 *rest_count, u32 scan_limit) {
+    __shared__ u32 s_w[8][4];
+    __shared__ u32 s_base;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 base = blockIdx.x * 1024;
+    bool f[4];
+    u32 m[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const u32 u = base + k * 256 + threadIdx.x;
+        f[k] = false;
+        if (u < n_sorted) {
+            const u32 g = gid[u];
+            const u32 gs = gstart[g], ge = (g + 1 < n_groups) ? gstart[g + 1] : n_sorted;
+            if (ge - gs <= 1) keep[sitem[u]] = 1; // a single interval: kept (plane_sweep_exact.rs:274-276)
+            else {
+                const SweepItem me = sdata[u];
+                if (me.end > me.start) { // (zero length: its End follows its Begin at the same position, never evaluated: keep stays 0)
+                    const bool alone = scan_limit != 0 && (u == gs || pmax[u - 1] <= me.start) && (u + 1 == ge || sdata[u + 1].start >= me.end);
+                    if (alone) keep[sitem[u]] = 1;
+                    else f[k] = true;
+                }
+            }
+        }
+        m[k] = __ballot_sync(0xFFFFFFFFu, f[k]);
+        if (lane == 0) s_w[warp][k] = __popc(m[k]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 tot = 0;
+        for (int k = 0; k < 4; k++)
+            for (int w = 0; w < 8; w++) { const u32 t = s_w[w][k]; s_w[w][k] = tot; tot += t; }
+        s_base = tot ? atomicAdd(rest_count, tot) : 0;
+    }
+    __syncthreads();
+    const u32 lt = (1u << lane) - 1;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (f[k]) rest[s_base + s_w[warp][k] + __popc(m[k] & lt)] = base + k * 256 + threadIdx.x;
+}
+__global__ void __launch_bounds__(256)
+k_sweep_flat1_rest(const u32 *__restrict__ rest, const u32 *__restrict__ rest_count, const u32 *__restrict__ sitem, const SweepItem *__restrict__ sdata,
+                   const u32 *__restrict__ gid, const u32 *__restrict__ gstart, const u32 *__restrict__ pmax, u32 n_groups, u32 n_sorted, double thr,
+                   u8 *__restrict__ keep, u32 *gflag, u32 *big_list, u32 *big_count, u64 *ctr, u32 scan_limit) {
+    const u32 n = *rest_count;
+    for (u32 x = blockIdx.x * blockDim.x + threadIdx.x; x < n; x += gridDim.x * blockDim.x)
+        sweep_flat1_item(rest[x], sitem, sdata, gid, gstart, pmax, n_groups, n_sorted, thr, keep, gflag, big_list, big_count, ctr, scan_limit);
 }
 
 // keep = good && !flagged for the items of the groups the warp kernel redid (n_keep == 1 path)

@@ -538,8 +538,12 @@ static void general_sweep_impl(swg_ctx *c, u32 n_items, const u8 *include, u8 in
     SWG_CUDA(cudaMemsetAsync(sw_ctr, 0, 4 * sizeof(u32), st));
     stage_mark(c, "gs_sweep");
     if (n_keep == 1 && !no_flat) {
-        k_sweep_flat1<<<cdiv(n_inc, 256), 256, 0, st>>>(ev, sdata, gid, gstart, pmax, n_groups, n_inc, thr, keep, gflag, big_list, sw_ctr + 1,
-                                                       ctr, c->knobs.sweep_tree_all ? 0u : SWF_LEFT);
+        u32 *rest = c->arena.take<u32>(n_inc);
+        const u32 limit = c->knobs.sweep_tree_all ? 0u : SWF_LEFT;
+        k_sweep_flat1<<<cdiv(n_inc, 1024), 256, 0, st>>>(ev, sdata, gid, gstart, pmax, n_groups, n_inc, keep, rest, sw_ctr + 3, limit);
+        k_sweep_flat1_rest<<<(u32)c->sm_count * 8, 256, 0, st>>>(rest, sw_ctr + 3, ev, sdata, gid, gstart, pmax, n_groups, n_inc, thr, keep, gflag,
+                                                                  big_list, sw_ctr + 1, ctr, limit);
+        c->lc.n++;
     } else {
         const int sweep_mult = c->knobs.sweep_mult;
         k_sweep_small<<<(u32)c->sm_count * sweep_mult, 128, 0, st>>>(ev, sdata, gstart, n_groups, n_inc, n_keep, thr, good, flagged, big_list,
