@@ -700,7 +700,11 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
     if (cfg.scaffold_gap != 0) { keys = A.take<u64>(N); keys2 = A.take<u64>(N); vals = A.take<u32>(N); vals2 = A.take<u32>(N); }
     // The record sort as a counting sort by group (group_sort.cuh) when the table of all possible groups fits.
     const u64 g_entries = 2ull * in.n_seq * in.n_seq;
-    const bool gsort = cfg.scaffold_gap != 0 && !K.force_wide && !K.pairs_sort && !K.no_group_sort && g_entries <= GS_MAX_TABLE && 2 * sb0 + 1 <= 31;
+    bool gsort = cfg.scaffold_gap != 0 && !K.force_wide && !K.pairs_sort && !K.no_group_sort && g_entries <= GS_MAX_TABLE && 2 * sb0 + 1 <= 31;
+    if (gsort) {
+        try { group_table(c, g_entries); } // (up to 512 MB for ~5800 sequences) no room: the LSD passes need no table
+        catch (const OomError &) { gsort = false; }
+    }
     SWG_CUDA(cudaEventRecord(c->ev_pre[0], st));
     if (fused_keys) k_prefilter<true><<<cdiv(N, 256), 256, 0, st>>>(in, cfg.min_block_length, cfg.min_identity, cfg.keep_self, flags, ctr, hk, hv, hcap - 1, rec4, sb0, keys, vals);
     else k_prefilter<false><<<cdiv(N, 256), 256, 0, st>>>(in, cfg.min_block_length, cfg.min_identity, cfg.keep_self, flags, ctr, hk, hv, hcap - 1, rec4);
