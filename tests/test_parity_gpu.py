@@ -480,3 +480,12 @@ def test_tree_sweep_pile(ctx, case):
     """configs[4] shape at a size the oracle finishes: the pile's groups leave the neighbour scans by themselves."""
     t = synth.skew(n_pile=20_000, n_tiny_groups=3_000, seed=5, window=3_000_000)
     check(ctx, swg.FilterConfig.from_cli(**CLI_CASES[case]), t, f"pile {case}")
+
+
+def test_record_sort_with_more_sequences_than_the_group_table_serves(ctx):
+    """6000 sequences: 2 * n_seq^2 entries would exceed the group table's limit, so the record sort runs the LSD passes (the plane
+    sweeps' item sort still fits its own, smaller table).  Same result as the oracle either way."""
+    t = fuzz_table(77, 5000, n_genomes=6000, n_chr=1, span=200000, max_len=3000, hashless=True)
+    for flags in ({}, dict(num_mappings="1:1", scaffold_filter="1:1", scaffold_jump="5000", scaffold_mass="0", scaffold_dist="2000")):
+        _, _, st = check(ctx, swg.FilterConfig.from_cli(**flags), t, f"6000 sequences {flags}")
+        assert st.n_sort_passes > 0
