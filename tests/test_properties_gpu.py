@@ -120,3 +120,16 @@ def test_prefetch_gives_the_same_result(ctx, big):
     ctx.prefetch_drop()
     s4, c4, _ = ctx.filter(cfg, big)
     assert np.array_equal(s0, s4) and np.array_equal(c0, c4)
+
+
+@pytest.mark.parametrize("n,bits", [(1, 8), (2, 64), (5375, 17), (5376, 33), (5377, 64), (100_000, 50), (2_097_151, 41), (2_097_152, 41), (3_000_000, 53)])
+def test_radix_sort_tiles(ctx, n, bits):
+    """The stable LSD sort of (key, payload) pairs on pseudo-random keys, checked on the device (sorted, stable, payload intact),
+    at sizes around the tile boundaries (5376 pairs per CTA) and with 1 .. 8 passes."""
+    import ctypes as C
+    from sweepga_b200 import _lib
+    fn = C.CDLL(_lib.LIB_PATH).swg__bench_sort
+    fn.restype = C.c_int
+    ms, ok = C.c_double(), C.c_int()
+    rc = fn(C.c_void_p(ctx._h), C.c_uint64(n), C.c_int(bits), C.c_int(1), C.byref(ms), C.byref(ok))
+    assert rc == 0 and ok.value == 1
