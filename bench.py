@@ -345,8 +345,14 @@ def modes_leg(ctx, d_in, d_res, n):
         ctx.filter_device(cfg, d_in, d_res)
         sts = [ctx.filter_device(cfg, d_in, d_res) for _ in range(3)]
         ms = min(s.ms_device for s in sts)
+        peak, _ = peaks()
         out["1:1/1:1 on the 20 M table"] = {"ms_device": ms, "Mmappings_per_s": n / ms / 1e3, "gpu_launches": int(sts[-1].gpu_launches),
-                                            "kept": int(sts[-1].n_kept), "pipeline_algorithmic_bytes_per_mapping": 1134}
+                                            "kept": int(sts[-1].n_kept), "pipeline_algorithmic_bytes_per_mapping": 1134,
+                                            "pipeline_fraction_of_hbm_roofline": n * 1134 / (ms / 1e3) / 1e9 / peak}
+        try:  # the sweep kernels themselves: DRAM fraction and threads per instruction come from an ncu capture, not from this run
+            out["roofline_sweep"] = json.load(open(os.path.join(ROOT, "profiles", "sweep_profile.json")))
+        except Exception:
+            pass
         t = synth.skew(n_pile=1_000_000, n_tiny_groups=100_000, seed=5)
         p_in, p_res = ctx.upload(t)
         cfg = swg.FilterConfig.from_cli(num_mappings="1:1", scaffold_jump="0")
