@@ -38,7 +38,7 @@
 
 namespace swg {
 
-struct t_fx_init; struct t_fx_count; struct t_fx_minpi; struct t_fx_all; struct t_fx_fill; struct t_fx_pred; struct t_fx_jump; struct t_fx_scatter;
+struct t_fx_init; struct t_fx_hg; struct t_fx_bkey; struct t_fx_brec; struct t_fx_dir; struct t_fx_count; struct t_fx_minpi; struct t_fx_all; struct t_fx_fill; struct t_fx_pred; struct t_fx_jump; struct t_fx_scatter;
 
 constexpr u32 FX_XCAP = 1024;     // blocked candidates remembered per position; a position with more is re-evaluated every round
 constexpr u16 FX_XOVER = 0xFFFF; // xcnt value of such a position
@@ -68,6 +68,13 @@ struct FxArrays {
     u32 *dirty, *dps;  // per block of successors: some picker list in it changed in the last round; prefix counts of that
     u32 use_dirty;     // 0: check every position (first round, or the feature is off)
     u32 *ctrs;         // [0] list length, [1] picks changed this round, [2] recompute work counter, [3] slots refused (pool full)
+    // target-bucket order (fx_bucket_pass): the positions of every huge group once more, ordered by (group, target bucket, k)
+    u32 *hg;           // dense number of the position's huge group
+    uint2 *bq;         // (query_start, t') of the entries in bucket order: all the gap rule reads of a candidate
+    u32 *bk;           // their positions k
+    u32 *dir;          // dir[hg * dirD + b] .. dir[hg * dirD + b + 1]: the entries of bucket b of the group
+    u32 dirD;          // directory entries per group (buckets + 1)
+    int bshift;        // bucket of a target coordinate x: x >> bshift
 };
 
 // smallest d over the pickers of j that precede position i, compared with d: true iff d < B(i,j)
@@ -234,7 +241,130 @@ __device__ __forceinline__ u32 fx_filter_seen(const uint4 *__restrict__ rec, con
     return out;
 }
 
+// The search of k_fx_recompute over the target-bucket order.  The query-axis window of a position in a centromeric pile holds
+// 10^5 candidates of which the target-gap rule admits a few dozen (configs[4]: the scattered half of the pile); in bucket order
+// the candidates whose target coordinate can satisfy the rule (paf_filter.rs:812-833: target_start within [te - G/5, te + G] on
+// the '+' strand, target_end within [ts - G, ts + G/5] on '-') are the entries of at most two buckets, and inside a bucket the
+// entries are in position order, i.e. by query_start: the same pruned outward scans as bb_best_successor_warp run there, from
+// the first entry whose query_start reaches query_end(i).  The arg-min is over (d, j) explicitly, so the reference's "first
+// minimal j" does not depend on the visiting order, and every candidate ranking before the final pick is visited (pruning drops
+// only candidates with q_gap^2 > best d), which is all the blocked-candidate record needs.
+// COLLECT = false: bd / bj receive the pick.  COLLECT = true: bd / bj are the final pick; the valid candidates ranking before
+// it are appended to xs (X(i)); returns their number.
+template <bool COLLECT, class Extra>
+__device__ __forceinline__ u32 fx_bucket_pass(const FxArrays &f, u32 i, const uint4 &a, bool fwd, u64 G, u64 G5, u64 &bd, u32 &bj, Extra ex,
+                                              u32 *xs) {
+    const u32 full = 0xFFFFFFFFu;
+    const u32 lane = lane_id();
+    constexpr u32 CW = 4; // chunks per round
+    u32 xn = 0;
+    if (!COLLECT) { bd = NONE64; bj = NONE32; }
+    // the candidate's target coordinate t' (start on '+', end on '-') against c: r_gap = |t' - c|, admitted down to c - below, up to c + above
+    const u64 c = fwd ? a.w : a.z;
+    const u64 below = fwd ? G5 : G, above = fwd ? G : G5;
+    const u64 W = 1ull << f.bshift;
+    const long long blo = (long long)((c > below ? c - below : 0) >> f.bshift), bhi = (long long)min((c + above) >> f.bshift, (u64)f.dirD - 2);
+    const long long bc = (long long)(c >> f.bshift);
+    const u32 *dir = f.dir + (size_t)f.hg[i] * f.dirD;
+    // buckets outwards from the one that holds c: a bucket whose nearest edge is further than sqrt(best d) holds no better candidate
+    bool live[2] = {true, true}; // upwards / downwards: buckets still worth a visit
+    for (long long step = 0; live[0] || live[1]; step++) {
+        for (int side = 0; side < 2; side++) {
+            if ((side && step == 0) || !live[side]) continue;
+            const long long b = side ? bc - step : bc + step;
+            if (b < blo || b > bhi) { live[side] = false; continue; }
+            const u64 rmin = step == 0 ? 0 : (side ? c - ((u64)(b + 1) * W - 1) : (u64)b * W - c);
+            if (rmin * rmin > bd) { live[side] = false; continue; } // and every bucket beyond it
+            const u32 lo0 = dir[b], hi0 = dir[b + 1];
+            if (lo0 == hi0) continue;
+            // first entry of the bucket whose query_start reaches query_end(i): 33-ary search, 32 probes in flight per round
+            u32 lo = lo0, hi = hi0;
+            while (hi - lo > 32) {
+                const u32 width = hi - lo;
+                const u32 p = lo + (u32)(((u64)(lane + 1) * width) / 33);
+                const u32 nb = __popc(__ballot_sync(full, f.bq[p].x < a.y));
+                const u32 nlo = nb ? lo + (u32)(((u64)nb * width) / 33) + 1 : lo;
+                const u32 nhi = nb < 32 ? lo + (u32)(((u64)(nb + 1) * width) / 33) : hi;
+                lo = nlo;
+                hi = nhi;
+            }
+            if (hi > lo) {
+                const u32 p = lo + lane;
+                lo += __popc(__ballot_sync(full, p < hi && f.bq[p].x < a.y));
+            }
+            const u32 org = lo;
+            for (u32 base = org; base < hi0; base += 32 * CW) { // right of the origin: q_gap = qs - qe >= 0 grows
+                uint2 rb[CW];
+                u32 rj[CW];
+#pragma unroll
+                for (u32 k = 0; k < CW; k++) {
+                    const u32 m = base + k * 32 + lane;
+                    rb[k] = make_uint2(0, 0);
+                    rj[k] = NONE32;
+                    if (m < hi0) { rb[k] = f.bq[m]; rj[k] = f.bk[m]; }
+                }
+                u64 ld = bd;
+                u32 lj = bj;
+                bool mono = false;
+#pragma unroll
+                for (u32 k = 0; k < CW; k++) {
+                    mono = false;
+                    if (rj[k] != NONE32) {
+                        const u64 qg = (u64)rb[k].x - a.y;
+                        mono = qg <= G && qg * qg <= bd;
+                    }
+                    const bool in = mono && rj[k] > i; // (a zero-length record meets earlier positions with the same start here)
+                    const uint4 rec = make_uint4(rb[k].x, 0, rb[k].y, rb[k].y); // the gap rule reads query_start and t' only
+                    if (COLLECT) xn = fx_collect_chunk(a, fwd, G, G5, bd, bj, rj[k], in, rec, xs, xn);
+                    else {
+                        u64 d;
+                        if (in && bb_candidate(a, rec, fwd, G, G5, d) && (d < ld || (d == ld && rj[k] < lj)) &&
+                            (d < f.minpd[rj[k]] || ex(rj[k], d, f.minpi[rj[k]]))) { ld = d; lj = rj[k]; }
+                    }
+                }
+                if (!COLLECT) { bb_argmin(ld, lj); bd = ld; bj = lj; }
+                if (!__shfl_sync(full, (int)mono, 31)) break; // monotone: once the last candidate is out, so is everything further right
+            }
+            for (u32 top = org; top > lo0;) { // left of the origin: overlap = qe - qs > 0 grows going left, positions descend
+                const u32 cnt = min(32u * CW, top - lo0);
+                uint2 rb[CW];
+                u32 rj[CW];
+#pragma unroll
+                for (u32 k = 0; k < CW; k++) {
+                    const u32 off = k * 32 + lane;
+                    rb[k] = make_uint2(0, 0);
+                    rj[k] = NONE32;
+                    if (off < cnt) { rb[k] = f.bq[top - 1 - off]; rj[k] = f.bk[top - 1 - off]; }
+                }
+                u64 ld = bd;
+                u32 lj = bj;
+                bool in = false;
+#pragma unroll
+                for (u32 k = 0; k < CW; k++) {
+                    in = false;
+                    if (rj[k] != NONE32) {
+                        const u64 ov = (u64)a.y - rb[k].x;
+                        in = ov <= G5 && ov * ov <= bd && rj[k] > i;
+                    }
+                    const uint4 rec = make_uint4(rb[k].x, 0, rb[k].y, rb[k].y);
+                    if (COLLECT) xn = fx_collect_chunk(a, fwd, G, G5, bd, bj, rj[k], in, rec, xs, xn);
+                    else {
+                        u64 d;
+                        if (in && bb_candidate(a, rec, fwd, G, G5, d) && (d < ld || (d == ld && rj[k] < lj)) &&
+                            (d < f.minpd[rj[k]] || ex(rj[k], d, f.minpi[rj[k]]))) { ld = d; lj = rj[k]; }
+                    }
+                }
+                if (!COLLECT) { bb_argmin(ld, lj); bd = ld; bj = lj; }
+                if (cnt < 32 * CW || !__shfl_sync(full, (int)in, 31)) break;
+                top -= 32 * CW;
+            }
+        }
+    }
+    return xn;
+}
+
 // step 3: one warp per listed position
+template <bool BUCKET>
 __global__ void __launch_bounds__(128) k_fx_recompute(FxArrays f, u64 G) {
     __shared__ u32 s_x[4][FX_XCAP];
     __shared__ u32 s_seen[4];
@@ -253,19 +383,21 @@ __global__ void __launch_bounds__(128) k_fx_recompute(FxArrays f, u64 G) {
         const u32 ge = f.gend[i];
         const u32 e = ge & ~FX_REV;
         const bool fwd = !(ge & FX_REV);
-        const u32 c0 = f.c0[i];
+        const u32 c0 = BUCKET ? NONE32 : f.c0[i];
         u64 bd;
         u32 bj;
         u32 *n_seen = &s_seen[threadIdx.x >> 5];
         if (lane == 0) *n_seen = 0;
         __syncwarp();
         FxExtra ex{f.minpi, f, i, xs, n_seen};
-        bb_best_successor_warp(f.rec, f.minpd, i, e, a, fwd, G, G5, bd, bj, c0, ex);
+        if (BUCKET) fx_bucket_pass<false>(f, i, a, fwd, G, G5, bd, bj, ex, nullptr);
+        else bb_best_successor_warp(f.rec, f.minpd, i, e, a, fwd, G, G5, bd, bj, c0, ex);
         __syncwarp();
         // X(i): normally out of the search's own record of blocked candidates; a separate pruned pass if that overflowed
         const u32 seen = *n_seen;
         const u32 xn = seen <= FX_XCAP ? fx_filter_seen(f.rec, a, fwd, G, G5, bd, bj, xs, seen)
-                                       : fx_collect_blocked(f.rec, i, e, a, fwd, G, G5, bd, bj, c0, xs);
+                       : BUCKET    ? fx_bucket_pass<true>(f, i, a, fwd, G, G5, bd, bj, ex, xs)
+                                   : fx_collect_blocked(f.rec, i, e, a, fwd, G, G5, bd, bj, c0, xs);
         __syncwarp();
         u32 xo = 0;
         u16 xc = FX_XOVER;
@@ -306,8 +438,11 @@ __global__ void __launch_bounds__(128) k_fx_recompute(FxArrays f, u64 G) {
 // sorted-position space; cand = k_chain_candidates' result there.  Writes root[] for the positions of huge groups and
 // returns true; returns false (root[] untouched) if the picks have not settled after SWG_FIXPOINT_MAX_ROUNDS rounds (default
 // 256): a dependency chain that long is walked faster sequentially, and the caller hands the groups to k_chain_resolve_warp.
+// cand == nullptr selects the target-bucket order: the first round evaluates every position against an empty snapshot (that IS
+// the unconstrained arg-min of the candidate pass), all searches go through fx_bucket_pass.  maxcoord bounds every coordinate.
 static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *srec, const u64 *skey, int cb, const u32 *gid, const u32 *gstart,
-                           u32 n_groups, u32 n_m, const Cand *cand, u64 G, u32 *root, u32 *bsum) {
+                           u32 n_groups, u32 n_m, const Cand *cand, u64 G, u32 *root, u32 *bsum, u32 maxcoord) {
+    const bool bucket = cand == nullptr;
     cudaStream_t st = c->stream;
     LaunchCounter &lc = c->lc;
     Arena &A = c->arena;
@@ -316,7 +451,7 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
     f.n = n_h;
     f.rec = A.take<uint4>(n_h);
     f.gend = A.take<u32>(n_h);
-    f.c0 = A.take<u32>(n_h);
+    f.c0 = bucket ? nullptr : A.take<u32>(n_h);
     f.pick = A.take<u32>(n_h);
     f.pd = A.take<u64>(n_h);
     f.cnt = A.take<u32>(n_h);
@@ -359,6 +494,7 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
             const bool fwd = ((skey[p] >> cb) & 1) == 0;
             g.rec[k] = srec[p];
             g.gend[k] = (k + (e - p)) | (fwd ? 0u : FX_REV);
+            if (bucket) { g.pick[k] = NONE32; g.xhi[k] = k; g.pd[k] = NONE64; return; }
             const Cand cd = cand[p];
             g.pick[k] = cd.j == NONE32 ? NONE32 : k + (cd.j - p);
             g.xhi[k] = cd.j == NONE32 ? k : k + (cd.j - p);
@@ -367,10 +503,94 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
         });
     }
     u32 *h = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
+    f.hg = nullptr; f.bq = nullptr; f.bk = nullptr; f.dir = nullptr; f.dirD = 0; f.bshift = 0;
+    if (bucket) {
+        // dense numbers of the huge groups (a group starts where the previous position's group ends)
+        f.hg = A.take<u32>(n_h);
+        {
+            const FxArrays g = f;
+            scan_apply([=] __device__(u32 k) -> u32 { return (k == 0 || (g.gend[k - 1] & ~FX_REV) == k) ? 1u : 0u; },
+                       [=] __device__(u32 k, u32 ex, u32 v) { g.hg[k] = ex + v - 1; }, n_h, bsum, scan_tot, st, lc);
+        }
+        SWG_CUDA(cudaMemcpyAsync(h, scan_tot, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        SWG_CUDA(cudaStreamSynchronize(st));
+        const u32 n_hg = h[0];
+        // bucket width: an eighth of the smallest power of two >= G + G/5 + 1 (SWG_FX_BUCKET_NARROW=<log2 of the divisor>: tuning aid).
+        // A search visits the buckets outwards from the one that holds its own target coordinate and stops at the first whose
+        // nearest edge is further than sqrt(best d): narrow buckets keep the scans of the dense diagonal short, wide ones spare
+        // the scattered positions origin searches.  Wider if the directory (one entry per group and bucket) would pass 2^25
+        // entries or 2^20 per group.
+        const int narrow = getenv("SWG_FX_BUCKET_NARROW") ? atoi(getenv("SWG_FX_BUCKET_NARROW")) : 3;
+        int bs = std::max(bits_for(G + G / 5) - narrow, 4);
+        while ((((u64)(maxcoord >> bs) + 2) * n_hg > (1ull << 25) || ((u64)maxcoord >> bs) + 2 > (1ull << 20)) && bs < 32) bs++;
+        f.bshift = bs;
+        const u32 nbk = (u32)(((u64)maxcoord >> bs) + 1);
+        f.dirD = nbk + 1;
+        const int tb = bits_for(nbk - 1 ? nbk - 1 : 1);
+        const size_t n_dir = (size_t)n_hg * f.dirD + 1;
+        u64 *bkey = A.take<u64>(n_h), *bkey2 = A.take<u64>(n_h);
+        u32 *bv = A.take<u32>(n_h), *bv2 = A.take<u32>(n_h);
+        {
+            const FxArrays g = f;
+            launch_for<t_fx_bkey>(n_h, st, lc, [=] __device__(u32 k) {
+                const uint4 r = g.rec[k];
+                const u32 t = (g.gend[k] & FX_REV) ? r.w : r.z; // '-' strand: the rule tests the candidate's target_end
+                bkey[k] = ((u64)g.hg[k] << tb) | (t >> bs);
+                bv[k] = k;
+            });
+        }
+        sort_pairs(c, bkey, bkey2, bv, bv2, n_h, tb + bits_for(n_hg > 1 ? n_hg - 1 : 1)); // stable: positions ascend inside a bucket
+        f.bk = bv;
+        f.bq = A.take<uint2>(n_h);
+        f.dir = A.take<u32>(n_dir);
+        {
+            const FxArrays g = f;
+            const u64 *ks = bkey;
+            const u32 D = f.dirD;
+            launch_for<t_fx_brec>(n_h, st, lc, [=] __device__(u32 m) {
+                {
+                    const u32 k = g.bk[m];
+                    const uint4 r = g.rec[k];
+                    g.bq[m] = make_uint2(r.x, (g.gend[k] & FX_REV) ? r.w : r.z);
+                }
+                // directory: dir[x] = first entry whose (group, bucket) slot is >= x
+                const u64 km = ks[m];
+                const u64 slot = (km >> tb) * D + (km & ((1ull << tb) - 1));
+                u64 from = 0;
+                if (m > 0) { const u64 kp = ks[m - 1]; from = (kp >> tb) * D + (kp & ((1ull << tb) - 1)) + 1; }
+                for (u64 x = from; x <= slot; x++) g.dir[x] = m;
+                if (m + 1 == g.n)
+                    for (u64 x = slot + 1; x < n_dir; x++) g.dir[x] = g.n;
+            });
+        }
+        if (verbose) fprintf(stderr, "[swg fixpoint] target buckets: %u huge groups, 2^%d wide, %u per group\n", n_hg, bs, nbk);
+    }
     int rounds = 0;
     const int max_rounds = getenv("SWG_FIXPOINT_MAX_ROUNDS") ? atoi(getenv("SWG_FIXPOINT_MAX_ROUNDS")) : 256;
     u64 total_recomputed = 0;
     auto t_round = std::chrono::steady_clock::now();
+    if (bucket) {
+        // round 0: every position against the empty snapshot = the unconstrained arg-min (nothing is blocked: X(i) stays empty)
+        const FxArrays g = f;
+        SWG_CUDA(cudaMemsetAsync(f.minpd, 0xFF, sizeof(u64) * (size_t)n_h, st));
+        SWG_CUDA(cudaMemsetAsync(f.minpi, 0xFF, sizeof(u32) * (size_t)n_h, st));
+        SWG_CUDA(cudaMemsetAsync(f.firstp, 0xFF, sizeof(u32) * (size_t)n_h, st));
+        SWG_CUDA(cudaMemsetAsync(f.off, 0, sizeof(u32) * ((size_t)n_h + 1), st));
+        SWG_CUDA(cudaMemsetAsync(f.dirty, 0, sizeof(u32) * (size_t)n_blk, st));
+        SWG_CUDA(cudaMemsetAsync(f.ctrs, 0, 4 * sizeof(u32), st));
+        launch_for<t_fx_all>(n_h, st, lc, [=] __device__(u32 k) {
+            g.list[k] = k;
+            if (k == 0) g.ctrs[0] = g.n;
+        });
+        k_fx_recompute<true><<<(u32)c->sm_count * 8, 128, 0, st>>>(f, G);
+        lc.n++;
+        if (verbose) {
+            SWG_CUDA(cudaStreamSynchronize(st));
+            const auto t1 = std::chrono::steady_clock::now();
+            fprintf(stderr, "[swg fixpoint] round 0 (unconstrained picks, bucket order): %.2f ms\n", std::chrono::duration<double, std::milli>(t1 - t_round).count());
+            t_round = t1;
+        }
+    }
     while (true) {
         // 0. which blocks of successors saw a picker list change in the last round (prefix counts for k_fx_check)
         if (dirty_on && rounds > 0) {
@@ -418,8 +638,18 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
             }
         });
         // 2. + 3.
+        double ms_snap = 0, ms_check = 0;
+        auto lap = [&](double &ms) { // diagnostics only (SWG_STAGE_TIMING): where a round spends its time
+            if (!verbose) return;
+            SWG_CUDA(cudaStreamSynchronize(st));
+            const auto t1 = std::chrono::steady_clock::now();
+            ms = std::chrono::duration<double, std::milli>(t1 - t_round).count();
+        };
+        lap(ms_snap);
         k_fx_check<<<cdiv(n_h, 256), 256, 0, st>>>(f, G);
-        k_fx_recompute<<<(u32)c->sm_count * 8, 128, 0, st>>>(f, G);
+        lap(ms_check);
+        if (bucket) k_fx_recompute<true><<<(u32)c->sm_count * 8, 128, 0, st>>>(f, G);
+        else k_fx_recompute<false><<<(u32)c->sm_count * 8, 128, 0, st>>>(f, G);
         lc.n += 2;
         SWG_CUDA(cudaMemcpyAsync(h, f.ctrs, 4 * sizeof(u32), cudaMemcpyDeviceToHost, st));
         if (verbose) SWG_CUDA(cudaMemcpyAsync(h + 4, f.pool_top, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -428,8 +658,8 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
         total_recomputed += h[0];
         if (verbose) {
             const auto t1 = std::chrono::steady_clock::now();
-            fprintf(stderr, "[swg fixpoint] round %d: %u of %u positions re-evaluated, %u picks changed, %.2f ms, pool %llu of %u (%u refused)\n", rounds,
-                    h[0], n_h, h[1], std::chrono::duration<double, std::milli>(t1 - t_round).count(),
+            fprintf(stderr, "[swg fixpoint] round %d: %u of %u positions re-evaluated, %u picks changed, %.2f ms (snapshot %.2f, check %.2f), pool %llu of %u (%u refused)\n", rounds,
+                    h[0], n_h, h[1], std::chrono::duration<double, std::milli>(t1 - t_round).count(), ms_snap, ms_check - ms_snap,
                     (unsigned long long)(h[4] | ((u64)h[5] << 32)), f.pool_cap, h[3]);
             t_round = t1;
         }
@@ -448,7 +678,8 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
             g.list[k] = k;
             if (k == 0) g.ctrs[0] = g.n;
         });
-        k_fx_recompute<<<(u32)c->sm_count * 8, 128, 0, st>>>(f, G);
+        if (bucket) k_fx_recompute<true><<<(u32)c->sm_count * 8, 128, 0, st>>>(f, G);
+        else k_fx_recompute<false><<<(u32)c->sm_count * 8, 128, 0, st>>>(f, G);
         lc.n++;
         SWG_CUDA(cudaMemcpyAsync(h, f.ctrs, 4 * sizeof(u32), cudaMemcpyDeviceToHost, st));
         SWG_CUDA(cudaStreamSynchronize(st));

@@ -118,7 +118,7 @@ struct Arena {
 namespace swg {
 // Environment knobs (diagnostics and tests).  Read once per entry point, never cached across calls.
 struct Knobs {
-    bool force_wide = false, sweep_no_flat = false, no_fixpoint = false, inv_grid = false, inv_no_grid = false, cuda_log = false;
+    bool force_wide = false, sweep_no_flat = false, no_fixpoint = false, fx_no_buckets = false, inv_grid = false, inv_no_grid = false, cuda_log = false;
     bool pairs_sort = false;   // SWG_SORT_PAIRS=1: the record sort keeps (key, payload) pairs through every pass
     bool no_fused_keys = false; // SWG_NO_FUSED_KEYS=1: the chain sort keys always come from k_chain_keys
     bool no_group_sort = false; // SWG_NO_GROUP_SORT=1: the record sort always runs the LSD passes (radix_sort.cuh)
@@ -136,6 +136,7 @@ static Knobs read_knobs() {
     k.force_wide = on("SWG_FORCE_WIDE_KEYS");
     k.sweep_no_flat = on("SWG_SWEEP_NO_FLAT");
     k.no_fixpoint = on("SWG_NO_FIXPOINT");
+    k.fx_no_buckets = on("SWG_FX_NO_BUCKETS");
     k.inv_grid = on("SWG_INV_GRID");
     k.inv_no_grid = on("SWG_INV_NO_GRID");
     k.pairs_sort = on("SWG_SORT_PAIRS");
@@ -986,12 +987,19 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             SWG_CUDA(cudaMemsetAsync(root_preset, 0xFF, sizeof(u32) * (size_t)n_m, st));
             scan_flags([=] __device__(u32 p) -> u32 { return is_huge(gid[p]) ? 1u : 0u; },
                        [=] __device__(u32 p, u32 ex, u32 v) { if (v) hpos[ex] = p; }, n_m, bsum, d_tot + 3, st, lc);
-            k_chain_candidates<true><<<(u32)c->sm_count * 16, 256, 0, st>>>(srec, skey, gid, gstart, n_groups, n_m, gshift, cfg.scaffold_gap, cand, nullptr,
-                                                                             nullptr, hpos, d_tot + 3); // their candidate records (position-parallel)
-            lc.n++;
-            if (!chain_fixpoint(c, n_huge, hpos, srec, skey, gshift, gid, gstart, n_groups, n_m, cand, cfg.scaffold_gap, root_preset, bsum)) {
+            // searches in target-bucket order (default; SWG_FX_NO_BUCKETS=1: along the query axis, from the candidate records)
+            const bool fx_buckets = !K.fx_no_buckets;
+            auto huge_candidates = [&] {
+                k_chain_candidates<true><<<(u32)c->sm_count * 16, 256, 0, st>>>(srec, skey, gid, gstart, n_groups, n_m, gshift, cfg.scaffold_gap, cand, nullptr,
+                                                                                 nullptr, hpos, d_tot + 3); // their candidate records (position-parallel)
+                lc.n++;
+            };
+            if (!fx_buckets) huge_candidates();
+            if (!chain_fixpoint(c, n_huge, hpos, srec, skey, gshift, gid, gstart, n_groups, n_m, fx_buckets ? nullptr : cand, cfg.scaffold_gap, root_preset,
+                                bsum, maxcoord)) {
                 // a dependency chain longer than the round limit: the huge groups go through the sequential warp walk after all
                 // (it resets the groups' pred / best_pred_score itself; root_preset is untouched)
+                if (fx_buckets) huge_candidates(); // the walk starts from the candidate records
                 SWG_CUDA(cudaMemsetAsync(bb_ctr + 2, 0, 2 * sizeof(u32), st));
                 scan_flags([=] __device__(u32 g) -> u32 { return is_huge(g) ? 1u : 0u; },
                            [=] __device__(u32 g, u32 ex, u32 v) { if (v) work_big[ex] = g; }, n_groups, bsum, bb_ctr + 2, st, lc);
