@@ -38,7 +38,7 @@
 
 namespace swg {
 
-struct t_fx_init; struct t_fx_hg; struct t_fx_bkey; struct t_fx_brec; struct t_fx_dir; struct t_fx_count; struct t_fx_minpi; struct t_fx_all; struct t_fx_fill; struct t_fx_pred; struct t_fx_jump; struct t_fx_scatter;
+struct t_fx_init; struct t_fx_snap; struct t_fx_hg; struct t_fx_bkey; struct t_fx_brec; struct t_fx_dir; struct t_fx_count; struct t_fx_minpi; struct t_fx_all; struct t_fx_fill; struct t_fx_pred; struct t_fx_jump; struct t_fx_scatter;
 
 constexpr u32 FX_XCAP = 1024;     // blocked candidates remembered per position; a position with more is re-evaluated every round
 constexpr u16 FX_XOVER = 0xFFFF; // xcnt value of such a position
@@ -61,6 +61,7 @@ struct FxArrays {
     u32 *xoff;         // X(i) lives at pool[xoff .. xoff + xcnt)
     u16 *xcnt, *xcap;
     u32 *pool;
+    u64 *pool_d;       // bucket order only: d(i, x) of every pool entry (k_fx_check then needs no record gather)
     unsigned long long *pool_top; // 64-bit: refused requests keep counting and must never wrap into live slots
     u32 pool_cap;
     u32 *list;         // positions to re-evaluate this round
@@ -70,6 +71,7 @@ struct FxArrays {
     u32 *ctrs;         // [0] list length, [1] picks changed this round, [2] recompute work counter, [3] slots refused (pool full)
     // target-bucket order (fx_bucket_pass): the positions of every huge group once more, ordered by (group, target bucket, k)
     u32 *hg;           // dense number of the position's huge group
+    uint4 *snap;       // (minpd lo, minpd hi, minpi, firstp) of every successor in one 16 B word: one gather per candidate
     uint2 *bq;         // (query_start, t') of the entries in bucket order: all the gap rule reads of a candidate
     u32 *bk;           // their positions k
     u32 *dir;          // dir[hg * dirD + b] .. dir[hg * dirD + b + 1]: the entries of bucket b of the group
@@ -95,6 +97,23 @@ struct FxExtra {
     FxArrays f;
     u32 i;
     u32 *seen, *n_seen; // shared memory of the warp: the blocked candidates met by the search (a superset of X(i))
+    // the same verdict from the packed snapshot word of j (mi = minpi[j], fp = firstp[j]); callers have established d >= minpd[j]
+    __device__ __forceinline__ bool packed(u32 j, u64 d, u32 mi, u32 fp) const {
+        bool el;
+        if (mi < i) el = false;
+        else if (mi == i || fp >= i) el = true;
+        else {
+            el = true;
+            const u32 a = f.off[j], b = f.off[j + 1];
+            for (u32 p = a; p < b; p++)
+                if (f.li[p] < i && f.ld[p] <= d) { el = false; break; }
+        }
+        if (!el) {
+            const u32 o = atomicAdd(n_seen, 1u);
+            if (o < FX_XCAP) seen[o] = j;
+        }
+        return el;
+    }
     __device__ __forceinline__ bool operator()(u32 j, u64 d, u32 mi) const {
         const bool el = fx_eligible(f, i, j, d, mi);
         if (!el) { // it beat the lane's best so far and is blocked: the only kind of candidate that can belong to X(i)
@@ -124,6 +143,19 @@ __global__ void __launch_bounds__(256) k_fx_check(FxArrays f, u64 G) {
                 const uint4 a = f.rec[k];
                 const bool fwd = !(f.gend[k] & FX_REV);
                 const u32 *x = f.pool + f.xoff[k];
+                if (f.pool_d) { // d stored with the entry, the successor's snapshot in one word
+                    const u64 *xd = f.pool_d + f.xoff[k];
+                    for (u32 q = 0; q < xc && !need; q++) {
+                        const u32 jx = x[q];
+                        const u64 d = xd[q];
+                        const uint4 sn = f.snap[jx];
+                        const u64 mp = ((u64)sn.y << 32) | sn.x;
+                        if (d < mp) need = true;
+                        else if (sn.z < k) need = false;
+                        else if (sn.z == k || sn.w >= k) need = true;
+                        else need = fx_eligible(f, k, jx, d, sn.z);
+                    }
+                } else
                 for (u32 q = 0; q < xc && !need; q++) {
                     const u32 jx = x[q];
                     u64 d;
@@ -241,6 +273,42 @@ __device__ __forceinline__ u32 fx_filter_seen(const uint4 *__restrict__ rec, con
     return out;
 }
 
+// One round of a bucket scan: the gap rule for every candidate of the round first (registers only), then the snapshot words of
+// those that beat the best so far — independent gathers, one memory round trip — then the verdicts in order.  (Loading the
+// words lazily, candidate by candidate, made a blocked candidate cost two dependent round trips; a position deep in a conflict
+// meets dozens of them before its first eligible one.)
+template <u32 CW, class Extra>
+__device__ __forceinline__ void fx_eval_round(const FxArrays &f, const uint4 &a, bool fwd, u64 G, u64 G5, const uint2 (&rb)[CW], const u32 (&rj)[CW],
+                                              const bool (&in)[CW], u64 &bd, u32 &bj, const Extra &ex) {
+    u64 dd[CW];
+    bool want[CW];
+    uint4 sn[CW];
+#pragma unroll
+    for (u32 k = 0; k < CW; k++) {
+        want[k] = false;
+        dd[k] = 0;
+        if (in[k]) {
+            const uint4 rec = make_uint4(rb[k].x, 0, rb[k].y, rb[k].y); // the gap rule reads query_start and t' only
+            u64 d;
+            if (bb_candidate(a, rec, fwd, G, G5, d) && (d < bd || (d == bd && rj[k] < bj))) { want[k] = true; dd[k] = d; }
+        }
+    }
+#pragma unroll
+    for (u32 k = 0; k < CW; k++)
+        if (want[k]) sn[k] = f.snap[rj[k]];
+    u64 ld = bd;
+    u32 lj = bj;
+#pragma unroll
+    for (u32 k = 0; k < CW; k++)
+        if (want[k] && (dd[k] < ld || (dd[k] == ld && rj[k] < lj))) {
+            const u64 mp = ((u64)sn[k].y << 32) | sn[k].x;
+            if (dd[k] < mp || ex.packed(rj[k], dd[k], sn[k].z, sn[k].w)) { ld = dd[k]; lj = rj[k]; }
+        }
+    bb_argmin(ld, lj);
+    bd = ld;
+    bj = lj;
+}
+
 // The search of k_fx_recompute over the target-bucket order.  The query-axis window of a position in a centromeric pile holds
 // 10^5 candidates of which the target-gap rule admits a few dozen (configs[4]: the scattered half of the pile); in bucket order
 // the candidates whose target coordinate can satisfy the rule (paf_filter.rs:812-833: target_start within [te - G/5, te + G] on
@@ -267,14 +335,14 @@ __device__ __forceinline__ u32 fx_bucket_pass(const FxArrays &f, u32 i, const ui
     const long long bc = (long long)(c >> f.bshift);
     const u32 *dir = f.dir + (size_t)f.hg[i] * f.dirD;
     // buckets outwards from the one that holds c: a bucket whose nearest edge is further than sqrt(best d) holds no better candidate
-    bool live[2] = {true, true}; // upwards / downwards: buckets still worth a visit
-    for (long long step = 0; live[0] || live[1]; step++) {
+    bool live_up = true, live_dn = true; // buckets still worth a visit in either direction
+    for (long long step = 0; live_up || live_dn; step++) {
         for (int side = 0; side < 2; side++) {
-            if ((side && step == 0) || !live[side]) continue;
+            if ((side && step == 0) || !(side ? live_dn : live_up)) continue;
             const long long b = side ? bc - step : bc + step;
-            if (b < blo || b > bhi) { live[side] = false; continue; }
+            if (b < blo || b > bhi) { (side ? live_dn : live_up) = false; continue; }
             const u64 rmin = step == 0 ? 0 : (side ? c - ((u64)(b + 1) * W - 1) : (u64)b * W - c);
-            if (rmin * rmin > bd) { live[side] = false; continue; } // and every bucket beyond it
+            if (rmin * rmin > bd) { (side ? live_dn : live_up) = false; continue; } // and every bucket beyond it
             const u32 lo0 = dir[b], hi0 = dir[b + 1];
             if (lo0 == hi0) continue;
             // first entry of the bucket whose query_start reaches query_end(i): 33-ary search, 32 probes in flight per round
@@ -303,9 +371,8 @@ __device__ __forceinline__ u32 fx_bucket_pass(const FxArrays &f, u32 i, const ui
                     rj[k] = NONE32;
                     if (m < hi0) { rb[k] = f.bq[m]; rj[k] = f.bk[m]; }
                 }
-                u64 ld = bd;
-                u32 lj = bj;
                 bool mono = false;
+                bool in[CW];
 #pragma unroll
                 for (u32 k = 0; k < CW; k++) {
                     mono = false;
@@ -313,16 +380,13 @@ __device__ __forceinline__ u32 fx_bucket_pass(const FxArrays &f, u32 i, const ui
                         const u64 qg = (u64)rb[k].x - a.y;
                         mono = qg <= G && qg * qg <= bd;
                     }
-                    const bool in = mono && rj[k] > i; // (a zero-length record meets earlier positions with the same start here)
-                    const uint4 rec = make_uint4(rb[k].x, 0, rb[k].y, rb[k].y); // the gap rule reads query_start and t' only
-                    if (COLLECT) xn = fx_collect_chunk(a, fwd, G, G5, bd, bj, rj[k], in, rec, xs, xn);
-                    else {
-                        u64 d;
-                        if (in && bb_candidate(a, rec, fwd, G, G5, d) && (d < ld || (d == ld && rj[k] < lj)) &&
-                            (d < f.minpd[rj[k]] || ex(rj[k], d, f.minpi[rj[k]]))) { ld = d; lj = rj[k]; }
-                    }
+                    in[k] = mono && rj[k] > i; // (a zero-length record meets earlier positions with the same start here)
                 }
-                if (!COLLECT) { bb_argmin(ld, lj); bd = ld; bj = lj; }
+                if (COLLECT) {
+#pragma unroll
+                    for (u32 k = 0; k < CW; k++)
+                        xn = fx_collect_chunk(a, fwd, G, G5, bd, bj, rj[k], in[k], make_uint4(rb[k].x, 0, rb[k].y, rb[k].y), xs, xn);
+                } else fx_eval_round<CW>(f, a, fwd, G, G5, rb, rj, in, bd, bj, ex);
                 if (!__shfl_sync(full, (int)mono, 31)) break; // monotone: once the last candidate is out, so is everything further right
             }
             for (u32 top = org; top > lo0;) { // left of the origin: overlap = qe - qs > 0 grows going left, positions descend
@@ -336,26 +400,21 @@ __device__ __forceinline__ u32 fx_bucket_pass(const FxArrays &f, u32 i, const ui
                     rj[k] = NONE32;
                     if (off < cnt) { rb[k] = f.bq[top - 1 - off]; rj[k] = f.bk[top - 1 - off]; }
                 }
-                u64 ld = bd;
-                u32 lj = bj;
-                bool in = false;
+                bool in[CW];
 #pragma unroll
                 for (u32 k = 0; k < CW; k++) {
-                    in = false;
+                    in[k] = false;
                     if (rj[k] != NONE32) {
                         const u64 ov = (u64)a.y - rb[k].x;
-                        in = ov <= G5 && ov * ov <= bd && rj[k] > i;
-                    }
-                    const uint4 rec = make_uint4(rb[k].x, 0, rb[k].y, rb[k].y);
-                    if (COLLECT) xn = fx_collect_chunk(a, fwd, G, G5, bd, bj, rj[k], in, rec, xs, xn);
-                    else {
-                        u64 d;
-                        if (in && bb_candidate(a, rec, fwd, G, G5, d) && (d < ld || (d == ld && rj[k] < lj)) &&
-                            (d < f.minpd[rj[k]] || ex(rj[k], d, f.minpi[rj[k]]))) { ld = d; lj = rj[k]; }
+                        in[k] = ov <= G5 && ov * ov <= bd && rj[k] > i;
                     }
                 }
-                if (!COLLECT) { bb_argmin(ld, lj); bd = ld; bj = lj; }
-                if (cnt < 32 * CW || !__shfl_sync(full, (int)in, 31)) break;
+                if (COLLECT) {
+#pragma unroll
+                    for (u32 k = 0; k < CW; k++)
+                        xn = fx_collect_chunk(a, fwd, G, G5, bd, bj, rj[k], in[k], make_uint4(rb[k].x, 0, rb[k].y, rb[k].y), xs, xn);
+                } else fx_eval_round<CW>(f, a, fwd, G, G5, rb, rj, in, bd, bj, ex);
+                if (cnt < 32 * CW || !__shfl_sync(full, (int)in[CW - 1], 31)) break;
                 top -= 32 * CW;
             }
         }
@@ -365,7 +424,7 @@ __device__ __forceinline__ u32 fx_bucket_pass(const FxArrays &f, u32 i, const ui
 
 // step 3: one warp per listed position
 template <bool BUCKET>
-__global__ void __launch_bounds__(128) k_fx_recompute(FxArrays f, u64 G) {
+__global__ void __launch_bounds__(128, BUCKET ? 8 : 3) k_fx_recompute(FxArrays f, u64 G) {
     __shared__ u32 s_x[4][FX_XCAP];
     __shared__ u32 s_seen[4];
     const u32 full = 0xFFFFFFFFu;
@@ -429,7 +488,15 @@ __global__ void __launch_bounds__(128) k_fx_recompute(FxArrays f, u64 G) {
         xo = __shfl_sync(full, xo, 0);
         xc = (u16)__shfl_sync(full, (u32)xc, 0);
         if (xc != FX_XOVER)
-            for (u32 q = lane; q < xn; q += 32) f.pool[xo + q] = xs[q];
+            for (u32 q = lane; q < xn; q += 32) {
+                const u32 jx = xs[q];
+                f.pool[xo + q] = jx;
+                if (BUCKET) {
+                    u64 d = 0;
+                    bb_candidate(a, f.rec[jx], fwd, G, G5, d); // valid by construction (fx_filter_seen / the collect pass)
+                    f.pool_d[xo + q] = d;
+                }
+            }
         __syncwarp();
     }
 }
@@ -468,10 +535,11 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
         // that at 50 M); slots are powers of two and an outgrown slot is abandoned, so be generous where memory allows
         size_t free_b = 0, total_b = 0;
         SWG_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        const u64 want = (u64)n_h * 96 + 4096, fit = free_b / 2 / sizeof(u32);
+        const u64 want = (u64)n_h * 96 + 4096, fit = free_b / 2 / (bucket ? 12 : 4);
         f.pool_cap = (u32)std::min<u64>(std::min<u64>(want, std::max<u64>(fit, (u64)n_h * 8 + 4096)), 0xF0000000ull);
     }
     f.pool = A.take<u32>(f.pool_cap);
+    f.pool_d = bucket ? A.take<u64>(f.pool_cap) : nullptr;
     f.pool_top = A.take<unsigned long long>(1);
     f.list = A.take<u32>(n_h);
     const u32 n_blk = (n_h >> FX_DB) + 1;
@@ -503,10 +571,11 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
         });
     }
     u32 *h = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
-    f.hg = nullptr; f.bq = nullptr; f.bk = nullptr; f.dir = nullptr; f.dirD = 0; f.bshift = 0;
+    f.hg = nullptr; f.snap = nullptr; f.bq = nullptr; f.bk = nullptr; f.dir = nullptr; f.dirD = 0; f.bshift = 0;
     if (bucket) {
         // dense numbers of the huge groups (a group starts where the previous position's group ends)
         f.hg = A.take<u32>(n_h);
+        f.snap = A.take<uint4>(n_h);
         {
             const FxArrays g = f;
             scan_apply([=] __device__(u32 k) -> u32 { return (k == 0 || (g.gend[k - 1] & ~FX_REV) == k) ? 1u : 0u; },
@@ -576,6 +645,7 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
         SWG_CUDA(cudaMemsetAsync(f.minpi, 0xFF, sizeof(u32) * (size_t)n_h, st));
         SWG_CUDA(cudaMemsetAsync(f.firstp, 0xFF, sizeof(u32) * (size_t)n_h, st));
         SWG_CUDA(cudaMemsetAsync(f.off, 0, sizeof(u32) * ((size_t)n_h + 1), st));
+        SWG_CUDA(cudaMemsetAsync(f.snap, 0xFF, sizeof(uint4) * (size_t)n_h, st)); // nobody picks anybody
         SWG_CUDA(cudaMemsetAsync(f.dirty, 0, sizeof(u32) * (size_t)n_blk, st));
         SWG_CUDA(cudaMemsetAsync(f.ctrs, 0, 4 * sizeof(u32), st));
         launch_for<t_fx_all>(n_h, st, lc, [=] __device__(u32 k) {
@@ -623,6 +693,11 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
             const u32 j = g.pick[k];
             if (j != NONE32 && g.pd[k] == g.minpd[j]) atomicMin(&g.minpi[j], k);
         });
+        if (bucket)
+            launch_for<t_fx_snap>(n_h, st, lc, [=] __device__(u32 k) {
+                const u64 mp = g.minpd[k];
+                g.snap[k] = make_uint4((u32)mp, (u32)(mp >> 32), g.minpi[k], g.firstp[k]);
+            });
         scan_apply([=] __device__(u32 k) -> u32 { return g.cnt[k]; },
                    [=] __device__(u32 k, u32 ex, u32 v) {
                        g.off[k] = ex;
