@@ -38,7 +38,7 @@
 
 namespace swg {
 
-struct t_fx_init; struct t_fx_snap; struct t_fx_hg; struct t_fx_bkey; struct t_fx_brec; struct t_fx_dir; struct t_fx_count; struct t_fx_minpi; struct t_fx_all; struct t_fx_fill; struct t_fx_pred; struct t_fx_jump; struct t_fx_scatter;
+struct t_fx_init; struct t_fx_skey; struct t_fx_pm; struct t_fx_snap; struct t_fx_hg; struct t_fx_bkey; struct t_fx_brec; struct t_fx_dir; struct t_fx_count; struct t_fx_minpi; struct t_fx_all; struct t_fx_fill; struct t_fx_pred; struct t_fx_jump; struct t_fx_scatter;
 
 constexpr u32 FX_XCAP = 1024;     // blocked candidates remembered per position; a position with more is re-evaluated every round
 constexpr u16 FX_XOVER = 0xFFFF; // xcnt value of such a position
@@ -57,7 +57,8 @@ struct FxArrays {
     u32 *minpi;        // the first picker of j that has that d
     u32 *firstp;       // the first picker of j at all (NONE32: nobody)
     u32 *li;           // picker position
-    u64 *ld;           // picker d
+    u64 *ld;           // picker d (sorted lists: the smallest d of the list up to and including this entry)
+    u32 sorted;        // 1: every picker list is in position order and ld holds prefix minima (bucket order)
     u32 *xoff;         // X(i) lives at pool[xoff .. xoff + xcnt)
     u16 *xcnt, *xcap;
     u32 *pool;
@@ -68,6 +69,7 @@ struct FxArrays {
     u32 *xhi;          // largest position in {pick(i)} U X(i) (i itself if there is none): how far i's verdict can depend
     u32 *dirty, *dps;  // per block of successors: some picker list in it changed in the last round; prefix counts of that
     u32 use_dirty;     // 0: check every position (first round, or the feature is off)
+    u32 *dbits, *dbits_w; // one bit per successor: its picker list changed in the last round (read by k_fx_check) / in this one
     u32 *ctrs;         // [0] list length, [1] picks changed this round, [2] recompute work counter, [3] slots refused (pool full)
     // target-bucket order (fx_bucket_pass): the positions of every huge group once more, ordered by (group, target bucket, k)
     u32 *hg;           // dense number of the position's huge group
@@ -79,16 +81,29 @@ struct FxArrays {
     int bshift;        // bucket of a target coordinate x: x >> bshift
 };
 
+// is some picker of j before position i with d' <= d?  (the caller knows that the list is not empty)
+__device__ __forceinline__ bool fx_list_blocks(const FxArrays &f, u32 i, u32 j, u64 d) {
+    const u32 a = f.off[j], b = f.off[j + 1];
+    if (f.sorted) { // position order + prefix minima: the last picker before i answers for all of them
+        u32 lo = a, hi = b;
+        while (hi - lo > 4) {
+            const u32 mid = (lo + hi) >> 1;
+            if (f.li[mid] < i) lo = mid + 1; else hi = mid;
+        }
+        while (lo < hi && f.li[lo] < i) lo++;
+        return lo > a && f.ld[lo - 1] <= d;
+    }
+    for (u32 p = a; p < b; p++)
+        if (f.li[p] < i && f.ld[p] <= d) return true;
+    return false;
+}
 // smallest d over the pickers of j that precede position i, compared with d: true iff d < B(i,j)
 // (callers have established d >= minpd[j]: if the picker that holds the minimum precedes i, that settles it)
 __device__ __forceinline__ bool fx_eligible(const FxArrays &f, u32 i, u32 j, u64 d, u32 mi /* = minpi[j] */) {
     if (mi < i) return false;
     if (mi == i) return true; // i itself holds the minimum and is the first to: every earlier picker has a larger d
     if (f.firstp[j] >= i) return true; // nobody picks j before i (ncu: the list walk below was 30 % of the stall samples of round 1)
-    const u32 a = f.off[j], b = f.off[j + 1];
-    for (u32 p = a; p < b; p++)
-        if (f.li[p] < i && f.ld[p] <= d) return false;
-    return true;
+    return !fx_list_blocks(f, i, j, d);
 }
 struct FxExtra {
     static constexpr u32 OUTWARD = 128; // wider rounds measured slower (256: 2.3x on the 8 M pile): most searches end within the first rounds
@@ -102,12 +117,7 @@ struct FxExtra {
         bool el;
         if (mi < i) el = false;
         else if (mi == i || fp >= i) el = true;
-        else {
-            el = true;
-            const u32 a = f.off[j], b = f.off[j + 1];
-            for (u32 p = a; p < b; p++)
-                if (f.li[p] < i && f.ld[p] <= d) { el = false; break; }
-        }
+        else el = !fx_list_blocks(f, i, j, d);
         if (!el) {
             const u32 o = atomicAdd(n_seen, 1u);
             if (o < FX_XCAP) seen[o] = j;
@@ -138,7 +148,9 @@ __global__ void __launch_bounds__(256) k_fx_check(FxArrays f, u64 G) {
         }
         if (xc == FX_XOVER) need = true;
         else if (!untouched) {
-            if (j != NONE32 && f.off[j + 1] - f.off[j] > 1) need = !fx_eligible(f, k, j, f.pd[k], f.minpi[j]);
+            // a successor whose picker list did not change in the last round gives the verdict it gave then: still blocked
+            const bool bits = f.use_dirty && f.dbits;
+            if (j != NONE32 && f.off[j + 1] - f.off[j] > 1 && (!bits || (f.dbits[j >> 5] >> (j & 31) & 1))) need = !fx_eligible(f, k, j, f.pd[k], f.minpi[j]);
             if (!need && xc) {
                 const uint4 a = f.rec[k];
                 const bool fwd = !(f.gend[k] & FX_REV);
@@ -147,6 +159,7 @@ __global__ void __launch_bounds__(256) k_fx_check(FxArrays f, u64 G) {
                     const u64 *xd = f.pool_d + f.xoff[k];
                     for (u32 q = 0; q < xc && !need; q++) {
                         const u32 jx = x[q];
+                        if (bits && !(f.dbits[jx >> 5] >> (jx & 31) & 1)) continue;
                         const u64 d = xd[q];
                         const uint4 sn = f.snap[jx];
                         const u64 mp = ((u64)sn.y << 32) | sn.x;
@@ -470,6 +483,10 @@ __global__ void __launch_bounds__(128, BUCKET ? 8 : 3) k_fx_recompute(FxArrays f
                 atomicAdd(&f.ctrs[1], 1u);
                 if (old != NONE32) f.dirty[old >> FX_DB] = 1; // the picker lists of both successors change
                 if (bj != NONE32) f.dirty[bj >> FX_DB] = 1;
+                if (f.dbits_w) {
+                    if (old != NONE32) atomicOr(&f.dbits_w[old >> 5], 1u << (old & 31));
+                    if (bj != NONE32) atomicOr(&f.dbits_w[bj >> 5], 1u << (bj & 31));
+                }
             }
             f.xhi[i] = hi;
             f.pick[i] = bj;
@@ -526,7 +543,8 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
     f.minpd = A.take<u64>(n_h);
     f.minpi = A.take<u32>(n_h);
     f.firstp = A.take<u32>(n_h);
-    f.li = A.take<u32>(n_h);
+    f.li = bucket ? nullptr : A.take<u32>(n_h); // bucket order: the sorted positions of the round's sort
+    f.sorted = bucket ? 1 : 0;
     f.ld = A.take<u64>(n_h);
     f.xoff = A.take<u32>(n_h);
     f.xcnt = A.take<u16>(n_h);
@@ -547,6 +565,9 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
     f.dirty = A.take<u32>(n_blk);
     f.dps = A.take<u32>((size_t)n_blk + 1);
     f.use_dirty = 0;
+    const size_t n_bw = ((size_t)n_h >> 5) + 1;
+    f.dbits = bucket ? A.take<u32>(n_bw) : nullptr;
+    f.dbits_w = bucket ? A.take<u32>(n_bw) : nullptr;
     const bool dirty_on = getenv("SWG_FX_NO_DIRTY") == nullptr; // testing aid: check every position in every round
     f.ctrs = A.take<u32>(4);
     u32 *scan_tot = A.take<u32>(1);
@@ -646,6 +667,7 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
         SWG_CUDA(cudaMemsetAsync(f.firstp, 0xFF, sizeof(u32) * (size_t)n_h, st));
         SWG_CUDA(cudaMemsetAsync(f.off, 0, sizeof(u32) * ((size_t)n_h + 1), st));
         SWG_CUDA(cudaMemsetAsync(f.snap, 0xFF, sizeof(uint4) * (size_t)n_h, st)); // nobody picks anybody
+        SWG_CUDA(cudaMemsetAsync(f.dbits_w, 0, sizeof(u32) * n_bw, st));
         SWG_CUDA(cudaMemsetAsync(f.dirty, 0, sizeof(u32) * (size_t)n_blk, st));
         SWG_CUDA(cudaMemsetAsync(f.ctrs, 0, 4 * sizeof(u32), st));
         launch_for<t_fx_all>(n_h, st, lc, [=] __device__(u32 k) {
@@ -661,7 +683,29 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
             t_round = t1;
         }
     }
+    // bucket order: picker lists in position order (stable sort of the positions by their pick), picker d as prefix minima
+    u64 *sk = nullptr, *sk2 = nullptr;
+    u32 *sv = nullptr, *sv2 = nullptr;
+    void *stmp = nullptr;
+    RadixSortPlan sp;
+    if (bucket) {
+        sk = A.take<u64>(n_h); sk2 = A.take<u64>(n_h); sv = A.take<u32>(n_h); sv2 = A.take<u32>(n_h);
+        sp = rs_plan(n_h, 0, bits_for(n_h));
+        stmp = A.take<char>(sp.temp_bytes);
+    }
     while (true) {
+        if (bucket) {
+            const FxArrays gs = f;
+            u64 *kk = sk;
+            u32 *vv = sv;
+            launch_for<t_fx_skey>(n_h, st, lc, [=] __device__(u32 k) {
+                const u32 j = gs.pick[k];
+                kk[k] = j == NONE32 ? gs.n : j; // positions without a pick sort behind every list
+                vv[k] = k;
+            });
+            rs_sort_pairs(sp, sk, sk2, sv, sv2, stmp, st, c->sm_count, lc);
+            f.li = sv;
+        }
         // 0. which blocks of successors saw a picker list change in the last round (prefix counts for k_fx_check)
         if (dirty_on && rounds > 0) {
             const FxArrays gd = f;
@@ -674,6 +718,10 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
             f.use_dirty = 1;
         }
         SWG_CUDA(cudaMemsetAsync(f.dirty, 0, sizeof(u32) * (size_t)n_blk, st));
+        if (f.dbits) { // what the last round's re-evaluations marked is read by this round's check
+            std::swap(f.dbits, f.dbits_w);
+            SWG_CUDA(cudaMemsetAsync(f.dbits_w, 0, sizeof(u32) * n_bw, st));
+        }
         // 1. snapshot of the picks
         const FxArrays g = f;
         SWG_CUDA(cudaMemsetAsync(f.cnt, 0, sizeof(u32) * (size_t)n_h, st));
@@ -704,6 +752,15 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
                        if (k + 1 == g.n) g.off[g.n] = ex + v;
                    },
                    n_h, bsum, scan_tot, st, lc);
+        if (bucket)
+            launch_for<t_fx_pm>(n_h, st, lc, [=] __device__(u32 j) {
+                u64 m = NONE64;
+                for (u32 p = g.off[j]; p < g.off[j + 1]; p++) {
+                    m = min(m, g.pd[g.li[p]]);
+                    g.ld[p] = m;
+                }
+            });
+        else
         launch_for<t_fx_fill>(n_h, st, lc, [=] __device__(u32 k) {
             const u32 j = g.pick[k];
             if (j != NONE32) {

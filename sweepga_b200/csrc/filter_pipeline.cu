@@ -118,7 +118,7 @@ struct Arena {
 namespace swg {
 // Environment knobs (diagnostics and tests).  Read once per entry point, never cached across calls.
 struct Knobs {
-    bool force_wide = false, sweep_no_flat = false, no_fixpoint = false, fx_no_buckets = false, inv_grid = false, inv_no_grid = false, cuda_log = false;
+    bool force_wide = false, sweep_no_flat = false, no_fixpoint = false, fx_no_buckets = false, inv_grid = false, inv_no_grid = false, inv_no_diag = false, cuda_log = false;
     bool pairs_sort = false;   // SWG_SORT_PAIRS=1: the record sort keeps (key, payload) pairs through every pass
     bool no_fused_keys = false; // SWG_NO_FUSED_KEYS=1: the chain sort keys always come from k_chain_keys
     bool no_group_sort = false; // SWG_NO_GROUP_SORT=1: the record sort always runs the LSD passes (radix_sort.cuh)
@@ -138,6 +138,7 @@ static Knobs read_knobs() {
     k.no_fixpoint = on("SWG_NO_FIXPOINT");
     k.fx_no_buckets = on("SWG_FX_NO_BUCKETS");
     k.inv_grid = on("SWG_INV_GRID");
+    k.inv_no_diag = on("SWG_INV_NO_DIAG");
     k.inv_no_grid = on("SWG_INV_NO_GRID");
     k.pairs_sort = on("SWG_SORT_PAIRS");
     k.no_fused_keys = on("SWG_NO_FUSED_KEYS");
@@ -1281,6 +1282,15 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             stage_mark(c, "inversion_grid");
             const u64 G = cfg.scaffold_gap;
             const u64 maxc = maxcoord;
+            // ... and in buckets of the diagonal (target_start - query_start of a chain against the centre diagonal of a mapping): the
+            // deviation test floor(|dev| / sqrt 2) <= G admits |dev| < (G + 1) * sqrt 2 only, so a mapping meets the chains of at most two
+            // diagonal buckets of width >= 2 R + 1 — in a repeat pile one bucket of the query axis alone holds 10^5 chains of which the
+            // scattered mappings pass a few hundred before their first hit.  No diagonal buckets when the key would not fit 64 bits.
+            const u64 R = (u64)std::ceil((double)(G + 1) * 1.4142135623730951) + 1; // |dev| > R  =>  perp > G
+            const int wd = bits_for(2 * R + 1);
+            const u64 doff = maxc + 1; // diagonals are shifted to be non-negative: they lie in [-maxc, maxc]
+            int db = bits_for((2 * maxc + 2) >> wd);
+            if (2 * sb + bb + db > 64 || K.inv_no_diag) db = 0;
             // entries: every kept '+' chain once per bucket its extended query interval [qs - G, qe + G] touches
             u32 *e_off = A.take<u32>(C2);
             u32 *d_cnt = A.take<u32>(2); // [0] entries, [1] candidate mappings
@@ -1302,9 +1312,10 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                     if (ik[u] == NONE64) return;
                     const u32 b0 = first_b(u), b1 = last_b(u);
                     u32 o = e_off[u];
-                    for (u32 b = b0; b <= b1; b++, o++) { ek[o] = (ik[u] << bb) | b; ev[o] = u; }
+                    const u64 dg = db ? ((u64)((i64)u_ts[u] - (i64)u_qs[u] + (i64)doff) >> wd) : 0;
+                    for (u32 b = b0; b <= b1; b++, o++) { ek[o] = (((ik[u] << bb) | b) << db) | dg; ev[o] = u; }
                 });
-                sort_pairs(c, ek, ek2, ev, ev2, n_ent, 2 * sb + bb); // stable: chains stay in k order inside a bucket
+                sort_pairs(c, ek, ek2, ev, ev2, n_ent, 2 * sb + bb + db); // stable: chains stay in k order inside a bucket
                 uint4 *ent = A.take<uint4>(n_ent);
                 {
                     const u32 *evc = ev;
@@ -1327,8 +1338,11 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                     const u64 qc = (mqs + mqe) / 2, tc = (mts + mte) / 2;
                     const u64 pairkey = qkc[x0] >> bb;
                     u32 best = NONE32; // smallest u = the first chain in the reference's order (paf_filter.rs:553-596)
-                    for (u64 b = mqs >> wb; b <= (mqe >> wb); b++) {
-                        const u64 key = (pairkey << bb) | b;
+                    const u64 dm = (u64)((i64)tc - (i64)qc + (i64)doff);
+                    const u64 d0 = db ? (dm > R ? dm - R : 0) >> wd : 0, d1 = db ? (dm + R) >> wd : 0;
+                    for (u64 b = mqs >> wb; b <= (mqe >> wb); b++)
+                    for (u64 dg = d0; dg <= d1; dg++) {
+                        const u64 key = (((pairkey << bb) | b) << db) | dg;
                         u32 lo = 0, hi = n_ent;
                         while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (ekc[mid] < key) lo = mid + 1; else hi = mid; }
                         for (u32 x = lo; x < n_ent && ekc[x] == key; x++) {

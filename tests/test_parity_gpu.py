@@ -170,6 +170,27 @@ def test_fixpoint_everywhere(ctx, yeast, what, monkeypatch):
             check(ctx, cfg, t, f"fixpoint-fuzz{seed}")
 
 
+@pytest.mark.parametrize("variant", ["query_axis", "narrow0", "narrow6", "narrow12"])
+def test_fixpoint_search_orders(ctx, yeast, variant, monkeypatch):
+    """The fixed point's searches: along the query axis from the candidate records (SWG_FX_NO_BUCKETS=1, the round-1 form) and
+    in target-bucket order with buckets from G + G/5 wide (at most two per search) down to a few bases (dozens per search)."""
+    monkeypatch.setenv("SWG_FIXPOINT_MIN", "2")
+    monkeypatch.setenv("SWG_FIXPOINT_VERIFY", "1")
+    if variant == "query_axis":
+        monkeypatch.setenv("SWG_FX_NO_BUCKETS", "1")
+    else:
+        monkeypatch.setenv("SWG_FX_BUCKET_NARROW", variant[6:])
+    check(ctx, swg.FilterConfig(), synth.skew(n_pile=20_000, n_tiny_groups=3_000, seed=5, window=3_000_000), variant)
+    check(ctx, swg.FilterConfig.from_cli(**CLI_CASES["1:1_rescue"]), yeast, variant)
+    for seed in (500, 503, 505, 506):
+        t = fuzz_table(seed, 6000, n_genomes=1, n_chr=2, span=[4000, 20000][seed % 2], max_len=[400, 60][seed // 4 % 2], zero_len_frac=0.0)
+        cfg = swg.FilterConfig.from_cli(scaffold_jump=str([200, 1000, 3000, 50][seed % 4]), scaffold_mass="0", keep_self=True)
+        check(ctx, cfg, t, f"{variant}-dense{seed}")
+    for seed in range(120, 126):
+        cfg = swg.FilterConfig.from_cli(scaffold_jump=str([50, 200, 1000][seed % 3]), scaffold_mass=str([0, 100][seed % 2]), keep_self=True)
+        check(ctx, cfg, fuzz_table(seed, 5000), f"{variant}-fuzz{seed}")
+
+
 def test_fixpoint_round_limit_falls_back_to_the_walk(ctx, monkeypatch):
     """Picks that have not settled after SWG_FIXPOINT_MAX_ROUNDS rounds: the groups go through the sequential warp walk."""
     monkeypatch.setenv("SWG_FIXPOINT_MIN", "2")
@@ -215,6 +236,15 @@ def test_inversion_grid_yeast(ctx, yeast, case, monkeypatch):
     """Inversion capture through the bucketed path (taken on its own when a huge group exists), forced onto ordinary input."""
     monkeypatch.setenv("SWG_INV_GRID", "1")
     check(ctx, swg.FilterConfig.from_cli(**CLI_CASES[case]), yeast, "invgrid-" + case)
+
+
+@pytest.mark.parametrize("case", ["defaults", "rescue100k", "tight_jump"])
+def test_inversion_grid_without_diagonal_buckets(ctx, yeast, case, monkeypatch):
+    """The bucketed inversion capture with query-axis buckets only (what a key beyond 64 bits falls back to)."""
+    monkeypatch.setenv("SWG_INV_GRID", "1")
+    monkeypatch.setenv("SWG_INV_NO_DIAG", "1")
+    check(ctx, swg.FilterConfig.from_cli(**CLI_CASES[case]), yeast, "invgrid-nodiag-" + case)
+    check(ctx, swg.FilterConfig.from_cli(**CLI_CASES[case]), synth.skew(n_pile=20_000, n_tiny_groups=3_000, seed=5, window=3_000_000), "invgrid-nodiag-skew")
 
 
 @pytest.mark.parametrize("seed", range(0, 160, 4))
