@@ -73,7 +73,7 @@ struct FxArrays {
     u32 *ctrs;         // [0] list length, [1] picks changed this round, [2] recompute work counter, [3] slots refused (pool full)
     // target-bucket order (fx_bucket_pass): the positions of every huge group once more, ordered by (group, target bucket, k)
     u32 *hg;           // dense number of the position's huge group
-    uint4 *snap;       // (minpd lo, minpd hi, minpi, firstp) of every successor in one 16 B word: one gather per candidate
+    uint4 *snap;       // 32 B (one sector) per successor: [2j] = (minpd lo, minpd hi, minpi, firstp), [2j+1] = (d of the first picker lo, hi, off[j], list length)
     uint2 *bq;         // (query_start, t') of the entries in bucket order: all the gap rule reads of a candidate
     u32 *bk;           // their positions k
     u32 *dir;          // dir[hg * dirD + b] .. dir[hg * dirD + b + 1]: the entries of bucket b of the group
@@ -82,8 +82,8 @@ struct FxArrays {
 };
 
 // is some picker of j before position i with d' <= d?  (the caller knows that the list is not empty)
-__device__ __forceinline__ bool fx_list_blocks(const FxArrays &f, u32 i, u32 j, u64 d) {
-    const u32 a = f.off[j], b = f.off[j + 1];
+__device__ __forceinline__ bool fx_list_blocks(const FxArrays &f, u32 i, u32 j, u64 d, u32 a = NONE32, u32 b = NONE32) {
+    if (a == NONE32) { a = f.off[j]; b = f.off[j + 1]; }
     if (f.sorted) { // position order + prefix minima: the last picker before i answers for all of them
         u32 lo = a, hi = b;
         while (hi - lo > 4) {
@@ -105,6 +105,18 @@ __device__ __forceinline__ bool fx_eligible(const FxArrays &f, u32 i, u32 j, u64
     if (f.firstp[j] >= i) return true; // nobody picks j before i (ncu: the list walk below was 30 % of the stall samples of round 1)
     return !fx_list_blocks(f, i, j, d);
 }
+// The verdict from the packed snapshot of j.  The holder of the smallest d and the first picker settle most cases; between them
+// (first picker < i < holder of the minimum) the first picker's own d settles a list of two, and only longer lists are searched
+// — the second word of the snapshot lies in the sector the first came from.
+__device__ __forceinline__ bool fx_eligible_packed(const FxArrays &f, u32 i, u32 j, u64 d, u32 mi, u32 fp) {
+    if (mi < i) return false;
+    if (mi == i || fp >= i) return true;
+    const uint4 s2 = f.snap[2 * (size_t)j + 1];
+    const u64 fd = ((u64)s2.y << 32) | s2.x;
+    if (fd <= d) return false;
+    if (s2.w <= 2) return true;
+    return !fx_list_blocks(f, i, j, d, s2.z, s2.z + s2.w);
+}
 struct FxExtra {
     static constexpr u32 OUTWARD = 128; // wider rounds measured slower (256: 2.3x on the 8 M pile): most searches end within the first rounds
     static constexpr bool PREFETCH = true;
@@ -114,10 +126,7 @@ struct FxExtra {
     u32 *seen, *n_seen; // shared memory of the warp: the blocked candidates met by the search (a superset of X(i))
     // the same verdict from the packed snapshot word of j (mi = minpi[j], fp = firstp[j]); callers have established d >= minpd[j]
     __device__ __forceinline__ bool packed(u32 j, u64 d, u32 mi, u32 fp) const {
-        bool el;
-        if (mi < i) el = false;
-        else if (mi == i || fp >= i) el = true;
-        else el = !fx_list_blocks(f, i, j, d);
+        const bool el = fx_eligible_packed(f, i, j, d, mi, fp);
         if (!el) {
             const u32 o = atomicAdd(n_seen, 1u);
             if (o < FX_XCAP) seen[o] = j;
@@ -161,12 +170,9 @@ __global__ void __launch_bounds__(256) k_fx_check(FxArrays f, u64 G) {
                         const u32 jx = x[q];
                         if (bits && !(f.dbits[jx >> 5] >> (jx & 31) & 1)) continue;
                         const u64 d = xd[q];
-                        const uint4 sn = f.snap[jx];
+                        const uint4 sn = f.snap[2 * (size_t)jx];
                         const u64 mp = ((u64)sn.y << 32) | sn.x;
-                        if (d < mp) need = true;
-                        else if (sn.z < k) need = false;
-                        else if (sn.z == k || sn.w >= k) need = true;
-                        else need = fx_eligible(f, k, jx, d, sn.z);
+                        need = d < mp || fx_eligible_packed(f, k, jx, d, sn.z, sn.w);
                     }
                 } else
                 for (u32 q = 0; q < xc && !need; q++) {
@@ -308,7 +314,7 @@ __device__ __forceinline__ void fx_eval_round(const FxArrays &f, const uint4 &a,
     }
 #pragma unroll
     for (u32 k = 0; k < CW; k++)
-        if (want[k]) sn[k] = f.snap[rj[k]];
+        if (want[k]) sn[k] = f.snap[2 * (size_t)rj[k]];
     u64 ld = bd;
     u32 lj = bj;
 #pragma unroll
@@ -596,7 +602,7 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
     if (bucket) {
         // dense numbers of the huge groups (a group starts where the previous position's group ends)
         f.hg = A.take<u32>(n_h);
-        f.snap = A.take<uint4>(n_h);
+        f.snap = A.take<uint4>(2 * (size_t)n_h);
         {
             const FxArrays g = f;
             scan_apply([=] __device__(u32 k) -> u32 { return (k == 0 || (g.gend[k - 1] & ~FX_REV) == k) ? 1u : 0u; },
@@ -666,7 +672,7 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
         SWG_CUDA(cudaMemsetAsync(f.minpi, 0xFF, sizeof(u32) * (size_t)n_h, st));
         SWG_CUDA(cudaMemsetAsync(f.firstp, 0xFF, sizeof(u32) * (size_t)n_h, st));
         SWG_CUDA(cudaMemsetAsync(f.off, 0, sizeof(u32) * ((size_t)n_h + 1), st));
-        SWG_CUDA(cudaMemsetAsync(f.snap, 0xFF, sizeof(uint4) * (size_t)n_h, st)); // nobody picks anybody
+        SWG_CUDA(cudaMemsetAsync(f.snap, 0xFF, 2 * sizeof(uint4) * (size_t)n_h, st)); // nobody picks anybody
         SWG_CUDA(cudaMemsetAsync(f.dbits_w, 0, sizeof(u32) * n_bw, st));
         SWG_CUDA(cudaMemsetAsync(f.dirty, 0, sizeof(u32) * (size_t)n_blk, st));
         SWG_CUDA(cudaMemsetAsync(f.ctrs, 0, 4 * sizeof(u32), st));
@@ -741,17 +747,20 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
             const u32 j = g.pick[k];
             if (j != NONE32 && g.pd[k] == g.minpd[j]) atomicMin(&g.minpi[j], k);
         });
-        if (bucket)
-            launch_for<t_fx_snap>(n_h, st, lc, [=] __device__(u32 k) {
-                const u64 mp = g.minpd[k];
-                g.snap[k] = make_uint4((u32)mp, (u32)(mp >> 32), g.minpi[k], g.firstp[k]);
-            });
         scan_apply([=] __device__(u32 k) -> u32 { return g.cnt[k]; },
                    [=] __device__(u32 k, u32 ex, u32 v) {
                        g.off[k] = ex;
                        if (k + 1 == g.n) g.off[g.n] = ex + v;
                    },
                    n_h, bsum, scan_tot, st, lc);
+        if (bucket)
+            launch_for<t_fx_snap>(n_h, st, lc, [=] __device__(u32 j) {
+                const u64 mp = g.minpd[j];
+                const u32 fp = g.firstp[j];
+                const u64 fd = fp != NONE32 ? g.pd[fp] : NONE64;
+                g.snap[2 * (size_t)j] = make_uint4((u32)mp, (u32)(mp >> 32), g.minpi[j], fp);
+                g.snap[2 * (size_t)j + 1] = make_uint4((u32)fd, (u32)(fd >> 32), g.off[j], g.off[j + 1] - g.off[j]);
+            });
         if (bucket)
             launch_for<t_fx_pm>(n_h, st, lc, [=] __device__(u32 j) {
                 u64 m = NONE64;
