@@ -318,18 +318,29 @@ def paf_file_leg(ctx, cfg, n_lines):
 
 
 def skew_leg(ctx, cfg, n_pile):
-    """Extra, informational: configs[4] (one centromeric pile + 100 k tiny groups) at --skew-pile mappings; the two strand
-    groups of the pile go through the fixed-point chaining.  Host buffers, wall clock.  Never fails the bench."""
+    """Extra, informational: configs[4] (one centromeric pile + 100 k tiny groups) at --skew-pile mappings (default: the full
+    50 M); the two strand groups of the pile go through the fixed-point chaining.  The first call runs with
+    SWG_FIXPOINT_VERIFY=1 (after the last round every position of the pile is re-evaluated from scratch against the final picks;
+    the call fails if one would choose differently) and doubles as the warm-up, the second is timed.  Host buffers, wall clock.
+    Never fails the bench."""
     try:
         from sweepga_b200 import synth
         t = synth.skew(n_pile=n_pile, n_tiny_groups=100_000, seed=5)
-        ctx.filter(cfg, t)
+        os.environ["SWG_FIXPOINT_VERIFY"] = "1"
+        try:
+            _, _, st0 = ctx.filter(cfg, t)
+            verified = True
+        finally:
+            del os.environ["SWG_FIXPOINT_VERIFY"]
         t0 = time.time()
-        _, _, st = ctx.filter(cfg, t)
+        s1, c1, st = ctx.filter(cfg, t)
         dt = time.time() - t0
-        return {"workload": f"configs[4] at reduced scale: {n_pile} mappings on one chromosome pair (95 % inside 6 Mbp) + 100000 tiny groups",
+        same = bool(st0.n_kept == st.n_kept and st0.n_chains_kept == st.n_chains_kept)
+        return {"workload": f"configs[4]: {n_pile} mappings on one chromosome pair (95 % inside 6 Mbp) + 100000 tiny groups, defaults",
                 "records": int(t.n), "wall_s": dt, "ms_device": float(st.ms_device), "Mmappings_per_s": t.n / dt / 1e6,
-                "gpu_launches": int(st.gpu_launches), "kept": int(st.n_kept), "chains": int(st.n_chains_kept)}
+                "gpu_launches": int(st.gpu_launches), "kept": int(st.n_kept), "chains": int(st.n_chains_kept),
+                "fixpoint_verified": verified and same,
+                "ms_device_with_verification_pass": float(st0.ms_device)}
     except Exception as e:  # informational leg only
         return {"error": repr(e)[:200]}
 
@@ -400,7 +411,7 @@ def main():
     ap.add_argument("--records", type=int, default=0, help="override the per-GPU record count (debug only)")
     ap.add_argument("--paf-lines", type=int, default=2_000_000,
                     help="N = 1 only: also time swg_filter_paf file to file on a synthetic PAF of this many lines (0 = skip)")
-    ap.add_argument("--skew-pile", type=int, default=5_000_000,
+    ap.add_argument("--skew-pile", type=int, default=50_000_000,
                     help="size of the configs[4] pile of the informational skew leg (0 = skip)")
     ap.add_argument("--cpu-sample", type=int, default=20_000_000,
                     help="records of the workload the CPU oracle is timed on (~20 core-seconds at the default)")

@@ -361,7 +361,8 @@ __device__ __forceinline__ u32 fx_bucket_pass(const FxArrays &f, u32 i, const ui
             const long long b = side ? bc - step : bc + step;
             if (b < blo || b > bhi) { (side ? live_dn : live_up) = false; continue; }
             const u64 rmin = step == 0 ? 0 : (side ? c - ((u64)(b + 1) * W - 1) : (u64)b * W - c);
-            if (rmin * rmin > bd) { (side ? live_dn : live_up) = false; continue; } // and every bucket beyond it
+            const u64 r2 = rmin * rmin; // every candidate of the bucket has d >= q_gap^2 + r2
+            if (r2 > bd) { (side ? live_dn : live_up) = false; continue; } // and every bucket beyond it
             const u32 lo0 = dir[b], hi0 = dir[b + 1];
             if (lo0 == hi0) continue;
             // first entry of the bucket whose query_start reaches query_end(i): 33-ary search, 32 probes in flight per round
@@ -397,7 +398,7 @@ __device__ __forceinline__ u32 fx_bucket_pass(const FxArrays &f, u32 i, const ui
                     mono = false;
                     if (rj[k] != NONE32) {
                         const u64 qg = (u64)rb[k].x - a.y;
-                        mono = qg <= G && qg * qg <= bd;
+                        mono = qg <= G && qg * qg + r2 <= bd;
                     }
                     in[k] = mono && rj[k] > i; // (a zero-length record meets earlier positions with the same start here)
                 }
@@ -425,7 +426,7 @@ __device__ __forceinline__ u32 fx_bucket_pass(const FxArrays &f, u32 i, const ui
                     in[k] = false;
                     if (rj[k] != NONE32) {
                         const u64 ov = (u64)a.y - rb[k].x;
-                        in[k] = ov <= G5 && ov * ov <= bd && rj[k] > i;
+                        in[k] = ov <= G5 && ov * ov + r2 <= bd && rj[k] > i;
                     }
                 }
                 if (COLLECT) {
@@ -611,12 +612,12 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
         SWG_CUDA(cudaMemcpyAsync(h, scan_tot, sizeof(u32), cudaMemcpyDeviceToHost, st));
         SWG_CUDA(cudaStreamSynchronize(st));
         const u32 n_hg = h[0];
-        // bucket width: an eighth of the smallest power of two >= G + G/5 + 1 (SWG_FX_BUCKET_NARROW=<log2 of the divisor>: tuning aid).
+        // bucket width: 1/32 of the smallest power of two >= G + G/5 + 1 (SWG_FX_BUCKET_NARROW=<log2 of the divisor>: tuning aid).
         // A search visits the buckets outwards from the one that holds its own target coordinate and stops at the first whose
         // nearest edge is further than sqrt(best d): narrow buckets keep the scans of the dense diagonal short, wide ones spare
         // the scattered positions origin searches.  Wider if the directory (one entry per group and bucket) would pass 2^25
         // entries or 2^20 per group.
-        const int narrow = getenv("SWG_FX_BUCKET_NARROW") ? atoi(getenv("SWG_FX_BUCKET_NARROW")) : 3;
+        const int narrow = getenv("SWG_FX_BUCKET_NARROW") ? atoi(getenv("SWG_FX_BUCKET_NARROW")) : 5;
         int bs = std::max(bits_for(G + G / 5) - narrow, 4);
         while ((((u64)(maxcoord >> bs) + 2) * n_hg > (1ull << 25) || ((u64)maxcoord >> bs) + 2 > (1ull << 20)) && bs < 32) bs++;
         f.bshift = bs;
