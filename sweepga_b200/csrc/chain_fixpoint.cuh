@@ -11,26 +11,30 @@
 // mapping); here ALL positions are evaluated against a snapshot of the picks and the evaluation is repeated until nothing
 // changes.  By induction on i the positions below the first wrong one stay correct and that one becomes correct in the
 // next round, so the iteration ends in the reference's picks; measured on the configs[4] piles it needs 6 rounds for a
-// 100 k group, 14 for a 500 k group and 56 for the two 25 M groups of the full configuration (12.3 s for the whole filter
+// 100 k group, 14 for a 500 k group and 56 for the two 25 M groups of the full configuration (2.05 s for the whole filter
 // call), and the number of positions that have to be re-evaluated shrinks geometrically.
 //
 // A round:
-//   1. snapshot: picker lists per successor j (CSR: count, scan, fill), minpd[j] = smallest d over all pickers of j,
-//      minpi[j] = the first picker holding it, firstp[j] = the first picker at all: "d < B(i,j)?" is answered from these
-//      three words in all but a few cases, without walking the list
+//   1. snapshot: picker lists per successor j (CSR) in position order — the positions sorted by their pick, stable — with the
+//      picker d stored as prefix minima; per successor one 32 B word: minpd[j] = smallest d over all pickers of j, minpi[j] = the
+//      first picker holding it, firstp[j] = the first picker at all and its d, the list range.  "d < B(i,j)?" is answered from
+//      that word in all but a few cases (fx_eligible_packed), else by one binary search over the list.
 //   2. k_fx_check (thread per position; a position is skipped outright when no picker list among the successors it can
 //      depend on — up to xhi[i] = max(pick(i), X(i)) — changed in the last round: dirty blocks of 512 successors and their
-//      prefix counts): position i must be re-evaluated iff its pick is now blocked (an earlier picker
+//      prefix counts; an entry whose successor's own list did not change — one bit per successor — keeps its verdict): position i
+//      must be re-evaluated iff its pick is now blocked (an earlier picker
 //      of the same j with d' <= d) or one of the candidates that rank BEFORE its pick — X(i), all of them ineligible when
-//      the pick was made, remembered explicitly — has become eligible.  This test is exact: a position whose pick stands
-//      and whose X(i) is still blocked would pick the same j again.
-//   3. k_fx_recompute (warp per listed position): the pruned window search of the sequential walk
-//      (bb_best_successor_warp) with eligibility against the snapshot.  The blocked candidates the search meets while they
-//      still beat the lane's best are recorded in shared memory — a superset of X(i), filtered against the final pick
-//      (fx_filter_seen); only if that record overflows, a second pruned pass collects X(i) (fx_collect_blocked).
+//      the pick was made, remembered explicitly with their d — has become eligible.  This test is exact: a position whose pick
+//      stands and whose X(i) is still blocked would pick the same j again.
+//   3. k_fx_recompute (warp per listed position): the search in target-bucket order (fx_bucket_pass: the group's positions
+//      once more by (bucket of the target coordinate the gap rule tests, position); buckets visited outwards from the position's
+//      own, pruned outward scans inside a bucket) with eligibility against the snapshot.  The blocked candidates the search meets
+//      while they still beat the lane's best are recorded in shared memory — a superset of X(i), filtered against the final pick
+//      (fx_filter_seen); only if that record overflows, a second pruned pass collects X(i).  SWG_FX_NO_BUCKETS=1: the pruned
+//      window search of the sequential walk (bb_best_successor_warp) along the query axis instead, from the candidate records.
 // A huge group whose picks have not settled after SWG_FIXPOINT_MAX_ROUNDS rounds goes to the sequential walk after all;
 // SWG_FIXPOINT_VERIFY=1 re-evaluates every position from scratch against the final picks (0 of 50 M change on configs[4]).
-// The first round starts from k_chain_candidates' unconstrained arg-min (X(i) is empty there by definition).
+// Round 0 evaluates every position against the empty snapshot: the unconstrained arg-min (X(i) is empty there by definition).
 // After the last round pred[j] = the last picker of j, roots by pointer jumping (union_find.rs:25-41: the root of a set is
 // its head), results scattered back to the sorted positions.  Everything runs in the compact index space k of the positions
 // that belong to huge groups (groups stay contiguous there, so successor offsets carry over).
@@ -58,6 +62,7 @@ struct FxArrays {
     u32 *firstp;       // the first picker of j at all (NONE32: nobody)
     u32 *li;           // picker position
     u64 *ld;           // picker d (sorted lists: the smallest d of the list up to and including this entry)
+    u32 force_collect; // testing aid (SWG_FX_FORCE_COLLECT=1): X(i) always from the separate collecting pass
     u32 sorted;        // 1: every picker list is in position order and ld holds prefix minima (bucket order)
     u32 *xoff;         // X(i) lives at pool[xoff .. xoff + xcnt)
     u16 *xcnt, *xcap;
@@ -474,7 +479,7 @@ __global__ void __launch_bounds__(128, BUCKET ? 8 : 3) k_fx_recompute(FxArrays f
         __syncwarp();
         // X(i): normally out of the search's own record of blocked candidates; a separate pruned pass if that overflowed
         const u32 seen = *n_seen;
-        const u32 xn = seen <= FX_XCAP ? fx_filter_seen(f.rec, a, fwd, G, G5, bd, bj, xs, seen)
+        const u32 xn = seen <= FX_XCAP && !f.force_collect ? fx_filter_seen(f.rec, a, fwd, G, G5, bd, bj, xs, seen)
                        : BUCKET    ? fx_bucket_pass<true>(f, i, a, fwd, G, G5, bd, bj, ex, xs)
                                    : fx_collect_blocked(f.rec, i, e, a, fwd, G, G5, bd, bj, c0, xs);
         __syncwarp();
@@ -552,6 +557,7 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
     f.firstp = A.take<u32>(n_h);
     f.li = bucket ? nullptr : A.take<u32>(n_h); // bucket order: the sorted positions of the round's sort
     f.sorted = bucket ? 1 : 0;
+    f.force_collect = getenv("SWG_FX_FORCE_COLLECT") != nullptr;
     f.ld = A.take<u64>(n_h);
     f.xoff = A.take<u32>(n_h);
     f.xcnt = A.take<u16>(n_h);

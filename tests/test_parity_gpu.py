@@ -170,12 +170,15 @@ def test_fixpoint_everywhere(ctx, yeast, what, monkeypatch):
             check(ctx, cfg, t, f"fixpoint-fuzz{seed}")
 
 
-@pytest.mark.parametrize("variant", ["query_axis", "narrow0", "narrow6", "narrow12"])
+@pytest.mark.parametrize("variant", ["query_axis", "query_axis_collect", "narrow0", "narrow6", "narrow12", "narrow5_collect"])
 def test_fixpoint_search_orders(ctx, yeast, variant, monkeypatch):
     """The fixed point's searches: along the query axis from the candidate records (SWG_FX_NO_BUCKETS=1, the round-1 form) and
     in target-bucket order with buckets from G + G/5 wide (at most two per search) down to a few bases (dozens per search)."""
     monkeypatch.setenv("SWG_FIXPOINT_MIN", "2")
     monkeypatch.setenv("SWG_FIXPOINT_VERIFY", "1")
+    if variant.endswith("_collect"):  # X(i) from the separate collecting pass (otherwise only after 1024 blocked candidates)
+        monkeypatch.setenv("SWG_FX_FORCE_COLLECT", "1")
+        variant = variant[:-8]
     if variant == "query_axis":
         monkeypatch.setenv("SWG_FX_NO_BUCKETS", "1")
     else:
