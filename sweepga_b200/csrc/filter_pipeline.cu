@@ -62,7 +62,7 @@ template <class Tag, class F> static inline void launch_for_dev(const u32 *n_ptr
 // tags: one per element-wise stage, so that the ncu launch list reads k_for<swg::t_assign, ...> etc.
 struct t_iota; struct t_maxp; struct t_scores; struct t_gkey; struct t_events; struct t_sweep_gather; struct t_sweep_keep;
 struct t_gather; struct t_chain_order; struct t_tspace; struct t_segapply; struct t_keys_c2min; struct t_keys_g2min;
-struct t_final_k; struct t_assign; struct t_invkeys; struct t_invent; struct t_inversion; struct t_anchor_keys; struct t_rescue;
+struct t_final_k; struct t_assign; struct t_invkeys; struct t_invw; struct t_invw2; struct t_invent; struct t_inversion; struct t_anchor_keys; struct t_rescue;
 
 // ---- grow-only HBM arena ----------------------------------------------------------------------
 // One block sized for the common path; a call that needs more (general sweeps, degenerate
@@ -118,7 +118,7 @@ struct Arena {
 namespace swg {
 // Environment knobs (diagnostics and tests).  Read once per entry point, never cached across calls.
 struct Knobs {
-    bool force_wide = false, sweep_no_flat = false, no_fixpoint = false, fx_no_buckets = false, inv_grid = false, inv_no_grid = false, inv_no_diag = false, cuda_log = false;
+    bool force_wide = false, sweep_no_flat = false, no_fixpoint = false, fx_no_buckets = false, inv_grid = false, inv_no_grid = false, inv_no_diag = false, inv_wide = false, cuda_log = false;
     bool pairs_sort = false;   // SWG_SORT_PAIRS=1: the record sort keeps (key, payload) pairs through every pass
     bool no_fused_keys = false; // SWG_NO_FUSED_KEYS=1: the chain sort keys always come from k_chain_keys
     bool no_group_sort = false; // SWG_NO_GROUP_SORT=1: the record sort always runs the LSD passes (radix_sort.cuh)
@@ -139,6 +139,7 @@ static Knobs read_knobs() {
     k.fx_no_buckets = on("SWG_FX_NO_BUCKETS");
     k.inv_grid = on("SWG_INV_GRID");
     k.inv_no_diag = on("SWG_INV_NO_DIAG");
+    k.inv_wide = on("SWG_INV_WIDE");
     k.inv_no_grid = on("SWG_INV_NO_GRID");
     k.pairs_sort = on("SWG_SORT_PAIRS");
     k.no_fused_keys = on("SWG_NO_FUSED_KEYS");
@@ -1275,35 +1276,80 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
         }
         // A chromosome pair that holds a huge group can hold 10^5..10^6 kept chains; walking all of them for every
         // reverse mapping is O(n * chains).  Then (or with SWG_INV_GRID=1) chains and mappings meet in buckets of the query axis.
-        const int wb = std::max(17, bits_for(2 * cfg.scaffold_gap + 1)); // bucket width 2^wb > 2 * jump
-        const int bb = cb > wb ? cb - wb : 1;
-        const bool inv_grid = (n_huge > 0 || K.inv_grid) && !K.inv_no_grid && 2 * sb + bb + 1 <= 64;
+        const int wb0 = std::max(17, bits_for(2 * cfg.scaffold_gap + 1)); // widest bucket: 2^wb0 > 2 * jump
+        const bool inv_grid = (n_huge > 0 || K.inv_grid) && !K.inv_no_grid && 2 * sb + (cb > wb0 ? cb - wb0 : 1) + 1 <= 64;
         if (inv_grid) {
             stage_mark(c, "inversion_grid");
             const u64 G = cfg.scaffold_gap;
             const u64 maxc = maxcoord;
+            u32 *d_cnt = A.take<u32>(2); // [0] entries, [1] candidate mappings
+            u32 *inv_list = A.take<u32>(N);
+            scan_flags([=] __device__(u32 i) -> u32 { return (flags[i] & (F_ALIVE | F_REV | F_ANCHOR)) == (F_ALIVE | F_REV) ? 1u : 0u; },
+                       [=] __device__(u32 i, u32 ex, u32 v) { if (v) inv_list[ex] = i; }, N, bsum, d_cnt + 1, st, lc);
+            // Bucket width of the query axis.  The chains of a (pair, '+') group are numbered in query order, so the entries of a bucket
+            // ascend along the query axis and a mapping in the middle of a wide bucket walks every chain that ends more than a jump to
+            // its left before the first it can belong to (20 M pile, 2^17: 1560 entries per mapping).  Narrow buckets make nearly every
+            // entry of a cell a hit on the query axis; they cost entries (a chain enters every bucket its extended interval touches)
+            // and cells per mapping.  Both are counted for the widths 2^wb0 .. 2^12 and the narrowest width within budget is taken.
+            constexpr int NW = 6;
+            unsigned long long *wcnt = (unsigned long long *)A.take<u64>(2 * NW);
+            SWG_CUDA(cudaMemsetAsync(wcnt, 0, 2 * NW * sizeof(u64), st));
+            launch_for<t_invw>(C2, st, lc, [=] __device__(u32 u) {
+                const bool f = ik[u] != NONE64;
+                const u64 a0 = u_qs[u] > G ? (u64)u_qs[u] - G : 0, e0 = (u64)u_qe[u] + G < maxc ? (u64)u_qe[u] + G : maxc;
+                const u32 am = __activemask();
+#pragma unroll
+                for (int k = 0; k < NW; k++) {
+                    const int w = wb0 - k;
+                    const u32 v = f && w >= 12 ? (u32)((e0 >> w) - (a0 >> w) + 1) : 0u;
+                    const u32 sum = __reduce_add_sync(am, v);
+                    if (sum && (threadIdx.x & 31) == (u32)(__ffs(am) - 1)) atomicAdd(&wcnt[k], (unsigned long long)sum);
+                }
+            });
+            launch_for_dev<t_invw2>(d_cnt + 1, c->sm_count, st, lc, [=] __device__(u32 x) {
+                const u32 i = inv_list[x];
+                const u32 qs0 = in.qs[i], qe0 = in.qe[i];
+                const u32 am = __activemask();
+#pragma unroll
+                for (int k = 0; k < NW; k++) {
+                    const int w = wb0 - k;
+                    const u32 v = w >= 12 ? (qe0 >> w) - (qs0 >> w) + 1 : 0u;
+                    const u32 sum = __reduce_add_sync(am, v);
+                    if (sum && (threadIdx.x & 31) == (u32)(__ffs(am) - 1)) atomicAdd(&wcnt[NW + k], (unsigned long long)sum);
+                }
+            });
+            u32 *h2 = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
+            unsigned long long hw[2 * NW];
+            SWG_CUDA(cudaMemcpyAsync(h2 + 1, d_cnt + 1, sizeof(u32), cudaMemcpyDeviceToHost, st));
+            SWG_CUDA(cudaMemcpyAsync(hw, wcnt, sizeof hw, cudaMemcpyDeviceToHost, st));
+            SWG_CUDA(cudaStreamSynchronize(st));
+            int wb = wb0;
+            for (int k = NW - 1; k > 0; k--) {
+                const int w = wb0 - k;
+                if (w < 12 || K.inv_wide) continue;
+                const bool fits = 2 * sb + (cb > w ? cb - w : 1) + 1 <= 64;
+                if (fits && hw[k] <= std::max<u64>(1ull << 25, 8ull * C2) && hw[k] < (1ull << 31) && hw[NW + k] <= 3ull * h2[1] + 1024) { wb = w; break; }
+            }
+            const int bb = cb > wb ? cb - wb : 1;
             // ... and in buckets of the diagonal (target_start - query_start of a chain against the centre diagonal of a mapping): the
-            // deviation test floor(|dev| / sqrt 2) <= G admits |dev| < (G + 1) * sqrt 2 only, so a mapping meets the chains of at most two
-            // diagonal buckets of width >= 2 R + 1 — in a repeat pile one bucket of the query axis alone holds 10^5 chains of which the
-            // scattered mappings pass a few hundred before their first hit.  No diagonal buckets when the key would not fit 64 bits.
+            // deviation test floor(|dev| / sqrt 2) <= G admits |dev| <= R only, so a mapping meets the chains of the diagonal buckets
+            // that [dm - R, dm + R] touches.  Width: an eighth of 2 R + 1 (a mapping walks up to ten narrow cells, but a cell it can only
+            // fail in is small); wider while the key would pass 64 bits, no diagonal buckets if it still does.
             const u64 R = (u64)std::ceil((double)(G + 1) * 1.4142135623730951) + 1; // |dev| > R  =>  perp > G
-            const int wd = bits_for(2 * R + 1);
+            int wd = std::max(bits_for(2 * R + 1) - 3, 8);
             const u64 doff = maxc + 1; // diagonals are shifted to be non-negative: they lie in [-maxc, maxc]
             int db = bits_for((2 * maxc + 2) >> wd);
+            while (2 * sb + bb + db > 64 && wd < bits_for(2 * R + 1)) { wd++; db = bits_for((2 * maxc + 2) >> wd); }
             if (2 * sb + bb + db > 64 || K.inv_no_diag) db = 0;
             // entries: every kept '+' chain once per bucket its extended query interval [qs - G, qe + G] touches
             u32 *e_off = A.take<u32>(C2);
-            u32 *d_cnt = A.take<u32>(2); // [0] entries, [1] candidate mappings
             auto first_b = [=] __device__(u32 u) -> u32 { const u64 a = u_qs[u]; return (u32)((a > G ? a - G : 0) >> wb); };
             auto last_b = [=] __device__(u32 u) -> u32 { const u64 e = (u64)u_qe[u] + G; return (u32)((e < maxc ? e : maxc) >> wb); };
             scan_apply([=] __device__(u32 u) -> u32 { return ik[u] != NONE64 ? last_b(u) - first_b(u) + 1 : 0u; },
                        [=] __device__(u32 u, u32 ex, u32) { e_off[u] = ex; }, C2, bsum, d_cnt, st, lc);
-            u32 *inv_list = A.take<u32>(N);
-            scan_flags([=] __device__(u32 i) -> u32 { return (flags[i] & (F_ALIVE | F_REV | F_ANCHOR)) == (F_ALIVE | F_REV) ? 1u : 0u; },
-                       [=] __device__(u32 i, u32 ex, u32 v) { if (v) inv_list[ex] = i; }, N, bsum, d_cnt + 1, st, lc);
-            u32 *h2 = reinterpret_cast<u32 *>(c->h_ctr + C_COUNT);
-            SWG_CUDA(cudaMemcpyAsync(h2, d_cnt, 2 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+            SWG_CUDA(cudaMemcpyAsync(h2, d_cnt, sizeof(u32), cudaMemcpyDeviceToHost, st));
             SWG_CUDA(cudaStreamSynchronize(st));
+            if (getenv("SWG_STAGE_TIMING")) fprintf(stderr, "[swg inversion] query buckets 2^%d (widest 2^%d), diagonal buckets 2^%d (%d bits)\n", wb, wb0, wd, db);
             const u32 n_ent = h2[0], n_inv = h2[1];
             if (n_ent && n_inv) {
                 u64 *ek = A.take<u64>(n_ent), *ek2 = A.take<u64>(n_ent);
@@ -1332,7 +1378,11 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                 sort_pairs(c, qk, qk2, qv, qv2, n_inv, 2 * sb + bb);
                 const u64 *ekc = ek, *qkc = qk;
                 const u32 *qvc = qv;
+                unsigned long long *inv_dbg = (unsigned long long *)A.take<u64>(4);
+                SWG_CUDA(cudaMemsetAsync(inv_dbg, 0, 4 * sizeof(u64), st));
+                const bool dbg = getenv("SWG_STAGE_TIMING") != nullptr;
                 launch_for<t_inversion>(n_inv, st, lc, [=] __device__(u32 x0) {
+                    u32 n_walk = 0, n_cells = 0;
                     const u32 i = qvc[x0];
                     const u64 mqs = in.qs[i], mqe = in.qe[i], mts = in.ts[i], mte = in.te[i];
                     const u64 qc = (mqs + mqe) / 2, tc = (mts + mte) / 2;
@@ -1345,7 +1395,9 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                         const u64 key = (((pairkey << bb) | b) << db) | dg;
                         u32 lo = 0, hi = n_ent;
                         while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (ekc[mid] < key) lo = mid + 1; else hi = mid; }
+                        n_cells++;
                         for (u32 x = lo; x < n_ent && ekc[x] == key; x++) {
+                            n_walk++;
                             const uint4 ch = ent[x];
                             if (ch.w >= best) break; // entries of a bucket ascend in u
                             const u64 cqs = ch.x, cqe = ch.y, cts = ch.z;
@@ -1358,7 +1410,14 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                         }
                     }
                     if (best != NONE32) { status[i] = 1; chain_id[i] = best + 1; flags[i] |= F_ANCHOR; }
+                    if (dbg) { atomicAdd(&inv_dbg[0], (unsigned long long)n_walk); atomicAdd(&inv_dbg[1], (unsigned long long)n_cells); atomicMax(&inv_dbg[2], (unsigned long long)n_walk); if (best != NONE32) atomicAdd(&inv_dbg[3], 1ull); }
                 });
+                if (dbg) {
+                    unsigned long long hd[4];
+                    SWG_CUDA(cudaMemcpyAsync(hd, inv_dbg, sizeof hd, cudaMemcpyDeviceToHost, st));
+                    SWG_CUDA(cudaStreamSynchronize(st));
+                    fprintf(stderr, "[swg inversion] %u candidates, %u entries, %llu entries walked (max %llu per candidate), %llu cells, %llu captured\n", n_inv, n_ent, hd[0], hd[2], hd[1], hd[3]);
+                }
             }
         } else {
         {

@@ -246,6 +246,8 @@ def test_inversion_grid_without_diagonal_buckets(ctx, yeast, case, monkeypatch):
     """The bucketed inversion capture with query-axis buckets only (what a key beyond 64 bits falls back to)."""
     monkeypatch.setenv("SWG_INV_GRID", "1")
     monkeypatch.setenv("SWG_INV_NO_DIAG", "1")
+    if case == "rescue100k":  # ... and the widest query buckets only (the default picks the narrowest width within budget)
+        monkeypatch.setenv("SWG_INV_WIDE", "1")
     check(ctx, swg.FilterConfig.from_cli(**CLI_CASES[case]), yeast, "invgrid-nodiag-" + case)
     check(ctx, swg.FilterConfig.from_cli(**CLI_CASES[case]), synth.skew(n_pile=20_000, n_tiny_groups=3_000, seed=5, window=3_000_000), "invgrid-nodiag-skew")
 
