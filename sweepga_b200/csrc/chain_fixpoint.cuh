@@ -738,43 +738,48 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
         // 1. snapshot of the picks
         const FxArrays g = f;
         SWG_CUDA(cudaMemsetAsync(f.cnt, 0, sizeof(u32) * (size_t)n_h, st));
-        SWG_CUDA(cudaMemsetAsync(f.minpd, 0xFF, sizeof(u64) * (size_t)n_h, st));
-        SWG_CUDA(cudaMemsetAsync(f.minpi, 0xFF, sizeof(u32) * (size_t)n_h, st));
-        SWG_CUDA(cudaMemsetAsync(f.firstp, 0xFF, sizeof(u32) * (size_t)n_h, st));
         SWG_CUDA(cudaMemsetAsync(f.ctrs, 0, 4 * sizeof(u32), st));
+        if (!bucket) {
+            SWG_CUDA(cudaMemsetAsync(f.minpd, 0xFF, sizeof(u64) * (size_t)n_h, st));
+            SWG_CUDA(cudaMemsetAsync(f.minpi, 0xFF, sizeof(u32) * (size_t)n_h, st));
+            SWG_CUDA(cudaMemsetAsync(f.firstp, 0xFF, sizeof(u32) * (size_t)n_h, st));
+        }
         launch_for<t_fx_count>(n_h, st, lc, [=] __device__(u32 k) {
             const u32 j = g.pick[k];
             if (j != NONE32) {
                 atomicAdd(&g.cnt[j], 1u);
-                atomicMin((unsigned long long *)&g.minpd[j], (unsigned long long)g.pd[k]);
-                atomicMin(&g.firstp[j], k);
+                if (!g.sorted) { // (sorted lists: the per-successor pass below reads both off its list)
+                    atomicMin((unsigned long long *)&g.minpd[j], (unsigned long long)g.pd[k]);
+                    atomicMin(&g.firstp[j], k);
+                }
             }
         });
-        launch_for<t_fx_minpi>(n_h, st, lc, [=] __device__(u32 k) {
-            const u32 j = g.pick[k];
-            if (j != NONE32 && g.pd[k] == g.minpd[j]) atomicMin(&g.minpi[j], k);
-        });
+        if (!bucket)
+            launch_for<t_fx_minpi>(n_h, st, lc, [=] __device__(u32 k) {
+                const u32 j = g.pick[k];
+                if (j != NONE32 && g.pd[k] == g.minpd[j]) atomicMin(&g.minpi[j], k);
+            });
         scan_apply([=] __device__(u32 k) -> u32 { return g.cnt[k]; },
                    [=] __device__(u32 k, u32 ex, u32 v) {
                        g.off[k] = ex;
                        if (k + 1 == g.n) g.off[g.n] = ex + v;
                    },
                    n_h, bsum, scan_tot, st, lc);
-        if (bucket)
-            launch_for<t_fx_snap>(n_h, st, lc, [=] __device__(u32 j) {
-                const u64 mp = g.minpd[j];
-                const u32 fp = g.firstp[j];
-                const u64 fd = fp != NONE32 ? g.pd[fp] : NONE64;
-                g.snap[2 * (size_t)j] = make_uint4((u32)mp, (u32)(mp >> 32), g.minpi[j], fp);
-                g.snap[2 * (size_t)j + 1] = make_uint4((u32)fd, (u32)(fd >> 32), g.off[j], g.off[j + 1] - g.off[j]);
-            });
-        if (bucket)
+        if (bucket) // one pass per successor over its list (position order): prefix minima, who holds the minimum first, the packed words
             launch_for<t_fx_pm>(n_h, st, lc, [=] __device__(u32 j) {
-                u64 m = NONE64;
-                for (u32 p = g.off[j]; p < g.off[j + 1]; p++) {
-                    m = min(m, g.pd[g.li[p]]);
+                const u32 a = g.off[j], b = g.off[j + 1];
+                u64 m = NONE64, fd = NONE64;
+                u32 mi = NONE32, fp = NONE32;
+                for (u32 p = a; p < b; p++) {
+                    const u32 k = g.li[p];
+                    const u64 d = g.pd[k];
+                    if (p == a) { fp = k; fd = d; }
+                    if (d < m) { m = d; mi = k; }
                     g.ld[p] = m;
                 }
+                g.minpd[j] = m; g.minpi[j] = mi; g.firstp[j] = fp;
+                g.snap[2 * (size_t)j] = make_uint4((u32)m, (u32)(m >> 32), mi, fp);
+                g.snap[2 * (size_t)j + 1] = make_uint4((u32)fd, (u32)(fd >> 32), a, b - a);
             });
         else
         launch_for<t_fx_fill>(n_h, st, lc, [=] __device__(u32 k) {
