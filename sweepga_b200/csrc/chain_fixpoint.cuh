@@ -11,7 +11,7 @@
 // mapping); here ALL positions are evaluated against a snapshot of the picks and the evaluation is repeated until nothing
 // changes.  By induction on i the positions below the first wrong one stay correct and that one becomes correct in the
 // next round, so the iteration ends in the reference's picks; measured on the configs[4] piles it needs 6 rounds for a
-// 100 k group, 14 for a 500 k group and 56 for the two 25 M groups of the full configuration (2.05 s for the whole filter
+// 100 k group, 14 for a 500 k group and 56 for the two 25 M groups of the full configuration (1.45 s for the whole filter
 // call), and the number of positions that have to be re-evaluated shrinks geometrically.
 //
 // A round:
