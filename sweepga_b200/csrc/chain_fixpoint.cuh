@@ -198,6 +198,34 @@ __global__ void __launch_bounds__(256) k_fx_check(FxArrays f, u64 G) {
     }
 }
 
+// Round 0 for the positions whose window ends within the next BB_LINEAR successors — every position of a chromosome-scale group of
+// collinear mappings, which is huge and sparse: one thread scans them in order (the unconstrained arg-min, first minimal j), no warp
+// search.  A position whose window goes on (a pile) is listed for k_fx_recompute.
+__global__ void __launch_bounds__(256) k_fx_round0_linear(FxArrays f, u64 G) {
+    const u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    bool more = false;
+    if (k < f.n) {
+        const uint4 a = f.rec[k];
+        const u32 ge = f.gend[k];
+        u64 bd;
+        u32 bj;
+        bb_best_successor<false>(f.rec, nullptr, k, ge & ~FX_REV, a, !(ge & FX_REV), G, G / 5, bd, bj, nullptr, &more);
+        if (!more) {
+            f.pick[k] = bj;
+            f.pd[k] = bd;
+            f.xhi[k] = bj != NONE32 ? bj : k;
+        }
+    }
+    const u32 m = __ballot_sync(0xFFFFFFFFu, more);
+    if (m) {
+        u32 base = 0;
+        const u32 leader = __ffs(m) - 1;
+        if (lane_id() == leader) base = atomicAdd(&f.ctrs[0], (u32)__popc(m));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (more) f.list[base + __popc(m & lanemask_lt())] = k;
+    }
+}
+
 // step 2 in bucket order: the same test, the X(i) lists read by whole warps.  A lane first judges its own position (skip tests, its
 // pick); the lists that still have to be looked at are then taken one at a time by all 32 lanes — coalesced reads of the pool instead
 // of 32 private strided walks (at 50 M the pool holds 2.7 * 10^9 entries and the thread-per-position loop moved them at a tenth of
@@ -740,10 +768,12 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
         SWG_CUDA(cudaMemsetAsync(f.dbits_w, 0, sizeof(u32) * n_bw, st));
         SWG_CUDA(cudaMemsetAsync(f.dirty, 0, sizeof(u32) * (size_t)n_blk, st));
         SWG_CUDA(cudaMemsetAsync(f.ctrs, 0, 4 * sizeof(u32), st));
-        launch_for<t_fx_all>(n_h, st, lc, [=] __device__(u32 k) {
-            g.list[k] = k;
-            if (k == 0) g.ctrs[0] = g.n;
-        });
+        if (getenv("SWG_FX_NO_LINEAR0"))
+            launch_for<t_fx_all>(n_h, st, lc, [=] __device__(u32 k) {
+                g.list[k] = k;
+                if (k == 0) g.ctrs[0] = g.n;
+            });
+        else { k_fx_round0_linear<<<cdiv(n_h, 256), 256, 0, st>>>(f, G); lc.n++; }
         k_fx_recompute<true><<<(u32)c->sm_count * 8, 128, 0, st>>>(f, G);
         lc.n++;
         if (verbose) {

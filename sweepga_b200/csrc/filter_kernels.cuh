@@ -280,7 +280,7 @@ __device__ __forceinline__ bool bb_candidate(const uint4 &a, const uint4 &b, boo
 constexpr u32 BB_LINEAR = 48;
 template <bool ELIG>
 __device__ __forceinline__ void bb_best_successor(const uint4 *__restrict__ srec, const u64 *bps, u32 i, u32 e, const uint4 &a,
-                                                  bool fwd, u64 G, u64 G5, u64 &bd, u32 &bj, u32 *c0_out = nullptr) {
+                                                  bool fwd, u64 G, u64 G5, u64 &bd, u32 &bj, u32 *c0_out = nullptr, bool *linear_only = nullptr) {
     const u64 bound = (u64)a.y + G;
     bd = NONE64;
     bj = NONE32;
@@ -294,6 +294,7 @@ __device__ __forceinline__ void bb_best_successor(const uint4 *__restrict__ srec
         if (bb_candidate(a, b, fwd, G, G5, d) && d < bd && (!ELIG || d < bps[j])) { bd = d; bj = j; }
     }
     if (j >= e) return;
+    if (linear_only) { *linear_only = true; return; } // the window goes on past the linear phase and the caller does not want the rest
     u32 lo = j, hi = e; // first position in [j, e) with query_start >= query_end(i)
     while (lo < hi) {
         const u32 mid = (lo + hi) >> 1;

@@ -118,7 +118,7 @@ struct Arena {
 namespace swg {
 // Environment knobs (diagnostics and tests).  Read once per entry point, never cached across calls.
 struct Knobs {
-    bool force_wide = false, sweep_no_flat = false, no_fixpoint = false, fx_no_buckets = false, inv_grid = false, inv_no_grid = false, inv_no_diag = false, inv_wide = false, cuda_log = false;
+    bool force_wide = false, sweep_no_flat = false, no_fixpoint = false, fx_no_buckets = false, inv_grid = false, inv_no_grid = false, inv_no_diag = false, inv_wide = false, inv_narrow = false, cuda_log = false;
     bool pairs_sort = false;   // SWG_SORT_PAIRS=1: the record sort keeps (key, payload) pairs through every pass
     bool no_fused_keys = false; // SWG_NO_FUSED_KEYS=1: the chain sort keys always come from k_chain_keys
     bool no_group_sort = false; // SWG_NO_GROUP_SORT=1: the record sort always runs the LSD passes (radix_sort.cuh)
@@ -140,6 +140,7 @@ static Knobs read_knobs() {
     k.inv_grid = on("SWG_INV_GRID");
     k.inv_no_diag = on("SWG_INV_NO_DIAG");
     k.inv_wide = on("SWG_INV_WIDE");
+    k.inv_narrow = on("SWG_INV_NARROW");
     k.inv_no_grid = on("SWG_INV_NO_GRID");
     k.pairs_sort = on("SWG_SORT_PAIRS");
     k.no_fused_keys = on("SWG_NO_FUSED_KEYS");
@@ -1324,9 +1325,11 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             SWG_CUDA(cudaMemcpyAsync(hw, wcnt, sizeof hw, cudaMemcpyDeviceToHost, st));
             SWG_CUDA(cudaStreamSynchronize(st));
             int wb = wb0;
+            // (only where chains are many: a pair with a pile holds 10^5 and more; a few hundred chromosome-scale chains would just be cut
+            // into thousands of entries each)
             for (int k = NW - 1; k > 0; k--) {
                 const int w = wb0 - k;
-                if (w < 12 || K.inv_wide) continue;
+                if (w < 12 || K.inv_wide || (C2 < 65536 && !K.inv_narrow)) continue;
                 const bool fits = 2 * sb + (cb > w ? cb - w : 1) + 1 <= 64;
                 if (fits && hw[k] <= std::max<u64>(1ull << 25, 8ull * C2) && hw[k] < (1ull << 31) && hw[NW + k] <= 3ull * h2[1] + 1024) { wb = w; break; }
             }

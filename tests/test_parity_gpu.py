@@ -183,6 +183,8 @@ def test_fixpoint_search_orders(ctx, yeast, variant, monkeypatch):
         monkeypatch.setenv("SWG_FX_NO_BUCKETS", "1")
     else:
         monkeypatch.setenv("SWG_FX_BUCKET_NARROW", variant[6:])
+        if variant == "narrow6":  # round 0 entirely through the warp search (default: a thread scans the next 48 successors first)
+            monkeypatch.setenv("SWG_FX_NO_LINEAR0", "1")
     check(ctx, swg.FilterConfig(), synth.skew(n_pile=20_000, n_tiny_groups=3_000, seed=5, window=3_000_000), variant)
     check(ctx, swg.FilterConfig.from_cli(**CLI_CASES["1:1_rescue"]), yeast, variant)
     for seed in (500, 503, 505, 506):
@@ -239,6 +241,8 @@ def test_inversion_grid_yeast(ctx, yeast, case, monkeypatch):
     """Inversion capture through the bucketed path (taken on its own when a huge group exists), forced onto ordinary input."""
     monkeypatch.setenv("SWG_INV_GRID", "1")
     check(ctx, swg.FilterConfig.from_cli(**CLI_CASES[case]), yeast, "invgrid-" + case)
+    monkeypatch.setenv("SWG_INV_NARROW", "1")  # the narrowest query buckets within budget (default only beyond 65 536 kept chains)
+    check(ctx, swg.FilterConfig.from_cli(**CLI_CASES[case]), yeast, "invgrid-narrow-" + case)
 
 
 @pytest.mark.parametrize("case", ["defaults", "rescue100k", "tight_jump"])
@@ -255,6 +259,8 @@ def test_inversion_grid_without_diagonal_buckets(ctx, yeast, case, monkeypatch):
 @pytest.mark.parametrize("seed", range(0, 160, 4))
 def test_inversion_grid_fuzz(ctx, seed, monkeypatch):
     monkeypatch.setenv("SWG_INV_GRID", "1")
+    if seed % 8 == 0:
+        monkeypatch.setenv("SWG_INV_NARROW", "1")
     test_fuzz_dense(ctx, seed)
 
 
