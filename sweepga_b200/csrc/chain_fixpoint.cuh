@@ -710,7 +710,7 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
         // entries or 2^20 per group.
         const int narrow = getenv("SWG_FX_BUCKET_NARROW") ? atoi(getenv("SWG_FX_BUCKET_NARROW")) : 5;
         int bs = std::max(bits_for(G + G / 5) - narrow, 4);
-        while ((((u64)(maxcoord >> bs) + 2) * n_hg > (1ull << 25) || ((u64)maxcoord >> bs) + 2 > (1ull << 20)) && bs < 32) bs++;
+        while (((((u64)maxcoord >> bs) + 2) * n_hg > (1ull << 25) || ((u64)maxcoord >> bs) + 2 > (1ull << 20)) && bs < 32) bs++;
         f.bshift = bs;
         const u32 nbk = (u32)(((u64)maxcoord >> bs) + 1);
         f.dirD = nbk + 1;
@@ -723,7 +723,7 @@ static bool chain_fixpoint(swg_ctx *c, u32 n_h, const u32 *hpos, const uint4 *sr
             launch_for<t_fx_bkey>(n_h, st, lc, [=] __device__(u32 k) {
                 const uint4 r = g.rec[k];
                 const u32 t = (g.gend[k] & FX_REV) ? r.w : r.z; // '-' strand: the rule tests the candidate's target_end
-                bkey[k] = ((u64)g.hg[k] << tb) | (t >> bs);
+                bkey[k] = ((u64)g.hg[k] << tb) | ((u64)t >> bs);
                 bv[k] = k;
             });
         }

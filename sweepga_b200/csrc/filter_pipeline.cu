@@ -1309,12 +1309,12 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
             });
             launch_for_dev<t_invw2>(d_cnt + 1, c->sm_count, st, lc, [=] __device__(u32 x) {
                 const u32 i = inv_list[x];
-                const u32 qs0 = in.qs[i], qe0 = in.qe[i];
+                const u64 qs0 = in.qs[i], qe0 = in.qe[i];
                 const u32 am = __activemask();
 #pragma unroll
                 for (int k = 0; k < NW; k++) {
                     const int w = wb0 - k;
-                    const u32 v = w >= 12 ? (qe0 >> w) - (qs0 >> w) + 1 : 0u;
+                    const u32 v = w >= 12 ? (u32)((qe0 >> w) - (qs0 >> w) + 1) : 0u;
                     const u32 sum = __reduce_add_sync(am, v);
                     if (sum && (threadIdx.x & 31) == (u32)(__ffs(am) - 1)) atomicAdd(&wcnt[NW + k], (unsigned long long)sum);
                 }
@@ -1375,7 +1375,7 @@ static void run_filter(swg_ctx *c, const swg_config &cfg, const DevIn &in, u8 *s
                 u32 *qv = A.take<u32>(n_inv), *qv2 = A.take<u32>(n_inv);
                 launch_for<t_invkeys>(n_inv, st, lc, [=] __device__(u32 x) {
                     const u32 i = inv_list[x];
-                    qk[x] = (((((u64)in.qid[i] << sb) | in.tid[i])) << bb) | (in.qs[i] >> wb);
+                    qk[x] = (((((u64)in.qid[i] << sb) | in.tid[i])) << bb) | ((u64)in.qs[i] >> wb);
                     qv[x] = i;
                 });
                 sort_pairs(c, qk, qk2, qv, qv2, n_inv, 2 * sb + bb);
