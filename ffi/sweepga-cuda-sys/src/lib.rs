@@ -193,6 +193,7 @@ extern "C" {
     pub fn swg_filter_paf(ctx: *mut swg_ctx, cfg: *const swg_config, in_path: *const c_char, out_path: *const c_char, stats: *mut swg_stats) -> c_int;
     pub fn swg_filter_paf_host(ctx: *mut swg_ctx, cfg: *const swg_config, in_path: *const c_char, out_path: *const c_char, stats: *mut swg_stats) -> c_int;
     pub fn swg_filter_file(ctx: *mut swg_ctx, cfg: *const swg_config, in_path: *const c_char, out_path: *const c_char, keep_self: c_int, stats: *mut swg_stats) -> c_int;
+    pub fn swg_aln_to_paf(aln_path: *const c_char, paf_path: *const c_char, threads: c_int) -> c_int;
     pub fn swg_shard_plan(host_in: *const swg_mappings, n_shards: c_int, shard_of: *mut u32, shard_sizes: *mut u64) -> c_int;
     pub fn swg_shard_plan_units(n_units: u64, unit_sizes: *const u64, n_shards: c_int, shard_of_unit: *mut u32, shard_sizes: *mut u64) -> c_int;
     pub fn swg_version() -> *const c_char;

@@ -55,7 +55,7 @@ enum {
     SWG_ERR_OOM = -4,     /* device or pinned-host allocation failed                     */
     SWG_ERR_IO = -5,      /* PAF front end: cannot open / read / write                   */
     SWG_ERR_PARSE = -6,   /* flag parsers: the reference would return Err / exit         */
-    SWG_ERR_UNSUPPORTED = -7 /* .1aln container (reference delegates it to fastga-rs)     */
+    SWG_ERR_UNSUPPORTED = -7 /* .1aln container without a converter (fastga-rs / ALNtoPAF)  */
 };
 
 #define SWG_NO_LIMIT (~(uint64_t)0)         /* Option<usize>::None (Some(0) stays representable) */
@@ -332,10 +332,17 @@ int swg_filter_paf(swg_ctx *ctx, const swg_config *cfg, const char *in_path, con
 /* Same call with the multi-threaded host parser and writer around swg_filter. */
 int swg_filter_paf_host(swg_ctx *ctx, const swg_config *cfg, const char *in_path, const char *out_path,
                         swg_stats *stats);
-/* unified_filter::filter_file (src/unified_filter.rs:280-347): sniffs "1 " => .1aln
- * => SWG_ERR_UNSUPPORTED (the container codec lives in fastga-rs, not in sweepga). */
+/* unified_filter::filter_file (src/unified_filter.rs:280-347): sniffs "1 " => .1aln.  The container codec lives in
+ * fastga-rs / ONElib, not in sweepga, so a .1aln input is converted through FastGA's own ALNtoPAF when that executable
+ * can be found (swg_aln_to_paf below) and the output path ends in ".paf" — the route of the reference's CLI
+ * (src/main.rs:737-770); .1aln OUTPUT (write_1aln_filtered, src/unified_filter.rs:158-277) and a .1aln input without the
+ * converter => SWG_ERR_UNSUPPORTED.  Parity of this route is unpinned: the reference holds no .1aln vector. */
 int swg_filter_file(swg_ctx *ctx, const swg_config *cfg, const char *in_path, const char *out_path,
                     int keep_self, swg_stats *stats);
+/* aln_to_paf's fallback (src/main.rs:743-770): runs `ALNtoPAF -x -T<threads> <aln_path>` and writes its standard output
+ * (PAF with X-CIGARs) to paf_path.  The executable is $SWG_ALNTOPAF if set, else "ALNtoPAF" on PATH; no shell is involved.
+ * SWG_ERR_UNSUPPORTED: no such executable; SWG_ERR_IO: it failed or paf_path cannot be written.  Host only. */
+int swg_aln_to_paf(const char *aln_path, const char *paf_path, int threads);
 
 /* ---- multi-GPU sharding helper ------------------------------------------ *
  * Size-balanced (LPT) assignment of genome-pair units (P(q),P(t)) to n_shards.

@@ -106,6 +106,7 @@ SYMBOLS = [
     ("swg_filter_paf", C.c_int, [_vp, _cfgp, C.c_char_p, C.c_char_p, _statp]),
     ("swg_filter_paf_host", C.c_int, [_vp, _cfgp, C.c_char_p, C.c_char_p, _statp]),
     ("swg_filter_file", C.c_int, [_vp, _cfgp, C.c_char_p, C.c_char_p, C.c_int, _statp]),
+    ("swg_aln_to_paf", C.c_int, [C.c_char_p, C.c_char_p, C.c_int]),
     ("swg_shard_plan", C.c_int, [_mapp, C.c_int, u32p, u64p]),
     ("swg_shard_plan_units", C.c_int, [C.c_uint64, u64p, C.c_int, u32p, u64p]),
     ("swg_last_chain_units", C.c_int, [_vp, C.c_uint64, u32p, u32p, u64p]),

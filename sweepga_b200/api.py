@@ -505,13 +505,22 @@ class PafFilter:
 
 
 def filter_file(input_path, output_path, config: FilterConfig, force_paf_output=False, keep_self=False, device=0):
-    """unified_filter::filter_file (src/unified_filter.rs:280-347).  .1aln input -> SwgError(UNSUPPORTED)."""
+    """unified_filter::filter_file (src/unified_filter.rs:280-347).  A .1aln input is converted through FastGA's ALNtoPAF when
+    that executable is found ($SWG_ALNTOPAF or PATH) and the output path ends in ".paf" (src/main.rs:737-770); otherwise, and for
+    .1aln output, SwgError(UNSUPPORTED)."""
     with Context(device) as ctx:
         stats = _lib.swg_stats()
         cc = config.to_c()
         ctx._check(lib.swg_filter_file(ctx._h, C.byref(cc), os.fsencode(input_path), os.fsencode(output_path), int(keep_self),
                                        C.byref(stats)))
         return stats
+
+
+def aln_to_paf(aln_path, paf_path, threads=8):
+    """aln_to_paf's fallback (src/main.rs:743-770): `ALNtoPAF -x -T<threads> <aln>` -> paf_path.  Host only."""
+    rc = lib.swg_aln_to_paf(os.fsencode(aln_path), os.fsencode(paf_path), int(threads))
+    if rc != 0:
+        raise SwgError(rc, "no ALNtoPAF executable ($SWG_ALNTOPAF / PATH)" if rc == _lib.ERR_UNSUPPORTED else "ALNtoPAF failed")
 
 
 def apply_paf_filter(paf_path: str, filter_config: FilterConfig, device=0) -> str:

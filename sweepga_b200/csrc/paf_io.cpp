@@ -8,6 +8,8 @@
 //   swg_filter_paf  <- PafFilter::filter_paf        (src/paf_filter.rs:278-289)
 //   swg_filter_file <- unified_filter::filter_file  (src/unified_filter.rs:280-347)
 #include <algorithm>
+#include <cerrno>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -18,6 +20,7 @@
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/wait.h>
 #include <unistd.h>
 #include <zlib.h>
 
@@ -598,6 +601,46 @@ int swg_filter_paf_host(swg_ctx *ctx, const swg_config *cfg, const char *in_path
     return rc;
 }
 
+// aln_to_paf's fallback, src/main.rs:743-770: `ALNtoPAF -x -T<threads> <file>`, PAF on its standard output
+int swg_aln_to_paf(const char *aln_path, const char *paf_path, int threads) {
+    if (!aln_path || !paf_path) return SWG_ERR_ARG;
+    const char *exe = getenv("SWG_ALNTOPAF");
+    if (!exe || !*exe) exe = "ALNtoPAF";
+    {   // is there such an executable?  (execvp's own search, done up front so that "absent" and "failed" stay apart)
+        bool found = false;
+        if (strchr(exe, '/')) found = access(exe, X_OK) == 0;
+        else if (const char *path = getenv("PATH")) {
+            std::string p(path);
+            size_t a = 0;
+            while (!found && a <= p.size()) {
+                size_t b = p.find(':', a);
+                if (b == std::string::npos) b = p.size();
+                const std::string cand = (b > a ? p.substr(a, b - a) : std::string(".")) + "/" + exe;
+                found = access(cand.c_str(), X_OK) == 0;
+                a = b + 1;
+            }
+        }
+        if (!found) return SWG_ERR_UNSUPPORTED;
+    }
+    const int fd = open(paf_path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return SWG_ERR_IO;
+    const std::string targ = "-T" + std::to_string(threads > 0 ? threads : 1);
+    const pid_t pid = fork();
+    if (pid < 0) { close(fd); return SWG_ERR_IO; }
+    if (pid == 0) {
+        dup2(fd, 1);
+        close(fd);
+        execlp(exe, exe, "-x", targ.c_str(), aln_path, (char *)nullptr);
+        _exit(127);
+    }
+    close(fd);
+    int st = 0;
+    while (waitpid(pid, &st, 0) < 0)
+        if (errno != EINTR) return SWG_ERR_IO;
+    if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) { remove(paf_path); return SWG_ERR_IO; }
+    return SWG_OK;
+}
+
 int swg_filter_file(swg_ctx *ctx, const swg_config *cfg, const char *in_path, const char *out_path, int keep_self,
                     swg_stats *stats) {
     if (!ctx || !cfg || !in_path || !out_path) return SWG_ERR_ARG;
@@ -607,7 +650,21 @@ int swg_filter_file(swg_ctx *ctx, const swg_config *cfg, const char *in_path, co
     char magic[2] = {0, 0};
     size_t got = fread(magic, 1, 2, f);
     fclose(f);
-    if (got == 2 && magic[0] == '1' && magic[1] == ' ') return SWG_ERR_UNSUPPORTED;
+    if (got == 2 && magic[0] == '1' && magic[1] == ' ') {
+        // .1aln in, PAF out: through FastGA's ALNtoPAF (the route of the reference's CLI, src/main.rs:737-770); .1aln out needs
+        // the container writer of fastga-rs (src/unified_filter.rs:158-277)
+        const size_t ol = strlen(out_path);
+        if (ol < 4 || strcmp(out_path + ol - 4, ".paf") != 0) return SWG_ERR_UNSUPPORTED;
+        std::string tmp = std::string(out_path) + ".swg-aln.paf";
+        int rc = swg_aln_to_paf(in_path, tmp.c_str(), 8);
+        if (rc == SWG_OK) {
+            swg_config c2 = *cfg;
+            c2.keep_self = keep_self ? 1 : 0;
+            rc = swg_filter_paf(ctx, &c2, tmp.c_str(), out_path, stats);
+        }
+        remove(tmp.c_str());
+        return rc;
+    }
     swg_config c2 = *cfg;
     c2.keep_self = keep_self ? 1 : 0; // .with_keep_self(keep_self), src/unified_filter.rs:340-343
     return swg_filter_paf(ctx, &c2, in_path, out_path, stats);

@@ -267,3 +267,47 @@ def test_oracle_ani_stats_known_answers(tmp_path):
     assert oracle_lib.ani_stats(str(p), 2, 3.0, 1) == ((0.9 + ac) / 2.0, 2)
     (tmp_path / "none.paf").write_text("A#1#x\t1\t0\t1\t+\tA#1#y\t1\t0\t1\t1\t1\t60\n")
     assert oracle_lib.ani_stats(str(tmp_path / "none.paf"), 0) == (0.0, 0)
+
+
+def _stub_alntopaf(tmp_path, paf_text, fail=False):
+    """A stand-in for FastGA's ALNtoPAF (not in this image): checks the argument convention of src/main.rs:750-757
+    (`-x -T<threads> <file>`), writes a PAF to its standard output."""
+    exe = tmp_path / "ALNtoPAF"
+    paf = tmp_path / "stub_source.paf"
+    paf.write_text(paf_text)
+    exe.write_text("#!/bin/sh\n"
+                   + ('exit 3\n' if fail else
+                      '[ "$1" = "-x" ] || exit 4\ncase "$2" in -T[0-9]*) ;; *) exit 5;; esac\n[ -f "$3" ] || exit 6\n'
+                      f'/bin/cat "{paf}"\n'))
+    exe.chmod(0o755)
+    return exe
+
+
+def test_aln_to_paf_bridge(tmp_path, monkeypatch):
+    """swg_aln_to_paf: the external-converter route for .1aln input (src/main.rs:737-770).  No converter -> UNSUPPORTED; a failing
+    converter -> IO error and no output left behind; else its standard output, byte for byte.  (.1aln parity itself is unpinned: the
+    reference holds no .1aln vector and the codec lives in fastga-rs.)"""
+    import sweepga_b200 as swg
+    from sweepga_b200 import _lib
+    aln = tmp_path / "x.1aln"
+    aln.write_bytes(b"1 3 aln\n")
+    out = tmp_path / "x.paf"
+    monkeypatch.setenv("PATH", str(tmp_path / "nowhere"))
+    monkeypatch.delenv("SWG_ALNTOPAF", raising=False)
+    with pytest.raises(swg.SwgError) as e:
+        swg.api.aln_to_paf(str(aln), str(out))
+    assert e.value.code == _lib.ERR_UNSUPPORTED
+    text = "q\t100\t0\t50\t+\tt\t100\t0\t50\t50\t50\t60\n"
+    exe = _stub_alntopaf(tmp_path, text)
+    monkeypatch.setenv("SWG_ALNTOPAF", str(exe))           # explicit path
+    swg.api.aln_to_paf(str(aln), str(out), threads=3)
+    assert out.read_text() == text
+    out.unlink()
+    monkeypatch.delenv("SWG_ALNTOPAF")
+    monkeypatch.setenv("PATH", f"{tmp_path}:/usr/bin:/bin")  # found on PATH
+    swg.api.aln_to_paf(str(aln), str(out))
+    assert out.read_text() == text
+    _stub_alntopaf(tmp_path, text, fail=True)
+    with pytest.raises(swg.SwgError) as e:
+        swg.api.aln_to_paf(str(aln), str(out))
+    assert e.value.code == _lib.ERR_IO and not out.exists()

@@ -216,10 +216,11 @@ def test_filter_paf_device_equals_host_and_oracle(ctx, tmp_path, flags):
     assert st.gpu_launches > 10 and st.ms_tokenize > 0
 
 
-def test_filter_file_and_apply_paf_filter(tmp_path):
+def test_filter_file_and_apply_paf_filter(tmp_path, monkeypatch):
     """unified_filter::filter_file (src/unified_filter.rs:280-347) and library_api::apply_paf_filter
     (src/library_api.rs:267-281): PAF input goes through filter_paf with the caller's keep_self / with keep_self = false;
-    a ONEcode container ("1 " magic) is reported as unsupported, never guessed."""
+    a ONEcode container ("1 " magic) goes through ALNtoPAF when there is one and PAF output is asked for, else it is reported as
+    unsupported, never guessed."""
     import os
     from sweepga_b200 import _lib
     t = synth.yeast_like(6000, seed=21)
@@ -256,6 +257,23 @@ def test_filter_file_and_apply_paf_filter(tmp_path):
     assert e.value.code == _lib.ERR_UNSUPPORTED
     with pytest.raises(swg.SwgError):
         swg.filter_file(str(tmp_path / "missing.paf"), str(tmp_path / "o.paf"), cfg)
+    # .1aln in, PAF out, through an ALNtoPAF stand-in that prints `src` (the converter route of src/main.rs:737-770):
+    # the same bytes as filtering the PAF itself; without a converter, or for .1aln output, UNSUPPORTED
+    monkeypatch.delenv("SWG_ALNTOPAF", raising=False)
+    monkeypatch.setenv("PATH", str(tmp_path / "nowhere"))
+    with pytest.raises(swg.SwgError) as e:
+        swg.filter_file(str(aln), str(tmp_path / "o_aln.paf"), cfg)
+    assert e.value.code == _lib.ERR_UNSUPPORTED
+    exe = tmp_path / "ALNtoPAF"
+    exe.write_text(f'#!/bin/sh\n[ "$1" = "-x" ] || exit 4\n/bin/cat "{src}"\n')
+    exe.chmod(0o755)
+    monkeypatch.setenv("SWG_ALNTOPAF", str(exe))
+    swg.filter_file(str(aln), str(tmp_path / "o_aln.paf"), cfg)
+    assert (tmp_path / "o_aln.paf").read_bytes() == outs[False]
+    assert not (tmp_path / "o_aln.paf.swg-aln.paf").exists()
+    with pytest.raises(swg.SwgError) as e:
+        swg.filter_file(str(aln), str(tmp_path / "o2.1aln"), cfg)
+    assert e.value.code == _lib.ERR_UNSUPPORTED
 
 
 def test_filter_paf_device_no_records_and_unwritable(ctx, tmp_path):
