@@ -4,6 +4,7 @@ front end agrees with the oracle's restatement of extract_metadata, the shard pl
 import ctypes as C
 import os
 import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -311,3 +312,20 @@ def test_aln_to_paf_bridge(tmp_path, monkeypatch):
     with pytest.raises(swg.SwgError) as e:
         swg.api.aln_to_paf(str(aln), str(out))
     assert e.value.code == _lib.ERR_IO and not out.exists()
+
+
+def test_c_example_builds_and_runs_host_side(tmp_path):
+    """examples/filter_paf.c: the boundary from plain C99 (no C++ in the header), linked against the product library; its
+    host-only mode needs no GPU, and without a device the filter mode fails loudly (no CPU path)."""
+    exe = str(tmp_path / "filter_paf")
+    libdir = os.path.join(ROOT, "sweepga_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "filter_paf.c"),
+                    "-o", exe, os.path.join(libdir, "libsweepga_b200.so"), f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([exe, "--plan"], capture_output=True, text=True)
+    assert r.returncode == 0 and "shard loads 110 100" in r.stdout and "default scaffold_gap 50000" in r.stdout
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage:" in r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, str(tmp_path / "in.paf"), str(tmp_path / "out.paf")], capture_output=True, text=True)
+        assert r.returncode == 3 and "no CPU fallback" in r.stderr
